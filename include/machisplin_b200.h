@@ -1,0 +1,184 @@
+/*
+ * machisplin_b200.h - C ABI of the B200-native TPS + ensemble raster-interpolation engine.
+ *
+ * This is the drop-in boundary for the hot path of jasonleebrown/machisplin
+ * (reference @ e3a31fa).  The reference has no FFI of its own: its hot path is a set of R
+ * generic calls into CRAN packages.  Each entry point below replaces one such call site
+ * (V73:n = R/ensemble.machine.learning.thin.plate.splines.V73.R line n); INTEGRATION.md
+ * shows the .Call shim an R maintainer adds.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success or a negative MB_E_*
+ *     code and never throws or aborts; mb_last_error() gives the message (thread-local).
+ *   - host entry points take caller-owned HOST arrays and perform H2D/D2H themselves;
+ *     the *_dev twins take DEVICE pointers (of the context's device) and a cudaStream_t
+ *     passed as void* (NULL = the context's stream) and do not synchronise.
+ *   - rasters: terra cell order = row-major from the NW corner, x fastest.  NA = any NaN in,
+ *     quiet NaN out.  Point / coefficient matrices are column-major ("R order").
+ *   - all handles are opaque; the library owns device memory, the caller owns host memory.
+ */
+#ifndef MACHISPLIN_B200_H
+#define MACHISPLIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_VERSION 100
+
+enum {
+  MB_OK = 0,
+  MB_E_ARG = -1,        /* bad argument */
+  MB_E_CUDA = -2,       /* CUDA runtime / driver failure */
+  MB_E_NUMERIC = -3,    /* collinear null space, non-SPD system, eigen failure ... */
+  MB_E_NOMEM = -4,
+  MB_E_UNSUPPORTED = -5
+};
+
+/* Grid geometry of a terra SpatRaster: extent + dimensions. */
+typedef struct {
+  double xmin, xmax, ymin, ymax;
+  int32_t nrow, ncol;
+} mb_grid;
+
+/* Half-open cell window rows [r0,r1) x cols [c0,c1). */
+typedef struct {
+  int32_t r0, r1, c0, c1;
+} mb_window;
+
+typedef struct mb_ctx mb_ctx;
+typedef struct mb_spline mb_spline;
+typedef struct mb_ensemble mb_ensemble;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+int mb_version(void);
+int mb_device_count(void);
+const char* mb_last_error(void);
+int mb_init(int device, mb_ctx** ctx);
+void mb_shutdown(mb_ctx* ctx);
+int mb_sync(mb_ctx* ctx);
+/* number of kernels this context has launched since creation (bench bookkeeping) */
+int64_t mb_launch_count(const mb_ctx* ctx);
+
+/* ---- a1: fields::Tps  (V73:722, V73:751) --------------------------------------------- */
+/* Fit a 2-D thin-plate smoothing spline (m=2, scale.type="range") to n observations.
+ * xy: n x 2 column-major (LONG, LAT); y: n x L column-major (L responses sharing the knots,
+ * L = 1 at the reference's call sites; L = 20 for BASELINE config 5).
+ * lambda < 0 selects fields' GCV search per response; lambda >= 0 is used as given.
+ * Duplicate locations are pooled exactly like Krig.replicates.  splines[L] receives handles. */
+int mb_tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, double lambda,
+               mb_spline** splines);
+/* Build a spline handle from coefficients computed elsewhere (e.g. an R Krig object):
+ * knots_xy np x 2 column-major UNSCALED, c[np], d[3], center[2], scale[2]. */
+int mb_spline_create(mb_ctx* ctx, const double* knots_xy, int np, const double* c, const double* d,
+                     const double* center, const double* scale, mb_spline** out);
+int mb_spline_np(const mb_spline* s);
+/* Any output pointer may be NULL.  knots_xy np x 2 column-major unscaled. */
+int mb_spline_get(const mb_spline* s, double* c, double* d, double* center, double* scale,
+                  double* knots_xy, double* lambda, double* eff_df, double* gcv_at_lambda);
+/* eigenvalues eta[np-3] and rotated data u[np] of the WBW decomposition (NULL-able) */
+int mb_spline_get_decomp(const mb_spline* s, double* eta, double* u);
+void mb_spline_free(mb_spline* s);
+
+/* ---- a2: terra::interpolate(rast(template), Tps)  (V73:726, V73:753) ----------------- */
+enum {
+  MB_EVAL_DIRECT = 0,  /* O(cells x knots) float64 pair sum, libm log: the parity kernel     */
+  MB_EVAL_FAST = 1     /* hierarchical Chebyshev far field + float64 near field: the roofline kernel */
+};
+/* Predict every cell of window w of grid g; out is (w.r1-w.r0) x (w.c1-w.c0) row-major. */
+int mb_tps_eval(mb_ctx* ctx, const mb_spline* s, const mb_grid* g, const mb_window* w, int method,
+                double* out_host);
+int mb_tps_eval_dev(mb_ctx* ctx, const mb_spline* s, const mb_grid* g, const mb_window* w, int method,
+                    double* out_dev, int64_t out_row_stride, void* stream);
+/* predict.Krig at arbitrary points (xy n x 2 column-major), float64 direct. */
+int mb_tps_predict_points(mb_ctx* ctx, const mb_spline* s, const double* xy, int n, double* out_host);
+
+/* ---- a5: terra::predict(rast_stack, model_k) x6 + weighted sum  (V73:468-606, 619) ---- */
+/* Flat descriptors of the fitted models.  P = C + 2 features in the
+ * order cov_1..cov_C, LONG, LAT (xnam, V73:194).  A NULL array / zero count = model absent. */
+typedef struct {
+  int32_t P;
+  /* g: mgcv::gam, parametric formula            coef[P+1], intercept first */
+  const double* gam_coef;
+  /* n: nnet(size=H, linout=TRUE)                 wts[(P+1)*H + H + 1]; y = net*max2 + min (V73:469-470) */
+  const double* nn_wts; int32_t nn_H; double nn_max2, nn_min;
+  /* m: earth                                     dirs[T*P] row-major (0,+-1,2), cuts[T*P], coef[T] */
+  int32_t mars_T; const int8_t* mars_dirs; const double* mars_cuts; const double* mars_coef;
+  /* v: kernlab::ksvm eps-svr rbfdot scaled       sv[S*P] row-major (scaled), alpha[S] */
+  int32_t svm_S; const double* svm_sv; const double* svm_alpha; double svm_b, svm_sigma;
+  const double* svm_x_center; const double* svm_x_scale; double svm_y_center, svm_y_scale;
+  /* r: randomForest regression                   arrays [ntree*nrnodes] tree-major; daughters 1-based, 0 = none */
+  int32_t rf_ntree, rf_nrnodes;
+  const int32_t* rf_left; const int32_t* rf_right; const int8_t* rf_status; const int32_t* rf_bestvar;
+  const double* rf_split; const double* rf_nodepred;
+  /* b: gbm gaussian                              tree t = nodes [tree_off[t], tree_off[t+1]) ; 0-based child offsets */
+  int32_t gbm_ntrees; double gbm_initF; const int32_t* gbm_tree_off;
+  const int32_t* gbm_splitvar; const double* gbm_splitcode;
+  const int32_t* gbm_left; const int32_t* gbm_right; const int32_t* gbm_missing;
+} mb_models;
+
+/* kept: letters of the retained models in evaluation order, e.g. "bgnmrv" (V73:340-362);
+ * w[strlen(kept)]: the round(p,2) weights; w_total: the UNROUNDED sum over all candidates (V73:337). */
+int mb_ensemble_create(mb_ctx* ctx, const mb_grid* g, const mb_models* m, const char* kept,
+                       const double* w, double w_total, mb_ensemble** out);
+void mb_ensemble_free(mb_ensemble* e);
+
+/* pred.elev (+ TPS surface, + NA propagation of part 5, V73:906-907) for window w.
+ * cov: C planes of the FULL grid, plane stride nrow*ncol, float32, NaN = NA.
+ * spline may be NULL (tps=FALSE); tps_surface may carry a precomputed TPS raster for the window
+ * (row-major, e.g. from mb_tiles_tps) and is added instead of evaluating `spline`. */
+int mb_ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov_host, int C,
+                     const mb_spline* spline, const double* tps_surface_host,
+                     const mb_window* w, double* out_host);
+int mb_ensemble_eval_dev(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C,
+                         const mb_spline* spline, const double* tps_surface_dev,
+                         const mb_window* w, double* out_dev, void* stream);
+/* the same predictors at n points; X is n x P column-major float64 (V73:477-611 residual side) */
+int mb_ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X, int n, double* out_host);
+
+/* ---- a3 + a4: mltps part 3 / 4  (V73:649-895) ---------------------------------------- */
+/* The TPS-of-residuals raster of the full grid with the reference's internal tiling:
+ * ceil(n/tile_px) tiles, fit box = tile +- fit_halo, keep box = tile +- keep_halo, < min_pts knots
+ * -> zero tile, mean mosaic + linear seam feather.  knots_xy n x 2 column-major (cell-centre
+ * LONG/LAT), resid[n].  Defaults of the reference: 1500, 0.2, 0.025, 10, lambda < 0 (GCV). */
+int mb_tiles_tps(mb_ctx* ctx, const mb_grid* g, const double* knots_xy, const double* resid, int n,
+                 int tile_px, double fit_halo, double keep_halo, int min_pts, double lambda,
+                 int method, double* out_host);
+int mb_tiles_tps_dev(mb_ctx* ctx, const mb_grid* g, const double* knots_xy, const double* resid, int n,
+                     int tile_px, double fit_halo, double keep_halo, int min_pts, double lambda,
+                     int method, double* out_dev, void* stream);
+
+/* ---- machisplin.tiles.merge  (V73:1392-1548) ------------------------------------------ */
+/* ntiles = nC*nR tile rasters in the reference's order (row-major from the SW tile); tile t covers
+ * window wins[t] of grid g and is (r1-r0) x (c1-c0) row-major. */
+int mb_tiles_merge(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_window* wins,
+                   const double* const* tiles_host, double* out_host);
+int mb_tiles_merge_dev(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_window* wins,
+                       const double* const* tiles_dev, double* out_dev, void* stream);
+
+/* ---- a6: RSS objective of the ensemble-weight search  (V73:329-333, 369-373) ---------- */
+/* G = R'R for R n x K column-major (K <= 8); fit(w) = w'Gw / (sum w)^2. */
+int mb_gram(mb_ctx* ctx, const double* R_host, int n, int K, double* G_host);
+int mb_gram_dev(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, void* stream);
+
+/* ---- a7: part 5  (V73:906-930) --------------------------------------------------------- */
+/* gather raster values at the cells (row[i], col[i]) - f.actual <- extract(final, points). */
+int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row,
+                        const int32_t* col, int n, double* out_host);
+
+/* ---- device memory helpers for hosts without a CUDA allocator (R) ---------------------- */
+int mb_dev_alloc(mb_ctx* ctx, size_t bytes, void** out);
+int mb_dev_free(mb_ctx* ctx, void* p);
+int mb_h2d(mb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int mb_d2h(mb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* Tunables of the fast evaluator (0 = automatic). */
+int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACHISPLIN_B200_H */

@@ -1,0 +1,388 @@
+// extern "C" entry points of libmachisplin_b200 (include/machisplin_b200.h).
+// Each one is a thin guarded wrapper: argument checks, H2D/D2H for the host variants, then the
+// device implementation in tps_eval.cu / tps_fit.cu / ensemble.cu / tiles.cu.
+#include "common.cuh"
+#include "internal.h"
+
+#include <cmath>
+
+namespace mb {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+int mb_version(void) { return MB_VERSION; }
+
+const char* mb_last_error(void) { return g_last_error.c_str(); }
+
+int mb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int mb_init(int device, mb_ctx** out) {
+  return guarded([&] {
+    MB_REQUIRE(out != nullptr, "ctx out pointer is NULL");
+    *out = nullptr;
+    int n = 0;
+    MB_CUDA(cudaGetDeviceCount(&n));
+    MB_REQUIRE(device >= 0 && device < n, "no such CUDA device");
+    MB_CUDA(cudaSetDevice(device));
+    auto ctx = std::make_unique<mb_ctx>();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    MB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    MB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    init_logtab(ctx.get());
+    *out = ctx.release();
+  });
+}
+
+void mb_shutdown(mb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  fit_release(ctx);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int mb_sync(mb_ctx* ctx) {
+  return guarded([&] {
+    MB_REQUIRE(ctx, "ctx is NULL");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int64_t mb_launch_count(const mb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows) {
+  return guarded([&] {
+    MB_REQUIRE(ctx, "ctx is NULL");
+    MB_REQUIRE(cheb_p == 0 || cheb_p == 8 || cheb_p == 10 || cheb_p == 12 || cheb_p == 14 || cheb_p == 16,
+               "cheb_p must be 0 (auto), 8, 10, 12, 14 or 16");
+    MB_REQUIRE(leaf_cols == 0 || leaf_cols == 32, "leaf_cols must be 0 (auto) or 32");
+    MB_REQUIRE(leaf_rows >= 0 && leaf_rows <= 128, "leaf_rows must be in [0, 128]");
+    ctx->cheb_p = cheb_p;
+    ctx->leaf_cols = leaf_cols;
+    ctx->leaf_rows = leaf_rows;
+  });
+}
+
+// ---- device memory helpers -----------------------------------------------------------------
+int mb_dev_alloc(mb_ctx* ctx, size_t bytes, void** out) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && out, "NULL argument");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) throw Error(MB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  });
+}
+int mb_dev_free(mb_ctx* ctx, void* p) {
+  return guarded([&] {
+    MB_REQUIRE(ctx, "ctx is NULL");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaFree(p));
+  });
+}
+int mb_h2d(mb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && dst && src, "NULL argument");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+int mb_d2h(mb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && dst && src, "NULL argument");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+// ---- splines ---------------------------------------------------------------------------------
+int mb_spline_create(mb_ctx* ctx, const double* knots_xy, int np, const double* c, const double* d,
+                     const double* center, const double* scale, mb_spline** out) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && knots_xy && c && d && center && scale && out, "NULL argument");
+    MB_REQUIRE(np >= 1, "spline needs at least one knot");
+    MB_REQUIRE(scale[0] > 0 && scale[1] > 0, "x.scale must be positive");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    auto s = std::make_unique<mb_spline>();
+    s->np = np;
+    s->kx.assign(knots_xy, knots_xy + np);
+    s->ky.assign(knots_xy + np, knots_xy + 2 * np);
+    s->sx.resize(np);
+    s->sy.resize(np);
+    for (int i = 0; i < np; ++i) {
+      s->sx[i] = (s->kx[i] - center[0]) / scale[0];
+      s->sy[i] = (s->ky[i] - center[1]) / scale[1];
+    }
+    s->c.assign(c, c + np);
+    for (int i = 0; i < 3; ++i) s->d[i] = d[i];
+    for (int i = 0; i < 2; ++i) { s->center[i] = center[i]; s->scale[i] = scale[i]; }
+    spline_finalize(ctx, s.get());
+    *out = s.release();
+  });
+}
+
+int mb_spline_np(const mb_spline* s) { return s ? s->np : MB_E_ARG; }
+
+int mb_spline_get(const mb_spline* s, double* c, double* d, double* center, double* scale, double* knots_xy,
+                  double* lambda, double* eff_df, double* gcv) {
+  return guarded([&] {
+    MB_REQUIRE(s, "spline is NULL");
+    if (c) std::copy(s->c.begin(), s->c.end(), c);
+    if (d) std::copy(s->d, s->d + 3, d);
+    if (center) std::copy(s->center, s->center + 2, center);
+    if (scale) std::copy(s->scale, s->scale + 2, scale);
+    if (knots_xy) {
+      std::copy(s->kx.begin(), s->kx.end(), knots_xy);
+      std::copy(s->ky.begin(), s->ky.end(), knots_xy + s->np);
+    }
+    if (lambda) *lambda = s->lambda;
+    if (eff_df) *eff_df = s->eff_df;
+    if (gcv) *gcv = s->gcv;
+  });
+}
+
+int mb_spline_get_decomp(const mb_spline* s, double* eta, double* u) {
+  return guarded([&] {
+    MB_REQUIRE(s, "spline is NULL");
+    MB_REQUIRE(!s->eta.empty(), "spline carries no WBW decomposition (fixed-lambda Cholesky fit or created from coefficients)");
+    if (eta) std::copy(s->eta.begin(), s->eta.end(), eta);
+    if (u) std::copy(s->u.begin(), s->u.end(), u);
+  });
+}
+
+void mb_spline_free(mb_spline* s) {
+  if (!s) return;
+  if (s->ctx) cudaSetDevice(s->ctx->device);
+  delete s;
+}
+
+int mb_tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, double lambda, mb_spline** splines) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && xy && y && splines, "NULL argument");
+    MB_REQUIRE(n > 3 && L >= 1, "need n > 3 observations and L >= 1 responses");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    tps_fit(ctx, xy, y, n, L, lambda, splines);
+  });
+}
+
+// ---- evaluation --------------------------------------------------------------------------------
+static void eval_dispatch(mb_ctx* ctx, const mb_spline* s, const mb_grid* g, const mb_window* w, int method,
+                          double* out_dev, int64_t stride, cudaStream_t st) {
+  if (method == MB_EVAL_DIRECT) tps_eval_direct(ctx, s, *g, *w, out_dev, stride, st);
+  else if (method == MB_EVAL_FAST) tps_eval_fast(ctx, s, *g, *w, out_dev, stride, st);
+  else throw Error(MB_E_ARG, "unknown evaluation method");
+}
+
+int mb_tps_eval_dev(mb_ctx* ctx, const mb_spline* s, const mb_grid* g, const mb_window* w, int method,
+                    double* out_dev, int64_t out_row_stride, void* stream) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && s && out_dev, "NULL argument");
+    check_grid(g);
+    check_window(g, w);
+    MB_REQUIRE(out_row_stride >= w->c1 - w->c0, "row stride shorter than the window");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    eval_dispatch(ctx, s, g, w, method, out_dev, out_row_stride, stream ? (cudaStream_t)stream : ctx->stream);
+  });
+}
+
+int mb_tps_eval(mb_ctx* ctx, const mb_spline* s, const mb_grid* g, const mb_window* w, int method,
+                double* out_host) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && s && out_host, "NULL argument");
+    check_grid(g);
+    check_window(g, w);
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)(w->r1 - w->r0) * (w->c1 - w->c0);
+    DevBuf<double> d(n);
+    eval_dispatch(ctx, s, g, w, method, d.p, w->c1 - w->c0, ctx->stream);
+    MB_CUDA(cudaMemcpyAsync(out_host, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int mb_tps_predict_points(mb_ctx* ctx, const mb_spline* s, const double* xy, int n, double* out_host) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && s && xy && out_host, "NULL argument");
+    MB_REQUIRE(n >= 0, "negative point count");
+    if (n == 0) return;
+    MB_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<double> dx(n), dy(n), df(n);
+    dx.upload(xy, n, ctx->stream);
+    dy.upload(xy + n, n, ctx->stream);
+    tps_predict_points_dev(ctx, s, dx.p, dy.p, n, df.p, ctx->stream);
+    MB_CUDA(cudaMemcpyAsync(out_host, df.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+// ---- ensemble ------------------------------------------------------------------------------------
+int mb_ensemble_create(mb_ctx* ctx, const mb_grid* g, const mb_models* m, const char* kept, const double* w,
+                       double w_total, mb_ensemble** out) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && m && kept && w && out, "NULL argument");
+    check_grid(g);
+    MB_CUDA(cudaSetDevice(ctx->device));
+    *out = ensemble_create(ctx, *g, *m, kept, w, w_total);
+  });
+}
+
+void mb_ensemble_free(mb_ensemble* e) { ensemble_free(e); }
+
+int mb_ensemble_eval_dev(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_spline* spline,
+                         const double* tps_surface_dev, const mb_window* w, double* out_dev, void* stream) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && e && out_dev, "NULL argument");
+    MB_REQUIRE(C == 0 || cov_dev, "covariate planes are NULL");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    ensemble_eval(ctx, e, cov_dev, C, spline, tps_surface_dev, w, out_dev, stream ? (cudaStream_t)stream : ctx->stream);
+  });
+}
+
+int mb_ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov_host, int C, const mb_spline* spline,
+                     const double* tps_surface_host, const mb_window* w, double* out_host) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && e && out_host && w, "NULL argument");
+    MB_REQUIRE(C == 0 || cov_host, "covariate planes are NULL");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const mb_grid g = ensemble_grid(e);
+    check_window(&g, w);
+    const size_t plane = (size_t)g.nrow * g.ncol;
+    const size_t nwin = (size_t)(w->r1 - w->r0) * (w->c1 - w->c0);
+    // only the rows of the window travel: plane p rows [r0, r1) -> device plane of the same geometry
+    DevBuf<float> d_cov((size_t)C * plane);
+    for (int p = 0; p < C; ++p) {
+      const size_t off = p * plane + (size_t)w->r0 * g.ncol;
+      MB_CUDA(cudaMemcpyAsync(d_cov.p + off, cov_host + off, sizeof(float) * (size_t)(w->r1 - w->r0) * g.ncol,
+                              cudaMemcpyHostToDevice, ctx->stream));
+    }
+    DevBuf<double> d_tps, d_out(nwin);
+    if (tps_surface_host) d_tps.upload(tps_surface_host, nwin, ctx->stream);
+    ensemble_eval(ctx, e, d_cov.p, C, spline, tps_surface_host ? d_tps.p : nullptr, w, d_out.p, ctx->stream);
+    MB_CUDA(cudaMemcpyAsync(out_host, d_out.p, nwin * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int mb_ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X, int n, double* out_host) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && e && X && out_host, "NULL argument");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    ensemble_predict_points(ctx, e, X, n, out_host);
+  });
+}
+
+// ---- tiles ---------------------------------------------------------------------------------------
+int mb_tiles_tps_dev(mb_ctx* ctx, const mb_grid* g, const double* knots_xy, const double* resid, int n,
+                     int tile_px, double fit_halo, double keep_halo, int min_pts, double lambda, int method,
+                     double* out_dev, void* stream) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && knots_xy && resid && out_dev, "NULL argument");
+    check_grid(g);
+    MB_REQUIRE(tile_px > 0 && fit_halo >= 0 && keep_halo >= 0 && keep_halo <= fit_halo, "bad tiling parameters");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    tiles_tps(ctx, *g, knots_xy, resid, n, tile_px, fit_halo, keep_halo, min_pts, lambda, method, out_dev,
+              stream ? (cudaStream_t)stream : ctx->stream);
+  });
+}
+
+int mb_tiles_tps(mb_ctx* ctx, const mb_grid* g, const double* knots_xy, const double* resid, int n, int tile_px,
+                 double fit_halo, double keep_halo, int min_pts, double lambda, int method, double* out_host) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && knots_xy && resid && out_host, "NULL argument");
+    check_grid(g);
+    MB_REQUIRE(tile_px > 0 && fit_halo >= 0 && keep_halo >= 0 && keep_halo <= fit_halo, "bad tiling parameters");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const size_t ncell = (size_t)g->nrow * g->ncol;
+    DevBuf<double> d_out(ncell);
+    tiles_tps(ctx, *g, knots_xy, resid, n, tile_px, fit_halo, keep_halo, min_pts, lambda, method, d_out.p,
+              ctx->stream);
+    MB_CUDA(cudaMemcpyAsync(out_host, d_out.p, ncell * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int mb_tiles_merge_dev(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_window* wins,
+                       const double* const* tiles_dev, double* out_dev, void* stream) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && wins && tiles_dev && out_dev, "NULL argument");
+    check_grid(g);
+    MB_REQUIRE(nC >= 1 && nR >= 1, "need at least one tile");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    tiles_merge(ctx, *g, nC, nR, wins, tiles_dev, out_dev, stream ? (cudaStream_t)stream : ctx->stream);
+  });
+}
+
+int mb_tiles_merge(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_window* wins,
+                   const double* const* tiles_host, double* out_host) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && wins && tiles_host && out_host, "NULL argument");
+    check_grid(g);
+    MB_REQUIRE(nC >= 1 && nR >= 1, "need at least one tile");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    const int nt = nC * nR;
+    std::vector<DevBuf<double>> bufs(nt);
+    std::vector<const double*> ptrs(nt);
+    for (int t = 0; t < nt; ++t) {
+      check_window(g, &wins[t]);
+      const size_t n = (size_t)(wins[t].r1 - wins[t].r0) * (wins[t].c1 - wins[t].c0);
+      bufs[t].upload(tiles_host[t], n, ctx->stream);
+      ptrs[t] = bufs[t].p;
+    }
+    const size_t ncell = (size_t)g->nrow * g->ncol;
+    DevBuf<double> d_out(ncell);
+    tiles_merge(ctx, *g, nC, nR, wins, ptrs.data(), d_out.p, ctx->stream);
+    MB_CUDA(cudaMemcpyAsync(out_host, d_out.p, ncell * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+// ---- gram / gather -----------------------------------------------------------------------------
+int mb_gram_dev(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, void* stream) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && R_dev && G_dev, "NULL argument");
+    MB_REQUIRE(n >= 1 && K >= 1 && K <= 8, "need n >= 1 and 1 <= K <= 8");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    gram(ctx, R_dev, n, K, G_dev, stream ? (cudaStream_t)stream : ctx->stream);
+  });
+}
+
+int mb_gram(mb_ctx* ctx, const double* R_host, int n, int K, double* G_host) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && R_host && G_host, "NULL argument");
+    MB_REQUIRE(n >= 1 && K >= 1 && K <= 8, "need n >= 1 and 1 <= K <= 8");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<double> dR((size_t)n * K), dG((size_t)K * K);
+    dR.upload(R_host, (size_t)n * K, ctx->stream);
+    gram(ctx, dR.p, n, K, dG.p, ctx->stream);
+    MB_CUDA(cudaMemcpyAsync(G_host, dG.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row,
+                        const int32_t* col, int n, double* out_host) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && raster_dev && row && col && out_host, "NULL argument");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    gather_cells(ctx, raster_dev, row_stride, row, col, n, out_host);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+// Shared internals of libmachisplin_b200: context, handles, error plumbing, small device helpers.
+// Nothing here is part of the C ABI (see include/machisplin_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include <memory>
+
+#include "../../include/machisplin_b200.h"
+
+namespace mb {
+
+// ---- error plumbing: exceptions never cross the ABI ------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string& m);
+
+#define MB_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      throw mb::Error(MB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +  \
+                                     __FILE__ + ":" + std::to_string(__LINE__) + ")");        \
+  } while (0)
+
+#define MB_REQUIRE(cond, msg)                                   \
+  do {                                                          \
+    if (!(cond)) throw mb::Error(MB_E_ARG, std::string(msg));   \
+  } while (0)
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return MB_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    set_last_error("host allocation failed");
+    return MB_E_NOMEM;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return MB_E_NUMERIC;
+  }
+}
+
+// ---- RAII device buffer -----------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n_) { alloc(n_); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t n_) {
+    release();
+    if (n_ == 0) return;
+    cudaError_t e = cudaMalloc(&p, n_ * sizeof(T));
+    if (e != cudaSuccess) throw Error(MB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    n = n_;
+  }
+  void ensure(size_t n_) { if (n_ > n) alloc(n_); }
+  void upload(const T* h, size_t cnt, cudaStream_t s) {
+    ensure(cnt);
+    if (cnt) MB_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+};
+
+}  // namespace mb
+
+// ---- handles ----------------------------------------------------------------------------
+struct mb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  // fast-evaluator tunables (0 = automatic)
+  int cheb_p = 0, leaf_cols = 0, leaf_rows = 0;
+  // 256-entry (1/m_k, -log(1/m_k)) table for the float64 table-driven log
+  mb::DevBuf<double2> logtab;
+  // scratch reused across calls
+  mb::DevBuf<double> scratch_d;
+  mb::DevBuf<char> scratch_b;
+};
+
+struct mb_spline {
+  mb_ctx* ctx = nullptr;
+  int np = 0;
+  std::vector<double> sx, sy;        // scaled knot coordinates
+  std::vector<double> kx, ky;        // unscaled
+  std::vector<double> c;             // np
+  double d[3] = {0, 0, 0};
+  double center[2] = {0, 0}, scale[2] = {1, 1};
+  double lambda = -1, eff_df = -1, gcv = -1;
+  std::vector<double> eta, u;        // WBW decomposition (GCV fits only)
+  double sum_abs_c = 0;              // sum |c_i|  (amplification estimate for the fast evaluator)
+  double fscale = 0;                 // max |f(knot_i)|
+  mb::DevBuf<double> d_sx, d_sy, d_c;
+};
+
+namespace mb {
+
+constexpr double kRbfConst = 0.039788735772973836;  // 1/(8 pi): radbas.constant(m=2, d=2)
+constexpr double kD2Clamp = 1e-20;                  // Fortran radfun clamp
+
+struct GridAffine {
+  // s_x(col) = (xmin + (col+0.5) rx - cx)/scx ; s_y(row) = (ymax - (row+0.5) ry - cy)/scy
+  double xmin, ymax, rx, ry, cx, cy, scx, scy;
+};
+inline GridAffine make_affine(const mb_grid& g, const mb_spline& s) {
+  GridAffine a;
+  a.xmin = g.xmin; a.ymax = g.ymax;
+  a.rx = (g.xmax - g.xmin) / g.ncol;
+  a.ry = (g.ymax - g.ymin) / g.nrow;
+  a.cx = s.center[0]; a.cy = s.center[1]; a.scx = s.scale[0]; a.scy = s.scale[1];
+  return a;
+}
+inline void check_grid(const mb_grid* g) {
+  MB_REQUIRE(g != nullptr, "grid is NULL");
+  MB_REQUIRE(g->nrow > 0 && g->ncol > 0, "grid has no cells");
+  MB_REQUIRE(g->xmax > g->xmin && g->ymax > g->ymin, "grid extent is empty");
+}
+inline void check_window(const mb_grid* g, const mb_window* w) {
+  MB_REQUIRE(w != nullptr, "window is NULL");
+  MB_REQUIRE(w->r0 >= 0 && w->c0 >= 0 && w->r1 <= g->nrow && w->c1 <= g->ncol && w->r1 > w->r0 && w->c1 > w->c0,
+             "window is empty or outside the grid");
+}
+
+// implemented in tps_eval.cu
+void spline_finalize(mb_ctx* ctx, mb_spline* s);   // uploads, computes sum|c| and fscale
+void tps_eval_direct(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
+                     int64_t stride, cudaStream_t st);
+void tps_eval_fast(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
+                   int64_t stride, cudaStream_t st);
+void tps_predict_points_dev(mb_ctx* ctx, const mb_spline* s, const double* x_dev, const double* y_dev, int n,
+                            double* out_dev, cudaStream_t st);
+void init_logtab(mb_ctx* ctx);
+
+}  // namespace mb

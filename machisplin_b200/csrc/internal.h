@@ -1,0 +1,30 @@
+// Cross-file declarations of the device implementations behind the C ABI.
+#pragma once
+#include "common.cuh"
+
+namespace mb {
+
+// tps_fit.cu - fields::Tps (V73:722, 751)
+void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, double lambda, mb_spline** out);
+void fit_release(mb_ctx* ctx);   // library handles owned on behalf of the context
+
+// ensemble.cu - terra::predict x6 + weighted sum (V73:468-619) + part-5 combine (V73:906-907)
+mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, const char* kept, const double* w,
+                             double w_total);
+void ensemble_free(mb_ensemble* e);
+mb_grid ensemble_grid(const mb_ensemble* e);
+void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_spline* spline,
+                   const double* tps_surface_dev, const mb_window* w, double* out_dev, cudaStream_t st);
+void ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X, int n, double* out_host);
+
+// tiles.cu - mltps part 3/4 (V73:649-895), machisplin.tiles.merge (V73:1392-1548), gram, gather
+void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const double* resid, int n, int tile_px,
+               double fit_halo, double keep_halo, int min_pts, double lambda, int method, double* out_dev,
+               cudaStream_t st);
+void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window* wins,
+                 const double* const* tiles_dev, double* out_dev, cudaStream_t st);
+void gram(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, cudaStream_t st);
+void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row, const int32_t* col,
+                  int n, double* out_host);
+
+}  // namespace mb

@@ -1,0 +1,588 @@
+// TPS surface evaluation on a raster window - replaces terra::interpolate(rast(template), Tps)
+// -> predict.Krig -> Fortran multrb at V73:726 and V73:753.
+//
+//   f(cell) = d0 + d1 sx + d2 sy + (1/16pi) sum_i c_i d2_i log(d2_i),   d2_i = max(|s - s_i|^2, 1e-20)
+//
+// Two device paths:
+//   tps_eval_direct  K4: O(cells x knots) float64 pair sum with libm log - the parity kernel.
+//   tps_eval_fast    K5: the roofline kernel.  The far field of every leaf box (32 x bh cells) is a
+//                    P x P Chebyshev expansion built by a kernel-independent treecode (P2L from the
+//                    interaction list of each quadtree level + exact polynomial re-expansion
+//                    parent -> child), the near field (knots in the 3 x 3 box neighbourhood) is summed
+//                    directly.  Everything is float64: the coefficients c cancel by up to 1e8
+//                    (T'c = 0), so float32 pair terms are not accurate enough.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+namespace mb {
+
+// =========================================================================================
+// float64 table-driven log: x = 2^e m, m in [1,2); m_k = centre of the 1/256-wide mantissa bin;
+// log x = e ln2 - log(inv_k) + log1p(m inv_k - 1), |m inv_k - 1| <= 2^-9, series to t^5
+// (truncation 2^-54/6).  ~10 FP64 ops instead of ~45 for libm log.
+// =========================================================================================
+void init_logtab(mb_ctx* ctx) {
+  std::vector<double2> tab(256);
+  for (int k = 0; k < 256; ++k) {
+    long double mk = 1.0L + (k + 0.5L) / 256.0L;
+    double inv = (double)(1.0L / mk);
+    tab[k].x = inv;
+    tab[k].y = (double)(-logl((long double)inv));
+  }
+  ctx->logtab.upload(tab.data(), tab.size(), ctx->stream);
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+__device__ __forceinline__ double4 ldg4(const double4* p) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ double tlog(double x, const double2* __restrict__ tab) {
+  int hi = __double2hiint(x);
+  int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  int idx = (hi >> 12) & 0xFF;
+  double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+  double2 t2 = tab[idx];
+  double t = fma(m, t2.x, -1.0);
+  double p = fma(t, 0.2, -0.25);
+  p = fma(t, p, 0.33333333333333333);
+  p = fma(t, p, -0.5);
+  p = fma(t * t, p, t);
+  double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;  // (double)e
+  return fma(ed, 0.69314718055994531, t2.y + p);
+}
+
+// =========================================================================================
+// K4: direct evaluation
+// =========================================================================================
+constexpr int kDirectTile = 256;
+
+__global__ void __launch_bounds__(256) k_tps_eval_direct(
+    const double* __restrict__ ksx, const double* __restrict__ ksy, const double* __restrict__ kc, int np,
+    double d0, double d1, double d2c, GridAffine a, mb_window w, double* __restrict__ out, int64_t stride) {
+  __shared__ double s_x[kDirectTile], s_y[kDirectTile], s_c[kDirectTile];
+  const int col = w.c0 + blockIdx.x * 32 + (threadIdx.x & 31);
+  const int row = w.r0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+  // terra xFromCol / yFromRow, then Krig's transformx - same operation order as the oracle
+  const double x = a.xmin + (col + 0.5) * a.rx;
+  const double y = a.ymax - (row + 0.5) * a.ry;
+  const double sx = (x - a.cx) / a.scx;
+  const double sy = (y - a.cy) / a.scy;
+  double acc = 0.0;
+  for (int base = 0; base < np; base += kDirectTile) {
+    const int n = min(kDirectTile, np - base);
+    __syncthreads();
+    if (threadIdx.x < n) {
+      s_x[threadIdx.x] = ksx[base + threadIdx.x];
+      s_y[threadIdx.x] = ksy[base + threadIdx.x];
+      s_c[threadIdx.x] = kc[base + threadIdx.x];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      const double dx = sx - s_x[i];
+      const double dy = sy - s_y[i];
+      double r2 = dx * dx + dy * dy;
+      r2 = fmax(r2, kD2Clamp);
+      acc += s_c[i] * (0.5 * log(r2) * r2);
+    }
+  }
+  if (col < w.c1 && row < w.r1)
+    out[(int64_t)(row - w.r0) * stride + (col - w.c0)] = d0 + d1 * sx + d2c * sy + kRbfConst * acc;
+}
+
+void tps_eval_direct(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
+                     int64_t stride, cudaStream_t st) {
+  GridAffine a = make_affine(g, *s);
+  dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
+  k_tps_eval_direct<<<grid, 256, 0, st>>>(s->d_sx.p, s->d_sy.p, s->d_c.p, s->np, s->d[0], s->d[1], s->d[2], a, w,
+                                          out, stride);
+  ctx->launches++;
+  MB_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) k_tps_points(
+    const double* __restrict__ ksx, const double* __restrict__ ksy, const double* __restrict__ kc, int np,
+    double d0, double d1, double d2c, double cx, double cy, double scx, double scy,
+    const double* __restrict__ px, const double* __restrict__ py, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double sx = (px[i] - cx) / scx;
+  const double sy = (py[i] - cy) / scy;
+  double acc = 0.0;
+  for (int k = 0; k < np; ++k) {
+    const double dx = sx - ksx[k];
+    const double dy = sy - ksy[k];
+    double r2 = fmax(dx * dx + dy * dy, kD2Clamp);
+    acc += kc[k] * (0.5 * log(r2) * r2);
+  }
+  out[i] = d0 + d1 * sx + d2c * sy + kRbfConst * acc;
+}
+
+void tps_predict_points_dev(mb_ctx* ctx, const mb_spline* s, const double* x_dev, const double* y_dev, int n,
+                            double* out_dev, cudaStream_t st) {
+  if (n <= 0) return;
+  k_tps_points<<<(n + 255) / 256, 256, 0, st>>>(s->d_sx.p, s->d_sy.p, s->d_c.p, s->np, s->d[0], s->d[1], s->d[2],
+                                                s->center[0], s->center[1], s->scale[0], s->scale[1], x_dev, y_dev,
+                                                n, out_dev);
+  ctx->launches++;
+  MB_CUDA(cudaGetLastError());
+}
+
+void spline_finalize(mb_ctx* ctx, mb_spline* s) {
+  s->ctx = ctx;
+  cudaStream_t st = ctx->stream;
+  s->d_sx.upload(s->sx, st);
+  s->d_sy.upload(s->sy, st);
+  s->d_c.upload(s->c, st);
+  s->sum_abs_c = 0;
+  for (double v : s->c) s->sum_abs_c += std::fabs(v);
+  // fscale = max |f(knot)|: sets the accuracy target of the fast evaluator
+  DevBuf<double> dx(s->np), dy(s->np), df(s->np);
+  dx.upload(s->kx, st);
+  dy.upload(s->ky, st);
+  tps_predict_points_dev(ctx, s, dx.p, dy.p, s->np, df.p, st);
+  std::vector<double> f(s->np);
+  MB_CUDA(cudaMemcpyAsync(f.data(), df.p, sizeof(double) * s->np, cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  s->fscale = 0;
+  for (double v : f) s->fscale = std::max(s->fscale, std::fabs(v));
+}
+
+// =========================================================================================
+// K5: fast evaluation
+// =========================================================================================
+struct ChebTables {
+  int P = 0;
+  std::vector<double> xn, C, R0, R1;     // nodes, values->coefficients, child re-expansions (row-major P x P)
+  DevBuf<double> d_tab;                  // [xn | C | R0 | R1]
+};
+
+static void cheb_T(int P, long double x, long double* T) {
+  T[0] = 1.0L;
+  if (P > 1) T[1] = x;
+  for (int k = 2; k < P; ++k) T[k] = 2.0L * x * T[k - 1] - T[k - 2];
+}
+
+static ChebTables* get_tables(mb_ctx* ctx, int P) {
+  static thread_local std::map<std::pair<int, int>, std::unique_ptr<ChebTables>> cache;
+  auto key = std::make_pair(ctx->device, P);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second.get();
+  auto t = std::make_unique<ChebTables>();
+  t->P = P;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  std::vector<long double> xn(P), C(P * P), T(P);
+  for (int k = 0; k < P; ++k) xn[k] = cosl((2 * k + 1) * pi / (2.0L * P));
+  for (int i = 0; i < P; ++i) {
+    cheb_T(P, xn[i], T.data());
+    for (int j = 0; j < P; ++j) C[j * P + i] = (j == 0 ? 1.0L : 2.0L) / P * T[j];
+  }
+  t->xn.resize(P); t->C.resize(P * P); t->R0.resize(P * P); t->R1.resize(P * P);
+  for (int k = 0; k < P; ++k) t->xn[k] = (double)xn[k];
+  for (int i = 0; i < P * P; ++i) t->C[i] = (double)C[i];
+  for (int c = 0; c < 2; ++c) {
+    std::vector<long double> R(P * P, 0.0L);
+    for (int i = 0; i < P; ++i) {
+      cheb_T(P, (xn[i] + (2 * c - 1)) / 2.0L, T.data());   // child node i in parent coordinates
+      for (int j = 0; j < P; ++j)
+        for (int k = 0; k < P; ++k) R[j * P + k] += C[j * P + i] * T[k];
+    }
+    auto& dst = c == 0 ? t->R0 : t->R1;
+    for (int i = 0; i < P * P; ++i) dst[i] = (double)R[i];
+  }
+  std::vector<double> all;
+  all.insert(all.end(), t->xn.begin(), t->xn.end());
+  all.insert(all.end(), t->C.begin(), t->C.end());
+  all.insert(all.end(), t->R0.begin(), t->R0.end());
+  all.insert(all.end(), t->R1.begin(), t->R1.end());
+  t->d_tab.upload(all, ctx->stream);
+  MB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ChebTables* raw = t.get();
+  cache[key] = std::move(t);
+  return raw;
+}
+
+__host__ __device__ __forceinline__ uint32_t part1by1(uint32_t x) {
+  x &= 0x0000ffff;
+  x = (x ^ (x << 8)) & 0x00ff00ff;
+  x = (x ^ (x << 4)) & 0x0f0f0f0f;
+  x = (x ^ (x << 2)) & 0x33333333;
+  x = (x ^ (x << 1)) & 0x55555555;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t morton(uint32_t i, uint32_t j) { return part1by1(i) | (part1by1(j) << 1); }
+
+struct Lattice {
+  // s_x = sxo + hx * U, s_y = syo + hy * V with (U, V) in leaf-box units; hy < 0 (rows run south)
+  double sxo, hx, syo, hy;
+  int L;            // leaf level: 2^L x 2^L boxes
+  int offx, offy;   // leaf box of the window's first cell
+  int nbx, nby;     // leaf boxes covering the window
+  int bh;           // rows per leaf box (columns are always 32)
+};
+
+struct LevelInfo {
+  int lvl, sh;      // level, L - level
+  int I0, J0, nI, nJ;
+  int nsplit;
+  size_t coef_off;  // offset (in doubles) of this level's coefficient block
+  size_t part_off;  // offset of the partial-sum block
+};
+
+// -----------------------------------------------------------------------------------------
+// P2L: node values of the far field produced by the interaction list of each active box.
+// grid = (box, split); thread = Chebyshev node (jy, ix).  Candidate source boxes are the 6 x 6
+// children of the parent's 3 x 3 neighbourhood minus the box's own 3 x 3 neighbourhood.
+// -----------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(((P * P + 31) / 32) * 32) k_far_p2l(
+    Lattice lat, LevelInfo lv, const double* __restrict__ tab, const int* __restrict__ start,
+    const double4* __restrict__ knots, const double2* __restrict__ logtab, double* __restrict__ partial) {
+  __shared__ double2 s_log[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_log[i] = logtab[i];
+  __syncthreads();
+  const int box = blockIdx.x;
+  const int split = blockIdx.y;
+  const int I = lv.I0 + box % lv.nI;
+  const int J = lv.J0 + box / lv.nI;
+  const int node = threadIdx.x;
+  const bool live = node < P * P;
+  const int jy = live ? node / P : 0, ix = live ? node % P : 0;
+  const double scale = (double)(1 << lv.sh);
+  const double sxn = lat.sxo + lat.hx * scale * (I + 0.5 * (1.0 + tab[ix]));
+  const double syn = lat.syo + lat.hy * scale * (J + 0.5 * (1.0 + tab[jy]));
+  const int nside = 1 << lv.lvl;
+  const int bi0 = ((I >> 1) - 1) * 2, bj0 = ((J >> 1) - 1) * 2;
+  double acc = 0.0;
+  for (int cand = split; cand < 36; cand += lv.nsplit) {
+    const int i = bi0 + cand % 6, j = bj0 + cand / 6;
+    if (i < 0 || j < 0 || i >= nside || j >= nside) continue;
+    if (abs(i - I) <= 1 && abs(j - J) <= 1) continue;
+    const uint32_t z = morton(i, j);
+    const int a = start[(size_t)z << (2 * lv.sh)];
+    const int b = start[((size_t)z + 1) << (2 * lv.sh)];
+    for (int k = a; k < b; ++k) {
+      const double4 kn = ldg4(&knots[k]);
+      const double dx = sxn - kn.x, dy = syn - kn.y;
+      double r2 = fmax(fma(dx, dx, dy * dy), kD2Clamp);
+      acc = fma(kn.z * r2, tlog(r2, s_log), acc);
+    }
+  }
+  if (live) partial[lv.part_off + ((size_t)box * lv.nsplit + split) * (P * P) + node] = acc;
+}
+
+// -----------------------------------------------------------------------------------------
+// values -> Chebyshev coefficients, plus the parent's expansion re-expanded on this child
+// (exact for polynomials), plus - at the first level - the affine part d0 + d1 sx + d2 sy.
+// -----------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(((P * P + 31) / 32) * 32) k_far_transform(
+    Lattice lat, LevelInfo lv, LevelInfo parent, int has_parent, const double* __restrict__ tab,
+    const double* __restrict__ partial, double* __restrict__ coef, double d0, double d1, double d2c) {
+  __shared__ double s_a[P * P], s_b[P * P], s_p[P * P];
+  const double* Cm = tab + P;
+  const int box = blockIdx.x;
+  const int I = lv.I0 + box % lv.nI;
+  const int J = lv.J0 + box / lv.nI;
+  const int t = threadIdx.x;
+  const bool live = t < P * P;
+  const int r = live ? t / P : 0, q = live ? t % P : 0;
+  if (live) {
+    double v = 0.0;
+    for (int s = 0; s < lv.nsplit; ++s) v += partial[lv.part_off + ((size_t)box * lv.nsplit + s) * (P * P) + t];
+    s_a[t] = v;                                   // vals[jy][ix]
+    if (has_parent) {
+      const int pb = ((J >> 1) - parent.J0) * parent.nI + ((I >> 1) - parent.I0);
+      s_p[t] = coef[parent.coef_off + (size_t)pb * (P * P) + t];
+    }
+  }
+  __syncthreads();
+  double tmp = 0.0, tmp2 = 0.0;
+  if (live) {
+    // tmp[j=r][ix=q] = sum_jy C[r][jy] vals[jy][q]
+    for (int m = 0; m < P; ++m) tmp = fma(Cm[r * P + m], s_a[m * P + q], tmp);
+    if (has_parent) {
+      const double* Ry = tab + P + P * P + ((J & 1) ? P * P : 0);
+      for (int m = 0; m < P; ++m) tmp2 = fma(Ry[r * P + m], s_p[m * P + q], tmp2);
+    }
+  }
+  __syncthreads();
+  if (live) { s_b[t] = tmp; s_a[t] = tmp2; }
+  __syncthreads();
+  if (live) {
+    double v = 0.0;
+    // coef[j=r][k=q] = sum_ix tmp[r][ix] C[q][ix]
+    for (int m = 0; m < P; ++m) v = fma(s_b[r * P + m], Cm[q * P + m], v);
+    v *= 0.5 * kRbfConst;                         // E/2 factored out of the pair terms
+    if (has_parent) {
+      const double* Rx = tab + P + P * P + ((I & 1) ? P * P : 0);
+      double v2 = 0.0;
+      for (int m = 0; m < P; ++m) v2 = fma(s_a[r * P + m], Rx[q * P + m], v2);
+      v += v2;
+    } else {
+      const double scale = (double)(1 << lv.sh);
+      const double sxc = lat.sxo + lat.hx * scale * (I + 0.5);
+      const double syc = lat.syo + lat.hy * scale * (J + 0.5);
+      if (r == 0 && q == 0) v += d0 + d1 * sxc + d2c * syc;
+      if (r == 0 && q == 1) v += d1 * lat.hx * scale * 0.5;
+      if (r == 1 && q == 0) v += d2c * lat.hy * scale * 0.5;
+    }
+    coef[lv.coef_off + (size_t)box * (P * P) + t] = v;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// Leaf kernel: one CTA per leaf box (32 columns x bh rows).  lane = column.
+//   G[lr][k] = sum_j T_j(ty_lr) A[j][k]          (collapse y once per box row)
+//   far      = sum_k G[lr][k] T_k(tx_lane)       (T_k(tx_lane) lives in registers)
+//   near     = sum over knots of the 3 x 3 neighbourhood, float64, table log
+// -----------------------------------------------------------------------------------------
+constexpr int kLeafThreads = 256;
+constexpr int kNearCap = 256;
+
+template <int P>
+__global__ void __launch_bounds__(kLeafThreads) k_leaf(
+    Lattice lat, LevelInfo leaf, mb_window w, const double* __restrict__ coef, const int* __restrict__ start,
+    const double4* __restrict__ knots, const double2* __restrict__ logtab, double* __restrict__ out,
+    int64_t stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* s_log = reinterpret_cast<double2*>(smem_raw);              // 256
+  double4* s_near = reinterpret_cast<double4*>(s_log + 256);          // kNearCap
+  double* s_A = reinterpret_cast<double*>(s_near + kNearCap);         // P*P
+  double* s_G = s_A + P * P;                                          // bh*P
+  __shared__ int s_rng[9][2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bi = blockIdx.x, bj = blockIdx.y;
+  const int I = lat.offx + bi, J = lat.offy + bj;
+  const int box = bj * leaf.nI + bi;   // leaf level: I0 = offx, J0 = offy
+  for (int i = tid; i < 256; i += kLeafThreads) s_log[i] = logtab[i];
+  for (int i = tid; i < P * P; i += kLeafThreads) s_A[i] = coef[leaf.coef_off + (size_t)box * (P * P) + i];
+  if (tid < 9) {
+    const int i = I + tid % 3 - 1, j = J + tid / 3 - 1;
+    const int nside = 1 << lat.L;
+    int a = 0, b = 0;
+    if (i >= 0 && j >= 0 && i < nside && j < nside) {
+      const uint32_t z = morton(i, j);
+      a = start[z];
+      b = start[z + 1];
+    }
+    s_rng[tid][0] = a;
+    s_rng[tid][1] = b;
+  }
+  // T_k(tx) of this lane's column: identical for every box
+  double Tx[P];
+  {
+    const double tx = (2.0 * lane + 1.0) / 32.0 - 1.0;
+    Tx[0] = 1.0;
+    if (P > 1) Tx[1] = tx;
+#pragma unroll
+    for (int k = 2; k < P; ++k) Tx[k] = 2.0 * tx * Tx[k - 1] - Tx[k - 2];
+  }
+  __syncthreads();
+  // collapse y: thread -> (lr, k)
+  for (int o = tid; o < lat.bh * P; o += kLeafThreads) {
+    const int lr = o / P, k = o % P;
+    const double ty = (2.0 * lr + 1.0) / lat.bh - 1.0;
+    double t0 = 1.0, t1 = ty, g = s_A[k];
+    if (P > 1) g = fma(t1, s_A[P + k], g);
+#pragma unroll
+    for (int j = 2; j < P; ++j) {
+      const double t2 = 2.0 * ty * t1 - t0;
+      g = fma(t2, s_A[j * P + k], g);
+      t0 = t1; t1 = t2;
+    }
+    s_G[o] = g;
+  }
+  int tot = 0;
+#pragma unroll
+  for (int r = 0; r < 9; ++r) tot += s_rng[r][1] - s_rng[r][0];
+  const int col = w.c0 + bi * 32 + lane;
+  const double sx = lat.sxo + lat.hx * (I + (lane + 0.5) / 32.0);
+  const int row_base = w.r0 + bj * lat.bh;
+  constexpr int kWarps = kLeafThreads / 32;
+  // knots of the 3 x 3 neighbourhood are streamed through shared memory kNearCap at a time;
+  // one chunk is the common case (about one knot per box).
+  int base = 0;
+  do {
+    const int n = min(kNearCap, tot - base);
+    __syncthreads();
+    for (int i = tid; i < n; i += kLeafThreads) {
+      int f = base + i, idx = 0;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const int len = s_rng[r][1] - s_rng[r][0];
+        if (f >= 0 && f < len) idx = s_rng[r][0] + f;
+        f -= len;
+      }
+      s_near[i] = ldg4(&knots[idx]);
+    }
+    __syncthreads();
+    for (int lr = warp; lr < lat.bh; lr += kWarps) {
+      const int row = row_base + lr;
+      if (row >= w.r1) break;
+      const double sy = lat.syo + lat.hy * (J + (lr + 0.5) / lat.bh);
+      double* dst = out + (int64_t)(row - w.r0) * stride + (col - w.c0);
+      double a = 0.0;
+      if (base == 0) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) a = fma(s_G[lr * P + k], Tx[k], a);
+      } else if (col < w.c1) {
+        a = *dst;
+      }
+#pragma unroll 2
+      for (int i = 0; i < n; ++i) {
+        const double4 kn = s_near[i];
+        const double dx = sx - kn.x, dy = sy - kn.y;
+        const double r2 = fmax(fma(dx, dx, dy * dy), kD2Clamp);
+        a = fma(kn.w * r2, tlog(r2, s_log), a);
+      }
+      if (col < w.c1) *dst = a;
+    }
+    base += kNearCap;
+  } while (base < tot);
+}
+
+// -----------------------------------------------------------------------------------------
+// host side: plan + launches
+// -----------------------------------------------------------------------------------------
+static int choose_p(const mb_ctx* ctx, const mb_spline* s) {
+  if (ctx->cheb_p) return ctx->cheb_p;
+  // measured interpolation error per unit sum|c| (3 x 3 near field), x3 margin
+  static const int ps[5] = {8, 10, 12, 14, 16};
+  static const double err[5] = {2.5e-11, 5e-13, 2e-14, 6e-16, 2e-17};
+  const double target = 2e-7 * std::max(s->fscale, 1e-300);
+  for (int i = 0; i < 5; ++i)
+    if (err[i] * s->sum_abs_c <= target) return ps[i];
+  return 16;
+}
+
+template <int P>
+static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const std::vector<LevelInfo>& levels,
+                     size_t coef_total, size_t part_total, const std::vector<int>& start,
+                     const std::vector<double4>& sorted, const mb_window& w, double* out, int64_t stride,
+                     cudaStream_t st) {
+  ChebTables* tabs = get_tables(ctx, P);
+  DevBuf<int> d_start;
+  DevBuf<double4> d_knots;
+  DevBuf<double> d_coef(coef_total), d_part(part_total);
+  d_start.upload(start, st);
+  d_knots.upload(sorted, st);
+  constexpr int threads = ((P * P + 31) / 32) * 32;
+  for (size_t li = 0; li < levels.size(); ++li) {
+    const LevelInfo& lv = levels[li];
+    dim3 grid(lv.nI * lv.nJ, lv.nsplit);
+    k_far_p2l<P><<<grid, threads, 0, st>>>(lat, lv, tabs->d_tab.p, d_start.p, d_knots.p, ctx->logtab.p, d_part.p);
+    ctx->launches++;
+    const LevelInfo& par = li ? levels[li - 1] : lv;
+    k_far_transform<P><<<lv.nI * lv.nJ, threads, 0, st>>>(lat, lv, par, li ? 1 : 0, tabs->d_tab.p, d_part.p,
+                                                           d_coef.p, s->d[0], s->d[1], s->d[2]);
+    ctx->launches++;
+  }
+  MB_CUDA(cudaGetLastError());
+  const LevelInfo& leaf = levels.back();
+  const size_t smem = 256 * sizeof(double2) + kNearCap * sizeof(double4) +
+                      sizeof(double) * (P * P + (size_t)lat.bh * P);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    MB_CUDA(cudaFuncSetAttribute(k_leaf<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(lat.nbx, lat.nby);
+  k_leaf<P><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef.p, d_start.p, d_knots.p, ctx->logtab.p, out,
+                                              stride);
+  ctx->launches++;
+  MB_CUDA(cudaGetLastError());
+  // the plan buffers are stream-ordered temporaries: wait before they are released
+  MB_CUDA(cudaStreamSynchronize(st));
+}
+
+void tps_eval_fast(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
+                   int64_t stride, cudaStream_t st) {
+  const GridAffine a = make_affine(g, *s);
+  const int P = choose_p(ctx, s);
+  const double ax = a.rx / a.scx, ay = -a.ry / a.scy;
+  int bh = ctx->leaf_rows;
+  if (bh <= 0) bh = (int)std::lround(32.0 * ax / std::fabs(ay));
+  bh = std::max(4, std::min(128, bh));
+  Lattice lat;
+  lat.bh = bh;
+  lat.hx = ax * 32.0;
+  lat.hy = ay * bh;
+  lat.nbx = (w.c1 - w.c0 + 31) / 32;
+  lat.nby = (w.r1 - w.r0 + bh - 1) / bh;
+  // s at the window's west / north cell edge
+  const double sxe = ((a.xmin + (w.c0 + 0.5) * a.rx) - a.cx) / a.scx - 0.5 * ax;
+  const double sye = ((a.ymax - (w.r0 + 0.5) * a.ry) - a.cy) / a.scy - 0.5 * ay;
+  // knot lattice coordinates relative to the window origin
+  const int np = s->np;
+  std::vector<int> ki(np), kj(np);
+  int imin = 0, jmin = 0, imax = lat.nbx - 1, jmax = lat.nby - 1;
+  for (int k = 0; k < np; ++k) {
+    ki[k] = (int)std::floor((s->sx[k] - sxe) / lat.hx);
+    kj[k] = (int)std::floor((s->sy[k] - sye) / lat.hy);
+    imin = std::min(imin, ki[k]); imax = std::max(imax, ki[k]);
+    jmin = std::min(jmin, kj[k]); jmax = std::max(jmax, kj[k]);
+  }
+  lat.offx = -imin;
+  lat.offy = -jmin;
+  const int span = std::max(imax - imin + 1, jmax - jmin + 1);
+  int L = 2;
+  while ((1 << L) < span) ++L;
+  if (L > 12) throw Error(MB_E_UNSUPPORTED, "fast evaluator: knot cloud too far outside the window (lattice > 4096^2 boxes)");
+  lat.L = L;
+  lat.sxo = sxe - lat.hx * lat.offx;
+  lat.syo = sye - lat.hy * lat.offy;
+  // Morton-sorted knots + CSR over leaf boxes; c is pre-multiplied only in the transform (E/2)
+  const size_t nleaf = (size_t)1 << (2 * L);
+  std::vector<int> start(nleaf + 1, 0);
+  std::vector<uint32_t> kz(np);
+  for (int k = 0; k < np; ++k) {
+    kz[k] = morton(ki[k] + lat.offx, kj[k] + lat.offy);
+    start[kz[k] + 1]++;
+  }
+  for (size_t z = 0; z < nleaf; ++z) start[z + 1] += start[z];
+  std::vector<int> cursor(start.begin(), start.end() - 1);
+  std::vector<double4> sorted(np);
+  for (int k = 0; k < np; ++k) {
+    const int dst = cursor[kz[k]]++;
+    // .z = c for the far field (E/2 applied after the transform), .w = c E/2 for the near field
+    sorted[dst] = make_double4(s->sx[k], s->sy[k], s->c[k], s->c[k] * 0.5 * kRbfConst);
+  }
+  // levels 2..L
+  std::vector<LevelInfo> levels;
+  size_t coef_total = 0, part_total = 0;
+  for (int lvl = 2; lvl <= L; ++lvl) {
+    LevelInfo lv;
+    lv.lvl = lvl;
+    lv.sh = L - lvl;
+    lv.I0 = lat.offx >> lv.sh;
+    lv.J0 = lat.offy >> lv.sh;
+    lv.nI = ((lat.offx + lat.nbx - 1) >> lv.sh) - lv.I0 + 1;
+    lv.nJ = ((lat.offy + lat.nby - 1) >> lv.sh) - lv.J0 + 1;
+    const int nb = lv.nI * lv.nJ;
+    lv.nsplit = std::max(1, std::min(36, (4 * ctx->sm_count + nb - 1) / nb));
+    lv.coef_off = coef_total;
+    lv.part_off = part_total;
+    coef_total += (size_t)nb * P * P;
+    part_total += (size_t)nb * lv.nsplit * P * P;
+    levels.push_back(lv);
+  }
+  switch (P) {
+    case 8:  run_fast<8>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
+    case 10: run_fast<10>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
+    case 12: run_fast<12>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
+    case 14: run_fast<14>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
+    case 16: run_fast<16>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
+    default: throw Error(MB_E_ARG, "cheb_p must be one of 8, 10, 12, 14, 16");
+  }
+}
+
+}  // namespace mb

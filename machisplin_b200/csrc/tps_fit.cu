@@ -1,0 +1,682 @@
+// Thin-plate smoothing-spline fit on the device - replaces fields::Tps(x, Y) at V73:722 and V73:751
+// (Tps -> Krig -> Krig.engine.default "WBW" decomposition -> gcv.Krig -> Krig.coef; SURVEY.md 3.2,
+// Appendix A).  m = 2, d = 2, scale.type = "range", method = "GCV" unless a lambda is given.
+//
+//   K1 k_assemble        W^1/2 K W^1/2,  K_ij = (1/8pi) 1/2 d2 log d2        (N x N float64, coalesced)
+//   K1b reflectors       M = Q2' K Q2 by three two-sided Householder updates  (gemv + rank-2)
+//   K2 Cholesky          fixed lambda: blocked right-looking LL' of M + lambda I; the trailing SYRK
+//                        runs on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA)
+//   K3 GCV               eigen(M) [cuSOLVER Dsyevd - LIBRARY CALL, stand-in until the in-house
+//                        tridiagonal solver lands], u = V'Q2'y, fields' 200-point df grid + golden
+//                        section on the host in float64.
+#include "common.cuh"
+#include "internal.h"
+
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <numeric>
+
+namespace mb {
+
+// ---------------------------------------------------------------------------------------------
+// library handles kept per context
+// ---------------------------------------------------------------------------------------------
+struct FitLibs {
+  cusolverDnHandle_t solver = nullptr;
+};
+static std::map<mb_ctx*, FitLibs>& libs_map() {
+  static std::map<mb_ctx*, FitLibs> m;
+  return m;
+}
+static FitLibs& libs(mb_ctx* ctx) {
+  FitLibs& l = libs_map()[ctx];
+  if (!l.solver) {
+    if (cusolverDnCreate(&l.solver) != CUSOLVER_STATUS_SUCCESS) throw Error(MB_E_CUDA, "cusolverDnCreate failed");
+    cusolverDnSetStream(l.solver, ctx->stream);
+  }
+  return l;
+}
+void fit_release(mb_ctx* ctx) {
+  auto it = libs_map().find(ctx);
+  if (it == libs_map().end()) return;
+  if (it->second.solver) cusolverDnDestroy(it->second.solver);
+  libs_map().erase(it);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: assemble sqrt(w_i) K_ij sqrt(w_j), column-major with leading dimension ld
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assemble(const double* __restrict__ sx, const double* __restrict__ sy,
+                                                  const double* __restrict__ w2, int np, double* __restrict__ K,
+                                                  int ld) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int j0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+  if (i >= np) return;
+  const double xi = sx[i], yi = sy[i], wi = w2[i];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = j0 + q;
+    if (j < np) {
+      const double dx = xi - sx[j], dy = yi - sy[j];
+      const double r2 = fmax(dx * dx + dy * dy, kD2Clamp);
+      K[(size_t)j * ld + i] = wi * w2[j] * (kRbfConst * (0.5 * log(r2) * r2));
+    }
+  }
+}
+
+// y_partial[chunk][i] = sum_{j in chunk} A[i, j] x[j]   (column-major, rows coalesced)
+constexpr int kGemvChunks = 32;
+__global__ void __launch_bounds__(128) k_gemv_n_partial(const double* __restrict__ A, int ld, int m, int n,
+                                                        const double* __restrict__ x, double* __restrict__ part) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int chunk = blockIdx.y;
+  const int per = (n + kGemvChunks - 1) / kGemvChunks;
+  const int j0 = chunk * per, j1 = min(n, j0 + per);
+  if (i >= m) return;
+  double acc = 0.0;
+  for (int j = j0; j < j1; ++j) acc = fma(A[(size_t)j * ld + i], x[j], acc);
+  part[(size_t)chunk * m + i] = acc;
+}
+__global__ void k_gemv_n_reduce(const double* __restrict__ part, int m, double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double acc = 0.0;
+  for (int c = 0; c < kGemvChunks; ++c) acc += part[(size_t)c * m + i];
+  y[i] = acc;
+}
+// y[j] = sum_i A[i, j] x[i] : one warp per column
+__global__ void __launch_bounds__(256) k_gemv_t(const double* __restrict__ A, int ld, int m, int n,
+                                                const double* __restrict__ x, double* __restrict__ y) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= n) return;
+  double acc = 0.0;
+  for (int i = lane; i < m; i += 32) acc = fma(A[(size_t)j * ld + i], x[i], acc);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[j] = acc;
+}
+
+// q = 2 p - 2 (v'p) v   (single CTA; H K H = K - v q' - q v')
+__global__ void __launch_bounds__(1024) k_make_q(const double* __restrict__ v, const double* __restrict__ p, int n,
+                                                 double* __restrict__ q) {
+  __shared__ double s_red[32];
+  __shared__ double s_alpha;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], p[i], acc);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += s_red[i];
+    s_alpha = a;
+  }
+  __syncthreads();
+  const double alpha = s_alpha;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) q[i] = 2.0 * p[i] - 2.0 * alpha * v[i];
+}
+__global__ void __launch_bounds__(256) k_rank2(double* __restrict__ K, int ld, int n, const double* __restrict__ v,
+                                               const double* __restrict__ q) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int j0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+  if (i >= n) return;
+  const double vi = v[i], qi = q[i];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = j0 + t;
+    if (j < n) K[(size_t)j * ld + i] -= vi * q[j] + qi * v[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: blocked Cholesky (lower) of the m x m matrix at A (column-major, ld), NB = 64
+// ---------------------------------------------------------------------------------------------
+constexpr int kNB = 64;
+
+__global__ void k_add_diag(double* A, int ld, int m, double lam) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) A[(size_t)i * ld + i] += lam;
+}
+
+// factor the kb x kb diagonal block in shared memory; info = 1 + failing column if not SPD
+__global__ void __launch_bounds__(kNB) k_potrf_diag(double* __restrict__ A, int ld, int kb, int col0,
+                                                    int* __restrict__ info) {
+  __shared__ double s[kNB][kNB + 1];
+  const int t = threadIdx.x;
+  for (int j = 0; j < kb; ++j)
+    if (t < kb) s[t][j] = A[(size_t)j * ld + t];
+  __syncthreads();
+  for (int j = 0; j < kb; ++j) {
+    const double djj = s[j][j];
+    if (!(djj > 0.0)) {
+      if (t == 0 && *info == 0) *info = col0 + j + 1;
+      return;
+    }
+    const double l = sqrt(djj);
+    __syncthreads();
+    if (t == j) s[j][j] = l;
+    if (t > j && t < kb) s[t][j] /= l;
+    __syncthreads();
+    if (t > j && t < kb) {
+      const double ltj = s[t][j];
+      for (int c = j + 1; c <= t; ++c) s[t][c] -= ltj * s[c][j];
+    }
+    __syncthreads();
+  }
+  for (int j = 0; j < kb; ++j)
+    if (t < kb) A[(size_t)j * ld + t] = (t >= j) ? s[t][j] : 0.0;
+}
+
+// rows below the diagonal block: X L11' = A21  ->  one thread per row
+__global__ void __launch_bounds__(128) k_trsm_panel(const double* __restrict__ L11, double* __restrict__ A21, int ld,
+                                                    int kb, int nrows) {
+  __shared__ double s[kNB][kNB + 1];
+  for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
+    const int r = idx % kb, c = idx / kb;
+    s[r][c] = L11[(size_t)c * ld + r];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  double x[kNB];
+#pragma unroll 8
+  for (int j = 0; j < kNB; ++j) x[j] = (j < kb) ? A21[(size_t)j * ld + i] : 0.0;
+  for (int j = 0; j < kb; ++j) {
+    double v = x[j];
+    for (int c = 0; c < j; ++c) v -= x[c] * s[j][c];
+    x[j] = v / s[j][j];
+  }
+  for (int j = 0; j < kb; ++j) A21[(size_t)j * ld + i] = x[j];
+}
+
+// trailing update on the FP64 tensor pipe:  C(lower tiles) -= P P',  P = panel (n x kb, column-major ld)
+// CTA = 64 x 64 tile of C, 8 warps; warp w owns tile rows [8w, 8w+8) and all 8 column blocks.
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256) k_syrk_dmma(const double* __restrict__ Pn, double* __restrict__ C, int ld,
+                                                   int n, int kb) {
+  const int ti = blockIdx.x, tj = blockIdx.y;
+  if (tj > ti) return;
+  constexpr int S = kNB + 4;               // padded stride: conflict-free 8 x 4 fragment reads
+  extern __shared__ __align__(16) double s_syrk[];
+  double* sA = s_syrk;                     // sA[row * S + k]
+  double* sB = s_syrk + kNB * S;
+  const int i0 = ti * kNB, j0 = tj * kNB;
+  for (int idx = threadIdx.x; idx < kNB * kNB; idx += 256) {
+    const int r = idx % kNB, k = idx / kNB;  // coalesced along rows of the column-major panel
+    sA[r * S + k] = (i0 + r < n && k < kb) ? Pn[(size_t)k * ld + i0 + r] : 0.0;
+    sB[r * S + k] = (j0 + r < n && k < kb) ? Pn[(size_t)k * ld + j0 + r] : 0.0;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[8][2];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
+#pragma unroll 4
+  for (int k0 = 0; k0 < kNB; k0 += 4) {
+    const double a = sA[(warp * 8 + fr) * S + k0 + fk];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const double b = sB[(nb * 8 + fr) * S + k0 + fk];
+      dmma_m8n8k4(acc[nb][0], acc[nb][1], a, b);
+    }
+  }
+  const int gi = i0 + warp * 8 + fr;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int gj = j0 + nb * 8 + fk * 2 + e;
+      if (gi < n && gj < n && gj <= gi) C[(size_t)gj * ld + gi] -= acc[nb][e];
+    }
+  }
+}
+
+// forward / backward substitution with the Cholesky factor for nrhs right-hand sides (single CTA;
+// O(m^2) work, negligible next to the O(m^3) factorisation).  The 64 x 64 diagonal block is staged
+// in shared memory and solved by warp 0; the off-diagonal update is spread over the whole CTA.
+__global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ Lm, int ld, int m,
+                                                     double* __restrict__ B, int ldb, int nrhs) {
+  __shared__ double s_L[kNB][kNB + 1];
+  __shared__ double s_x[kNB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int r = 0; r < nrhs; ++r) {
+    double* b = B + (size_t)r * ldb;
+    // ---- L y = b ----
+    for (int k0 = 0; k0 < m; k0 += kNB) {
+      const int kb = min(kNB, m - k0);
+      for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
+        const int i = idx % kb, j = idx / kb;
+        s_L[i][j] = Lm[(size_t)(k0 + j) * ld + k0 + i];
+      }
+      if (threadIdx.x < kb) s_x[threadIdx.x] = b[k0 + threadIdx.x];
+      __syncthreads();
+      if (warp == 0) {
+        for (int j = 0; j < kb; ++j) {
+          const double v = s_x[j] / s_L[j][j];
+          __syncwarp();
+          if (lane == 0) s_x[j] = v;
+          for (int i = j + 1 + lane; i < kb; i += 32) s_x[i] -= v * s_L[i][j];
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < kb) b[k0 + threadIdx.x] = s_x[threadIdx.x];
+      for (int i = k0 + kb + threadIdx.x; i < m; i += blockDim.x) {
+        double acc = b[i];
+        for (int j = 0; j < kb; ++j) acc -= Lm[(size_t)(k0 + j) * ld + i] * s_x[j];
+        b[i] = acc;
+      }
+      __syncthreads();
+    }
+    // ---- L' x = y ----
+    for (int k1 = m; k1 > 0; k1 -= kNB) {
+      const int k0 = max(0, k1 - kNB);
+      const int kb = k1 - k0;
+      for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
+        const int i = idx % kb, j = idx / kb;
+        s_L[i][j] = Lm[(size_t)(k0 + j) * ld + k0 + i];
+      }
+      // tail: s_x[j] = b[k0 + j] - sum_{i >= k1} L[i, k0 + j] x[i]
+      for (int j = warp; j < kb; j += nwarp) {
+        double acc = 0.0;
+        for (int i = k1 + lane; i < m; i += 32) acc = fma(Lm[(size_t)(k0 + j) * ld + i], b[i], acc);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_x[j] = b[k0 + j] - acc;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        for (int j = kb - 1; j >= 0; --j) {
+          const double v = s_x[j] / s_L[j][j];
+          __syncwarp();
+          if (lane == 0) s_x[j] = v;
+          for (int i = lane; i < j; i += 32) s_x[i] -= v * s_L[j][i];
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < kb) b[k0 + threadIdx.x] = s_x[threadIdx.x];
+      __syncthreads();
+    }
+  }
+}
+
+static void cholesky_lower(mb_ctx* ctx, double* A, int ld, int m, cudaStream_t st) {
+  constexpr size_t kSyrkSmem = 2 * kNB * (kNB + 4) * sizeof(double);
+  MB_CUDA(cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
+  DevBuf<int> d_info(1);
+  MB_CUDA(cudaMemsetAsync(d_info.p, 0, sizeof(int), st));
+  for (int k = 0; k < m; k += kNB) {
+    const int kb = std::min(kNB, m - k);
+    double* Akk = A + (size_t)k * ld + k;
+    k_potrf_diag<<<1, kNB, 0, st>>>(Akk, ld, kb, k, d_info.p);
+    ctx->launches++;
+    const int rest = m - k - kb;
+    if (rest > 0) {
+      k_trsm_panel<<<(rest + 127) / 128, 128, 0, st>>>(Akk, Akk + kb, ld, kb, rest);
+      const int nt = (rest + kNB - 1) / kNB;
+      k_syrk_dmma<<<dim3(nt, nt), 256, kSyrkSmem, st>>>(Akk + kb, A + (size_t)(k + kb) * ld + (k + kb), ld, rest, kb);
+      ctx->launches += 2;
+    }
+  }
+  int info = 0;
+  MB_CUDA(cudaMemcpyAsync(&info, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  MB_CUDA(cudaGetLastError());
+  if (info != 0)
+    throw Error(MB_E_NUMERIC, "Cholesky: Q2'KQ2 + lambda I is not positive definite at column " + std::to_string(info));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: Householder QR of sqrt(w) [1, s1, s2], replicate pooling, fields' GCV search
+// ---------------------------------------------------------------------------------------------
+struct QRT {
+  int n = 0;
+  std::vector<double> v[3];   // unit Householder vectors, v[j][i] = 0 for i < j
+  double R[3][3] = {{0}};
+  explicit QRT(const std::vector<double>* T, int n_) : n(n_) {
+    std::vector<double> A[3] = {T[0], T[1], T[2]};
+    for (int j = 0; j < 3; ++j) {
+      double nrm = 0;
+      for (int i = j; i < n; ++i) nrm += A[j][i] * A[j][i];
+      nrm = std::sqrt(nrm);
+      const double alpha = -std::copysign(nrm, A[j][j] != 0 ? A[j][j] : 1.0);
+      v[j].assign(n, 0.0);
+      for (int i = j; i < n; ++i) v[j][i] = A[j][i];
+      v[j][j] -= alpha;
+      double vn = 0;
+      for (int i = j; i < n; ++i) vn += v[j][i] * v[j][i];
+      vn = std::sqrt(vn);
+      if (!(vn > 0)) throw Error(MB_E_NUMERIC, "Regression matrix for fixed part of model is colinear");
+      for (int i = j; i < n; ++i) v[j][i] /= vn;
+      for (int c = j; c < 3; ++c) {
+        double dot = 0;
+        for (int i = j; i < n; ++i) dot += v[j][i] * A[c][i];
+        for (int i = j; i < n; ++i) A[c][i] -= 2.0 * dot * v[j][i];
+      }
+    }
+    double dmax = 0, dmin = 1e300;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) R[r][c] = (c >= r) ? A[c][r] : 0.0;
+    for (int r = 0; r < 3; ++r) { dmax = std::max(dmax, std::fabs(R[r][r])); dmin = std::min(dmin, std::fabs(R[r][r])); }
+    if (dmin < 1e-12 * dmax) throw Error(MB_E_NUMERIC, "Regression matrix for fixed part of model is colinear");
+  }
+  void qty(std::vector<double>& b) const {
+    for (int j = 0; j < 3; ++j) {
+      double dot = 0;
+      for (int i = j; i < n; ++i) dot += v[j][i] * b[i];
+      for (int i = j; i < n; ++i) b[i] -= 2.0 * dot * v[j][i];
+    }
+  }
+  void qy(std::vector<double>& b) const {
+    for (int j = 2; j >= 0; --j) {
+      double dot = 0;
+      for (int i = j; i < n; ++i) dot += v[j][i] * b[i];
+      for (int i = j; i < n; ++i) b[i] -= 2.0 * dot * v[j][i];
+    }
+  }
+  void coef(std::vector<double> b, double* d) const {   // R^-1 Q1' b
+    qty(b);
+    for (int r = 2; r >= 0; --r) {
+      double s = b[r];
+      for (int c = r + 1; c < 3; ++c) s -= R[r][c] * d[c];
+      d[r] = s / R[r][r];
+    }
+  }
+};
+
+namespace gcv {
+static double tr_a(double lam, const std::vector<double>& D) {
+  double s = 0;
+  for (double d : D) s += 1.0 / (1.0 + lam * d);
+  return s;
+}
+static double value(double lam, const std::vector<double>& D, const std::vector<double>& u, int n_obs, double pure_ss) {
+  const int np = (int)D.size();
+  double rss = 0, tra = 0;
+  for (int k = 0; k < np; ++k) {
+    const double lD = D[k] * lam;
+    const double t = (u[k] * lD) / (1.0 + lD);
+    rss += t * t;
+    tra += 1.0 / (1.0 + lD);
+  }
+  double mse = rss / np;
+  if (n_obs - np > 0) mse += pure_ss / (n_obs - np);
+  const double den = 1.0 - ((tra - 3.0) + 3.0) / np;   // cost = 1, offset = 0, nt = 3
+  return den > 0 ? mse / (den * den) : NAN;
+}
+static double df_to_lambda(double df, const std::vector<double>& D) {
+  double l1 = 1.0;
+  for (int k = 0; k < 25; ++k) { if (tr_a(l1, D) <= df) break; l1 *= 4.0; }
+  double l2 = 1.0;
+  for (int k = 0; k < 25; ++k) { if (tr_a(l2, D) >= df) break; l2 /= 4.0; }
+  double x1 = std::log(l1), x2 = std::log(l2);
+  double f1 = tr_a(std::exp(x1), D) - df, f2 = tr_a(std::exp(x2), D) - df;
+  if (f1 > f2) throw Error(MB_E_NUMERIC, "bisection.search: f1 must be < f2");
+  for (int k = 0; k < 25; ++k) {
+    const double xm = (x1 + x2) / 2.0;
+    const double fm = tr_a(std::exp(xm), D) - df;
+    if (fm < 0) { x1 = xm; f1 = fm; } else { x2 = xm; f2 = fm; }
+    if (std::fabs(fm) < 1e-5) break;
+  }
+  return std::exp((x1 + x2) / 2.0);
+}
+static std::vector<double> lambda_grid(const std::vector<double>& D) {
+  const int np = (int)D.size(), nstep = 200;
+  std::vector<double> g(nstep);
+  for (int k = 0; k < nstep; ++k) {
+    double df = 3.0 + (0.95 * np - 3.0) * k / (nstep - 1.0);
+    if (k == 0) df += 0.001;
+    g[k] = df_to_lambda(df, D);
+  }
+  std::sort(g.begin(), g.end());
+  return g;
+}
+template <class F>
+static double golden(double ax, double bx, double cx, F f, double tol) {
+  const double r = 0.61803399, con = 1.0 - r;
+  double x0 = ax, x3 = cx, x1, x2;
+  if (std::fabs(cx - bx) > std::fabs(bx - ax)) { x1 = bx; x2 = bx + con * (bx - ax); }
+  else { x2 = bx; x1 = bx - con * (bx - ax); }
+  double f1 = f(x1), f2 = f(x2);
+  for (int k = 0; k < 25; ++k) {
+    if (f2 < f1) { x0 = x1; x1 = x2; x2 = r * x1 + con * x3; f1 = f2; f2 = f(x2); }
+    else { x3 = x2; x2 = x1; x1 = r * x2 + con * x0; f2 = f1; f1 = f(x1); }
+    if (std::fabs(f2 - f1) < tol) break;
+  }
+  return f1 < f2 ? x1 : x2;
+}
+static double search(const std::vector<double>& D, const std::vector<double>& u, const std::vector<double>& grid,
+                     int n_obs, double pure_ss, double* gcv_min) {
+  std::vector<double> lg, gg;
+  for (double l : grid) {
+    const double g = value(l, D, u, n_obs, pure_ss);
+    if (!std::isnan(g)) { lg.push_back(l); gg.push_back(g); }
+  }
+  if (lg.empty()) throw Error(MB_E_NUMERIC, "GCV is undefined on the whole lambda grid");
+  const int il = (int)(std::min_element(gg.begin(), gg.end()) - gg.begin());
+  double lam = lg[il];
+  if (il > 0 && il < (int)lg.size() - 1) {
+    auto f = [&](double l) { return value(l, D, u, n_obs, pure_ss); };
+    lam = golden(lg[il - 1], lg[il], lg[il + 1], f, 1e-5 * gg[il]);
+  }  // else: fields warns "GCV search gives a minimum at the endpoints of the grid search" and keeps the endpoint
+  if (gcv_min) *gcv_min = value(lam, D, u, n_obs, pure_ss);
+  return lam;
+}
+}  // namespace gcv
+
+// ---------------------------------------------------------------------------------------------
+// the fit
+// ---------------------------------------------------------------------------------------------
+static void gemv_n(mb_ctx* ctx, const double* A, int ld, int m, int n, const double* x, double* y, double* part,
+                   cudaStream_t st) {
+  k_gemv_n_partial<<<dim3((m + 127) / 128, kGemvChunks), 128, 0, st>>>(A, ld, m, n, x, part);
+  k_gemv_n_reduce<<<(m + 255) / 256, 256, 0, st>>>(part, m, y);
+  ctx->launches += 2;
+}
+
+void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, double lambda, mb_spline** out) {
+  cudaStream_t st = ctx->stream;
+  for (int r = 0; r < L; ++r) out[r] = nullptr;
+  // ---- transformx (scale.type = "range") + Krig.replicates -------------------------------------
+  double cmin[2] = {1e300, 1e300}, cmax[2] = {-1e300, -1e300};
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < 2; ++a) {
+      const double v = xy[(size_t)a * n + i];
+      MB_REQUIRE(std::isfinite(v), "non-finite coordinate in xy");
+      cmin[a] = std::min(cmin[a], v);
+      cmax[a] = std::max(cmax[a], v);
+    }
+  const double scale[2] = {cmax[0] - cmin[0], cmax[1] - cmin[1]};
+  if (!(scale[0] > 0 && scale[1] > 0)) throw Error(MB_E_NUMERIC, "degenerate knot cloud (zero range)");
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (xy[a] != xy[b]) return xy[a] < xy[b];
+    return xy[(size_t)n + a] < xy[(size_t)n + b];
+  });
+  std::vector<int> group(n);
+  int np = 0;
+  for (int k = 0; k < n; ++k) {
+    if (k == 0 || xy[order[k]] != xy[order[k - 1]] || xy[(size_t)n + order[k]] != xy[(size_t)n + order[k - 1]]) ++np;
+    group[order[k]] = np - 1;
+  }
+  const bool replicated = np < n;
+  if (!replicated)
+    for (int i = 0; i < n; ++i) group[i] = i;     // keep the caller's order when locations are distinct
+  if (np <= 3) throw Error(MB_E_NUMERIC, "need more than 3 unique locations");
+  std::vector<double> kx(np), ky(np), wM(np, 0.0);
+  std::vector<std::vector<double>> yM(L, std::vector<double>(np, 0.0));
+  std::vector<double> pure_ss(L, 0.0);
+  for (int i = 0; i < n; ++i) {
+    const int gidx = group[i];
+    kx[gidx] = xy[i];
+    ky[gidx] = xy[(size_t)n + i];
+    wM[gidx] += 1.0;
+    for (int r = 0; r < L; ++r) yM[r][gidx] += y[(size_t)r * n + i];
+  }
+  for (int r = 0; r < L; ++r) {
+    for (int k = 0; k < np; ++k) yM[r][k] /= wM[k];
+    if (replicated)
+      for (int i = 0; i < n; ++i) {
+        const double e = y[(size_t)r * n + i] - yM[r][group[i]];
+        pure_ss[r] += e * e;
+      }
+  }
+  std::vector<double> sx(np), sy(np), w2(np);
+  for (int k = 0; k < np; ++k) {
+    sx[k] = (kx[k] - cmin[0]) / scale[0];
+    sy[k] = (ky[k] - cmin[1]) / scale[1];
+    w2[k] = std::sqrt(wM[k]);
+  }
+  // ---- qr(sqrt(w) T) ------------------------------------------------------------------------------
+  std::vector<double> T[3] = {std::vector<double>(np), std::vector<double>(np), std::vector<double>(np)};
+  for (int k = 0; k < np; ++k) { T[0][k] = w2[k]; T[1][k] = w2[k] * sx[k]; T[2][k] = w2[k] * sy[k]; }
+  QRT qr(T, np);
+  const int m = np - 3;
+  // ---- device: K, projection ------------------------------------------------------------------------
+  DevBuf<double> d_sx, d_sy, d_w2, d_K((size_t)np * np), d_v(np), d_p(np), d_q(np), d_part((size_t)kGemvChunks * np);
+  d_sx.upload(sx, st);
+  d_sy.upload(sy, st);
+  d_w2.upload(w2, st);
+  const dim3 g2((np + 31) / 32, (np + 31) / 32);
+  k_assemble<<<g2, 256, 0, st>>>(d_sx.p, d_sy.p, d_w2.p, np, d_K.p, np);
+  ctx->launches++;
+  for (int j = 0; j < 3; ++j) {
+    d_v.upload(qr.v[j], st);
+    gemv_n(ctx, d_K.p, np, np, np, d_v.p, d_p.p, d_part.p, st);
+    k_make_q<<<1, 1024, 0, st>>>(d_v.p, d_p.p, np, d_q.p);
+    k_rank2<<<g2, 256, 0, st>>>(d_K.p, np, np, d_v.p, d_q.p);
+    ctx->launches += 2;
+    MB_CUDA(cudaStreamSynchronize(st));   // d_v is re-uploaded from a host vector next iteration
+  }
+  MB_CUDA(cudaGetLastError());
+  // M = Q2' W^1/2 K W^1/2 Q2 = rows/cols 3.. of the reflected matrix, compacted to a 16-byte aligned m x m block
+  DevBuf<double> d_M((size_t)m * m);
+  MB_CUDA(cudaMemcpy2DAsync(d_M.p, sizeof(double) * m, d_K.p + (size_t)3 * np + 3, sizeof(double) * np,
+                            sizeof(double) * m, m, cudaMemcpyDeviceToDevice, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  d_K.release();
+  double* M = d_M.p;
+
+  // z_r = Q2' sqrt(w) yM_r
+  std::vector<std::vector<double>> z(L);
+  for (int r = 0; r < L; ++r) {
+    std::vector<double> b(np);
+    for (int k = 0; k < np; ++k) b[k] = w2[k] * yM[r][k];
+    qr.qty(b);
+    z[r].assign(b.begin() + 3, b.end());
+  }
+
+  std::vector<double> lam(L, lambda), edf(L, -1.0), gcvv(L, -1.0);
+  std::vector<std::vector<double>> beta(L, std::vector<double>(m));
+  std::vector<double> eta_desc;
+  std::vector<std::vector<double>> u_full(L);
+
+  if (lambda < 0) {
+    // ---- eigen(M): cuSOLVER Dsyevd (library stand-in, see file header) -----------------------------
+    FitLibs& lb = libs(ctx);
+    DevBuf<double> d_eta(m);
+    DevBuf<int> d_info(1);
+    int lwork = 0;
+    if (cusolverDnDsyevd_bufferSize(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p,
+                                    &lwork) != CUSOLVER_STATUS_SUCCESS)
+      throw Error(MB_E_CUDA, "cusolverDnDsyevd_bufferSize failed");
+    DevBuf<double> d_work((size_t)lwork);
+    if (cusolverDnDsyevd(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p, d_work.p,
+                         lwork, d_info.p) != CUSOLVER_STATUS_SUCCESS)
+      throw Error(MB_E_CUDA, "cusolverDnDsyevd failed");
+    ctx->launches++;
+    int info = 0;
+    std::vector<double> eta(m);
+    MB_CUDA(cudaMemcpyAsync(&info, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(eta.data(), d_eta.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (info != 0) throw Error(MB_E_NUMERIC, "symmetric eigensolver did not converge (info=" + std::to_string(info) + ")");
+    if (!(eta[0] > 0)) throw Error(MB_E_NUMERIC, "Q2'KQ2 is not positive definite (smallest eigenvalue <= 0)");
+    // D = c(0,0,0, 1/eta) in R's decreasing-eigenvalue order; eta from syevd is ascending
+    std::vector<double> D(np, 0.0);
+    for (int k = 0; k < m; ++k) D[3 + k] = 1.0 / eta[m - 1 - k];
+    eta_desc.assign(eta.rbegin(), eta.rend());
+    const std::vector<double> grid = gcv::lambda_grid(D);
+    DevBuf<double> d_z(m), d_u(m), d_g(m), d_beta(m);
+    for (int r = 0; r < L; ++r) {
+      d_z.upload(z[r], st);
+      k_gemv_t<<<(m + 7) / 8, 256, 0, st>>>(M, m, m, m, d_z.p, d_u.p);   // u = V' z (ascending order)
+      ctx->launches++;
+      std::vector<double> u_asc(m);
+      MB_CUDA(cudaMemcpyAsync(u_asc.data(), d_u.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+      MB_CUDA(cudaStreamSynchronize(st));
+      std::vector<double> u(np, 0.0);
+      for (int k = 0; k < m; ++k) u[3 + k] = u_asc[m - 1 - k];
+      lam[r] = gcv::search(D, u, grid, n, pure_ss[r], &gcvv[r]);
+      edf[r] = gcv::tr_a(lam[r], D);
+      std::vector<double> gvec(m);
+      for (int k = 0; k < m; ++k) gvec[k] = u_asc[k] / (eta[k] + lam[r]);
+      d_g.upload(gvec, st);
+      gemv_n(ctx, M, m, m, m, d_g.p, d_beta.p, d_part.p, st);              // beta = V diag(1/(eta+lambda)) u
+      MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_beta.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+      MB_CUDA(cudaStreamSynchronize(st));
+      u_full[r] = u;
+    }
+  } else {
+    // ---- fixed lambda: (M + lambda I) beta = z by tensor-core Cholesky ------------------------------
+    k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(M, m, m, lambda);
+    ctx->launches++;
+    cholesky_lower(ctx, M, m, m, st);
+    DevBuf<double> d_B((size_t)m * L);
+    for (int r = 0; r < L; ++r)
+      MB_CUDA(cudaMemcpyAsync(d_B.p + (size_t)r * m, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    k_chol_solve<<<1, 1024, 0, st>>>(M, m, m, d_B.p, m, L);
+    ctx->launches++;
+    for (int r = 0; r < L; ++r)
+      MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p + (size_t)r * m, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    MB_CUDA(cudaGetLastError());
+  }
+
+  // ---- Krig.coef: c = sqrt(w) Q (0; beta), d = qr.coef(sqrt(w) (yM - K c)) -----------------------------
+  std::vector<std::unique_ptr<mb_spline>> res(L);
+  for (int r = 0; r < L; ++r) {
+    std::vector<double> cfull(np, 0.0);
+    std::copy(beta[r].begin(), beta[r].end(), cfull.begin() + 3);
+    qr.qy(cfull);
+    for (int k = 0; k < np; ++k) cfull[k] *= w2[k];
+    auto s = std::make_unique<mb_spline>();
+    s->np = np;
+    s->kx = kx; s->ky = ky; s->sx = sx; s->sy = sy;
+    s->c = cfull;
+    s->center[0] = cmin[0]; s->center[1] = cmin[1];
+    s->scale[0] = scale[0]; s->scale[1] = scale[1];
+    s->d[0] = s->d[1] = s->d[2] = 0.0;
+    s->lambda = lam[r]; s->eff_df = edf[r]; s->gcv = gcvv[r];
+    if (lambda < 0) { s->eta = eta_desc; s->u = u_full[r]; }
+    // K c through the evaluation kernel with d = 0 (K was overwritten by the projection)
+    s->ctx = ctx;
+    s->d_sx.upload(s->sx, st); s->d_sy.upload(s->sy, st); s->d_c.upload(s->c, st);
+    DevBuf<double> d_kx, d_ky, d_kc(np);
+    d_kx.upload(kx, st); d_ky.upload(ky, st);
+    tps_predict_points_dev(ctx, s.get(), d_kx.p, d_ky.p, np, d_kc.p, st);
+    std::vector<double> Kc(np);
+    MB_CUDA(cudaMemcpyAsync(Kc.data(), d_kc.p, sizeof(double) * np, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    std::vector<double> rhs(np);
+    for (int k = 0; k < np; ++k) rhs[k] = w2[k] * (yM[r][k] - Kc[k]);
+    qr.coef(rhs, s->d);
+    spline_finalize(ctx, s.get());
+    res[r] = std::move(s);
+  }
+  for (int r = 0; r < L; ++r) out[r] = res[r].release();
+}
+
+}  // namespace mb

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """One Engine (context on cuda:0) per test session; fails loudly when the CUDA library or GPU is absent."""
+    import machisplin_b200 as mb
+    eng = mb.Engine(0)
+    yield eng
+    eng.close()

@@ -1,0 +1,139 @@
+"""GPU parity: TPS fit + evaluation through the C ABI vs the float64 oracle."""
+import numpy as np
+import pytest
+
+from machisplin_b200 import synth
+from oracle import tps as otps
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5   # north_star: <= 1e-5 relative on predicted cell values (relative to max |ref| over the raster)
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def _case(nrow, ncol, n, seed, lam=None):
+    geom = synth.make_geom(nrow, ncol)
+    xy, _, _ = synth.make_knots(geom, n, seed)
+    y = synth.residual_field(xy, seed)
+    fit = otps.tps_fit(xy, y, lam=lam)
+    return geom, xy, y, fit
+
+
+@pytest.mark.parametrize("method", ["direct", "fast"])
+@pytest.mark.parametrize("shape", [(256, 256), (200, 333), (97, 64)])
+def test_eval_from_oracle_coefficients(engine, method, shape):
+    geom, xy, y, fit = _case(shape[0], shape[1], 300, 5)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    got = engine.tps_eval(sp, geom, method=method)
+    ref = otps.tps_interpolate(fit, geom.as_tuple())
+    assert relerr(got, ref) < (1e-11 if method == "direct" else 1e-6)
+
+
+@pytest.mark.parametrize("p", [8, 10, 12, 14, 16])
+def test_fast_eval_orders(engine, p):
+    geom, xy, y, fit = _case(512, 512, 1000, 11)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    engine.set_fast_eval_params(cheb_p=p)
+    try:
+        got = engine.tps_eval(sp, geom, method="fast")
+    finally:
+        engine.set_fast_eval_params()
+    ref = otps.tps_interpolate(fit, geom.as_tuple())
+    bound = {8: 3e-6, 10: 2e-7, 12: 1e-8, 14: 1e-9, 16: 1e-9}[p]
+    assert relerr(got, ref) < bound
+
+
+def test_fast_eval_near_interpolating(engine):
+    """lambda -> 0: sum|c| / max|f| ~ 1e7; the automatic order selection must still hold 1e-5."""
+    geom, xy, y, fit = _case(512, 512, 1000, 11, lam=1e-8)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    got = engine.tps_eval(sp, geom, method="fast")
+    ref = otps.tps_interpolate(fit, geom.as_tuple())
+    assert relerr(got, ref) < 1e-6
+
+
+def test_window_eval_matches_full(engine):
+    geom, xy, y, fit = _case(300, 280, 200, 3)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    win = (37, 251, 19, 200)
+    ref = otps.tps_interpolate(fit, geom.as_tuple(), *win)
+    for method in ("direct", "fast"):
+        got = engine.tps_eval(sp, geom, window=win, method=method)
+        assert got.shape == ref.shape
+        assert relerr(got, ref) < 1e-6
+
+
+def test_r_zero_cells_are_finite(engine):
+    """knots sit on cell centres (V73:145): d2 = 0 hits the 1e-20 clamp of radfun."""
+    geom, xy, y, fit = _case(64, 64, 60, 2)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    for method in ("direct", "fast"):
+        got = engine.tps_eval(sp, geom, method=method)
+        assert np.isfinite(got).all()
+
+
+@pytest.mark.parametrize("n", [60, 500, 1500])
+def test_fit_gcv_matches_oracle(engine, n):
+    geom = synth.make_geom(1024, 1024)
+    xy, _, _ = synth.make_knots(geom, n, 21 + n)
+    y = synth.residual_field(xy, 21 + n)
+    ref = otps.tps_fit(xy, y)
+    sp = engine.tps_fit(xy, y)
+    assert abs(sp.lam - ref.lam) <= 1e-6 * ref.lam
+    assert abs(sp.eff_df - ref.eff_df) <= 1e-6 * ref.eff_df
+    np.testing.assert_allclose(sp.d, ref.d, rtol=1e-7, atol=1e-9 * np.abs(ref.d).max())
+    assert np.max(np.abs(sp.c - ref.c)) <= 1e-7 * np.max(np.abs(ref.c))
+    eta, u = sp.decomposition()
+    np.testing.assert_allclose(eta, ref.eta, rtol=1e-8)
+    # predictions at the knots: f(x_i) = y_i - lambda c_i
+    f = engine.tps_predict_points(sp, xy)
+    assert np.max(np.abs(f - (y - sp.lam * sp.c))) < 1e-9 * max(1.0, np.abs(y).max())
+
+
+@pytest.mark.parametrize("lam", [1e-2, 1e-5])
+def test_fit_fixed_lambda_cholesky(engine, lam):
+    geom = synth.make_geom(1024, 1024)
+    xy, _, _ = synth.make_knots(geom, 700, 77)
+    y = synth.residual_field(xy, 77)
+    ref = otps.tps_fit(xy, y, lam=lam)
+    sp = engine.tps_fit(xy, y, lam=lam)
+    assert np.max(np.abs(sp.c - ref.c)) <= 1e-7 * np.max(np.abs(ref.c))
+    np.testing.assert_allclose(sp.d, ref.d, rtol=1e-7, atol=1e-9 * np.abs(ref.d).max())
+
+
+def test_fit_replicates_pooled(engine):
+    geom = synth.make_geom(256, 256)
+    xy, _, _ = synth.make_knots(geom, 120, 9)
+    y = synth.residual_field(xy, 9)
+    xy2 = np.vstack([xy, xy[:30]])
+    y2 = np.concatenate([y, y[:30] + 0.05])
+    ref = otps.tps_fit(xy2, y2)
+    sp = engine.tps_fit(xy2, y2)
+    assert sp.np == ref.knots_xy.shape[0] == 120
+    assert abs(sp.lam - ref.lam) <= 1e-6 * ref.lam
+    # knot order differs only by a permutation: compare through predictions
+    pts = xy[:50] + 1e-3
+    assert np.max(np.abs(engine.tps_predict_points(sp, pts) - otps.tps_predict_points(ref, pts))) < 1e-8
+
+
+def test_fit_multi_response_shares_decomposition(engine):
+    geom = synth.make_geom(512, 512)
+    xy, _, _ = synth.make_knots(geom, 400, 13)
+    Y = synth.residual_field(xy, 13, L=4)
+    sps = engine.tps_fit(xy, Y)
+    for k, sp in enumerate(sps):
+        ref = otps.tps_fit(xy, Y[:, k])
+        assert abs(sp.lam - ref.lam) <= 1e-6 * ref.lam
+        assert np.max(np.abs(sp.c - ref.c)) <= 1e-7 * np.max(np.abs(ref.c))
+
+
+def test_errors_are_reported_not_thrown(engine):
+    import machisplin_b200._lib as L
+    xy = np.zeros((10, 2))
+    with pytest.raises(L.MbError):
+        engine.tps_fit(xy, np.zeros(10))          # zero range
+    with pytest.raises(L.MbError):
+        engine.tps_fit(np.column_stack([np.arange(10.0), np.arange(10.0)]), np.zeros(10))   # collinear
