@@ -1,9 +1,372 @@
-// placeholder until the tiling kernels land (next commit)
+// mltps part 3 / part 4 on the device (V73:649-895) and machisplin.tiles.merge (V73:1392-1548):
+//   tiles_tps    ceil(n/1500)-px tiling, per-tile knot selection + Tps fit + evaluation on the keep
+//                window, then the merge below.
+//   tiles_merge  K7: NA-ignoring mean mosaic of the tiles, linear cross-fade on every seam strip
+//                (strip = bounding box of the cells where both neighbours are non-NA, fade between the
+//                first and last cell centre of that box), mean of all strip blends covering a cell, strips
+//                take priority over the tile mean.  One pass over the output raster: each cell reads the
+//                <= 4 tiles that cover it; no full-extent per-tile rasters are ever materialised
+//                (the reference extends every tile to the full extent, V73:729).
+//   gram         K8: G = R'R of the cross-validation residual matrix (V73:329-331 objective).
+//   gather_cells part 5 point extraction (V73:910).
 #include "common.cuh"
 #include "internal.h"
+
+#include <algorithm>
+#include <cmath>
+
 namespace mb {
-void tiles_tps(mb_ctx*, const mb_grid&, const double*, const double*, int, int, double, double, int, double, int, double*, cudaStream_t) { throw Error(MB_E_UNSUPPORTED, "tiles: not built yet"); }
-void tiles_merge(mb_ctx*, const mb_grid&, int, int, const mb_window*, const double* const*, double*, cudaStream_t) { throw Error(MB_E_UNSUPPORTED, "tiles: not built yet"); }
-void gram(mb_ctx*, const double*, int, int, double*, cudaStream_t) { throw Error(MB_E_UNSUPPORTED, "gram: not built yet"); }
-void gather_cells(mb_ctx*, const double*, int64_t, const int32_t*, const int32_t*, int, double*) { throw Error(MB_E_UNSUPPORTED, "gather: not built yet"); }
+
+static int cround(double x) { return x >= 0 ? (int)std::floor(x + 0.5) : -(int)std::floor(-x + 0.5); }
+
+// terra::crop(rast, ext) as an index window: snap = "near" on the cell edges, clipped to the raster
+static mb_window crop_window(const mb_grid& g, double exmin, double exmax, double eymin, double eymax) {
+  const double rx = (g.xmax - g.xmin) / g.ncol, ry = (g.ymax - g.ymin) / g.nrow;
+  int c0 = cround((exmin - g.xmin) / rx), c1 = cround((exmax - g.xmin) / rx);
+  int b0 = cround((eymin - g.ymin) / ry), b1 = cround((eymax - g.ymin) / ry);
+  c0 = std::max(0, std::min(g.ncol, c0)); c1 = std::max(0, std::min(g.ncol, c1));
+  b0 = std::max(0, std::min(g.nrow, b0)); b1 = std::max(0, std::min(g.nrow, b1));
+  return mb_window{g.nrow - b1, g.nrow - b0, c0, c1};
 }
+
+// ---------------------------------------------------------------------------------------------
+// K7 tile blend
+// ---------------------------------------------------------------------------------------------
+struct TileDesc {
+  const double* p;
+  int r0, r1, c0, c1;
+};
+struct SeamDesc {
+  int a, b;        // tile indices: a = west / south tile ("tile 1" of the reference), b = east / north
+  int axis;        // 0 = vertical seam (fade in x), 1 = horizontal seam (fade in y)
+  int r0, r1, c0, c1;   // window intersection
+};
+
+__global__ void __launch_bounds__(256) k_seam_bbox(const TileDesc* __restrict__ tiles,
+                                                   const SeamDesc* __restrict__ seams, int* __restrict__ bbox) {
+  const SeamDesc s = seams[blockIdx.y];
+  const int wc = s.c1 - s.c0, wr = s.r1 - s.r0;
+  const int64_t n = (int64_t)wc * wr;
+  int rmin = INT_MAX, rmax = INT_MIN, cmin = INT_MAX, cmax = INT_MIN;
+  const TileDesc ta = tiles[s.a], tb = tiles[s.b];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = s.r0 + (int)(i / wc), c = s.c0 + (int)(i % wc);
+    const double va = ta.p[(int64_t)(r - ta.r0) * (ta.c1 - ta.c0) + (c - ta.c0)];
+    const double vb = tb.p[(int64_t)(r - tb.r0) * (tb.c1 - tb.c0) + (c - tb.c0)];
+    if (va == va && vb == vb) {
+      rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+    }
+  }
+  rmin = __reduce_min_sync(0xffffffffu, rmin); rmax = __reduce_max_sync(0xffffffffu, rmax);
+  cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
+  if ((threadIdx.x & 31) == 0 && rmin <= rmax) {
+    int* bb = bbox + 4 * blockIdx.y;
+    atomicMin(bb + 0, rmin); atomicMax(bb + 1, rmax); atomicMin(bb + 2, cmin); atomicMax(bb + 3, cmax);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tile_blend(
+    const TileDesc* __restrict__ tiles, int nC, int nR, const int2* __restrict__ colcand,
+    const int2* __restrict__ rowcand, const int* __restrict__ vbbox, const int* __restrict__ hbbox,
+    double xmin, double ymax, double rx, double ry, int nrow, int ncol, double* __restrict__ out) {
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int row = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (col >= ncol || row >= nrow) return;
+  const int2 hc = colcand[col];     // tile columns h in [hc.x, hc.y]
+  const int2 jc = rowcand[row];     // tile rows    j in [jc.x, jc.y]  (j counts from the south)
+  double v[3][3];
+  bool ok[3][3];
+  double tsum = 0.0;
+  int tcnt = 0;
+#pragma unroll
+  for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      ok[dj][dh] = false;
+      v[dj][dh] = 0.0;
+      const int j = jc.x + dj, h = hc.x + dh;
+      if (j <= jc.y && h <= hc.y) {
+        const TileDesc t = tiles[j * nC + h];
+        if (row >= t.r0 && row < t.r1 && col >= t.c0 && col < t.c1) {
+          const double x = t.p[(int64_t)(row - t.r0) * (t.c1 - t.c0) + (col - t.c0)];
+          if (x == x) { ok[dj][dh] = true; v[dj][dh] = x; tsum += x; ++tcnt; }
+        }
+      }
+    }
+  double ssum = 0.0;
+  int scnt = 0;
+  // vertical seams (tile (j,h) | (j,h+1)), V73:764-806
+#pragma unroll
+  for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh) {
+      const int j = jc.x + dj, h = hc.x + dh;
+      if (j <= jc.y && h + 1 <= hc.y && ok[dj][dh] && ok[dj][dh + 1]) {
+        const int* bb = vbbox + 4 * (j * (nC - 1) + h);
+        if (row >= bb[0] && row <= bb[1] && col >= bb[2] && col <= bb[3]) {
+          const double x = xmin + (col + 0.5) * rx;
+          const double x0 = xmin + (bb[2] + 0.5) * rx, x1 = xmin + (bb[3] + 0.5) * rx;
+          const double t = (x - x0) / (x1 - x0);
+          const double f = v[dj][dh + 1] * t + v[dj][dh] * (1.0 - t);
+          if (f == f) { ssum += f; ++scnt; }
+        }
+      }
+    }
+  // horizontal seams (tile (j,h) south | (j+1,h) north), V73:815-877
+#pragma unroll
+  for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int j = jc.x + dj, h = hc.x + dh;
+      if (j + 1 <= jc.y && h <= hc.y && ok[dj][dh] && ok[dj + 1][dh]) {
+        const int* bb = hbbox + 4 * (j * nC + h);
+        if (row >= bb[0] && row <= bb[1] && col >= bb[2] && col <= bb[3]) {
+          const double y = ymax - (row + 0.5) * ry;
+          const double y0 = ymax - (bb[1] + 0.5) * ry, y1 = ymax - (bb[0] + 0.5) * ry;   // min / max latitude
+          const double t = (y - y0) / (y1 - y0);
+          const double f = v[dj + 1][dh] * t + v[dj][dh] * (1.0 - t);
+          if (f == f) { ssum += f; ++scnt; }
+        }
+      }
+    }
+  double r;
+  if (scnt > 0) r = ssum / scnt;
+  else if (tcnt > 0) r = tsum / tcnt;
+  else r = __longlong_as_double(0x7ff8000000000000LL);
+  out[(int64_t)row * ncol + col] = r;
+}
+
+void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window* wins,
+                 const double* const* tiles_dev, double* out_dev, cudaStream_t st) {
+  const int nt = nC * nR;
+  std::vector<TileDesc> td(nt);
+  for (int t = 0; t < nt; ++t) {
+    check_window(&g, &wins[t]);
+    td[t] = TileDesc{tiles_dev[t], wins[t].r0, wins[t].r1, wins[t].c0, wins[t].c1};
+  }
+  // candidate tile columns / rows of every raster column / row (windows are monotone along the lattice)
+  std::vector<int2> colcand(g.ncol, make_int2(0, -1)), rowcand(g.nrow, make_int2(0, -1));
+  for (int h = 0; h < nC; ++h) {
+    int lo = g.ncol, hi = 0;
+    for (int j = 0; j < nR; ++j) { lo = std::min(lo, wins[j * nC + h].c0); hi = std::max(hi, wins[j * nC + h].c1); }
+    for (int c = lo; c < hi; ++c) {
+      if (colcand[c].y < colcand[c].x) colcand[c] = make_int2(h, h);
+      else colcand[c].y = h;
+    }
+  }
+  for (int j = 0; j < nR; ++j) {
+    int lo = g.nrow, hi = 0;
+    for (int h = 0; h < nC; ++h) { lo = std::min(lo, wins[j * nC + h].r0); hi = std::max(hi, wins[j * nC + h].r1); }
+    for (int r = lo; r < hi; ++r) {
+      if (rowcand[r].y < rowcand[r].x) rowcand[r] = make_int2(j, j);
+      else rowcand[r].y = j;
+    }
+  }
+  for (auto& c : colcand) MB_REQUIRE(c.y - c.x <= 2, "more than three tile columns overlap on one raster column");
+  for (auto& r : rowcand) MB_REQUIRE(r.y - r.x <= 2, "more than three tile rows overlap on one raster row");
+  // seams
+  std::vector<SeamDesc> seams;
+  auto add_seam = [&](int a, int b, int axis) {
+    SeamDesc s{a, b, axis, std::max(wins[a].r0, wins[b].r0), std::min(wins[a].r1, wins[b].r1),
+               std::max(wins[a].c0, wins[b].c0), std::min(wins[a].c1, wins[b].c1)};
+    if (s.r1 <= s.r0 || s.c1 <= s.c0) { s.r0 = s.r1 = s.c0 = s.c1 = 0; }
+    seams.push_back(s);
+  };
+  const int nv = nR * (nC - 1), nh = (nR - 1) * nC;
+  for (int j = 0; j < nR; ++j)
+    for (int h = 0; h + 1 < nC; ++h) add_seam(j * nC + h, j * nC + h + 1, 0);
+  for (int j = 0; j + 1 < nR; ++j)
+    for (int h = 0; h < nC; ++h) add_seam(j * nC + h, (j + 1) * nC + h, 1);
+  DevBuf<TileDesc> d_tiles;
+  DevBuf<SeamDesc> d_seams;
+  DevBuf<int2> d_col, d_row;
+  DevBuf<int> d_bbox((size_t)4 * std::max<size_t>(1, seams.size()));
+  d_tiles.upload(td, st);
+  d_col.upload(colcand, st);
+  d_row.upload(rowcand, st);
+  std::vector<int> bbox_init(4 * std::max<size_t>(1, seams.size()));
+  for (size_t s = 0; s < bbox_init.size() / 4; ++s) {
+    bbox_init[4 * s + 0] = INT_MAX; bbox_init[4 * s + 1] = INT_MIN;
+    bbox_init[4 * s + 2] = INT_MAX; bbox_init[4 * s + 3] = INT_MIN;
+  }
+  d_bbox.upload(bbox_init, st);
+  if (!seams.empty()) {
+    d_seams.upload(seams, st);
+    k_seam_bbox<<<dim3(64, (unsigned)seams.size()), 256, 0, st>>>(d_tiles.p, d_seams.p, d_bbox.p);
+    ctx->launches++;
+  }
+  const double rx = (g.xmax - g.xmin) / g.ncol, ry = (g.ymax - g.ymin) / g.nrow;
+  dim3 grid((g.ncol + 31) / 32, (g.nrow + 7) / 8);
+  k_tile_blend<<<grid, 256, 0, st>>>(d_tiles.p, nC, nR, d_col.p, d_row.p, d_bbox.p, d_bbox.p + 4 * (size_t)nv,
+                                     g.xmin, g.ymax, rx, ry, g.nrow, g.ncol, out_dev);
+  ctx->launches++;
+  (void)nh;
+  MB_CUDA(cudaGetLastError());
+  MB_CUDA(cudaStreamSynchronize(st));   // descriptor buffers are stream-ordered temporaries
+}
+
+// ---------------------------------------------------------------------------------------------
+// mltps part 3: tiling + per-tile fit + evaluation
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fill(double* p, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const double* resid, int n, int tile_px,
+               double fit_halo, double keep_halo, int min_pts, double lambda, int method, double* out_dev,
+               cudaStream_t st) {
+  const int nRx = (g.nrow + tile_px - 1) / tile_px;       // V73:656-657
+  const int nCx = (g.ncol + tile_px - 1) / tile_px;       // V73:660-661
+  const mb_window full{0, g.nrow, 0, g.ncol};
+  auto eval = [&](const mb_spline* s, const mb_window& w, double* dst) {
+    if (method == MB_EVAL_DIRECT) tps_eval_direct(ctx, s, g, w, dst, w.c1 - w.c0, st);
+    else tps_eval_fast(ctx, s, g, w, dst, w.c1 - w.c0, st);
+  };
+  if (nRx * nCx == 1) {                                    // V73:748-753
+    mb_spline* sp = nullptr;
+    tps_fit(ctx, knots_xy, resid, n, 1, lambda, &sp);
+    std::unique_ptr<mb_spline> hold(sp);
+    eval(sp, full, out_dev);
+    MB_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  const double longDist = (g.xmax - g.xmin) / nCx, latDist = (g.ymax - g.ymin) / nRx;
+  const double rx = (g.xmax - g.xmin) / g.ncol, ry = (g.ymax - g.ymin) / g.nrow;
+  // cell of every knot (terra::extract: the containing cell)
+  std::vector<int> krow(n), kcol(n);
+  for (int i = 0; i < n; ++i) {
+    const double x = knots_xy[i], y = knots_xy[(size_t)n + i];
+    int c = (int)std::floor((x - g.xmin) / rx), r = (int)std::floor((g.ymax - y) / ry);
+    if (x == g.xmax) c = g.ncol - 1;
+    if (y == g.ymin) r = g.nrow - 1;
+    if (x < g.xmin || x > g.xmax || y < g.ymin || y > g.ymax) c = r = -1;
+    kcol[i] = c; krow[i] = r;
+  }
+  const int nt = nRx * nCx;
+  std::vector<mb_window> keep(nt);
+  std::vector<DevBuf<double>> bufs(nt);
+  std::vector<const double*> ptrs(nt);
+  std::vector<double> txy, ty;
+  for (int j = 1; j <= nRx; ++j)
+    for (int h = 1; h <= nCx; ++h) {
+      const int t = (j - 1) * nCx + (h - 1);
+      const mb_window fw = crop_window(g, g.xmin + ((longDist * (h - 1)) - (longDist * fit_halo)),
+                                       g.xmin + ((longDist * h) + (longDist * fit_halo)),
+                                       g.ymin + ((latDist * (j - 1))) - (latDist * fit_halo),
+                                       g.ymin + ((latDist * j)) + (latDist * fit_halo));      // V73:673
+      mb_window kw = crop_window(g, g.xmin + ((longDist * (h - 1)) - (longDist * keep_halo)),
+                                 g.xmin + ((longDist * h) + (longDist * keep_halo)),
+                                 g.ymin + ((latDist * (j - 1))) - (latDist * keep_halo),
+                                 g.ymin + ((latDist * j)) + (latDist * keep_halo));           // V73:680
+      kw.r0 = std::max(kw.r0, fw.r0); kw.r1 = std::min(kw.r1, fw.r1);
+      kw.c0 = std::max(kw.c0, fw.c0); kw.c1 = std::min(kw.c1, fw.c1);
+      MB_REQUIRE(kw.r1 > kw.r0 && kw.c1 > kw.c0, "empty tile window");
+      keep[t] = kw;
+      txy.clear(); ty.clear();
+      std::vector<double> tx, tyy;
+      for (int i = 0; i < n; ++i)
+        if (krow[i] >= fw.r0 && krow[i] < fw.r1 && kcol[i] >= fw.c0 && kcol[i] < fw.c1) {   // V73:699-706
+          tx.push_back(knots_xy[i]); tyy.push_back(knots_xy[(size_t)n + i]); ty.push_back(resid[i]);
+        }
+      const int m = (int)ty.size();
+      const size_t cells = (size_t)(kw.r1 - kw.r0) * (kw.c1 - kw.c0);
+      bufs[t].alloc(cells);
+      ptrs[t] = bufs[t].p;
+      if (m < min_pts) {                                                                     // V73:710-721
+        k_fill<<<256, 256, 0, st>>>(bufs[t].p, (int64_t)cells, 0.0);
+        ctx->launches++;
+        continue;
+      }
+      txy.resize((size_t)2 * m);
+      std::copy(tx.begin(), tx.end(), txy.begin());
+      std::copy(tyy.begin(), tyy.end(), txy.begin() + m);
+      mb_spline* sp = nullptr;
+      tps_fit(ctx, txy.data(), ty.data(), m, 1, lambda, &sp);                                 // V73:722
+      std::unique_ptr<mb_spline> hold(sp);
+      eval(sp, kw, bufs[t].p);                                                               // V73:726-728
+      MB_CUDA(cudaStreamSynchronize(st));
+    }
+  tiles_merge(ctx, g, nCx, nRx, keep.data(), ptrs.data(), out_dev, st);                       // V73:739-895
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8 gram: G = R'R, R n x K column-major, K <= 8
+// ---------------------------------------------------------------------------------------------
+constexpr int kGramBlocks = 296;
+
+__global__ void __launch_bounds__(256) k_gram_partial(const double* __restrict__ R, int n, int K,
+                                                      double* __restrict__ part) {
+  double acc[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    double x[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) x[a] = a < K ? R[(size_t)a * n + r] : 0.0;
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) { acc[q] = fma(x[a], x[b], acc[q]); ++q; }
+  }
+  __shared__ double s[8][36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    double v = 0.0;
+    for (int wq = 0; wq < 8; ++wq) v += s[wq][threadIdx.x];
+    part[(size_t)blockIdx.x * 36 + threadIdx.x] = v;
+  }
+}
+__global__ void k_gram_final(const double* __restrict__ part, int nblocks, int K, double* __restrict__ G) {
+  const int t = threadIdx.x;
+  if (t >= 36) return;
+  double v = 0.0;
+  for (int b = 0; b < nblocks; ++b) v += part[(size_t)b * 36 + t];
+  int a = 0, q = t;
+  while (q > a) { q -= a + 1; ++a; }   // t = a(a+1)/2 + b
+  const int b = q;
+  if (a < K && b < K) { G[(size_t)b * K + a] = v; G[(size_t)a * K + b] = v; }
+}
+
+void gram(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, cudaStream_t st) {
+  DevBuf<double> part((size_t)kGramBlocks * 36);
+  const int blocks = std::min(kGramBlocks, (n + 255) / 256);
+  k_gram_partial<<<blocks, 256, 0, st>>>(R_dev, n, K, part.p);
+  k_gram_final<<<1, 64, 0, st>>>(part.p, blocks, K, G_dev);
+  ctx->launches += 2;
+  MB_CUDA(cudaGetLastError());
+  MB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------------------------------------
+// part 5: f.actual <- extract(final, points)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gather(const double* __restrict__ ras, int64_t stride, const int* __restrict__ row,
+                         const int* __restrict__ col, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ras[(int64_t)row[i] * stride + col[i]];
+}
+
+void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row, const int32_t* col,
+                  int n, double* out_host) {
+  if (n <= 0) return;
+  cudaStream_t st = ctx->stream;
+  DevBuf<int> dr(n), dc(n);
+  DevBuf<double> dout(n);
+  dr.upload(row, n, st);
+  dc.upload(col, n, st);
+  k_gather<<<(n + 255) / 256, 256, 0, st>>>(raster_dev, row_stride, dr.p, dc.p, n, dout.p);
+  ctx->launches++;
+  MB_CUDA(cudaGetLastError());
+  MB_CUDA(cudaMemcpyAsync(out_host, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace mb
