@@ -175,6 +175,13 @@ int mb_dev_free(mb_ctx* ctx, void* p);
 int mb_h2d(mb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int mb_d2h(mb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
+/* ---- per-kernel device timing (bench bookkeeping) ---------------------------------------- */
+/* When enabled, every kernel launch of this context is bracketed by CUDA events on the launching
+ * stream.  mb_timing_collect synchronises, sums the elapsed time per kernel name and resets the
+ * log; it returns the number of distinct names written (<= cap).  names[i] points to static strings. */
+int mb_timing_enable(mb_ctx* ctx, int on);
+int mb_timing_collect(mb_ctx* ctx, int cap, const char** names, double* total_ms, int64_t* launches);
+
 /* Tunables of the fast evaluator (0 = automatic). */
 int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows);
 

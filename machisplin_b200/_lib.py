@@ -91,6 +91,8 @@ SIGNATURES = {
     "mb_dev_free": (C.c_int, [VP, VP]),
     "mb_h2d": (C.c_int, [VP, VP, VP, C.c_size_t]),
     "mb_d2h": (C.c_int, [VP, VP, VP, C.c_size_t]),
+    "mb_timing_enable": (C.c_int, [VP, C.c_int]),
+    "mb_timing_collect": (C.c_int, [VP, C.c_int, C.POINTER(C.c_char_p), PD, C.POINTER(C.c_int64)]),
     "mb_set_fast_eval_params": (C.c_int, [VP, C.c_int, C.c_int, C.c_int]),
 }
 

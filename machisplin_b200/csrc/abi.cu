@@ -52,6 +52,8 @@ void mb_shutdown(mb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   fit_release(ctx);
+  for (const mb_timed_launch& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -65,6 +67,39 @@ int mb_sync(mb_ctx* ctx) {
 }
 
 int64_t mb_launch_count(const mb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mb_timing_enable(mb_ctx* ctx, int on) {
+  return guarded([&] {
+    MB_REQUIRE(ctx, "ctx is NULL");
+    ctx->timing = on != 0;
+  });
+}
+
+int mb_timing_collect(mb_ctx* ctx, int cap, const char** names, double* total_ms, int64_t* launches) {
+  int n = 0;
+  const int rc = guarded([&] {
+    MB_REQUIRE(ctx && names && total_ms && launches && cap > 0, "bad argument");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    MB_CUDA(cudaDeviceSynchronize());
+    for (const mb_timed_launch& t : ctx->timed) {
+      float ms = 0.f;
+      MB_CUDA(cudaEventElapsedTime(&ms, t.start, t.stop));
+      int k = 0;
+      for (; k < n; ++k)
+        if (std::strcmp(names[k], t.name) == 0) break;
+      if (k == n) {
+        if (n == cap) continue;
+        names[n] = t.name; total_ms[n] = 0; launches[n] = 0; ++n;
+      }
+      total_ms[k] += ms;
+      launches[k] += 1;
+      ctx->event_pool.push_back(t.start);
+      ctx->event_pool.push_back(t.stop);
+    }
+    ctx->timed.clear();
+  });
+  return rc == MB_OK ? n : rc;
+}
 
 int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows) {
   return guarded([&] {

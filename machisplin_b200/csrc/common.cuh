@@ -86,8 +86,16 @@ struct DevBuf {
 }  // namespace mb
 
 // ---- handles ----------------------------------------------------------------------------
+struct mb_timed_launch {
+  const char* name;
+  cudaEvent_t start, stop;
+};
+
 struct mb_ctx {
   int device = 0;
+  bool timing = false;
+  std::vector<mb_timed_launch> timed;
+  std::vector<cudaEvent_t> event_pool;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
@@ -142,6 +150,34 @@ inline void check_window(const mb_grid* g, const mb_window* w) {
   MB_REQUIRE(w->r0 >= 0 && w->c0 >= 0 && w->r1 <= g->nrow && w->c1 <= g->ncol && w->r1 > w->r0 && w->c1 > w->c0,
              "window is empty or outside the grid");
 }
+
+// Brackets a launch with events when timing is on:  { KernelTimer t(ctx, "k_name", stream); k<<<...>>>(...); }
+struct KernelTimer {
+  mb_ctx* ctx;
+  cudaStream_t st;
+  mb_timed_launch rec{};
+  bool on;
+  KernelTimer(mb_ctx* c, const char* name, cudaStream_t s) : ctx(c), st(s), on(c->timing) {
+    c->launches++;
+    if (!on) return;
+    rec.name = name;
+    rec.start = take();
+    rec.stop = take();
+    cudaEventRecord(rec.start, st);
+  }
+  ~KernelTimer() {
+    if (!on) return;
+    cudaEventRecord(rec.stop, st);
+    ctx->timed.push_back(rec);
+  }
+  cudaEvent_t take() {
+    if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+#define MB_LAUNCH(ctx, name, st) for (mb::KernelTimer _kt(ctx, name, st), *_once = &_kt; _once; _once = nullptr)
 
 // implemented in tps_eval.cu
 void spline_finalize(mb_ctx* ctx, mb_spline* s);   // uploads, computes sum|c| and fscale

@@ -610,7 +610,8 @@ static SmoothParams smooth_params(const mb_ensemble* e) {
 template <int PP>
 static void launch_svm(const mb_ensemble* e, const float* cov, int64_t plane, const EnsGeom& eg, const mb_window& w,
                        double* acc, int64_t ncell, cudaStream_t st) {
-  k_ens_svm<PP><<<(unsigned)((ncell + kSvmThreads - 1) / kSvmThreads), kSvmThreads, 0, st>>>(
+  mb_ctx* ctx = e->ctx;
+  MB_LAUNCH(ctx, "k_ens_svm", st) k_ens_svm<PP><<<(unsigned)((ncell + kSvmThreads - 1) / kSvmThreads), kSvmThreads, 0, st>>>(
       cov, e->C, plane, eg, w, e->svm_sv.p, e->svm_b.p, e->svm_alpha.p, e->svm_S, e->svm_xc.p, e->svm_xis.p,
       e->svm_sigma, e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], acc);
 }
@@ -630,11 +631,10 @@ void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, c
     acc.alloc((size_t)ncell);
     MB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * ncell, st));
     if (e->has[MB_R] || e->has[MB_B]) {
-      k_ens_trees<<<(unsigned)((ncell + kTreeThreads - 1) / kTreeThreads), kTreeThreads, 0, st>>>(
+      MB_LAUNCH(ctx, "k_ens_trees", st) k_ens_trees<<<(unsigned)((ncell + kTreeThreads - 1) / kTreeThreads), kTreeThreads, 0, st>>>(
           cov, C, plane, eg, w, e->rf.nodes.p, e->rf.root.p, e->has[MB_R] ? e->rf.ntrees : 0, e->w[MB_R],
           e->rf.offset, e->gbm.nodes.p, e->gbm.root.p, e->has[MB_B] ? e->gbm.ntrees : 0, e->w[MB_B], e->gb_initF,
           e->only_gbm ? 1 : 0, acc.p);
-      ctx->launches++;
     }
     if (e->has[MB_V]) {
       switch (e->P) {
@@ -644,7 +644,6 @@ void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, c
         MB_SVM_CASE(15) MB_SVM_CASE(16)
 #undef MB_SVM_CASE
       }
-      ctx->launches++;
     }
   }
   const double* tps = tps_surface;
@@ -654,8 +653,7 @@ void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, c
     tps = out;
   }
   dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
-  k_ens_final<<<grid, 256, 0, st>>>(cov, C, plane, eg, w, smooth_params(e), heavy ? acc.p : nullptr, tps, out);
-  ctx->launches++;
+  MB_LAUNCH(ctx, "k_ens_final", st) k_ens_final<<<grid, 256, 0, st>>>(cov, C, plane, eg, w, smooth_params(e), heavy ? acc.p : nullptr, tps, out);
   MB_CUDA(cudaGetLastError());
   if (heavy) MB_CUDA(cudaStreamSynchronize(st));   // acc is a stream-ordered temporary
 }
@@ -677,8 +675,7 @@ void ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X,
   pm.S = e->has[MB_V] ? e->svm_S : 0; pm.sv = e->svp_sv.p; pm.alpha = e->svp_alpha.p; pm.xc = e->svm_xc.p;
   pm.xis = e->svm_xis.p; pm.sigma = e->svm_sigma; pm.bias = e->svm_bias; pm.ys = e->svm_ys; pm.yc = e->svm_yc;
   pm.w_v = e->w[MB_V];
-  k_ens_points<<<(n + 127) / 128, 128, 0, st>>>(dX.p, n, pm, dO.p);
-  ctx->launches++;
+  MB_LAUNCH(ctx, "k_ens_points", st) k_ens_points<<<(n + 127) / 128, 128, 0, st>>>(dX.p, n, pm, dO.p);
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaMemcpyAsync(out_host, dO.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaStreamSynchronize(st));

@@ -192,14 +192,12 @@ void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window*
   d_bbox.upload(bbox_init, st);
   if (!seams.empty()) {
     d_seams.upload(seams, st);
-    k_seam_bbox<<<dim3(64, (unsigned)seams.size()), 256, 0, st>>>(d_tiles.p, d_seams.p, d_bbox.p);
-    ctx->launches++;
+    MB_LAUNCH(ctx, "k_seam_bbox", st) k_seam_bbox<<<dim3(64, (unsigned)seams.size()), 256, 0, st>>>(d_tiles.p, d_seams.p, d_bbox.p);
   }
   const double rx = (g.xmax - g.xmin) / g.ncol, ry = (g.ymax - g.ymin) / g.nrow;
   dim3 grid((g.ncol + 31) / 32, (g.nrow + 7) / 8);
-  k_tile_blend<<<grid, 256, 0, st>>>(d_tiles.p, nC, nR, d_col.p, d_row.p, d_bbox.p, d_bbox.p + 4 * (size_t)nv,
+  MB_LAUNCH(ctx, "k_tile_blend", st) k_tile_blend<<<grid, 256, 0, st>>>(d_tiles.p, nC, nR, d_col.p, d_row.p, d_bbox.p, d_bbox.p + 4 * (size_t)nv,
                                      g.xmin, g.ymax, rx, ry, g.nrow, g.ncol, out_dev);
-  ctx->launches++;
   (void)nh;
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaStreamSynchronize(st));   // descriptor buffers are stream-ordered temporaries
@@ -273,8 +271,7 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
       bufs[t].alloc(cells);
       ptrs[t] = bufs[t].p;
       if (m < min_pts) {                                                                     // V73:710-721
-        k_fill<<<256, 256, 0, st>>>(bufs[t].p, (int64_t)cells, 0.0);
-        ctx->launches++;
+        MB_LAUNCH(ctx, "k_fill", st) k_fill<<<256, 256, 0, st>>>(bufs[t].p, (int64_t)cells, 0.0);
         continue;
       }
       txy.resize((size_t)2 * m);
@@ -338,9 +335,8 @@ __global__ void k_gram_final(const double* __restrict__ part, int nblocks, int K
 void gram(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, cudaStream_t st) {
   DevBuf<double> part((size_t)kGramBlocks * 36);
   const int blocks = std::min(kGramBlocks, (n + 255) / 256);
-  k_gram_partial<<<blocks, 256, 0, st>>>(R_dev, n, K, part.p);
-  k_gram_final<<<1, 64, 0, st>>>(part.p, blocks, K, G_dev);
-  ctx->launches += 2;
+  MB_LAUNCH(ctx, "k_gram_partial", st) k_gram_partial<<<blocks, 256, 0, st>>>(R_dev, n, K, part.p);
+  MB_LAUNCH(ctx, "k_gram_final", st) k_gram_final<<<1, 64, 0, st>>>(part.p, blocks, K, G_dev);
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaStreamSynchronize(st));
 }
@@ -362,8 +358,7 @@ void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, con
   DevBuf<double> dout(n);
   dr.upload(row, n, st);
   dc.upload(col, n, st);
-  k_gather<<<(n + 255) / 256, 256, 0, st>>>(raster_dev, row_stride, dr.p, dc.p, n, dout.p);
-  ctx->launches++;
+  MB_LAUNCH(ctx, "k_gather", st) k_gather<<<(n + 255) / 256, 256, 0, st>>>(raster_dev, row_stride, dr.p, dc.p, n, dout.p);
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaMemcpyAsync(out_host, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaStreamSynchronize(st));

@@ -101,9 +101,8 @@ void tps_eval_direct(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb
                      int64_t stride, cudaStream_t st) {
   GridAffine a = make_affine(g, *s);
   dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
-  k_tps_eval_direct<<<grid, 256, 0, st>>>(s->d_sx.p, s->d_sy.p, s->d_c.p, s->np, s->d[0], s->d[1], s->d[2], a, w,
+  MB_LAUNCH(ctx, "k_tps_eval_direct", st) k_tps_eval_direct<<<grid, 256, 0, st>>>(s->d_sx.p, s->d_sy.p, s->d_c.p, s->np, s->d[0], s->d[1], s->d[2], a, w,
                                           out, stride);
-  ctx->launches++;
   MB_CUDA(cudaGetLastError());
 }
 
@@ -128,10 +127,9 @@ __global__ void __launch_bounds__(256) k_tps_points(
 void tps_predict_points_dev(mb_ctx* ctx, const mb_spline* s, const double* x_dev, const double* y_dev, int n,
                             double* out_dev, cudaStream_t st) {
   if (n <= 0) return;
-  k_tps_points<<<(n + 255) / 256, 256, 0, st>>>(s->d_sx.p, s->d_sy.p, s->d_c.p, s->np, s->d[0], s->d[1], s->d[2],
+  MB_LAUNCH(ctx, "k_tps_points", st) k_tps_points<<<(n + 255) / 256, 256, 0, st>>>(s->d_sx.p, s->d_sy.p, s->d_c.p, s->np, s->d[0], s->d[1], s->d[2],
                                                 s->center[0], s->center[1], s->scale[0], s->scale[1], x_dev, y_dev,
                                                 n, out_dev);
-  ctx->launches++;
   MB_CUDA(cudaGetLastError());
 }
 
@@ -479,12 +477,10 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
   for (size_t li = 0; li < levels.size(); ++li) {
     const LevelInfo& lv = levels[li];
     dim3 grid(lv.nI * lv.nJ, lv.nsplit);
-    k_far_p2l<P><<<grid, threads, 0, st>>>(lat, lv, tabs->d_tab.p, d_start.p, d_knots.p, ctx->logtab.p, d_part.p);
-    ctx->launches++;
+    MB_LAUNCH(ctx, "k_far_p2l", st) k_far_p2l<P><<<grid, threads, 0, st>>>(lat, lv, tabs->d_tab.p, d_start.p, d_knots.p, ctx->logtab.p, d_part.p);
     const LevelInfo& par = li ? levels[li - 1] : lv;
-    k_far_transform<P><<<lv.nI * lv.nJ, threads, 0, st>>>(lat, lv, par, li ? 1 : 0, tabs->d_tab.p, d_part.p,
+    MB_LAUNCH(ctx, "k_far_transform", st) k_far_transform<P><<<lv.nI * lv.nJ, threads, 0, st>>>(lat, lv, par, li ? 1 : 0, tabs->d_tab.p, d_part.p,
                                                            d_coef.p, s->d[0], s->d[1], s->d[2]);
-    ctx->launches++;
   }
   MB_CUDA(cudaGetLastError());
   const LevelInfo& leaf = levels.back();
@@ -496,9 +492,8 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
     attr_set = true;
   }
   dim3 grid(lat.nbx, lat.nby);
-  k_leaf<P><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef.p, d_start.p, d_knots.p, ctx->logtab.p, out,
+  MB_LAUNCH(ctx, "k_leaf", st) k_leaf<P><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef.p, d_start.p, d_knots.p, ctx->logtab.p, out,
                                               stride);
-  ctx->launches++;
   MB_CUDA(cudaGetLastError());
   // the plan buffers are stream-ordered temporaries: wait before they are released
   MB_CUDA(cudaStreamSynchronize(st));

@@ -319,14 +319,12 @@ static void cholesky_lower(mb_ctx* ctx, double* A, int ld, int m, cudaStream_t s
   for (int k = 0; k < m; k += kNB) {
     const int kb = std::min(kNB, m - k);
     double* Akk = A + (size_t)k * ld + k;
-    k_potrf_diag<<<1, kNB, 0, st>>>(Akk, ld, kb, k, d_info.p);
-    ctx->launches++;
+    MB_LAUNCH(ctx, "k_potrf_diag", st) k_potrf_diag<<<1, kNB, 0, st>>>(Akk, ld, kb, k, d_info.p);
     const int rest = m - k - kb;
     if (rest > 0) {
-      k_trsm_panel<<<(rest + 127) / 128, 128, 0, st>>>(Akk, Akk + kb, ld, kb, rest);
+      MB_LAUNCH(ctx, "k_trsm_panel", st) k_trsm_panel<<<(rest + 127) / 128, 128, 0, st>>>(Akk, Akk + kb, ld, kb, rest);
       const int nt = (rest + kNB - 1) / kNB;
-      k_syrk_dmma<<<dim3(nt, nt), 256, kSyrkSmem, st>>>(Akk + kb, A + (size_t)(k + kb) * ld + (k + kb), ld, rest, kb);
-      ctx->launches += 2;
+      MB_LAUNCH(ctx, "k_syrk_dmma", st) k_syrk_dmma<<<dim3(nt, nt), 256, kSyrkSmem, st>>>(Akk + kb, A + (size_t)(k + kb) * ld + (k + kb), ld, rest, kb);
     }
   }
   int info = 0;
@@ -480,9 +478,8 @@ static double search(const std::vector<double>& D, const std::vector<double>& u,
 // ---------------------------------------------------------------------------------------------
 static void gemv_n(mb_ctx* ctx, const double* A, int ld, int m, int n, const double* x, double* y, double* part,
                    cudaStream_t st) {
-  k_gemv_n_partial<<<dim3((m + 127) / 128, kGemvChunks), 128, 0, st>>>(A, ld, m, n, x, part);
-  k_gemv_n_reduce<<<(m + 255) / 256, 256, 0, st>>>(part, m, y);
-  ctx->launches += 2;
+  MB_LAUNCH(ctx, "k_gemv_n_partial", st) k_gemv_n_partial<<<dim3((m + 127) / 128, kGemvChunks), 128, 0, st>>>(A, ld, m, n, x, part);
+  MB_LAUNCH(ctx, "k_gemv_n_reduce", st) k_gemv_n_reduce<<<(m + 255) / 256, 256, 0, st>>>(part, m, y);
 }
 
 void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, double lambda, mb_spline** out) {
@@ -550,14 +547,12 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
   d_sy.upload(sy, st);
   d_w2.upload(w2, st);
   const dim3 g2((np + 31) / 32, (np + 31) / 32);
-  k_assemble<<<g2, 256, 0, st>>>(d_sx.p, d_sy.p, d_w2.p, np, d_K.p, np);
-  ctx->launches++;
+  MB_LAUNCH(ctx, "k_assemble", st) k_assemble<<<g2, 256, 0, st>>>(d_sx.p, d_sy.p, d_w2.p, np, d_K.p, np);
   for (int j = 0; j < 3; ++j) {
     d_v.upload(qr.v[j], st);
     gemv_n(ctx, d_K.p, np, np, np, d_v.p, d_p.p, d_part.p, st);
-    k_make_q<<<1, 1024, 0, st>>>(d_v.p, d_p.p, np, d_q.p);
-    k_rank2<<<g2, 256, 0, st>>>(d_K.p, np, np, d_v.p, d_q.p);
-    ctx->launches += 2;
+    MB_LAUNCH(ctx, "k_make_q", st) k_make_q<<<1, 1024, 0, st>>>(d_v.p, d_p.p, np, d_q.p);
+    MB_LAUNCH(ctx, "k_rank2", st) k_rank2<<<g2, 256, 0, st>>>(d_K.p, np, np, d_v.p, d_q.p);
     MB_CUDA(cudaStreamSynchronize(st));   // d_v is re-uploaded from a host vector next iteration
   }
   MB_CUDA(cudaGetLastError());
@@ -593,10 +588,11 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
                                     &lwork) != CUSOLVER_STATUS_SUCCESS)
       throw Error(MB_E_CUDA, "cusolverDnDsyevd_bufferSize failed");
     DevBuf<double> d_work((size_t)lwork);
-    if (cusolverDnDsyevd(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p, d_work.p,
-                         lwork, d_info.p) != CUSOLVER_STATUS_SUCCESS)
-      throw Error(MB_E_CUDA, "cusolverDnDsyevd failed");
-    ctx->launches++;
+    cusolverStatus_t cs = CUSOLVER_STATUS_SUCCESS;
+    MB_LAUNCH(ctx, "cusolverDnDsyevd", st)
+      cs = cusolverDnDsyevd(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p, d_work.p,
+                            lwork, d_info.p);
+    if (cs != CUSOLVER_STATUS_SUCCESS) throw Error(MB_E_CUDA, "cusolverDnDsyevd failed");
     int info = 0;
     std::vector<double> eta(m);
     MB_CUDA(cudaMemcpyAsync(&info, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -612,8 +608,7 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     DevBuf<double> d_z(m), d_u(m), d_g(m), d_beta(m);
     for (int r = 0; r < L; ++r) {
       d_z.upload(z[r], st);
-      k_gemv_t<<<(m + 7) / 8, 256, 0, st>>>(M, m, m, m, d_z.p, d_u.p);   // u = V' z (ascending order)
-      ctx->launches++;
+      MB_LAUNCH(ctx, "k_gemv_t", st) k_gemv_t<<<(m + 7) / 8, 256, 0, st>>>(M, m, m, m, d_z.p, d_u.p);   // u = V' z (ascending order)
       std::vector<double> u_asc(m);
       MB_CUDA(cudaMemcpyAsync(u_asc.data(), d_u.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
       MB_CUDA(cudaStreamSynchronize(st));
@@ -631,14 +626,12 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     }
   } else {
     // ---- fixed lambda: (M + lambda I) beta = z by tensor-core Cholesky ------------------------------
-    k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(M, m, m, lambda);
-    ctx->launches++;
+    MB_LAUNCH(ctx, "k_add_diag", st) k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(M, m, m, lambda);
     cholesky_lower(ctx, M, m, m, st);
     DevBuf<double> d_B((size_t)m * L);
     for (int r = 0; r < L; ++r)
       MB_CUDA(cudaMemcpyAsync(d_B.p + (size_t)r * m, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
-    k_chol_solve<<<1, 1024, 0, st>>>(M, m, m, d_B.p, m, L);
-    ctx->launches++;
+    MB_LAUNCH(ctx, "k_chol_solve", st) k_chol_solve<<<1, 1024, 0, st>>>(M, m, m, d_B.p, m, L);
     for (int r = 0; r < L; ++r)
       MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p + (size_t)r * m, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));

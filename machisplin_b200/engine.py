@@ -221,6 +221,20 @@ class Engine:
     def launches(self) -> int:
         return int(self.lib.mb_launch_count(self._h))
 
+    def timing(self, on: bool):
+        check(self.lib.mb_timing_enable(self._h, 1 if on else 0))
+
+    def timing_collect(self) -> dict:
+        """{kernel name: (total device ms, launches)} since the last collect (CUDA events on the launching stream)."""
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        cnt = (C.c_int64 * cap)()
+        n = self.lib.mb_timing_collect(self._h, cap, names, ms, cnt)
+        if n < 0:
+            check(n)
+        return {names[i].decode(): (ms[i], int(cnt[i])) for i in range(n)}
+
     def set_fast_eval_params(self, cheb_p=0, leaf_cols=0, leaf_rows=0):
         check(self.lib.mb_set_fast_eval_params(self._h, cheb_p, leaf_cols, leaf_rows))
 

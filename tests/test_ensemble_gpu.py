@@ -1,0 +1,122 @@
+"""GPU parity: per-cell ensemble evaluation, Gram reduction (a6) vs the oracle."""
+import numpy as np
+import pytest
+
+from machisplin_b200 import synth
+from oracle import cbind, models as om, mltps as omt, tps as otps
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def case():
+    geom = synth.make_geom(160, 224)
+    C = 4
+    models = synth.make_models(geom, C, 700, 5, kept="bgnmrv", rf_trees=50, gbm_trees=80)
+    cov = synth.covariate_planes(geom, C)
+    return geom, C, models, cov
+
+
+def _cmp(got, ref, tol):
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), "NA mask differs"
+    m = ~np.isnan(ref)
+    err = np.max(np.abs(got[m] - ref[m])) / np.max(np.abs(ref[m]))
+    assert err < tol, err
+    return err
+
+
+@pytest.mark.parametrize("letter", list("bgnmrv"))
+def test_single_model_raster(engine, case, letter):
+    geom, C, models, cov = case
+    ens = engine.ensemble_create(geom, models, letter, [1.0], 1.0, C + 2)
+    got = engine.ensemble_eval(ens, cov)
+    ref = cbind.ensemble_eval(models, letter, [1.0], 1.0, cov, geom.as_tuple())
+    # trees decide on identical comparisons -> only leaf-value float rounding; gam/nnet/earth are float64
+    tol = {"b": 2e-7, "r": 2e-7, "g": 1e-12, "n": 1e-12, "m": 1e-12, "v": 5e-6}[letter]
+    _cmp(got, ref, tol)
+
+
+def test_tree_decisions_bit_exact(engine, case):
+    """every RF / GBM comparison must take the same branch as the float64 reference comparison:
+    with integer-valued leaves the float32 leaf storage is exact, so the result must be identical."""
+    geom, C, models, cov = case
+    m2 = {"r": dict(models["r"]), "b": dict(models["b"])}
+    rng = np.random.default_rng(0)
+    m2["r"]["nodepred"] = rng.integers(-50, 50, models["r"]["nodepred"].shape).astype(np.float64)
+    sc = models["b"]["splitcode"].copy()
+    leaf = models["b"]["splitvar"] == -1
+    sc[leaf] = rng.integers(-8, 8, int(leaf.sum()))
+    m2["b"]["splitcode"] = sc
+    m2["b"]["initF"] = 3.0
+    for letter in "rb":
+        ens = engine.ensemble_create(geom, m2, letter, [1.0], 1.0, C + 2)
+        got = engine.ensemble_eval(ens, cov)
+        ref = cbind.ensemble_eval(m2, letter, [1.0], 1.0, cov, geom.as_tuple())
+        m = ~np.isnan(ref)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        if letter == "b":
+            assert np.array_equal(got[m], ref[m])
+        else:   # mean of integers over ntree: identical up to the final division
+            assert np.max(np.abs(got[m] - ref[m])) < 1e-12
+
+
+def test_full_ensemble_plus_tps(engine, case):
+    geom, C, models, cov = case
+    kept, w, wt = synth.ensemble_weights("bgnmrv")
+    xy, _, _ = synth.make_knots(geom, 250, 8)
+    y = synth.residual_field(xy, 8)
+    fit = otps.tps_fit(xy, y)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
+    got = engine.ensemble_eval(ens, cov, spline=sp)
+    surf = cbind.tps_eval(fit, geom.as_tuple())
+    ref = cbind.ensemble_eval(models, kept, w, wt, cov, geom.as_tuple(), tps=surf)
+    _cmp(got, ref, 2e-6)
+    # same through a precomputed surface and on a window
+    win = (17, 131, 40, 199)
+    got_w = engine.ensemble_eval(ens, cov, tps_surface=surf[win[0]:win[1], win[2]:win[3]], window=win)
+    _cmp(got_w, ref[win[0]:win[1], win[2]:win[3]], 2e-6)
+
+
+def test_smooth_only_and_weight_rule(engine, case):
+    geom, C, models, cov = case
+    p = np.array([0.41, 0.03, 0.333, 0.9])            # g n m v raw optimiser output
+    kept, w, wt = om.select_models(p, om.MODEL_LETTERS_SMOOTH)
+    assert kept == "gmv" and np.allclose(w, [0.41, 0.33, 0.9]) and abs(wt - p.sum()) < 1e-15
+    ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
+    got = engine.ensemble_eval(ens, cov)
+    ref = cbind.ensemble_eval(models, kept, w, wt, cov, geom.as_tuple())
+    _cmp(got, ref, 2e-6)
+
+
+def test_gbm_alone_predicts_na_cells(engine, case):
+    """gbm routes NA through MissingNode and returns numbers where every other model gives NA."""
+    geom, C, models, cov = case
+    ens = engine.ensemble_create(geom, models, "b", [1.0], 1.0, C + 2)
+    got = engine.ensemble_eval(ens, cov)
+    assert np.isnan(cov[0]).any() and not np.isnan(got).any()
+    ref = cbind.ensemble_eval(models, "b", [1.0], 1.0, cov, geom.as_tuple())
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 2e-7
+
+
+def test_point_predictions(engine, case):
+    geom, C, models, cov = case
+    kept, w, wt = synth.ensemble_weights("bgnmrv")
+    ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
+    _, row, col = synth.make_knots(geom, 300, 3)
+    X = omt.point_features(geom.as_tuple(), cov.astype(np.float64), row, col)
+    got = engine.ensemble_predict_points(ens, X)
+    ref = om.ensemble_predict(models, kept, w, wt, X)
+    _cmp(got, ref, 1e-10)
+
+
+@pytest.mark.parametrize("K", [4, 6])
+def test_gram(engine, K):
+    rng = np.random.default_rng(K)
+    R = rng.standard_normal((45000, K)) * rng.uniform(0.5, 20, K)
+    G = engine.gram(R)
+    ref = om.gram(R)
+    assert np.max(np.abs(G - ref)) <= 1e-12 * np.max(np.abs(ref))
+    k = rng.uniform(0, 1, K)
+    assert abs(om.rss_from_gram(k, G) - om.rss_objective(k, R)) <= 1e-10 * om.rss_objective(k, R)

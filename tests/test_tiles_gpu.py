@@ -1,0 +1,59 @@
+"""GPU parity: mltps part 3/4 tiling + seam feather and machisplin.tiles.merge."""
+import numpy as np
+import pytest
+
+from machisplin_b200 import synth
+from oracle import tiles as otl
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(b)
+    return float(np.max(np.abs(a[m] - b[m])) / np.max(np.abs(b[m])))
+
+
+@pytest.mark.parametrize("shape,tile_px", [((300, 420), 150), ((257, 190), 100), ((128, 300), 150), ((200, 200), 1500)])
+@pytest.mark.parametrize("method", ["direct", "fast"])
+def test_tiled_tps_surface(engine, shape, tile_px, method):
+    geom = synth.make_geom(*shape)
+    xy, _, _ = synth.make_knots(geom, 900, 17)
+    y = synth.residual_field(xy, 17)
+    ref = otl.tps_tiled_surface(geom.as_tuple(), xy, y, tile_px=tile_px)
+    got = engine.tiles_tps(geom, xy, y, tile_px=tile_px, method=method)
+    assert relerr(got, ref) < (1e-8 if method == "direct" else 2e-6)
+
+
+def test_sparse_tile_becomes_zero_tile(engine):
+    """< 10 knots in a fit box -> the tile is zeros (V73:710-721)."""
+    geom = synth.make_geom(200, 400)
+    xy, _, _ = synth.make_knots(geom, 400, 23)
+    xy = xy[xy[:, 0] < 0.45]                     # empty the east half
+    y = synth.residual_field(xy, 23)
+    ref = otl.tps_tiled_surface(geom.as_tuple(), xy, y, tile_px=100)
+    got = engine.tiles_tps(geom, xy, y, tile_px=100, method="fast")
+    assert relerr(got, ref) < 2e-6
+    assert np.all(got[:, 350:] == 0.0)
+
+
+@pytest.mark.parametrize("nc,nr", [(2, 2), (3, 2), (2, 1), (1, 3), (1, 1)])
+def test_tiles_merge_with_na(engine, nc, nr):
+    geom = synth.make_geom(240, 310)
+    rng = np.random.default_rng(nc * 10 + nr)
+    tc = otl.tiles_create(geom.as_tuple(), np.zeros((0, 2)), out_ncol=nc, out_nrow=nr, feather_d=30)
+    wins, rasters = [], []
+    yy, xx = np.mgrid[0:geom.nrow, 0:geom.ncol]
+    base = np.sin(xx / 40.0) + np.cos(yy / 55.0)
+    hole = (xx - 150) ** 2 + (yy - 120) ** 2 < 30 ** 2
+    for k, t in enumerate(tc["tiles"]):
+        w = t["win"]
+        r = (base + 0.1 * k + 0.01 * rng.standard_normal(base.shape))[w[0]:w[1], w[2]:w[3]].copy()
+        r[hole[w[0]:w[1], w[2]:w[3]]] = np.nan
+        if k == 0:
+            r[:5, :] = np.nan                    # ragged NA edge inside an overlap
+        wins.append(w)
+        rasters.append(r)
+    ref = otl.tiles_merge(geom.as_tuple(), wins, rasters, nc, nr)
+    got = engine.tiles_merge(geom, wins, rasters, nc, nr)
+    assert relerr(got, ref) < 1e-13
