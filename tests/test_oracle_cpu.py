@@ -1,0 +1,180 @@
+"""CPU tests of the oracle itself: analytic known-answer tests of the thin-plate smoothing spline
+(the reference has no tests and ships no expected outputs - SURVEY.md 4, 8c), the committed golden
+fixture generated from the reference's bundled inputs, and the tiling / weight-rule restatements."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cbind, models as om, tiles as otl, tps as otps
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "bundled_c1.npz")
+
+
+@pytest.fixture(scope="module")
+def cloud():
+    rng = np.random.default_rng(0)
+    n = 400
+    xy = rng.uniform(0, 1, (n, 2)) * [3.0, 2.0] + [10, -5]
+    y = np.sin(2 * xy[:, 0]) * np.cos(3 * xy[:, 1]) + 0.1 * rng.standard_normal(n)
+    return xy, y, otps.tps_fit(xy, y)
+
+
+def test_system_identities(cloud):
+    xy, y, f = cloud
+    s = f.knots_s
+    T = np.column_stack([np.ones(len(s)), s])
+    K = otps.rad_cov(s, s)
+    assert np.abs(T.T @ f.c).max() < 1e-8 * np.abs(f.c).sum()                 # T'c = 0
+    assert np.abs(K @ f.c + f.lam * f.c + T @ f.d - y).max() < 1e-10          # (K + lambda I)c + Td = y
+    p = otps.tps_predict_points(f, xy)
+    assert np.abs(p - (y - f.lam * f.c)).max() < 1e-10                        # f(x_i) = y_i - lambda c_i
+    assert abs(f.eff_df - (3 + np.sum(f.eta / (f.eta + f.lam)))) < 1e-9       # trA
+    assert np.all(np.diff(f.gcv_grid[:, 0]) > 0) and np.all(np.diff(f.gcv_grid[:, 1]) < 0)   # trA monotone in lambda
+    assert not f.gcv_at_endpoint and f.gcv_grid.shape == (200, 3)
+    assert abs(f.gcv_grid[:, 1].max() - 0.95 * len(s)) < 1e-3 and abs(f.gcv_grid[:, 1].min() - 3.001) < 1e-4
+
+
+def test_affine_is_reproduced_exactly(cloud):
+    xy, _, _ = cloud
+    ya = 2.0 + 3.0 * xy[:, 0] - 0.5 * xy[:, 1]
+    f = otps.tps_fit(xy, ya, lam=1e-3)
+    assert np.abs(f.c).max() < 1e-7
+    q = np.array([[11.0, -4.0], [12.5, -3.2]])
+    assert np.allclose(otps.tps_predict_points(f, q), 2.0 + 3.0 * q[:, 0] - 0.5 * q[:, 1], atol=1e-9)
+
+
+def test_lambda_limits(cloud):
+    xy, y, _ = cloud
+    f0 = otps.tps_fit(xy, y, lam=1e-12)                                       # lambda -> 0 interpolates
+    assert np.abs(otps.tps_predict_points(f0, xy) - y).max() < 1e-5
+    finf = otps.tps_fit(xy, y, lam=1e9)                                       # lambda -> inf: least-squares plane
+    A = np.column_stack([np.ones(len(xy)), xy])
+    plane = A @ np.linalg.lstsq(A, y, rcond=None)[0]
+    assert np.abs(otps.tps_predict_points(finf, xy) - plane).max() < 1e-5
+
+
+def test_axis_rescale_invariance(cloud):
+    """scale.type = "range" makes the fit invariant to per-axis affine maps of the coordinates."""
+    xy, y, f = cloud
+    xy2 = xy * [7.0, 0.01] + [100.0, 3.0]
+    f2 = otps.tps_fit(xy2, y)
+    assert abs(f2.lam - f.lam) < 1e-9 * f.lam
+    assert np.abs(f2.c - f.c).max() < 1e-6 * np.abs(f.c).max()
+
+
+def test_replicates_are_pooled(cloud):
+    xy, y, _ = cloud
+    xy2 = np.vstack([xy, xy[:50]])
+    y2 = np.concatenate([y, y[:50] + 0.2])
+    f = otps.tps_fit(xy2, y2)
+    assert f.knots_s.shape[0] == len(xy) and f.n_obs == len(xy2)
+    assert abs(f.pure_ss - 50 * 2 * 0.1 ** 2) < 1e-9 and f.weights.sum() == len(xy2)
+
+
+def test_knot_on_cell_centre_is_finite():
+    geom = (0.0, 1.0, 0.0, 1.0, 32, 32)
+    rng = np.random.default_rng(1)
+    cells = rng.choice(32 * 32, 40, replace=False)
+    x, yv = otps.cell_centres(geom, cells // 32, cells % 32)
+    xy = np.column_stack([x, yv])
+    f = otps.tps_fit(xy, rng.standard_normal(40), lam=1e-3)
+    ras = otps.tps_interpolate(f, geom)
+    assert np.isfinite(ras).all()
+    assert np.allclose(ras[cells // 32, cells % 32], otps.tps_predict_points(f, xy), atol=1e-12)
+
+
+def test_c_restatement_matches_numpy(cloud):
+    xy, y, f = cloud
+    geom = (10.0, 13.0, -5.0, -3.0, 70, 90)
+    a = otps.tps_interpolate(f, geom, 5, 60, 7, 80)
+    b = cbind.tps_eval(f, geom, (5, 60, 7, 80))
+    assert np.abs(a - b).max() < 1e-11 * np.abs(a).max()
+
+
+# ---- golden fixture from the reference's bundled inputs -----------------------------------------
+def test_bundled_data_tiling_and_fits():
+    z = np.load(GOLD)
+    geom = tuple(float(v) if i < 4 else int(v) for i, v in enumerate(z["geom"]))
+    assert geom[4:] == (2476, 3264)
+    knots_xy, krow, kcol = otl.knot_coordinates(geom, z["points"][:, :2])
+    assert np.array_equal(krow, z["krow"]) and np.array_equal(kcol, z["kcol"])
+    assert np.unique(knots_xy, axis=0).shape[0] == 813                        # no duplicates
+    lay = otl.mltps_tile_layout(geom)
+    assert (lay.nRx, lay.nCx) == (2, 3)                                       # V73:651-661
+    counts = []
+    for fw in lay.fit_win:
+        counts.append(int(((krow >= fw[0]) & (krow < fw[1]) & (kcol >= fw[2]) & (kcol < fw[3])).sum()))
+    # numbers derived independently in the survey from V73:651-673
+    assert counts == [190, 220, 199, 200, 237, 204] == list(z["tile_counts"])
+    assert np.array_equal(np.array(lay.fit_win), z["fit_win"]) and np.array_equal(np.array(lay.keep_win), z["keep_win"])
+    # one tile refit against the pinned oracle values
+    fw = lay.fit_win[4]
+    ins = (krow >= fw[0]) & (krow < fw[1]) & (kcol >= fw[2]) & (kcol < fw[3])
+    f = otps.tps_fit(knots_xy[ins], z["points"][ins, 2])
+    pin = z["tile_fits"][4]
+    assert abs(f.lam - pin[0]) < 1e-8 * pin[0] and abs(f.eff_df - pin[1]) < 1e-6
+    assert np.allclose(f.d, pin[2:5], rtol=1e-7) and abs(np.abs(f.c).sum() - pin[5]) < 1e-6 * pin[5]
+
+
+# ---- tiling / feather ---------------------------------------------------------------------------------
+def test_feather_is_a_partition_of_unity():
+    geom = (0.0, 3.0, 0.0, 2.0, 200, 300)
+    lay = otl.mltps_tile_layout(geom, tile_px=100)
+    tiles = [np.full((w[1] - w[0], w[3] - w[2]), 5.0) for w in lay.keep_win]
+    out = otl.feather_merge(geom, lay.keep_win, tiles, lay.nCx, lay.nRx)
+    assert np.allclose(out, 5.0) and not np.isnan(out).any()
+
+
+def test_feather_weights_on_a_vertical_seam():
+    geom = (0.0, 2.0, 0.0, 1.0, 10, 200)
+    lay = otl.mltps_tile_layout(geom, tile_px=100)
+    assert (lay.nRx, lay.nCx) == (1, 2)
+    a, b = lay.keep_win
+    tiles = [np.zeros((a[1] - a[0], a[3] - a[2])), np.ones((b[1] - b[0], b[3] - b[2]))]
+    out = otl.feather_merge(geom, lay.keep_win, tiles, 2, 1)
+    strip = out[0, b[2]:a[3]]
+    assert strip[0] == 0.0 and strip[-1] == 1.0 and np.allclose(np.diff(strip), 1.0 / (len(strip) - 1))
+    assert np.all(out[0, :b[2]] == 0) and np.all(out[0, a[3]:] == 1)
+
+
+def test_horizontal_seam_uses_the_southern_tile_as_tile_one():
+    geom = (0.0, 1.0, 0.0, 2.0, 200, 10)
+    lay = otl.mltps_tile_layout(geom, tile_px=100)
+    assert (lay.nRx, lay.nCx) == (2, 1)
+    south, north = lay.keep_win                      # order: j = 1 (south) first, V73:670
+    assert south[0] > north[0]
+    tiles = [np.zeros((south[1] - south[0], 10)), np.ones((north[1] - north[0], 10))]
+    out = otl.feather_merge(geom, lay.keep_win, tiles, 1, 2)
+    strip = out[south[0]:north[1], 0]
+    assert strip[0] == 1.0 and strip[-1] == 0.0      # north end -> north tile, south end -> south tile
+
+
+def test_crop_window_snaps_to_nearest_edge():
+    geom = (0.0, 10.0, 0.0, 5.0, 50, 100)
+    assert otl.crop_window(geom, (0.26, 9.74, 0.0, 5.0)) == (0, 50, 3, 97)
+    assert otl.crop_window(geom, (-3.0, 20.0, 1.04, 3.96)) == (10, 40, 0, 100)
+
+
+def test_tiles_create_matches_v73_arithmetic():
+    geom = (0.0, 3.0, 0.0, 3.0, 300, 300)
+    pts = np.array([[0.1, 0.1], [1.24, 0.5], [1.26, 0.5], [2.9, 2.9]])
+    tc = otl.tiles_create(geom, pts, out_ncol=3, out_nrow=3, feather_d=50)
+    t0 = tc["tiles"][0]
+    assert np.allclose(t0["ext"], (-0.25, 1.25, -0.25, 1.25))                 # +- feather.d/2 pixels, V73:1170,1195
+    assert t0["win"] == (175, 300, 0, 125)                                    # south-west tile first
+    assert list(t0["points"]) == [0, 1] and list(tc["tiles"][1]["points"]) == [1, 2]
+    assert list(tc["tiles"][8]["points"]) == [3]
+
+
+# ---- ensemble weight rule / RSS objective --------------------------------------------------------------
+def test_weight_rule_and_rss():
+    p = np.array([0.5, 0.024, 0.026, 0.3, 0.0, 0.149])
+    kept, w, tot = om.select_models(p)
+    cut = 0.05 * p.sum()
+    assert kept == "bmv" and np.allclose(w, [0.5, 0.3, 0.15]) and tot == p.sum() and cut > 0.03
+    rng = np.random.default_rng(2)
+    R = rng.standard_normal((900, 6))
+    k = rng.uniform(0, 1, 6)
+    assert abs(om.rss_objective(k, R) - om.rss_from_gram(k, om.gram(R))) < 1e-9
+    assert abs(om.rss_objective(3 * k, R) - om.rss_objective(k, R)) < 1e-9    # homogeneous of degree 0
