@@ -57,8 +57,8 @@ def test_tree_decisions_bit_exact(engine, case):
         assert np.array_equal(np.isnan(got), np.isnan(ref))
         if letter == "b":
             assert np.array_equal(got[m], ref[m])
-        else:   # mean of integers over ntree: identical up to the final division
-            assert np.max(np.abs(got[m] - ref[m])) < 1e-12
+        else:   # leaves are stored as float32(value - offset): one wrong branch would move the mean by >= 1/ntree
+            assert np.max(np.abs(got[m] - ref[m])) < 1e-5 < 0.1 / m2["r"]["ntree"]
 
 
 def test_full_ensemble_plus_tps(engine, case):
