@@ -167,7 +167,21 @@ int mb_gram_dev(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, v
 /* ---- a7: part 5  (V73:906-930) --------------------------------------------------------- */
 /* gather raster values at the cells (row[i], col[i]) - f.actual <- extract(final, points). */
 int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row,
-                        const int32_t* col, int n, double* out_host);
+                        const int32_t* col, int n, double* out_host, void* stream);
+
+/* ---- mltps parts 2-5 for one response in ONE call  (V73:442-932) --------------------------- */
+/* final = (sum_k round(w_k,2) f_k(cell)) / sum_all w  +  TPS(residuals)(cell), NA-propagating.
+ * The per-cell tree / svm kernels (part 2) run on a second stream while fields::Tps is fitted (part 3);
+ * the TPS surface, the smooth models and the combine (parts 3-5) are one fused pass over the grid.
+ * e may be NULL (tps only); knots_xy / resid may be NULL (tps = FALSE).  tile_px <= 0: one global spline
+ * (the nRx*nCx == 1 branch, V73:748-753); tile_px > 0: the reference's rule with that tile size (1500).
+ * spline_out (NULL-able) receives the global spline (NULL in tiled mode).  g is the full raster grid. */
+int mb_mltps_predict_dev(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, const float* cov_dev, int C,
+                         const double* knots_xy, const double* resid, int n, double lambda, int tile_px,
+                         double* out_dev, mb_spline** spline_out, void* stream);
+int mb_mltps_predict(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, const float* cov_host, int C,
+                     const double* knots_xy, const double* resid, int n, double lambda, int tile_px,
+                     double* out_host, mb_spline** spline_out);
 
 /* ---- device memory helpers for hosts without a CUDA allocator (R) ---------------------- */
 int mb_dev_alloc(mb_ctx* ctx, size_t bytes, void** out);
@@ -184,6 +198,9 @@ int mb_timing_collect(mb_ctx* ctx, int cap, const char** names, double* total_ms
 
 /* Tunables of the fast evaluator (0 = automatic). */
 int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows);
+/* Named integer tunables (0 = automatic): "tree_rows" = cells per thread of the forest tile (1, 2, 4);
+ * "eval_precision" = leaf kernel code path of the fast evaluator (1 = float64 only, 2 = force mixed). */
+int mb_set_param(mb_ctx* ctx, const char* name, int value);
 
 #ifdef __cplusplus
 }

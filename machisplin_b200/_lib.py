@@ -86,7 +86,9 @@ SIGNATURES = {
     "mb_tiles_merge_dev": (C.c_int, [VP, PG, C.c_int, C.c_int, PW, PVP, VP, VP]),
     "mb_gram": (C.c_int, [VP, PD, C.c_int, C.c_int, PD]),
     "mb_gram_dev": (C.c_int, [VP, VP, C.c_int, C.c_int, VP, VP]),
-    "mb_gather_cells_dev": (C.c_int, [VP, VP, C.c_int64, PI32, PI32, C.c_int, PD]),
+    "mb_gather_cells_dev": (C.c_int, [VP, VP, C.c_int64, PI32, PI32, C.c_int, PD, VP]),
+    "mb_mltps_predict_dev": (C.c_int, [VP, PG, VP, VP, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, VP, PVP, VP]),
+    "mb_mltps_predict": (C.c_int, [VP, PG, VP, PF, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, PD, PVP]),
     "mb_dev_alloc": (C.c_int, [VP, C.c_size_t, PVP]),
     "mb_dev_free": (C.c_int, [VP, VP]),
     "mb_h2d": (C.c_int, [VP, VP, VP, C.c_size_t]),
@@ -94,6 +96,7 @@ SIGNATURES = {
     "mb_timing_enable": (C.c_int, [VP, C.c_int]),
     "mb_timing_collect": (C.c_int, [VP, C.c_int, C.POINTER(C.c_char_p), PD, C.POINTER(C.c_int64)]),
     "mb_set_fast_eval_params": (C.c_int, [VP, C.c_int, C.c_int, C.c_int]),
+    "mb_set_param": (C.c_int, [VP, C.c_char_p, C.c_int]),
 }
 
 _lib = None

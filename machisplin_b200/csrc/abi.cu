@@ -42,6 +42,9 @@ int mb_init(int device, mb_ctx** out) {
     MB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     MB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    MB_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     init_logtab(ctx.get());
     *out = ctx.release();
   });
@@ -54,6 +57,11 @@ void mb_shutdown(mb_ctx* ctx) {
   fit_release(ctx);
   for (const mb_timed_launch& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  cudaDeviceSynchronize();
+  ctx->arena.release();
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -114,6 +122,22 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
   });
 }
 
+int mb_set_param(mb_ctx* ctx, const char* name, int value) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && name, "NULL argument");
+    const std::string n(name);
+    if (n == "tree_rows") {
+      MB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4, "tree_rows must be 0, 1, 2 or 4");
+      ctx->tree_rows = value;
+    } else if (n == "eval_precision") {
+      MB_REQUIRE(value >= 0 && value <= 2, "eval_precision must be 0 (auto), 1 (float64) or 2 (mixed)");
+      ctx->eval_precision = value;
+    } else {
+      throw Error(MB_E_ARG, "unknown parameter '" + n + "'");
+    }
+  });
+}
+
 // ---- device memory helpers -----------------------------------------------------------------
 int mb_dev_alloc(mb_ctx* ctx, size_t bytes, void** out) {
   return guarded([&] {
@@ -168,6 +192,7 @@ int mb_spline_create(mb_ctx* ctx, const double* knots_xy, int np, const double* 
     s->c.assign(c, c + np);
     for (int i = 0; i < 3; ++i) s->d[i] = d[i];
     for (int i = 0; i < 2; ++i) { s->center[i] = center[i]; s->scale[i] = scale[i]; }
+    ctx->arena.begin(ctx->stream);
     spline_finalize(ctx, s.get());
     *out = s.release();
   });
@@ -213,6 +238,7 @@ int mb_tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, dou
     MB_REQUIRE(ctx && xy && y && splines, "NULL argument");
     MB_REQUIRE(n > 3 && L >= 1, "need n > 3 observations and L >= 1 responses");
     MB_CUDA(cudaSetDevice(ctx->device));
+    ctx->arena.begin(ctx->stream);
     tps_fit(ctx, xy, y, n, L, lambda, splines);
   });
 }
@@ -233,7 +259,9 @@ int mb_tps_eval_dev(mb_ctx* ctx, const mb_spline* s, const mb_grid* g, const mb_
     check_window(g, w);
     MB_REQUIRE(out_row_stride >= w->c1 - w->c0, "row stride shorter than the window");
     MB_CUDA(cudaSetDevice(ctx->device));
-    eval_dispatch(ctx, s, g, w, method, out_dev, out_row_stride, stream ? (cudaStream_t)stream : ctx->stream);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    eval_dispatch(ctx, s, g, w, method, out_dev, out_row_stride, st);
   });
 }
 
@@ -245,7 +273,8 @@ int mb_tps_eval(mb_ctx* ctx, const mb_spline* s, const mb_grid* g, const mb_wind
     check_window(g, w);
     MB_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)(w->r1 - w->r0) * (w->c1 - w->c0);
-    DevBuf<double> d(n);
+    ctx->arena.begin(ctx->stream);
+    ABuf<double> d(ctx->arena, n);
     eval_dispatch(ctx, s, g, w, method, d.p, w->c1 - w->c0, ctx->stream);
     MB_CUDA(cudaMemcpyAsync(out_host, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -258,7 +287,8 @@ int mb_tps_predict_points(mb_ctx* ctx, const mb_spline* s, const double* xy, int
     MB_REQUIRE(n >= 0, "negative point count");
     if (n == 0) return;
     MB_CUDA(cudaSetDevice(ctx->device));
-    DevBuf<double> dx(n), dy(n), df(n);
+    ctx->arena.begin(ctx->stream);
+    ABuf<double> dx(ctx->arena, n), dy(ctx->arena, n), df(ctx->arena, n);
     dx.upload(xy, n, ctx->stream);
     dy.upload(xy + n, n, ctx->stream);
     tps_predict_points_dev(ctx, s, dx.p, dy.p, n, df.p, ctx->stream);
@@ -286,7 +316,9 @@ int mb_ensemble_eval_dev(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev
     MB_REQUIRE(ctx && e && out_dev, "NULL argument");
     MB_REQUIRE(C == 0 || cov_dev, "covariate planes are NULL");
     MB_CUDA(cudaSetDevice(ctx->device));
-    ensemble_eval(ctx, e, cov_dev, C, spline, tps_surface_dev, w, out_dev, stream ? (cudaStream_t)stream : ctx->stream);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    ensemble_eval(ctx, e, cov_dev, C, spline, tps_surface_dev, w, out_dev, st);
   });
 }
 
@@ -301,13 +333,14 @@ int mb_ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov_host, i
     const size_t plane = (size_t)g.nrow * g.ncol;
     const size_t nwin = (size_t)(w->r1 - w->r0) * (w->c1 - w->c0);
     // only the rows of the window travel: plane p rows [r0, r1) -> device plane of the same geometry
-    DevBuf<float> d_cov((size_t)C * plane);
+    ctx->arena.begin(ctx->stream);
+    ABuf<float> d_cov(ctx->arena, (size_t)C * plane);
     for (int p = 0; p < C; ++p) {
       const size_t off = p * plane + (size_t)w->r0 * g.ncol;
       MB_CUDA(cudaMemcpyAsync(d_cov.p + off, cov_host + off, sizeof(float) * (size_t)(w->r1 - w->r0) * g.ncol,
                               cudaMemcpyHostToDevice, ctx->stream));
     }
-    DevBuf<double> d_tps, d_out(nwin);
+    ABuf<double> d_tps(ctx->arena), d_out(ctx->arena, nwin);
     if (tps_surface_host) d_tps.upload(tps_surface_host, nwin, ctx->stream);
     ensemble_eval(ctx, e, d_cov.p, C, spline, tps_surface_host ? d_tps.p : nullptr, w, d_out.p, ctx->stream);
     MB_CUDA(cudaMemcpyAsync(out_host, d_out.p, nwin * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -319,6 +352,7 @@ int mb_ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* 
   return guarded([&] {
     MB_REQUIRE(ctx && e && X && out_host, "NULL argument");
     MB_CUDA(cudaSetDevice(ctx->device));
+    ctx->arena.begin(ctx->stream);
     ensemble_predict_points(ctx, e, X, n, out_host);
   });
 }
@@ -332,8 +366,9 @@ int mb_tiles_tps_dev(mb_ctx* ctx, const mb_grid* g, const double* knots_xy, cons
     check_grid(g);
     MB_REQUIRE(tile_px > 0 && fit_halo >= 0 && keep_halo >= 0 && keep_halo <= fit_halo, "bad tiling parameters");
     MB_CUDA(cudaSetDevice(ctx->device));
-    tiles_tps(ctx, *g, knots_xy, resid, n, tile_px, fit_halo, keep_halo, min_pts, lambda, method, out_dev,
-              stream ? (cudaStream_t)stream : ctx->stream);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    tiles_tps(ctx, *g, knots_xy, resid, n, tile_px, fit_halo, keep_halo, min_pts, lambda, method, out_dev, st);
   });
 }
 
@@ -345,7 +380,8 @@ int mb_tiles_tps(mb_ctx* ctx, const mb_grid* g, const double* knots_xy, const do
     MB_REQUIRE(tile_px > 0 && fit_halo >= 0 && keep_halo >= 0 && keep_halo <= fit_halo, "bad tiling parameters");
     MB_CUDA(cudaSetDevice(ctx->device));
     const size_t ncell = (size_t)g->nrow * g->ncol;
-    DevBuf<double> d_out(ncell);
+    ctx->arena.begin(ctx->stream);
+    ABuf<double> d_out(ctx->arena, ncell);
     tiles_tps(ctx, *g, knots_xy, resid, n, tile_px, fit_halo, keep_halo, min_pts, lambda, method, d_out.p,
               ctx->stream);
     MB_CUDA(cudaMemcpyAsync(out_host, d_out.p, ncell * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -360,7 +396,9 @@ int mb_tiles_merge_dev(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_w
     check_grid(g);
     MB_REQUIRE(nC >= 1 && nR >= 1, "need at least one tile");
     MB_CUDA(cudaSetDevice(ctx->device));
-    tiles_merge(ctx, *g, nC, nR, wins, tiles_dev, out_dev, stream ? (cudaStream_t)stream : ctx->stream);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    tiles_merge(ctx, *g, nC, nR, wins, tiles_dev, out_dev, st);
   });
 }
 
@@ -372,16 +410,15 @@ int mb_tiles_merge(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_windo
     MB_REQUIRE(nC >= 1 && nR >= 1, "need at least one tile");
     MB_CUDA(cudaSetDevice(ctx->device));
     const int nt = nC * nR;
-    std::vector<DevBuf<double>> bufs(nt);
+    ctx->arena.begin(ctx->stream);
     std::vector<const double*> ptrs(nt);
     for (int t = 0; t < nt; ++t) {
       check_window(g, &wins[t]);
       const size_t n = (size_t)(wins[t].r1 - wins[t].r0) * (wins[t].c1 - wins[t].c0);
-      bufs[t].upload(tiles_host[t], n, ctx->stream);
-      ptrs[t] = bufs[t].p;
+      ptrs[t] = ctx->arena.upload(tiles_host[t], n, ctx->stream);
     }
     const size_t ncell = (size_t)g->nrow * g->ncol;
-    DevBuf<double> d_out(ncell);
+    ABuf<double> d_out(ctx->arena, ncell);
     tiles_merge(ctx, *g, nC, nR, wins, ptrs.data(), d_out.p, ctx->stream);
     MB_CUDA(cudaMemcpyAsync(out_host, d_out.p, ncell * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -394,7 +431,9 @@ int mb_gram_dev(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, v
     MB_REQUIRE(ctx && R_dev && G_dev, "NULL argument");
     MB_REQUIRE(n >= 1 && K >= 1 && K <= 8, "need n >= 1 and 1 <= K <= 8");
     MB_CUDA(cudaSetDevice(ctx->device));
-    gram(ctx, R_dev, n, K, G_dev, stream ? (cudaStream_t)stream : ctx->stream);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    gram(ctx, R_dev, n, K, G_dev, st);
   });
 }
 
@@ -403,7 +442,8 @@ int mb_gram(mb_ctx* ctx, const double* R_host, int n, int K, double* G_host) {
     MB_REQUIRE(ctx && R_host && G_host, "NULL argument");
     MB_REQUIRE(n >= 1 && K >= 1 && K <= 8, "need n >= 1 and 1 <= K <= 8");
     MB_CUDA(cudaSetDevice(ctx->device));
-    DevBuf<double> dR((size_t)n * K), dG((size_t)K * K);
+    ctx->arena.begin(ctx->stream);
+    ABuf<double> dR(ctx->arena, (size_t)n * K), dG(ctx->arena, (size_t)K * K);
     dR.upload(R_host, (size_t)n * K, ctx->stream);
     gram(ctx, dR.p, n, K, dG.p, ctx->stream);
     MB_CUDA(cudaMemcpyAsync(G_host, dG.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));
@@ -412,11 +452,107 @@ int mb_gram(mb_ctx* ctx, const double* R_host, int n, int K, double* G_host) {
 }
 
 int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row,
-                        const int32_t* col, int n, double* out_host) {
+                        const int32_t* col, int n, double* out_host, void* stream) {
   return guarded([&] {
     MB_REQUIRE(ctx && raster_dev && row && col && out_host, "NULL argument");
     MB_CUDA(cudaSetDevice(ctx->device));
-    gather_cells(ctx, raster_dev, row_stride, row, col, n, out_host);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    gather_cells(ctx, raster_dev, row_stride, row, col, n, out_host, st);
+  });
+}
+
+// ---- mltps parts 2-5 in one call -----------------------------------------------------------------
+static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, const float* cov, int C,
+                          const double* knots_xy, const double* resid, int n, double lambda, int tile_px,
+                          double* out, mb_spline** spline_out, cudaStream_t st) {
+  const mb_window full{0, g.nrow, 0, g.ncol};
+  const size_t ncell = (size_t)g.nrow * g.ncol;
+  if (spline_out) *spline_out = nullptr;
+  if (e) {
+    const mb_grid eg = ensemble_grid(e);
+    MB_REQUIRE(eg.nrow == g.nrow && eg.ncol == g.ncol && eg.xmin == g.xmin && eg.xmax == g.xmax &&
+                   eg.ymin == g.ymin && eg.ymax == g.ymax, "grid differs from the grid the ensemble was created for");
+    MB_REQUIRE(C == ensemble_ncov(e), "number of covariate planes does not match the model descriptors (P = C + 2)");
+    MB_REQUIRE(C == 0 || cov, "covariate planes are NULL");
+  }
+  // part 2 (trees + svm) starts on the side stream; it only needs the covariates
+  double* acc = nullptr;
+  const bool heavy = e && ensemble_has_heavy(e);
+  if (heavy) {
+    acc = ctx->arena.take_n<double>(ncell);
+    MB_CUDA(cudaEventRecord(ctx->ev_fork, st));
+    MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    ensemble_heavy(ctx, e, cov, C, full, acc, ctx->side);
+    MB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  }
+  // part 3: fields::Tps of the residuals on the context stream, beside the kernels above
+  const bool tps = knots_xy && resid && n > 0;
+  std::unique_ptr<mb_spline> sp;
+  const double* surface = nullptr;
+  if (tps) {
+    const int nRx = tile_px > 0 ? (g.nrow + tile_px - 1) / tile_px : 1;
+    const int nCx = tile_px > 0 ? (g.ncol + tile_px - 1) / tile_px : 1;
+    if (nRx * nCx == 1) {                                            // V73:748-753
+      mb_spline* raw = nullptr;
+      tps_fit(ctx, knots_xy, resid, n, 1, lambda, &raw);
+      sp.reset(raw);
+    } else {                                                         // V73:649-895
+      double* surf = ctx->arena.take_n<double>(ncell);
+      tiles_tps(ctx, g, knots_xy, resid, n, tile_px, 0.2, 0.025, 10, lambda, MB_EVAL_FAST, surf, ctx->stream);
+      MB_CUDA(cudaStreamSynchronize(ctx->stream));
+      surface = surf;
+    }
+  }
+  if (heavy) MB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  // parts 3-5: TPS surface + smooth models + combine, one pass over the grid
+  if (e) {
+    ensemble_finish(ctx, e, cov, C, sp.get(), surface, full, acc, out, st);
+  } else if (sp) {
+    tps_eval_fast(ctx, sp.get(), g, full, out, g.ncol, st);
+  } else if (surface) {
+    MB_CUDA(cudaMemcpyAsync(out, surface, ncell * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  } else {
+    throw Error(MB_E_ARG, "nothing to predict: no ensemble and no TPS input");
+  }
+  if (spline_out) *spline_out = sp.release();
+  else if (sp) { MB_CUDA(cudaStreamSynchronize(st)); }
+}
+
+int mb_mltps_predict_dev(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, const float* cov_dev, int C,
+                         const double* knots_xy, const double* resid, int n, double lambda, int tile_px,
+                         double* out_dev, mb_spline** spline_out, void* stream) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && out_dev, "NULL argument");
+    check_grid(g);
+    MB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    mltps_predict(ctx, *g, e, cov_dev, C, knots_xy, resid, n, lambda, tile_px, out_dev, spline_out, st);
+  });
+}
+
+int mb_mltps_predict(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, const float* cov_host, int C,
+                     const double* knots_xy, const double* resid, int n, double lambda, int tile_px,
+                     double* out_host, mb_spline** spline_out) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && out_host, "NULL argument");
+    check_grid(g);
+    MB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->side;   // keeps ctx->stream free for the fit; copies and kernels are ordered on one stream
+    ctx->arena.begin(st);
+    const size_t ncell = (size_t)g->nrow * g->ncol;
+    float* d_cov = nullptr;
+    if (e && C > 0) {
+      MB_REQUIRE(cov_host, "covariate planes are NULL");
+      d_cov = ctx->arena.take_n<float>((size_t)C * ncell);
+      MB_CUDA(cudaMemcpyAsync(d_cov, cov_host, sizeof(float) * (size_t)C * ncell, cudaMemcpyHostToDevice, st));
+    }
+    double* d_out = ctx->arena.take_n<double>(ncell);
+    // the user stream of this call is a private one, so part 2 needs no fork: run it in line
+    mltps_predict(ctx, *g, e, d_cov, C, knots_xy, resid, n, lambda, tile_px, d_out, spline_out, st);
+    MB_CUDA(cudaMemcpyAsync(out_host, d_out, ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
   });
 }
 

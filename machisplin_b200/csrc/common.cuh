@@ -10,6 +10,7 @@
 #include <vector>
 #include <stdexcept>
 #include <memory>
+#include <algorithm>
 
 #include "../../include/machisplin_b200.h"
 
@@ -83,6 +84,62 @@ struct DevBuf {
   void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
 };
 
+// ---- per-context scratch arena ------------------------------------------------------------
+// Temporaries of one top-level call are bump-allocated from blocks that stay alive across calls, so
+// the hot path performs no cudaMalloc / cudaFree (both synchronise the device).  begin(stream) starts a
+// new call: if the previous call ran on a different stream it is drained first, because its kernels may
+// still be reading the blocks that are about to be reused.
+struct Arena {
+  struct Block { char* p; size_t cap; };
+  std::vector<Block> blocks;
+  size_t cur = 0, off = 0;
+  cudaStream_t last = nullptr;
+  bool used = false;
+  void begin(cudaStream_t st) {
+    if (used && last != st) cudaStreamSynchronize(last);
+    last = st; used = true; cur = 0; off = 0;
+  }
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    for (; cur < blocks.size(); ++cur, off = 0)
+      if (off + bytes <= blocks[cur].cap) { void* r = blocks[cur].p + off; off += bytes; return r; }
+    Block b{nullptr, std::max(bytes, size_t(8) << 20)};
+    cudaError_t e = cudaMalloc(&b.p, b.cap);
+    if (e != cudaSuccess) throw Error(MB_E_NOMEM, std::string("cudaMalloc (arena): ") + cudaGetErrorString(e));
+    blocks.push_back(b);
+    cur = blocks.size() - 1; off = bytes;
+    return b.p;
+  }
+  template <class T> T* take_n(size_t n) { return static_cast<T*>(take(n * sizeof(T))); }
+  template <class T> T* upload(const T* h, size_t n, cudaStream_t st) {
+    T* d = take_n<T>(std::max<size_t>(n, 1));
+    if (n) {
+      cudaError_t e = cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) throw Error(MB_E_CUDA, std::string("cudaMemcpyAsync (arena): ") + cudaGetErrorString(e));
+    }
+    return d;
+  }
+  void release() { for (Block& b : blocks) cudaFree(b.p); blocks.clear(); cur = off = 0; used = false; }
+};
+
+// Arena-backed array with the DevBuf surface the kernels' call sites use (.p, upload).
+template <class T>
+struct ABuf {
+  T* p = nullptr;
+  size_t n = 0;
+  Arena* ar = nullptr;
+  explicit ABuf(Arena& a, size_t n_ = 0) : ar(&a) { if (n_) { p = a.take_n<T>(n_); n = n_; } }
+  void ensure(size_t n_) { if (n_ > n) { p = ar->take_n<T>(n_); n = n_; } }
+  void upload(const T* h, size_t cnt, cudaStream_t s) {
+    ensure(cnt);
+    if (cnt) {
+      cudaError_t e = cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) throw Error(MB_E_CUDA, std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e));
+    }
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+};
+
 }  // namespace mb
 
 // ---- handles ----------------------------------------------------------------------------
@@ -101,11 +158,15 @@ struct mb_ctx {
   int64_t launches = 0;
   // fast-evaluator tunables (0 = automatic)
   int cheb_p = 0, leaf_cols = 0, leaf_rows = 0;
+  int tree_rows = 0;          // cells per thread of the tree tile (1, 2, 4; 0 = automatic)
   // 256-entry (1/m_k, -log(1/m_k)) table for the float64 table-driven log
   mb::DevBuf<double2> logtab;
+  int eval_precision = 0;     // fast evaluator: 0 = automatic, 1 = float64 only, 2 = force mixed
   // scratch reused across calls
-  mb::DevBuf<double> scratch_d;
-  mb::DevBuf<char> scratch_b;
+  mb::Arena arena;
+  // second stream + events: the TPS fit runs beside the per-cell ensemble kernels (mb_mltps_predict*)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 struct mb_spline {
@@ -183,8 +244,10 @@ struct KernelTimer {
 void spline_finalize(mb_ctx* ctx, mb_spline* s);   // uploads, computes sum|c| and fscale
 void tps_eval_direct(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
                      int64_t stride, cudaStream_t st);
+struct EnsFuse;   // ens_device.cuh
+// Temporaries come from ctx->arena: the caller must have called ctx->arena.begin(st) for this call.
 void tps_eval_fast(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
-                   int64_t stride, cudaStream_t st);
+                   int64_t stride, cudaStream_t st, const EnsFuse* fuse = nullptr);
 void tps_predict_points_dev(mb_ctx* ctx, const mb_spline* s, const double* x_dev, const double* y_dev, int n,
                             double* out_dev, cudaStream_t st);
 void init_logtab(mb_ctx* ctx);

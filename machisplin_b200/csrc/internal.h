@@ -15,6 +15,14 @@ void ensemble_free(mb_ensemble* e);
 mb_grid ensemble_grid(const mb_ensemble* e);
 void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_spline* spline,
                    const double* tps_surface_dev, const mb_window* w, double* out_dev, cudaStream_t st);
+// the two halves of ensemble_eval, exposed so that mltps_predict can run the TPS fit between them
+bool ensemble_has_heavy(const mb_ensemble* e);
+int ensemble_ncov(const mb_ensemble* e);
+void ensemble_heavy(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_window& w, double* acc,
+                    cudaStream_t st);
+void ensemble_finish(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_spline* spline,
+                     const double* tps_surface_dev, const mb_window& w, const double* acc, double* out_dev,
+                     cudaStream_t st);
 void ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X, int n, double* out_host);
 
 // tiles.cu - mltps part 3/4 (V73:649-895), machisplin.tiles.merge (V73:1392-1548), gram, gather
@@ -25,6 +33,6 @@ void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window*
                  const double* const* tiles_dev, double* out_dev, cudaStream_t st);
 void gram(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, cudaStream_t st);
 void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row, const int32_t* col,
-                  int n, double* out_host);
+                  int n, double* out_host, cudaStream_t st);
 
 }  // namespace mb

@@ -177,10 +177,11 @@ void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window*
     for (int h = 0; h + 1 < nC; ++h) add_seam(j * nC + h, j * nC + h + 1, 0);
   for (int j = 0; j + 1 < nR; ++j)
     for (int h = 0; h < nC; ++h) add_seam(j * nC + h, (j + 1) * nC + h, 1);
-  DevBuf<TileDesc> d_tiles;
-  DevBuf<SeamDesc> d_seams;
-  DevBuf<int2> d_col, d_row;
-  DevBuf<int> d_bbox((size_t)4 * std::max<size_t>(1, seams.size()));
+  Arena& ar = ctx->arena;
+  ABuf<TileDesc> d_tiles(ar);
+  ABuf<SeamDesc> d_seams(ar);
+  ABuf<int2> d_col(ar), d_row(ar);
+  ABuf<int> d_bbox(ar, (size_t)4 * std::max<size_t>(1, seams.size()));
   d_tiles.upload(td, st);
   d_col.upload(colcand, st);
   d_row.upload(rowcand, st);
@@ -200,7 +201,7 @@ void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window*
                                      g.xmin, g.ymax, rx, ry, g.nrow, g.ncol, out_dev);
   (void)nh;
   MB_CUDA(cudaGetLastError());
-  MB_CUDA(cudaStreamSynchronize(st));   // descriptor buffers are stream-ordered temporaries
+  MB_CUDA(cudaStreamSynchronize(st));   // descriptor uploads come from host vectors that die here
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,7 +243,7 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
   }
   const int nt = nRx * nCx;
   std::vector<mb_window> keep(nt);
-  std::vector<DevBuf<double>> bufs(nt);
+  std::vector<double*> bufs(nt);
   std::vector<const double*> ptrs(nt);
   std::vector<double> txy, ty;
   for (int j = 1; j <= nRx; ++j)
@@ -268,10 +269,10 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
         }
       const int m = (int)ty.size();
       const size_t cells = (size_t)(kw.r1 - kw.r0) * (kw.c1 - kw.c0);
-      bufs[t].alloc(cells);
-      ptrs[t] = bufs[t].p;
+      bufs[t] = ctx->arena.take_n<double>(cells);
+      ptrs[t] = bufs[t];
       if (m < min_pts) {                                                                     // V73:710-721
-        MB_LAUNCH(ctx, "k_fill", st) k_fill<<<256, 256, 0, st>>>(bufs[t].p, (int64_t)cells, 0.0);
+        MB_LAUNCH(ctx, "k_fill", st) k_fill<<<256, 256, 0, st>>>(bufs[t], (int64_t)cells, 0.0);
         continue;
       }
       txy.resize((size_t)2 * m);
@@ -280,7 +281,7 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
       mb_spline* sp = nullptr;
       tps_fit(ctx, txy.data(), ty.data(), m, 1, lambda, &sp);                                 // V73:722
       std::unique_ptr<mb_spline> hold(sp);
-      eval(sp, kw, bufs[t].p);                                                               // V73:726-728
+      eval(sp, kw, bufs[t]);                                                               // V73:726-728
       MB_CUDA(cudaStreamSynchronize(st));
     }
   tiles_merge(ctx, g, nCx, nRx, keep.data(), ptrs.data(), out_dev, st);                       // V73:739-895
@@ -333,12 +334,11 @@ __global__ void k_gram_final(const double* __restrict__ part, int nblocks, int K
 }
 
 void gram(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, cudaStream_t st) {
-  DevBuf<double> part((size_t)kGramBlocks * 36);
+  ABuf<double> part(ctx->arena, (size_t)kGramBlocks * 36);
   const int blocks = std::min(kGramBlocks, (n + 255) / 256);
   MB_LAUNCH(ctx, "k_gram_partial", st) k_gram_partial<<<blocks, 256, 0, st>>>(R_dev, n, K, part.p);
   MB_LAUNCH(ctx, "k_gram_final", st) k_gram_final<<<1, 64, 0, st>>>(part.p, blocks, K, G_dev);
   MB_CUDA(cudaGetLastError());
-  MB_CUDA(cudaStreamSynchronize(st));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -351,11 +351,10 @@ __global__ void k_gather(const double* __restrict__ ras, int64_t stride, const i
 }
 
 void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row, const int32_t* col,
-                  int n, double* out_host) {
+                  int n, double* out_host, cudaStream_t st) {
   if (n <= 0) return;
-  cudaStream_t st = ctx->stream;
-  DevBuf<int> dr(n), dc(n);
-  DevBuf<double> dout(n);
+  ABuf<int> dr(ctx->arena, n), dc(ctx->arena, n);
+  ABuf<double> dout(ctx->arena, n);
   dr.upload(row, n, st);
   dc.upload(col, n, st);
   MB_LAUNCH(ctx, "k_gather", st) k_gather<<<(n + 255) / 256, 256, 0, st>>>(raster_dev, row_stride, dr.p, dc.p, n, dout.p);

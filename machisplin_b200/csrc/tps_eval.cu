@@ -12,6 +12,7 @@
 //                    directly.  Everything is float64: the coefficients c cancel by up to 1e8
 //                    (T'c = 0), so float32 pair terms are not accurate enough.
 #include "common.cuh"
+#include "ens_device.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -142,7 +143,7 @@ void spline_finalize(mb_ctx* ctx, mb_spline* s) {
   s->sum_abs_c = 0;
   for (double v : s->c) s->sum_abs_c += std::fabs(v);
   // fscale = max |f(knot)|: sets the accuracy target of the fast evaluator
-  DevBuf<double> dx(s->np), dy(s->np), df(s->np);
+  ABuf<double> dx(ctx->arena, s->np), dy(ctx->arena, s->np), df(ctx->arena, s->np);
   dx.upload(s->kx, st);
   dy.upload(s->ky, st);
   tps_predict_points_dev(ctx, s, dx.p, dy.p, s->np, df.p, st);
@@ -337,31 +338,81 @@ __global__ void __launch_bounds__(((P * P + 31) / 32) * 32) k_far_transform(
 }
 
 // -----------------------------------------------------------------------------------------
-// Leaf kernel: one CTA per leaf box (32 columns x bh rows).  lane = column.
-//   G[lr][k] = sum_j T_j(ty_lr) A[j][k]          (collapse y once per box row)
+// Accuracy estimate of the mixed-precision leaf path (one warp per leaf box, max over boxes):
+//   far : the k >= 1 columns of the expansion are evaluated in float32 -> (P + 2) 2^-24 sum_{(j,k) != (0,0)} |A_jk|
+//   near: pair terms in float32 with box-local coordinates      -> 4 2^-24 phi(r_max) sum_{3x3} |c_i E/2|
+// k_leaf compares the estimate with its threshold and picks the float64 or the mixed code path itself,
+// so the decision costs no host round trip.
+// -----------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256) k_leaf_bounds(Lattice lat, LevelInfo leaf, const double* __restrict__ coef,
+                                                     const int* __restrict__ start, const double4* __restrict__ knots,
+                                                     double phi_max, unsigned long long* __restrict__ est_bits) {
+  const int lane = threadIdx.x & 31;
+  const int box = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (box >= leaf.nI * leaf.nJ) return;
+  const double* A = coef + leaf.coef_off + (size_t)box * (P * P);
+  double v = 0.0;
+  for (int i = 1 + lane; i < P * P; i += 32) v += fabs(A[i]);
+  double wsum = 0.0;
+  if (lane < 9) {
+    const int I = lat.offx + box % leaf.nI + lane % 3 - 1, J = lat.offy + box / leaf.nI + lane / 3 - 1;
+    const int nside = 1 << lat.L;
+    if (I >= 0 && J >= 0 && I < nside && J < nside) {
+      const uint32_t z = morton(I, J);
+      for (int k = start[z]; k < start[z + 1]; ++k) wsum += fabs(knots[k].w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  }
+  if (lane == 0) {
+    const double est = 5.9604644775390625e-08 * ((P + 2) * v + 4.0 * phi_max * wsum);
+    atomicMax(est_bits, (unsigned long long)__double_as_longlong(est));   // est >= 0: bit order = value order
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// Leaf kernel (the grid-evaluation kernel): one CTA per leaf box (32 columns x bh rows), lane = column.
+//   G[lr][k] = sum_j T_j(ty_lr) A[j][k]          (collapse y once per box row, float64)
 //   far      = sum_k G[lr][k] T_k(tx_lane)       (T_k(tx_lane) lives in registers)
-//   near     = sum over knots of the 3 x 3 neighbourhood, float64, table log
+//   near     = sum over the knots of the 3 x 3 box neighbourhood
+// Two code paths, chosen per launch from the device-side estimate above:
+//   float64  everything in float64 with the table-driven log (always correct)
+//   mixed    G[lr][0] in float64; the k >= 1 columns (the variation of the far field inside the box)
+//            and the near pair terms in float32 with box-local coordinates and MUFU.LG2.  The large,
+//            cancelling part of the sum never leaves float64, so the result keeps ~1e-9 relative accuracy
+//            while the per-cell float64 work drops from ~30 to 2 operations: the kernel becomes a pure
+//            HBM-write stream (8 B / cell).
+// With an EnsFuse descriptor the same pass finishes mltps part 2 + 5: covariates -> gam / nnet / earth,
+// + trees / svm accumulator, / total weight, NA rule, + TPS (V73:604-620, 906-907).
 // -----------------------------------------------------------------------------------------
 constexpr int kLeafThreads = 256;
 constexpr int kNearCap = 256;
 
-template <int P>
+template <int P, bool kFuse>
 __global__ void __launch_bounds__(kLeafThreads) k_leaf(
     Lattice lat, LevelInfo leaf, mb_window w, const double* __restrict__ coef, const int* __restrict__ start,
-    const double4* __restrict__ knots, const double2* __restrict__ logtab, double* __restrict__ out,
-    int64_t stride) {
+    const double4* __restrict__ knots, const double2* __restrict__ logtab,
+    const unsigned long long* __restrict__ est_bits, double mixed_threshold, EnsFuse fz,
+    double* __restrict__ out, int64_t stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* s_log = reinterpret_cast<double2*>(smem_raw);              // 256
   double4* s_near = reinterpret_cast<double4*>(s_log + 256);          // kNearCap
   double* s_A = reinterpret_cast<double*>(s_near + kNearCap);         // P*P
-  double* s_G = s_A + P * P;                                          // bh*P
+  double* s_G = s_A + P * P;                                          // bh*P (float64 path) | bh (mixed: column 0)
+  float* s_Gf = reinterpret_cast<float*>(s_G + lat.bh * P);           // bh*(P-1) (mixed path)
   __shared__ int s_rng[9][2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bi = blockIdx.x, bj = blockIdx.y;
   const int I = lat.offx + bi, J = lat.offy + bj;
   const int box = bj * leaf.nI + bi;   // leaf level: I0 = offx, J0 = offy
-  for (int i = tid; i < 256; i += kLeafThreads) s_log[i] = logtab[i];
+  const bool mixed = __longlong_as_double((long long)__ldg(est_bits)) <= mixed_threshold;
+  if (!mixed)
+    for (int i = tid; i < 256; i += kLeafThreads) s_log[i] = logtab[i];
   for (int i = tid; i < P * P; i += kLeafThreads) s_A[i] = coef[leaf.coef_off + (size_t)box * (P * P) + i];
   if (tid < 9) {
     const int i = I + tid % 3 - 1, j = J + tid / 3 - 1;
@@ -374,15 +425,6 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf(
     }
     s_rng[tid][0] = a;
     s_rng[tid][1] = b;
-  }
-  // T_k(tx) of this lane's column: identical for every box
-  double Tx[P];
-  {
-    const double tx = (2.0 * lane + 1.0) / 32.0 - 1.0;
-    Tx[0] = 1.0;
-    if (P > 1) Tx[1] = tx;
-#pragma unroll
-    for (int k = 2; k < P; ++k) Tx[k] = 2.0 * tx * Tx[k - 1] - Tx[k - 2];
   }
   __syncthreads();
   // collapse y: thread -> (lr, k)
@@ -397,15 +439,103 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf(
       g = fma(t2, s_A[j * P + k], g);
       t0 = t1; t1 = t2;
     }
-    s_G[o] = g;
+    if (!mixed) s_G[o] = g;
+    else if (k == 0) s_G[lr] = g;
+    else s_Gf[lr * (P - 1) + (k - 1)] = (float)g;
   }
   int tot = 0;
 #pragma unroll
   for (int r = 0; r < 9; ++r) tot += s_rng[r][1] - s_rng[r][0];
   const int col = w.c0 + bi * 32 + lane;
-  const double sx = lat.sxo + lat.hx * (I + (lane + 0.5) / 32.0);
   const int row_base = w.r0 + bj * lat.bh;
   constexpr int kWarps = kLeafThreads / 32;
+  // per-cell epilogue: plain store, or the fused ensemble combine
+  auto finish = [&](int row, double tps, double* dst) {
+    if (!kFuse) { *dst = tps; return; }
+    double x[16];
+    bool anynan = false;
+    for (int f = 0; f < fz.C; ++f) {
+      const float v = __ldg(&fz.cov[f * fz.plane + (int64_t)row * fz.eg.ncol + col]);
+      anynan |= (v != v);
+      x[f] = (double)v;
+    }
+    x[fz.C] = fz.eg.xmin + (col + 0.5) * fz.eg.rx;
+    x[fz.C + 1] = fz.eg.ymax - (row + 0.5) * fz.eg.ry;
+    double s = fz.acc ? fz.acc[(int64_t)(row - w.r0) * (w.c1 - w.c0) + (col - w.c0)] : 0.0;
+    if (!anynan) s += smooth_models(x, fz.C + 2, fz.sp);
+    double r = s / fz.sp.w_total;
+    if (anynan && !fz.sp.only_gbm) r = __longlong_as_double(0x7ff8000000000000LL);
+    *dst = r + tps;
+  };
+  if (mixed) {
+    // ---- mixed path ----------------------------------------------------------------------------
+    float Txf[P];
+    {
+      const float tx = (2.0f * lane + 1.0f) / 32.0f - 1.0f;   // exact in float32
+      Txf[0] = 1.0f;
+      if (P > 1) Txf[1] = tx;
+#pragma unroll
+      for (int k = 2; k < P; ++k) Txf[k] = 2.0f * tx * Txf[k - 1] - Txf[k - 2];
+    }
+    float4* s_nf = reinterpret_cast<float4*>(s_near);     // box-local (x, y, c E/2 ln2, -)
+    const double ox = lat.sxo + lat.hx * I, oy = lat.syo + lat.hy * J;
+    const float cxl = (float)(lat.hx * ((lane + 0.5) / 32.0));
+    int base = 0;
+    do {
+      const int n = min(2 * kNearCap, tot - base);
+      __syncthreads();
+      for (int i = tid; i < n; i += kLeafThreads) {
+        int f = base + i, idx = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const int len = s_rng[r][1] - s_rng[r][0];
+          if (f >= 0 && f < len) idx = s_rng[r][0] + f;
+          f -= len;
+        }
+        const double4 kn = ldg4(&knots[idx]);
+        s_nf[i] = make_float4((float)(kn.x - ox), (float)(kn.y - oy), (float)(kn.w * 0.69314718055994531), 0.f);
+      }
+      __syncthreads();
+      for (int lr = warp; lr < lat.bh; lr += kWarps) {
+        const int row = row_base + lr;
+        if (row >= w.r1) break;
+        const float cyl = (float)(lat.hy * ((lr + 0.5) / lat.bh));
+        double* dst = out + (int64_t)(row - w.r0) * stride + (col - w.c0);
+        float a = 0.f;
+        if (base == 0) {
+#pragma unroll
+          for (int k = 1; k < P; ++k) a = fmaf(s_Gf[lr * (P - 1) + (k - 1)], Txf[k], a);
+        }
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+          const float4 kn = s_nf[i];
+          const float dx = cxl - kn.x, dy = cyl - kn.y;
+          const float r2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-20f);
+          a = fmaf(kn.z * r2, __log2f(r2), a);
+        }
+        if (col < w.c1) {
+          if (base + n >= tot) {
+            const double tps = (base == 0 ? s_G[lr] : *dst) + (double)a;
+            finish(row, tps, dst);
+          } else {
+            *dst = (base == 0 ? s_G[lr] : *dst) + (double)a;
+          }
+        }
+      }
+      base += 2 * kNearCap;
+    } while (base < tot);
+    return;
+  }
+  // ---- float64 path ------------------------------------------------------------------------------
+  double Tx[P];
+  {
+    const double tx = (2.0 * lane + 1.0) / 32.0 - 1.0;
+    Tx[0] = 1.0;
+    if (P > 1) Tx[1] = tx;
+#pragma unroll
+    for (int k = 2; k < P; ++k) Tx[k] = 2.0 * tx * Tx[k - 1] - Tx[k - 2];
+  }
+  const double sx = lat.sxo + lat.hx * (I + (lane + 0.5) / 32.0);
   // knots of the 3 x 3 neighbourhood are streamed through shared memory kNearCap at a time;
   // one chunk is the common case (about one knot per box).
   int base = 0;
@@ -442,7 +572,10 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf(
         const double r2 = fmax(fma(dx, dx, dy * dy), kD2Clamp);
         a = fma(kn.w * r2, tlog(r2, s_log), a);
       }
-      if (col < w.c1) *dst = a;
+      if (col < w.c1) {
+        if (base + n >= tot) finish(row, a, dst);
+        else *dst = a;
+      }
     }
     base += kNearCap;
   } while (base < tot);
@@ -462,45 +595,72 @@ static int choose_p(const mb_ctx* ctx, const mb_spline* s) {
   return 16;
 }
 
+struct FastPlan {
+  Lattice lat;
+  LevelInfo leaf;
+  const double* coef;
+  const int* start;
+  const double4* knots;
+  const unsigned long long* est_bits;
+  double mixed_threshold;
+};
+
 template <int P>
 static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const std::vector<LevelInfo>& levels,
                      size_t coef_total, size_t part_total, const std::vector<int>& start,
                      const std::vector<double4>& sorted, const mb_window& w, double* out, int64_t stride,
-                     cudaStream_t st) {
+                     const EnsFuse* fuse, cudaStream_t st) {
   ChebTables* tabs = get_tables(ctx, P);
-  DevBuf<int> d_start;
-  DevBuf<double4> d_knots;
-  DevBuf<double> d_coef(coef_total), d_part(part_total);
-  d_start.upload(start, st);
-  d_knots.upload(sorted, st);
+  Arena& ar = ctx->arena;
+  const int* d_start = ar.upload(start.data(), start.size(), st);
+  const double4* d_knots = ar.upload(sorted.data(), sorted.size(), st);
+  double* d_coef = ar.take_n<double>(coef_total);
+  double* d_part = ar.take_n<double>(part_total);
+  unsigned long long* d_est = ar.take_n<unsigned long long>(1);
   constexpr int threads = ((P * P + 31) / 32) * 32;
   for (size_t li = 0; li < levels.size(); ++li) {
     const LevelInfo& lv = levels[li];
     dim3 grid(lv.nI * lv.nJ, lv.nsplit);
-    MB_LAUNCH(ctx, "k_far_p2l", st) k_far_p2l<P><<<grid, threads, 0, st>>>(lat, lv, tabs->d_tab.p, d_start.p, d_knots.p, ctx->logtab.p, d_part.p);
+    MB_LAUNCH(ctx, "k_far_p2l", st) k_far_p2l<P><<<grid, threads, 0, st>>>(lat, lv, tabs->d_tab.p, d_start, d_knots, ctx->logtab.p, d_part);
     const LevelInfo& par = li ? levels[li - 1] : lv;
-    MB_LAUNCH(ctx, "k_far_transform", st) k_far_transform<P><<<lv.nI * lv.nJ, threads, 0, st>>>(lat, lv, par, li ? 1 : 0, tabs->d_tab.p, d_part.p,
-                                                           d_coef.p, s->d[0], s->d[1], s->d[2]);
+    MB_LAUNCH(ctx, "k_far_transform", st) k_far_transform<P><<<lv.nI * lv.nJ, threads, 0, st>>>(lat, lv, par, li ? 1 : 0, tabs->d_tab.p, d_part,
+                                                           d_coef, s->d[0], s->d[1], s->d[2]);
   }
   MB_CUDA(cudaGetLastError());
   const LevelInfo& leaf = levels.back();
-  const size_t smem = 256 * sizeof(double2) + kNearCap * sizeof(double4) +
-                      sizeof(double) * (P * P + (size_t)lat.bh * P);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    MB_CUDA(cudaFuncSetAttribute(k_leaf<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
+  // mixed-precision decision (device side).  Explicit cheb_p / eval_precision = 1 force float64.
+  double thr = 2e-8 * std::max(s->fscale, 1e-300);
+  const double r2max = 4.0 * (lat.hx * lat.hx + lat.hy * lat.hy);
+  if (ctx->eval_precision == 1 || (ctx->eval_precision == 0 && ctx->cheb_p != 0) || r2max >= 0.3) thr = -1.0;
+  if (ctx->eval_precision == 2) thr = 1e300;
+  MB_CUDA(cudaMemsetAsync(d_est, 0, sizeof(unsigned long long), st));
+  if (thr > 0 && thr < 1e300) {
+    const double phi_max = r2max * std::fabs(std::log(r2max));
+    MB_LAUNCH(ctx, "k_leaf_bounds", st) k_leaf_bounds<P><<<(leaf.nI * leaf.nJ + 7) / 8, 256, 0, st>>>(lat, leaf, d_coef, d_start, d_knots, phi_max, d_est);
   }
+  const size_t smem = 256 * sizeof(double2) + kNearCap * sizeof(double4) +
+                      sizeof(double) * (P * P + (size_t)lat.bh * P) + sizeof(float) * (size_t)lat.bh * (P - 1);
   dim3 grid(lat.nbx, lat.nby);
-  MB_LAUNCH(ctx, "k_leaf", st) k_leaf<P><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef.p, d_start.p, d_knots.p, ctx->logtab.p, out,
-                                              stride);
+  if (fuse) {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+      MB_CUDA(cudaFuncSetAttribute(k_leaf<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_set = true;
+    }
+    MB_LAUNCH(ctx, "k_leaf_fused", st) k_leaf<P, true><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_start, d_knots, ctx->logtab.p, d_est, thr, *fuse, out, stride);
+  } else {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+      MB_CUDA(cudaFuncSetAttribute(k_leaf<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_set = true;
+    }
+    MB_LAUNCH(ctx, "k_leaf", st) k_leaf<P, false><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_start, d_knots, ctx->logtab.p, d_est, thr, EnsFuse{}, out, stride);
+  }
   MB_CUDA(cudaGetLastError());
-  // the plan buffers are stream-ordered temporaries: wait before they are released
-  MB_CUDA(cudaStreamSynchronize(st));
 }
 
 void tps_eval_fast(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
-                   int64_t stride, cudaStream_t st) {
+                   int64_t stride, cudaStream_t st, const EnsFuse* fuse) {
   const GridAffine a = make_affine(g, *s);
   const int P = choose_p(ctx, s);
   const double ax = a.rx / a.scx, ay = -a.ry / a.scy;
@@ -571,11 +731,11 @@ void tps_eval_fast(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_w
     levels.push_back(lv);
   }
   switch (P) {
-    case 8:  run_fast<8>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
-    case 10: run_fast<10>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
-    case 12: run_fast<12>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
-    case 14: run_fast<14>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
-    case 16: run_fast<16>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, st); break;
+    case 8:  run_fast<8>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, fuse, st); break;
+    case 10: run_fast<10>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, fuse, st); break;
+    case 12: run_fast<12>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, fuse, st); break;
+    case 14: run_fast<14>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, fuse, st); break;
+    case 16: run_fast<16>(ctx, s, lat, levels, coef_total, part_total, start, sorted, w, out, stride, fuse, st); break;
     default: throw Error(MB_E_ARG, "cheb_p must be one of 8, 10, 12, 14, 16");
   }
 }

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ 
 static void cholesky_lower(mb_ctx* ctx, double* A, int ld, int m, cudaStream_t st) {
   constexpr size_t kSyrkSmem = 2 * kNB * (kNB + 4) * sizeof(double);
   MB_CUDA(cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
-  DevBuf<int> d_info(1);
+  ABuf<int> d_info(ctx->arena, 1);
   MB_CUDA(cudaMemsetAsync(d_info.p, 0, sizeof(int), st));
   for (int k = 0; k < m; k += kNB) {
     const int kb = std::min(kNB, m - k);
@@ -542,7 +542,9 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
   QRT qr(T, np);
   const int m = np - 3;
   // ---- device: K, projection ------------------------------------------------------------------------
-  DevBuf<double> d_sx, d_sy, d_w2, d_K((size_t)np * np), d_v(np), d_p(np), d_q(np), d_part((size_t)kGemvChunks * np);
+  Arena& ar = ctx->arena;   // no cudaMalloc / cudaFree here: the fit overlaps the ensemble kernels of another stream
+  ABuf<double> d_sx(ar), d_sy(ar), d_w2(ar), d_K(ar, (size_t)np * np), d_v(ar, np), d_p(ar, np), d_q(ar, np),
+      d_part(ar, (size_t)kGemvChunks * np);
   d_sx.upload(sx, st);
   d_sy.upload(sy, st);
   d_w2.upload(w2, st);
@@ -557,11 +559,9 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
   }
   MB_CUDA(cudaGetLastError());
   // M = Q2' W^1/2 K W^1/2 Q2 = rows/cols 3.. of the reflected matrix, compacted to a 16-byte aligned m x m block
-  DevBuf<double> d_M((size_t)m * m);
+  ABuf<double> d_M(ar, (size_t)m * m);
   MB_CUDA(cudaMemcpy2DAsync(d_M.p, sizeof(double) * m, d_K.p + (size_t)3 * np + 3, sizeof(double) * np,
                             sizeof(double) * m, m, cudaMemcpyDeviceToDevice, st));
-  MB_CUDA(cudaStreamSynchronize(st));
-  d_K.release();
   double* M = d_M.p;
 
   // z_r = Q2' sqrt(w) yM_r
@@ -581,13 +581,13 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
   if (lambda < 0) {
     // ---- eigen(M): cuSOLVER Dsyevd (library stand-in, see file header) -----------------------------
     FitLibs& lb = libs(ctx);
-    DevBuf<double> d_eta(m);
-    DevBuf<int> d_info(1);
+    ABuf<double> d_eta(ar, m);
+    ABuf<int> d_info(ar, 1);
     int lwork = 0;
     if (cusolverDnDsyevd_bufferSize(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p,
                                     &lwork) != CUSOLVER_STATUS_SUCCESS)
       throw Error(MB_E_CUDA, "cusolverDnDsyevd_bufferSize failed");
-    DevBuf<double> d_work((size_t)lwork);
+    ABuf<double> d_work(ar, (size_t)lwork);
     cusolverStatus_t cs = CUSOLVER_STATUS_SUCCESS;
     MB_LAUNCH(ctx, "cusolverDnDsyevd", st)
       cs = cusolverDnDsyevd(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p, d_work.p,
@@ -605,7 +605,7 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     for (int k = 0; k < m; ++k) D[3 + k] = 1.0 / eta[m - 1 - k];
     eta_desc.assign(eta.rbegin(), eta.rend());
     const std::vector<double> grid = gcv::lambda_grid(D);
-    DevBuf<double> d_z(m), d_u(m), d_g(m), d_beta(m);
+    ABuf<double> d_z(ar, m), d_u(ar, m), d_g(ar, m), d_beta(ar, m);
     for (int r = 0; r < L; ++r) {
       d_z.upload(z[r], st);
       MB_LAUNCH(ctx, "k_gemv_t", st) k_gemv_t<<<(m + 7) / 8, 256, 0, st>>>(M, m, m, m, d_z.p, d_u.p);   // u = V' z (ascending order)
@@ -628,7 +628,7 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     // ---- fixed lambda: (M + lambda I) beta = z by tensor-core Cholesky ------------------------------
     MB_LAUNCH(ctx, "k_add_diag", st) k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(M, m, m, lambda);
     cholesky_lower(ctx, M, m, m, st);
-    DevBuf<double> d_B((size_t)m * L);
+    ABuf<double> d_B(ar, (size_t)m * L);
     for (int r = 0; r < L; ++r)
       MB_CUDA(cudaMemcpyAsync(d_B.p + (size_t)r * m, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
     MB_LAUNCH(ctx, "k_chol_solve", st) k_chol_solve<<<1, 1024, 0, st>>>(M, m, m, d_B.p, m, L);
@@ -657,7 +657,7 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     // K c through the evaluation kernel with d = 0 (K was overwritten by the projection)
     s->ctx = ctx;
     s->d_sx.upload(s->sx, st); s->d_sy.upload(s->sy, st); s->d_c.upload(s->c, st);
-    DevBuf<double> d_kx, d_ky, d_kc(np);
+    ABuf<double> d_kx(ar), d_ky(ar), d_kc(ar, np);
     d_kx.upload(kx, st); d_ky.upload(ky, st);
     tps_predict_points_dev(ctx, s.get(), d_kx.p, d_ky.p, np, d_kc.p, st);
     std::vector<double> Kc(np);

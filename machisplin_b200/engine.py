@@ -238,6 +238,9 @@ class Engine:
     def set_fast_eval_params(self, cheb_p=0, leaf_cols=0, leaf_rows=0):
         check(self.lib.mb_set_fast_eval_params(self._h, cheb_p, leaf_cols, leaf_rows))
 
+    def set_param(self, name: str, value: int):
+        check(self.lib.mb_set_param(self._h, name.encode(), int(value)))
+
     # -- a1: fields::Tps ---------------------------------------------------------------------------
     def tps_fit(self, xy, y, lam: Optional[float] = None):
         """``fields::Tps(xy, y)`` (V73:722, 751).  y may be (n,) or (n, L); returns Spline or list."""
