@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lam", type=float, default=None, help="fixed lambda (Cholesky path) instead of GCV")
+    ap.add_argument("--tree-rows", type=int, default=0, help="forest tile: cells per thread (1, 2, 4; 0 = auto)")
+    ap.add_argument("--eval-precision", type=int, default=0, help="leaf kernel path: 0 auto, 1 float64, 2 mixed")
     return ap.parse_args()
 
 
@@ -287,6 +289,8 @@ def run_b200(args):
     cfg = workload(args)
     geom, xy, krow, kcol, resid, models, kept, w, wt = build_inputs(cfg, rank)
     eng = mb.Engine(local)
+    eng.set_param("tree_rows", args.tree_rows)
+    eng.set_param("eval_precision", args.eval_precision)
     C = cfg["C"]
     P = C + 2
     cov = device_covariates(geom, C, dev) if C else torch.zeros((0,), device=dev)
@@ -304,12 +308,10 @@ def run_b200(args):
         if world > 1:
             g = torch.from_numpy(G).to(dev)
             dist.all_reduce(g)
-        sp = eng.tps_fit(xy, resid, lam=args.lam)
-        if ens is not None:
-            eng.ensemble_eval_dev(ens, cov.data_ptr(), C, out.data_ptr(), spline=sp, stream=stream)
-        else:
-            eng.tps_eval_dev(sp, geom, out.data_ptr(), geom.ncol, method="fast", stream=stream)
-        f_actual = eng.gather_cells_dev(out.data_ptr(), geom.ncol, krow, kcol)
+        # parts 2-5 (V73:442-932): ensemble kernels || fields::Tps fit, then the fused per-cell pass
+        sp = eng.mltps_predict_dev(geom, ens, cov.data_ptr() if C else 0, C, xy, resid, out.data_ptr(), lam=args.lam,
+                                   stream=stream)
+        f_actual = eng.gather_cells_dev(out.data_ptr(), geom.ncol, krow, kcol, stream=stream)
         state["sp"], state["f_actual"] = sp, f_actual
         return f_actual
 
@@ -352,29 +354,24 @@ def run_b200(args):
     # ---- e2e: pinned host inputs -> device -> result back to pinned host ---------------------------
     e2e = None
     if not args.no_e2e:
+        # the call a user (the R shim) makes: host buffers in, host raster out, through the C ABI
         h_cov = torch.empty(cov.shape, dtype=torch.float32, pin_memory=True)
         h_cov.copy_(cov)
         h_out = torch.empty(out.shape, dtype=torch.float64, pin_memory=True)
-        d_cov = torch.empty_like(cov)
+        cov_np = h_cov.numpy() if C else None
+        out_np = h_out.numpy()
 
         def step_e2e():
-            d_cov.copy_(h_cov, non_blocking=True)
             ens2 = eng.ensemble_create(geom, models, kept, w, wt, P) if kept else None   # descriptor upload + tree packing
-            sp = eng.tps_fit(xy, resid, lam=args.lam)
-            if ens2 is not None:
-                eng.ensemble_eval_dev(ens2, d_cov.data_ptr(), C, out.data_ptr(), spline=sp, stream=stream)
-            else:
-                eng.tps_eval_dev(sp, geom, out.data_ptr(), geom.ncol, method="fast", stream=stream)
-            h_out.copy_(out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return h_out[krow, kcol]
+            eng.mltps_predict(geom, ens2, cov_np, xy, resid, lam=args.lam, out=out_np)
+            return out_np[krow, kcol]
 
         step_e2e()
         ms_e2e = timed(step_e2e, max(1, args.steps))
         e2e = {"value": world * cells / (ms_e2e * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h_cov.numel() * 4 + xy.nbytes + resid.nbytes),
                "d2h_bytes_per_step": int(h_out.numel() * 8)}
-        del h_cov, d_cov
+        del h_cov
 
     if rank != 0:
         if world > 1:
@@ -385,8 +382,10 @@ def run_b200(args):
     peak, peak_src = measured_peak()
     kern = {}
     tot_ms = sum(v[0] for v in ktimes.values()) or 1.0
-    bytes_per_cell = {"k_leaf": 8.0, "k_ens_final": 4.0 * C + 8.0 + 8.0 + (8.0 if kept and set(kept) & set("brv") else 0.0),
-                      "k_ens_trees": 4.0 * C + 16.0, "k_ens_svm": 4.0 * C + 16.0}
+    heavy = bool(kept) and bool(set(kept) & set("brv"))
+    bytes_per_cell = {"k_leaf": 8.0, "k_leaf_fused": 4.0 * C + 8.0 + (8.0 if heavy else 0.0),
+                      "k_ens_final": 4.0 * C + 8.0 + 8.0 + (8.0 if heavy else 0.0),
+                      "k_ens_trees": 4.0 * C + 8.0, "k_ens_svm": 4.0 * C + 16.0}
     for name, (tms, cnt) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
         per_launch = tms / max(cnt, 1)
         ent = {"ms_per_step": tms / args.steps, "launches_per_step": cnt / args.steps, "share": tms / tot_ms}
@@ -394,10 +393,13 @@ def run_b200(args):
             gbs = cells * bytes_per_cell[name] / (per_launch * 1e-3) / 1e9
             ent.update({"algorithmic_bytes_per_cell": bytes_per_cell[name], "achieved_gbs": gbs, "hbm_frac": gbs / peak})
         kern[name] = ent
-    leaf = kern.get("k_leaf", {})
-    roofline = {"kernel": "k_leaf (per-cell TPS evaluation)", "bound": "hbm", "achieved": leaf.get("achieved_gbs"),
+    lname = "k_leaf_fused" if "k_leaf_fused" in kern else "k_leaf"
+    leaf = kern.get(lname, {})
+    roofline = {"kernel": f"{lname} (grid-evaluation kernel: per-cell TPS surface" +
+                          (" + smooth models + ensemble combine)" if lname == "k_leaf_fused" else ")"),
+                "bound": "hbm", "achieved": leaf.get("achieved_gbs"),
                 "peak": peak, "unit": "GB/s", "frac": leaf.get("hbm_frac"), "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_cell": 8.0,
+                "algorithmic_bytes_per_cell": bytes_per_cell[lname],
                 "note": "roofline of the north-star kernel; `kernels` lists every kernel of the step with its share"}
 
     # ---- parity + CPU baseline on a bounded row sample ---------------------------------------------------

@@ -6,5 +6,7 @@ The compute lives in ``libmachisplin_b200.so`` (hand-written sm_100a CUDA behind
 There is no CPU fallback: creating an Engine without the library or without a GPU raises.
 """
 from .engine import Engine, Geom, Spline, Ensemble, as_geom, EVAL_DIRECT, EVAL_FAST  # noqa: F401
+from .mltps import mltps_response, select_models, rss_objective_from_gram, knot_cells  # noqa: F401
+from .tiles import tiles_create, tiles_merge, crop_window  # noqa: F401
 
 __version__ = "0.1.0"

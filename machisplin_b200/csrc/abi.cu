@@ -41,8 +41,12 @@ int mb_init(int device, mb_ctx** out) {
     cudaDeviceProp prop;
     MB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    MB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    MB_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    // the fit is the critical path of mb_mltps_predict*: its stream outranks the one the bulk per-cell
+    // kernels run on, so its many small kernels are scheduled as soon as an SM frees up
+    int prio_lo = 0, prio_hi = 0;
+    MB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    MB_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+    MB_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo));
     MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     init_logtab(ctx.get());

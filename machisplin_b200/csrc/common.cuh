@@ -241,7 +241,8 @@ struct KernelTimer {
 #define MB_LAUNCH(ctx, name, st) for (mb::KernelTimer _kt(ctx, name, st), *_once = &_kt; _once; _once = nullptr)
 
 // implemented in tps_eval.cu
-void spline_finalize(mb_ctx* ctx, mb_spline* s);   // uploads, computes sum|c| and fscale
+// uploads, computes sum|c| and fscale = max |f(knot)| (evaluated on the device unless the caller knows it)
+void spline_finalize(mb_ctx* ctx, mb_spline* s, double fscale_known = -1.0);
 void tps_eval_direct(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
                      int64_t stride, cudaStream_t st);
 struct EnsFuse;   // ens_device.cuh

@@ -134,7 +134,7 @@ void tps_predict_points_dev(mb_ctx* ctx, const mb_spline* s, const double* x_dev
   MB_CUDA(cudaGetLastError());
 }
 
-void spline_finalize(mb_ctx* ctx, mb_spline* s) {
+void spline_finalize(mb_ctx* ctx, mb_spline* s, double fscale_known) {
   s->ctx = ctx;
   cudaStream_t st = ctx->stream;
   s->d_sx.upload(s->sx, st);
@@ -143,6 +143,7 @@ void spline_finalize(mb_ctx* ctx, mb_spline* s) {
   s->sum_abs_c = 0;
   for (double v : s->c) s->sum_abs_c += std::fabs(v);
   // fscale = max |f(knot)|: sets the accuracy target of the fast evaluator
+  if (fscale_known >= 0) { s->fscale = fscale_known; return; }
   ABuf<double> dx(ctx->arena, s->np), dy(ctx->arena, s->np), df(ctx->arena, s->np);
   dx.upload(s->kx, st);
   dy.upload(s->ky, st);

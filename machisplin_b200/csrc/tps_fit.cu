@@ -474,6 +474,54 @@ static double search(const std::vector<double>& D, const std::vector<double>& u,
 }  // namespace gcv
 
 // ---------------------------------------------------------------------------------------------
+// K3: fields' lambda grid on the device.  One CTA per grid point runs Krig.df.to.lambda for its
+// target df (x4 bracketing, then bisection.search on log lambda, <= 25 steps, |f| < 1e-5) with
+// trA(lambda) = sum_k 1 / (1 + lambda D_k) reduced in a fixed order (deterministic).  The 200
+// searches are independent, which is all the parallelism there is: ~15 000 O(np) trace evaluations
+// that cost ~35 ms of scalar host time at np = 5000 take < 1 ms here.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGcvThreads = 256;
+
+__device__ __forceinline__ double block_tr_a(double lam, const double* __restrict__ s_D, int np, double* s_red) {
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < np; k += kGcvThreads) acc += 1.0 / (1.0 + lam * s_D[k]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __syncthreads();                       // s_red may still be read by the previous evaluation
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int q = 0; q < kGcvThreads / 32; ++q) tot += s_red[q];
+  return tot;
+}
+
+__global__ void __launch_bounds__(kGcvThreads) k_gcv_grid(const double* __restrict__ D, int np, int nstep,
+                                                         double* __restrict__ grid, int* __restrict__ err) {
+  extern __shared__ double s_D[];
+  __shared__ double s_red[kGcvThreads / 32];
+  for (int k = threadIdx.x; k < np; k += kGcvThreads) s_D[k] = D[k];
+  __syncthreads();
+  const int g = blockIdx.x;
+  double df = 3.0 + (0.95 * np - 3.0) * g / (nstep - 1.0);
+  if (g == 0) df += 0.001;
+  double l1 = 1.0;
+  for (int k = 0; k < 25; ++k) { if (block_tr_a(l1, s_D, np, s_red) <= df) break; l1 *= 4.0; }
+  double l2 = 1.0;
+  for (int k = 0; k < 25; ++k) { if (block_tr_a(l2, s_D, np, s_red) >= df) break; l2 /= 4.0; }
+  double x1 = log(l1), x2 = log(l2);
+  const double f1 = block_tr_a(exp(x1), s_D, np, s_red) - df, f2 = block_tr_a(exp(x2), s_D, np, s_red) - df;
+  if (f1 > f2) { if (threadIdx.x == 0) *err = 1; return; }     // bisection.search: "f1 must be < f2"
+  for (int k = 0; k < 25; ++k) {
+    const double xm = (x1 + x2) / 2.0;
+    const double fm = block_tr_a(exp(xm), s_D, np, s_red) - df;
+    if (fm < 0) x1 = xm; else x2 = xm;
+    if (fabs(fm) < 1e-5) break;
+  }
+  if (threadIdx.x == 0) grid[g] = exp((x1 + x2) / 2.0);
+}
+
+// ---------------------------------------------------------------------------------------------
 // the fit
 // ---------------------------------------------------------------------------------------------
 static void gemv_n(mb_ctx* ctx, const double* A, int ld, int m, int n, const double* x, double* y, double* part,
@@ -604,7 +652,31 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     std::vector<double> D(np, 0.0);
     for (int k = 0; k < m; ++k) D[3 + k] = 1.0 / eta[m - 1 - k];
     eta_desc.assign(eta.rbegin(), eta.rend());
-    const std::vector<double> grid = gcv::lambda_grid(D);
+    // lambda grid: device kernel when D fits in shared memory, host loop otherwise
+    std::vector<double> grid;
+    const int nstep = 200;
+    if ((size_t)np * sizeof(double) <= 200 * 1024) {
+      ABuf<double> d_D(ar), d_grid(ar, nstep);
+      ABuf<int> d_err(ar, 1);
+      d_D.upload(D, st);
+      MB_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+      static thread_local bool attr = false;
+      if (!attr) {
+        MB_CUDA(cudaFuncSetAttribute(k_gcv_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+      }
+      MB_LAUNCH(ctx, "k_gcv_grid", st) k_gcv_grid<<<nstep, kGcvThreads, (size_t)np * sizeof(double), st>>>(d_D.p, np, nstep, d_grid.p, d_err.p);
+      MB_CUDA(cudaGetLastError());
+      grid.resize(nstep);
+      int gerr = 0;
+      MB_CUDA(cudaMemcpyAsync(grid.data(), d_grid.p, sizeof(double) * nstep, cudaMemcpyDeviceToHost, st));
+      MB_CUDA(cudaMemcpyAsync(&gerr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MB_CUDA(cudaStreamSynchronize(st));
+      if (gerr) throw Error(MB_E_NUMERIC, "bisection.search: f1 must be < f2");
+      std::sort(grid.begin(), grid.end());
+    } else {
+      grid = gcv::lambda_grid(D);
+    }
     ABuf<double> d_z(ar, m), d_u(ar, m), d_g(ar, m), d_beta(ar, m);
     for (int r = 0; r < L; ++r) {
       d_z.upload(z[r], st);
@@ -666,7 +738,10 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     std::vector<double> rhs(np);
     for (int k = 0; k < np; ++k) rhs[k] = w2[k] * (yM[r][k] - Kc[k]);
     qr.coef(rhs, s->d);
-    spline_finalize(ctx, s.get());
+    // f(x_k) = yM_k - lambda c_k / w_k at the knots (first block row of the Krig system): no evaluation needed
+    double fs = 0.0;
+    for (int k = 0; k < np; ++k) fs = std::max(fs, std::fabs(yM[r][k] - lam[r] * s->c[k] / wM[k]));
+    spline_finalize(ctx, s.get(), fs);
     res[r] = std::move(s);
   }
   for (int r = 0; r < L; ++r) out[r] = res[r].release();

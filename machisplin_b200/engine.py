@@ -373,11 +373,54 @@ class Engine:
         check(self.lib.mb_gram(self._h, _pd(R), n, K, _pd(G)))
         return G
 
-    def gather_cells_dev(self, raster_ptr: int, row_stride: int, row, col) -> np.ndarray:
+    def gather_cells_dev(self, raster_ptr: int, row_stride: int, row, col, stream: int = 0) -> np.ndarray:
         row = np.ascontiguousarray(row, dtype=np.int32)
         col = np.ascontiguousarray(col, dtype=np.int32)
         out = np.empty(row.size)
         check(self.lib.mb_gather_cells_dev(self._h, C.c_void_p(raster_ptr), row_stride,
                                            row.ctypes.data_as(_lib.PI32), col.ctypes.data_as(_lib.PI32), row.size,
-                                           _pd(out)))
+                                           _pd(out), C.c_void_p(stream)))
         return out
+
+    # -- mltps parts 2-5 in one call (V73:442-932) ---------------------------------------------------------
+    def _mltps_args(self, geom, ens, knots_xy, resid, lam, tile_px):
+        geom = as_geom(geom)
+        k = r = None
+        n = 0
+        if knots_xy is not None:
+            k = np.asfortranarray(np.asarray(knots_xy, dtype=np.float64))
+            r = _f64(resid)
+            n = k.shape[0]
+            assert k.shape == (n, 2) and r.shape == (n,)
+        return geom, k, r, n, (-1.0 if lam is None else float(lam)), int(tile_px)
+
+    def mltps_predict_dev(self, geom, ens: Optional[Ensemble], cov_ptr: int, Cn: int, knots_xy, resid, out_ptr: int,
+                          lam: Optional[float] = None, tile_px: int = 0, stream: int = 0, want_spline: bool = True):
+        """Ensemble raster prediction (part 2) overlapped with the TPS fit of the residuals (part 3), then the
+        fused surface + combine pass (parts 3-5).  Device pointers; asynchronous on ``stream`` after the fit."""
+        geom, k, r, n, lamv, tile_px = self._mltps_args(geom, ens, knots_xy, resid, lam, tile_px)
+        g = geom.c()
+        h = C.c_void_p()
+        check(self.lib.mb_mltps_predict_dev(self._h, C.byref(g), ens._h if ens is not None else None,
+                                            C.c_void_p(cov_ptr) if cov_ptr else None, Cn, _pd(k), _pd(r), n, lamv,
+                                            tile_px, C.c_void_p(out_ptr), C.byref(h) if want_spline else None,
+                                            C.c_void_p(stream)))
+        return Spline(self, h.value) if (want_spline and h.value) else None
+
+    def mltps_predict(self, geom, ens: Optional[Ensemble], cov: Optional[np.ndarray], knots_xy, resid,
+                      lam: Optional[float] = None, tile_px: int = 0, out: Optional[np.ndarray] = None):
+        """Host-buffer twin: cov (C, nrow, ncol) float32 in, (nrow, ncol) float64 out.  Returns (raster, Spline|None)."""
+        geom, k, r, n, lamv, tile_px = self._mltps_args(geom, ens, knots_xy, resid, lam, tile_px)
+        Cn = 0 if cov is None else cov.shape[0]
+        if cov is not None:
+            cov = np.ascontiguousarray(cov, dtype=np.float32)
+            assert cov.shape == (Cn, geom.nrow, geom.ncol)
+        if out is None:
+            out = np.empty((geom.nrow, geom.ncol))
+        assert out.shape == (geom.nrow, geom.ncol) and out.dtype == np.float64 and out.flags.c_contiguous
+        g = geom.c()
+        h = C.c_void_p()
+        check(self.lib.mb_mltps_predict(self._h, C.byref(g), ens._h if ens is not None else None,
+                                        None if cov is None else cov.ctypes.data_as(_lib.PF), Cn, _pd(k), _pd(r), n,
+                                        lamv, tile_px, _pd(out), C.byref(h)))
+        return out, (Spline(self, h.value) if h.value else None)

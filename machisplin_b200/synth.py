@@ -99,13 +99,15 @@ def _training_table(geom: Geom, C: int, n: int, seed: int):
 
 
 def make_models(geom: Geom, C: int, n_train: int, seed: int, kept: str = "bgnmrv", rf_trees: int = 500,
-                gbm_trees: int = 1000, svm_frac: float = 0.5, mars_terms: int = 21) -> dict:
+                gbm_trees: int = 1000, svm_frac: float = 0.5, mars_terms: int = 21,
+                keep_estimators: bool = False) -> dict:
     """Six fitted-model descriptors with the reference's structural sizes: gam (linear), nnet(10),
     earth (<= 21 hinge terms), ksvm (~0.5 n SVs), randomForest (500 trees), gbm (1000 trees, 5 splits)."""
     P = C + 2
     X, resp = _training_table(geom, C, n_train, seed)
     rng = np.random.default_rng(seed + 77)
     out = {}
+    sk = {"X": X, "resp": resp}     # fitted scikit-learn objects (tests: independent check of the descriptors)
     if "g" in kept:
         A = np.column_stack([np.ones(len(X)), X])
         out["g"] = {"coef": np.linalg.lstsq(A, resp, rcond=None)[0]}
@@ -138,6 +140,7 @@ def make_models(geom: Geom, C: int, n_train: int, seed: int, kept: str = "bgnmrv
         sigma = 1.0 / (2.0 * P) * 1.5
         # epsilon tuned so that about svm_frac of the rows become support vectors
         svr = SVR(kernel="rbf", gamma=sigma, C=1.0, epsilon=0.1 if svm_frac >= 0.5 else 0.3).fit(Xs, ysc)
+        sk["v"] = svr
         out["v"] = {"sv": svr.support_vectors_.copy(), "alpha": svr.dual_coef_.ravel().copy(),
                     "b": -float(svr.intercept_[0]), "sigma": sigma, "x_center": xc, "x_scale": xs,
                     "y_center": yc, "y_scale": ys}
@@ -145,6 +148,7 @@ def make_models(geom: Geom, C: int, n_train: int, seed: int, kept: str = "bgnmrv
         from sklearn.ensemble import RandomForestRegressor
         rf = RandomForestRegressor(n_estimators=rf_trees, min_samples_leaf=5, max_features=max(1, P // 3),
                                    random_state=seed, n_jobs=-1).fit(X, resp)
+        sk["r"] = rf
         nrn = max(e.tree_.node_count for e in rf.estimators_)
         nt = len(rf.estimators_)
         left = np.zeros((nt, nrn), np.int32); right = np.zeros((nt, nrn), np.int32)
@@ -167,6 +171,7 @@ def make_models(geom: Geom, C: int, n_train: int, seed: int, kept: str = "bgnmrv
         lr = 0.01
         gb = GradientBoostingRegressor(n_estimators=gbm_trees, learning_rate=lr, max_leaf_nodes=6, max_depth=None,
                                        subsample=0.5, random_state=seed).fit(X, resp)
+        sk["b"] = gb
         off = [0]
         sv, sc, ln, rn, mn_ = [], [], [], [], []
         for e in gb.estimators_[:, 0]:
@@ -190,6 +195,8 @@ def make_models(geom: Geom, C: int, n_train: int, seed: int, kept: str = "bgnmrv
                     "splitvar": svat.astype(np.int32), "splitcode": scat,
                     "left": np.concatenate(ln).astype(np.int32), "right": np.concatenate(rn).astype(np.int32),
                     "missing": np.concatenate(mn_).astype(np.int32)}
+    if keep_estimators:
+        out["_sk"] = sk
     return out
 
 

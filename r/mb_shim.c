@@ -1,0 +1,118 @@
+/*
+ * .Call shim between R and libmachisplin_b200.so (include/machisplin_b200.h).
+ * NOT compiled in the build image (no R toolchain there); build where R exists with
+ *     R CMD SHLIB mb_shim.c -I../include -L../machisplin_b200 -lmachisplin_b200
+ * Every wrapper converts SEXP <-> plain pointers, calls ONE C-ABI entry point and turns a non-zero status
+ * into an R error after the C frames have unwound.  Device-resident handles (context, spline, ensemble) are
+ * R external pointers with finalizers.  R owns every host array for the duration of the call.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include "machisplin_b200.h"
+
+#define MB_CHECK(call) do { int rc_ = (call); if (rc_ != MB_OK) Rf_error("machisplin_b200: %s", mb_last_error()); } while (0)
+
+static void ctx_fin(SEXP p) { mb_shutdown((mb_ctx*)R_ExternalPtrAddr(p)); R_ClearExternalPtr(p); }
+static void spl_fin(SEXP p) { mb_spline_free((mb_spline*)R_ExternalPtrAddr(p)); R_ClearExternalPtr(p); }
+static void ens_fin(SEXP p) { mb_ensemble_free((mb_ensemble*)R_ExternalPtrAddr(p)); R_ClearExternalPtr(p); }
+
+static SEXP wrap(void* h, R_CFinalizer_t fin) {
+  SEXP p = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(p, fin, TRUE);
+  UNPROTECT(1);
+  return p;
+}
+static mb_grid grid_of(SEXP g) {           /* c(xmin, xmax, ymin, ymax, nrow, ncol) = c(ext(r)[1:4], dim(r)[1:2]) */
+  const double* v = REAL(g);
+  mb_grid out = {v[0], v[1], v[2], v[3], (int32_t)v[4], (int32_t)v[5]};
+  return out;
+}
+
+SEXP mbR_init(SEXP device) {
+  mb_ctx* ctx = NULL;
+  MB_CHECK(mb_init(Rf_asInteger(device), &ctx));
+  return wrap(ctx, ctx_fin);
+}
+
+/* fields::Tps(x, Y) -> external pointer of the fitted spline (V73:722, V73:751).  lambda < 0 = GCV. */
+SEXP mbR_tps_fit(SEXP ctx, SEXP xy, SEXP y, SEXP lambda) {
+  const int n = Rf_nrows(xy);
+  mb_spline* s = NULL;
+  MB_CHECK(mb_tps_fit((mb_ctx*)R_ExternalPtrAddr(ctx), REAL(xy), REAL(y), n, 1, Rf_asReal(lambda), &s));
+  return wrap(s, spl_fin);
+}
+
+/* terra::interpolate(rast(template), Tps): values in terra cell order (V73:726, V73:753). */
+SEXP mbR_tps_eval(SEXP ctx, SEXP spline, SEXP grid) {
+  mb_grid g = grid_of(grid);
+  mb_window w = {0, g.nrow, 0, g.ncol};
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)g.nrow * g.ncol));
+  MB_CHECK(mb_tps_eval((mb_ctx*)R_ExternalPtrAddr(ctx), (mb_spline*)R_ExternalPtrAddr(spline), &g, &w, MB_EVAL_FAST,
+                       REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
+
+/* Flat model descriptors (a named list built by mb_export_models() in machisplin_b200.R) -> ensemble handle. */
+static const double* dbl(SEXP l, const char* name);
+static const int* int_(SEXP l, const char* name);
+static SEXP elt(SEXP l, const char* name) {
+  SEXP names = Rf_getAttrib(l, R_NamesSymbol);
+  for (R_xlen_t i = 0; i < Rf_xlength(l); ++i)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(l, i);
+  return R_NilValue;
+}
+static const double* dbl(SEXP l, const char* name) { SEXP e = elt(l, name); return e == R_NilValue ? NULL : REAL(e); }
+static const int* int_(SEXP l, const char* name) { SEXP e = elt(l, name); return e == R_NilValue ? NULL : INTEGER(e); }
+static double num(SEXP l, const char* name, double dflt) { SEXP e = elt(l, name); return e == R_NilValue ? dflt : Rf_asReal(e); }
+
+SEXP mbR_ensemble_create(SEXP ctx, SEXP grid, SEXP d, SEXP kept, SEXP w, SEXP w_total) {
+  mb_grid g = grid_of(grid);
+  mb_models m;
+  memset(&m, 0, sizeof m);
+  m.P = (int32_t)num(d, "P", 0);
+  m.gam_coef = dbl(d, "gam_coef");
+  m.nn_wts = dbl(d, "nn_wts"); m.nn_H = (int32_t)num(d, "nn_H", 0); m.nn_max2 = num(d, "nn_max2", 1); m.nn_min = num(d, "nn_min", 0);
+  m.mars_T = (int32_t)num(d, "mars_T", 0); m.mars_dirs = (const int8_t*)(elt(d, "mars_dirs") == R_NilValue ? NULL : RAW(elt(d, "mars_dirs")));
+  m.mars_cuts = dbl(d, "mars_cuts"); m.mars_coef = dbl(d, "mars_coef");
+  m.svm_S = (int32_t)num(d, "svm_S", 0); m.svm_sv = dbl(d, "svm_sv"); m.svm_alpha = dbl(d, "svm_alpha");
+  m.svm_b = num(d, "svm_b", 0); m.svm_sigma = num(d, "svm_sigma", 0);
+  m.svm_x_center = dbl(d, "svm_x_center"); m.svm_x_scale = dbl(d, "svm_x_scale");
+  m.svm_y_center = num(d, "svm_y_center", 0); m.svm_y_scale = num(d, "svm_y_scale", 1);
+  m.rf_ntree = (int32_t)num(d, "rf_ntree", 0); m.rf_nrnodes = (int32_t)num(d, "rf_nrnodes", 0);
+  m.rf_left = int_(d, "rf_left"); m.rf_right = int_(d, "rf_right");
+  m.rf_status = (const int8_t*)(elt(d, "rf_status") == R_NilValue ? NULL : RAW(elt(d, "rf_status")));
+  m.rf_bestvar = int_(d, "rf_bestvar"); m.rf_split = dbl(d, "rf_split"); m.rf_nodepred = dbl(d, "rf_nodepred");
+  m.gbm_ntrees = (int32_t)num(d, "gbm_ntrees", 0); m.gbm_initF = num(d, "gbm_initF", 0); m.gbm_tree_off = int_(d, "gbm_tree_off");
+  m.gbm_splitvar = int_(d, "gbm_splitvar"); m.gbm_splitcode = dbl(d, "gbm_splitcode");
+  m.gbm_left = int_(d, "gbm_left"); m.gbm_right = int_(d, "gbm_right"); m.gbm_missing = int_(d, "gbm_missing");
+  mb_ensemble* e = NULL;
+  MB_CHECK(mb_ensemble_create((mb_ctx*)R_ExternalPtrAddr(ctx), &g, &m, CHAR(STRING_ELT(kept, 0)), REAL(w),
+                              Rf_asReal(w_total), &e));
+  return wrap(e, ens_fin);
+}
+
+/* mltps parts 2-5 for one response (V73:442-932): cov = float32 planes packed in a raw vector (C x nrow x ncol,
+ * terra cell order), knots_xy n x 2, resid n.  Returns the final raster values. */
+SEXP mbR_mltps_predict(SEXP ctx, SEXP grid, SEXP ens, SEXP cov_raw, SEXP C, SEXP knots_xy, SEXP resid, SEXP lambda,
+                       SEXP tile_px) {
+  mb_grid g = grid_of(grid);
+  const int tps = knots_xy != R_NilValue;
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)g.nrow * g.ncol));
+  MB_CHECK(mb_mltps_predict((mb_ctx*)R_ExternalPtrAddr(ctx), &g,
+                            ens == R_NilValue ? NULL : (mb_ensemble*)R_ExternalPtrAddr(ens),
+                            cov_raw == R_NilValue ? NULL : (const float*)RAW(cov_raw), Rf_asInteger(C),
+                            tps ? REAL(knots_xy) : NULL, tps ? REAL(resid) : NULL, tps ? Rf_nrows(knots_xy) : 0,
+                            Rf_asReal(lambda), Rf_asInteger(tile_px), REAL(out), NULL));
+  UNPROTECT(1);
+  return out;
+}
+
+/* G = R'R for the ensemble-weight objective (V73:329-333, 369-373). */
+SEXP mbR_gram(SEXP ctx, SEXP R) {
+  const int n = Rf_nrows(R), K = Rf_ncols(R);
+  SEXP G = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+  MB_CHECK(mb_gram((mb_ctx*)R_ExternalPtrAddr(ctx), REAL(R), n, K, REAL(G)));
+  UNPROTECT(1);
+  return G;
+}

@@ -120,3 +120,66 @@ def test_gram(engine, K):
     assert np.max(np.abs(G - ref)) <= 1e-12 * np.max(np.abs(ref))
     k = rng.uniform(0, 1, K)
     assert abs(om.rss_from_gram(k, G) - om.rss_objective(k, R)) <= 1e-10 * om.rss_objective(k, R)
+
+
+# ---- the one-call path (mb_mltps_predict*) and the tunable kernel variants ---------------------------
+def test_mltps_predict_one_call_matches_oracle(engine, case):
+    """parts 2-5 in one call: ensemble kernels beside the GCV fit, fused TPS + combine pass."""
+    geom, C, models, cov = case
+    kept, w, wt = synth.ensemble_weights("bgnmrv")
+    xy, _, _ = synth.make_knots(geom, 250, 8)
+    y = synth.residual_field(xy, 8)
+    fit = otps.tps_fit(xy, y)
+    ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
+    got, sp = engine.mltps_predict(geom, ens, cov, xy, y)
+    assert abs(sp.lam - fit.lam) <= 1e-6 * fit.lam
+    surf = cbind.tps_eval(fit, geom.as_tuple())
+    ref = cbind.ensemble_eval(models, kept, w, wt, cov, geom.as_tuple(), tps=surf)
+    _cmp(got, ref, 2e-6)
+    # tps = FALSE and ensemble-less variants
+    got2, sp2 = engine.mltps_predict(geom, ens, cov, None, None)
+    assert sp2 is None
+    _cmp(got2, cbind.ensemble_eval(models, kept, w, wt, cov, geom.as_tuple()), 2e-6)
+    got3, _ = engine.mltps_predict(geom, None, None, xy, y)
+    assert np.max(np.abs(got3 - surf)) < 1e-6 * np.max(np.abs(surf))
+
+
+def test_mltps_predict_tiled_mode(engine, case):
+    """tile_px > 0 and more than one tile: the reference's internal tiling (V73:649-895) feeds the combine."""
+    from oracle import tiles as otl
+    geom, C, models, cov = case
+    kept, w, wt = synth.ensemble_weights("gnm")
+    xy, _, _ = synth.make_knots(geom, 600, 18)
+    y = synth.residual_field(xy, 18)
+    ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
+    got, sp = engine.mltps_predict(geom, ens, cov, xy, y, tile_px=100)
+    assert sp is None
+    surf = otl.tps_tiled_surface(geom.as_tuple(), xy, y, tile_px=100)
+    ref = cbind.ensemble_eval(models, kept, w, wt, cov, geom.as_tuple(), tps=surf)
+    _cmp(got, ref, 2e-6)
+
+
+@pytest.mark.parametrize("rows", [1, 2, 4])
+def test_forest_tile_shapes_agree(engine, case, rows):
+    """the tile-pruned forest kernel must give the same raster for every tile height (same comparisons,
+    only the order of the float64 sum over trees changes)."""
+    geom, C, models, cov = case
+    ens = engine.ensemble_create(geom, models, "rb", [0.6, 0.4], 1.0, C + 2)
+    engine.set_param("tree_rows", rows)
+    try:
+        got = engine.ensemble_eval(ens, cov, window=(3, 150, 5, 217))
+    finally:
+        engine.set_param("tree_rows", 0)
+    ref = cbind.ensemble_eval(models, "rb", [0.6, 0.4], 1.0, cov, geom.as_tuple())[3:150, 5:217]
+    _cmp(got, ref, 2e-7)
+
+
+def test_forest_on_rough_raster(engine, case):
+    """white-noise covariates defeat the tile pruning (every tree forks in every tile): same answer."""
+    geom, C, models, cov = case
+    rng = np.random.default_rng(4)
+    rough = (cov + rng.normal(0, 60, cov.shape)).astype(np.float32)
+    ens = engine.ensemble_create(geom, models, "rb", [0.5, 0.5], 1.0, C + 2)
+    got = engine.ensemble_eval(ens, rough)
+    ref = cbind.ensemble_eval(models, "rb", [0.5, 0.5], 1.0, rough, geom.as_tuple())
+    _cmp(got, ref, 2e-7)

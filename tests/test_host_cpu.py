@@ -1,0 +1,110 @@
+"""CPU tests of the host-side mirror of the reference interface (machisplin_b200/{tiles,mltps,parallel}.py):
+index arithmetic and sharding logic only - no compute call (that needs the GPU)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from machisplin_b200 import mltps as pm, parallel as par, synth, tiles as pt   # noqa: E402
+from oracle import models as om, tiles as otl                                    # noqa: E402
+
+
+def test_tiles_create_matches_oracle_and_v73():
+    geom = synth.make_geom(3264, 2476)
+    rng = np.random.default_rng(0)
+    pts = rng.uniform([geom.xmin, geom.ymin], [geom.xmax, geom.ymax], (813, 2))
+    for nc, nr, fd in [(3, 3, 50), (2, 4, 50), (5, 1, 20), (1, 1, 50)]:
+        ts = pt.tiles_create(geom, pts, nc, nr, fd)
+        ref = otl.tiles_create(geom.as_tuple(), pts, nc, nr, fd)
+        assert ts.nC == nc and ts.nR == nr and len(ts.tiles) == nc * nr
+        for t, r in zip(ts.tiles, ref["tiles"]):
+            assert t.win == tuple(r["win"])
+            np.testing.assert_allclose(t.ext, r["ext"], rtol=0, atol=0)
+            assert np.array_equal(t.points, r["points"])
+            assert t.geom.as_tuple() == pytest.approx(r["geom"], abs=0)
+    # tile 1 is the south-west tile (V73:1192-1197); neighbours overlap by feather.d pixels
+    ts = pt.tiles_create(geom, pts, 3, 3, 50)
+    assert ts.tiles[0].win[1] == geom.nrow and ts.tiles[0].win[2] == 0
+    assert ts.tiles[0].win[3] - ts.tiles[1].win[2] == 50
+
+
+def test_crop_window_snaps_like_terra():
+    geom = synth.make_geom(100, 200)
+    r = geom.rx
+    assert pt.crop_window(geom, (10.4 * r, 20.6 * r, 0.0, 5.5 * r)) == (100 - 6, 100, 10, 21)
+    assert pt.crop_window(geom, (-1.0, 2.0, -1.0, 2.0)) == (0, 100, 0, 200)          # clipped to the raster
+
+
+def test_weight_rule_and_quadratic_objective():
+    p = np.array([0.41, 0.03, 0.333, 0.9, 0.0449, 0.21])
+    assert pm.select_models(p)[0] == om.select_models(p)[0]
+    np.testing.assert_array_equal(pm.select_models(p)[1], om.select_models(p)[1])
+    assert pm.select_models(p)[2] == om.select_models(p)[2]
+    rng = np.random.default_rng(3)
+    R = rng.standard_normal((500, 6))
+    fit = pm.rss_objective_from_gram(R.T @ R)
+    k = rng.uniform(0, 1, 6)
+    assert abs(fit(k) - om.rss_objective(k, R)) < 1e-10 * om.rss_objective(k, R)
+
+
+def test_knot_cells_are_cell_centres():
+    geom = synth.make_geom(64, 96)
+    xy = np.array([[geom.xmin, geom.ymax], [geom.xmax, geom.ymin], [0.5 * geom.xmax, 0.5 * geom.ymax], [2.0, 2.0]])
+    k, row, col = pm.knot_cells(geom, xy)
+    assert list(row) == [0, 63, 32, -1] and list(col) == [0, 95, 48, -1]
+    ref_k, ref_r, ref_c = otl.knot_coordinates(geom.as_tuple(), xy[:3])
+    np.testing.assert_allclose(k[:3], ref_k)
+    assert np.array_equal(row[:3], ref_r) and np.array_equal(col[:3], ref_c)
+
+
+def test_sharding_covers_everything_once():
+    for world in (1, 2, 3, 8):
+        owned = sorted(t for r in range(world) for t in par.tiles_of_rank(121, world, r))
+        assert owned == list(range(121))
+        blocks = par.row_blocks(8192 + 17, world)
+        assert blocks[0][0] == 0 and blocks[-1][1] == 8192 + 17
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert all(b[0] % 32 == 0 for b in blocks)
+        rows = np.concatenate([np.arange(90001)[par.shard_rows(90001, world, r)] for r in range(world)])
+        assert np.array_equal(rows, np.arange(90001))
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["MB_ROOT"])
+import torch.distributed as dist
+from machisplin_b200 import parallel as par
+rank, world = par.init("gloo")
+rng = np.random.default_rng(7)
+R = rng.standard_normal((9001, 6)) * rng.uniform(0.5, 20, 6)      # same matrix on every rank
+sl = par.shard_rows(R.shape[0], world, rank)
+G = par.allreduce_gram(R[sl].T @ R[sl])                            # per-rank Gram (mb_gram on a GPU box) + all-reduce
+assert np.allclose(G, R.T @ R, rtol=1e-12), "Gram all-reduce"
+assert par.max_over_ranks(10.0 + rank) == 10.0 + world - 1
+mine = [(t, np.full((2, 2), float(t))) for t in par.tiles_of_rank(7, world, rank)]
+got = par.gather_tiles(mine, 7, dst=0)
+if rank == 0:
+    assert [int(g[0, 0]) for g in got] == list(range(7))
+else:
+    assert got is None
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_gram_allreduce_and_tile_gather(tmp_path):
+    """world_size 2 over gloo on CPU: the N > 1 plumbing of SURVEY.md 8e (sharded CV-residual Gram + tile ownership)."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MB_ROOT=ROOT, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

@@ -178,3 +178,41 @@ def test_weight_rule_and_rss():
     k = rng.uniform(0, 1, 6)
     assert abs(om.rss_objective(k, R) - om.rss_from_gram(k, om.gram(R))) < 1e-9
     assert abs(om.rss_objective(3 * k, R) - om.rss_objective(k, R)) < 1e-9    # homogeneous of degree 0
+
+
+# ---- independent anchors: third-party implementations of the same mathematics ---------------------------
+def test_tps_solve_matches_scipy_rbf_interpolator():
+    """scipy.interpolate.RBFInterpolator(kernel='thin_plate_spline', degree=1) solves the same
+    smoothing-spline system with phi = r^2 log r = 8 pi * fields' Rad.cov, so smoothing = 8 pi lambda gives
+    the same surface.  Pins the oracle's (K + lambda I) c + T d = y restatement and predict.Krig on an
+    implementation we did not write (parity with R fields itself stays unpinned)."""
+    from scipy.interpolate import RBFInterpolator
+    rng = np.random.default_rng(42)
+    xy = rng.uniform(0, 1, (400, 2)) * [3.0, 1.5] + [10.0, -4.0]
+    y = np.sin(2 * xy[:, 0]) * np.cos(3 * xy[:, 1]) + 0.05 * rng.standard_normal(400)
+    pts = rng.uniform(0, 1, (500, 2)) * [3.0, 1.5] + [10.0, -4.0]
+    for lam in (1e-2, 1e-4, 1e-7):
+        fit = otps.tps_fit(xy, y, lam=lam)
+        s = (xy - fit.center) / fit.scale                     # Krig's transformx, scale.type = "range"
+        rbf = RBFInterpolator(s, y, kernel="thin_plate_spline", smoothing=8 * np.pi * lam, degree=1)
+        ref = rbf((pts - fit.center) / fit.scale)
+        got = otps.tps_predict_points(fit, pts)
+        assert np.max(np.abs(got - ref)) < 1e-7 * np.max(np.abs(ref))
+
+
+def test_model_descriptors_match_scikit_learn_predict():
+    """the flat randomForest / gbm / ksvm descriptors + the oracle's predictors reproduce the predict() of
+    the scikit-learn estimators they were exported from (same tree walks, same RBF expansion)."""
+    from machisplin_b200 import synth
+    from oracle import models as om
+    geom = synth.make_geom(96, 128)
+    m = synth.make_models(geom, 3, 400, 3, kept="brv", rf_trees=20, gbm_trees=30, keep_estimators=True)
+    sk = m["_sk"]
+    rng = np.random.default_rng(1)
+    X = sk["X"][rng.integers(0, len(sk["X"]), 300)] + rng.normal(0, 0.3, (300, 5)) * sk["X"].std(0)
+    X[:, :3] = X[:, :3].astype(np.float32)                    # raster values are float32
+    np.testing.assert_allclose(om.predict_rf(m["r"], X), sk["r"].predict(X), rtol=1e-12)
+    np.testing.assert_allclose(om.predict_gbm(m["b"], X), sk["b"].predict(X), rtol=1e-10)
+    v = m["v"]
+    ref = sk["v"].predict((X - v["x_center"]) / v["x_scale"]) * v["y_scale"] + v["y_center"]
+    np.testing.assert_allclose(om.predict_svm_exact(v, X), ref, rtol=1e-9)

@@ -137,3 +137,26 @@ def test_errors_are_reported_not_thrown(engine):
         engine.tps_fit(xy, np.zeros(10))          # zero range
     with pytest.raises(L.MbError):
         engine.tps_fit(np.column_stack([np.arange(10.0), np.arange(10.0)]), np.zeros(10))   # collinear
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_leaf_precision_paths(engine, mode):
+    """float64-only and forced mixed-precision leaf paths against the oracle (automatic mode picks per launch)."""
+    geom, xy, y, fit = _case(768, 1024, 1200, 31)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    engine.set_param("eval_precision", mode)
+    try:
+        got = engine.tps_eval(sp, geom, method="fast")
+    finally:
+        engine.set_param("eval_precision", 0)
+    ref = otps.tps_interpolate(fit, geom.as_tuple())
+    assert relerr(got, ref) < (3e-7 if mode == 1 else 1e-6)
+
+
+def test_mixed_path_is_refused_when_inaccurate(engine):
+    """near-interpolating spline on a coarse grid: the device-side estimate must fall back to float64."""
+    geom, xy, y, fit = _case(96, 96, 400, 12, lam=1e-9)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    got = engine.tps_eval(sp, geom, method="fast")
+    ref = otps.tps_interpolate(fit, geom.as_tuple())
+    assert relerr(got, ref) < 1e-6

@@ -5,7 +5,7 @@ set -u
 TAG=${1:-r1}
 KREG=${2:-'k_leaf|k_ens_trees|k_ens_svm|k_ens_final'}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" 
+python -m pytest tests -m gpu -x -q --durations=12 > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" 
 tail -3 gpurun_out/${TAG}_pytest.log
 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_c3.json 2> gpurun_out/${TAG}_bench_c3.err; echo "bench rc=$?"
 python bench.py --config c2 --nrow 8192 --ncol 8192 --knots 5000 --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_tps8192.json 2> gpurun_out/${TAG}_bench_tps8192.err; echo "bench tps rc=$?"
