@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--lam", type=float, default=None, help="fixed lambda (Cholesky path) instead of GCV")
     ap.add_argument("--tree-rows", type=int, default=0, help="forest tile: cells per thread (1, 2, 4; 0 = auto)")
     ap.add_argument("--eval-precision", type=int, default=0, help="leaf kernel path: 0 auto, 1 float64, 2 mixed")
+    ap.add_argument("--param", action="append", default=[], help="engine tunable name=value (mb_set_param), repeatable")
     return ap.parse_args()
 
 
@@ -291,6 +292,9 @@ def run_b200(args):
     eng = mb.Engine(local)
     eng.set_param("tree_rows", args.tree_rows)
     eng.set_param("eval_precision", args.eval_precision)
+    for kv in args.param:
+        name, val = kv.split("=")
+        eng.set_param(name, int(val))
     C = cfg["C"]
     P = C + 2
     cov = device_covariates(geom, C, dev) if C else torch.zeros((0,), device=dev)
@@ -383,9 +387,13 @@ def run_b200(args):
     kern = {}
     tot_ms = sum(v[0] for v in ktimes.values()) or 1.0
     heavy = bool(kept) and bool(set(kept) & set("brv"))
-    bytes_per_cell = {"k_leaf": 8.0, "k_leaf_fused": 4.0 * C + 8.0 + (8.0 if heavy else 0.0),
-                      "k_ens_final": 4.0 * C + 8.0 + 8.0 + (8.0 if heavy else 0.0),
-                      "k_ens_trees": 4.0 * C + 8.0, "k_ens_svm": 4.0 * C + 16.0}
+    # algorithmic HBM bytes per cell: k_leaf writes the float64 surface; k_leaf_fused reads the
+    # float64 ensemble accumulator and writes the final raster; the ensemble kernels read the C float32 planes
+    # and write (k_ens_trees) or read-modify-write (k_ens_svm, k_ens_smooth) the accumulator
+    bytes_per_cell = {"k_leaf": 8.0, "k_leaf_f64": 8.0, "k_leaf_fused": 16.0, "k_leaf_f64_fused": 16.0,
+                      "k_ens_final": 24.0, "k_ens_trees": 4.0 * C + 8.0,
+                      "k_ens_svm": 4.0 * C + (16.0 if set(kept) & set("br") else 8.0),
+                      "k_ens_smooth": 4.0 * C + (16.0 if heavy else 8.0)}
     for name, (tms, cnt) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
         per_launch = tms / max(cnt, 1)
         ent = {"ms_per_step": tms / args.steps, "launches_per_step": cnt / args.steps, "share": tms / tot_ms}
@@ -393,10 +401,10 @@ def run_b200(args):
             gbs = cells * bytes_per_cell[name] / (per_launch * 1e-3) / 1e9
             ent.update({"algorithmic_bytes_per_cell": bytes_per_cell[name], "achieved_gbs": gbs, "hbm_frac": gbs / peak})
         kern[name] = ent
-    lname = "k_leaf_fused" if "k_leaf_fused" in kern else "k_leaf"
+    lname = next((k for k in ("k_leaf_fused", "k_leaf", "k_leaf_f64_fused", "k_leaf_f64") if k in kern), "k_leaf")
     leaf = kern.get(lname, {})
     roofline = {"kernel": f"{lname} (grid-evaluation kernel: per-cell TPS surface" +
-                          (" + smooth models + ensemble combine)" if lname == "k_leaf_fused" else ")"),
+                          (" + ensemble combine, mltps part 5)" if "fused" in lname else ")"),
                 "bound": "hbm", "achieved": leaf.get("achieved_gbs"),
                 "peak": peak, "unit": "GB/s", "frac": leaf.get("hbm_frac"), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": bytes_per_cell[lname],

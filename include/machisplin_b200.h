@@ -79,8 +79,10 @@ int mb_spline_np(const mb_spline* s);
 /* Any output pointer may be NULL.  knots_xy np x 2 column-major unscaled. */
 int mb_spline_get(const mb_spline* s, double* c, double* d, double* center, double* scale,
                   double* knots_xy, double* lambda, double* eff_df, double* gcv_at_lambda);
-/* eigenvalues eta[np-3] and rotated data u[np] of the WBW decomposition (NULL-able) */
-int mb_spline_get_decomp(const mb_spline* s, double* eta, double* u);
+/* GCV fits only (all outputs NULL-able): eigenvalues eta[np-3] of Q2'KQ2 (decreasing, = 1/D of Krig's "WBW"
+ * decomposition), and the tridiagonal form the lambda search runs on: T = Q'(Q2'KQ2)Q as tri_diag[np-3],
+ * tri_off[np-4], and the rotated data zhat[np-3] = Q'Q2' sqrt(w) yM. */
+int mb_spline_get_decomp(const mb_spline* s, double* eta, double* tri_diag, double* tri_off, double* zhat);
 void mb_spline_free(mb_spline* s);
 
 /* ---- a2: terra::interpolate(rast(template), Tps)  (V73:726, V73:753) ----------------- */
@@ -199,7 +201,10 @@ int mb_timing_collect(mb_ctx* ctx, int cap, const char** names, double* total_ms
 /* Tunables of the fast evaluator (0 = automatic). */
 int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows);
 /* Named integer tunables (0 = automatic): "tree_rows" = cells per thread of the forest tile (1, 2, 4);
- * "eval_precision" = leaf kernel code path of the fast evaluator (1 = float64 only, 2 = force mixed). */
+ * "eval_precision" = leaf kernel code path of the fast evaluator (1 = float64 only, 2 = force mixed);
+ * "sytrd_mode" = 2 runs the tridiagonalisation as one kernel per phase instead of the persistent kernel;
+ * "sytrd_ctas_per_sm" = persistent grid size; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd
+ * (validation of the in-house path only). */
 int mb_set_param(mb_ctx* ctx, const char* name, int value);
 
 #ifdef __cplusplus

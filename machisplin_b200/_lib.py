@@ -68,7 +68,7 @@ SIGNATURES = {
     "mb_spline_create": (C.c_int, [VP, PD, C.c_int, PD, PD, PD, PD, PVP]),
     "mb_spline_np": (C.c_int, [VP]),
     "mb_spline_get": (C.c_int, [VP, PD, PD, PD, PD, PD, PD, PD, PD]),
-    "mb_spline_get_decomp": (C.c_int, [VP, PD, PD]),
+    "mb_spline_get_decomp": (C.c_int, [VP, PD, PD, PD, PD]),
     "mb_spline_free": (None, [VP]),
     "mb_tps_eval": (C.c_int, [VP, VP, PG, PW, C.c_int, PD]),
     "mb_tps_eval_dev": (C.c_int, [VP, VP, PG, PW, C.c_int, VP, C.c_int64, VP]),

@@ -133,6 +133,15 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
     if (n == "tree_rows") {
       MB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4, "tree_rows must be 0, 1, 2 or 4");
       ctx->tree_rows = value;
+    } else if (n == "eigen_impl") {
+      MB_REQUIRE(value == 0 || value == 1, "eigen_impl must be 0 (in-house) or 1 (cuSOLVER, validation)");
+      ctx->eigen_impl = value;
+    } else if (n == "sytrd_mode") {
+      MB_REQUIRE(value >= 0 && value <= 2, "sytrd_mode must be 0 / 1 (persistent kernel) or 2 (kernel per phase)");
+      ctx->sytrd_mode = value;
+    } else if (n == "sytrd_ctas_per_sm") {
+      MB_REQUIRE(value >= 0 && value <= 4, "sytrd_ctas_per_sm must be in [0, 4]");
+      ctx->sytrd_ctas_per_sm = value;
     } else if (n == "eval_precision") {
       MB_REQUIRE(value >= 0 && value <= 2, "eval_precision must be 0 (auto), 1 (float64) or 2 (mixed)");
       ctx->eval_precision = value;
@@ -222,12 +231,22 @@ int mb_spline_get(const mb_spline* s, double* c, double* d, double* center, doub
   });
 }
 
-int mb_spline_get_decomp(const mb_spline* s, double* eta, double* u) {
+int mb_spline_get_decomp(const mb_spline* s, double* eta, double* tri_diag, double* tri_off, double* zhat) {
   return guarded([&] {
     MB_REQUIRE(s, "spline is NULL");
-    MB_REQUIRE(!s->eta.empty(), "spline carries no WBW decomposition (fixed-lambda Cholesky fit or created from coefficients)");
+    MB_REQUIRE(!s->eta.empty(), "spline carries no decomposition (fixed-lambda Cholesky fit or created from coefficients)");
     if (eta) std::copy(s->eta.begin(), s->eta.end(), eta);
-    if (u) std::copy(s->u.begin(), s->u.end(), u);
+    const int m = s->np - 3;
+    const double nan = std::nan("");
+    if (s->tri_diag.empty()) {   // fitted through the eigenvector (validation) path: no tridiagonal form
+      if (tri_diag) std::fill(tri_diag, tri_diag + m, nan);
+      if (tri_off) std::fill(tri_off, tri_off + m - 1, nan);
+      if (zhat) std::fill(zhat, zhat + m, nan);
+      return;
+    }
+    if (tri_diag) std::copy(s->tri_diag.begin(), s->tri_diag.end(), tri_diag);
+    if (tri_off) std::copy(s->tri_off.begin(), s->tri_off.end(), tri_off);
+    if (zhat) std::copy(s->zhat.begin(), s->zhat.end(), zhat);
   });
 }
 
@@ -482,12 +501,12 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, c
   }
   // part 2 (trees + svm) starts on the side stream; it only needs the covariates
   double* acc = nullptr;
-  const bool heavy = e && ensemble_has_heavy(e);
+  const bool heavy = e != nullptr;
   if (heavy) {
-    acc = ctx->arena.take_n<double>(ncell);
+    acc = ctx->arena.take_n<double>((size_t)(acc_stride(full) * acc_rows(full)));
     MB_CUDA(cudaEventRecord(ctx->ev_fork, st));
     MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    ensemble_heavy(ctx, e, cov, C, full, acc, ctx->side);
+    ensemble_accumulate(ctx, e, cov, C, full, acc, ctx->side);
     MB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   }
   // part 3: fields::Tps of the residuals on the context stream, beside the kernels above
@@ -511,7 +530,7 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, c
   if (heavy) MB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
   // parts 3-5: TPS surface + smooth models + combine, one pass over the grid
   if (e) {
-    ensemble_finish(ctx, e, cov, C, sp.get(), surface, full, acc, out, st);
+    ensemble_finish(ctx, e, sp.get(), surface, full, acc, out, st);
   } else if (sp) {
     tps_eval_fast(ctx, sp.get(), g, full, out, g.ncol, st);
   } else if (surface) {

@@ -162,6 +162,9 @@ struct mb_ctx {
   // 256-entry (1/m_k, -log(1/m_k)) table for the float64 table-driven log
   mb::DevBuf<double2> logtab;
   int eval_precision = 0;     // fast evaluator: 0 = automatic, 1 = float64 only, 2 = force mixed
+  int eigen_impl = 0;         // GCV fit: 0 = in-house tridiagonalisation + bisection, 1 = cuSOLVER Dsyevd (validation)
+  int sytrd_mode = 0;         // tridiagonalisation: 0 / 1 = persistent kernel with grid barrier, 2 = one kernel per phase
+  int sytrd_ctas_per_sm = 0;  // persistent grid size (0 = 2 per SM)
   // scratch reused across calls
   mb::Arena arena;
   // second stream + events: the TPS fit runs beside the per-cell ensemble kernels (mb_mltps_predict*)
@@ -178,7 +181,8 @@ struct mb_spline {
   double d[3] = {0, 0, 0};
   double center[2] = {0, 0}, scale[2] = {1, 1};
   double lambda = -1, eff_df = -1, gcv = -1;
-  std::vector<double> eta, u;        // WBW decomposition (GCV fits only)
+  std::vector<double> eta;           // eigenvalues of Q2'KQ2, decreasing (GCV fits only)
+  std::vector<double> tri_diag, tri_off, zhat;   // T = Q'(Q2'KQ2)Q and Q'Q2'y of the in-house GCV fit
   double sum_abs_c = 0;              // sum |c_i|  (amplification estimate for the fast evaluator)
   double fscale = 0;                 // max |f(knot_i)|
   mb::DevBuf<double> d_sx, d_sy, d_c;
@@ -245,10 +249,20 @@ struct KernelTimer {
 void spline_finalize(mb_ctx* ctx, mb_spline* s, double fscale_known = -1.0);
 void tps_eval_direct(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
                      int64_t stride, cudaStream_t st);
-struct EnsFuse;   // ens_device.cuh
+// Part 5 fused into the grid-evaluation kernel: final = acc * inv_w + TPS (V73:619, 906-907).  acc is the
+// weighted ensemble sum of the window (every kept model; NaN = NA cell) in the padded accumulator layout:
+// row stride acc_stride(w) doubles, acc_rows(w) rows, so that a 32-column x bh-row tile of any leaf lattice is
+// 16-byte aligned and in bounds for the bulk copies of k_leaf_stream.
+struct AccFuse {
+  const double* acc;
+  int64_t stride;
+  double inv_w;
+};
+inline int64_t acc_stride(const mb_window& w) { return ((int64_t)(w.c1 - w.c0) + 31) / 32 * 32; }
+inline int64_t acc_rows(const mb_window& w) { return (int64_t)(w.r1 - w.r0) + 128; }
 // Temporaries come from ctx->arena: the caller must have called ctx->arena.begin(st) for this call.
 void tps_eval_fast(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
-                   int64_t stride, cudaStream_t st, const EnsFuse* fuse = nullptr);
+                   int64_t stride, cudaStream_t st, const AccFuse* fuse = nullptr);
 void tps_predict_points_dev(mb_ctx* ctx, const mb_spline* s, const double* x_dev, const double* y_dev, int n,
                             double* out_dev, cudaStream_t st);
 void init_logtab(mb_ctx* ctx);

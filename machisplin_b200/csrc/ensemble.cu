@@ -18,8 +18,11 @@
 //                 are spatially coherent, so >90 % of the node visits of the per-cell walk disappear while
 //                 every surviving comparison is the reference's own (results are identical).
 //   k_ens_svm     ksvm rbfdot: exp2(a + b_i + x . sv'_i), float32 dot product, float64 accumulation.
-//   k_ens_final   gam + nnet + earth in float64, adds the tree/svm accumulator, divides by the total
-//                 weight, adds the TPS surface, applies the NA rule.
+//   smooth models gam + nnet + earth in float64: folded into k_ens_svm (whose FP64 pipe is idle) when ksvm is
+//                 kept, else k_ens_smooth.  The last kernel of the chain also encodes the NA rule: the
+//                 accumulator holds NaN where any covariate is NA.
+//   k_ens_final   acc / total weight + precomputed TPS surface (the fused path is k_leaf_stream, tps_eval.cu).
+// The accumulator uses the padded layout of AccFuse (common.cuh): row stride acc_stride(w).
 #include "common.cuh"
 #include "internal.h"
 #include "ens_device.cuh"
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kTreeThreads) k_ens_trees_plain(
     const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg, mb_window w,
     const int2* __restrict__ rf_nodes, const int* __restrict__ rf_root, int rf_n, double rf_w, double rf_off,
     const int2* __restrict__ gb_nodes, const int* __restrict__ gb_root, int gb_n, double gb_w, double gb_init,
-    int gbm_missing, double* __restrict__ acc) {
+    int gbm_missing, int64_t acc_stride, double* __restrict__ acc) {
   __shared__ float s_feat[16 * kTreeThreads];
   const int wc = w.c1 - w.c0;
   const int64_t cell = (int64_t)blockIdx.x * kTreeThreads + threadIdx.x;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(kTreeThreads) k_ens_trees_plain(
     else for (int t = 0; t < gb_n; ++t) s += (double)walk_tree<false>(gb_nodes, __ldg(&gb_root[t]), sf);
     out += gb_w * (s + gb_init);
   }
-  acc[cell] += out;
+  acc[(int64_t)(row - w.r0) * acc_stride + (col - w.c0)] += out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -212,7 +215,7 @@ template <int R>
 __global__ void __launch_bounds__(kTreeThreads) k_ens_trees(
     const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg, mb_window w,
     const int2* __restrict__ nodes, const int* __restrict__ roots, int n_rf, int n_gb, int zero_leaf,
-    double rf_scale, double gb_scale, double base, int accumulate, double* __restrict__ acc) {
+    double rf_scale, double gb_scale, double base, int accumulate, int64_t acc_stride, double* __restrict__ acc) {
   extern __shared__ __align__(16) unsigned char tree_smem[];
   float* s_feat = reinterpret_cast<float*>(tree_smem);                    // [(C + 2)][256 R]
   int* s_list = reinterpret_cast<int*>(s_feat + (C + 2) * kTreeThreads * R);   // [8][kTreeSeg + kTreeIlp]
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(kTreeThreads) k_ens_trees(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int col = w.c0 + blockIdx.x * 32 + lane;
   const int row0 = w.r0 + blockIdx.y * (8 * R) + warp;
-  const int wc = w.c1 - w.c0;
+  const int64_t wc = acc_stride;
   // ---- phase 1 -------------------------------------------------------------------------------
   unsigned evalmask = 0;          // bit r: cell r of this thread is inside the window and has no NA
 #pragma unroll
@@ -388,18 +391,39 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// the float64 smooth models of one cell, kept out of line so that the register allocation of the
+// support-vector loop is not affected (called once per cell before the loop)
+__device__ __noinline__ double smooth_cell(const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg, int row,
+                                           int col, SmoothParams sp) {
+  double x[16];
+  for (int f = 0; f < C; ++f) x[f] = (double)__ldg(&cov[f * plane + (int64_t)row * eg.ncol + col]);
+  x[C] = eg.xmin + (col + 0.5) * eg.rx;
+  x[C + 1] = eg.ymax - (row + 0.5) * eg.ry;
+  return smooth_models(x, C + 2, sp);
+}
+
 template <int NQ>   // NQ = ceil(P / 2) feature pairs
-__global__ void __launch_bounds__(kSvmThreads) k_ens_svm(
+__global__ void __launch_bounds__(kSvmThreads, NQ <= 4 ? 5 : 3) k_ens_svm(
     const float* __restrict__ cov, int C, int P, int64_t plane, EnsGeom eg, mb_window w,
     const float4* __restrict__ svp, const float4* __restrict__ bap, int npairs,
     const double* __restrict__ xc, const double* __restrict__ xis, double sigma, double bias, double ys, double yc,
-    double wv, int accumulate, double* __restrict__ acc) {
+    double wv, int accumulate, SmoothParams sp, int64_t acc_stride, double* __restrict__ acc) {
   __shared__ float4 s_sv[kSvmPairs * NQ];
   __shared__ float4 s_ba[kSvmPairs];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int col = w.c0 + blockIdx.x * 32 + lane;
   const int row0 = w.r0 + blockIdx.y * 16 + warp;
-  const int wc = w.c1 - w.c0;
+  const int64_t wc = acc_stride;
+  // gam / nnet / earth ride along (this kernel is MUFU / issue bound and leaves the FP64 pipe idle); evaluated
+  // first, while almost nothing is live across the out-of-line call
+  double smooth[2] = {0.0, 0.0};
+  if (sp.gam || sp.nn || sp.mars_T > 0) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int row = row0 + 8 * c;
+      if (col < w.c1 && row < w.r1) smooth[c] = smooth_cell(cov, C, plane, eg, row, col, sp);
+    }
+  }
   float2 xd[2][2 * NQ];      // features of both cells, each duplicated into the two halves of a pair
   float2 a0d[2];
   bool ok[2];
@@ -462,23 +486,24 @@ __global__ void __launch_bounds__(kSvmThreads) k_ens_svm(
     const int row = row0 + 8 * c;
     if (col < w.c1 && row < w.r1) {
       double* dst = acc + (int64_t)(row - w.r0) * wc + (col - w.c0);
-      const double v = ok[c] ? wv * ((total[c] - bias) * ys + yc) : 0.0;
-      *dst = accumulate ? *dst + v : v;
+      // last kernel of the chain: NA rule (V73: terra::predict returns NA where any layer is NA)
+      double v = __longlong_as_double(0x7ff8000000000000LL);
+      if (ok[c]) v = (accumulate ? *dst : 0.0) + wv * ((total[c] - bias) * ys + yc) + smooth[c];
+      *dst = v;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_ens_final: smooth models in float64 + combine
+// k_ens_smooth: gam / nnet / earth in float64 when no ksvm kernel carries them; closes the chain (NA rule).
+// k_ens_final : acc / total weight + precomputed TPS surface (tiled mode, tps = FALSE).
 // ---------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256) k_ens_final(const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg,
-                                                   mb_window w, SmoothParams sp, const double* __restrict__ acc,
-                                                   const double* __restrict__ tps, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_ens_smooth(const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg,
+                                                    mb_window w, SmoothParams sp, int accumulate, int64_t acc_stride,
+                                                    double* __restrict__ acc) {
   const int col = w.c0 + blockIdx.x * 32 + (threadIdx.x & 31);
   const int row = w.r0 + blockIdx.y * 8 + (threadIdx.x >> 5);
   if (col >= w.c1 || row >= w.r1) return;
-  const int64_t o = (int64_t)(row - w.r0) * (w.c1 - w.c0) + (col - w.c0);
   double x[16];
   bool anynan = false;
   for (int f = 0; f < C; ++f) {
@@ -488,11 +513,21 @@ __global__ void __launch_bounds__(256) k_ens_final(const float* __restrict__ cov
   }
   x[C] = eg.xmin + (col + 0.5) * eg.rx;
   x[C + 1] = eg.ymax - (row + 0.5) * eg.ry;
-  const int P = C + 2;
-  double s = acc ? acc[o] : 0.0;
-  if (!anynan) s += smooth_models(x, P, sp);
-  double r = s / sp.w_total;
-  if (anynan && !sp.only_gbm) r = __longlong_as_double(0x7ff8000000000000LL);
+  double* dst = acc + (int64_t)(row - w.r0) * acc_stride + (col - w.c0);
+  double s = accumulate ? *dst : 0.0;
+  if (!anynan) s += smooth_models(x, C + 2, sp);
+  if (anynan && !sp.only_gbm) s = __longlong_as_double(0x7ff8000000000000LL);
+  *dst = s;
+}
+
+__global__ void __launch_bounds__(256) k_ens_final(mb_window w, const double* __restrict__ acc, int64_t acc_stride,
+                                                   double inv_w, const double* __restrict__ tps,
+                                                   double* __restrict__ out) {
+  const int col = w.c0 + blockIdx.x * 32 + (threadIdx.x & 31);
+  const int row = w.r0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (col >= w.c1 || row >= w.r1) return;
+  const int64_t o = (int64_t)(row - w.r0) * (w.c1 - w.c0) + (col - w.c0);
+  double r = acc[(int64_t)(row - w.r0) * acc_stride + (col - w.c0)] * inv_w;
   if (tps) r += tps[o];
   out[o] = r;
 }
@@ -791,7 +826,7 @@ static void launch_trees(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
     }                                                                                                             \
     MB_LAUNCH(ctx, "k_ens_trees", st) k_ens_trees<RR><<<grid, kTreeThreads, smem, st>>>(                          \
         cov, C, plane, eg, w, e->forest_nodes.p, roots, n_rf, n_gb, e->forest_zero_leaf, rf_scale, gb_scale, base, \
-        0, acc);                                                                                                  \
+        0, acc_stride(w), acc);                                                                                   \
   } break;
   switch (R) {
     MB_TREES_CASE(1) MB_TREES_CASE(2) MB_TREES_CASE(4)
@@ -800,6 +835,8 @@ static void launch_trees(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
 #undef MB_TREES_CASE
 }
 
+static SmoothParams smooth_params(const mb_ensemble* e);
+
 template <int NQ>
 static void launch_svm(const mb_ensemble* e, const float* cov, int64_t plane, const EnsGeom& eg, const mb_window& w,
                        double* acc, int accumulate, cudaStream_t st) {
@@ -807,7 +844,7 @@ static void launch_svm(const mb_ensemble* e, const float* cov, int64_t plane, co
   dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 15) / 16);
   MB_LAUNCH(ctx, "k_ens_svm", st) k_ens_svm<NQ><<<grid, kSvmThreads, 0, st>>>(
       cov, e->C, e->P, plane, eg, w, e->svm_svp.p, e->svm_bap.p, e->svm_pairs, e->svm_xc.p, e->svm_xis.p,
-      e->svm_sigma, e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], accumulate, acc);
+      e->svm_sigma, e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], accumulate, smooth_params(e), acc_stride(w), acc);
 }
 
 static EnsGeom ens_geom(const mb_grid& g) {
@@ -816,52 +853,58 @@ static EnsGeom ens_geom(const mb_grid& g) {
 
 bool ensemble_has_heavy(const mb_ensemble* e) { return e->has[MB_R] || e->has[MB_B] || e->has[MB_V]; }
 
-// trees + svm of window w -> acc (row-major, window stride); every cell of the window is written
-void ensemble_heavy(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, const mb_window& w, double* acc,
-                    cudaStream_t st) {
+// acc <- sum_k round(w_k, 2) f_k(cell) over EVERY kept model for window w, in the padded accumulator layout
+// (acc_stride(w) x acc_rows(w) doubles); NaN where a covariate is NA (except a gbm-only ensemble, which
+// follows MissingNode).  Chain: trees -> svm (+ smooth models) | smooth; the last kernel applies the NA rule.
+void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, const mb_window& w, double* acc,
+                         cudaStream_t st) {
   const mb_grid& g = e->g;
   const int64_t plane = (int64_t)g.nrow * g.ncol;
-  const int64_t ncell = (int64_t)(w.r1 - w.r0) * (w.c1 - w.c0);
+  const int64_t astride = acc_stride(w);
   const EnsGeom eg = ens_geom(g);
+  bool started = false;
   if (e->has[MB_R] || e->has[MB_B]) {
     const int n_rf = e->has[MB_R] ? e->rf.ntrees : 0, n_gb = e->has[MB_B] ? e->gbm.ntrees : 0;
     const int* roots = e->forest_roots.p;   // rf trees first (if kept), then gbm
     if (e->only_gbm) {
-      MB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ncell, st));   // k_ens_trees_plain accumulates
+      const int64_t ncell = (int64_t)(w.r1 - w.r0) * (w.c1 - w.c0);
+      MB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * astride * (w.r1 - w.r0), st));   // k_ens_trees_plain accumulates
       MB_LAUNCH(ctx, "k_ens_trees_plain", st) k_ens_trees_plain<<<(unsigned)((ncell + kTreeThreads - 1) / kTreeThreads), kTreeThreads, 0, st>>>(
           cov, C, plane, eg, w, e->forest_nodes.p, roots, 0, 0.0, 0.0, e->forest_nodes.p, roots, n_gb, e->w[MB_B],
-          e->gb_initF, 1, acc);
-    } else {
-      launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, st);
+          e->gb_initF, 1, astride, acc);
+      MB_CUDA(cudaGetLastError());
+      return;                                // gbm alone: numbers on NA cells too, nothing else to add
     }
+    launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, st);
+    started = true;
   }
   if (e->has[MB_V]) {
-    const int accumulate = (e->has[MB_R] || e->has[MB_B]) ? 1 : 0;
     switch ((e->P + 1) / 2) {
-#define MB_SVM_CASE(n) case n: launch_svm<n>(e, cov, plane, eg, w, acc, accumulate, st); break;
+#define MB_SVM_CASE(n) case n: launch_svm<n>(e, cov, plane, eg, w, acc, started ? 1 : 0, st); break;
       MB_SVM_CASE(1) MB_SVM_CASE(2) MB_SVM_CASE(3) MB_SVM_CASE(4) MB_SVM_CASE(5) MB_SVM_CASE(6) MB_SVM_CASE(7)
       MB_SVM_CASE(8)
 #undef MB_SVM_CASE
     }
+  } else {
+    dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
+    MB_LAUNCH(ctx, "k_ens_smooth", st) k_ens_smooth<<<grid, 256, 0, st>>>(cov, C, plane, eg, w, smooth_params(e), started ? 1 : 0, astride, acc);
   }
   MB_CUDA(cudaGetLastError());
 }
 
-// smooth models + acc + normalisation + NA rule + TPS (spline evaluated in the same pass, or a precomputed
-// surface, or none) -> out.  acc may be NULL when no tree / svm model is kept.
-void ensemble_finish(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, const mb_spline* spline,
-                     const double* tps_surface, const mb_window& w, const double* acc, double* out, cudaStream_t st) {
-  const mb_grid& g = e->g;
-  const int64_t plane = (int64_t)g.nrow * g.ncol;
-  const EnsGeom eg = ens_geom(g);
+// acc / total weight + TPS (spline evaluated in the same pass by the grid-evaluation kernel, or a precomputed
+// surface, or none) -> out  (V73:619, 906-907)
+void ensemble_finish(mb_ctx* ctx, const mb_ensemble* e, const mb_spline* spline, const double* tps_surface,
+                     const mb_window& w, const double* acc, double* out, cudaStream_t st) {
+  const double inv_w = 1.0 / e->w_total;
   if (spline) {
     MB_REQUIRE(!tps_surface, "pass either a spline or a precomputed TPS surface, not both");
-    EnsFuse fz{cov, C, plane, eg, smooth_params(e), acc};
-    tps_eval_fast(ctx, spline, g, w, out, w.c1 - w.c0, st, &fz);
+    const AccFuse fz{acc, acc_stride(w), inv_w};
+    tps_eval_fast(ctx, spline, e->g, w, out, w.c1 - w.c0, st, &fz);
     return;
   }
   dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
-  MB_LAUNCH(ctx, "k_ens_final", st) k_ens_final<<<grid, 256, 0, st>>>(cov, C, plane, eg, w, smooth_params(e), acc, tps_surface, out);
+  MB_LAUNCH(ctx, "k_ens_final", st) k_ens_final<<<grid, 256, 0, st>>>(w, acc, acc_stride(w), inv_w, tps_surface, out);
   MB_CUDA(cudaGetLastError());
 }
 
@@ -870,12 +913,9 @@ void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, c
   check_window(&e->g, wp);
   const mb_window w = *wp;
   MB_REQUIRE(C == e->C, "number of covariate planes does not match the model descriptors (P = C + 2)");
-  double* acc = nullptr;
-  if (ensemble_has_heavy(e)) {
-    acc = ctx->arena.take_n<double>((size_t)(w.r1 - w.r0) * (w.c1 - w.c0));
-    ensemble_heavy(ctx, e, cov, C, w, acc, st);
-  }
-  ensemble_finish(ctx, e, cov, C, spline, tps_surface, w, acc, out, st);
+  double* acc = ctx->arena.take_n<double>((size_t)(acc_stride(w) * acc_rows(w)));
+  ensemble_accumulate(ctx, e, cov, C, w, acc, st);
+  ensemble_finish(ctx, e, spline, tps_surface, w, acc, out, st);
 }
 
 void ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X, int n, double* out_host) {

@@ -8,6 +8,10 @@ namespace mb {
 void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, double lambda, mb_spline** out);
 void fit_release(mb_ctx* ctx);   // library handles owned on behalf of the context
 
+// sytrd.cu - in-house tridiagonalisation + Sturm bisection for the GCV fit
+void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L, std::vector<double>& diag,
+                     std::vector<double>& off, std::vector<double>& eta, cudaStream_t st);
+
 // ensemble.cu - terra::predict x6 + weighted sum (V73:468-619) + part-5 combine (V73:906-907)
 mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, const char* kept, const double* w,
                              double w_total);
@@ -18,11 +22,11 @@ void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int 
 // the two halves of ensemble_eval, exposed so that mltps_predict can run the TPS fit between them
 bool ensemble_has_heavy(const mb_ensemble* e);
 int ensemble_ncov(const mb_ensemble* e);
-void ensemble_heavy(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_window& w, double* acc,
-                    cudaStream_t st);
-void ensemble_finish(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_spline* spline,
-                     const double* tps_surface_dev, const mb_window& w, const double* acc, double* out_dev,
-                     cudaStream_t st);
+// acc: padded accumulator layout (AccFuse, common.cuh): acc_stride(w) * acc_rows(w) doubles
+void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_window& w,
+                         double* acc, cudaStream_t st);
+void ensemble_finish(mb_ctx* ctx, const mb_ensemble* e, const mb_spline* spline, const double* tps_surface_dev,
+                     const mb_window& w, const double* acc, double* out_dev, cudaStream_t st);
 void ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X, int n, double* out_host);
 
 // tiles.cu - mltps part 3/4 (V73:649-895), machisplin.tiles.merge (V73:1392-1548), gram, gather

@@ -12,7 +12,6 @@
 //                    directly.  Everything is float64: the coefficients c cancel by up to 1e8
 //                    (T'c = 0), so float32 pair terms are not accurate enough.
 #include "common.cuh"
-#include "ens_device.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -339,151 +338,352 @@ __global__ void __launch_bounds__(((P * P + 31) / 32) * 32) k_far_transform(
 }
 
 // -----------------------------------------------------------------------------------------
-// Accuracy estimate of the mixed-precision leaf path (one warp per leaf box, max over boxes):
-//   far : the k >= 1 columns of the expansion are evaluated in float32 -> (P + 2) 2^-24 sum_{(j,k) != (0,0)} |A_jk|
-//   near: pair terms in float32 with box-local coordinates      -> 4 2^-24 phi(r_max) sum_{3x3} |c_i E/2|
-// k_leaf compares the estimate with its threshold and picks the float64 or the mixed code path itself,
-// so the decision costs no host round trip.
+// Leaf preparation (one warp per leaf box):
+//  (1) accuracy estimate of the mixed-precision leaf path, max over boxes:
+//        far : the k >= 1 columns of the expansion are evaluated in float32 -> (P + 2) 2^-24 sum_{(j,k) != (0,0)} |A_jk|
+//        near: pair terms in float32 with box-local coordinates      -> 4 2^-24 phi(r_max) sum_{3x3} |c_i E/2|
+//      The leaf kernels compare the estimate with their threshold on the device (no host round trip):
+//      k_leaf_stream runs when the mixed path is accurate enough, k_leaf_f64 otherwise.
+//  (2) the near list of the box - the knots of its 3 x 3 neighbourhood in box-local float32 coordinates
+//      (x - ox, y - oy, c E/2 ln2) - as one 256-byte block {count, overflow offset, 15 inline entries}
+//      that k_leaf_stream fetches with a single bulk copy; longer lists go to an overflow array.
 // -----------------------------------------------------------------------------------------
+constexpr int kNearInline = 15;
+struct __align__(16) NearBlk {
+  int cnt, off, pad0, pad1;
+  float4 e[kNearInline];
+};
+static_assert(sizeof(NearBlk) == 256, "NearBlk must be one 256-byte record");
+
 template <int P>
-__global__ void __launch_bounds__(256) k_leaf_bounds(Lattice lat, LevelInfo leaf, const double* __restrict__ coef,
-                                                     const int* __restrict__ start, const double4* __restrict__ knots,
-                                                     double phi_max, unsigned long long* __restrict__ est_bits) {
+__global__ void __launch_bounds__(256) k_leaf_prep(Lattice lat, LevelInfo leaf, const double* __restrict__ coef,
+                                                   const int* __restrict__ start, const double4* __restrict__ knots,
+                                                   double phi_max, unsigned long long* __restrict__ est_bits,
+                                                   NearBlk* __restrict__ near, float4* __restrict__ near_over,
+                                                   int* __restrict__ over_cursor) {
   const int lane = threadIdx.x & 31;
   const int box = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (box >= leaf.nI * leaf.nJ) return;
   const double* A = coef + leaf.coef_off + (size_t)box * (P * P);
   double v = 0.0;
   for (int i = 1 + lane; i < P * P; i += 32) v += fabs(A[i]);
+  const int I = lat.offx + box % leaf.nI, J = lat.offy + box / leaf.nI;
+  int ra = 0, rlen = 0;
   double wsum = 0.0;
   if (lane < 9) {
-    const int I = lat.offx + box % leaf.nI + lane % 3 - 1, J = lat.offy + box / leaf.nI + lane / 3 - 1;
+    const int i = I + lane % 3 - 1, j = J + lane / 3 - 1;
     const int nside = 1 << lat.L;
-    if (I >= 0 && J >= 0 && I < nside && J < nside) {
-      const uint32_t z = morton(I, J);
-      for (int k = start[z]; k < start[z + 1]; ++k) wsum += fabs(knots[k].w);
+    if (i >= 0 && j >= 0 && i < nside && j < nside) {
+      const uint32_t z = morton(i, j);
+      ra = start[z];
+      rlen = start[z + 1] - ra;
+      for (int k = 0; k < rlen; ++k) wsum += fabs(knots[ra + k].w);
     }
   }
+  int tot = rlen;
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
     v += __shfl_xor_sync(0xffffffffu, v, o);
     wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
   }
   if (lane == 0) {
     const double est = 5.9604644775390625e-08 * ((P + 2) * v + 4.0 * phi_max * wsum);
     atomicMax(est_bits, (unsigned long long)__double_as_longlong(est));   // est >= 0: bit order = value order
   }
+  int off = 0;
+  if (tot > kNearInline) {
+    if (lane == 0) off = atomicAdd(over_cursor, tot);
+    off = __shfl_sync(0xffffffffu, off, 0);
+  }
+  NearBlk* nb = near + box;
+  if (lane == 0) { nb->cnt = tot; nb->off = off; nb->pad0 = 0; nb->pad1 = 0; }
+  const double ox = lat.sxo + lat.hx * I, oy = lat.syo + lat.hy * J;
+  for (int base = 0; base < tot; base += 32) {
+    int f = base + lane, idx = -1;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int la = __shfl_sync(0xffffffffu, ra, r), ll = __shfl_sync(0xffffffffu, rlen, r);
+      if (f >= 0 && f < ll) idx = la + f;
+      f -= ll;
+    }
+    if (idx >= 0) {
+      const double4 kn = ldg4(&knots[idx]);
+      const float4 ent = make_float4((float)(kn.x - ox), (float)(kn.y - oy), (float)(kn.w * 0.69314718055994531), 0.f);
+      if (tot <= kNearInline) nb->e[base + lane] = ent;
+      else near_over[off + base + lane] = ent;
+    }
+  }
 }
 
 // -----------------------------------------------------------------------------------------
-// Leaf kernel (the grid-evaluation kernel): one CTA per leaf box (32 columns x bh rows), lane = column.
-//   G[lr][k] = sum_j T_j(ty_lr) A[j][k]          (collapse y once per box row, float64)
-//   far      = sum_k G[lr][k] T_k(tx_lane)       (T_k(tx_lane) lives in registers)
-//   near     = sum over the knots of the 3 x 3 box neighbourhood
-// Two code paths, chosen per launch from the device-side estimate above:
-//   float64  everything in float64 with the table-driven log (always correct)
-//   mixed    G[lr][0] in float64; the k >= 1 columns (the variation of the far field inside the box)
-//            and the near pair terms in float32 with box-local coordinates and MUFU.LG2.  The large,
-//            cancelling part of the sum never leaves float64, so the result keeps ~1e-9 relative accuracy
-//            while the per-cell float64 work drops from ~30 to 2 operations: the kernel becomes a pure
-//            HBM-write stream (8 B / cell).
-// With an EnsFuse descriptor the same pass finishes mltps part 2 + 5: covariates -> gam / nnet / earth,
-// + trees / svm accumulator, / total weight, NA rule, + TPS (V73:604-620, 906-907).
+// async-copy plumbing of k_leaf_stream: mbarrier + cp.async.bulk (the TMA unit's 1-D bulk copy, UBLKCP)
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// -----------------------------------------------------------------------------------------
+// k_leaf_stream - the grid-evaluation kernel (mixed-precision path).
+// Persistent CTAs; CTA c owns leaf boxes c, c + G, c + 2G ... (row-major over the window: concurrently active
+// CTAs write neighbouring boxes).  Per box the inputs are three bulk copies into a 3-stage shared-memory ring
+// (the P x P expansion block, the 256-byte near block and - with an accumulator - the box's 32 x bh tile of
+// it, one 256-byte copy per row), completion tracked by one mbarrier per stage; nothing is staged through
+// registers, so the copies of the next boxes are in flight while the current one is computed.
+//   collapse(i+1)  G[lr][k] = sum_j T_j(ty_lr) A[j][k]   float64; column 0 kept in float64, columns k >= 1
+//                  (the variation of the far field inside the box) rounded to float32
+//   rows(i)        lane = column: far = G0[lr] + sum_{k>=1} Gf[lr][k] T_k(tx_lane)  (float32 FMA, T_k in registers)
+//                  near = sum over the near list, float32 with box-local coordinates and MUFU.LG2
+//                  out  = far + near (+ acc * inv_w : mltps part 5, NaN in acc = NA cell)
+// collapse(i+1) and rows(i) share one __syncthreads per box (G is double-buffered).  The large, cancelling part
+// of the sum never leaves float64, so the result keeps ~1e-9 relative accuracy while the per-cell work is
+// P - 1 FFMA + one conversion + one float64 add: the kernel is an HBM stream (8 B written per cell, + 8 B read
+// with an accumulator).
 // -----------------------------------------------------------------------------------------
 constexpr int kLeafThreads = 256;
+constexpr int kLeafStages = 3;
+__host__ __device__ constexpr int leaf_gfs(int P) { return ((P - 1 + 3) / 4) * 4; }
+__host__ __device__ inline int leaf_stage_bytes(int P, int bh, bool acc) {
+  return (P * P * 8 + 256 + (acc ? bh * 256 : 0) + 127) / 128 * 128;
+}
+
+template <int P, bool kAcc>
+__global__ void __launch_bounds__(kLeafThreads) k_leaf_stream(
+    Lattice lat, LevelInfo leaf, mb_window w, const double* __restrict__ coef, const NearBlk* __restrict__ near,
+    const float4* __restrict__ near_over, const unsigned long long* __restrict__ est_bits, double mixed_threshold,
+    AccFuse fz, double* __restrict__ out, int64_t stride) {
+  static_assert(P % 2 == 0, "P must be even");
+  if (!(__longlong_as_double((long long)__ldg(est_bits)) <= mixed_threshold)) return;   // k_leaf_f64 runs instead
+  constexpr int GFS = leaf_gfs(P);
+  extern __shared__ __align__(128) unsigned char leaf_smem[];
+  __shared__ __align__(8) uint64_t s_full[kLeafStages];
+  const int bh = lat.bh;
+  const int stage_bytes = leaf_stage_bytes(P, bh, kAcc);
+  double* s_G0 = reinterpret_cast<double*>(leaf_smem + kLeafStages * stage_bytes);   // [2][bh]
+  float* s_Gf = reinterpret_cast<float*>(s_G0 + 2 * bh);                             // [2][bh][GFS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nboxes = lat.nbx * lat.nby;
+  const int nmine = (nboxes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kLeafStages; ++s) mbar_init(&s_full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  constexpr uint32_t kRecBytes = P * P * 8 + 256;
+  auto issue = [&](int i) {   // warp 0: bulk copies of this CTA's i-th box into stage i % kLeafStages
+    const int s = i % kLeafStages;
+    const int b = blockIdx.x + i * gridDim.x;
+    unsigned char* sp = leaf_smem + s * stage_bytes;
+    if (lane == 0) {
+      mbar_expect_tx(&s_full[s], kRecBytes + (kAcc ? (uint32_t)bh * 256u : 0u));
+      bulk_g2s(sp, coef + leaf.coef_off + (size_t)b * (P * P), P * P * 8, &s_full[s]);
+      bulk_g2s(sp + P * P * 8, near + b, 256, &s_full[s]);
+    }
+    if (kAcc) {
+      __syncwarp();
+      const int bi = b % lat.nbx, bj = b / lat.nbx;
+      const double* src = fz.acc + (int64_t)bj * bh * fz.stride + bi * 32;
+      for (int r = lane; r < bh; r += 32) bulk_g2s(sp + kRecBytes + r * 256, src + (int64_t)r * fz.stride, 256, &s_full[s]);
+    }
+  };
+  if (warp == 0)
+    for (int i = 0; i < min(kLeafStages, nmine); ++i) issue(i);
+
+  float Txf[P];
+  {
+    const float tx = (2.0f * lane + 1.0f) / 32.0f - 1.0f;   // exact in float32
+    Txf[0] = 1.0f;
+    Txf[1] = tx;
+#pragma unroll
+    for (int k = 2; k < P; ++k) Txf[k] = 2.0f * tx * Txf[k - 1] - Txf[k - 2];
+  }
+  const float cxl = (float)(lat.hx * ((lane + 0.5) / 32.0));
+  const double hyb = lat.hy / bh, inv_bh = 1.0 / bh;
+
+  auto collapse = [&](int i) {   // expansion block of box i -> G buffer i & 1
+    const double2* A2 = reinterpret_cast<const double2*>(leaf_smem + (i % kLeafStages) * stage_bytes);
+    double* g0buf = s_G0 + (i & 1) * bh;
+    float* gfbuf = s_Gf + (i & 1) * bh * GFS;
+    for (int o = tid; o < bh * (P / 2); o += kLeafThreads) {
+      const int lr = o / (P / 2), kp = o % (P / 2);
+      const double ty = (2.0 * lr + 1.0) * inv_bh - 1.0;
+      double t0 = 1.0, t1 = ty;
+      const double2 a0 = A2[kp], a1 = A2[(P / 2) + kp];
+      double ga = fma(t1, a1.x, a0.x), gb = fma(t1, a1.y, a0.y);
+#pragma unroll
+      for (int j = 2; j < P; ++j) {
+        const double t2 = 2.0 * ty * t1 - t0;
+        const double2 a = A2[j * (P / 2) + kp];
+        ga = fma(t2, a.x, ga);
+        gb = fma(t2, a.y, gb);
+        t0 = t1; t1 = t2;
+      }
+      if (kp == 0) { g0buf[lr] = ga; gfbuf[lr * GFS] = (float)gb; }
+      else { gfbuf[lr * GFS + 2 * kp - 1] = (float)ga; gfbuf[lr * GFS + 2 * kp] = (float)gb; }
+    }
+  };
+
+  mbar_wait(&s_full[0], 0);
+  collapse(0);
+  __syncthreads();
+  for (int i = 0; i < nmine; ++i) {
+    if (i + 1 < nmine) {
+      mbar_wait(&s_full[(i + 1) % kLeafStages], ((i + 1) / kLeafStages) & 1);
+      collapse(i + 1);
+    }
+    // ---- rows of box i ---------------------------------------------------------------------------
+    {
+      const unsigned char* sp = leaf_smem + (i % kLeafStages) * stage_bytes;
+      const NearBlk* nb = reinterpret_cast<const NearBlk*>(sp + P * P * 8);
+      const double* accT = reinterpret_cast<const double*>(sp + kRecBytes);
+      const int cnt = nb->cnt;
+      const int b = blockIdx.x + i * gridDim.x;
+      const int bi = b % lat.nbx, bj = b / lat.nbx;
+      const int col = w.c0 + bi * 32 + lane;
+      const int row_base = w.r0 + bj * bh;
+      const double* g0buf = s_G0 + (i & 1) * bh;
+      const float* gfbuf = s_Gf + (i & 1) * bh * GFS;
+      for (int lr = warp; lr < bh; lr += kLeafThreads / 32) {
+        const int row = row_base + lr;
+        if (row >= w.r1) break;
+        const float4* g4 = reinterpret_cast<const float4*>(gfbuf + lr * GFS);
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < GFS / 4; ++q) {
+          const float4 g = g4[q];
+          if (4 * q + 1 < P) a = fmaf(g.x, Txf[4 * q + 1], a);
+          if (4 * q + 2 < P) a = fmaf(g.y, Txf[4 * q + 2], a);
+          if (4 * q + 3 < P) a = fmaf(g.z, Txf[4 * q + 3], a);
+          if (4 * q + 4 < P) a = fmaf(g.w, Txf[4 * q + 4], a);
+        }
+        if (cnt > 0) {
+          const float cyl = (float)(hyb * (lr + 0.5));
+          if (cnt <= kNearInline) {
+            for (int q = 0; q < cnt; ++q) {
+              const float4 kn = nb->e[q];
+              const float dx = cxl - kn.x, dy = cyl - kn.y;
+              const float r2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-20f);
+              a = fmaf(kn.z * r2, __log2f(r2), a);
+            }
+          } else {
+            const float4* src = near_over + nb->off;
+            for (int q = 0; q < cnt; ++q) {
+              const float4 kn = __ldg(&src[q]);
+              const float dx = cxl - kn.x, dy = cyl - kn.y;
+              const float r2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-20f);
+              a = fmaf(kn.z * r2, __log2f(r2), a);
+            }
+          }
+        }
+        double v = g0buf[lr] + (double)a;
+        if (kAcc) v = fma(accT[lr * 32 + lane], fz.inv_w, v);
+        if (col < w.c1) __stcs(out + (int64_t)(row - w.r0) * stride + (col - w.c0), v);
+      }
+    }
+    __syncthreads();   // stage i % kLeafStages and G buffer i & 1 are free again
+    if (warp == 0 && i + kLeafStages < nmine) issue(i + kLeafStages);
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// k_leaf_f64 - the same evaluation entirely in float64 with the table-driven log (always valid; runs when the
+// device-side estimate says the mixed path would not be accurate enough, or on request).  One leaf box per loop
+// iteration of a persistent CTA, lane = column:
+//   G[lr][k] = sum_j T_j(ty_lr) A[j][k]      (collapse y once per box row)
+//   far      = sum_k G[lr][k] T_k(tx_lane)   (T_k(tx_lane) lives in registers)
+//   near     = sum over the knots of the 3 x 3 box neighbourhood, streamed through shared memory
+// -----------------------------------------------------------------------------------------
 constexpr int kNearCap = 256;
 
-template <int P, bool kFuse>
-__global__ void __launch_bounds__(kLeafThreads) k_leaf(
+template <int P, bool kAcc>
+__global__ void __launch_bounds__(kLeafThreads) k_leaf_f64(
     Lattice lat, LevelInfo leaf, mb_window w, const double* __restrict__ coef, const int* __restrict__ start,
     const double4* __restrict__ knots, const double2* __restrict__ logtab,
-    const unsigned long long* __restrict__ est_bits, double mixed_threshold, EnsFuse fz,
+    const unsigned long long* __restrict__ est_bits, double mixed_threshold, AccFuse fz,
     double* __restrict__ out, int64_t stride) {
+  if (__longlong_as_double((long long)__ldg(est_bits)) <= mixed_threshold) return;   // k_leaf_stream ran instead
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* s_log = reinterpret_cast<double2*>(smem_raw);              // 256
   double4* s_near = reinterpret_cast<double4*>(s_log + 256);          // kNearCap
   double* s_A = reinterpret_cast<double*>(s_near + kNearCap);         // P*P
-  double* s_G = s_A + P * P;                                          // bh*P (float64 path) | bh (mixed: column 0)
-  float* s_Gf = reinterpret_cast<float*>(s_G + lat.bh * P);           // bh*(P-1) (mixed path)
+  double* s_G = s_A + P * P;                                          // bh*P
   __shared__ int s_rng[9][2];
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int bi = blockIdx.x, bj = blockIdx.y;
-  const int I = lat.offx + bi, J = lat.offy + bj;
-  const int box = bj * leaf.nI + bi;   // leaf level: I0 = offx, J0 = offy
-  const bool mixed = __longlong_as_double((long long)__ldg(est_bits)) <= mixed_threshold;
-  if (!mixed)
-    for (int i = tid; i < 256; i += kLeafThreads) s_log[i] = logtab[i];
-  for (int i = tid; i < P * P; i += kLeafThreads) s_A[i] = coef[leaf.coef_off + (size_t)box * (P * P) + i];
-  if (tid < 9) {
-    const int i = I + tid % 3 - 1, j = J + tid / 3 - 1;
-    const int nside = 1 << lat.L;
-    int a = 0, b = 0;
-    if (i >= 0 && j >= 0 && i < nside && j < nside) {
-      const uint32_t z = morton(i, j);
-      a = start[z];
-      b = start[z + 1];
-    }
-    s_rng[tid][0] = a;
-    s_rng[tid][1] = b;
-  }
-  __syncthreads();
-  // collapse y: thread -> (lr, k)
-  for (int o = tid; o < lat.bh * P; o += kLeafThreads) {
-    const int lr = o / P, k = o % P;
-    const double ty = (2.0 * lr + 1.0) / lat.bh - 1.0;
-    double t0 = 1.0, t1 = ty, g = s_A[k];
-    if (P > 1) g = fma(t1, s_A[P + k], g);
-#pragma unroll
-    for (int j = 2; j < P; ++j) {
-      const double t2 = 2.0 * ty * t1 - t0;
-      g = fma(t2, s_A[j * P + k], g);
-      t0 = t1; t1 = t2;
-    }
-    if (!mixed) s_G[o] = g;
-    else if (k == 0) s_G[lr] = g;
-    else s_Gf[lr * (P - 1) + (k - 1)] = (float)g;
-  }
-  int tot = 0;
-#pragma unroll
-  for (int r = 0; r < 9; ++r) tot += s_rng[r][1] - s_rng[r][0];
-  const int col = w.c0 + bi * 32 + lane;
-  const int row_base = w.r0 + bj * lat.bh;
   constexpr int kWarps = kLeafThreads / 32;
-  // per-cell epilogue: plain store, or the fused ensemble combine
-  auto finish = [&](int row, double tps, double* dst) {
-    if (!kFuse) { *dst = tps; return; }
-    double x[16];
-    bool anynan = false;
-    for (int f = 0; f < fz.C; ++f) {
-      const float v = __ldg(&fz.cov[f * fz.plane + (int64_t)row * fz.eg.ncol + col]);
-      anynan |= (v != v);
-      x[f] = (double)v;
-    }
-    x[fz.C] = fz.eg.xmin + (col + 0.5) * fz.eg.rx;
-    x[fz.C + 1] = fz.eg.ymax - (row + 0.5) * fz.eg.ry;
-    double s = fz.acc ? fz.acc[(int64_t)(row - w.r0) * (w.c1 - w.c0) + (col - w.c0)] : 0.0;
-    if (!anynan) s += smooth_models(x, fz.C + 2, fz.sp);
-    double r = s / fz.sp.w_total;
-    if (anynan && !fz.sp.only_gbm) r = __longlong_as_double(0x7ff8000000000000LL);
-    *dst = r + tps;
-  };
-  if (mixed) {
-    // ---- mixed path ----------------------------------------------------------------------------
-    float Txf[P];
-    {
-      const float tx = (2.0f * lane + 1.0f) / 32.0f - 1.0f;   // exact in float32
-      Txf[0] = 1.0f;
-      if (P > 1) Txf[1] = tx;
+  for (int i = tid; i < 256; i += kLeafThreads) s_log[i] = logtab[i];
+  double Tx[P];
+  {
+    const double tx = (2.0 * lane + 1.0) / 32.0 - 1.0;
+    Tx[0] = 1.0;
+    if (P > 1) Tx[1] = tx;
 #pragma unroll
-      for (int k = 2; k < P; ++k) Txf[k] = 2.0f * tx * Txf[k - 1] - Txf[k - 2];
+    for (int k = 2; k < P; ++k) Tx[k] = 2.0 * tx * Tx[k - 1] - Tx[k - 2];
+  }
+  const int nboxes = lat.nbx * lat.nby;
+  for (int box = blockIdx.x; box < nboxes; box += gridDim.x) {
+    const int bi = box % lat.nbx, bj = box / lat.nbx;
+    const int I = lat.offx + bi, J = lat.offy + bj;
+    __syncthreads();   // previous box done with s_A / s_G / s_near / s_rng
+    for (int i = tid; i < P * P; i += kLeafThreads) s_A[i] = coef[leaf.coef_off + (size_t)box * (P * P) + i];
+    if (tid < 9) {
+      const int i = I + tid % 3 - 1, j = J + tid / 3 - 1;
+      const int nside = 1 << lat.L;
+      int a = 0, b = 0;
+      if (i >= 0 && j >= 0 && i < nside && j < nside) {
+        const uint32_t z = morton(i, j);
+        a = start[z];
+        b = start[z + 1];
+      }
+      s_rng[tid][0] = a;
+      s_rng[tid][1] = b;
     }
-    float4* s_nf = reinterpret_cast<float4*>(s_near);     // box-local (x, y, c E/2 ln2, -)
-    const double ox = lat.sxo + lat.hx * I, oy = lat.syo + lat.hy * J;
-    const float cxl = (float)(lat.hx * ((lane + 0.5) / 32.0));
+    __syncthreads();
+    // collapse y: thread -> (lr, k)
+    for (int o = tid; o < lat.bh * P; o += kLeafThreads) {
+      const int lr = o / P, k = o % P;
+      const double ty = (2.0 * lr + 1.0) / lat.bh - 1.0;
+      double t0 = 1.0, t1 = ty, g = s_A[k];
+      if (P > 1) g = fma(t1, s_A[P + k], g);
+#pragma unroll
+      for (int j = 2; j < P; ++j) {
+        const double t2 = 2.0 * ty * t1 - t0;
+        g = fma(t2, s_A[j * P + k], g);
+        t0 = t1; t1 = t2;
+      }
+      s_G[o] = g;
+    }
+    int tot = 0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) tot += s_rng[r][1] - s_rng[r][0];
+    const int col = w.c0 + bi * 32 + lane;
+    const int row_base = w.r0 + bj * lat.bh;
+    const double sx = lat.sxo + lat.hx * (I + (lane + 0.5) / 32.0);
+    // knots of the 3 x 3 neighbourhood are streamed through shared memory kNearCap at a time;
+    // one chunk is the common case (about one knot per box).
     int base = 0;
     do {
-      const int n = min(2 * kNearCap, tot - base);
+      const int n = min(kNearCap, tot - base);
       __syncthreads();
       for (int i = tid; i < n; i += kLeafThreads) {
         int f = base + i, idx = 0;
@@ -493,93 +693,36 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf(
           if (f >= 0 && f < len) idx = s_rng[r][0] + f;
           f -= len;
         }
-        const double4 kn = ldg4(&knots[idx]);
-        s_nf[i] = make_float4((float)(kn.x - ox), (float)(kn.y - oy), (float)(kn.w * 0.69314718055994531), 0.f);
+        s_near[i] = ldg4(&knots[idx]);
       }
       __syncthreads();
       for (int lr = warp; lr < lat.bh; lr += kWarps) {
         const int row = row_base + lr;
         if (row >= w.r1) break;
-        const float cyl = (float)(lat.hy * ((lr + 0.5) / lat.bh));
+        const double sy = lat.syo + lat.hy * (J + (lr + 0.5) / lat.bh);
         double* dst = out + (int64_t)(row - w.r0) * stride + (col - w.c0);
-        float a = 0.f;
+        double a = 0.0;
         if (base == 0) {
 #pragma unroll
-          for (int k = 1; k < P; ++k) a = fmaf(s_Gf[lr * (P - 1) + (k - 1)], Txf[k], a);
+          for (int k = 0; k < P; ++k) a = fma(s_G[lr * P + k], Tx[k], a);
+        } else if (col < w.c1) {
+          a = *dst;
         }
-#pragma unroll 4
+#pragma unroll 2
         for (int i = 0; i < n; ++i) {
-          const float4 kn = s_nf[i];
-          const float dx = cxl - kn.x, dy = cyl - kn.y;
-          const float r2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-20f);
-          a = fmaf(kn.z * r2, __log2f(r2), a);
+          const double4 kn = s_near[i];
+          const double dx = sx - kn.x, dy = sy - kn.y;
+          const double r2 = fmax(fma(dx, dx, dy * dy), kD2Clamp);
+          a = fma(kn.w * r2, tlog(r2, s_log), a);
         }
         if (col < w.c1) {
-          if (base + n >= tot) {
-            const double tps = (base == 0 ? s_G[lr] : *dst) + (double)a;
-            finish(row, tps, dst);
-          } else {
-            *dst = (base == 0 ? s_G[lr] : *dst) + (double)a;
-          }
+          if (kAcc && base + n >= tot) a = fma(fz.acc[(int64_t)(row - w.r0) * fz.stride + (col - w.c0)], fz.inv_w, a);
+          *dst = a;
         }
       }
-      base += 2 * kNearCap;
+      base += kNearCap;
     } while (base < tot);
-    return;
   }
-  // ---- float64 path ------------------------------------------------------------------------------
-  double Tx[P];
-  {
-    const double tx = (2.0 * lane + 1.0) / 32.0 - 1.0;
-    Tx[0] = 1.0;
-    if (P > 1) Tx[1] = tx;
-#pragma unroll
-    for (int k = 2; k < P; ++k) Tx[k] = 2.0 * tx * Tx[k - 1] - Tx[k - 2];
-  }
-  const double sx = lat.sxo + lat.hx * (I + (lane + 0.5) / 32.0);
-  // knots of the 3 x 3 neighbourhood are streamed through shared memory kNearCap at a time;
-  // one chunk is the common case (about one knot per box).
-  int base = 0;
-  do {
-    const int n = min(kNearCap, tot - base);
-    __syncthreads();
-    for (int i = tid; i < n; i += kLeafThreads) {
-      int f = base + i, idx = 0;
-#pragma unroll
-      for (int r = 0; r < 9; ++r) {
-        const int len = s_rng[r][1] - s_rng[r][0];
-        if (f >= 0 && f < len) idx = s_rng[r][0] + f;
-        f -= len;
-      }
-      s_near[i] = ldg4(&knots[idx]);
-    }
-    __syncthreads();
-    for (int lr = warp; lr < lat.bh; lr += kWarps) {
-      const int row = row_base + lr;
-      if (row >= w.r1) break;
-      const double sy = lat.syo + lat.hy * (J + (lr + 0.5) / lat.bh);
-      double* dst = out + (int64_t)(row - w.r0) * stride + (col - w.c0);
-      double a = 0.0;
-      if (base == 0) {
-#pragma unroll
-        for (int k = 0; k < P; ++k) a = fma(s_G[lr * P + k], Tx[k], a);
-      } else if (col < w.c1) {
-        a = *dst;
-      }
-#pragma unroll 2
-      for (int i = 0; i < n; ++i) {
-        const double4 kn = s_near[i];
-        const double dx = sx - kn.x, dy = sy - kn.y;
-        const double r2 = fmax(fma(dx, dx, dy * dy), kD2Clamp);
-        a = fma(kn.w * r2, tlog(r2, s_log), a);
-      }
-      if (col < w.c1) {
-        if (base + n >= tot) finish(row, a, dst);
-        else *dst = a;
-      }
-    }
-    base += kNearCap;
-  } while (base < tot);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -596,28 +739,33 @@ static int choose_p(const mb_ctx* ctx, const mb_spline* s) {
   return 16;
 }
 
-struct FastPlan {
-  Lattice lat;
-  LevelInfo leaf;
-  const double* coef;
-  const int* start;
-  const double4* knots;
-  const unsigned long long* est_bits;
-  double mixed_threshold;
-};
+
+template <class K>
+static int leaf_grid(mb_ctx* ctx, K kernel, size_t smem, int nboxes) {
+  int occ = 0;
+  MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+  MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kLeafThreads, smem));
+  if (occ < 1) throw Error(MB_E_UNSUPPORTED, "leaf kernel does not fit on an SM (leaf box too tall)");
+  return std::max(1, std::min(nboxes, occ * ctx->sm_count));
+}
 
 template <int P>
 static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const std::vector<LevelInfo>& levels,
                      size_t coef_total, size_t part_total, const std::vector<int>& start,
                      const std::vector<double4>& sorted, const mb_window& w, double* out, int64_t stride,
-                     const EnsFuse* fuse, cudaStream_t st) {
+                     const AccFuse* fuse, cudaStream_t st) {
   ChebTables* tabs = get_tables(ctx, P);
   Arena& ar = ctx->arena;
   const int* d_start = ar.upload(start.data(), start.size(), st);
   const double4* d_knots = ar.upload(sorted.data(), sorted.size(), st);
   double* d_coef = ar.take_n<double>(coef_total);
   double* d_part = ar.take_n<double>(part_total);
-  unsigned long long* d_est = ar.take_n<unsigned long long>(1);
+  // {estimate bits, overflow cursor}
+  unsigned long long* d_est = ar.take_n<unsigned long long>(2);
+  int* d_cursor = reinterpret_cast<int*>(d_est + 1);
+  const int nboxes = lat.nbx * lat.nby;
+  NearBlk* d_near = ar.take_n<NearBlk>(nboxes);
+  float4* d_over = ar.take_n<float4>(9 * sorted.size() + 1);
   constexpr int threads = ((P * P + 31) / 32) * 32;
   for (size_t li = 0; li < levels.size(); ++li) {
     const LevelInfo& lv = levels[li];
@@ -634,34 +782,40 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
   const double r2max = 4.0 * (lat.hx * lat.hx + lat.hy * lat.hy);
   if (ctx->eval_precision == 1 || (ctx->eval_precision == 0 && ctx->cheb_p != 0) || r2max >= 0.3) thr = -1.0;
   if (ctx->eval_precision == 2) thr = 1e300;
-  MB_CUDA(cudaMemsetAsync(d_est, 0, sizeof(unsigned long long), st));
-  if (thr > 0 && thr < 1e300) {
+  MB_CUDA(cudaMemsetAsync(d_est, 0, 2 * sizeof(unsigned long long), st));
+  if (thr > 0) {
     const double phi_max = r2max * std::fabs(std::log(r2max));
-    MB_LAUNCH(ctx, "k_leaf_bounds", st) k_leaf_bounds<P><<<(leaf.nI * leaf.nJ + 7) / 8, 256, 0, st>>>(lat, leaf, d_coef, d_start, d_knots, phi_max, d_est);
+    MB_LAUNCH(ctx, "k_leaf_prep", st) k_leaf_prep<P><<<(nboxes + 7) / 8, 256, 0, st>>>(lat, leaf, d_coef, d_start, d_knots, phi_max, d_est, d_near, d_over, d_cursor);
+    MB_CUDA(cudaGetLastError());
   }
-  const size_t smem = 256 * sizeof(double2) + kNearCap * sizeof(double4) +
-                      sizeof(double) * (P * P + (size_t)lat.bh * P) + sizeof(float) * (size_t)lat.bh * (P - 1);
-  dim3 grid(lat.nbx, lat.nby);
-  if (fuse) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-      MB_CUDA(cudaFuncSetAttribute(k_leaf<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr_set = true;
+  const AccFuse fz = fuse ? *fuse : AccFuse{nullptr, 0, 0.0};
+  if (thr > 0) {
+    const size_t smem = (size_t)kLeafStages * leaf_stage_bytes(P, lat.bh, fuse != nullptr) +
+                        2 * (size_t)lat.bh * (sizeof(double) + leaf_gfs(P) * sizeof(float));
+    if (fuse) {
+      const int grid = leaf_grid(ctx, k_leaf_stream<P, true>, smem, nboxes);
+      MB_LAUNCH(ctx, "k_leaf_fused", st) k_leaf_stream<P, true><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_near, d_over, d_est, thr, fz, out, stride);
+    } else {
+      const int grid = leaf_grid(ctx, k_leaf_stream<P, false>, smem, nboxes);
+      MB_LAUNCH(ctx, "k_leaf", st) k_leaf_stream<P, false><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_near, d_over, d_est, thr, fz, out, stride);
     }
-    MB_LAUNCH(ctx, "k_leaf_fused", st) k_leaf<P, true><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_start, d_knots, ctx->logtab.p, d_est, thr, *fuse, out, stride);
-  } else {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-      MB_CUDA(cudaFuncSetAttribute(k_leaf<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr_set = true;
-    }
-    MB_LAUNCH(ctx, "k_leaf", st) k_leaf<P, false><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_start, d_knots, ctx->logtab.p, d_est, thr, EnsFuse{}, out, stride);
+    MB_CUDA(cudaGetLastError());
   }
-  MB_CUDA(cudaGetLastError());
+  if (thr < 1e300) {
+    const size_t smem = 256 * sizeof(double2) + kNearCap * sizeof(double4) + sizeof(double) * (P * P + (size_t)lat.bh * P);
+    if (fuse) {
+      const int grid = leaf_grid(ctx, k_leaf_f64<P, true>, smem, nboxes);
+      MB_LAUNCH(ctx, "k_leaf_f64_fused", st) k_leaf_f64<P, true><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_start, d_knots, ctx->logtab.p, d_est, thr, fz, out, stride);
+    } else {
+      const int grid = leaf_grid(ctx, k_leaf_f64<P, false>, smem, nboxes);
+      MB_LAUNCH(ctx, "k_leaf_f64", st) k_leaf_f64<P, false><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_start, d_knots, ctx->logtab.p, d_est, thr, fz, out, stride);
+    }
+    MB_CUDA(cudaGetLastError());
+  }
 }
 
 void tps_eval_fast(mb_ctx* ctx, const mb_spline* s, const mb_grid& g, const mb_window& w, double* out,
-                   int64_t stride, cudaStream_t st, const EnsFuse* fuse) {
+                   int64_t stride, cudaStream_t st, const AccFuse* fuse) {
   const GridAffine a = make_affine(g, *s);
   const int P = choose_p(ctx, s);
   const double ax = a.rx / a.scx, ay = -a.ry / a.scy;

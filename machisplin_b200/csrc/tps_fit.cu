@@ -6,9 +6,11 @@
 //   K1b reflectors       M = Q2' K Q2 by three two-sided Householder updates  (gemv + rank-2)
 //   K2 Cholesky          fixed lambda: blocked right-looking LL' of M + lambda I; the trailing SYRK
 //                        runs on the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> DMMA)
-//   K3 GCV               eigen(M) [cuSOLVER Dsyevd - LIBRARY CALL, stand-in until the in-house
-//                        tridiagonal solver lands], u = V'Q2'y, fields' 200-point df grid + golden
-//                        section on the host in float64.
+//   K3 GCV               M = Q T Q' by the in-house persistent Householder kernel (sytrd.cu), eta = eig(T) by Sturm
+//                        bisection, z^ = Q'Q2'y; fields' 200-point df grid on the device (k_gcv_grid), golden
+//                        section on the host with RSS(lambda) = lambda^2 |(T + lambda I)^-1 z^|^2 (O(m) solves);
+//                        coefficients at the selected lambda through the Cholesky of K2.  No eigenvector is
+//                        formed.  (mb_set_param "eigen_impl" = 1 selects cuSOLVER Dsyevd - validation only.)
 #include "common.cuh"
 #include "internal.h"
 
@@ -399,15 +401,50 @@ static double tr_a(double lam, const std::vector<double>& D) {
   for (double d : D) s += 1.0 / (1.0 + lam * d);
   return s;
 }
-static double value(double lam, const std::vector<double>& D, const std::vector<double>& u, int n_obs, double pure_ss) {
-  const int np = (int)D.size();
-  double rss = 0, tra = 0;
-  for (int k = 0; k < np; ++k) {
-    const double lD = D[k] * lam;
-    const double t = (u[k] * lD) / (1.0 + lD);
-    rss += t * t;
-    tra += 1.0 / (1.0 + lD);
+// RSS(lambda) = sum_k (u_k lambda D_k / (1 + lambda D_k))^2, from the rotated data u (eigenbasis) ...
+struct RssEigen {
+  const std::vector<double>& D;
+  const std::vector<double>& u;
+  double operator()(double lam) const {
+    double rss = 0;
+    for (size_t k = 0; k < D.size(); ++k) {
+      const double lD = D[k] * lam;
+      const double t = (u[k] * lD) / (1.0 + lD);
+      rss += t * t;
+    }
+    return rss;
   }
+};
+// ... or, equivalently, lambda^2 |(T + lambda I)^-1 z^|^2 from the tridiagonal form (no eigenvectors): one
+// symmetric positive definite tridiagonal solve (Thomas) per evaluation
+struct RssTridiag {
+  const std::vector<double>& dg;
+  const std::vector<double>& of;
+  const std::vector<double>& zh;
+  mutable std::vector<double> piv, rhs;
+  double operator()(double lam) const {
+    const size_t m = dg.size();
+    piv.resize(m); rhs.resize(m);
+    piv[0] = dg[0] + lam; rhs[0] = zh[0];
+    for (size_t i = 1; i < m; ++i) {
+      const double w = of[i - 1] / piv[i - 1];
+      piv[i] = dg[i] + lam - w * of[i - 1];
+      rhs[i] = zh[i] - w * rhs[i - 1];
+    }
+    double x = rhs[m - 1] / piv[m - 1], rss = x * x;
+    for (size_t i = m - 1; i-- > 0;) {
+      x = (rhs[i] - of[i] * x) / piv[i];
+      rss += x * x;
+    }
+    return lam * lam * rss;
+  }
+};
+template <class R>
+static double value(double lam, const std::vector<double>& D, const R& rssfun, int n_obs, double pure_ss) {
+  const int np = (int)D.size();
+  const double rss = rssfun(lam);
+  double tra = 0;
+  for (int k = 0; k < np; ++k) tra += 1.0 / (1.0 + D[k] * lam);
   double mse = rss / np;
   if (n_obs - np > 0) mse += pure_ss / (n_obs - np);
   const double den = 1.0 - ((tra - 3.0) + 3.0) / np;   // cost = 1, offset = 0, nt = 3
@@ -454,7 +491,8 @@ static double golden(double ax, double bx, double cx, F f, double tol) {
   }
   return f1 < f2 ? x1 : x2;
 }
-static double search(const std::vector<double>& D, const std::vector<double>& u, const std::vector<double>& grid,
+template <class R>
+static double search(const std::vector<double>& D, const R& u, const std::vector<double>& grid,
                      int n_obs, double pure_ss, double* gcv_min) {
   std::vector<double> lg, gg;
   for (double l : grid) {
@@ -623,78 +661,116 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
 
   std::vector<double> lam(L, lambda), edf(L, -1.0), gcvv(L, -1.0);
   std::vector<std::vector<double>> beta(L, std::vector<double>(m));
-  std::vector<double> eta_desc;
-  std::vector<std::vector<double>> u_full(L);
+  std::vector<double> eta_desc, tri_diag, tri_off;
+  std::vector<std::vector<double>> zhat(L);
 
   if (lambda < 0) {
-    // ---- eigen(M): cuSOLVER Dsyevd (library stand-in, see file header) -----------------------------
-    FitLibs& lb = libs(ctx);
-    ABuf<double> d_eta(ar, m);
-    ABuf<int> d_info(ar, 1);
-    int lwork = 0;
-    if (cusolverDnDsyevd_bufferSize(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p,
-                                    &lwork) != CUSOLVER_STATUS_SUCCESS)
-      throw Error(MB_E_CUDA, "cusolverDnDsyevd_bufferSize failed");
-    ABuf<double> d_work(ar, (size_t)lwork);
-    cusolverStatus_t cs = CUSOLVER_STATUS_SUCCESS;
-    MB_LAUNCH(ctx, "cusolverDnDsyevd", st)
-      cs = cusolverDnDsyevd(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p, d_work.p,
-                            lwork, d_info.p);
-    if (cs != CUSOLVER_STATUS_SUCCESS) throw Error(MB_E_CUDA, "cusolverDnDsyevd failed");
-    int info = 0;
-    std::vector<double> eta(m);
-    MB_CUDA(cudaMemcpyAsync(&info, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    MB_CUDA(cudaMemcpyAsync(eta.data(), d_eta.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-    MB_CUDA(cudaStreamSynchronize(st));
-    if (info != 0) throw Error(MB_E_NUMERIC, "symmetric eigensolver did not converge (info=" + std::to_string(info) + ")");
-    if (!(eta[0] > 0)) throw Error(MB_E_NUMERIC, "Q2'KQ2 is not positive definite (smallest eigenvalue <= 0)");
-    // D = c(0,0,0, 1/eta) in R's decreasing-eigenvalue order; eta from syevd is ascending
+    MB_REQUIRE(L <= 32, "GCV fit: at most 32 responses per call");
+    std::vector<double> eta;            // ascending eigenvalues of M
     std::vector<double> D(np, 0.0);
-    for (int k = 0; k < m; ++k) D[3 + k] = 1.0 / eta[m - 1 - k];
-    eta_desc.assign(eta.rbegin(), eta.rend());
-    // lambda grid: device kernel when D fits in shared memory, host loop otherwise
-    std::vector<double> grid;
     const int nstep = 200;
-    if ((size_t)np * sizeof(double) <= 200 * 1024) {
-      ABuf<double> d_D(ar), d_grid(ar, nstep);
-      ABuf<int> d_err(ar, 1);
-      d_D.upload(D, st);
-      MB_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
-      static thread_local bool attr = false;
-      if (!attr) {
-        MB_CUDA(cudaFuncSetAttribute(k_gcv_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
+    auto make_grid = [&]() {
+      if (!(eta[0] > 0)) throw Error(MB_E_NUMERIC, "Q2'KQ2 is not positive definite (smallest eigenvalue <= 0)");
+      // D = c(0,0,0, 1/eta) in R's decreasing-eigenvalue order
+      for (int k = 0; k < m; ++k) D[3 + k] = 1.0 / eta[m - 1 - k];
+      eta_desc.assign(eta.rbegin(), eta.rend());
+      // lambda grid: device kernel when D fits in shared memory, host loop otherwise
+      std::vector<double> grid;
+      if ((size_t)np * sizeof(double) <= 200 * 1024) {
+        ABuf<double> d_D(ar), d_grid(ar, nstep);
+        ABuf<int> d_err(ar, 1);
+        d_D.upload(D, st);
+        MB_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+        static thread_local bool attr = false;
+        if (!attr) {
+          MB_CUDA(cudaFuncSetAttribute(k_gcv_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr = true;
+        }
+        MB_LAUNCH(ctx, "k_gcv_grid", st) k_gcv_grid<<<nstep, kGcvThreads, (size_t)np * sizeof(double), st>>>(d_D.p, np, nstep, d_grid.p, d_err.p);
+        MB_CUDA(cudaGetLastError());
+        grid.resize(nstep);
+        int gerr = 0;
+        MB_CUDA(cudaMemcpyAsync(grid.data(), d_grid.p, sizeof(double) * nstep, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaMemcpyAsync(&gerr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        if (gerr) throw Error(MB_E_NUMERIC, "bisection.search: f1 must be < f2");
+        std::sort(grid.begin(), grid.end());
+      } else {
+        grid = gcv::lambda_grid(D);
       }
-      MB_LAUNCH(ctx, "k_gcv_grid", st) k_gcv_grid<<<nstep, kGcvThreads, (size_t)np * sizeof(double), st>>>(d_D.p, np, nstep, d_grid.p, d_err.p);
-      MB_CUDA(cudaGetLastError());
-      grid.resize(nstep);
-      int gerr = 0;
-      MB_CUDA(cudaMemcpyAsync(grid.data(), d_grid.p, sizeof(double) * nstep, cudaMemcpyDeviceToHost, st));
-      MB_CUDA(cudaMemcpyAsync(&gerr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      return grid;
+    };
+    if (ctx->eigen_impl != 1) {
+      // ---- in-house: M = Q T Q' on a work copy (M itself is kept for the Cholesky below) ----------------
+      ABuf<double> d_T(ar, (size_t)m * m), d_z(ar, (size_t)m * L);
+      MB_CUDA(cudaMemcpyAsync(d_T.p, M, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToDevice, st));
+      for (int r = 0; r < L; ++r)
+        MB_CUDA(cudaMemcpyAsync(d_z.p + (size_t)r * m, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+      std::vector<double> tdiag, toff;
+      sym_tridiag_eig(ctx, d_T.p, m, m, d_z.p, L, tdiag, toff, eta, st);
+      std::vector<double> zh((size_t)m * L);
+      MB_CUDA(cudaMemcpyAsync(zh.data(), d_z.p, sizeof(double) * m * L, cudaMemcpyDeviceToHost, st));
       MB_CUDA(cudaStreamSynchronize(st));
-      if (gerr) throw Error(MB_E_NUMERIC, "bisection.search: f1 must be < f2");
-      std::sort(grid.begin(), grid.end());
+      const std::vector<double> grid = make_grid();
+      tri_diag = tdiag; tri_off = toff;
+      for (int r = 0; r < L; ++r) {
+        zhat[r].assign(zh.begin() + (size_t)r * m, zh.begin() + (size_t)(r + 1) * m);
+        gcv::RssTridiag rss{tdiag, toff, zhat[r], {}, {}};
+        lam[r] = gcv::search(D, rss, grid, n, pure_ss[r], &gcvv[r]);
+        edf[r] = gcv::tr_a(lam[r], D);
+      }
+      // ---- Krig.coef at the selected lambda: (M + lambda I) beta = z by the tensor-core Cholesky ----------
+      ABuf<double> d_B(ar, m);
+      for (int r = 0; r < L; ++r) {
+        MB_CUDA(cudaMemcpyAsync(d_T.p, M, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToDevice, st));
+        MB_LAUNCH(ctx, "k_add_diag", st) k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(d_T.p, m, m, lam[r]);
+        cholesky_lower(ctx, d_T.p, m, m, st);
+        MB_CUDA(cudaMemcpyAsync(d_B.p, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+        MB_LAUNCH(ctx, "k_chol_solve", st) k_chol_solve<<<1, 1024, 0, st>>>(d_T.p, m, m, d_B.p, m, 1);
+        MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+      }
     } else {
-      grid = gcv::lambda_grid(D);
-    }
-    ABuf<double> d_z(ar, m), d_u(ar, m), d_g(ar, m), d_beta(ar, m);
-    for (int r = 0; r < L; ++r) {
-      d_z.upload(z[r], st);
-      MB_LAUNCH(ctx, "k_gemv_t", st) k_gemv_t<<<(m + 7) / 8, 256, 0, st>>>(M, m, m, m, d_z.p, d_u.p);   // u = V' z (ascending order)
-      std::vector<double> u_asc(m);
-      MB_CUDA(cudaMemcpyAsync(u_asc.data(), d_u.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+      // ---- validation path: eigen(M) by cuSOLVER Dsyevd (library call) ---------------------------------
+      FitLibs& lb = libs(ctx);
+      ABuf<double> d_eta(ar, m);
+      ABuf<int> d_info(ar, 1);
+      int lwork = 0;
+      if (cusolverDnDsyevd_bufferSize(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p,
+                                      &lwork) != CUSOLVER_STATUS_SUCCESS)
+        throw Error(MB_E_CUDA, "cusolverDnDsyevd_bufferSize failed");
+      ABuf<double> d_work(ar, (size_t)lwork);
+      cusolverStatus_t cs = CUSOLVER_STATUS_SUCCESS;
+      MB_LAUNCH(ctx, "cusolverDnDsyevd", st)
+        cs = cusolverDnDsyevd(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p, d_work.p,
+                              lwork, d_info.p);
+      if (cs != CUSOLVER_STATUS_SUCCESS) throw Error(MB_E_CUDA, "cusolverDnDsyevd failed");
+      int info = 0;
+      eta.resize(m);
+      MB_CUDA(cudaMemcpyAsync(&info, d_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MB_CUDA(cudaMemcpyAsync(eta.data(), d_eta.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
       MB_CUDA(cudaStreamSynchronize(st));
-      std::vector<double> u(np, 0.0);
-      for (int k = 0; k < m; ++k) u[3 + k] = u_asc[m - 1 - k];
-      lam[r] = gcv::search(D, u, grid, n, pure_ss[r], &gcvv[r]);
-      edf[r] = gcv::tr_a(lam[r], D);
-      std::vector<double> gvec(m);
-      for (int k = 0; k < m; ++k) gvec[k] = u_asc[k] / (eta[k] + lam[r]);
-      d_g.upload(gvec, st);
-      gemv_n(ctx, M, m, m, m, d_g.p, d_beta.p, d_part.p, st);              // beta = V diag(1/(eta+lambda)) u
-      MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_beta.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-      MB_CUDA(cudaStreamSynchronize(st));
-      u_full[r] = u;
+      if (info != 0) throw Error(MB_E_NUMERIC, "symmetric eigensolver did not converge (info=" + std::to_string(info) + ")");
+      const std::vector<double> grid = make_grid();
+      ABuf<double> d_z(ar, m), d_u(ar, m), d_g(ar, m), d_beta(ar, m);
+      for (int r = 0; r < L; ++r) {
+        d_z.upload(z[r], st);
+        MB_LAUNCH(ctx, "k_gemv_t", st) k_gemv_t<<<(m + 7) / 8, 256, 0, st>>>(M, m, m, m, d_z.p, d_u.p);   // u = V' z (ascending order)
+        std::vector<double> u_asc(m);
+        MB_CUDA(cudaMemcpyAsync(u_asc.data(), d_u.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        std::vector<double> u(np, 0.0);
+        for (int k = 0; k < m; ++k) u[3 + k] = u_asc[m - 1 - k];
+        gcv::RssEigen rss{D, u};
+        lam[r] = gcv::search(D, rss, grid, n, pure_ss[r], &gcvv[r]);
+        edf[r] = gcv::tr_a(lam[r], D);
+        std::vector<double> gvec(m);
+        for (int k = 0; k < m; ++k) gvec[k] = u_asc[k] / (eta[k] + lam[r]);
+        d_g.upload(gvec, st);
+        gemv_n(ctx, M, m, m, m, d_g.p, d_beta.p, d_part.p, st);              // beta = V diag(1/(eta+lambda)) u
+        MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_beta.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+      }
     }
   } else {
     // ---- fixed lambda: (M + lambda I) beta = z by tensor-core Cholesky ------------------------------
@@ -725,7 +801,7 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     s->scale[0] = scale[0]; s->scale[1] = scale[1];
     s->d[0] = s->d[1] = s->d[2] = 0.0;
     s->lambda = lam[r]; s->eff_df = edf[r]; s->gcv = gcvv[r];
-    if (lambda < 0) { s->eta = eta_desc; s->u = u_full[r]; }
+    if (lambda < 0) { s->eta = eta_desc; s->tri_diag = tri_diag; s->tri_off = tri_off; s->zhat = zhat[r]; }
     // K c through the evaluation kernel with d = 0 (K was overwritten by the projection)
     s->ctx = ctx;
     s->d_sx.upload(s->sx, st); s->d_sy.upload(s->sy, st); s->d_c.upload(s->c, st);

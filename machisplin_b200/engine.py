@@ -84,10 +84,12 @@ class Spline:
         self.lam, self.eff_df, self.gcv = lam.value, edf.value, gcv.value
 
     def decomposition(self):
-        eta = np.empty(self.np - 3)
-        u = np.empty(self.np)
-        check(self.engine.lib.mb_spline_get_decomp(self._h, _pd(eta), _pd(u)))
-        return eta, u
+        """GCV fits: eigenvalues of Q2'KQ2 (decreasing) and the tridiagonal form (diag, off, zhat) the lambda
+        search ran on."""
+        m = self.np - 3
+        eta, dg, of, zh = np.empty(m), np.empty(m), np.empty(m - 1), np.empty(m)
+        check(self.engine.lib.mb_spline_get_decomp(self._h, _pd(eta), _pd(dg), _pd(of), _pd(zh)))
+        return eta, (dg, of, zh)
 
     def free(self):
         if self._h:

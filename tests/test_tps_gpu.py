@@ -86,8 +86,12 @@ def test_fit_gcv_matches_oracle(engine, n):
     assert abs(sp.eff_df - ref.eff_df) <= 1e-6 * ref.eff_df
     np.testing.assert_allclose(sp.d, ref.d, rtol=1e-7, atol=1e-9 * np.abs(ref.d).max())
     assert np.max(np.abs(sp.c - ref.c)) <= 1e-7 * np.max(np.abs(ref.c))
-    eta, u = sp.decomposition()
-    np.testing.assert_allclose(eta, ref.eta, rtol=1e-8)
+    eta, (dg, of, zh) = sp.decomposition()
+    np.testing.assert_allclose(eta, ref.eta, rtol=1e-7, atol=1e-13 * ref.eta.max())
+    # the tridiagonal form is orthogonally similar to Q2'KQ2: same spectrum, same |z|
+    tri = np.diag(dg) + np.diag(of, 1) + np.diag(of, -1)
+    np.testing.assert_allclose(np.linalg.eigvalsh(tri)[::-1], ref.eta, rtol=1e-7, atol=1e-13 * ref.eta.max())
+    assert abs(np.linalg.norm(zh) - np.linalg.norm(ref.u[3:])) <= 1e-10 * np.linalg.norm(zh)
     # predictions at the knots: f(x_i) = y_i - lambda c_i
     f = engine.tps_predict_points(sp, xy)
     assert np.max(np.abs(f - (y - sp.lam * sp.c))) < 1e-9 * max(1.0, np.abs(y).max())
@@ -160,3 +164,30 @@ def test_mixed_path_is_refused_when_inaccurate(engine):
     got = engine.tps_eval(sp, geom, method="fast")
     ref = otps.tps_interpolate(fit, geom.as_tuple())
     assert relerr(got, ref) < 1e-6
+
+
+@pytest.mark.parametrize("n", [35, 200, 1100])
+def test_fit_gcv_tridiagonal_paths_agree(engine, n):
+    """The in-house GCV fit (persistent Householder kernel + Sturm bisection + Cholesky) against its two
+    alternates: one kernel per phase (sytrd_mode = 2) and the cuSOLVER eigenvector path (eigen_impl = 1)."""
+    geom = synth.make_geom(1024, 1024)
+    xy, _, _ = synth.make_knots(geom, n, 300 + n)
+    y = synth.residual_field(xy, 300 + n)
+    sp0 = engine.tps_fit(xy, y)
+    try:
+        engine.set_param("sytrd_mode", 2)
+        sp2 = engine.tps_fit(xy, y)
+        engine.set_param("sytrd_mode", 0)
+        engine.set_param("eigen_impl", 1)
+        sp1 = engine.tps_fit(xy, y)
+    finally:
+        engine.set_param("sytrd_mode", 0)
+        engine.set_param("eigen_impl", 0)
+    # the two schedules of the same algorithm are bit-identical (fixed summation order)
+    assert sp2.lam == sp0.lam
+    np.testing.assert_array_equal(sp2.c, sp0.c)
+    np.testing.assert_array_equal(sp2.decomposition()[0], sp0.decomposition()[0])
+    assert abs(sp1.lam - sp0.lam) <= 1e-6 * sp0.lam
+    assert np.max(np.abs(sp1.c - sp0.c)) <= 1e-7 * np.max(np.abs(sp0.c))
+    np.testing.assert_allclose(sp1.decomposition()[0], sp0.decomposition()[0], rtol=1e-7,
+                               atol=1e-13 * sp0.decomposition()[0].max())
