@@ -198,6 +198,11 @@ int mb_d2h(mb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int mb_timing_enable(mb_ctx* ctx, int on);
 int mb_timing_collect(mb_ctx* ctx, int cap, const char** names, double* total_ms, int64_t* launches);
 
+/* Named diagnostic vectors; returns the number of values written or a negative MB_E_* code.
+ * "sytrd_phase_ms": time per phase of the last tridiagonalisation seen by CTA 0 while timing was enabled
+ * (P1, barrier, P2, barrier, P3, barrier, panel update, barrier). */
+int mb_debug_values(mb_ctx* ctx, const char* name, double* out, int cap);
+
 /* Tunables of the fast evaluator (0 = automatic). */
 int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows);
 /* Named integer tunables (0 = automatic): "tree_rows" = cells per thread of the forest tile (1, 2, 4);

@@ -70,6 +70,7 @@ SIGNATURES = {
     "mb_spline_get": (C.c_int, [VP, PD, PD, PD, PD, PD, PD, PD, PD]),
     "mb_spline_get_decomp": (C.c_int, [VP, PD, PD, PD, PD]),
     "mb_spline_free": (None, [VP]),
+    "mb_debug_values": (C.c_int, [VP, C.c_char_p, PD, C.c_int]),
     "mb_tps_eval": (C.c_int, [VP, VP, PG, PW, C.c_int, PD]),
     "mb_tps_eval_dev": (C.c_int, [VP, VP, PG, PW, C.c_int, VP, C.c_int64, VP]),
     "mb_tps_predict_points": (C.c_int, [VP, VP, PD, C.c_int, PD]),

@@ -47,6 +47,7 @@ int mb_init(int device, mb_ctx** out) {
     MB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     MB_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
     MB_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo));
+    MB_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
     MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     init_logtab(ctx.get());
@@ -66,6 +67,8 @@ void mb_shutdown(mb_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->copy) cudaStreamDestroy(ctx->copy);
+  for (cudaEvent_t ev : ctx->ev_blocks) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -124,6 +127,19 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
     ctx->leaf_cols = leaf_cols;
     ctx->leaf_rows = leaf_rows;
   });
+}
+
+int mb_debug_values(mb_ctx* ctx, const char* name, double* out, int cap) {
+  int n = 0;
+  const int rc = guarded([&] {
+    MB_REQUIRE(ctx && name && out, "NULL argument");
+    if (std::string(name) == "sytrd_phase_ms") {
+      for (; n < 8 && n < cap; ++n) out[n] = ctx->sytrd_prof_ms[n];
+    } else {
+      throw Error(MB_E_ARG, std::string("unknown debug vector '") + name + "'");
+    }
+  });
+  return rc < 0 ? rc : n;
 }
 
 int mb_set_param(mb_ctx* ctx, const char* name, int value) {
@@ -486,9 +502,12 @@ int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_strid
 }
 
 // ---- mltps parts 2-5 in one call -----------------------------------------------------------------
-static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, const float* cov, int C,
+// cov_host != NULL (host-buffer entry point): `cov` is an empty device buffer; the planes are uploaded in row
+// blocks on the copy stream and every block's ensemble kernels start as soon as its rows have landed, so the
+// PCIe transfer (1.6 GB at config 3) hides behind part 2 instead of preceding it.
+static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, float* cov, int C,
                           const double* knots_xy, const double* resid, int n, double lambda, int tile_px,
-                          double* out, mb_spline** spline_out, cudaStream_t st) {
+                          double* out, mb_spline** spline_out, cudaStream_t st, const float* cov_host = nullptr) {
   const mb_window full{0, g.nrow, 0, g.ncol};
   const size_t ncell = (size_t)g.nrow * g.ncol;
   if (spline_out) *spline_out = nullptr;
@@ -506,7 +525,31 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, c
     acc = ctx->arena.take_n<double>((size_t)(acc_stride(full) * acc_rows(full)));
     MB_CUDA(cudaEventRecord(ctx->ev_fork, st));
     MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    ensemble_accumulate(ctx, e, cov, C, full, acc, ctx->side);
+    if (cov_host && C > 0) {
+      MB_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
+      const int nblk = std::max(1, std::min(8, g.nrow / 256));
+      const int rows_per = ((g.nrow + nblk - 1) / nblk + 63) / 64 * 64;
+      int b = 0;
+      for (int r0 = 0; r0 < g.nrow; r0 += rows_per, ++b) {
+        const int r1 = std::min(g.nrow, r0 + rows_per);
+        for (int p = 0; p < C; ++p) {
+          const size_t off = (size_t)p * ncell + (size_t)r0 * g.ncol;
+          MB_CUDA(cudaMemcpyAsync(cov + off, cov_host + off, sizeof(float) * (size_t)(r1 - r0) * g.ncol,
+                                  cudaMemcpyHostToDevice, ctx->copy));
+        }
+        if ((int)ctx->ev_blocks.size() <= b) {
+          cudaEvent_t ev;
+          MB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          ctx->ev_blocks.push_back(ev);
+        }
+        MB_CUDA(cudaEventRecord(ctx->ev_blocks[b], ctx->copy));
+        MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_blocks[b], 0));
+        const mb_window wb{r0, r1, 0, g.ncol};
+        ensemble_accumulate(ctx, e, cov, C, wb, acc + (int64_t)r0 * acc_stride(full), ctx->side);
+      }
+    } else {
+      ensemble_accumulate(ctx, e, cov, C, full, acc, ctx->side);
+    }
     MB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   }
   // part 3: fields::Tps of the residuals on the context stream, beside the kernels above
@@ -551,7 +594,7 @@ int mb_mltps_predict_dev(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, co
     MB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     ctx->arena.begin(st);
-    mltps_predict(ctx, *g, e, cov_dev, C, knots_xy, resid, n, lambda, tile_px, out_dev, spline_out, st);
+    mltps_predict(ctx, *g, e, const_cast<float*>(cov_dev), C, knots_xy, resid, n, lambda, tile_px, out_dev, spline_out, st);
   });
 }
 
@@ -569,11 +612,11 @@ int mb_mltps_predict(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, const 
     if (e && C > 0) {
       MB_REQUIRE(cov_host, "covariate planes are NULL");
       d_cov = ctx->arena.take_n<float>((size_t)C * ncell);
-      MB_CUDA(cudaMemcpyAsync(d_cov, cov_host, sizeof(float) * (size_t)C * ncell, cudaMemcpyHostToDevice, st));
     }
     double* d_out = ctx->arena.take_n<double>(ncell);
-    // the user stream of this call is a private one, so part 2 needs no fork: run it in line
-    mltps_predict(ctx, *g, e, d_cov, C, knots_xy, resid, n, lambda, tile_px, d_out, spline_out, st);
+    // planes travel in row blocks on the copy stream, block b's ensemble kernels follow on `side`, the fit
+    // runs on the context stream meanwhile
+    mltps_predict(ctx, *g, e, d_cov, C, knots_xy, resid, n, lambda, tile_px, d_out, spline_out, st, cov_host);
     MB_CUDA(cudaMemcpyAsync(out_host, d_out, ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
   });

@@ -165,11 +165,15 @@ struct mb_ctx {
   int eigen_impl = 0;         // GCV fit: 0 = in-house tridiagonalisation + bisection, 1 = cuSOLVER Dsyevd (validation)
   int sytrd_mode = 0;         // tridiagonalisation: 0 / 1 = persistent kernel with grid barrier, 2 = one kernel per phase
   int sytrd_ctas_per_sm = 0;  // persistent grid size (0 = 2 per SM)
+  double sytrd_prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per-phase time of the last k_sytrd launch (timing on)
   // scratch reused across calls
   mb::Arena arena;
   // second stream + events: the TPS fit runs beside the per-cell ensemble kernels (mb_mltps_predict*)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // copy stream + per-row-block events of the host-buffer path (H2D of block b+1 overlaps the kernels of block b)
+  cudaStream_t copy = nullptr;
+  std::vector<cudaEvent_t> ev_blocks;
 };
 
 struct mb_spline {

@@ -25,9 +25,10 @@
 namespace mb {
 
 constexpr int kTs = 64;            // tile edge
-constexpr int kTsPad = kTs + 1;    // shared-memory column stride (conflict-free transposed pass)
+constexpr int kTsPad = kTs + 4;    // shared-memory column stride: conflict-free for both passes (see sytrd_p2)
+constexpr int kSeg = 4;            // tiles per strip segment
 constexpr int kNbMax = 32;         // panel width
-constexpr int kSW = 128;           // doubles per CTA in the P1 partial block: [0] |x|^2, [1..32] z dots, [32+q] W'x, [64+q] V'x
+constexpr int kSW = 128;           // doubles per row chunk in the P1 partial block: [0] |x|^2, [1..32] z dots, [33+q] W'x, [65+q] V'x
 constexpr int kSyThreads = 256;
 constexpr int kChunk = 32;         // rows per ownership chunk
 
@@ -35,26 +36,33 @@ struct SytrdArgs {
   double* A; int ld; int m;
   double* V; double* W;            // m x kNbMax, column-major, ld = m
   double* x;                       // m
-  double* Pb;                      // nt x m partial products
-  double* S;                       // G x kSW      P1 partials
-  double* S2;                      // G            P2 partials (v'Av)
-  double* fin;                     // 4 + 2 kNbMax + 32: tau, scale, beta, alpha | g1 | g2 | z dots
+  double* Pb;                      // nt x m partial products (slot a, rows of block b)
+  double* S;                       // nchunk x kSW  P1 partials, one block per row chunk
+  double* S2;                      // G             P2 partials (v'Av)
+  double* fin;                     // [0..3] tau, scale, beta, alpha | [4 + r] v'z_r | [36 + q] W'v | [68 + q] V'v
   double* z; int L;                // m x L right-hand sides, transformed in place
   double* d; double* e;            // diagonal (m), off-diagonal (m - 1)
-  unsigned* bar;
+  unsigned* bar;                   // [0] arrival counter, [32] release flag (separate 128-byte lines)
   int nt;                          // tiles per dimension
+  unsigned long long* prof;        // [8] nanoseconds per phase seen by CTA 0 (P1, sync, P2, sync, P3, sync, update, sync)
 };
 
-// ---- grid barrier -------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target) {
+// ---- grid barrier: arrivals on a counter, the last arriver publishes the generation on a separate line that the
+// others poll, so polling never delays an arrival ------------------------------------------------------------
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& gen) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    target += gridDim.x;
-    unsigned seen;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-    } while ((int)(seen - target) < 0);
+    ++gen;
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+    if (old == gen * gridDim.x - 1) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 32), "r"(gen) : "memory");
+    } else {
+      unsigned seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 32) : "memory");
+      } while ((int)(seen - gen) < 0);
+    }
   }
   __syncthreads();
 }
@@ -85,19 +93,16 @@ __device__ __forceinline__ Scal householder_scalars(double alpha, double xnorm2)
   return s;
 }
 
-// ---- P1: true column j (rows >= j), partial norms / dots ------------------------------------------
+// ---- P1: true column j (rows >= j), partial norms / dots per row chunk ---------------------------------
 __device__ void sytrd_p1(const SytrdArgs& a, int j, int jj, double* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m = a.m;
+  const int m = a.m, G = gridDim.x;
   double* s_red = smem;                       // [8][32]
-  double* s_part = smem + 8 * 32;             // [kSW] accumulated over this CTA's chunks
-  for (int i = tid; i < kSW; i += kSyThreads) s_part[i] = 0.0;
-  __syncthreads();
   const int first_chunk = j / kChunk;
   const int nchunk = (m + kChunk - 1) / kChunk;
-  // chunk c is owned by CTA c % gridDim.x
-  int c = first_chunk + (((int)blockIdx.x - first_chunk) % (int)gridDim.x + (int)gridDim.x) % (int)gridDim.x;
-  for (; c < nchunk; c += gridDim.x) {
+  // chunk c is owned by CTA c % G
+  int c = first_chunk + (((int)blockIdx.x - first_chunk) % G + G) % G;
+  for (; c < nchunk; c += G) {
     const int i = c * kChunk + lane;
     const bool act = i >= j && i < m;
     // slice of the deferred update: q = warp, warp + 8, ...
@@ -106,6 +111,7 @@ __device__ void sytrd_p1(const SytrdArgs& a, int j, int jj, double* smem) {
       for (int q = warp; q < jj; q += 8)
         acc += __ldcg(&a.V[(size_t)q * m + i]) * __ldcg(&a.W[(size_t)q * m + j]) +
                __ldcg(&a.W[(size_t)q * m + i]) * __ldcg(&a.V[(size_t)q * m + j]);
+    __syncthreads();                           // previous chunk done with s_red
     s_red[warp * 32 + lane] = acc;
     __syncthreads();
     double xi = 0.0;
@@ -118,122 +124,171 @@ __device__ void sytrd_p1(const SytrdArgs& a, int j, int jj, double* smem) {
         if (i == j) a.d[j] = xi;
         else a.x[i] = xi;
       }
-      s_red[lane] = (act && i > j) ? xi : 0.0;     // x of this chunk for the other warps
     }
+    __syncthreads();
+    if (warp == 0) s_red[lane] = (act && i > j) ? xi : 0.0;     // x of this chunk for the other warps
     __syncthreads();
     xi = s_red[lane];
     const bool tail = act && i > j + 1;            // rows below the pivot row j + 1
-    // warp 0: |x|^2 ; warps: z dots, W'x, V'x slices (x of the FULL column incl. the pivot row for W'x / V'x)
+    double* Sc = a.S + (size_t)c * kSW;
     if (warp == 0) {
       const double n2 = warp_sum(tail ? xi * xi : 0.0);
-      if (lane == 0) s_part[0] += n2;
+      if (lane == 0) Sc[0] = n2;
     }
     for (int r = warp; r < a.L; r += 8) {
       const double t = warp_sum(tail ? xi * __ldcg(&a.z[(size_t)r * m + i]) : 0.0);
-      if (lane == 0) s_part[1 + r] += t;
+      if (lane == 0) Sc[1 + r] = t;
     }
     for (int q = warp; q < jj; q += 8) {
       const double t1 = warp_sum(tail ? xi * __ldcg(&a.W[(size_t)q * m + i]) : 0.0);
       const double t2 = warp_sum(tail ? xi * __ldcg(&a.V[(size_t)q * m + i]) : 0.0);
-      if (lane == 0) { s_part[33 + q] += t1; s_part[65 + q] += t2; }
+      if (lane == 0) { Sc[33 + q] = t1; Sc[65 + q] = t2; }
     }
-    __syncthreads();
   }
-  __syncthreads();
-  for (int i = tid; i < kSW; i += kSyThreads) a.S[(size_t)blockIdx.x * kSW + i] = s_part[i];
 }
 
-// ---- P2: y = A v on the lower tiles; reduction of the P1 partials by the last CTA -------------------
+// segments of block row r (relative to the first active block): r / kSeg + 1; rows 4a .. 4a+3 before them hold
+// 2a(a+1) + b(a+1) segments in total
+__device__ __forceinline__ void segment_of(int s, int& Ii, int& seg) {
+  int aq = (int)((sqrt(1.0 + 2.0 * s) - 1.0) * 0.5);
+  while (2 * aq * (aq + 1) > s) --aq;
+  while (2 * (aq + 1) * (aq + 2) <= s) ++aq;
+  const int rem = s - 2 * aq * (aq + 1);
+  Ii = kSeg * aq + rem / (aq + 1);
+  seg = rem % (aq + 1);
+}
+__device__ __forceinline__ int segment_count(int na) {
+  const int aq = na / kSeg, bq = na % kSeg;
+  return (aq + 1) * (2 * aq + bq);
+}
+
+// ---- P2: y = A v on the lower tiles ------------------------------------------------------------------------
+// Work unit = segment of <= 4 consecutive tiles of one block row I.  Pass A (thread = row r, 16 columns): the tile
+// comes from global memory (coalesced along rows, prefetched one tile ahead into registers), feeds the running
+// row product t_r += A[r,c] v_c and is parked in shared memory; pass B (thread = column c, rows rq, rq+4, ...):
+// the transposed product u_c = sum_r A[r,c] v_r from shared memory, the 4 row slices of a column sit in adjacent
+// lanes and are combined by two shuffles.  Column stride 68 makes both passes bank-conflict free; the tile
+// buffer is double-buffered so that one __syncthreads per tile suffices.
+// Slots: Pb[a][rows of block b] holds, for a <= b, the row product of the segment of block row b that STARTS at
+// tile column a (zero for the other columns of the segment) and, for a > b, the transposed product of tile (a, b).
 __device__ void sytrd_p2(const SytrdArgs& a, int j, int jj, double* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.m, G = gridDim.x;
-  double* s_tile = smem;                        // [64][65]
-  double* s_vI = s_tile + kTs * kTsPad;         // 64
-  double* s_vJ = s_vI + kTs;                    // 64
-  double* s_red = s_vJ + kTs;                   // [4][64]
-  double* s_sc = s_red + 4 * kTs;               // scalars: 0 xnorm2, 1 vAv accumulator
+  double* s_tile = smem;                              // [2][64][68]
+  double* s_vJ = s_tile + 2 * kTs * kTsPad;           // [2][64]
+  double* s_vI = s_vJ + 2 * kTs;                      // 64
+  double* s_red = s_vI + kTs;                         // [8][64]: t_off, t_diag per column group
+  double* s_ud = s_red + 8 * kTs;                     // 64: transposed product of the diagonal tile
+  double* s_sc = s_ud + kTs;                          // scalars
+  const int first_chunk = j / kChunk;
+  const int nchunk = (m + kChunk - 1) / kChunk;
   if (warp == 0) {
-    const double n2 = warp_strided_sum(a.S, G, kSW, lane);
-    if (lane == 0) { s_sc[0] = n2; s_sc[1] = 0.0; }
+    const double n2 = warp_strided_sum(a.S + (size_t)first_chunk * kSW, nchunk - first_chunk, kSW, lane);
+    if (lane == 0) s_sc[0] = n2;
   }
   __syncthreads();
   const double alpha = __ldcg(&a.x[j + 1]);
   const Scal sc = householder_scalars(alpha, s_sc[0]);
-  // the last CTA publishes the scalars and the reduced dots for P3
-  if (blockIdx.x == G - 1) {
-    if (tid == 0) {
-      a.fin[0] = sc.tau; a.fin[1] = sc.scale; a.fin[2] = sc.beta; a.fin[3] = sc.alpha;
-      a.e[j] = sc.beta;
-    }
-    // v'z_r = z[j+1] + scale sum_{i>j+1} x_i z_i ;  g1 = W'v, g2 = V'v likewise (pivot row enters with v = 1)
-    for (int k = warp; k < a.L + 2 * jj; k += 8) {
+  if (blockIdx.x == 0 && tid == 0) {
+    a.fin[0] = sc.tau; a.fin[1] = sc.scale; a.fin[2] = sc.beta; a.fin[3] = sc.alpha;
+    a.e[j] = sc.beta;
+  }
+  // reduced dots for P3, one per CTA (from the back of the grid: those CTAs have the fewest segments):
+  // v'z_r = z[j+1] + scale sum_{i>j+1} x_i z_i ;  g1 = W'v, g2 = V'v likewise (the pivot row enters with v = 1)
+  if (warp == 0) {
+    for (int k = G - 1 - (int)blockIdx.x; k < a.L + 2 * jj; k += G) {
       int col; const double* piv;
       if (k < a.L) { col = 1 + k; piv = &a.z[(size_t)k * m + j + 1]; }
       else if (k < a.L + jj) { col = 33 + (k - a.L); piv = &a.W[(size_t)(k - a.L) * m + j + 1]; }
       else { col = 65 + (k - a.L - jj); piv = &a.V[(size_t)(k - a.L - jj) * m + j + 1]; }
-      const double t = warp_strided_sum(a.S + col, G, kSW, lane);
-      if (lane == 0) a.fin[4 + (col - 1)] = __ldcg(piv) + sc.scale * t;   // fin[4 + r] z dots, fin[36 + q] g1, fin[68 + q] g2
+      const double t = warp_strided_sum(a.S + (size_t)first_chunk * kSW + col, nchunk - first_chunk, kSW, lane);
+      if (lane == 0) a.fin[4 + (col - 1)] = __ldcg(piv) + sc.scale * t;
     }
   }
   const int Ib0 = (j + 1) / kTs;
   const int na = a.nt - Ib0;
-  const int ntiles = na * (na + 1) / 2;
-  const int r = tid & 63, cg = tid >> 6;
+  const int nseg = segment_count(na);
+  const int r = tid & 63, cg = tid >> 6;              // pass A
+  const int c2 = tid >> 2, rq = tid & 3;              // pass B
   double vav = 0.0;
-  for (int t = blockIdx.x; t < ntiles; t += G) {
-    int Ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while (Ii * (Ii + 1) / 2 > t) --Ii;
-    while ((Ii + 1) * (Ii + 2) / 2 <= t) ++Ii;
-    const int Ji = t - Ii * (Ii + 1) / 2;
-    const int I = Ib0 + Ii, J = Ib0 + Ji;
-    const int R0 = I * kTs, C0 = J * kTs;
-    __syncthreads();                                        // previous tile done with shared memory
+  for (int sidx = blockIdx.x; sidx < nseg; sidx += G) {
+    int Ii, seg;
+    segment_of(sidx, Ii, seg);
+    const int I = Ib0 + Ii;
+    const int Ja = Ib0 + seg * kSeg, Jb = min(I + 1, Ja + kSeg);     // tile columns [Ja, Jb)
+    const int R0 = I * kTs, rg = R0 + r;
+    __syncthreads();                                   // previous segment done with shared memory
     if (tid < kTs) {
       const int i = R0 + tid;
       double v = 0.0;
       if (i == j + 1) v = 1.0; else if (i > j + 1 && i < m) v = __ldcg(&a.x[i]) * sc.scale;
       s_vI[tid] = v;
-    } else if (tid < 2 * kTs) {
-      const int i = C0 + tid - kTs;
-      double v = 0.0;
-      if (i == j + 1) v = 1.0; else if (i > j + 1 && i < m) v = __ldcg(&a.x[i]) * sc.scale;
-      s_vJ[tid - kTs] = v;
     }
+    auto load_vJ = [&](int J, int buf) {
+      if (tid >= kTs && tid < 2 * kTs) {
+        const int i = J * kTs + tid - kTs;
+        double v = 0.0;
+        if (i == j + 1) v = 1.0; else if (i > j + 1 && i < m) v = __ldcg(&a.x[i]) * sc.scale;
+        s_vJ[buf * kTs + tid - kTs] = v;
+      }
+    };
+    double pre[16];
+    auto load_tile = [&](int J) {
+      const bool rowok = rg < m && rg > j;
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        const int c = cg * 16 + cc;
+        const int cgl = J * kTs + c;
+        pre[cc] = (rowok && cgl > j && (I != J || r >= c)) ? __ldcg(&a.A[(size_t)cgl * a.ld + rg]) : 0.0;
+      }
+    };
+    load_tile(Ja);
+    load_vJ(Ja, 0);
     __syncthreads();
-    // pass A: rows along lanes (coalesced), 16 columns per thread
-    const int rg = R0 + r;
-    double tacc = 0.0;
-#pragma unroll 4
-    for (int cc = 0; cc < 16; ++cc) {
-      const int c = cg * 16 + cc;
-      const int cgl = C0 + c;
-      double v = 0.0;
-      if (rg < m && rg > j && cgl > j && (I != J || r >= c)) v = __ldcg(&a.A[(size_t)cgl * a.ld + rg]);
-      tacc = fma(v, s_vJ[c], tacc);
-      s_tile[c * kTsPad + r] = (I == J && r == c) ? 0.0 : v;   // the diagonal is used once (pass A)
+    double viB[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) viB[rr] = s_vI[rq + 4 * rr];
+    double toff = 0.0, tdiag = 0.0;
+    for (int J = Ja; J < Jb; ++J) {
+      const int buf = (J - Ja) & 1;
+      // pass A
+      double* tb = s_tile + buf * kTs * kTsPad;
+      const double* vj = s_vJ + buf * kTs;
+      double tacc = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        const int c = cg * 16 + cc;
+        tacc = fma(pre[cc], vj[c], tacc);
+        tb[c * kTsPad + r] = (I == J && r == c) ? 0.0 : pre[cc];   // the diagonal is used once (pass A)
+      }
+      if (I == J) tdiag = tacc; else toff += tacc;
+      if (J + 1 < Jb) { load_tile(J + 1); load_vJ(J + 1, buf ^ 1); }   // in flight during pass B
+      __syncthreads();
+      // pass B
+      double u = 0.0;
+      const double* tc = tb + c2 * kTsPad + rq;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) u = fma(tc[4 * rr], viB[rr], u);
+      u += __shfl_xor_sync(0xffffffffu, u, 1);
+      u += __shfl_xor_sync(0xffffffffu, u, 2);
+      if (rq == 0) {
+        if (I == J) s_ud[c2] = u;
+        else if (J * kTs + c2 < m) a.Pb[(size_t)I * m + J * kTs + c2] = u;
+      }
     }
-    s_red[cg * kTs + r] = tacc;
-    __syncthreads();
-    // pass B: columns along lanes, 16 rows per thread (transposed product from shared memory)
-    const int c2 = tid & 63, rq = tid >> 6;
-    double uacc = 0.0;
-#pragma unroll 4
-    for (int rr = 0; rr < 16; ++rr) uacc = fma(s_tile[c2 * kTsPad + rq * 16 + rr], s_vI[rq * 16 + rr], uacc);
-    double tr = 0.0;
-    if (tid < kTs) tr = s_red[r] + s_red[kTs + r] + s_red[2 * kTs + r] + s_red[3 * kTs + r];
-    __syncthreads();
-    s_red[rq * kTs + c2] = uacc;
+    s_red[cg * kTs + r] = toff;
+    s_red[(4 + cg) * kTs + r] = tdiag;
     __syncthreads();
     if (tid < kTs) {
-      const double uc = s_red[tid] + s_red[kTs + tid] + s_red[2 * kTs + tid] + s_red[3 * kTs + tid];
-      if (I == J) {
-        if (R0 + tid < m) a.Pb[(size_t)I * m + R0 + tid] = tr + uc;
-        vav += s_vI[tid] * (tr + uc);
-      } else {
-        if (R0 + tid < m) a.Pb[(size_t)J * m + R0 + tid] = tr;
-        if (C0 + tid < m) a.Pb[(size_t)I * m + C0 + tid] = uc;
-        vav += 2.0 * s_vI[tid] * tr;
+      const double to = s_red[tid] + s_red[kTs + tid] + s_red[2 * kTs + tid] + s_red[3 * kTs + tid];
+      const bool has_diag = Jb == I + 1;
+      double td = 0.0;
+      if (has_diag) td = s_red[4 * kTs + tid] + s_red[5 * kTs + tid] + s_red[6 * kTs + tid] + s_red[7 * kTs + tid] + s_ud[tid];
+      if (R0 + tid < m) {
+        a.Pb[(size_t)Ja * m + R0 + tid] = to + td;
+        for (int J = Ja + 1; J < Jb; ++J) a.Pb[(size_t)J * m + R0 + tid] = 0.0;
       }
+      vav += s_vI[tid] * (2.0 * to + td);
     }
   }
   __syncthreads();
@@ -369,29 +424,49 @@ __device__ void sytrd_tail(const SytrdArgs& a) {
   }
 }
 
-constexpr size_t kSytrdSmemP2 = sizeof(double) * (kTs * kTsPad + 2 * kTs + 4 * kTs + 8);
+constexpr size_t kSytrdSmemP2 = sizeof(double) * (2 * kTs * kTsPad + 2 * kTs + kTs + 8 * kTs + kTs + 8);
 constexpr size_t kSytrdSmemUpd = sizeof(double) * 4 * kNbMax * kTs;
 constexpr size_t kSytrdSmem = kSytrdSmemP2 > kSytrdSmemUpd ? kSytrdSmemP2 : kSytrdSmemUpd;
 
-__global__ void __launch_bounds__(kSyThreads) k_sytrd(SytrdArgs a) {
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(kSyThreads, 2) k_sytrd(SytrdArgs a) {
   extern __shared__ __align__(16) double sy_smem[];
   unsigned target = 0;
   const int m = a.m;
+  const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = prof ? gtimer() : 0;
+#define MB_PROF(slot) if (prof) { const unsigned long long t1 = gtimer(); acc[slot] += t1 - t0; t0 = t1; }
   for (int j0 = 0; j0 < m - 2; j0 += kNbMax) {
     const int nbp = min(kNbMax, m - 2 - j0);
     for (int jj = 0; jj < nbp; ++jj) {
       const int j = j0 + jj;
       sytrd_p1(a, j, jj, sy_smem);
+      MB_PROF(0)
       grid_sync(a.bar, target);
+      MB_PROF(1)
       sytrd_p2(a, j, jj, sy_smem);
+      MB_PROF(2)
       grid_sync(a.bar, target);
+      MB_PROF(3)
       sytrd_p3(a, j, jj, sy_smem);
+      MB_PROF(4)
       grid_sync(a.bar, target);
+      MB_PROF(5)
     }
     sytrd_update(a, j0 + nbp, nbp, sy_smem);
+    MB_PROF(6)
     grid_sync(a.bar, target);
+    MB_PROF(7)
   }
+#undef MB_PROF
   sytrd_tail(a);
+  if (prof)
+    for (int k = 0; k < 8; ++k) a.prof[k] = acc[k];
 }
 
 // the same phases as separate kernels (kernel boundaries instead of the grid barrier)
@@ -399,7 +474,7 @@ __global__ void __launch_bounds__(kSyThreads) k_sytrd_p1(SytrdArgs a, int j, int
   extern __shared__ __align__(16) double sy_smem[];
   sytrd_p1(a, j, jj, sy_smem);
 }
-__global__ void __launch_bounds__(kSyThreads) k_sytrd_p2(SytrdArgs a, int j, int jj) {
+__global__ void __launch_bounds__(kSyThreads, 2) k_sytrd_p2(SytrdArgs a, int j, int jj) {
   extern __shared__ __align__(16) double sy_smem[];
   sytrd_p2(a, j, jj, sy_smem);
 }
@@ -415,30 +490,37 @@ __global__ void __launch_bounds__(kSyThreads) k_sytrd_update(SytrdArgs a, int jn
 __global__ void k_sytrd_tail(SytrdArgs a) { sytrd_tail(a); }
 
 // ---------------------------------------------------------------------------------------------
-// Eigenvalues of the symmetric tridiagonal (d, e) by bisection on the Sturm count.  One thread per eigenvalue
-// index (ascending); the start interval is the Gershgorin hull.  The count uses the three-term recurrence
-// p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (two dependent FP64 operations per step instead of a division),
-// rescaled by an exact power of two every 4 steps; #{eigenvalues < x} = #{i : sign p_i != sign p_{i-1}}, an
-// exact zero counting as a change.  Every eigenvalue is resolved until the midpoint stops moving.
+// Eigenvalues of the symmetric tridiagonal (d, e) by multisection on the Sturm count.  Eight threads share one
+// eigenvalue index k (ascending): each evaluates the count at one of 8 interior points of the current bracket,
+// the bracket shrinks 9-fold per round (3.17 bits instead of 1), start = Gershgorin hull.  The count uses the
+// three-term recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (one FP64 FMA on the critical path instead of
+// a division), rescaled by an exact power of two every 4 steps; #{eigenvalues < x} = #{i : sign p_i != sign
+// p_{i-1}}, an exact zero counting as a change.  Rounds stop when the bracket is below abstol (a fixed fraction
+// of ulp(|T|)) or 2 ulp of its own magnitude - deterministic, independent of the launch geometry.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_tri_eig(const double* __restrict__ d, const double* __restrict__ e2, int m,
-                                                double lo, double hi, double* __restrict__ eta) {
+constexpr int kEigThreads = 128;            // 16 eigenvalues x 8 section points per CTA
+__global__ void __launch_bounds__(kEigThreads) k_tri_eig(const double* __restrict__ d, const double* __restrict__ e2,
+                                                         int m, double lo, double hi, double abstol,
+                                                         double* __restrict__ eta) {
   extern __shared__ double s_tri[];           // d | e2
   double* s_d = s_tri;
   double* s_e2 = s_tri + m;
   for (int i = threadIdx.x; i < m; i += blockDim.x) { s_d[i] = d[i]; s_e2[i] = i < m - 1 ? e2[i] : 0.0; }
   __syncthreads();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;     // k-th smallest eigenvalue
-  if (k >= m) return;
+  const int sec = threadIdx.x & 7;
+  int k = blockIdx.x * (kEigThreads / 8) + (threadIdx.x >> 3);   // k-th smallest eigenvalue
+  const bool live = k < m;
+  if (!live) k = m - 1;                       // keep the whole warp in the shuffles
   double a = lo, b = hi;
-  for (int it = 0; it < 100; ++it) {
-    const double mid = 0.5 * (a + b);
-    if (!(mid > a && mid < b)) break;
-    double p0 = 1.0, p1 = s_d[0] - mid;
+  for (int it = 0; it < 40; ++it) {
+    const double w = b - a;
+    if (!(w > abstol && w > 4.4e-16 * fmax(fabs(a), fabs(b)))) break;   // uniform within the group of 8
+    const double x = a + w * ((sec + 1) * (1.0 / 9.0));
+    double p0 = 1.0, p1 = s_d[0] - x;
     bool neg1 = p1 < 0.0 || p1 == 0.0;        // p_0 = 1 > 0: a zero counts as a sign change
     int cnt = neg1;
     for (int i = 1; i < m; ++i) {
-      const double p2 = fma(s_d[i] - mid, p1, -s_e2[i - 1] * p0);
+      const double p2 = fma(s_d[i] - x, p1, -s_e2[i - 1] * p0);
       const bool neg2 = p2 < 0.0 || (p2 == 0.0 && !neg1);
       cnt += neg2 != neg1;
       p0 = p1; p1 = p2; neg1 = neg2;
@@ -451,9 +533,15 @@ __global__ void __launch_bounds__(64) k_tri_eig(const double* __restrict__ d, co
         }
       }
     }
-    if (cnt > k) b = mid; else a = mid;      // cnt = #eigenvalues < mid
+    // cnt = #eigenvalues < x, non-decreasing in sec: the new bracket is [largest x with cnt <= k, smallest x with cnt > k]
+    const unsigned grp = 0xffu << ((threadIdx.x & 31) & ~7);
+    const unsigned above = __ballot_sync(0xffffffffu, cnt > k) & grp;
+    const int first = above ? (__ffs(above) - 1) & 7 : 8;    // first section point whose count exceeds k
+    const double na = first == 0 ? a : a + w * (first * (1.0 / 9.0));
+    const double nb = first == 8 ? b : a + w * ((first + 1) * (1.0 / 9.0));
+    a = na; b = nb;
   }
-  eta[k] = 0.5 * (a + b);
+  if (live && sec == 0) eta[k] = 0.5 * (a + b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -478,7 +566,8 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
   a.d = ar.take_n<double>(m);
   a.e = ar.take_n<double>(m);
   a.fin = ar.take_n<double>(128);
-  a.bar = ar.take_n<unsigned>(4);
+  a.bar = ar.take_n<unsigned>(64);
+  a.prof = ctx->timing ? ar.take_n<unsigned long long>(8) : nullptr;
   static thread_local bool attr = false;
   if (!attr) {
     MB_CUDA(cudaFuncSetAttribute(k_sytrd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSytrdSmem));
@@ -493,9 +582,9 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
   if (occ < 1) throw Error(MB_E_UNSUPPORTED, "k_sytrd does not fit on an SM");
   // the grid barrier needs every CTA resident: at most two per SM, and never more than the device can hold
   const int G = std::max(1, std::min(occ, ctx->sytrd_ctas_per_sm > 0 ? ctx->sytrd_ctas_per_sm : 2)) * ctx->sm_count;
-  a.S = ar.take_n<double>((size_t)G * kSW);
+  a.S = ar.take_n<double>((size_t)((m + kChunk - 1) / kChunk) * kSW);
   a.S2 = ar.take_n<double>(G);
-  MB_CUDA(cudaMemsetAsync(a.bar, 0, 4 * sizeof(unsigned), st));
+  MB_CUDA(cudaMemsetAsync(a.bar, 0, 64 * sizeof(unsigned), st));
   if (ctx->sytrd_mode != 2) {
     void* params[] = {&a};
     MB_LAUNCH(ctx, "k_sytrd", st)
@@ -516,10 +605,14 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
   MB_CUDA(cudaGetLastError());
   diag.resize(m);
   off.resize(m - 1);
+  unsigned long long prof_ns[8] = {0};
+  if (a.prof && ctx->sytrd_mode != 2)
+    MB_CUDA(cudaMemcpyAsync(prof_ns, a.prof, sizeof(prof_ns), cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaMemcpyAsync(diag.data(), a.d, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaMemcpyAsync(off.data(), a.e, sizeof(double) * (m - 1), cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaStreamSynchronize(st));
-  // Gershgorin hull and the dlaebz pivot guard
+  for (int k = 0; k < 8; ++k) ctx->sytrd_prof_ms[k] = prof_ns[k] * 1e-6;
+  // Gershgorin hull
   double lo = 1e300, hi = -1e300, emax2 = 0.0;
   std::vector<double> e2(m, 0.0);
   for (int i = 0; i < m; ++i) {
@@ -541,7 +634,10 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
     MB_CUDA(cudaFuncSetAttribute(k_tri_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr2 = true;
   }
-  MB_LAUNCH(ctx, "k_tri_eig", st) k_tri_eig<<<(m + 63) / 64, 64, smem, st>>>(a.d, d_e2, m, lo, hi, d_eta);
+  double tnorm = 0.0;
+  for (int i = 0; i < m; ++i) tnorm = std::max(tnorm, std::fabs(diag[i]) + (i > 0 ? std::fabs(off[i - 1]) : 0.0) + (i < m - 1 ? std::fabs(off[i]) : 0.0));
+  const double abstol = 1e-3 * 2.220446049250313e-16 * tnorm;   // far below what the reduction itself resolves
+  MB_LAUNCH(ctx, "k_tri_eig", st) k_tri_eig<<<(m + 15) / 16, kEigThreads, smem, st>>>(a.d, d_e2, m, lo, hi, abstol, d_eta);
   MB_CUDA(cudaGetLastError());
   eta.resize(m);
   MB_CUDA(cudaMemcpyAsync(eta.data(), d_eta, sizeof(double) * m, cudaMemcpyDeviceToHost, st));

@@ -483,7 +483,8 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf_stream(
   float* s_Gf = reinterpret_cast<float*>(s_G0 + 2 * bh);                             // [2][bh][GFS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nboxes = lat.nbx * lat.nby;
-  const int nmine = (nboxes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int G = gridDim.x;
+  const int nmine = (nboxes - (int)blockIdx.x + G - 1) / G;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kLeafStages; ++s) mbar_init(&s_full[s], 1);
@@ -491,9 +492,13 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf_stream(
   }
   __syncthreads();
   constexpr uint32_t kRecBytes = P * P * 8 + 256;
-  auto issue = [&](int i) {   // warp 0: bulk copies of this CTA's i-th box into stage i % kLeafStages
-    const int s = i % kLeafStages;
-    const int b = blockIdx.x + i * gridDim.x;
+  // box walk without divisions: box b = blockIdx.x + i G has lattice position (bi, bj); every step adds (dI, dJ)
+  const int dI = G % lat.nbx, dJ = G / lat.nbx;
+  int pbi = blockIdx.x % lat.nbx, pbj = blockIdx.x / lat.nbx;      // producer cursor (warp 0)
+  int ibox = 0;                                                     // producer: next box to issue
+  auto issue = [&]() {   // warp 0: bulk copies of this CTA's next box into stage ibox % kLeafStages
+    const int s = ibox % kLeafStages;
+    const int b = blockIdx.x + ibox * G;
     unsigned char* sp = leaf_smem + s * stage_bytes;
     if (lane == 0) {
       mbar_expect_tx(&s_full[s], kRecBytes + (kAcc ? (uint32_t)bh * 256u : 0u));
@@ -502,107 +507,122 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf_stream(
     }
     if (kAcc) {
       __syncwarp();
-      const int bi = b % lat.nbx, bj = b / lat.nbx;
-      const double* src = fz.acc + (int64_t)bj * bh * fz.stride + bi * 32;
+      const double* src = fz.acc + (int64_t)pbj * bh * fz.stride + pbi * 32;
       for (int r = lane; r < bh; r += 32) bulk_g2s(sp + kRecBytes + r * 256, src + (int64_t)r * fz.stride, 256, &s_full[s]);
     }
+    pbi += dI; pbj += dJ;
+    if (pbi >= lat.nbx) { pbi -= lat.nbx; ++pbj; }
+    ++ibox;
   };
   if (warp == 0)
-    for (int i = 0; i < min(kLeafStages, nmine); ++i) issue(i);
+    for (int i = 0; i < min(kLeafStages, nmine); ++i) issue();
 
+  // lane = (half, l): half selects one row of a row pair, l the column pair (l, 31 - l): tx_{31-l} = -tx_l, so the
+  // even and the odd part of the expansion serve both columns
+  const int half = lane >> 4, l = lane & 15;
   float Txf[P];
   {
-    const float tx = (2.0f * lane + 1.0f) / 32.0f - 1.0f;   // exact in float32
+    const float tx = (2.0f * l + 1.0f) / 32.0f - 1.0f;   // exact in float32
     Txf[0] = 1.0f;
     Txf[1] = tx;
 #pragma unroll
     for (int k = 2; k < P; ++k) Txf[k] = 2.0f * tx * Txf[k - 1] - Txf[k - 2];
   }
-  const float cxl = (float)(lat.hx * ((lane + 0.5) / 32.0));
+  const float cxa = (float)(lat.hx * ((l + 0.5) / 32.0)), cxb = (float)(lat.hx * ((31 - l + 0.5) / 32.0));
   const double hyb = lat.hy / bh, inv_bh = 1.0 / bh;
+  const int npair = (bh + 1) >> 1;
 
-  auto collapse = [&](int i) {   // expansion block of box i -> G buffer i & 1
+  auto collapse = [&](int i) {   // expansion block of box i -> G buffer i & 1; rows lr and bh - 1 - lr share the products
     const double2* A2 = reinterpret_cast<const double2*>(leaf_smem + (i % kLeafStages) * stage_bytes);
     double* g0buf = s_G0 + (i & 1) * bh;
     float* gfbuf = s_Gf + (i & 1) * bh * GFS;
-    for (int o = tid; o < bh * (P / 2); o += kLeafThreads) {
+    for (int o = tid; o < npair * (P / 2); o += kLeafThreads) {
       const int lr = o / (P / 2), kp = o % (P / 2);
       const double ty = (2.0 * lr + 1.0) * inv_bh - 1.0;
       double t0 = 1.0, t1 = ty;
       const double2 a0 = A2[kp], a1 = A2[(P / 2) + kp];
-      double ga = fma(t1, a1.x, a0.x), gb = fma(t1, a1.y, a0.y);
+      double ea = a0.x, eb = a0.y, oa = t1 * a1.x, ob = t1 * a1.y;   // even / odd part in ty, columns 2 kp and 2 kp + 1
 #pragma unroll
       for (int j = 2; j < P; ++j) {
         const double t2 = 2.0 * ty * t1 - t0;
         const double2 a = A2[j * (P / 2) + kp];
-        ga = fma(t2, a.x, ga);
-        gb = fma(t2, a.y, gb);
+        if (j & 1) { oa = fma(t2, a.x, oa); ob = fma(t2, a.y, ob); }
+        else { ea = fma(t2, a.x, ea); eb = fma(t2, a.y, eb); }
         t0 = t1; t1 = t2;
       }
-      if (kp == 0) { g0buf[lr] = ga; gfbuf[lr * GFS] = (float)gb; }
-      else { gfbuf[lr * GFS + 2 * kp - 1] = (float)ga; gfbuf[lr * GFS + 2 * kp] = (float)gb; }
+      const int lm = bh - 1 - lr;
+      if (kp == 0) {
+        g0buf[lr] = ea + oa; g0buf[lm] = ea - oa;
+        gfbuf[lr * GFS] = (float)(eb + ob); gfbuf[lm * GFS] = (float)(eb - ob);
+      } else {
+        gfbuf[lr * GFS + 2 * kp - 1] = (float)(ea + oa); gfbuf[lm * GFS + 2 * kp - 1] = (float)(ea - oa);
+        gfbuf[lr * GFS + 2 * kp] = (float)(eb + ob); gfbuf[lm * GFS + 2 * kp] = (float)(eb - ob);
+      }
     }
   };
 
   mbar_wait(&s_full[0], 0);
   collapse(0);
   __syncthreads();
+  int cbi = blockIdx.x % lat.nbx, cbj = blockIdx.x / lat.nbx;      // consumer cursor (all threads)
   for (int i = 0; i < nmine; ++i) {
     if (i + 1 < nmine) {
       mbar_wait(&s_full[(i + 1) % kLeafStages], ((i + 1) / kLeafStages) & 1);
       collapse(i + 1);
     }
-    // ---- rows of box i ---------------------------------------------------------------------------
+    // ---- rows of box i: warp -> row pairs warp, warp + 8, ... ; lane half -> row of the pair -------------------
     {
       const unsigned char* sp = leaf_smem + (i % kLeafStages) * stage_bytes;
       const NearBlk* nb = reinterpret_cast<const NearBlk*>(sp + P * P * 8);
       const double* accT = reinterpret_cast<const double*>(sp + kRecBytes);
       const int cnt = nb->cnt;
-      const int b = blockIdx.x + i * gridDim.x;
-      const int bi = b % lat.nbx, bj = b / lat.nbx;
-      const int col = w.c0 + bi * 32 + lane;
-      const int row_base = w.r0 + bj * bh;
+      const int colA = w.c0 + cbi * 32 + l, colB = colA + 31 - 2 * l;
+      const bool okA = colA < w.c1, okB = colB < w.c1;
+      const int row_base = w.r0 + cbj * bh;
+      const int rows_here = min(bh, w.r1 - row_base);
       const double* g0buf = s_G0 + (i & 1) * bh;
       const float* gfbuf = s_Gf + (i & 1) * bh * GFS;
-      for (int lr = warp; lr < bh; lr += kLeafThreads / 32) {
-        const int row = row_base + lr;
-        if (row >= w.r1) break;
+      int lr = 2 * warp + half;
+      double* dst = out + (int64_t)(row_base - w.r0 + lr) * stride + (colA - w.c0);
+      const int64_t dstep = 16 * stride;
+      for (; lr < rows_here; lr += 16, dst += dstep) {
         const float4* g4 = reinterpret_cast<const float4*>(gfbuf + lr * GFS);
-        float a = 0.f;
+        float ev = 0.f, od = 0.f;
 #pragma unroll
         for (int q = 0; q < GFS / 4; ++q) {
           const float4 g = g4[q];
-          if (4 * q + 1 < P) a = fmaf(g.x, Txf[4 * q + 1], a);
-          if (4 * q + 2 < P) a = fmaf(g.y, Txf[4 * q + 2], a);
-          if (4 * q + 3 < P) a = fmaf(g.z, Txf[4 * q + 3], a);
-          if (4 * q + 4 < P) a = fmaf(g.w, Txf[4 * q + 4], a);
+          if (4 * q + 1 < P) od = fmaf(g.x, Txf[4 * q + 1], od);
+          if (4 * q + 2 < P) ev = fmaf(g.y, Txf[4 * q + 2], ev);
+          if (4 * q + 3 < P) od = fmaf(g.z, Txf[4 * q + 3], od);
+          if (4 * q + 4 < P) ev = fmaf(g.w, Txf[4 * q + 4], ev);
         }
+        float fa = ev + od, fb = ev - od;
         if (cnt > 0) {
           const float cyl = (float)(hyb * (lr + 0.5));
-          if (cnt <= kNearInline) {
-            for (int q = 0; q < cnt; ++q) {
-              const float4 kn = nb->e[q];
-              const float dx = cxl - kn.x, dy = cyl - kn.y;
-              const float r2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-20f);
-              a = fmaf(kn.z * r2, __log2f(r2), a);
-            }
-          } else {
-            const float4* src = near_over + nb->off;
-            for (int q = 0; q < cnt; ++q) {
-              const float4 kn = __ldg(&src[q]);
-              const float dx = cxl - kn.x, dy = cyl - kn.y;
-              const float r2 = fmaxf(fmaf(dx, dx, dy * dy), 1e-20f);
-              a = fmaf(kn.z * r2, __log2f(r2), a);
-            }
+          const float4* src = cnt <= kNearInline ? nb->e : near_over + nb->off;   // shared or global, generic loads
+          for (int q = 0; q < cnt; ++q) {
+            const float4 kn = src[q];
+            const float dy = cyl - kn.y, dy2 = dy * dy;
+            const float dxa = cxa - kn.x, dxb = cxb - kn.x;
+            const float r2a = fmaxf(fmaf(dxa, dxa, dy2), 1e-20f), r2b = fmaxf(fmaf(dxb, dxb, dy2), 1e-20f);
+            fa = fmaf(kn.z * r2a, __log2f(r2a), fa);
+            fb = fmaf(kn.z * r2b, __log2f(r2b), fb);
           }
         }
-        double v = g0buf[lr] + (double)a;
-        if (kAcc) v = fma(accT[lr * 32 + lane], fz.inv_w, v);
-        if (col < w.c1) __stcs(out + (int64_t)(row - w.r0) * stride + (col - w.c0), v);
+        const double g0 = g0buf[lr];
+        double va = g0 + (double)fa, vb = g0 + (double)fb;
+        if (kAcc) {
+          va = fma(accT[lr * 32 + l], fz.inv_w, va);
+          vb = fma(accT[lr * 32 + 31 - l], fz.inv_w, vb);
+        }
+        if (okA) __stcs(dst, va);
+        if (okB) __stcs(dst + (31 - 2 * l), vb);
       }
     }
+    cbi += dI; cbj += dJ;
+    if (cbi >= lat.nbx) { cbi -= lat.nbx; ++cbj; }
     __syncthreads();   // stage i % kLeafStages and G buffer i & 1 are free again
-    if (warp == 0 && i + kLeafStages < nmine) issue(i + kLeafStages);
+    if (warp == 0 && ibox < nmine) issue();
   }
 }
 

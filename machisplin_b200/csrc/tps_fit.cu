@@ -145,55 +145,69 @@ __global__ void k_add_diag(double* A, int ld, int m, double lam) {
   if (i < m) A[(size_t)i * ld + i] += lam;
 }
 
-// factor the kb x kb diagonal block in shared memory; info = 1 + failing column if not SPD
-__global__ void __launch_bounds__(kNB) k_potrf_diag(double* __restrict__ A, int ld, int kb, int col0,
+// factor the kb x kb diagonal block in shared memory (256 threads: thread = (row, column slice) of the rank-1
+// update); info = 1 + failing column if not SPD
+__global__ void __launch_bounds__(256) k_potrf_diag(double* __restrict__ A, int ld, int kb, int col0,
                                                     int* __restrict__ info) {
   __shared__ double s[kNB][kNB + 1];
-  const int t = threadIdx.x;
-  for (int j = 0; j < kb; ++j)
+  __shared__ int s_bad;
+  const int t = threadIdx.x & 63, cq = threadIdx.x >> 6;
+  if (threadIdx.x == 0) s_bad = 0;
+  for (int j = cq; j < kb; j += 4)
     if (t < kb) s[t][j] = A[(size_t)j * ld + t];
   __syncthreads();
   for (int j = 0; j < kb; ++j) {
     const double djj = s[j][j];
     if (!(djj > 0.0)) {
-      if (t == 0 && *info == 0) *info = col0 + j + 1;
-      return;
+      if (threadIdx.x == 0 && *info == 0) *info = col0 + j + 1;
+      return;                                   // uniform: every thread reads the same s[j][j]
     }
-    const double l = sqrt(djj);
-    __syncthreads();
-    if (t == j) s[j][j] = l;
-    if (t > j && t < kb) s[t][j] /= l;
+    const double rl = 1.0 / sqrt(djj);
+    __syncthreads();                            // everyone has read the pivot
+    if (cq == 0) {
+      if (t == j) s[j][j] = sqrt(djj);
+      else if (t > j && t < kb) s[t][j] *= rl;
+    }
     __syncthreads();
     if (t > j && t < kb) {
       const double ltj = s[t][j];
-      for (int c = j + 1; c <= t; ++c) s[t][c] -= ltj * s[c][j];
+      for (int c = j + 1 + cq; c <= t; c += 4) s[t][c] = fma(-ltj, s[c][j], s[t][c]);
     }
-    __syncthreads();
+    __syncthreads();                            // the next pivot is final
   }
-  for (int j = 0; j < kb; ++j)
+  for (int j = cq; j < kb; j += 4)
     if (t < kb) A[(size_t)j * ld + t] = (t >= j) ? s[t][j] : 0.0;
 }
 
-// rows below the diagonal block: X L11' = A21  ->  one thread per row
-__global__ void __launch_bounds__(128) k_trsm_panel(const double* __restrict__ L11, double* __restrict__ A21, int ld,
-                                                    int kb, int nrows) {
-  __shared__ double s[kNB][kNB + 1];
-  for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
-    const int r = idx % kb, c = idx / kb;
-    s[r][c] = L11[(size_t)c * ld + r];
+// rows below the diagonal block: X L11' = A21.  One thread per row, x[64] in registers, column-oriented
+// substitution (after x_c is final it is eliminated from every later column: independent FMAs, fully unrolled).
+// Right-hand sides ride along as extra rows of the panel (forward substitution for free).
+__global__ void __launch_bounds__(64, 1) k_trsm_panel(const double* __restrict__ L11, double* __restrict__ A21, int ld,
+                                                   int kb, int nrows) {
+  __shared__ double s[kNB][kNB + 1];            // s[j][c] = L11[j][c], diagonal replaced by its reciprocal
+  for (int idx = threadIdx.x; idx < kNB * kNB; idx += blockDim.x) {
+    const int r = idx % kNB, c = idx / kNB;
+    double v = 0.0;
+    if (r < kb && c < kb) v = L11[(size_t)c * ld + r];
+    if (r == c) v = (r < kb) ? 1.0 / v : 1.0;
+    s[r][c] = v;
   }
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
   double x[kNB];
-#pragma unroll 8
+#pragma unroll
   for (int j = 0; j < kNB; ++j) x[j] = (j < kb) ? A21[(size_t)j * ld + i] : 0.0;
-  for (int j = 0; j < kb; ++j) {
-    double v = x[j];
-    for (int c = 0; c < j; ++c) v -= x[c] * s[j][c];
-    x[j] = v / s[j][j];
+#pragma unroll
+  for (int c = 0; c < kNB; ++c) {
+    const double xc = x[c] * s[c][c];
+    x[c] = xc;
+#pragma unroll
+    for (int j = c + 1; j < kNB; ++j) x[j] = fma(-xc, s[j][c], x[j]);
   }
-  for (int j = 0; j < kb; ++j) A21[(size_t)j * ld + i] = x[j];
+#pragma unroll
+  for (int j = 0; j < kNB; ++j)
+    if (j < kb) A21[(size_t)j * ld + i] = x[j];
 }
 
 // trailing update on the FP64 tensor pipe:  C(lower tiles) -= P P',  P = panel (n x kb, column-major ld)
@@ -243,26 +257,31 @@ __global__ void __launch_bounds__(256) k_syrk_dmma(const double* __restrict__ Pn
   }
 }
 
-// forward / backward substitution with the Cholesky factor for nrhs right-hand sides (single CTA;
-// O(m^2) work, negligible next to the O(m^3) factorisation).  The 64 x 64 diagonal block is staged
-// in shared memory and solved by warp 0; the off-diagonal update is spread over the whole CTA.
-__global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ Lm, int ld, int m,
-                                                     double* __restrict__ B, int ldb, int nrhs) {
+// Forward (L y = b) / backward (L' x = y) substitution with the Cholesky factor, one launch per 64-column block,
+// right-looking in both directions: every CTA solves the 64 x 64 triangular block redundantly (warp 0, operands
+// in shared memory) and then eliminates it from its share of the remaining unknowns - rows below the block
+// (forward; coalesced over rows) or columns left of it (backward; each thread streams 64 contiguous doubles).
+// The solved block goes to `out`, the remaining right-hand side is updated in place: no two CTAs touch the same
+// element within a launch.
+template <bool kBackward>
+__global__ void __launch_bounds__(256) k_chol_sweep(const double* __restrict__ Lm, int ld, int m, int k0, int kb,
+                                                    double* __restrict__ B, double* __restrict__ out, int ldb,
+                                                    int nrhs) {
   __shared__ double s_L[kNB][kNB + 1];
   __shared__ double s_x[kNB];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
+    const int i = idx % kb, j = idx / kb;
+    s_L[i][j] = Lm[(size_t)(k0 + j) * ld + k0 + i];
+  }
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   for (int r = 0; r < nrhs; ++r) {
     double* b = B + (size_t)r * ldb;
-    // ---- L y = b ----
-    for (int k0 = 0; k0 < m; k0 += kNB) {
-      const int kb = min(kNB, m - k0);
-      for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
-        const int i = idx % kb, j = idx / kb;
-        s_L[i][j] = Lm[(size_t)(k0 + j) * ld + k0 + i];
-      }
-      if (threadIdx.x < kb) s_x[threadIdx.x] = b[k0 + threadIdx.x];
-      __syncthreads();
-      if (warp == 0) {
+    __syncthreads();
+    if (threadIdx.x < kb) s_x[threadIdx.x] = b[k0 + threadIdx.x];
+    __syncthreads();
+    if (warp == 0) {
+      if (!kBackward) {
         for (int j = 0; j < kb; ++j) {
           const double v = s_x[j] / s_L[j][j];
           __syncwarp();
@@ -270,34 +289,7 @@ __global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ 
           for (int i = j + 1 + lane; i < kb; i += 32) s_x[i] -= v * s_L[i][j];
           __syncwarp();
         }
-      }
-      __syncthreads();
-      if (threadIdx.x < kb) b[k0 + threadIdx.x] = s_x[threadIdx.x];
-      for (int i = k0 + kb + threadIdx.x; i < m; i += blockDim.x) {
-        double acc = b[i];
-        for (int j = 0; j < kb; ++j) acc -= Lm[(size_t)(k0 + j) * ld + i] * s_x[j];
-        b[i] = acc;
-      }
-      __syncthreads();
-    }
-    // ---- L' x = y ----
-    for (int k1 = m; k1 > 0; k1 -= kNB) {
-      const int k0 = max(0, k1 - kNB);
-      const int kb = k1 - k0;
-      for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
-        const int i = idx % kb, j = idx / kb;
-        s_L[i][j] = Lm[(size_t)(k0 + j) * ld + k0 + i];
-      }
-      // tail: s_x[j] = b[k0 + j] - sum_{i >= k1} L[i, k0 + j] x[i]
-      for (int j = warp; j < kb; j += nwarp) {
-        double acc = 0.0;
-        for (int i = k1 + lane; i < m; i += 32) acc = fma(Lm[(size_t)(k0 + j) * ld + i], b[i], acc);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) s_x[j] = b[k0 + j] - acc;
-      }
-      __syncthreads();
-      if (warp == 0) {
+      } else {
         for (int j = kb - 1; j >= 0; --j) {
           const double v = s_x[j] / s_L[j][j];
           __syncwarp();
@@ -306,11 +298,46 @@ __global__ void __launch_bounds__(1024) k_chol_solve(const double* __restrict__ 
           __syncwarp();
         }
       }
-      __syncthreads();
-      if (threadIdx.x < kb) b[k0 + threadIdx.x] = s_x[threadIdx.x];
-      __syncthreads();
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < kb) out[(size_t)r * ldb + k0 + threadIdx.x] = s_x[threadIdx.x];
+    if (!kBackward) {
+      const int i = k0 + kb + gid;
+      if (i < m) {
+        double acc = b[i];
+#pragma unroll 8
+        for (int j = 0; j < kb; ++j) acc = fma(-Lm[(size_t)(k0 + j) * ld + i], s_x[j], acc);
+        b[i] = acc;
+      }
+    } else {
+      const int c = gid;
+      if (c < k0) {
+        const double* col = Lm + (size_t)c * ld + k0;
+        double acc = b[c];
+#pragma unroll 8
+        for (int j = 0; j < kb; ++j) acc = fma(-col[j], s_x[j], acc);
+        b[c] = acc;
+      }
     }
   }
+}
+
+// x <- (L L')^-1 b for nrhs right-hand sides: B (m x nrhs, ldb) is overwritten with the solution; tmp is
+// scratch of the same shape.
+static void cholesky_solve(mb_ctx* ctx, const double* Lm, int ld, int m, double* B, double* tmp, int ldb, int nrhs,
+                           cudaStream_t st) {
+  for (int k0 = 0; k0 < m; k0 += kNB) {          // L y = b : y -> tmp
+    const int kb = std::min(kNB, m - k0);
+    const int rest = m - k0 - kb;
+    MB_LAUNCH(ctx, "k_chol_sweep", st) k_chol_sweep<false><<<std::max(1, (rest + 255) / 256), 256, 0, st>>>(Lm, ld, m, k0, kb, B, tmp, ldb, nrhs);
+  }
+  for (int k1 = m; k1 > 0;) {                    // L' x = y : x -> B
+    const int k0 = ((k1 - 1) / kNB) * kNB;
+    const int kb = k1 - k0;
+    MB_LAUNCH(ctx, "k_chol_sweep", st) k_chol_sweep<true><<<std::max(1, (k0 + 255) / 256), 256, 0, st>>>(Lm, ld, m, k0, kb, tmp, B, ldb, nrhs);
+    k1 = k0;
+  }
+  MB_CUDA(cudaGetLastError());
 }
 
 static void cholesky_lower(mb_ctx* ctx, double* A, int ld, int m, cudaStream_t st) {
@@ -321,10 +348,10 @@ static void cholesky_lower(mb_ctx* ctx, double* A, int ld, int m, cudaStream_t s
   for (int k = 0; k < m; k += kNB) {
     const int kb = std::min(kNB, m - k);
     double* Akk = A + (size_t)k * ld + k;
-    MB_LAUNCH(ctx, "k_potrf_diag", st) k_potrf_diag<<<1, kNB, 0, st>>>(Akk, ld, kb, k, d_info.p);
+    MB_LAUNCH(ctx, "k_potrf_diag", st) k_potrf_diag<<<1, 256, 0, st>>>(Akk, ld, kb, k, d_info.p);
     const int rest = m - k - kb;
     if (rest > 0) {
-      MB_LAUNCH(ctx, "k_trsm_panel", st) k_trsm_panel<<<(rest + 127) / 128, 128, 0, st>>>(Akk, Akk + kb, ld, kb, rest);
+      MB_LAUNCH(ctx, "k_trsm_panel", st) k_trsm_panel<<<(rest + 63) / 64, 64, 0, st>>>(Akk, Akk + kb, ld, kb, rest);
       const int nt = (rest + kNB - 1) / kNB;
       MB_LAUNCH(ctx, "k_syrk_dmma", st) k_syrk_dmma<<<dim3(nt, nt), 256, kSyrkSmem, st>>>(Akk + kb, A + (size_t)(k + kb) * ld + (k + kb), ld, rest, kb);
     }
@@ -720,13 +747,13 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
         edf[r] = gcv::tr_a(lam[r], D);
       }
       // ---- Krig.coef at the selected lambda: (M + lambda I) beta = z by the tensor-core Cholesky ----------
-      ABuf<double> d_B(ar, m);
+      ABuf<double> d_B(ar, m), d_tmp(ar, m);
       for (int r = 0; r < L; ++r) {
         MB_CUDA(cudaMemcpyAsync(d_T.p, M, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToDevice, st));
         MB_LAUNCH(ctx, "k_add_diag", st) k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(d_T.p, m, m, lam[r]);
         cholesky_lower(ctx, d_T.p, m, m, st);
         MB_CUDA(cudaMemcpyAsync(d_B.p, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
-        MB_LAUNCH(ctx, "k_chol_solve", st) k_chol_solve<<<1, 1024, 0, st>>>(d_T.p, m, m, d_B.p, m, 1);
+        cholesky_solve(ctx, d_T.p, m, m, d_B.p, d_tmp.p, m, 1, st);
         MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
       }
@@ -779,7 +806,8 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     ABuf<double> d_B(ar, (size_t)m * L);
     for (int r = 0; r < L; ++r)
       MB_CUDA(cudaMemcpyAsync(d_B.p + (size_t)r * m, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
-    MB_LAUNCH(ctx, "k_chol_solve", st) k_chol_solve<<<1, 1024, 0, st>>>(M, m, m, d_B.p, m, L);
+    ABuf<double> d_tmp(ar, (size_t)m * L);
+    cholesky_solve(ctx, M, m, m, d_B.p, d_tmp.p, m, L, st);
     for (int r = 0; r < L; ++r)
       MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p + (size_t)r * m, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));

@@ -240,6 +240,13 @@ class Engine:
     def set_fast_eval_params(self, cheb_p=0, leaf_cols=0, leaf_rows=0):
         check(self.lib.mb_set_fast_eval_params(self._h, cheb_p, leaf_cols, leaf_rows))
 
+    def debug_values(self, name: str, cap: int = 16):
+        out = np.zeros(cap)
+        n = self.lib.mb_debug_values(self._h, name.encode(), _pd(out), cap)
+        if n < 0:
+            check(n)
+        return out[:n]
+
     def set_param(self, name: str, value: int):
         check(self.lib.mb_set_param(self._h, name.encode(), int(value)))
 
