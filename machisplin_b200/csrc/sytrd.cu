@@ -8,12 +8,13 @@
 //
 // k_sytrd: ONE persistent kernel, blocked right-looking reduction on the LOWER triangle only (the 100 MB lower
 // half of a 5 000 x 5 000 float64 matrix stays in the 126 MB L2; the full matrix would not).  Per column j:
-//   P1 rows   x = A[j+1:, j] - V W[j,:]' - W V[j,:]'   (deferred rank-2k update of the panel), d_j, partial norms / dots
-//   P2 tiles  y = A v on 64 x 64 lower tiles: each tile is read once and used for both y_I += A_IJ v_J and
-//             y_J += A_IJ' v_I (second pass from shared memory); partial results go to fixed slots (no atomics:
-//             the summation order, hence T, is deterministic)
-//   P3 rows   w = tau (y - V W'v - W V'v) - 1/2 tau (p'v) v ; z^ <- H_j z^
-// separated by a software grid barrier (release/acquire on one counter); every 32 columns the trailing matrix
+//   P2  tiles  y = A v on 64 x 64 lower tiles: each tile is read once and used for both y_I += A_IJ v_J and
+//              y_J += A_IJ' v_I (second pass from shared memory); partial results go to fixed slots (no atomics:
+//              the summation order, hence T, is deterministic); a few CTAs also reduce the panel dots W'v, V'v, v'z
+//   P31 rows   w = tau (y - V W'v - W V'v) - 1/2 tau (p'v) v ; z^ <- H_j z^ ; then the next column
+//              x = A[j+2:, j+1] - V W[j+1,:]' - W V[j+1,:]' (deferred rank-2k update of the panel), d_{j+1}, |x|^2
+// separated by a software grid barrier (two per column; arrivals on a counter, release through a flag on its own
+// cache line); every 32 columns the trailing matrix
 // takes the rank-64 update A -= V W' + W V' (lower tiles).  The same phase functions are also exposed as separate
 // kernels (mb_set_param "sytrd_mode" = 2): kernel boundaries replace the grid barrier.
 #include "common.cuh"
@@ -25,7 +26,6 @@
 namespace mb {
 
 constexpr int kTs = 64;            // tile edge
-constexpr int kTsPad = kTs + 4;    // shared-memory column stride: conflict-free for both passes (see sytrd_p2)
 constexpr int kSeg = 4;            // tiles per strip segment
 constexpr int kNbMax = 32;         // panel width
 constexpr int kSW = 128;           // doubles per row chunk in the P1 partial block: [0] |x|^2, [1..32] z dots, [33+q] W'x, [65+q] V'x
@@ -76,7 +76,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 // fixed-order sum of n doubles spaced `stride` apart, by one warp (all lanes return the sum)
 __device__ __forceinline__ double warp_strided_sum(const double* p, int n, int stride, int lane) {
   double acc = 0.0;
-  for (int i = lane; i < n; i += 32) acc += __ldcg(p + (size_t)i * stride);
+  for (int base = 0; base < n; base += 256) {       // 8 independent loads per lane in flight
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * 32 + lane;
+      v[u] = i < n ? __ldcg(p + (size_t)i * stride) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
   return warp_sum(acc);
 }
 
@@ -93,58 +102,28 @@ __device__ __forceinline__ Scal householder_scalars(double alpha, double xnorm2)
   return s;
 }
 
-// ---- P1: true column j (rows >= j), partial norms / dots per row chunk ---------------------------------
-__device__ void sytrd_p1(const SytrdArgs& a, int j, int jj, double* smem) {
+// ---- P1 (first column of a panel; later columns are formed by P31): true column j (rows >= j), |x|^2 per chunk
+__device__ void sytrd_p1(const SytrdArgs& a, int j, double* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.m, G = gridDim.x;
-  double* s_red = smem;                       // [8][32]
   const int first_chunk = j / kChunk;
   const int nchunk = (m + kChunk - 1) / kChunk;
-  // chunk c is owned by CTA c % G
+  // chunk c is owned by CTA c % G; jj = 0: no deferred update to apply
   int c = first_chunk + (((int)blockIdx.x - first_chunk) % G + G) % G;
   for (; c < nchunk; c += G) {
+    if (warp != 0) continue;
     const int i = c * kChunk + lane;
     const bool act = i >= j && i < m;
-    // slice of the deferred update: q = warp, warp + 8, ...
-    double acc = 0.0;
-    if (act)
-      for (int q = warp; q < jj; q += 8)
-        acc += __ldcg(&a.V[(size_t)q * m + i]) * __ldcg(&a.W[(size_t)q * m + j]) +
-               __ldcg(&a.W[(size_t)q * m + i]) * __ldcg(&a.V[(size_t)q * m + j]);
-    __syncthreads();                           // previous chunk done with s_red
-    s_red[warp * 32 + lane] = acc;
-    __syncthreads();
     double xi = 0.0;
-    if (warp == 0) {
-      double corr = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) corr += s_red[k * 32 + lane];
-      if (act) {
-        xi = __ldcg(&a.A[(size_t)j * a.ld + i]) - corr;
-        if (i == j) a.d[j] = xi;
-        else a.x[i] = xi;
-      }
+    if (act) {
+      xi = __ldcg(&a.A[(size_t)j * a.ld + i]);
+      if (i == j) a.d[j] = xi;
+      else a.x[i] = xi;
     }
-    __syncthreads();
-    if (warp == 0) s_red[lane] = (act && i > j) ? xi : 0.0;     // x of this chunk for the other warps
-    __syncthreads();
-    xi = s_red[lane];
-    const bool tail = act && i > j + 1;            // rows below the pivot row j + 1
-    double* Sc = a.S + (size_t)c * kSW;
-    if (warp == 0) {
-      const double n2 = warp_sum(tail ? xi * xi : 0.0);
-      if (lane == 0) Sc[0] = n2;
-    }
-    for (int r = warp; r < a.L; r += 8) {
-      const double t = warp_sum(tail ? xi * __ldcg(&a.z[(size_t)r * m + i]) : 0.0);
-      if (lane == 0) Sc[1 + r] = t;
-    }
-    for (int q = warp; q < jj; q += 8) {
-      const double t1 = warp_sum(tail ? xi * __ldcg(&a.W[(size_t)q * m + i]) : 0.0);
-      const double t2 = warp_sum(tail ? xi * __ldcg(&a.V[(size_t)q * m + i]) : 0.0);
-      if (lane == 0) { Sc[33 + q] = t1; Sc[65 + q] = t2; }
-    }
+    const double n2 = warp_sum((act && i > j + 1) ? xi * xi : 0.0);
+    if (lane == 0) a.S[(size_t)c * kSW] = n2;
   }
+  (void)smem;
 }
 
 // segments of block row r (relative to the first active block): r / kSeg + 1; rows 4a .. 4a+3 before them hold
@@ -163,23 +142,21 @@ __device__ __forceinline__ int segment_count(int na) {
 }
 
 // ---- P2: y = A v on the lower tiles ------------------------------------------------------------------------
-// Work unit = segment of <= 4 consecutive tiles of one block row I.  Pass A (thread = row r, 16 columns): the tile
-// comes from global memory (coalesced along rows, prefetched one tile ahead into registers), feeds the running
-// row product t_r += A[r,c] v_c and is parked in shared memory; pass B (thread = column c, rows rq, rq+4, ...):
-// the transposed product u_c = sum_r A[r,c] v_r from shared memory, the 4 row slices of a column sit in adjacent
-// lanes and are combined by two shuffles.  Column stride 68 makes both passes bank-conflict free; the tile
-// buffer is double-buffered so that one __syncthreads per tile suffices.
+// Work unit = segment of <= 4 consecutive tiles of one block row I.  No shared memory and no barrier per tile:
+// lane = (rgrp, cgrp), thread = 8 rows x 2 columns of the tile in registers (128-bit loads, 512 contiguous bytes
+// per column across the 8 row groups; the next tile is prefetched while the current one is used).  Each element
+// feeds both products: t_r += A[r,c] v_c accumulates over the whole segment in registers, u_c = sum_r A[r,c] v_r is
+// reduced over the 8 row groups by three shuffles.  v is zero outside (j, m), so stale rows / columns <= j and the
+// zero padding of the work matrix need no predicate; only the diagonal tile masks its upper triangle.
 // Slots: Pb[a][rows of block b] holds, for a <= b, the row product of the segment of block row b that STARTS at
 // tile column a (zero for the other columns of the segment) and, for a > b, the transposed product of tile (a, b).
 __device__ void sytrd_p2(const SytrdArgs& a, int j, int jj, double* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.m, G = gridDim.x;
-  double* s_tile = smem;                              // [2][64][68]
-  double* s_vJ = s_tile + 2 * kTs * kTsPad;           // [2][64]
-  double* s_vI = s_vJ + 2 * kTs;                      // 64
-  double* s_red = s_vI + kTs;                         // [8][64]: t_off, t_diag per column group
-  double* s_ud = s_red + 8 * kTs;                     // 64: transposed product of the diagonal tile
-  double* s_sc = s_ud + kTs;                          // scalars
+  double* s_red = smem;                               // [8][64]: row products per warp
+  double* s_ud = s_red + 8 * kTs;                    // 64: transposed product of the diagonal tile
+  double* s_vI = s_ud + kTs;                          // 64
+  double* s_sc = s_vI + kTs;                          // scalars
   const int first_chunk = j / kChunk;
   const int nchunk = (m + kChunk - 1) / kChunk;
   if (warp == 0) {
@@ -193,161 +170,246 @@ __device__ void sytrd_p2(const SytrdArgs& a, int j, int jj, double* smem) {
     a.fin[0] = sc.tau; a.fin[1] = sc.scale; a.fin[2] = sc.beta; a.fin[3] = sc.alpha;
     a.e[j] = sc.beta;
   }
-  // reduced dots for P3, one per CTA (from the back of the grid: those CTAs have the fewest segments):
+  // dots for P31, one per CTA (from the back of the grid: those CTAs own the fewest segments), straight from x:
   // v'z_r = z[j+1] + scale sum_{i>j+1} x_i z_i ;  g1 = W'v, g2 = V'v likewise (the pivot row enters with v = 1)
-  if (warp == 0) {
-    for (int k = G - 1 - (int)blockIdx.x; k < a.L + 2 * jj; k += G) {
-      int col; const double* piv;
-      if (k < a.L) { col = 1 + k; piv = &a.z[(size_t)k * m + j + 1]; }
-      else if (k < a.L + jj) { col = 33 + (k - a.L); piv = &a.W[(size_t)(k - a.L) * m + j + 1]; }
-      else { col = 65 + (k - a.L - jj); piv = &a.V[(size_t)(k - a.L - jj) * m + j + 1]; }
-      const double t = warp_strided_sum(a.S + (size_t)first_chunk * kSW + col, nchunk - first_chunk, kSW, lane);
-      if (lane == 0) a.fin[4 + (col - 1)] = __ldcg(piv) + sc.scale * t;
+  for (int k = G - 1 - (int)blockIdx.x; k < a.L + 2 * jj; k += G) {
+    int slot; const double* colp;
+    if (k < a.L) { slot = 4 + k; colp = a.z + (size_t)k * m; }
+    else if (k < a.L + jj) { slot = 36 + (k - a.L); colp = a.W + (size_t)(k - a.L) * m; }
+    else { slot = 68 + (k - a.L - jj); colp = a.V + (size_t)(k - a.L - jj) * m; }
+    double acc = 0.0;
+    for (int i0 = j + 2 + tid; i0 < m; i0 += 4 * kSyThreads) {
+      double xv[4], cv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kSyThreads;
+        xv[u] = i < m ? __ldcg(&a.x[i]) : 0.0;
+        cv[u] = i < m ? __ldcg(&colp[i]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = fma(xv[u], cv[u], acc);
+    }
+    acc = warp_sum(acc);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < kSyThreads / 32; ++q) t += s_red[q];
+      a.fin[slot] = __ldcg(&colp[j + 1]) + sc.scale * t;
     }
   }
   const int Ib0 = (j + 1) / kTs;
   const int na = a.nt - Ib0;
   const int nseg = segment_count(na);
-  const int r = tid & 63, cg = tid >> 6;              // pass A
-  const int c2 = tid >> 2, rq = tid & 3;              // pass B
+  const int rgrp = lane & 7, cgrp = lane >> 3;
+  const int r0 = rgrp * 8;                            // rows r0 .. r0 + 7 of the tile
+  const int c0 = warp * 8 + cgrp * 2;                 // columns c0, c0 + 1 of the tile
+  auto vval = [&](int i) -> double {                  // v_i: 0 outside (j, m), 1 at the pivot row
+    if (i <= j || i >= m) return 0.0;
+    return i == j + 1 ? 1.0 : __ldcg(&a.x[i]) * sc.scale;
+  };
   double vav = 0.0;
   for (int sidx = blockIdx.x; sidx < nseg; sidx += G) {
     int Ii, seg;
     segment_of(sidx, Ii, seg);
     const int I = Ib0 + Ii;
     const int Ja = Ib0 + seg * kSeg, Jb = min(I + 1, Ja + kSeg);     // tile columns [Ja, Jb)
-    const int R0 = I * kTs, rg = R0 + r;
-    __syncthreads();                                   // previous segment done with shared memory
-    if (tid < kTs) {
-      const int i = R0 + tid;
-      double v = 0.0;
-      if (i == j + 1) v = 1.0; else if (i > j + 1 && i < m) v = __ldcg(&a.x[i]) * sc.scale;
-      s_vI[tid] = v;
-    }
-    auto load_vJ = [&](int J, int buf) {
-      if (tid >= kTs && tid < 2 * kTs) {
-        const int i = J * kTs + tid - kTs;
-        double v = 0.0;
-        if (i == j + 1) v = 1.0; else if (i > j + 1 && i < m) v = __ldcg(&a.x[i]) * sc.scale;
-        s_vJ[buf * kTs + tid - kTs] = v;
-      }
-    };
-    double pre[16];
-    auto load_tile = [&](int J) {
-      const bool rowok = rg < m && rg > j;
+    const int R0 = I * kTs;
+    double vI[8];
 #pragma unroll
-      for (int cc = 0; cc < 16; ++cc) {
-        const int c = cg * 16 + cc;
-        const int cgl = J * kTs + c;
-        pre[cc] = (rowok && cgl > j && (I != J || r >= c)) ? __ldcg(&a.A[(size_t)cgl * a.ld + rg]) : 0.0;
-      }
+    for (int rr = 0; rr < 8; ++rr) vI[rr] = vval(R0 + r0 + rr);
+    double pre[16], pvj[2];
+    auto load_tile = [&](int J) {
+      const double* base = a.A + (size_t)(J * kTs + c0) * a.ld + R0 + r0;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const double2 v2 = __ldcg(reinterpret_cast<const double2*>(base + (size_t)cc * a.ld) + h);
+          pre[cc * 8 + 2 * h] = v2.x;
+          pre[cc * 8 + 2 * h + 1] = v2.y;
+        }
+      pvj[0] = vval(J * kTs + c0);
+      pvj[1] = vval(J * kTs + c0 + 1);
     };
     load_tile(Ja);
-    load_vJ(Ja, 0);
-    __syncthreads();
-    double viB[16];
+    double tsum[8];                                    // row products of the whole segment (off-diagonal + diagonal tile)
 #pragma unroll
-    for (int rr = 0; rr < 16; ++rr) viB[rr] = s_vI[rq + 4 * rr];
-    double toff = 0.0, tdiag = 0.0;
+    for (int rr = 0; rr < 8; ++rr) tsum[rr] = 0.0;
     for (int J = Ja; J < Jb; ++J) {
-      const int buf = (J - Ja) & 1;
-      // pass A
-      double* tb = s_tile + buf * kTs * kTsPad;
-      const double* vj = s_vJ + buf * kTs;
-      double tacc = 0.0;
+      const double vj0 = pvj[0], vj1 = pvj[1];
+      double u0a = 0.0, u0b = 0.0, u1a = 0.0, u1b = 0.0;
+      if (I != J) {
 #pragma unroll
-      for (int cc = 0; cc < 16; ++cc) {
-        const int c = cg * 16 + cc;
-        tacc = fma(pre[cc], vj[c], tacc);
-        tb[c * kTsPad + r] = (I == J && r == c) ? 0.0 : pre[cc];   // the diagonal is used once (pass A)
+        for (int rr = 0; rr < 8; ++rr) {
+          tsum[rr] = fma(pre[rr], vj0, fma(pre[8 + rr], vj1, tsum[rr]));
+          if (rr & 1) { u0b = fma(pre[rr], vI[rr], u0b); u1b = fma(pre[8 + rr], vI[rr], u1b); }
+          else { u0a = fma(pre[rr], vI[rr], u0a); u1a = fma(pre[8 + rr], vI[rr], u1a); }
+        }
+      } else {
+        // diagonal tile: lower triangle only; the diagonal itself belongs to the row product.  Its row product
+        // enters v'Av once, not twice like the off-diagonal tiles: remember q = v_I' t_diag and take it off below.
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = r0 + rr;
+          const double a0 = r >= c0 ? pre[rr] : 0.0, a1 = r >= c0 + 1 ? pre[8 + rr] : 0.0;
+          const double td = fma(a0, vj0, a1 * vj1);
+          tsum[rr] += td;
+          vav -= vI[rr] * td;
+          u0a = fma(r > c0 ? a0 : 0.0, vI[rr], u0a);
+          u1a = fma(r > c0 + 1 ? a1 : 0.0, vI[rr], u1a);
+        }
       }
-      if (I == J) tdiag = tacc; else toff += tacc;
-      if (J + 1 < Jb) { load_tile(J + 1); load_vJ(J + 1, buf ^ 1); }   // in flight during pass B
-      __syncthreads();
-      // pass B
-      double u = 0.0;
-      const double* tc = tb + c2 * kTsPad + rq;
+      if (J + 1 < Jb) load_tile(J + 1);               // in flight during the reduction below and the other warps' work
+      double u0 = u0a + u0b, u1 = u1a + u1b;
 #pragma unroll
-      for (int rr = 0; rr < 16; ++rr) u = fma(tc[4 * rr], viB[rr], u);
-      u += __shfl_xor_sync(0xffffffffu, u, 1);
-      u += __shfl_xor_sync(0xffffffffu, u, 2);
-      if (rq == 0) {
-        if (I == J) s_ud[c2] = u;
-        else if (J * kTs + c2 < m) a.Pb[(size_t)I * m + J * kTs + c2] = u;
+      for (int o = 1; o < 8; o <<= 1) {
+        u0 += __shfl_xor_sync(0xffffffffu, u0, o);
+        u1 += __shfl_xor_sync(0xffffffffu, u1, o);
+      }
+      if (rgrp == 0) {
+        if (I == J) { s_ud[c0] = u0; s_ud[c0 + 1] = u1; }
+        else {
+          if (J * kTs + c0 < m) a.Pb[(size_t)I * m + J * kTs + c0] = u0;
+          if (J * kTs + c0 + 1 < m) a.Pb[(size_t)I * m + J * kTs + c0 + 1] = u1;
+        }
       }
     }
-    s_red[cg * kTs + r] = toff;
-    s_red[(4 + cg) * kTs + r] = tdiag;
+    // segment end: the row products of the 4 column groups of a warp, then of the 8 warps (fixed order)
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      tsum[rr] += __shfl_xor_sync(0xffffffffu, tsum[rr], 8);
+      tsum[rr] += __shfl_xor_sync(0xffffffffu, tsum[rr], 16);
+    }
+    if (cgrp == 0) {
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) s_red[(size_t)warp * kTs + r0 + rr] = tsum[rr];
+    }
+    if (warp == 0 && cgrp == 1) {
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) s_vI[r0 + rr] = vI[rr];
+    }
     __syncthreads();
     if (tid < kTs) {
-      const double to = s_red[tid] + s_red[kTs + tid] + s_red[2 * kTs + tid] + s_red[3 * kTs + tid];
       const bool has_diag = Jb == I + 1;
-      double td = 0.0;
-      if (has_diag) td = s_red[4 * kTs + tid] + s_red[5 * kTs + tid] + s_red[6 * kTs + tid] + s_red[7 * kTs + tid] + s_ud[tid];
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += s_red[(size_t)q * kTs + tid];
+      const double ud = has_diag ? s_ud[tid] : 0.0;
       if (R0 + tid < m) {
-        a.Pb[(size_t)Ja * m + R0 + tid] = to + td;
+        a.Pb[(size_t)Ja * m + R0 + tid] = t + ud;
         for (int J = Ja + 1; J < Jb; ++J) a.Pb[(size_t)J * m + R0 + tid] = 0.0;
       }
-      vav += s_vI[tid] * (2.0 * to + td);
+      // v'Av: off-diagonal tiles count twice (tile and its mirror), the diagonal tile once (t_diag + u_diag):
+      // 2 t + u_diag here, minus the v' t_diag every thread took off above
+      vav += s_vI[tid] * (2.0 * t + ud);
     }
+    __syncthreads();                        // s_red / s_ud / s_vI are free for the next segment
   }
+  // v'Av partial of this CTA: fixed-order reduction over all threads
+  vav = warp_sum(vav);
   __syncthreads();
-  // v'Av partial of this CTA (threads 0..63 hold the pieces): fixed-order reduction
-  if (tid < kTs) s_red[tid] = vav;
+  if (lane == 0) s_red[warp] = vav;
   __syncthreads();
-  if (warp == 0) {
-    const double t = warp_sum(s_red[lane] + s_red[32 + lane]);
-    if (lane == 0) a.S2[blockIdx.x] = t;
+  if (tid == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < kSyThreads / 32; ++q) t += s_red[q];
+    a.S2[blockIdx.x] = t;
   }
 }
 
-// ---- P3: w column of the panel, z update ------------------------------------------------------------
-__device__ void sytrd_p3(const SytrdArgs& a, int j, int jj, double* smem) {
+// ---- P31: w column of the panel and z update for column j, then (with_next) the true column j + 1 ---------
+// Every CTA first forms row j + 1 of the new panel column redundantly (w_{j+1}; v_{j+1} = 1), which is all the
+// next column needs from the other CTAs, so P3 of column j and P1 of column j + 1 share one barrier interval.
+__device__ void sytrd_p31(const SytrdArgs& a, int j, int jj, bool with_next, double* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.m, G = gridDim.x;
-  double* s_red = smem;                 // [8][32] y slices, [8][32] corr slices
-  double* s_g = smem + 2 * 8 * 32;      // fin copy (4 + 96)
-  double* s_sc = s_g + 128;
+  double* s_red = smem;                 // [8][32] x 3 slices
+  double* s_g = smem + 3 * 8 * 32;      // fin copy (4 + 96)
+  double* s_sc = s_g + 128;             // 0 v'Av, 1 y_{j+1}, 2 corr_{j+1}
+  double* s_row = s_sc + 8;             // [2][kNbMax]: W[j+1, 0..jj), V[j+1, 0..jj)
+  const int Ib0 = (j + 1) / kTs;
   for (int i = tid; i < 4 + 32 + 2 * kNbMax; i += kSyThreads) s_g[i] = __ldcg(&a.fin[i]);
+  if (tid < jj) { s_row[tid] = __ldcg(&a.W[(size_t)tid * m + j + 1]); s_row[kNbMax + tid] = __ldcg(&a.V[(size_t)tid * m + j + 1]); }
   if (warp == 0) {
     const double t = warp_strided_sum(a.S2, G, 1, lane);
     if (lane == 0) s_sc[0] = t;
+  } else if (warp == 1) {
+    const double t = warp_strided_sum(a.Pb + (size_t)Ib0 * m + j + 1, a.nt - Ib0, m, lane);
+    if (lane == 0) s_sc[1] = t;
   }
   __syncthreads();
   const double tau = s_g[0], scale = s_g[1];
   const double* g1 = s_g + 36;          // W'v
   const double* g2 = s_g + 68;          // V'v
-  double g12 = 0.0;
-  for (int q = 0; q < jj; ++q) g12 += g1[q] * g2[q];
+  double g12 = 0.0, cpiv = 0.0;
+  for (int q = 0; q < jj; ++q) {
+    g12 += g1[q] * g2[q];
+    cpiv += s_row[kNbMax + q] * g1[q] + s_row[q] * g2[q];
+  }
   const double ptv = tau * (s_sc[0] - 2.0 * g12);
-  const int Ib0 = (j + 1) / kTs;
+  const double wpiv = tau * (s_sc[1] - cpiv) - 0.5 * tau * ptv;    // w_{j+1}
   const int first_chunk = (j + 1) / kChunk;
   const int nchunk = (m + kChunk - 1) / kChunk;
   int c = first_chunk + (((int)blockIdx.x - first_chunk) % G + G) % G;
   for (; c < nchunk; c += G) {
     const int i = c * kChunk + lane;
     const bool act = i > j && i < m;
-    double ys = 0.0, cs = 0.0;
+    double ys = 0.0, cs = 0.0, us = 0.0;
     if (act) {
-      for (int t = Ib0 + warp; t < a.nt; t += 8) ys += __ldcg(&a.Pb[(size_t)t * m + i]);
-      for (int q = warp; q < jj; q += 8)
-        cs += __ldcg(&a.V[(size_t)q * m + i]) * g1[q] + __ldcg(&a.W[(size_t)q * m + i]) * g2[q];
+      for (int t0 = Ib0 + warp; t0 < a.nt; t0 += 32) {          // 4 independent loads in flight
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (t0 + 8 * u < a.nt) ? __ldcg(&a.Pb[(size_t)(t0 + 8 * u) * m + i]) : 0.0;
+        ys += (v[0] + v[1]) + (v[2] + v[3]);
+      }
+      double vq[kNbMax / 8], wq[kNbMax / 8];
+#pragma unroll
+      for (int u = 0; u < kNbMax / 8; ++u) {
+        const int q = warp + 8 * u;
+        vq[u] = q < jj ? __ldcg(&a.V[(size_t)q * m + i]) : 0.0;
+        wq[u] = q < jj ? __ldcg(&a.W[(size_t)q * m + i]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kNbMax / 8; ++u) {
+        const int q = warp + 8 * u;
+        if (q < jj) {
+          cs += vq[u] * g1[q] + wq[u] * g2[q];
+          us += vq[u] * s_row[q] + wq[u] * s_row[kNbMax + q];  // deferred update of the next column
+        }
+      }
     }
     __syncthreads();
     s_red[warp * 32 + lane] = ys;
     s_red[256 + warp * 32 + lane] = cs;
+    s_red[512 + warp * 32 + lane] = us;
     __syncthreads();
-    if (warp == 0 && act) {
-      double y = 0.0, corr = 0.0;
+    if (warp == 0) {
+      double xn = 0.0;
+      if (act) {
+        double y = 0.0, corr = 0.0, upd = 0.0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { y += s_red[k * 32 + lane]; corr += s_red[256 + k * 32 + lane]; }
-      const double vi = (i == j + 1) ? 1.0 : __ldcg(&a.x[i]) * scale;
-      const double p = tau * (y - corr);
-      a.V[(size_t)jj * m + i] = vi;
-      a.W[(size_t)jj * m + i] = p - 0.5 * tau * ptv * vi;
-      for (int r = 0; r < a.L; ++r) {
-        double* zp = &a.z[(size_t)r * m + i];
-        *zp = __ldcg(zp) - tau * s_g[4 + r] * vi;
+        for (int k = 0; k < 8; ++k) { y += s_red[k * 32 + lane]; corr += s_red[256 + k * 32 + lane]; upd += s_red[512 + k * 32 + lane]; }
+        const double vi = (i == j + 1) ? 1.0 : __ldcg(&a.x[i]) * scale;
+        const double wi = tau * (y - corr) - 0.5 * tau * ptv * vi;
+        a.V[(size_t)jj * m + i] = vi;
+        a.W[(size_t)jj * m + i] = wi;
+        for (int r = 0; r < a.L; ++r) {
+          double* zp = &a.z[(size_t)r * m + i];
+          *zp = __ldcg(zp) - tau * s_g[4 + r] * vi;
+        }
+        if (with_next) {
+          xn = __ldcg(&a.A[(size_t)(j + 1) * a.ld + i]) - upd - (vi * wpiv + wi);
+          if (i == j + 1) a.d[j + 1] = xn;
+          else a.x[i] = xn;
+        }
+      }
+      if (with_next) {
+        const double n2 = warp_sum((act && i > j + 2) ? xn * xn : 0.0);
+        if (lane == 0) a.S[(size_t)c * kSW] = n2;
       }
     }
   }
@@ -424,7 +486,7 @@ __device__ void sytrd_tail(const SytrdArgs& a) {
   }
 }
 
-constexpr size_t kSytrdSmemP2 = sizeof(double) * (2 * kTs * kTsPad + 2 * kTs + kTs + 8 * kTs + kTs + 8);
+constexpr size_t kSytrdSmemP2 = sizeof(double) * (8 * kTs + 2 * kTs + 8);
 constexpr size_t kSytrdSmemUpd = sizeof(double) * 4 * kNbMax * kTs;
 constexpr size_t kSytrdSmem = kSytrdSmemP2 > kSytrdSmemUpd ? kSytrdSmemP2 : kSytrdSmemUpd;
 
@@ -443,17 +505,17 @@ __global__ void __launch_bounds__(kSyThreads, 2) k_sytrd(SytrdArgs a) {
 #define MB_PROF(slot) if (prof) { const unsigned long long t1 = gtimer(); acc[slot] += t1 - t0; t0 = t1; }
   for (int j0 = 0; j0 < m - 2; j0 += kNbMax) {
     const int nbp = min(kNbMax, m - 2 - j0);
+    sytrd_p1(a, j0, sy_smem);
+    MB_PROF(0)
+    grid_sync(a.bar, target);
+    MB_PROF(1)
     for (int jj = 0; jj < nbp; ++jj) {
       const int j = j0 + jj;
-      sytrd_p1(a, j, jj, sy_smem);
-      MB_PROF(0)
-      grid_sync(a.bar, target);
-      MB_PROF(1)
       sytrd_p2(a, j, jj, sy_smem);
       MB_PROF(2)
       grid_sync(a.bar, target);
       MB_PROF(3)
-      sytrd_p3(a, j, jj, sy_smem);
+      sytrd_p31(a, j, jj, jj + 1 < nbp, sy_smem);
       MB_PROF(4)
       grid_sync(a.bar, target);
       MB_PROF(5)
@@ -470,17 +532,17 @@ __global__ void __launch_bounds__(kSyThreads, 2) k_sytrd(SytrdArgs a) {
 }
 
 // the same phases as separate kernels (kernel boundaries instead of the grid barrier)
-__global__ void __launch_bounds__(kSyThreads) k_sytrd_p1(SytrdArgs a, int j, int jj) {
+__global__ void __launch_bounds__(kSyThreads) k_sytrd_p1(SytrdArgs a, int j) {
   extern __shared__ __align__(16) double sy_smem[];
-  sytrd_p1(a, j, jj, sy_smem);
+  sytrd_p1(a, j, sy_smem);
 }
 __global__ void __launch_bounds__(kSyThreads, 2) k_sytrd_p2(SytrdArgs a, int j, int jj) {
   extern __shared__ __align__(16) double sy_smem[];
   sytrd_p2(a, j, jj, sy_smem);
 }
-__global__ void __launch_bounds__(kSyThreads) k_sytrd_p3(SytrdArgs a, int j, int jj) {
+__global__ void __launch_bounds__(kSyThreads) k_sytrd_p31(SytrdArgs a, int j, int jj, int with_next) {
   extern __shared__ __align__(16) double sy_smem[];
-  sytrd_p3(a, j, jj, sy_smem);
+  sytrd_p31(a, j, jj, with_next != 0, sy_smem);
 }
 __global__ void __launch_bounds__(kSyThreads) k_sytrd_update(SytrdArgs a, int jn, int nbp, int last) {
   extern __shared__ __align__(16) double sy_smem[];
@@ -547,12 +609,15 @@ __global__ void __launch_bounds__(kEigThreads) k_tri_eig(const double* __restric
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
-// Tridiagonalises the symmetric m x m matrix at A (column-major, ld; the LOWER triangle is read and destroyed),
+// Tridiagonalises the symmetric m x m matrix at A (column-major, ld = 64 ceil(m / 64) rows AND columns allocated, zero
+// outside m x m: the tile loads carry no bounds predicate; the LOWER triangle is read and destroyed),
 // transforms the L right-hand sides z (m x L, ld = m) to Q'z in place and returns the eigenvalues of T
 // (ascending) together with T itself.  All outputs are host vectors; synchronises st.
 void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L, std::vector<double>& diag,
                      std::vector<double>& off, std::vector<double>& eta, cudaStream_t st) {
   MB_REQUIRE(m >= 3, "tridiagonalisation needs m >= 3");
+  MB_REQUIRE(ld >= (m + kTs - 1) / kTs * kTs && ld % 2 == 0,
+             "tridiagonalisation: the work matrix must be zero-padded to a multiple of 64 rows and columns");
   MB_REQUIRE(L >= 0 && L <= 32, "at most 32 right-hand sides per tridiagonalisation");
   Arena& ar = ctx->arena;
   SytrdArgs a{};
@@ -573,7 +638,7 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
     MB_CUDA(cudaFuncSetAttribute(k_sytrd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSytrdSmem));
     MB_CUDA(cudaFuncSetAttribute(k_sytrd_p1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSytrdSmem));
     MB_CUDA(cudaFuncSetAttribute(k_sytrd_p2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSytrdSmem));
-    MB_CUDA(cudaFuncSetAttribute(k_sytrd_p3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSytrdSmem));
+    MB_CUDA(cudaFuncSetAttribute(k_sytrd_p31, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSytrdSmem));
     MB_CUDA(cudaFuncSetAttribute(k_sytrd_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSytrdSmem));
     attr = true;
   }
@@ -592,10 +657,10 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
   } else {
     for (int j0 = 0; j0 < m - 2; j0 += kNbMax) {
       const int nbp = std::min(kNbMax, m - 2 - j0);
+      k_sytrd_p1<<<G, kSyThreads, kSytrdSmem, st>>>(a, j0);
       for (int jj = 0; jj < nbp; ++jj) {
-        k_sytrd_p1<<<G, kSyThreads, kSytrdSmem, st>>>(a, j0 + jj, jj);
         k_sytrd_p2<<<G, kSyThreads, kSytrdSmem, st>>>(a, j0 + jj, jj);
-        k_sytrd_p3<<<G, kSyThreads, kSytrdSmem, st>>>(a, j0 + jj, jj);
+        k_sytrd_p31<<<G, kSyThreads, kSytrdSmem, st>>>(a, j0 + jj, jj, jj + 1 < nbp ? 1 : 0);
       }
       k_sytrd_update<<<G, kSyThreads, kSytrdSmem, st>>>(a, j0 + nbp, nbp, 0);
     }

@@ -729,12 +729,15 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     };
     if (ctx->eigen_impl != 1) {
       // ---- in-house: M = Q T Q' on a work copy (M itself is kept for the Cholesky below) ----------------
-      ABuf<double> d_T(ar, (size_t)m * m), d_z(ar, (size_t)m * L);
-      MB_CUDA(cudaMemcpyAsync(d_T.p, M, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToDevice, st));
+      const int ldT = (m + 63) / 64 * 64;      // zero-padded to whole 64 x 64 tiles (no bounds predicates in k_sytrd)
+      ABuf<double> d_T(ar, (size_t)ldT * ldT), d_z(ar, (size_t)m * L);
+      MB_CUDA(cudaMemsetAsync(d_T.p, 0, sizeof(double) * (size_t)ldT * ldT, st));
+      MB_CUDA(cudaMemcpy2DAsync(d_T.p, sizeof(double) * ldT, M, sizeof(double) * m, sizeof(double) * m, m,
+                                cudaMemcpyDeviceToDevice, st));
       for (int r = 0; r < L; ++r)
         MB_CUDA(cudaMemcpyAsync(d_z.p + (size_t)r * m, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
       std::vector<double> tdiag, toff;
-      sym_tridiag_eig(ctx, d_T.p, m, m, d_z.p, L, tdiag, toff, eta, st);
+      sym_tridiag_eig(ctx, d_T.p, ldT, m, d_z.p, L, tdiag, toff, eta, st);
       std::vector<double> zh((size_t)m * L);
       MB_CUDA(cudaMemcpyAsync(zh.data(), d_z.p, sizeof(double) * m * L, cudaMemcpyDeviceToHost, st));
       MB_CUDA(cudaStreamSynchronize(st));

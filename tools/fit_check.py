@@ -14,6 +14,8 @@ if mode == "phases":
     eng.set_param("sytrd_mode", 2)
 elif mode == "cusolver":
     eng.set_param("eigen_impl", 1)
+elif mode == "persistent1":
+    eng.set_param("sytrd_ctas_per_sm", 1)
 geom = synth.make_geom(8192, 8192)
 for n in sizes:
     xy, _, _ = synth.make_knots(geom, n, 300 + n)
@@ -31,7 +33,7 @@ for n in sizes:
     resid = np.max(np.abs(f - (y - sp.lam * sp.c))) / max(1.0, np.abs(y).max())
     print(f"{mode} n={n} wall={dt*1e3:.1f} ms lam={sp.lam!r} edf={sp.eff_df:.6f} eta[0]={eta[0]!r} eta[-1]={eta[-1]!r} "
           f"knot-identity={resid:.2e} sum|c|={np.abs(sp.c).sum():.6e}", flush=True)
-    if mode == "persistent":
+    if mode.startswith("persistent"):
         print("   k_sytrd phases [P1 bar P2 bar P3 bar upd bar] ms:", np.round(eng.debug_values("sytrd_phase_ms"), 2), flush=True)
     print("   kernels:", ", ".join(f"{k} {v[0]:.2f}ms x{v[1]}" for k, v in top), flush=True)
 eng.close()

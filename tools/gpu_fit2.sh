@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+TAG=${1:-fit}
+mkdir -p gpurun_out
+L=gpurun_out/${TAG}_fit.log; : > $L
+timeout -k 10 200 python tools/fit_check.py persistent 35 200 1100 5000 >> $L 2>&1; echo "fit_check rc=$?" | tee -a $L
+cat $L
+timeout -k 10 300 python -m pytest tests/test_tps_gpu.py -m gpu -x -q -k "fit" > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/${TAG}_pytest.log
