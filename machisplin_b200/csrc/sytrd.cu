@@ -156,20 +156,48 @@ __device__ void sytrd_p2(const SytrdArgs& a, int j, int jj, double* smem) {
   double* s_red = smem;                               // [8][64]: row products per warp
   double* s_ud = s_red + 8 * kTs;                    // 64: transposed product of the diagonal tile
   double* s_vI = s_ud + kTs;                          // 64
-  double* s_sc = s_vI + kTs;                          // scalars
   const int first_chunk = j / kChunk;
   const int nchunk = (m + kChunk - 1) / kChunk;
-  if (warp == 0) {
-    const double n2 = warp_strided_sum(a.S + (size_t)first_chunk * kSW, nchunk - first_chunk, kSW, lane);
-    if (lane == 0) s_sc[0] = n2;
+  const int Ib0 = (j + 1) / kTs;
+  const int na = a.nt - Ib0;
+  const int nseg = segment_count(na);
+  const int rgrp = lane & 7, cgrp = lane >> 3;
+  const int r0 = rgrp * 8;                            // rows r0 .. r0 + 7 of the tile
+  const int c0 = warp * 8 + cgrp * 2;                 // columns c0, c0 + 1 of the tile
+  // Everything that does not depend on the Householder scalars is requested first: the first tile of this CTA's
+  // first segment and the raw x entries it needs travel while |x|^2 is being reduced.
+  double pre[16], pvj[2], vI[8];
+  auto load_tile = [&](int I, int J) {
+    const double* base = a.A + (size_t)(J * kTs + c0) * a.ld + I * kTs + r0;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const double2 v2 = __ldcg(reinterpret_cast<const double2*>(base + (size_t)cc * a.ld) + h);
+        pre[cc * 8 + 2 * h] = v2.x;
+        pre[cc * 8 + 2 * h + 1] = v2.y;
+      }
+  };
+  auto xraw = [&](int i) -> double { return (i > j + 1 && i < m) ? __ldcg(&a.x[i]) : 0.0; };
+  int sidx = blockIdx.x, Ii = 0, seg = 0;
+  if (sidx < nseg) {
+    segment_of(sidx, Ii, seg);
+    load_tile(Ib0 + Ii, Ib0 + seg * kSeg);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) vI[rr] = xraw((Ib0 + Ii) * kTs + r0 + rr);
+    pvj[0] = xraw((Ib0 + seg * kSeg) * kTs + c0);
+    pvj[1] = xraw((Ib0 + seg * kSeg) * kTs + c0 + 1);
   }
-  __syncthreads();
   const double alpha = __ldcg(&a.x[j + 1]);
-  const Scal sc = householder_scalars(alpha, s_sc[0]);
+  // every warp reduces the |x|^2 partials itself (same order, same result): no barrier on the critical path
+  const double xn2 = warp_strided_sum(a.S + (size_t)first_chunk * kSW, nchunk - first_chunk, kSW, lane);
+  const Scal sc = householder_scalars(alpha, xn2);
   if (blockIdx.x == 0 && tid == 0) {
     a.fin[0] = sc.tau; a.fin[1] = sc.scale; a.fin[2] = sc.beta; a.fin[3] = sc.alpha;
     a.e[j] = sc.beta;
   }
+  // v_i from the raw x entry (0 outside (j + 1, m)); the pivot row carries v = 1, rows <= j and >= m stay 0
+  auto vfix = [&](double raw, int i) -> double { return i == j + 1 ? 1.0 : raw * sc.scale; };
   // dots for P31, one per CTA (from the back of the grid: those CTAs own the fewest segments), straight from x:
   // v'z_r = z[j+1] + scale sum_{i>j+1} x_i z_i ;  g1 = W'v, g2 = V'v likewise (the pivot row enters with v = 1)
   for (int k = G - 1 - (int)blockIdx.x; k < a.L + 2 * jj; k += G) {
@@ -200,46 +228,28 @@ __device__ void sytrd_p2(const SytrdArgs& a, int j, int jj, double* smem) {
       a.fin[slot] = __ldcg(&colp[j + 1]) + sc.scale * t;
     }
   }
-  const int Ib0 = (j + 1) / kTs;
-  const int na = a.nt - Ib0;
-  const int nseg = segment_count(na);
-  const int rgrp = lane & 7, cgrp = lane >> 3;
-  const int r0 = rgrp * 8;                            // rows r0 .. r0 + 7 of the tile
-  const int c0 = warp * 8 + cgrp * 2;                 // columns c0, c0 + 1 of the tile
-  auto vval = [&](int i) -> double {                  // v_i: 0 outside (j, m), 1 at the pivot row
-    if (i <= j || i >= m) return 0.0;
-    return i == j + 1 ? 1.0 : __ldcg(&a.x[i]) * sc.scale;
-  };
   double vav = 0.0;
-  for (int sidx = blockIdx.x; sidx < nseg; sidx += G) {
-    int Ii, seg;
-    segment_of(sidx, Ii, seg);
+  bool first = true;
+  for (; sidx < nseg; sidx += G) {
+    if (!first) segment_of(sidx, Ii, seg);
     const int I = Ib0 + Ii;
     const int Ja = Ib0 + seg * kSeg, Jb = min(I + 1, Ja + kSeg);     // tile columns [Ja, Jb)
     const int R0 = I * kTs;
-    double vI[8];
+    if (!first) {
+      load_tile(I, Ja);
 #pragma unroll
-    for (int rr = 0; rr < 8; ++rr) vI[rr] = vval(R0 + r0 + rr);
-    double pre[16], pvj[2];
-    auto load_tile = [&](int J) {
-      const double* base = a.A + (size_t)(J * kTs + c0) * a.ld + R0 + r0;
+      for (int rr = 0; rr < 8; ++rr) vI[rr] = xraw(R0 + r0 + rr);
+      pvj[0] = xraw(Ja * kTs + c0);
+      pvj[1] = xraw(Ja * kTs + c0 + 1);
+    }
+    first = false;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const double2 v2 = __ldcg(reinterpret_cast<const double2*>(base + (size_t)cc * a.ld) + h);
-          pre[cc * 8 + 2 * h] = v2.x;
-          pre[cc * 8 + 2 * h + 1] = v2.y;
-        }
-      pvj[0] = vval(J * kTs + c0);
-      pvj[1] = vval(J * kTs + c0 + 1);
-    };
-    load_tile(Ja);
+    for (int rr = 0; rr < 8; ++rr) vI[rr] = vfix(vI[rr], R0 + r0 + rr);
     double tsum[8];                                    // row products of the whole segment (off-diagonal + diagonal tile)
 #pragma unroll
     for (int rr = 0; rr < 8; ++rr) tsum[rr] = 0.0;
     for (int J = Ja; J < Jb; ++J) {
-      const double vj0 = pvj[0], vj1 = pvj[1];
+      const double vj0 = vfix(pvj[0], J * kTs + c0), vj1 = vfix(pvj[1], J * kTs + c0 + 1);
       double u0a = 0.0, u0b = 0.0, u1a = 0.0, u1b = 0.0;
       if (I != J) {
 #pragma unroll
@@ -262,7 +272,11 @@ __device__ void sytrd_p2(const SytrdArgs& a, int j, int jj, double* smem) {
           u1a = fma(r > c0 + 1 ? a1 : 0.0, vI[rr], u1a);
         }
       }
-      if (J + 1 < Jb) load_tile(J + 1);               // in flight during the reduction below and the other warps' work
+      if (J + 1 < Jb) {                               // in flight during the reduction below and the other warps' work
+        load_tile(I, J + 1);
+        pvj[0] = xraw((J + 1) * kTs + c0);
+        pvj[1] = xraw((J + 1) * kTs + c0 + 1);
+      }
       double u0 = u0a + u0b, u1 = u1a + u1b;
 #pragma unroll
       for (int o = 1; o < 8; o <<= 1) {
@@ -327,62 +341,74 @@ __device__ void sytrd_p2(const SytrdArgs& a, int j, int jj, double* smem) {
 __device__ void sytrd_p31(const SytrdArgs& a, int j, int jj, bool with_next, double* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.m, G = gridDim.x;
-  double* s_red = smem;                 // [8][32] x 3 slices
-  double* s_g = smem + 3 * 8 * 32;      // fin copy (4 + 96)
-  double* s_sc = s_g + 128;             // 0 v'Av, 1 y_{j+1}, 2 corr_{j+1}
-  double* s_row = s_sc + 8;             // [2][kNbMax]: W[j+1, 0..jj), V[j+1, 0..jj)
+  double* s_red = smem;                 // [3][8][32]: y, corr, next-column update slices
   const int Ib0 = (j + 1) / kTs;
-  for (int i = tid; i < 4 + 32 + 2 * kNbMax; i += kSyThreads) s_g[i] = __ldcg(&a.fin[i]);
-  if (tid < jj) { s_row[tid] = __ldcg(&a.W[(size_t)tid * m + j + 1]); s_row[kNbMax + tid] = __ldcg(&a.V[(size_t)tid * m + j + 1]); }
-  if (warp == 0) {
-    const double t = warp_strided_sum(a.S2, G, 1, lane);
-    if (lane == 0) s_sc[0] = t;
-  } else if (warp == 1) {
-    const double t = warp_strided_sum(a.Pb + (size_t)Ib0 * m + j + 1, a.nt - Ib0, m, lane);
-    if (lane == 0) s_sc[1] = t;
-  }
-  __syncthreads();
-  const double tau = s_g[0], scale = s_g[1];
-  const double* g1 = s_g + 36;          // W'v
-  const double* g2 = s_g + 68;          // V'v
-  double g12 = 0.0, cpiv = 0.0;
-  for (int q = 0; q < jj; ++q) {
-    g12 += g1[q] * g2[q];
-    cpiv += s_row[kNbMax + q] * g1[q] + s_row[q] * g2[q];
-  }
-  const double ptv = tau * (s_sc[0] - 2.0 * g12);
-  const double wpiv = tau * (s_sc[1] - cpiv) - 0.5 * tau * ptv;    // w_{j+1}
   const int first_chunk = (j + 1) / kChunk;
   const int nchunk = (m + kChunk - 1) / kChunk;
   int c = first_chunk + (((int)blockIdx.x - first_chunk) % G + G) % G;
+  if (c >= nchunk) return;              // no rows of this CTA left: nothing to do in this phase
+  // per-warp constants of the panel: g1 = W'v, g2 = V'v and row j + 1 of W, V for q = warp + 8 u
+  double g1q[kNbMax / 8], g2q[kNbMax / 8], rwq[kNbMax / 8], rvq[kNbMax / 8];
+#pragma unroll
+  for (int u = 0; u < kNbMax / 8; ++u) {
+    const int q = warp + 8 * u;
+    const bool on = q < jj;
+    g1q[u] = on ? __ldcg(&a.fin[36 + q]) : 0.0;
+    g2q[u] = on ? __ldcg(&a.fin[68 + q]) : 0.0;
+    rwq[u] = on ? __ldcg(&a.W[(size_t)q * m + j + 1]) : 0.0;
+    rvq[u] = on ? __ldcg(&a.V[(size_t)q * m + j + 1]) : 0.0;
+  }
+  // warp 0 owns the scalars: tau, scale, p'v and w_{j+1}; lane q carries column q of the panel
+  double tau = 0.0, scale = 0.0, ptv = 0.0, wpiv = 0.0;
+  bool have_scalars = false;
   for (; c < nchunk; c += G) {
     const int i = c * kChunk + lane;
     const bool act = i > j && i < m;
-    double ys = 0.0, cs = 0.0, us = 0.0;
-    if (act) {
-      for (int t0 = Ib0 + warp; t0 < a.nt; t0 += 32) {          // 4 independent loads in flight
-        double v[4];
+    // ---- requests first --------------------------------------------------------------------------------
+    double pb[12];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (t0 + 8 * u < a.nt) ? __ldcg(&a.Pb[(size_t)(t0 + 8 * u) * m + i]) : 0.0;
-        ys += (v[0] + v[1]) + (v[2] + v[3]);
-      }
-      double vq[kNbMax / 8], wq[kNbMax / 8];
-#pragma unroll
-      for (int u = 0; u < kNbMax / 8; ++u) {
-        const int q = warp + 8 * u;
-        vq[u] = q < jj ? __ldcg(&a.V[(size_t)q * m + i]) : 0.0;
-        wq[u] = q < jj ? __ldcg(&a.W[(size_t)q * m + i]) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < kNbMax / 8; ++u) {
-        const int q = warp + 8 * u;
-        if (q < jj) {
-          cs += vq[u] * g1[q] + wq[u] * g2[q];
-          us += vq[u] * s_row[q] + wq[u] * s_row[kNbMax + q];  // deferred update of the next column
-        }
-      }
+    for (int u = 0; u < 12; ++u) {
+      const int t = Ib0 + warp + 8 * u;
+      pb[u] = (act && t < a.nt) ? __ldcg(&a.Pb[(size_t)t * m + i]) : 0.0;
     }
-    __syncthreads();
+    double vq[kNbMax / 8], wq[kNbMax / 8];
+#pragma unroll
+    for (int u = 0; u < kNbMax / 8; ++u) {
+      const int q = warp + 8 * u;
+      vq[u] = (act && q < jj) ? __ldcg(&a.V[(size_t)q * m + i]) : 0.0;
+      wq[u] = (act && q < jj) ? __ldcg(&a.W[(size_t)q * m + i]) : 0.0;
+    }
+    double xi = 0.0, anext = 0.0;
+    if (warp == 0 && act) {
+      xi = __ldcg(&a.x[i]);
+      if (with_next) anext = __ldcg(&a.A[(size_t)(j + 1) * a.ld + i]);
+    }
+    if (warp == 0 && !have_scalars) {
+      const double s2 = warp_strided_sum(a.S2, G, 1, lane);
+      const double ypiv = warp_strided_sum(a.Pb + (size_t)Ib0 * m + j + 1, a.nt - Ib0, m, lane);
+      tau = __ldcg(&a.fin[0]);
+      scale = __ldcg(&a.fin[1]);
+      const bool on = lane < jj;
+      const double g1 = on ? __ldcg(&a.fin[36 + lane]) : 0.0, g2 = on ? __ldcg(&a.fin[68 + lane]) : 0.0;
+      const double rw = on ? __ldcg(&a.W[(size_t)lane * m + j + 1]) : 0.0, rv = on ? __ldcg(&a.V[(size_t)lane * m + j + 1]) : 0.0;
+      const double g12 = warp_sum(g1 * g2);
+      const double cpiv = warp_sum(rv * g1 + rw * g2);
+      ptv = tau * (s2 - 2.0 * g12);
+      wpiv = tau * (ypiv - cpiv) - 0.5 * tau * ptv;      // w_{j+1}
+      have_scalars = true;
+    }
+    // ---- slices ----------------------------------------------------------------------------------------
+    double ys = 0.0, cs = 0.0, us = 0.0;
+#pragma unroll
+    for (int u = 0; u < 12; u += 4) ys += (pb[u] + pb[u + 1]) + (pb[u + 2] + pb[u + 3]);
+    if (Ib0 + warp + 96 < a.nt)                                 // more than 96 tile rows (m > 6144): remaining slots
+      for (int t = Ib0 + warp + 96; t < a.nt; t += 8) ys += act ? __ldcg(&a.Pb[(size_t)t * m + i]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < kNbMax / 8; ++u) {
+      cs += vq[u] * g1q[u] + wq[u] * g2q[u];
+      us += vq[u] * rwq[u] + wq[u] * rvq[u];                    // deferred update of the next column
+    }
+    __syncthreads();                                            // previous chunk done with s_red
     s_red[warp * 32 + lane] = ys;
     s_red[256 + warp * 32 + lane] = cs;
     s_red[512 + warp * 32 + lane] = us;
@@ -393,16 +419,16 @@ __device__ void sytrd_p31(const SytrdArgs& a, int j, int jj, bool with_next, dou
         double y = 0.0, corr = 0.0, upd = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { y += s_red[k * 32 + lane]; corr += s_red[256 + k * 32 + lane]; upd += s_red[512 + k * 32 + lane]; }
-        const double vi = (i == j + 1) ? 1.0 : __ldcg(&a.x[i]) * scale;
+        const double vi = (i == j + 1) ? 1.0 : xi * scale;
         const double wi = tau * (y - corr) - 0.5 * tau * ptv * vi;
         a.V[(size_t)jj * m + i] = vi;
         a.W[(size_t)jj * m + i] = wi;
         for (int r = 0; r < a.L; ++r) {
           double* zp = &a.z[(size_t)r * m + i];
-          *zp = __ldcg(zp) - tau * s_g[4 + r] * vi;
+          *zp = __ldcg(zp) - tau * __ldcg(&a.fin[4 + r]) * vi;
         }
         if (with_next) {
-          xn = __ldcg(&a.A[(size_t)(j + 1) * a.ld + i]) - upd - (vi * wpiv + wi);
+          xn = anext - upd - (vi * wpiv + wi);
           if (i == j + 1) a.d[j + 1] = xn;
           else a.x[i] = xn;
         }

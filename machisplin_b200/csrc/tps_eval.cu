@@ -467,8 +467,15 @@ __host__ __device__ inline int leaf_stage_bytes(int P, int bh, bool acc) {
   return (P * P * 8 + 256 + (acc ? bh * 256 : 0) + 127) / 128 * 128;
 }
 
+// r2 is clamped to >= 1e-20 (a normal float32): the plain MUFU.LG2 without the denormal pre-scaling of __log2f
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int P, bool kAcc>
-__global__ void __launch_bounds__(kLeafThreads) k_leaf_stream(
+__global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? (kAcc ? 4 : 5) : 3) k_leaf_stream(
     Lattice lat, LevelInfo leaf, mb_window w, const double* __restrict__ coef, const NearBlk* __restrict__ near,
     const float4* __restrict__ near_over, const unsigned long long* __restrict__ est_bits, double mixed_threshold,
     AccFuse fz, double* __restrict__ out, int64_t stride) {
@@ -516,17 +523,25 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf_stream(
   };
   if (warp == 0)
     for (int i = 0; i < min(kLeafStages, nmine); ++i) issue();
+  // the padding entries of the G rows (k >= P) meet T = 0 in the packed FMA: they must be finite
+  for (int i = tid; i < 2 * bh * GFS; i += kLeafThreads) s_Gf[i] = 0.f;
+  __syncthreads();
 
   // lane = (half, l): half selects one row of a row pair, l the column pair (l, 31 - l): tx_{31-l} = -tx_l, so the
-  // even and the odd part of the expansion serve both columns
+  // even and the odd part of the expansion serve both columns.  (odd, even) terms are packed: one FFMA2 each.
   const int half = lane >> 4, l = lane & 15;
-  float Txf[P];
+  constexpr int NP = P / 2;                // pairs (T_1,T_2), (T_3,T_4), ... ; the last pair is (T_{P-1}, 0)
+  float2 Tp[NP];
   {
+    float T[P + 1];
     const float tx = (2.0f * l + 1.0f) / 32.0f - 1.0f;   // exact in float32
-    Txf[0] = 1.0f;
-    Txf[1] = tx;
+    T[0] = 1.0f;
+    T[1] = tx;
 #pragma unroll
-    for (int k = 2; k < P; ++k) Txf[k] = 2.0f * tx * Txf[k - 1] - Txf[k - 2];
+    for (int k = 2; k < P; ++k) T[k] = 2.0f * tx * T[k - 1] - T[k - 2];
+    T[P] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) Tp[q] = make_float2(T[2 * q + 1], T[2 * q + 2]);
   }
   const float cxa = (float)(lat.hx * ((l + 0.5) / 32.0)), cxb = (float)(lat.hx * ((31 - l + 0.5) / 32.0));
   const double hyb = lat.hy / bh, inv_bh = 1.0 / bh;
@@ -536,35 +551,75 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf_stream(
     const double2* A2 = reinterpret_cast<const double2*>(leaf_smem + (i % kLeafStages) * stage_bytes);
     double* g0buf = s_G0 + (i & 1) * bh;
     float* gfbuf = s_Gf + (i & 1) * bh * GFS;
-    for (int o = tid; o < npair * (P / 2); o += kLeafThreads) {
-      const int lr = o / (P / 2), kp = o % (P / 2);
+    const double* A1 = reinterpret_cast<const double*>(A2);
+    for (int o = tid; o < npair * P; o += kLeafThreads) {      // item = (row pair lr / bh - 1 - lr, column k)
+      const int lr = o / P, k = o % P;
       const double ty = (2.0 * lr + 1.0) * inv_bh - 1.0;
       double t0 = 1.0, t1 = ty;
-      const double2 a0 = A2[kp], a1 = A2[(P / 2) + kp];
-      double ea = a0.x, eb = a0.y, oa = t1 * a1.x, ob = t1 * a1.y;   // even / odd part in ty, columns 2 kp and 2 kp + 1
+      double ev = A1[k], od = t1 * A1[P + k];                  // even / odd part in ty
 #pragma unroll
       for (int j = 2; j < P; ++j) {
         const double t2 = 2.0 * ty * t1 - t0;
-        const double2 a = A2[j * (P / 2) + kp];
-        if (j & 1) { oa = fma(t2, a.x, oa); ob = fma(t2, a.y, ob); }
-        else { ea = fma(t2, a.x, ea); eb = fma(t2, a.y, eb); }
+        if (j & 1) od = fma(t2, A1[j * P + k], od);
+        else ev = fma(t2, A1[j * P + k], ev);
         t0 = t1; t1 = t2;
       }
       const int lm = bh - 1 - lr;
-      if (kp == 0) {
-        g0buf[lr] = ea + oa; g0buf[lm] = ea - oa;
-        gfbuf[lr * GFS] = (float)(eb + ob); gfbuf[lm * GFS] = (float)(eb - ob);
+      if (k == 0) { g0buf[lr] = ev + od; g0buf[lm] = ev - od; }
+      else { gfbuf[lr * GFS + k - 1] = (float)(ev + od); gfbuf[lm * GFS + k - 1] = (float)(ev - od); }
+    }
+  };
+
+  // one row of the box for this lane's two columns: far field from G, near field from the near list
+  auto row_pass = [&](int lr, const float* gfbuf, const double* g0buf, const NearBlk* nb, int cnt, const double* accT,
+                      double* dst, bool okA, bool okB) {
+    const float4* g4 = reinterpret_cast<const float4*>(gfbuf + lr * GFS);
+    float2 eo = make_float2(0.f, 0.f);                  // (odd, even) parts
+#pragma unroll
+    for (int q = 0; q < GFS / 4; ++q) {
+      const float4 g = g4[q];
+      if (2 * q < NP) eo = __ffma2_rn(make_float2(g.x, g.y), Tp[2 * q], eo);
+      if (2 * q + 1 < NP) eo = __ffma2_rn(make_float2(g.z, g.w), Tp[2 * q + 1], eo);
+    }
+    float fa = eo.y + eo.x, fb = eo.y - eo.x;
+    if (cnt > 0) {
+      const float cyl = (float)(hyb * (lr + 0.5));
+      auto pair_term = [&](const float4 kn) {
+        const float dy = cyl - kn.y, dy2 = dy * dy;
+        const float dxa = cxa - kn.x, dxb = cxb - kn.x;
+        const float r2a = fmaxf(fmaf(dxa, dxa, dy2), 1e-20f), r2b = fmaxf(fmaf(dxb, dxb, dy2), 1e-20f);
+        fa = fmaf(kn.z * r2a, lg2_fast(r2a), fa);
+        fb = fmaf(kn.z * r2b, lg2_fast(r2b), fb);
+      };
+      if (cnt <= kNearInline) {
+#pragma unroll 1
+        for (int q = 0; q < cnt; ++q) pair_term(nb->e[q]);
       } else {
-        gfbuf[lr * GFS + 2 * kp - 1] = (float)(ea + oa); gfbuf[lm * GFS + 2 * kp - 1] = (float)(ea - oa);
-        gfbuf[lr * GFS + 2 * kp] = (float)(eb + ob); gfbuf[lm * GFS + 2 * kp] = (float)(eb - ob);
+        const float4* src = near_over + nb->off;
+#pragma unroll 1
+        for (int q = 0; q < cnt; ++q) pair_term(__ldg(&src[q]));
       }
     }
+    const double g0 = g0buf[lr];
+    double va = g0 + (double)fa, vb = g0 + (double)fb;
+    if (kAcc) {
+      va = fma(accT[lr * 32 + l], fz.inv_w, va);
+      vb = fma(accT[lr * 32 + 31 - l], fz.inv_w, vb);
+    }
+    if (okA) __stcs(dst, va);
+    if (okB) __stcs(dst + (31 - 2 * l), vb);
   };
 
   mbar_wait(&s_full[0], 0);
   collapse(0);
   __syncthreads();
-  int cbi = blockIdx.x % lat.nbx, cbj = blockIdx.x / lat.nbx;      // consumer cursor (all threads)
+  // consumer cursor: lattice position of the current box and the address of this lane's first cell in it
+  int cbi = blockIdx.x % lat.nbx, cbj = blockIdx.x / lat.nbx;
+  const int lr0 = 2 * warp + half;
+  double* dst0 = out + ((int64_t)cbj * bh + lr0) * stride + (cbi * 32 + l);
+  const int64_t box_step = (int64_t)dJ * bh * stride + dI * 32, wrap_step = (int64_t)bh * stride - (int64_t)lat.nbx * 32;
+  const int64_t dstep = 16 * stride;
+  const int wcols = w.c1 - w.c0, wrows = w.r1 - w.r0;
   for (int i = 0; i < nmine; ++i) {
     if (i + 1 < nmine) {
       mbar_wait(&s_full[(i + 1) % kLeafStages], ((i + 1) / kLeafStages) & 1);
@@ -576,51 +631,20 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf_stream(
       const NearBlk* nb = reinterpret_cast<const NearBlk*>(sp + P * P * 8);
       const double* accT = reinterpret_cast<const double*>(sp + kRecBytes);
       const int cnt = nb->cnt;
-      const int colA = w.c0 + cbi * 32 + l, colB = colA + 31 - 2 * l;
-      const bool okA = colA < w.c1, okB = colB < w.c1;
-      const int row_base = w.r0 + cbj * bh;
-      const int rows_here = min(bh, w.r1 - row_base);
       const double* g0buf = s_G0 + (i & 1) * bh;
       const float* gfbuf = s_Gf + (i & 1) * bh * GFS;
-      int lr = 2 * warp + half;
-      double* dst = out + (int64_t)(row_base - w.r0 + lr) * stride + (colA - w.c0);
-      const int64_t dstep = 16 * stride;
-      for (; lr < rows_here; lr += 16, dst += dstep) {
-        const float4* g4 = reinterpret_cast<const float4*>(gfbuf + lr * GFS);
-        float ev = 0.f, od = 0.f;
-#pragma unroll
-        for (int q = 0; q < GFS / 4; ++q) {
-          const float4 g = g4[q];
-          if (4 * q + 1 < P) od = fmaf(g.x, Txf[4 * q + 1], od);
-          if (4 * q + 2 < P) ev = fmaf(g.y, Txf[4 * q + 2], ev);
-          if (4 * q + 3 < P) od = fmaf(g.z, Txf[4 * q + 3], od);
-          if (4 * q + 4 < P) ev = fmaf(g.w, Txf[4 * q + 4], ev);
-        }
-        float fa = ev + od, fb = ev - od;
-        if (cnt > 0) {
-          const float cyl = (float)(hyb * (lr + 0.5));
-          const float4* src = cnt <= kNearInline ? nb->e : near_over + nb->off;   // shared or global, generic loads
-          for (int q = 0; q < cnt; ++q) {
-            const float4 kn = src[q];
-            const float dy = cyl - kn.y, dy2 = dy * dy;
-            const float dxa = cxa - kn.x, dxb = cxb - kn.x;
-            const float r2a = fmaxf(fmaf(dxa, dxa, dy2), 1e-20f), r2b = fmaxf(fmaf(dxb, dxb, dy2), 1e-20f);
-            fa = fmaf(kn.z * r2a, __log2f(r2a), fa);
-            fb = fmaf(kn.z * r2b, __log2f(r2b), fb);
-          }
-        }
-        const double g0 = g0buf[lr];
-        double va = g0 + (double)fa, vb = g0 + (double)fb;
-        if (kAcc) {
-          va = fma(accT[lr * 32 + l], fz.inv_w, va);
-          vb = fma(accT[lr * 32 + 31 - l], fz.inv_w, vb);
-        }
-        if (okA) __stcs(dst, va);
-        if (okB) __stcs(dst + (31 - 2 * l), vb);
+      const int rows_here = min(bh, wrows - cbj * bh);
+      if (bh == 32 && rows_here == 32 && cbi * 32 + 32 <= wcols) {   // full box: no predicates
+        row_pass(lr0, gfbuf, g0buf, nb, cnt, accT, dst0, true, true);
+        row_pass(lr0 + 16, gfbuf, g0buf, nb, cnt, accT, dst0 + dstep, true, true);
+      } else {
+        const bool okA = cbi * 32 + l < wcols, okB = cbi * 32 + 31 - l < wcols;
+        double* dst = dst0;
+        for (int lr = lr0; lr < rows_here; lr += 16, dst += dstep) row_pass(lr, gfbuf, g0buf, nb, cnt, accT, dst, okA, okB);
       }
     }
-    cbi += dI; cbj += dJ;
-    if (cbi >= lat.nbx) { cbi -= lat.nbx; ++cbj; }
+    cbi += dI; cbj += dJ; dst0 += box_step;
+    if (cbi >= lat.nbx) { cbi -= lat.nbx; ++cbj; dst0 += wrap_step; }
     __syncthreads();   // stage i % kLeafStages and G buffer i & 1 are free again
     if (warp == 0 && ibox < nmine) issue();
   }
