@@ -93,9 +93,11 @@ def build_inputs(cfg, rank):
     return geom, xy, krow, kcol, resid, models, kept, w, wt
 
 
-def device_covariates(geom, C, device, seed=99):
-    """Same generator as synth.covariate_planes, evaluated on the GPU with torch (plumbing only)."""
+def device_covariates(geom, C, device, seed=99, disc_geom=None):
+    """Same generator as synth.covariate_planes, evaluated on the GPU with torch (plumbing only).  disc_geom: the
+    grid whose extent places the NaN discs (the full raster when geom is one tile of it)."""
     import torch
+    dg = disc_geom or geom
     x = torch.tensor(geom.xmin, dtype=torch.float64, device=device) + \
         (torch.arange(geom.ncol, device=device, dtype=torch.float64) + 0.5) * geom.rx
     y = torch.tensor(geom.ymax, dtype=torch.float64, device=device) - \
@@ -113,9 +115,9 @@ def device_covariates(geom, C, device, seed=99):
             out[k, r0:r1] = (100.0 * (k + 1) + 50.0 * acc).to(torch.float32)
     rng = np.random.default_rng(seed + 1000)
     ndisc, nan_frac = 8, 0.02
-    rad = np.sqrt(nan_frac * (geom.xmax - geom.xmin) * (geom.ymax - geom.ymin) / (ndisc * np.pi))
+    rad = np.sqrt(nan_frac * (dg.xmax - dg.xmin) * (dg.ymax - dg.ymin) / (ndisc * np.pi))
     for _ in range(ndisc):
-        cx, cy = rng.uniform(geom.xmin, geom.xmax), rng.uniform(geom.ymin, geom.ymax)
+        cx, cy = rng.uniform(dg.xmin, dg.xmax), rng.uniform(dg.ymin, dg.ymax)
         for r0 in range(0, geom.nrow, blk):
             r1 = min(geom.nrow, r0 + blk)
             m = (x[None, :] - cx) ** 2 + (y[r0:r1, None] - cy) ** 2 < rad * rad
@@ -449,10 +451,126 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# config 4: one raster tiled across the GPUs with machisplin.tiles.* (strong scaling)
+# ------------------------------------------------------------------------------------------------
+def run_tiled(args):
+    """BASELINE config 4: machisplin.tiles.create cuts the raster into world-size tiles with a feather halo
+    (V73:1165-1256); every rank runs mltps parts 2-5 on its tile (internal 1500-px tiling, V73:649-895); the
+    tiles travel to rank 0 over NCCL and machisplin.tiles.merge blends the seams there (V73:1392-1548); the
+    Gram of the cross-validation residuals is all-reduced (V73:329-333)."""
+    import torch
+    import torch.distributed as dist
+    import machisplin_b200 as mb
+    from machisplin_b200 import synth, tiles as mtiles, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = workload(args)
+    geom = synth.make_geom(cfg["nrow"], cfg["ncol"])
+    xy, krow, kcol = synth.make_knots(geom, cfg["knots"], cfg["seed"])
+    resid = synth.residual_field(xy, cfg["seed"])
+    nC, nR = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
+    ts = mtiles.tiles_create(geom, xy, nC, nR, feather_d=50)
+    tile = ts.tiles[rank]
+    tg, pts = tile.geom, tile.points
+    kept, C = cfg["kept"], cfg["C"]
+    cache = f"/tmp/mb_models_{cfg['nrow']}x{cfg['ncol']}_{cfg['knots']}_{C}_{kept}_{cfg['seed']}.npz"
+    if os.path.exists(cache):
+        models = np.load(cache, allow_pickle=True)["models"].item()
+    else:
+        models = synth.make_models(geom, C, min(cfg["knots"], 5000), cfg["seed"], kept=kept)
+        if rank == 0:
+            try:
+                np.savez(cache, models=np.array(models, dtype=object))
+            except Exception:
+                pass
+    kept, w, wt = synth.ensemble_weights(kept)
+    eng = mb.Engine(local)
+    for kv in args.param:
+        name, val = kv.split("=")
+        eng.set_param(name, int(val))
+    cov = device_covariates(tg, C, dev, disc_geom=geom)
+    ens = eng.ensemble_create(tg, models, kept, w, wt, C + 2)
+    out_tile = torch.empty((tg.nrow, tg.ncol), dtype=torch.float64, device=dev)
+    out_full = torch.empty((geom.nrow, geom.ncol), dtype=torch.float64, device=dev) if rank == 0 else None
+    shapes = [(t.geom.nrow, t.geom.ncol) for t in ts.tiles]
+    wins = [t.win for t in ts.tiles]
+    Rcv = np.random.default_rng(5).standard_normal((cfg["knots"], 6))[parallel.shard_rows(cfg["knots"], world, rank)]
+    stream = torch.cuda.current_stream().cuda_stream
+    tile_px = 1500
+
+    def step():
+        G = eng.gram(Rcv)
+        if world > 1:
+            g = torch.from_numpy(G).to(dev)
+            dist.all_reduce(g)
+        eng.mltps_predict_dev(tg, ens, cov.data_ptr(), C, xy[pts], resid[pts], out_tile.data_ptr(), lam=args.lam,
+                              tile_px=tile_px, stream=stream)
+        tl = parallel.gather_tiles_device(out_tile, shapes, dst=0)
+        if rank == 0:
+            eng.tiles_merge_dev(geom, wins, [t.data_ptr() for t in tl], nC, nR, out_full.data_ptr(), stream=stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.timing(True)
+    eng.timing_collect()
+    l0 = eng.launches
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = eng.launches - l0
+    ktimes = eng.timing_collect()
+    eng.timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        cells = geom.nrow * geom.ncol
+        tot = sum(v[0] for v in ktimes.values()) or 1.0
+        kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps, "share": v[0] / tot}
+                for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:12]}
+        conf = workload_config(cfg, args, f"mltps tiling {tile_px} px inside {nC}x{nR} machisplin.tiles")
+        conf["parallelism"] = f"tiles{nC}x{nR}"
+        nan_frac = float(torch.isnan(out_full).float().mean().item())
+        line = {"metric": METRIC, "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
+                "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "kernels_rank0": kern,
+                "roofline": None, "cpu_baseline": None, "na_fraction": nan_frac,
+                "collectives": {"gram": "all_reduce 36 doubles", "tile_gather_bytes": int(sum(a * b for a, b in shapes[1:]) * 8)}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c4":
+        run_tiled(args)
     else:
         run_b200(args)
 

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(((P * P + 31) / 32) * 32) k_far_transform(
 // -----------------------------------------------------------------------------------------
 // Leaf preparation (one warp per leaf box):
 //  (1) accuracy estimate of the mixed-precision leaf path, max over boxes:
-//        far : the k >= 1 columns of the expansion are evaluated in float32 -> (P + 2) 2^-24 sum_{(j,k) != (0,0)} |A_jk|
+//        far : the k >= 1 columns of the expansion are collapsed AND evaluated in float32 -> 2 (P + 2) 2^-24 sum_{(j,k) != (0,0)} |A_jk|
 //        near: pair terms in float32 with box-local coordinates      -> 4 2^-24 phi(r_max) sum_{3x3} |c_i E/2|
 //      The leaf kernels compare the estimate with their threshold on the device (no host round trip):
 //      k_leaf_stream runs when the mixed path is accurate enough, k_leaf_f64 otherwise.
@@ -354,19 +354,40 @@ struct __align__(16) NearBlk {
   float4 e[kNearInline];
 };
 static_assert(sizeof(NearBlk) == 256, "NearBlk must be one 256-byte record");
+// Leaf record of one box, fetched by k_leaf_stream with ONE bulk copy:
+//   [0, 256)            NearBlk
+//   [256, 256 + 8 P)    a0[j] = A[j][0]      float64: the column that carries the cancellation
+//   then                af[j][k - 1] = (float) A[j][k], k >= 1, row stride GFS (zero padded): the variation of the far
+//                       field inside the box, which the mixed path evaluates in float32 anyway
+__host__ __device__ constexpr int leaf_gfs(int P) { return ((P - 1 + 3) / 4) * 4; }
+__host__ __device__ constexpr int leaf_rec_bytes(int P) { return 256 + 8 * P + 4 * P * leaf_gfs(P); }
 
 template <int P>
 __global__ void __launch_bounds__(256) k_leaf_prep(Lattice lat, LevelInfo leaf, const double* __restrict__ coef,
                                                    const int* __restrict__ start, const double4* __restrict__ knots,
                                                    double phi_max, unsigned long long* __restrict__ est_bits,
-                                                   NearBlk* __restrict__ near, float4* __restrict__ near_over,
+                                                   unsigned char* __restrict__ recs, float4* __restrict__ near_over,
                                                    int* __restrict__ over_cursor) {
+  constexpr int GFS = leaf_gfs(P);
   const int lane = threadIdx.x & 31;
   const int box = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (box >= leaf.nI * leaf.nJ) return;
   const double* A = coef + leaf.coef_off + (size_t)box * (P * P);
+  unsigned char* rec = recs + (size_t)box * leaf_rec_bytes(P);
+  double* a0 = reinterpret_cast<double*>(rec + 256);
+  float* af = reinterpret_cast<float*>(rec + 256 + 8 * P);
   double v = 0.0;
-  for (int i = 1 + lane; i < P * P; i += 32) v += fabs(A[i]);
+  for (int i = lane; i < P * GFS; i += 32) {          // (j, k - 1) incl. the zero padding of every row
+    const int jr = i / GFS, k = i % GFS + 1;
+    const double aij = k < P ? A[jr * P + k] : 0.0;
+    af[i] = (float)aij;
+    v += fabs(aij);
+  }
+  for (int jr = lane; jr < P; jr += 32) {
+    const double aj0 = A[jr * P];
+    a0[jr] = aj0;
+    if (jr > 0) v += fabs(aj0);
+  }
   const int I = lat.offx + box % leaf.nI, J = lat.offy + box / leaf.nI;
   int ra = 0, rlen = 0;
   double wsum = 0.0;
@@ -388,7 +409,7 @@ __global__ void __launch_bounds__(256) k_leaf_prep(Lattice lat, LevelInfo leaf, 
     tot += __shfl_xor_sync(0xffffffffu, tot, o);
   }
   if (lane == 0) {
-    const double est = 5.9604644775390625e-08 * ((P + 2) * v + 4.0 * phi_max * wsum);
+    const double est = 5.9604644775390625e-08 * (2 * (P + 2) * v + 4.0 * phi_max * wsum);
     atomicMax(est_bits, (unsigned long long)__double_as_longlong(est));   // est >= 0: bit order = value order
   }
   int off = 0;
@@ -396,7 +417,7 @@ __global__ void __launch_bounds__(256) k_leaf_prep(Lattice lat, LevelInfo leaf, 
     if (lane == 0) off = atomicAdd(over_cursor, tot);
     off = __shfl_sync(0xffffffffu, off, 0);
   }
-  NearBlk* nb = near + box;
+  NearBlk* nb = reinterpret_cast<NearBlk*>(rec);
   if (lane == 0) { nb->cnt = tot; nb->off = off; nb->pad0 = 0; nb->pad1 = 0; }
   const double ox = lat.sxo + lat.hx * I, oy = lat.syo + lat.hy * J;
   for (int base = 0; base < tot; base += 32) {
@@ -461,10 +482,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // with an accumulator).
 // -----------------------------------------------------------------------------------------
 constexpr int kLeafThreads = 256;
-constexpr int kLeafStages = 3;
-__host__ __device__ constexpr int leaf_gfs(int P) { return ((P - 1 + 3) / 4) * 4; }
+constexpr int kLeafStages = 4;
 __host__ __device__ inline int leaf_stage_bytes(int P, int bh, bool acc) {
-  return (P * P * 8 + 256 + (acc ? bh * 256 : 0) + 127) / 128 * 128;
+  return (leaf_rec_bytes(P) + (acc ? bh * 256 : 0) + 127) / 128 * 128;
 }
 
 // r2 is clamped to >= 1e-20 (a normal float32): the plain MUFU.LG2 without the denormal pre-scaling of __log2f
@@ -475,13 +495,16 @@ __device__ __forceinline__ float lg2_fast(float x) {
 }
 
 template <int P, bool kAcc>
-__global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? (kAcc ? 4 : 5) : 3) k_leaf_stream(
-    Lattice lat, LevelInfo leaf, mb_window w, const double* __restrict__ coef, const NearBlk* __restrict__ near,
-    const float4* __restrict__ near_over, const unsigned long long* __restrict__ est_bits, double mixed_threshold,
-    AccFuse fz, double* __restrict__ out, int64_t stride) {
+__global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream(
+    Lattice lat, mb_window w, const unsigned char* __restrict__ recs, const float4* __restrict__ near_over,
+    const unsigned long long* __restrict__ est_bits, double mixed_threshold, AccFuse fz, double* __restrict__ out,
+    int64_t stride) {
   static_assert(P % 2 == 0, "P must be even");
+  static_assert((kLeafStages & (kLeafStages - 1)) == 0, "stage count must be a power of two");
   if (!(__longlong_as_double((long long)__ldg(est_bits)) <= mixed_threshold)) return;   // k_leaf_f64 runs instead
   constexpr int GFS = leaf_gfs(P);
+  constexpr int NQ = GFS / 2;              // float2 column pairs (k = 2q+1, 2q+2) of a G row
+  constexpr uint32_t kRecBytes = leaf_rec_bytes(P);
   extern __shared__ __align__(128) unsigned char leaf_smem[];
   __shared__ __align__(8) uint64_t s_full[kLeafStages];
   const int bh = lat.bh;
@@ -498,75 +521,88 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? (kAcc ? 4 : 5) : 3) 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  constexpr uint32_t kRecBytes = P * P * 8 + 256;
   // box walk without divisions: box b = blockIdx.x + i G has lattice position (bi, bj); every step adds (dI, dJ)
   const int dI = G % lat.nbx, dJ = G / lat.nbx;
   int pbi = blockIdx.x % lat.nbx, pbj = blockIdx.x / lat.nbx;      // producer cursor (warp 0)
   int ibox = 0;                                                     // producer: next box to issue
   auto issue = [&]() {   // warp 0: bulk copies of this CTA's next box into stage ibox % kLeafStages
-    const int s = ibox % kLeafStages;
-    const int b = blockIdx.x + ibox * G;
+    const int s = ibox & (kLeafStages - 1);
     unsigned char* sp = leaf_smem + s * stage_bytes;
     if (lane == 0) {
       mbar_expect_tx(&s_full[s], kRecBytes + (kAcc ? (uint32_t)bh * 256u : 0u));
-      bulk_g2s(sp, coef + leaf.coef_off + (size_t)b * (P * P), P * P * 8, &s_full[s]);
-      bulk_g2s(sp + P * P * 8, near + b, 256, &s_full[s]);
+      bulk_g2s(sp, recs + (size_t)(blockIdx.x + ibox * G) * kRecBytes, kRecBytes, &s_full[s]);
     }
     if (kAcc) {
       __syncwarp();
       const double* src = fz.acc + (int64_t)pbj * bh * fz.stride + pbi * 32;
       for (int r = lane; r < bh; r += 32) bulk_g2s(sp + kRecBytes + r * 256, src + (int64_t)r * fz.stride, 256, &s_full[s]);
+      pbi += dI; pbj += dJ;
+      if (pbi >= lat.nbx) { pbi -= lat.nbx; ++pbj; }
     }
-    pbi += dI; pbj += dJ;
-    if (pbi >= lat.nbx) { pbi -= lat.nbx; ++pbj; }
     ++ibox;
   };
   if (warp == 0)
     for (int i = 0; i < min(kLeafStages, nmine); ++i) issue();
-  // the padding entries of the G rows (k >= P) meet T = 0 in the packed FMA: they must be finite
-  for (int i = tid; i < 2 * bh * GFS; i += kLeafThreads) s_Gf[i] = 0.f;
-  __syncthreads();
 
   // lane = (half, l): half selects one row of a row pair, l the column pair (l, 31 - l): tx_{31-l} = -tx_l, so the
   // even and the odd part of the expansion serve both columns.  (odd, even) terms are packed: one FFMA2 each.
   const int half = lane >> 4, l = lane & 15;
-  constexpr int NP = P / 2;                // pairs (T_1,T_2), (T_3,T_4), ... ; the last pair is (T_{P-1}, 0)
-  float2 Tp[NP];
+  float2 Tp[NQ];                           // (T_1,T_2), (T_3,T_4), ... ; entries with k >= P are 0 (G is zero padded too)
   {
-    float T[P + 1];
+    float T[2 * NQ + 1];
     const float tx = (2.0f * l + 1.0f) / 32.0f - 1.0f;   // exact in float32
     T[0] = 1.0f;
     T[1] = tx;
 #pragma unroll
-    for (int k = 2; k < P; ++k) T[k] = 2.0f * tx * T[k - 1] - T[k - 2];
-    T[P] = 0.0f;
+    for (int k = 2; k <= 2 * NQ; ++k) T[k] = k < P ? 2.0f * tx * T[k - 1] - T[k - 2] : 0.0f;
 #pragma unroll
-    for (int q = 0; q < NP; ++q) Tp[q] = make_float2(T[2 * q + 1], T[2 * q + 2]);
+    for (int q = 0; q < NQ; ++q) Tp[q] = make_float2(T[2 * q + 1], T[2 * q + 2]);
   }
   const float cxa = (float)(lat.hx * ((l + 0.5) / 32.0)), cxb = (float)(lat.hx * ((31 - l + 0.5) / 32.0));
   const double hyb = lat.hy / bh, inv_bh = 1.0 / bh;
   const int npair = (bh + 1) >> 1;
 
-  auto collapse = [&](int i) {   // expansion block of box i -> G buffer i & 1; rows lr and bh - 1 - lr share the products
-    const double2* A2 = reinterpret_cast<const double2*>(leaf_smem + (i % kLeafStages) * stage_bytes);
+  // Collapse y of box i into G buffer i & 1.  Rows lr and bh - 1 - lr have ty of opposite sign: the even and the odd
+  // part in ty serve both.  Column 0 in float64 (one thread per row pair), columns k >= 1 in float32, two columns per
+  // thread (packed FMA): G[lr][k] = sum_j T_j(ty_lr) A[j][k].
+  auto collapse = [&](int i) {
+    const unsigned char* rec = leaf_smem + (i & (kLeafStages - 1)) * stage_bytes;
+    const double* a0 = reinterpret_cast<const double*>(rec + 256);
+    const float2* af = reinterpret_cast<const float2*>(rec + 256 + 8 * P);     // [P][NQ]
     double* g0buf = s_G0 + (i & 1) * bh;
     float* gfbuf = s_Gf + (i & 1) * bh * GFS;
-    const double* A1 = reinterpret_cast<const double*>(A2);
-    for (int o = tid; o < npair * P; o += kLeafThreads) {      // item = (row pair lr / bh - 1 - lr, column k)
-      const int lr = o / P, k = o % P;
-      const double ty = (2.0 * lr + 1.0) * inv_bh - 1.0;
-      double t0 = 1.0, t1 = ty;
-      double ev = A1[k], od = t1 * A1[P + k];                  // even / odd part in ty
+    const int n32 = npair * NQ;
+    for (int o = tid; o < n32 + npair; o += kLeafThreads) {
+      if (o < n32) {
+        const int lr = o / NQ, q = o % NQ;
+        const float ty = (float)((2.0 * lr + 1.0) * inv_bh - 1.0);
+        float t0 = 1.0f, t1 = ty;
+        float2 ev = af[q], od = af[NQ + q];
+        od.x *= ty; od.y *= ty;
 #pragma unroll
-      for (int j = 2; j < P; ++j) {
-        const double t2 = 2.0 * ty * t1 - t0;
-        if (j & 1) od = fma(t2, A1[j * P + k], od);
-        else ev = fma(t2, A1[j * P + k], ev);
-        t0 = t1; t1 = t2;
+        for (int j = 2; j < P; ++j) {
+          const float t2 = 2.0f * ty * t1 - t0;
+          if (j & 1) od = __ffma2_rn(make_float2(t2, t2), af[j * NQ + q], od);
+          else ev = __ffma2_rn(make_float2(t2, t2), af[j * NQ + q], ev);
+          t0 = t1; t1 = t2;
+        }
+        const int lm = bh - 1 - lr;
+        *reinterpret_cast<float2*>(gfbuf + lr * GFS + 2 * q) = make_float2(ev.x + od.x, ev.y + od.y);
+        *reinterpret_cast<float2*>(gfbuf + lm * GFS + 2 * q) = make_float2(ev.x - od.x, ev.y - od.y);
+      } else {
+        const int lr = o - n32;
+        const double ty = (2.0 * lr + 1.0) * inv_bh - 1.0;
+        double t0 = 1.0, t1 = ty, ev = a0[0], od = ty * a0[1];
+#pragma unroll
+        for (int j = 2; j < P; ++j) {
+          const double t2 = 2.0 * ty * t1 - t0;
+          if (j & 1) od = fma(t2, a0[j], od);
+          else ev = fma(t2, a0[j], ev);
+          t0 = t1; t1 = t2;
+        }
+        g0buf[lr] = ev + od;
+        g0buf[bh - 1 - lr] = ev - od;
       }
-      const int lm = bh - 1 - lr;
-      if (k == 0) { g0buf[lr] = ev + od; g0buf[lm] = ev - od; }
-      else { gfbuf[lr * GFS + k - 1] = (float)(ev + od); gfbuf[lm * GFS + k - 1] = (float)(ev - od); }
     }
   };
 
@@ -578,8 +614,8 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? (kAcc ? 4 : 5) : 3) 
 #pragma unroll
     for (int q = 0; q < GFS / 4; ++q) {
       const float4 g = g4[q];
-      if (2 * q < NP) eo = __ffma2_rn(make_float2(g.x, g.y), Tp[2 * q], eo);
-      if (2 * q + 1 < NP) eo = __ffma2_rn(make_float2(g.z, g.w), Tp[2 * q + 1], eo);
+      eo = __ffma2_rn(make_float2(g.x, g.y), Tp[2 * q], eo);
+      eo = __ffma2_rn(make_float2(g.z, g.w), Tp[2 * q + 1], eo);
     }
     float fa = eo.y + eo.x, fb = eo.y - eo.x;
     if (cnt > 0) {
@@ -622,13 +658,13 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? (kAcc ? 4 : 5) : 3) 
   const int wcols = w.c1 - w.c0, wrows = w.r1 - w.r0;
   for (int i = 0; i < nmine; ++i) {
     if (i + 1 < nmine) {
-      mbar_wait(&s_full[(i + 1) % kLeafStages], ((i + 1) / kLeafStages) & 1);
+      mbar_wait(&s_full[(i + 1) & (kLeafStages - 1)], ((i + 1) / kLeafStages) & 1);
       collapse(i + 1);
     }
     // ---- rows of box i: warp -> row pairs warp, warp + 8, ... ; lane half -> row of the pair -------------------
     {
-      const unsigned char* sp = leaf_smem + (i % kLeafStages) * stage_bytes;
-      const NearBlk* nb = reinterpret_cast<const NearBlk*>(sp + P * P * 8);
+      const unsigned char* sp = leaf_smem + (i & (kLeafStages - 1)) * stage_bytes;
+      const NearBlk* nb = reinterpret_cast<const NearBlk*>(sp);
       const double* accT = reinterpret_cast<const double*>(sp + kRecBytes);
       const int cnt = nb->cnt;
       const double* g0buf = s_G0 + (i & 1) * bh;
@@ -808,7 +844,7 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
   unsigned long long* d_est = ar.take_n<unsigned long long>(2);
   int* d_cursor = reinterpret_cast<int*>(d_est + 1);
   const int nboxes = lat.nbx * lat.nby;
-  NearBlk* d_near = ar.take_n<NearBlk>(nboxes);
+  unsigned char* d_recs = ar.take_n<unsigned char>((size_t)nboxes * leaf_rec_bytes(P));
   float4* d_over = ar.take_n<float4>(9 * sorted.size() + 1);
   constexpr int threads = ((P * P + 31) / 32) * 32;
   for (size_t li = 0; li < levels.size(); ++li) {
@@ -829,7 +865,7 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
   MB_CUDA(cudaMemsetAsync(d_est, 0, 2 * sizeof(unsigned long long), st));
   if (thr > 0) {
     const double phi_max = r2max * std::fabs(std::log(r2max));
-    MB_LAUNCH(ctx, "k_leaf_prep", st) k_leaf_prep<P><<<(nboxes + 7) / 8, 256, 0, st>>>(lat, leaf, d_coef, d_start, d_knots, phi_max, d_est, d_near, d_over, d_cursor);
+    MB_LAUNCH(ctx, "k_leaf_prep", st) k_leaf_prep<P><<<(nboxes + 7) / 8, 256, 0, st>>>(lat, leaf, d_coef, d_start, d_knots, phi_max, d_est, d_recs, d_over, d_cursor);
     MB_CUDA(cudaGetLastError());
   }
   const AccFuse fz = fuse ? *fuse : AccFuse{nullptr, 0, 0.0};
@@ -838,10 +874,10 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
                         2 * (size_t)lat.bh * (sizeof(double) + leaf_gfs(P) * sizeof(float));
     if (fuse) {
       const int grid = leaf_grid(ctx, k_leaf_stream<P, true>, smem, nboxes);
-      MB_LAUNCH(ctx, "k_leaf_fused", st) k_leaf_stream<P, true><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_near, d_over, d_est, thr, fz, out, stride);
+      MB_LAUNCH(ctx, "k_leaf_fused", st) k_leaf_stream<P, true><<<grid, kLeafThreads, smem, st>>>(lat, w, d_recs, d_over, d_est, thr, fz, out, stride);
     } else {
       const int grid = leaf_grid(ctx, k_leaf_stream<P, false>, smem, nboxes);
-      MB_LAUNCH(ctx, "k_leaf", st) k_leaf_stream<P, false><<<grid, kLeafThreads, smem, st>>>(lat, leaf, w, d_coef, d_near, d_over, d_est, thr, fz, out, stride);
+      MB_LAUNCH(ctx, "k_leaf", st) k_leaf_stream<P, false><<<grid, kLeafThreads, smem, st>>>(lat, w, d_recs, d_over, d_est, thr, fz, out, stride);
     }
     MB_CUDA(cudaGetLastError());
   }

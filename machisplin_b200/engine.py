@@ -374,6 +374,16 @@ class Engine:
         check(self.lib.mb_tiles_merge(self._h, C.byref(g), ncol, nrow, wa, pa, _pd(out)))
         return out
 
+    def tiles_merge_dev(self, geom, wins, tile_ptrs: Sequence[int], ncol: int, nrow: int, out_ptr: int, stream: int = 0):
+        """``machisplin.tiles.merge`` on device-resident tile rasters (row-major, window-shaped); asynchronous."""
+        geom = as_geom(geom)
+        nt = ncol * nrow
+        assert len(wins) == nt and len(tile_ptrs) == nt
+        wa = (Window * nt)(*[Window(*map(int, w)) for w in wins])
+        pa = (C.c_void_p * nt)(*[C.c_void_p(int(p)) for p in tile_ptrs])
+        g = geom.c()
+        check(self.lib.mb_tiles_merge_dev(self._h, C.byref(g), ncol, nrow, wa, pa, C.c_void_p(out_ptr), C.c_void_p(stream)))
+
     # -- a6 / a7 --------------------------------------------------------------------------------------------
     def gram(self, R) -> np.ndarray:
         R = np.asfortranarray(np.asarray(R, dtype=np.float64))

@@ -93,3 +93,28 @@ def gather_tiles(local: Sequence[Tuple[int, np.ndarray]], n_tiles: int, dst: int
     got = {t: r for part in buf for (t, r) in part}
     assert len(got) == n_tiles, "a tile is missing: ownership map and results disagree"
     return [got[t] for t in range(n_tiles)]
+
+
+def gather_tiles_device(local_tile, tile_shapes: Sequence[Tuple[int, int]], dst: int = 0):
+    """Tile-border blend, step 1 (V73:1392-1548 across GPUs): every rank owns the ``$final`` raster of tile
+    ``rank`` as a float64 torch tensor on its GPU; rank ``dst`` receives all of them over NCCL (point-to-point
+    on NVLink, device to device - nothing is staged on the host) and then runs ``Engine.tiles_merge_dev``.
+    Returns the list of tile tensors (tile order) on ``dst``, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [local_tile]
+    rank, world = dist.get_rank(), dist.get_world_size()
+    assert len(tile_shapes) == world, "one tile per rank"
+    if rank != dst:
+        dist.send(local_tile.contiguous(), dst=dst)
+        return None
+    tiles = []
+    for r in range(world):
+        if r == dst:
+            tiles.append(local_tile)
+        else:
+            buf = torch.empty(tuple(tile_shapes[r]), dtype=local_tile.dtype, device=local_tile.device)
+            dist.recv(buf, src=r)
+            tiles.append(buf)
+    return tiles

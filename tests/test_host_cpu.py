@@ -92,6 +92,15 @@ if rank == 0:
     assert [int(g[0, 0]) for g in got] == list(range(7))
 else:
     assert got is None
+# tile-border blend, step 1: tensors travel point-to-point to the merging rank (NCCL on GPUs, gloo here)
+import torch
+shapes = [(3, 4), (2, 5)]
+tile = torch.full(shapes[rank], float(rank + 1), dtype=torch.float64)
+tl = par.gather_tiles_device(tile, shapes, dst=0)
+if rank == 0:
+    assert [tuple(t.shape) for t in tl] == shapes and float(tl[1][1, 4]) == 2.0 and float(tl[0][0, 0]) == 1.0
+else:
+    assert tl is None
 dist.barrier()
 dist.destroy_process_group()
 sys.stdout.write(f"rank{rank}ok\n"); sys.stdout.flush()
