@@ -651,8 +651,13 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
   __syncthreads();
   // consumer cursor: lattice position of the current box and the address of this lane's first cell in it
   int cbi = blockIdx.x % lat.nbx, cbj = blockIdx.x / lat.nbx;
-  const int lr0 = 2 * warp + half;
+  // Full 32-row boxes: the collapse of the next box occupies warps 0-3, so those take one of the 16 row pairs each
+  // and warps 4-7 three each (equal instruction counts per warp between two barriers).  Other boxes: row pairs
+  // warp, warp + 8, ...
+  const int pfirst = warp < 4 ? warp : 4 + (warp - 4) * 3;
+  const int lr0 = 2 * pfirst + half, lrg = 2 * warp + half;
   double* dst0 = out + ((int64_t)cbj * bh + lr0) * stride + (cbi * 32 + l);
+  const int64_t gen_off = (int64_t)(lrg - lr0) * stride;
   const int64_t box_step = (int64_t)dJ * bh * stride + dI * 32, wrap_step = (int64_t)bh * stride - (int64_t)lat.nbx * 32;
   const int64_t dstep = 16 * stride;
   const int wcols = w.c1 - w.c0, wrows = w.r1 - w.r0;
@@ -672,11 +677,14 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
       const int rows_here = min(bh, wrows - cbj * bh);
       if (bh == 32 && rows_here == 32 && cbi * 32 + 32 <= wcols) {   // full box: no predicates
         row_pass(lr0, gfbuf, g0buf, nb, cnt, accT, dst0, true, true);
-        row_pass(lr0 + 16, gfbuf, g0buf, nb, cnt, accT, dst0 + dstep, true, true);
+        if (warp >= 4) {
+          row_pass(lr0 + 2, gfbuf, g0buf, nb, cnt, accT, dst0 + 2 * stride, true, true);
+          row_pass(lr0 + 4, gfbuf, g0buf, nb, cnt, accT, dst0 + 4 * stride, true, true);
+        }
       } else {
         const bool okA = cbi * 32 + l < wcols, okB = cbi * 32 + 31 - l < wcols;
-        double* dst = dst0;
-        for (int lr = lr0; lr < rows_here; lr += 16, dst += dstep) row_pass(lr, gfbuf, g0buf, nb, cnt, accT, dst, okA, okB);
+        double* dst = dst0 + gen_off;
+        for (int lr = lrg; lr < rows_here; lr += 16, dst += dstep) row_pass(lr, gfbuf, g0buf, nb, cnt, accT, dst, okA, okB);
       }
     }
     cbi += dI; cbj += dJ; dst0 += box_step;
