@@ -68,6 +68,13 @@ void mb_shutdown(mb_ctx* ctx) {
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->copy) cudaStreamDestroy(ctx->copy);
+  for (auto& w : ctx->lanes) {
+    w->logtab.p = nullptr; w->logtab.n = 0;
+    w->arena.release();
+    for (cudaEvent_t e : w->event_pool) cudaEventDestroy(e);
+    if (w->stream) cudaStreamDestroy(w->stream);
+  }
+  ctx->lanes.clear();
   for (cudaEvent_t ev : ctx->ev_blocks) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -174,6 +174,8 @@ struct mb_ctx {
   // copy stream + per-row-block events of the host-buffer path (H2D of block b+1 overlaps the kernels of block b)
   cudaStream_t copy = nullptr;
   std::vector<cudaEvent_t> ev_blocks;
+  // worker lanes of the tile loop (mltps part 3): own stream + arena each, created on first use
+  std::vector<std::unique_ptr<mb_ctx>> lanes;
 };
 
 struct mb_spline {

@@ -672,7 +672,14 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
   MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sytrd, kSyThreads, kSytrdSmem));
   if (occ < 1) throw Error(MB_E_UNSUPPORTED, "k_sytrd does not fit on an SM");
   // the grid barrier needs every CTA resident: at most two per SM, and never more than the device can hold
-  const int G = std::max(1, std::min(occ, ctx->sytrd_ctas_per_sm > 0 ? ctx->sytrd_ctas_per_sm : 2)) * ctx->sm_count;
+  int G = std::max(1, std::min(occ, ctx->sytrd_ctas_per_sm > 0 ? ctx->sytrd_ctas_per_sm : 2)) * ctx->sm_count;
+  {
+    // small matrices (the 1 500-px tiles of mltps carry a few hundred knots): no more CTAs than there is work for -
+    // row chunks, strip segments, panel dot products - so that the barrier and the partial reductions stay cheap
+    const int nchunk = (m + kChunk - 1) / kChunk;
+    const int na = a.nt, nseg = (na / kSeg + 1) * (2 * (na / kSeg) + na % kSeg);
+    G = std::min(G, std::max(std::max(nchunk, nseg), 8));
+  }
   a.S = ar.take_n<double>((size_t)((m + kChunk - 1) / kChunk) * kSW);
   a.S2 = ar.take_n<double>(G);
   MB_CUDA(cudaMemsetAsync(a.bar, 0, 64 * sizeof(unsigned), st));

@@ -10,6 +10,9 @@
 //   gram         K8: G = R'R of the cross-validation residual matrix (V73:329-331 objective).
 //   gather_cells part 5 point extraction (V73:910).
 #include "common.cuh"
+
+#include <exception>
+#include <thread>
 #include "internal.h"
 
 #include <algorithm>
@@ -245,7 +248,10 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
   std::vector<mb_window> keep(nt);
   std::vector<double*> bufs(nt);
   std::vector<const double*> ptrs(nt);
-  std::vector<double> txy, ty;
+  // ---- per tile: windows, knots, output buffer (host arithmetic only) ---------------------------------
+  struct TileJob { std::vector<double> xy, y; int m = 0; };
+  std::vector<TileJob> jobs(nt);
+  int m_max = 0;
   for (int j = 1; j <= nRx; ++j)
     for (int h = 1; h <= nCx; ++h) {
       const int t = (j - 1) * nCx + (h - 1);
@@ -261,29 +267,86 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
       kw.c0 = std::max(kw.c0, fw.c0); kw.c1 = std::min(kw.c1, fw.c1);
       MB_REQUIRE(kw.r1 > kw.r0 && kw.c1 > kw.c0, "empty tile window");
       keep[t] = kw;
-      txy.clear(); ty.clear();
-      std::vector<double> tx, tyy;
+      std::vector<double> tx, tyy, ty;
       for (int i = 0; i < n; ++i)
         if (krow[i] >= fw.r0 && krow[i] < fw.r1 && kcol[i] >= fw.c0 && kcol[i] < fw.c1) {   // V73:699-706
           tx.push_back(knots_xy[i]); tyy.push_back(knots_xy[(size_t)n + i]); ty.push_back(resid[i]);
         }
-      const int m = (int)ty.size();
+      TileJob& job = jobs[t];
+      job.m = (int)ty.size();
+      m_max = std::max(m_max, job.m);
+      job.xy.resize((size_t)2 * job.m);
+      std::copy(tx.begin(), tx.end(), job.xy.begin());
+      std::copy(tyy.begin(), tyy.end(), job.xy.begin() + job.m);
+      job.y = std::move(ty);
       const size_t cells = (size_t)(kw.r1 - kw.r0) * (kw.c1 - kw.c0);
       bufs[t] = ctx->arena.take_n<double>(cells);
       ptrs[t] = bufs[t];
-      if (m < min_pts) {                                                                     // V73:710-721
-        MB_LAUNCH(ctx, "k_fill", st) k_fill<<<256, 256, 0, st>>>(bufs[t], (int64_t)cells, 0.0);
-        continue;
-      }
-      txy.resize((size_t)2 * m);
-      std::copy(tx.begin(), tx.end(), txy.begin());
-      std::copy(tyy.begin(), tyy.end(), txy.begin() + m);
-      mb_spline* sp = nullptr;
-      tps_fit(ctx, txy.data(), ty.data(), m, 1, lambda, &sp);                                 // V73:722
-      std::unique_ptr<mb_spline> hold(sp);
-      eval(sp, kw, bufs[t]);                                                               // V73:726-728
-      MB_CUDA(cudaStreamSynchronize(st));
     }
+  // ---- fit + evaluate every tile (V73:710-728) -----------------------------------------------------------
+  auto run_tile = [&](mb_ctx* c, cudaStream_t cs, int t) {
+    const TileJob& job = jobs[t];
+    const mb_window& kw = keep[t];
+    const size_t cells = (size_t)(kw.r1 - kw.r0) * (kw.c1 - kw.c0);
+    if (job.m < min_pts) {                                                                   // V73:710-721
+      MB_LAUNCH(c, "k_fill", cs) k_fill<<<256, 256, 0, cs>>>(bufs[t], (int64_t)cells, 0.0);
+      return;
+    }
+    mb_spline* sp = nullptr;
+    tps_fit(c, job.xy.data(), job.y.data(), job.m, 1, lambda, &sp);                           // V73:722
+    std::unique_ptr<mb_spline> hold(sp);
+    if (method == MB_EVAL_DIRECT) tps_eval_direct(c, sp, g, kw, bufs[t], kw.c1 - kw.c0, cs);   // V73:726-728
+    else tps_eval_fast(c, sp, g, kw, bufs[t], kw.c1 - kw.c0, cs);
+    MB_CUDA(cudaStreamSynchronize(cs));
+  };
+  // Tiles are independent: four worker lanes (own stream + scratch arena) keep the device busy while one lane sits
+  // in a host synchronisation of its fit.  Only for small fits: their persistent kernels use small grids, so
+  // several are co-resident; a large fit takes the whole device and runs alone.
+  constexpr int kLanes = 4;
+  const bool concurrent = nt >= 2 && m_max <= 1200 && ctx->eigen_impl == 0 && st == ctx->stream;
+  if (!concurrent) {
+    for (int t = 0; t < nt; ++t) run_tile(ctx, st, t);
+  } else {
+    while ((int)ctx->lanes.size() < kLanes) {
+      auto w = std::make_unique<mb_ctx>();
+      w->device = ctx->device;
+      w->sm_count = ctx->sm_count;
+      int prio_lo = 0, prio_hi = 0;
+      MB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      MB_CUDA(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, prio_hi));
+      ctx->lanes.push_back(std::move(w));
+    }
+    std::vector<std::exception_ptr> errs(kLanes);
+    std::vector<std::thread> threads;
+    for (int l = 0; l < kLanes; ++l) {
+      mb_ctx* w = ctx->lanes[l].get();
+      w->timing = ctx->timing;
+      w->cheb_p = ctx->cheb_p; w->leaf_cols = ctx->leaf_cols; w->leaf_rows = ctx->leaf_rows;
+      w->eval_precision = ctx->eval_precision; w->sytrd_mode = ctx->sytrd_mode; w->sytrd_ctas_per_sm = ctx->sytrd_ctas_per_sm;
+      w->logtab.p = ctx->logtab.p; w->logtab.n = ctx->logtab.n;        // borrowed (read-only table)
+      threads.emplace_back([&, l, w] {
+        try {
+          MB_CUDA(cudaSetDevice(w->device));
+          for (int t = l; t < nt; t += kLanes) {
+            w->arena.begin(w->stream);
+            run_tile(w, w->stream, t);
+          }
+          MB_CUDA(cudaStreamSynchronize(w->stream));
+        } catch (...) {
+          errs[l] = std::current_exception();
+        }
+      });
+    }
+    for (auto& th : threads) th.join();
+    for (int l = 0; l < kLanes; ++l) {
+      mb_ctx* w = ctx->lanes[l].get();
+      w->logtab.p = nullptr; w->logtab.n = 0;                          // give the borrowed table back
+      ctx->launches += w->launches; w->launches = 0;
+      ctx->timed.insert(ctx->timed.end(), w->timed.begin(), w->timed.end());
+      w->timed.clear();
+    }
+    for (auto& e : errs) if (e) std::rethrow_exception(e);
+  }
   tiles_merge(ctx, g, nCx, nRx, keep.data(), ptrs.data(), out_dev, st);                       // V73:739-895
 }
 

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <mutex>
 
 namespace mb {
 
@@ -170,7 +171,10 @@ static void cheb_T(int P, long double x, long double* T) {
 }
 
 static ChebTables* get_tables(mb_ctx* ctx, int P) {
-  static thread_local std::map<std::pair<int, int>, std::unique_ptr<ChebTables>> cache;
+  // one table set per (device, P) for the whole process; the tile lanes of tiles_tps call this concurrently
+  static std::map<std::pair<int, int>, std::unique_ptr<ChebTables>> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   auto key = std::make_pair(ctx->device, P);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second.get();
