@@ -405,10 +405,18 @@ def run_b200(args):
         kern[name] = ent
     lname = next((k for k in ("k_leaf_fused", "k_leaf", "k_leaf_f64_fused", "k_leaf_f64") if k in kern), "k_leaf")
     leaf = kern.get(lname, {})
+    # DRAM traffic of the kernel per launch from the committed ncu --set full capture of this workload (profiles/)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        key = f"{lname}@{cfg['nrow']}x{cfg['ncol']}"
+        traffic = tr.get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     roofline = {"kernel": f"{lname} (grid-evaluation kernel: per-cell TPS surface" +
                           (" + ensemble combine, mltps part 5)" if "fused" in lname else ")"),
                 "bound": "hbm", "achieved": leaf.get("achieved_gbs"),
-                "peak": peak, "unit": "GB/s", "frac": leaf.get("hbm_frac"), "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": leaf.get("hbm_frac"), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": bytes_per_cell[lname],
                 "note": "roofline of the north-star kernel; `kernels` lists every kernel of the step with its share"}
 

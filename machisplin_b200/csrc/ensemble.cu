@@ -814,7 +814,7 @@ static void launch_trees(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
                          const mb_window& w, const int* roots, int n_rf, int n_gb, double* acc, cudaStream_t st) {
   const double rf_scale = n_rf ? e->w[MB_R] / n_rf : 0.0, gb_scale = e->w[MB_B];
   const double base = (n_rf ? e->w[MB_R] * e->rf.offset : 0.0) + (n_gb ? e->w[MB_B] * e->gb_initF : 0.0);
-  const int R = ctx->tree_rows > 0 ? ctx->tree_rows : 2;
+  const int R = ctx->tree_rows > 0 ? ctx->tree_rows : 1;   // measured: R = 1 gives the shortest step (profiles/r1r_tree_rows.txt)
   const size_t smem = sizeof(float) * (size_t)(C + 2) * kTreeThreads * R + sizeof(int) * 8 * (kTreeSeg + kTreeIlp);
   dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 8 * R - 1) / (8 * R));
 #define MB_TREES_CASE(RR)                                                                                         \
