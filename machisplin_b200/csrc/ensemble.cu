@@ -30,7 +30,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <queue>
+#include <thread>
 
 struct PackedForest {
   int ntrees = 0;
@@ -689,48 +691,67 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
   }
   std::vector<int2> nodes;          // both forests, rf first (child indices are absolute)
   std::vector<int> froots;
+  // Trees are re-laid out independently (breadth-first, children adjacent, child indices local to the tree) on all
+  // host threads, then concatenated; the child index of every split node is shifted by the tree's offset.
+  auto pack_forest = [&](int nt, auto&& pack_one) {
+    std::vector<std::vector<int2>> packs(nt);
+    std::vector<std::exception_ptr> errs;
+    const int nthr = std::max(1, std::min<int>(nt, (int)std::thread::hardware_concurrency()));
+    errs.resize(nthr);
+    std::vector<std::thread> thr;
+    for (int w = 0; w < nthr; ++w)
+      thr.emplace_back([&, w] {
+        try {
+          for (int t = w; t < nt; t += nthr) pack_one(t, packs[t]);
+        } catch (...) { errs[w] = std::current_exception(); }
+      });
+    for (auto& th : thr) th.join();
+    for (auto& er : errs) if (er) std::rethrow_exception(er);
+    for (int t = 0; t < nt; ++t) {
+      const size_t off = nodes.size();
+      MB_REQUIRE(off + packs[t].size() < ((size_t)1 << 26), "forest too large for the packed node format");
+      froots.push_back((int)off);
+      for (const int2& nd : packs[t])
+        nodes.push_back((nd.y & kMetaLeaf) ? nd : make_int2(nd.x, nd.y + (int)(off << 5)));
+    }
+  };
   if (e->has[MB_R]) {
     MB_REQUIRE(m.rf_ntree >= 1 && m.rf_nrnodes >= 1 && m.rf_left && m.rf_right && m.rf_status && m.rf_bestvar &&
                    m.rf_split && m.rf_nodepred, "randomForest kept but descriptor is empty");
     const int nt = m.rf_ntree, nn = m.rf_nrnodes;
-    // leaf offset: mean of the root-reachable leaf values of the first tree is a good centre
+    // leaf offset: the mean leaf value of the first tree is a good centre for the float32 leaf storage
     double off = 0; int cnt = 0;
-    for (int k = 0; k < nn; ++k) if (m.rf_status[k] == -1 && (k == 0 || true)) { off += m.rf_nodepred[k]; ++cnt; }
+    for (int k = 0; k < nn; ++k) if (m.rf_status[k] == -1) { off += m.rf_nodepred[k]; ++cnt; }
     off = cnt ? off / cnt : 0.0;
-    std::vector<int> roots(nt);
-    nodes.reserve((size_t)nt * 64);
-    for (int t = 0; t < nt; ++t) {
+    pack_forest(nt, [&](int t, std::vector<int2>& out) {
       const size_t o = (size_t)t * nn;
-      // breadth-first re-layout with adjacent children
       std::queue<std::pair<int, size_t>> q;   // (reference node, packed position)
-      roots[t] = (int)nodes.size();
-      nodes.push_back(make_int2(0, 0));
-      q.push({0, (size_t)roots[t]});
+      out.reserve(256);
+      out.push_back(make_int2(0, 0));
+      q.push({0, 0});
       while (!q.empty()) {
         auto [k, pos] = q.front();
         q.pop();
         MB_REQUIRE(k >= 0 && k < nn, "randomForest: daughter index out of range");
         if (m.rf_status[o + k] == -1) {
           const float v = (float)(m.rf_nodepred[o + k] - off);
-          nodes[pos] = make_int2(__builtin_bit_cast(int, v), kMetaLeaf);
+          out[pos] = make_int2(__builtin_bit_cast(int, v), kMetaLeaf);
           continue;
         }
         const int var = m.rf_bestvar[o + k] - 1;
         MB_REQUIRE(var >= 0 && var < P, "randomForest: bestvar out of range");
         float thr; bool swap;
         convert_split(g, C, var, m.rf_split[o + k], false, &thr, &swap);
-        const size_t child = nodes.size();
-        MB_REQUIRE(child < ((size_t)1 << 26), "forest too large for the packed node format");
-        nodes.push_back(make_int2(0, 0));
-        nodes.push_back(make_int2(0, 0));
-        nodes[pos] = make_int2(__builtin_bit_cast(int, thr), (int)(child << 5) | var);
+        const size_t child = out.size();
+        out.push_back(make_int2(0, 0));
+        out.push_back(make_int2(0, 0));
+        out[pos] = make_int2(__builtin_bit_cast(int, thr), (int)(child << 5) | var);
         const int l = m.rf_left[o + k] - 1, r = m.rf_right[o + k] - 1;
         q.push({swap ? r : l, child});
         q.push({swap ? l : r, child + 1});
       }
-    }
+    });
     e->rf.ntrees = nt; e->rf.offset = off;
-    froots.insert(froots.end(), roots.begin(), roots.end());
     e->rf_ntree = nt; e->rf_nrnodes = nn;
     const size_t tot = (size_t)nt * nn;
     e->rfp_left.upload(m.rf_left, tot, st); e->rfp_right.upload(m.rf_right, tot, st);
@@ -741,13 +762,12 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
     MB_REQUIRE(m.gbm_ntrees >= 1 && m.gbm_tree_off && m.gbm_splitvar && m.gbm_splitcode && m.gbm_left &&
                    m.gbm_right && m.gbm_missing, "gbm kept but descriptor is empty");
     const int nt = m.gbm_ntrees;
-    std::vector<int> roots(nt);
-    for (int t = 0; t < nt; ++t) {
+    pack_forest(nt, [&](int t, std::vector<int2>& out) {
       const int o = m.gbm_tree_off[t], cntn = m.gbm_tree_off[t + 1] - o;
       std::queue<std::pair<int, size_t>> q;
-      roots[t] = (int)nodes.size();
-      nodes.push_back(make_int2(0, 0));
-      q.push({0, (size_t)roots[t]});
+      out.reserve(64);
+      out.push_back(make_int2(0, 0));
+      q.push({0, 0});
       while (!q.empty()) {
         auto [k, pos] = q.front();
         q.pop();
@@ -755,24 +775,22 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
         const int var = m.gbm_splitvar[o + k];
         if (var == -1) {
           const float v = (float)m.gbm_splitcode[o + k];
-          nodes[pos] = make_int2(__builtin_bit_cast(int, v), kMetaLeaf);
+          out[pos] = make_int2(__builtin_bit_cast(int, v), kMetaLeaf);
           continue;
         }
         MB_REQUIRE(var >= 0 && var < P, "gbm: SplitVar out of range");
         float thr; bool swap;
         convert_split(g, C, var, m.gbm_splitcode[o + k], true, &thr, &swap);
-        const size_t child = nodes.size();
-        MB_REQUIRE(child < ((size_t)1 << 26), "boosted model too large for the packed node format");
-        for (int c3 = 0; c3 < 3; ++c3) nodes.push_back(make_int2(0, 0));
-        nodes[pos] = make_int2(__builtin_bit_cast(int, thr), (int)(child << 5) | var);
+        const size_t child = out.size();
+        for (int c3 = 0; c3 < 3; ++c3) out.push_back(make_int2(0, 0));
+        out[pos] = make_int2(__builtin_bit_cast(int, thr), (int)(child << 5) | var);
         const int l = m.gbm_left[o + k], r = m.gbm_right[o + k];
         q.push({swap ? r : l, child});
         q.push({swap ? l : r, child + 1});
         q.push({m.gbm_missing[o + k], child + 2});
       }
-    }
+    });
     e->gbm.ntrees = nt;
-    froots.insert(froots.end(), roots.begin(), roots.end());
     e->gb_ntrees = nt; e->gb_initF = m.gbm_initF;
     const size_t tot = m.gbm_tree_off[nt];
     e->gbp_off.upload(m.gbm_tree_off, nt + 1, st); e->gbp_var.upload(m.gbm_splitvar, tot, st);

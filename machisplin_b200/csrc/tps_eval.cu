@@ -564,6 +564,7 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
   }
   const float cxa = (float)(lat.hx * ((l + 0.5) / 32.0)), cxb = (float)(lat.hx * ((31 - l + 0.5) / 32.0));
   const double hyb = lat.hy / bh, inv_bh = 1.0 / bh;
+  const float inv_bh_f = (float)inv_bh;
   const int npair = (bh + 1) >> 1;
 
   // Collapse y of box i into G buffer i & 1.  Rows lr and bh - 1 - lr have ty of opposite sign: the even and the odd
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
     for (int o = tid; o < n32 + npair; o += kLeafThreads) {
       if (o < n32) {
         const int lr = o / NQ, q = o % NQ;
-        const float ty = (float)((2.0 * lr + 1.0) * inv_bh - 1.0);
+        const float ty = fmaf((float)(2 * lr + 1), inv_bh_f, -1.0f);   // exact for bh = 32
         float t0 = 1.0f, t1 = ty;
         float2 ev = af[q], od = af[NQ + q];
         od.x *= ty; od.y *= ty;
@@ -650,6 +651,7 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
     if (okB) __stcs(dst + (31 - 2 * l), vb);
   };
 
+  const int n_items = npair * (NQ + 1);
   mbar_wait(&s_full[0], 0);
   collapse(0);
   __syncthreads();
@@ -660,13 +662,15 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
   // warp, warp + 8, ...
   const int pfirst = warp < 4 ? warp : 4 + (warp - 4) * 3;
   const int lr0 = 2 * pfirst + half, lrg = 2 * warp + half;
-  double* dst0 = out + ((int64_t)cbj * bh + lr0) * stride + (cbi * 32 + l);
+  // element offset of this lane's first cell of the current box (64-bit only where the address is formed)
+  int64_t e0 = ((int64_t)cbj * bh + lr0) * stride + (cbi * 32 + l);
   const int64_t gen_off = (int64_t)(lrg - lr0) * stride;
   const int64_t box_step = (int64_t)dJ * bh * stride + dI * 32, wrap_step = (int64_t)bh * stride - (int64_t)lat.nbx * 32;
   const int64_t dstep = 16 * stride;
   const int wcols = w.c1 - w.c0, wrows = w.r1 - w.r0;
+  const int full_bi = wcols >> 5, full_bj = bh == 32 ? (wrows >> 5) : 0;   // boxes below these indices are complete 32 x 32
   for (int i = 0; i < nmine; ++i) {
-    if (i + 1 < nmine) {
+    if (i + 1 < nmine && warp * 32 < n_items) {   // warps without collapse items are ordered behind these by the box barrier
       mbar_wait(&s_full[(i + 1) & (kLeafStages - 1)], ((i + 1) / kLeafStages) & 1);
       collapse(i + 1);
     }
@@ -678,21 +682,22 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
       const int cnt = nb->cnt;
       const double* g0buf = s_G0 + (i & 1) * bh;
       const float* gfbuf = s_Gf + (i & 1) * bh * GFS;
-      const int rows_here = min(bh, wrows - cbj * bh);
-      if (bh == 32 && rows_here == 32 && cbi * 32 + 32 <= wcols) {   // full box: no predicates
+      double* dst0 = out + e0;
+      if (cbi < full_bi && cbj < full_bj) {   // complete box: no predicates
         row_pass(lr0, gfbuf, g0buf, nb, cnt, accT, dst0, true, true);
         if (warp >= 4) {
           row_pass(lr0 + 2, gfbuf, g0buf, nb, cnt, accT, dst0 + 2 * stride, true, true);
           row_pass(lr0 + 4, gfbuf, g0buf, nb, cnt, accT, dst0 + 4 * stride, true, true);
         }
       } else {
+        const int rows_here = min(bh, wrows - cbj * bh);
         const bool okA = cbi * 32 + l < wcols, okB = cbi * 32 + 31 - l < wcols;
         double* dst = dst0 + gen_off;
         for (int lr = lrg; lr < rows_here; lr += 16, dst += dstep) row_pass(lr, gfbuf, g0buf, nb, cnt, accT, dst, okA, okB);
       }
     }
-    cbi += dI; cbj += dJ; dst0 += box_step;
-    if (cbi >= lat.nbx) { cbi -= lat.nbx; ++cbj; dst0 += wrap_step; }
+    cbi += dI; cbj += dJ; e0 += box_step;
+    if (cbi >= lat.nbx) { cbi -= lat.nbx; ++cbj; e0 += wrap_step; }
     __syncthreads();   // stage i % kLeafStages and G buffer i & 1 are free again
     if (warp == 0 && ibox < nmine) issue();
   }
