@@ -573,12 +573,104 @@ def run_tiled(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# config 5: 20 response layers sharing the knots (smooth.outputs.only = TRUE: gam, nnet, earth, ksvm)
+# ------------------------------------------------------------------------------------------------
+def run_batch(args):
+    """BASELINE config 5: the NA filter runs on the joined table (V73:154), so all L response layers share the knots:
+    ONE tridiagonalisation serves the L GCV searches (mb_tps_fit with L responses), then every layer gets its own
+    ensemble + TPS raster (V73:203 loop).  Multi-GPU: the layers are dealt round-robin to the ranks (the deleted
+    snowfall path of the reference parallelised exactly this loop, old/...V69.R:937-968)."""
+    import torch
+    import torch.distributed as dist
+    import machisplin_b200 as mb
+    from machisplin_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = workload(args)
+    L = cfg["L"]
+    geom, xy, krow, kcol, _, models, kept, w, wt = build_inputs(cfg, 0)
+    Y = synth.residual_field(xy, cfg["seed"], L=L)
+    mine = [r for r in range(L) if r % world == rank]
+    eng = mb.Engine(local)
+    for kv in args.param:
+        name, val = kv.split("=")
+        eng.set_param(name, int(val))
+    C = cfg["C"]
+    cov = device_covariates(geom, C, dev)
+    out = torch.empty((geom.nrow, geom.ncol), dtype=torch.float64, device=dev)
+    ens = eng.ensemble_create(geom, models, kept, w, wt, C + 2)     # same descriptors for every layer (synthetic)
+    stream = torch.cuda.current_stream().cuda_stream
+    state = {}
+
+    def step():
+        sps = eng.tps_fit(xy, Y[:, mine]) if len(mine) > 1 else [eng.tps_fit(xy, Y[:, mine[0]])]
+        for sp in sps:
+            eng.ensemble_eval_dev(ens, cov.data_ptr(), C, out.data_ptr(), spline=sp, stream=stream)
+            state["f"] = eng.gather_cells_dev(out.data_ptr(), geom.ncol, krow, kcol, stream=stream)
+        state["lam"] = [sp.lam for sp in sps]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.timing(True)
+    eng.timing_collect()
+    l0 = eng.launches
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = eng.launches - l0
+    ktimes = eng.timing_collect()
+    eng.timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        cells = geom.nrow * geom.ncol * L
+        tot = sum(v[0] for v in ktimes.values()) or 1.0
+        kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps, "share": v[0] / tot}
+                for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:12]}
+        conf = workload_config(cfg, args, "global")
+        conf["parallelism"] = f"layers{world}"
+        line = {"metric": METRIC, "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
+                "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "kernels_rank0": kern,
+                "roofline": None, "cpu_baseline": None, "layers": L, "lambda_rank0": state["lam"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.config == "c4":
         run_tiled(args)
+    elif args.config == "c5":
+        run_batch(args)
     else:
         run_b200(args)
 

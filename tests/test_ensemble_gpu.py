@@ -183,3 +183,36 @@ def test_forest_on_rough_raster(engine, case):
     got = engine.ensemble_eval(ens, rough)
     ref = cbind.ensemble_eval(models, "rb", [0.5, 0.5], 1.0, rough, geom.as_tuple())
     _cmp(got, ref, 2e-7)
+
+
+def test_fused_part5_on_ragged_windows(engine, case):
+    """The accumulator-fused grid-evaluation kernel (TPS + part 5) on windows whose size and origin are not
+    multiples of the 32 x 32 leaf box: the padded accumulator layout and the bulk-copied tiles must line up."""
+    geom, C, models, cov = case
+    kept, w, wt = synth.ensemble_weights("gnmrv")
+    xy, _, _ = synth.make_knots(geom, 300, 28)
+    y = synth.residual_field(xy, 28)
+    fit = otps.tps_fit(xy, y, lam=2e-3)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
+    surf = cbind.tps_eval(fit, geom.as_tuple())
+    ref = cbind.ensemble_eval(models, kept, w, wt, cov, geom.as_tuple(), tps=surf)
+    for win in [(0, 160, 0, 224), (7, 150, 13, 201), (64, 97, 32, 65), (159, 160, 0, 224)]:
+        got = engine.ensemble_eval(ens, cov, spline=sp, window=win)
+        _cmp(got, ref[win[0]:win[1], win[2]:win[3]], 2e-6)
+
+
+def test_tiled_mode_is_independent_of_lane_concurrency(engine, case):
+    """mltps part 3 runs its tiles on four worker lanes; the raster must be bit-identical to the one-lane order
+    (a user stream forces the sequential path)."""
+    import torch
+    geom, C, models, cov = case
+    xy, _, _ = synth.make_knots(geom, 600, 18)
+    y = synth.residual_field(xy, 18)
+    a = engine.tiles_tps(geom, xy, y, tile_px=60)
+    out = torch.empty((geom.nrow, geom.ncol), dtype=torch.float64, device="cuda:0")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        engine.tiles_tps_dev(geom, xy, y, out.data_ptr(), tile_px=60, stream=s.cuda_stream)
+    s.synchronize()
+    np.testing.assert_array_equal(a, out.cpu().numpy())

@@ -57,3 +57,20 @@ def test_tiles_merge_with_na(engine, nc, nr):
     ref = otl.tiles_merge(geom.as_tuple(), wins, rasters, nc, nr)
     got = engine.tiles_merge(geom, wins, rasters, nc, nr)
     assert relerr(got, ref) < 1e-13
+
+
+def test_tiles_merge_dev_matches_host_entry_point(engine):
+    """machisplin.tiles.merge on device-resident tiles (what the multi-GPU path calls after the NCCL tile gather)."""
+    import torch
+    from machisplin_b200 import tiles as mt
+    geom = synth.make_geom(240, 310)
+    rng = np.random.default_rng(3)
+    pts = rng.uniform([geom.xmin, geom.ymin], [geom.xmax, geom.ymax], (50, 2))
+    ts = mt.tiles_create(geom, pts, 2, 2, feather_d=30)
+    rasters = [rng.standard_normal((t.geom.nrow, t.geom.ncol)) for t in ts.tiles]
+    ref = mt.tiles_merge(engine, geom, ts, rasters)
+    dev = [torch.from_numpy(r).to("cuda:0") for r in rasters]
+    out = torch.empty((geom.nrow, geom.ncol), dtype=torch.float64, device="cuda:0")
+    engine.tiles_merge_dev(geom, [t.win for t in ts.tiles], [d.data_ptr() for d in dev], 2, 2, out.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)

@@ -191,3 +191,48 @@ def test_fit_gcv_tridiagonal_paths_agree(engine, n):
     assert np.max(np.abs(sp1.c - sp0.c)) <= 1e-7 * np.max(np.abs(sp0.c))
     np.testing.assert_allclose(sp1.decomposition()[0], sp0.decomposition()[0], rtol=1e-7,
                                atol=1e-13 * sp0.decomposition()[0].max())
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_leaf_dense_knots_overflow_near_lists(engine, mode):
+    """Many knots per leaf box (a 3 x 3 neighbourhood holds far more than the 15 inline entries of a leaf record):
+    the overflow near list, partial boxes at both window edges (97 x 161 cells) and, with mode 2, the forced
+    mixed-precision kernel."""
+    geom, xy, y, fit = _case(97, 161, 700, 41, lam=3e-3)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    engine.set_param("eval_precision", mode)
+    try:
+        got = engine.tps_eval(sp, geom, method="fast")
+        win = (5, 90, 33, 150)
+        gotw = engine.tps_eval(sp, geom, window=win, method="fast")
+    finally:
+        engine.set_param("eval_precision", 0)
+    ref = otps.tps_interpolate(fit, geom.as_tuple())
+    tol = 2e-6 if mode == 0 else TOL
+    assert relerr(got, ref) < tol
+    assert np.max(np.abs(gotw - ref[win[0]:win[1], win[2]:win[3]])) < tol * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("strip", ["x", "y"])
+def test_leaf_elongated_knot_cloud(engine, strip):
+    """Knots confined to a strip: scale.type = "range" stretches one axis, so cells are far from square in scaled
+    coordinates and the leaf boxes are 32 columns x bh rows with bh = 4 (strip along x) or ~ 107 (strip along y):
+    the generic row loop and the mirror-row collapse of k_leaf_stream for bh != 32."""
+    geom = synth.make_geom(256, 512)
+    xy, _, _ = synth.make_knots(geom, 6000, 47)
+    if strip == "x":
+        keep = (xy[:, 1] > 0.1) & (xy[:, 1] < 0.2)          # y range 0.1 of a 0.5-high raster, x range 1
+    else:
+        keep = (xy[:, 0] > 0.2) & (xy[:, 0] < 0.5)          # x range 0.3, y range 0.5
+    xy = xy[keep][:400]
+    y = synth.residual_field(xy, 47)
+    fit = otps.tps_fit(xy, y, lam=1e-3)
+    sp = engine.spline_create(fit.knots_xy, fit.c, fit.d, fit.center, fit.scale)
+    ref = otps.tps_interpolate(fit, geom.as_tuple())
+    for mode in (0, 2):
+        engine.set_param("eval_precision", mode)
+        try:
+            got = engine.tps_eval(sp, geom, method="fast")
+        finally:
+            engine.set_param("eval_precision", 0)
+        assert relerr(got, ref) < (2e-6 if mode == 0 else TOL)
