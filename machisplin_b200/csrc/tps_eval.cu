@@ -840,7 +840,12 @@ static int choose_p(const mb_ctx* ctx, const mb_spline* s) {
 template <class K>
 static int leaf_grid(mb_ctx* ctx, K kernel, size_t smem, int nboxes) {
   int occ = 0;
-  MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+  // a fixed, generous opt-in limit: the attribute is global per kernel, and the tile lanes of tiles_tps launch the
+  // same kernel concurrently with different leaf-box heights (a smaller value set by one lane would make the
+  // launch of another fail with "invalid argument")
+  constexpr size_t kLeafSmemLimit = 200 * 1024;
+  if (smem > kLeafSmemLimit) throw Error(MB_E_UNSUPPORTED, "leaf kernel: leaf box too tall for shared memory");
+  MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmemLimit));
   MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kLeafThreads, smem));
   if (occ < 1) throw Error(MB_E_UNSUPPORTED, "leaf kernel does not fit on an SM (leaf box too tall)");
   return std::max(1, std::min(nboxes, occ * ctx->sm_count));

@@ -74,3 +74,21 @@ def test_tiles_merge_dev_matches_host_entry_point(engine):
     engine.tiles_merge_dev(geom, [t.win for t in ts.tiles], [d.data_ptr() for d in dev], 2, 2, out.data_ptr())
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+def test_tiled_surface_with_heterogeneous_tiles(engine):
+    """Tiles whose knot clouds have very different aspect ratios get different leaf-box heights (hence different
+    shared-memory footprints of the grid-evaluation kernel) while they run concurrently on the tile lanes."""
+    geom = synth.make_geom(300, 420)
+    rng = np.random.default_rng(91)
+    xy_all, _, _ = synth.make_knots(geom, 9000, 91)
+    third = (geom.xmax - geom.xmin) / 3
+    left = xy_all[(xy_all[:, 0] < third) & (np.abs(xy_all[:, 1] % 0.18 - 0.09) < 0.012)][:260]      # thin horizontal bands
+    mid = xy_all[(xy_all[:, 0] >= third) & (xy_all[:, 0] < 2 * third)][:300]                        # isotropic
+    right = xy_all[(xy_all[:, 0] >= 2 * third) & (np.abs(xy_all[:, 0] - 2.5 * third) < 0.02)][:260]  # thin vertical band
+    xy = np.vstack([left, mid, right])
+    y = synth.residual_field(xy, 91)
+    ref = otl.tps_tiled_surface(geom.as_tuple(), xy, y, tile_px=150, lam=2e-3)
+    for _ in range(3):                                     # the lanes race differently every time
+        got = engine.tiles_tps(geom, xy, y, tile_px=150, lam=2e-3)
+        assert relerr(got, ref) < 2e-6
