@@ -299,11 +299,15 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
     else tps_eval_fast(c, sp, g, kw, bufs[t], kw.c1 - kw.c0, cs);
     MB_CUDA(cudaStreamSynchronize(cs));
   };
-  // Tiles are independent: four worker lanes (own stream + scratch arena) keep the device busy while one lane sits
-  // in a host synchronisation of its fit.  Only for small fits: their persistent kernels use small grids, so
+  // Tiles are independent: up to eight worker lanes (own stream + scratch arena) keep the device busy while one lane
+  // sits in a host synchronisation of its fit.  Only for small fits: their persistent kernels use small grids, so
   // several are co-resident; a large fit takes the whole device and runs alone.
-  constexpr int kLanes = 4;
-  const bool concurrent = nt >= 2 && m_max <= 1200 && ctx->eigen_impl == 0 && st == ctx->stream;
+  // lanes: as many as keep every fit's persistent grid co-resident (the grid of k_sytrd follows the matrix size:
+  // row chunks of 32, strip segments of 4 tiles; 2 CTAs per SM fit on the device)
+  const int nchunk_max = (m_max + 31) / 32, ntile_max = (m_max + 63) / 64;
+  const int g_est = std::max(8, std::max(nchunk_max, (ntile_max / 4 + 1) * (2 * (ntile_max / 4) + ntile_max % 4)));
+  const int kLanes = std::max(1, std::min(std::min(8, nt), (2 * ctx->sm_count) / g_est));
+  const bool concurrent = kLanes >= 2 && ctx->eigen_impl == 0 && st == ctx->stream;
   if (!concurrent) {
     for (int t = 0; t < nt; ++t) run_tile(ctx, st, t);
   } else {
