@@ -1,5 +1,5 @@
-// Device-side pieces shared by ensemble.cu (k_ens_final, k_ens_points) and tps_eval.cu (the fused
-// per-cell kernel): grid geometry, the float64 "smooth" models g / n / m, and the fusion descriptor.
+// Device-side pieces of ensemble.cu (k_ens_svm, k_ens_smooth, k_ens_points): grid geometry and the float64
+// "smooth" models g / n / m.  (Part 5 is fused into the grid-evaluation kernel through AccFuse, common.cuh.)
 #pragma once
 #include "common.cuh"
 
@@ -54,16 +54,5 @@ __device__ __forceinline__ double smooth_models(const double* x, int P, const Sm
   }
   return s;
 }
-
-// What the fused per-cell kernel needs to finish mltps part 2 + part 5 in the same pass as the TPS
-// surface: pred = (acc + smooth) / w_total (+ NA rule), final = pred + TPS  (V73:619, 906-907).
-struct EnsFuse {
-  const float* cov;     // C planes of the full grid
-  int C;
-  int64_t plane;
-  EnsGeom eg;
-  SmoothParams sp;
-  const double* acc;    // trees + svm accumulator of the window (row-major, window stride) or NULL
-};
 
 }  // namespace mb

@@ -869,8 +869,6 @@ static EnsGeom ens_geom(const mb_grid& g) {
   return EnsGeom{g.xmin, g.ymax, (g.xmax - g.xmin) / g.ncol, (g.ymax - g.ymin) / g.nrow, g.nrow, g.ncol};
 }
 
-bool ensemble_has_heavy(const mb_ensemble* e) { return e->has[MB_R] || e->has[MB_B] || e->has[MB_V]; }
-
 // acc <- sum_k round(w_k, 2) f_k(cell) over EVERY kept model for window w, in the padded accumulator layout
 // (acc_stride(w) x acc_rows(w) doubles); NaN where a covariate is NA (except a gbm-only ensemble, which
 // follows MissingNode).  Chain: trees -> svm (+ smooth models) | smooth; the last kernel applies the NA rule.

@@ -20,7 +20,6 @@ mb_grid ensemble_grid(const mb_ensemble* e);
 void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_spline* spline,
                    const double* tps_surface_dev, const mb_window* w, double* out_dev, cudaStream_t st);
 // the two halves of ensemble_eval, exposed so that mltps_predict can run the TPS fit between them
-bool ensemble_has_heavy(const mb_ensemble* e);
 int ensemble_ncov(const mb_ensemble* e);
 // acc: padded accumulator layout (AccFuse, common.cuh): acc_stride(w) * acc_rows(w) doubles
 void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_window& w,
