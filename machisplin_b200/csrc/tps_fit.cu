@@ -145,16 +145,20 @@ __global__ void k_add_diag(double* A, int ld, int m, double lam) {
   if (i < m) A[(size_t)i * ld + i] += lam;
 }
 
-// factor the kb x kb diagonal block in shared memory (256 threads: thread = (row, column slice) of the rank-1
-// update); info = 1 + failing column if not SPD
+// Factor the kb x kb diagonal block in shared memory (256 threads: thread = (row, column slice) of the rank-1
+// update) and leave its inverse in `inv` (64 x 64, row-major, zero above the diagonal): the panel solve and the
+// substitution sweeps then are plain matrix products.  info = 1 + failing column if not SPD.
 __global__ void __launch_bounds__(256) k_potrf_diag(double* __restrict__ A, int ld, int kb, int col0,
-                                                    int* __restrict__ info) {
-  __shared__ double s[kNB][kNB + 1];
-  __shared__ int s_bad;
+                                                    double* __restrict__ inv, int* __restrict__ info) {
+  extern __shared__ __align__(16) double potrf_smem[];
+  double (*s)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(potrf_smem);
+  double (*sx)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(potrf_smem + kNB * (kNB + 1));   // inverse, built row by row
+  double (*sp)[kNB] = reinterpret_cast<double (*)[kNB]>(potrf_smem + 2 * kNB * (kNB + 1));
   const int t = threadIdx.x & 63, cq = threadIdx.x >> 6;
-  if (threadIdx.x == 0) s_bad = 0;
-  for (int j = cq; j < kb; j += 4)
-    if (t < kb) s[t][j] = A[(size_t)j * ld + t];
+  for (int j = cq; j < kNB; j += 4) {
+    s[t][j] = (t < kb && j < kb) ? A[(size_t)j * ld + t] : (t == j ? 1.0 : 0.0);   // identity padding
+    sx[t][j] = 0.0;
+  }
   __syncthreads();
   for (int j = 0; j < kb; ++j) {
     const double djj = s[j][j];
@@ -162,52 +166,72 @@ __global__ void __launch_bounds__(256) k_potrf_diag(double* __restrict__ A, int 
       if (threadIdx.x == 0 && *info == 0) *info = col0 + j + 1;
       return;                                   // uniform: every thread reads the same s[j][j]
     }
-    const double rl = 1.0 / sqrt(djj);
+    const double rl = rsqrt(djj);
     __syncthreads();                            // everyone has read the pivot
     if (cq == 0) {
-      if (t == j) s[j][j] = sqrt(djj);
+      if (t == j) s[j][j] = djj * rl;
       else if (t > j && t < kb) s[t][j] *= rl;
     }
     __syncthreads();
     if (t > j && t < kb) {
       const double ltj = s[t][j];
-      for (int c = j + 1 + cq; c <= t; c += 4) s[t][c] = fma(-ltj, s[c][j], s[t][c]);
+      int c = j + 1 + cq;
+      for (; c + 12 <= t; c += 16) {            // four independent updates in flight
+        const double u0 = s[c][j], u1 = s[c + 4][j], u2 = s[c + 8][j], u3 = s[c + 12][j];
+        const double v0 = s[t][c], v1 = s[t][c + 4], v2 = s[t][c + 8], v3 = s[t][c + 12];
+        s[t][c] = fma(-ltj, u0, v0); s[t][c + 4] = fma(-ltj, u1, v1);
+        s[t][c + 8] = fma(-ltj, u2, v2); s[t][c + 12] = fma(-ltj, u3, v3);
+      }
+      for (; c <= t; c += 4) s[t][c] = fma(-ltj, s[c][j], s[t][c]);
     }
     __syncthreads();                            // the next pivot is final
   }
+  // inverse: column c of X = L^-1 by forward substitution, the sum over k split over the 4 slices of a column
+  // X[r][c] = (delta_rc - sum_{k=c}^{r-1} L[r][k] X[k][c]) / L[r][r]; rows are processed in lock step (one barrier each)
+  for (int r = 0; r < kNB; ++r) {
+    double part = 0.0;
+    if (t <= r)                                   // t = column c of X
+      for (int k = t + cq; k < r; k += 4) part = fma(s[r][k], sx[k][t], part);
+    sp[cq][t] = part;
+    __syncthreads();
+    if (cq == 0 && t <= r) {
+      const double sum = sp[0][t] + sp[1][t] + sp[2][t] + sp[3][t];
+      sx[r][t] = ((t == r ? 1.0 : 0.0) - sum) / s[r][r];
+    }
+    __syncthreads();
+  }
   for (int j = cq; j < kb; j += 4)
     if (t < kb) A[(size_t)j * ld + t] = (t >= j) ? s[t][j] : 0.0;
+  for (int j = cq; j < kNB; j += 4) inv[(size_t)t * kNB + j] = sx[t][j];
 }
 
-// rows below the diagonal block: X L11' = A21.  One thread per row, x[64] in registers, column-oriented
-// substitution (after x_c is final it is eliminated from every later column: independent FMAs, fully unrolled).
-// Right-hand sides ride along as extra rows of the panel (forward substitution for free).
-__global__ void __launch_bounds__(64, 1) k_trsm_panel(const double* __restrict__ L11, double* __restrict__ A21, int ld,
-                                                   int kb, int nrows) {
-  __shared__ double s[kNB][kNB + 1];            // s[j][c] = L11[j][c], diagonal replaced by its reciprocal
-  for (int idx = threadIdx.x; idx < kNB * kNB; idx += blockDim.x) {
-    const int r = idx % kNB, c = idx / kNB;
-    double v = 0.0;
-    if (r < kb && c < kb) v = L11[(size_t)c * ld + r];
-    if (r == c) v = (r < kb) ? 1.0 / v : 1.0;
-    s[r][c] = v;
-  }
+// rows below the diagonal block: X = A21 L11^-T = A21 inv', one thread per row with the row in registers and four
+// independent dot products in flight; right-hand sides ride along as extra rows.
+__global__ void __launch_bounds__(128) k_trsm_panel(const double* __restrict__ inv, double* __restrict__ A21, int ld,
+                                                    int kb, int nrows) {
+  __shared__ double s[kNB][kNB + 1];            // s[j][c] = inv[j][c]
+  for (int idx = threadIdx.x; idx < kNB * kNB; idx += blockDim.x) s[idx / kNB][idx % kNB] = inv[idx];
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows) return;
-  double x[kNB];
+  double a[kNB];
 #pragma unroll
-  for (int j = 0; j < kNB; ++j) x[j] = (j < kb) ? A21[(size_t)j * ld + i] : 0.0;
+  for (int c = 0; c < kNB; ++c) a[c] = (c < kb) ? A21[(size_t)c * ld + i] : 0.0;
 #pragma unroll
-  for (int c = 0; c < kNB; ++c) {
-    const double xc = x[c] * s[c][c];
-    x[c] = xc;
+  for (int j0 = 0; j0 < kNB; j0 += 4) {
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
 #pragma unroll
-    for (int j = c + 1; j < kNB; ++j) x[j] = fma(-xc, s[j][c], x[j]);
+    for (int c = 0; c < j0 + 4; ++c) {          // inv is lower triangular: columns c <= j
+      x0 = fma(a[c], s[j0][c], x0);
+      x1 = fma(a[c], s[j0 + 1][c], x1);
+      x2 = fma(a[c], s[j0 + 2][c], x2);
+      x3 = fma(a[c], s[j0 + 3][c], x3);
+    }
+    if (j0 < kb) A21[(size_t)j0 * ld + i] = x0;
+    if (j0 + 1 < kb) A21[(size_t)(j0 + 1) * ld + i] = x1;
+    if (j0 + 2 < kb) A21[(size_t)(j0 + 2) * ld + i] = x2;
+    if (j0 + 3 < kb) A21[(size_t)(j0 + 3) * ld + i] = x3;
   }
-#pragma unroll
-  for (int j = 0; j < kNB; ++j)
-    if (j < kb) A21[(size_t)j * ld + i] = x[j];
 }
 
 // trailing update on the FP64 tensor pipe:  C(lower tiles) -= P P',  P = panel (n x kb, column-major ld)
@@ -265,39 +289,28 @@ __global__ void __launch_bounds__(256) k_syrk_dmma(const double* __restrict__ Pn
 // element within a launch.
 template <bool kBackward>
 __global__ void __launch_bounds__(256) k_chol_sweep(const double* __restrict__ Lm, int ld, int m, int k0, int kb,
-                                                    double* __restrict__ B, double* __restrict__ out, int ldb,
-                                                    int nrhs) {
-  __shared__ double s_L[kNB][kNB + 1];
-  __shared__ double s_x[kNB];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
-    const int i = idx % kb, j = idx / kb;
-    s_L[i][j] = Lm[(size_t)(k0 + j) * ld + k0 + i];
-  }
+                                                    const double* __restrict__ inv, double* __restrict__ B,
+                                                    double* __restrict__ out, int ldb, int nrhs) {
+  __shared__ double s_I[kNB][kNB + 1];          // inverse of the diagonal block (row-major, lower triangular)
+  __shared__ double s_b[kNB], s_x[kNB];
+  for (int idx = threadIdx.x; idx < kNB * kNB; idx += blockDim.x) s_I[idx / kNB][idx % kNB] = inv[idx];
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   for (int r = 0; r < nrhs; ++r) {
     double* b = B + (size_t)r * ldb;
     __syncthreads();
-    if (threadIdx.x < kb) s_x[threadIdx.x] = b[k0 + threadIdx.x];
+    if (threadIdx.x < kNB) s_b[threadIdx.x] = threadIdx.x < kb ? b[k0 + threadIdx.x] : 0.0;
     __syncthreads();
-    if (warp == 0) {
-      if (!kBackward) {
-        for (int j = 0; j < kb; ++j) {
-          const double v = s_x[j] / s_L[j][j];
-          __syncwarp();
-          if (lane == 0) s_x[j] = v;
-          for (int i = j + 1 + lane; i < kb; i += 32) s_x[i] -= v * s_L[i][j];
-          __syncwarp();
-        }
-      } else {
-        for (int j = kb - 1; j >= 0; --j) {
-          const double v = s_x[j] / s_L[j][j];
-          __syncwarp();
-          if (lane == 0) s_x[j] = v;
-          for (int i = lane; i < j; i += 32) s_x[i] -= v * s_L[j][i];
-          __syncwarp();
-        }
+    if (threadIdx.x < kNB) {
+      const int j = threadIdx.x;
+      double a0 = 0.0, a1 = 0.0;
+      if (!kBackward) {                         // y = L^-1 b
+        for (int c = 0; c + 1 <= j; c += 2) { a0 = fma(s_I[j][c], s_b[c], a0); a1 = fma(s_I[j][c + 1], s_b[c + 1], a1); }
+        if (!(j & 1)) a0 = fma(s_I[j][j], s_b[j], a0);
+      } else {                                  // x = L^-T y
+        for (int c = j; c + 1 < kNB; c += 2) { a0 = fma(s_I[c][j], s_b[c], a0); a1 = fma(s_I[c + 1][j], s_b[c + 1], a1); }
+        if ((kNB - j) & 1) a0 = fma(s_I[kNB - 1][j], s_b[kNB - 1], a0);
       }
+      s_x[j] = a0 + a1;
     }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x < kb) out[(size_t)r * ldb + k0 + threadIdx.x] = s_x[threadIdx.x];
@@ -324,34 +337,39 @@ __global__ void __launch_bounds__(256) k_chol_sweep(const double* __restrict__ L
 
 // x <- (L L')^-1 b for nrhs right-hand sides: B (m x nrhs, ldb) is overwritten with the solution; tmp is
 // scratch of the same shape.
-static void cholesky_solve(mb_ctx* ctx, const double* Lm, int ld, int m, double* B, double* tmp, int ldb, int nrhs,
-                           cudaStream_t st) {
+static void cholesky_solve(mb_ctx* ctx, const double* Lm, int ld, int m, const double* inv, double* B, double* tmp,
+                           int ldb, int nrhs, cudaStream_t st) {
   for (int k0 = 0; k0 < m; k0 += kNB) {          // L y = b : y -> tmp
     const int kb = std::min(kNB, m - k0);
     const int rest = m - k0 - kb;
-    MB_LAUNCH(ctx, "k_chol_sweep", st) k_chol_sweep<false><<<std::max(1, (rest + 255) / 256), 256, 0, st>>>(Lm, ld, m, k0, kb, B, tmp, ldb, nrhs);
+    MB_LAUNCH(ctx, "k_chol_sweep", st) k_chol_sweep<false><<<std::max(1, (rest + 255) / 256), 256, 0, st>>>(Lm, ld, m, k0, kb, inv + (size_t)(k0 / kNB) * kNB * kNB, B, tmp, ldb, nrhs);
   }
   for (int k1 = m; k1 > 0;) {                    // L' x = y : x -> B
     const int k0 = ((k1 - 1) / kNB) * kNB;
     const int kb = k1 - k0;
-    MB_LAUNCH(ctx, "k_chol_sweep", st) k_chol_sweep<true><<<std::max(1, (k0 + 255) / 256), 256, 0, st>>>(Lm, ld, m, k0, kb, tmp, B, ldb, nrhs);
+    MB_LAUNCH(ctx, "k_chol_sweep", st) k_chol_sweep<true><<<std::max(1, (k0 + 255) / 256), 256, 0, st>>>(Lm, ld, m, k0, kb, inv + (size_t)(k0 / kNB) * kNB * kNB, tmp, B, ldb, nrhs);
     k1 = k0;
   }
   MB_CUDA(cudaGetLastError());
 }
 
-static void cholesky_lower(mb_ctx* ctx, double* A, int ld, int m, cudaStream_t st) {
+// returns the inverses of the 64 x 64 diagonal blocks of L (block k at + k 64 64), for cholesky_solve
+static const double* cholesky_lower(mb_ctx* ctx, double* A, int ld, int m, cudaStream_t st) {
   constexpr size_t kSyrkSmem = 2 * kNB * (kNB + 4) * sizeof(double);
+  constexpr size_t kPotrfSmem = (2 * kNB * (kNB + 1) + 4 * kNB) * sizeof(double);
   MB_CUDA(cudaFuncSetAttribute(k_syrk_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
+  MB_CUDA(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
   ABuf<int> d_info(ctx->arena, 1);
+  double* d_inv = ctx->arena.take_n<double>((size_t)((m + kNB - 1) / kNB) * kNB * kNB);
   MB_CUDA(cudaMemsetAsync(d_info.p, 0, sizeof(int), st));
   for (int k = 0; k < m; k += kNB) {
     const int kb = std::min(kNB, m - k);
     double* Akk = A + (size_t)k * ld + k;
-    MB_LAUNCH(ctx, "k_potrf_diag", st) k_potrf_diag<<<1, 256, 0, st>>>(Akk, ld, kb, k, d_info.p);
+    double* invk = d_inv + (size_t)(k / kNB) * kNB * kNB;
+    MB_LAUNCH(ctx, "k_potrf_diag", st) k_potrf_diag<<<1, 256, kPotrfSmem, st>>>(Akk, ld, kb, k, invk, d_info.p);
     const int rest = m - k - kb;
     if (rest > 0) {
-      MB_LAUNCH(ctx, "k_trsm_panel", st) k_trsm_panel<<<(rest + 63) / 64, 64, 0, st>>>(Akk, Akk + kb, ld, kb, rest);
+      MB_LAUNCH(ctx, "k_trsm_panel", st) k_trsm_panel<<<(rest + 127) / 128, 128, 0, st>>>(invk, Akk + kb, ld, kb, rest);
       const int nt = (rest + kNB - 1) / kNB;
       MB_LAUNCH(ctx, "k_syrk_dmma", st) k_syrk_dmma<<<dim3(nt, nt), 256, kSyrkSmem, st>>>(Akk + kb, A + (size_t)(k + kb) * ld + (k + kb), ld, rest, kb);
     }
@@ -362,6 +380,7 @@ static void cholesky_lower(mb_ctx* ctx, double* A, int ld, int m, cudaStream_t s
   MB_CUDA(cudaGetLastError());
   if (info != 0)
     throw Error(MB_E_NUMERIC, "Cholesky: Q2'KQ2 + lambda I is not positive definite at column " + std::to_string(info));
+  return d_inv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -754,9 +773,9 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
       for (int r = 0; r < L; ++r) {
         MB_CUDA(cudaMemcpyAsync(d_T.p, M, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToDevice, st));
         MB_LAUNCH(ctx, "k_add_diag", st) k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(d_T.p, m, m, lam[r]);
-        cholesky_lower(ctx, d_T.p, m, m, st);
+        const double* d_inv = cholesky_lower(ctx, d_T.p, m, m, st);
         MB_CUDA(cudaMemcpyAsync(d_B.p, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
-        cholesky_solve(ctx, d_T.p, m, m, d_B.p, d_tmp.p, m, 1, st);
+        cholesky_solve(ctx, d_T.p, m, m, d_inv, d_B.p, d_tmp.p, m, 1, st);
         MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
       }
@@ -805,12 +824,12 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
   } else {
     // ---- fixed lambda: (M + lambda I) beta = z by tensor-core Cholesky ------------------------------
     MB_LAUNCH(ctx, "k_add_diag", st) k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(M, m, m, lambda);
-    cholesky_lower(ctx, M, m, m, st);
+    const double* d_inv = cholesky_lower(ctx, M, m, m, st);
     ABuf<double> d_B(ar, (size_t)m * L);
     for (int r = 0; r < L; ++r)
       MB_CUDA(cudaMemcpyAsync(d_B.p + (size_t)r * m, z[r].data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
     ABuf<double> d_tmp(ar, (size_t)m * L);
-    cholesky_solve(ctx, M, m, m, d_B.p, d_tmp.p, m, L, st);
+    cholesky_solve(ctx, M, m, m, d_inv, d_B.p, d_tmp.p, m, L, st);
     for (int r = 0; r < L; ++r)
       MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p + (size_t)r * m, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
