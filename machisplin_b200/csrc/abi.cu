@@ -142,6 +142,9 @@ int mb_debug_values(mb_ctx* ctx, const char* name, double* out, int cap) {
     MB_REQUIRE(ctx && name && out, "NULL argument");
     if (std::string(name) == "sytrd_phase_ms") {
       for (; n < 8 && n < cap; ++n) out[n] = ctx->sytrd_prof_ms[n];
+    } else if (std::string(name) == "sbr_band") {
+      // 64 x m band storage after stage 1 of the two-stage tridiagonalisation (B[off + 64 j] = A[j + off, j])
+      for (; n < (int)ctx->dbg_band.size() && n < cap; ++n) out[n] = ctx->dbg_band[n];
     } else {
       throw Error(MB_E_ARG, std::string("unknown debug vector '") + name + "'");
     }
@@ -160,8 +163,12 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value == 0 || value == 1, "eigen_impl must be 0 (in-house) or 1 (cuSOLVER, validation)");
       ctx->eigen_impl = value;
     } else if (n == "sytrd_mode") {
-      MB_REQUIRE(value >= 0 && value <= 2, "sytrd_mode must be 0 / 1 (persistent kernel) or 2 (kernel per phase)");
+      MB_REQUIRE(value >= 0 && value <= 3,
+                 "sytrd_mode must be 0 / 1 (persistent kernel), 2 (kernel per phase) or 3 (two-stage band reduction)");
       ctx->sytrd_mode = value;
+    } else if (n == "sbr_debug") {
+      MB_REQUIRE(value == 0 || value == 1, "sbr_debug must be 0 or 1");
+      ctx->sbr_debug = value;
     } else if (n == "sytrd_ctas_per_sm") {
       MB_REQUIRE(value >= 0 && value <= 4, "sytrd_ctas_per_sm must be in [0, 4]");
       ctx->sytrd_ctas_per_sm = value;

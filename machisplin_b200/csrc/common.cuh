@@ -163,7 +163,10 @@ struct mb_ctx {
   mb::DevBuf<double2> logtab;
   int eval_precision = 0;     // fast evaluator: 0 = automatic, 1 = float64 only, 2 = force mixed
   int eigen_impl = 0;         // GCV fit: 0 = in-house tridiagonalisation + bisection, 1 = cuSOLVER Dsyevd (validation)
-  int sytrd_mode = 0;         // tridiagonalisation: 0 / 1 = persistent kernel with grid barrier, 2 = one kernel per phase
+  int sytrd_mode = 0;         // tridiagonalisation: 0 / 1 = persistent kernel with grid barrier, 2 = one kernel per phase,
+                              // 3 = two-stage (band reduction + bulge chasing, sbr.cu)
+  int sbr_debug = 0;          // two-stage path: keep the band matrix of stage 1 for mb_debug_values("sbr_band")
+  std::vector<double> dbg_band;
   int sytrd_ctas_per_sm = 0;  // persistent grid size (0 = 2 per SM)
   double sytrd_prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per-phase time of the last k_sytrd launch (timing on)
   // scratch reused across calls

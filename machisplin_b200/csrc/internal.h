@@ -12,6 +12,10 @@ void fit_release(mb_ctx* ctx);   // library handles owned on behalf of the conte
 void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L, std::vector<double>& diag,
                      std::vector<double>& off, std::vector<double>& eta, cudaStream_t st);
 
+// sbr.cu - two-stage alternative (dense -> band -> tridiagonal), mb_set_param("sytrd_mode", 3); d, e on the device
+void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L, double* d_dev, double* e_dev,
+                      cudaStream_t st);
+
 // ensemble.cu - terra::predict x6 + weighted sum (V73:468-619) + part-5 combine (V73:906-907)
 mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, const char* kept, const double* w,
                              double w_total);
