@@ -166,6 +166,9 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 3,
                  "sytrd_mode must be 0 / 1 (persistent kernel), 2 (kernel per phase) or 3 (two-stage band reduction)");
       ctx->sytrd_mode = value;
+    } else if (n == "sbr_qr_grid") {
+      MB_REQUIRE(value == 0 || value == 1, "sbr_qr_grid must be 0 or 1");
+      ctx->sbr_qr_grid = value;
     } else if (n == "sbr_debug") {
       MB_REQUIRE(value == 0 || value == 1, "sbr_debug must be 0 or 1");
       ctx->sbr_debug = value;

@@ -167,6 +167,7 @@ struct mb_ctx {
                               // 3 = two-stage (band reduction + bulge chasing, sbr.cu)
   int sbr_debug = 0;          // two-stage path: keep the band matrix of stage 1 for mb_debug_values("sbr_band")
   std::vector<double> dbg_band;
+  int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits
   int sytrd_ctas_per_sm = 0;  // persistent grid size (0 = 2 per SM)
   double sytrd_prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per-phase time of the last k_sytrd launch (timing on)
   // scratch reused across calls

@@ -17,10 +17,14 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 
 namespace mb {
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -90,11 +94,16 @@ struct QrArgs {
   double* A; int ld; int m; int j0;
   double* V; int ldv;              // ldv x 32, column-major; row 0 = matrix row j0 + kBw; rows >= r are written as zero
   double* T;                       // 32 x 32, row-major, upper triangular
-  double* slots;                   // 2 x (G + 1) x 32: per-CTA partial sums (+ the pivot row), double-buffered by column parity
-  unsigned* bar;
+  double* slots;                   // grid version: 2 x (G + 1) x 32 per-CTA partial sums (+ the pivot row), by column parity
+  unsigned* bar;                   // grid version: barrier words
 };
-constexpr size_t kQrSmem = sizeof(double) * (kQrRows * kPad + 16 * 32 + 32 + 32 + 32 * kPad);
+// X | red | s | piv | T | part (cluster version: [parity][partial sums 32 | pivot row 32], read by the peers over DSMEM)
+constexpr size_t kQrSmem = sizeof(double) * (kQrRows * kPad + 16 * 32 + 32 + 32 + 32 * kPad + 2 * 64);
 
+// kCluster: the CTAs form ONE thread-block cluster; the per-column reduction goes through distributed shared memory and the
+// hardware cluster barrier.  Otherwise (more than 16 x 512 rows, or no cluster of that size schedulable): global slots and the
+// software grid barrier (cooperative launch).
+template <bool kCluster>
 __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
   extern __shared__ double sm_qr[];
   double* X = sm_qr;                      // [512][33]   row t = this thread's row of the panel
@@ -102,6 +111,8 @@ __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
   double* s_sh = red + 16 * 32;           // [32]
   double* piv_sh = s_sh + 32;             // [32]
   double* Tsh = piv_sh + 32;              // [32][33]
+  double* part = Tsh + 32 * kPad;         // [2][64]
+  cg::cluster_group cluster = cg::this_cluster();
   const int t = threadIdx.x, blk = blockIdx.x, G = gridDim.x;
   const int r = a.m - a.j0 - kBw;
   const int gi = blk * kQrRows + t;
@@ -115,29 +126,50 @@ __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
   const int c = t & 31, seg = t >> 5;
   for (int j = 0; j < nref; ++j) {
     // ---- s_c = sum over rows i > j of x_i[j] x_i[c] ----------------------------------------------------
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
     const int rbase = seg * 32;
+    const int first = j + 1 - blk * kQrRows;        // local rows >= first take part
 #pragma unroll 8
-    for (int rr = 0; rr < 32; ++rr) {
+    for (int rr = 0; rr < 32; rr += 2) {
       const int rw = rbase + rr;
-      if (blk * kQrRows + rw > j) acc = fma(X[rw * kPad + j], X[rw * kPad + c], acc);
+      const double a0 = X[rw * kPad + j] * X[rw * kPad + c], a1 = X[(rw + 1) * kPad + j] * X[(rw + 1) * kPad + c];
+      if (rw >= first) acc0 += a0;
+      if (rw + 1 >= first) acc1 += a1;
     }
-    red[seg * 32 + c] = acc;
+    red[seg * 32 + c] = acc0 + acc1;
     __syncthreads();
-    double* slot = a.slots + (size_t)(j & 1) * (G + 1) * 32;
-    if (t < 32) {
-      double p = 0.0;
+    if (kCluster) {
+      double* mine = part + (j & 1) * 64;
+      if (t < 32) {
+        double p = 0.0;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) p += red[q * 32 + t];
-      slot[blk * 32 + t] = p;
-      if (blk == 0) slot[G * 32 + t] = X[j * kPad + t];     // the pivot row
-    }
-    sbr_grid_sync(a.bar, gen);
-    if (t < 32) {
-      double s = 0.0;
-      for (int q = 0; q < G; ++q) s += __ldcg(slot + q * 32 + t);
-      s_sh[t] = s;
-      piv_sh[t] = __ldcg(slot + G * 32 + t);
+        for (int q = 0; q < 16; ++q) p += red[q * 32 + t];
+        mine[t] = p;
+        if (blk == 0) mine[32 + t] = X[j * kPad + t];          // the pivot row
+      }
+      cluster.sync();
+      if (t < 32) {
+        double s = 0.0;
+        for (int q = 0; q < G; ++q) s += cluster.map_shared_rank(mine, q)[t];
+        s_sh[t] = s;
+        piv_sh[t] = cluster.map_shared_rank(mine, 0)[32 + t];
+      }
+    } else {
+      double* slot = a.slots + (size_t)(j & 1) * (G + 1) * 32;
+      if (t < 32) {
+        double p = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) p += red[q * 32 + t];
+        slot[blk * 32 + t] = p;
+        if (blk == 0) slot[G * 32 + t] = X[j * kPad + t];
+      }
+      sbr_grid_sync(a.bar, gen);
+      if (t < 32) {
+        double s = 0.0;
+        for (int q = 0; q < G; ++q) s += __ldcg(slot + q * 32 + t);
+        s_sh[t] = s;
+        piv_sh[t] = __ldcg(slot + G * 32 + t);
+      }
     }
     __syncthreads();
     const double alpha = piv_sh[j];
@@ -180,10 +212,12 @@ __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
     for (int cc = t; cc < 32; ++cc) a.A[row + (size_t)(a.j0 + cc) * a.ld] = X[t * kPad + cc];
   if (blk == 0)
     for (int i = t; i < 1024; i += kQrRows) a.T[i] = Tsh[(i >> 5) * kPad + (i & 31)];
+  if (kCluster) cluster.sync();           // nobody leaves while a peer may still read its partial sums
 }
 
 // ---------------------------------------------------------------------------------------------
-// Z0 = A22 V : CTA = 128 rows x 32 columns over the k range [sp * chunk, (sp + 1) * chunk); thread = 8 x 4 outputs
+// Z0 = A22 V : CTA = 128 rows x 32 columns over the k range [sp * chunk, (sp + 1) * chunk); thread = 8 x 4 outputs;
+// the next 16-column slab of A22 and V travels in registers while the current one is multiplied
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_sbr_av(const double* __restrict__ A22, int ld, int r, const double* __restrict__ V,
                                                 int ldv, double* __restrict__ Zp, int chunk) {
@@ -198,19 +232,31 @@ __global__ void __launch_bounds__(128) k_sbr_av(const double* __restrict__ A22, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   const int gi = I + t;
-  for (int kb = k0; kb < k1; kb += 16) {
+  double pa[16], pv[4];
+  auto fetch = [&](int kb) {
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       const int k = kb + kk;
-      As[kk][t] = (gi < r && k < k1) ? __ldg(A22 + gi + (size_t)k * ld) : 0.0;
+      pa[kk] = (gi < r && k < k1) ? __ldg(A22 + gi + (size_t)k * ld) : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int idx = t + 128 * q, kk = idx & 15, cc = idx >> 4;
       const int k = kb + kk;
-      Vs[kk][cc] = k < k1 ? __ldg(V + k + (size_t)cc * ldv) : 0.0;
+      pv[q] = k < k1 ? __ldg(V + k + (size_t)cc * ldv) : 0.0;
+    }
+  };
+  fetch(k0);
+  for (int kb = k0; kb < k1; kb += 16) {
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) As[kk][t] = pa[kk];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = t + 128 * q;
+      Vs[idx & 15][idx >> 4] = pv[q];
     }
     __syncthreads();
+    if (kb + 16 < k1) fetch(kb + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       double av[8], vv[4];
@@ -240,20 +286,26 @@ __global__ void __launch_bounds__(128) k_sbr_av(const double* __restrict__ A22, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Z0 = sum of the k-split partials; per-CTA partial of G0 = V'Z0 (32 x 32) and gz = V'z (32 x L)
+// Z0 = sum of the k-split partials; per-CTA partial of G0 = V'Z0 (32 x 32) and gz = V'z (32 x L).  CTA = 128 rows in two
+// halves of 64; thread = (row of G, two columns).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sbr_vtz(const double* __restrict__ V, int ldv, int r, const double* __restrict__ Zp,
+constexpr size_t kVtzSmem = sizeof(double) * 3 * 64 * kPad;
+
+__global__ void __launch_bounds__(512) k_sbr_vtz(const double* __restrict__ V, int ldv, int r, const double* __restrict__ Zp,
                                                  int nsplit, double* __restrict__ Z0, const double* __restrict__ z, int ldz,
                                                  int zrow0, int L, double* __restrict__ Gp) {
-  __shared__ double Vs[32][kPad], Zs[32][kPad], zs[32][kPad];
+  extern __shared__ double sm_vtz[];
+  double (*Vs)[kPad] = reinterpret_cast<double (*)[kPad]>(sm_vtz);
+  double (*Zs)[kPad] = reinterpret_cast<double (*)[kPad]>(sm_vtz + 64 * kPad);
+  double (*zs)[kPad] = reinterpret_cast<double (*)[kPad]>(sm_vtz + 2 * 64 * kPad);
   const int t = threadIdx.x, I = blockIdx.x * 128;
-  const int a = t & 31, bq = t >> 5;            // outputs G[a][bq*4 + x]
-  double g[4] = {0.0, 0.0, 0.0, 0.0}, gz[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int h = 0; h < 4; ++h) {
-    const int R0 = I + h * 32;
+  const int a = t & 31, bq = t >> 5;            // outputs G[a][bq*2 + x]
+  double g[2] = {0.0, 0.0}, gz[2] = {0.0, 0.0};
+  for (int h = 0; h < 2; ++h) {
+    const int R0 = I + h * 64;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int idx = t + 256 * q, rw = idx & 31, col = idx >> 5;
+      const int idx = t + 512 * q, rw = idx & 63, col = idx >> 6;
       const int gi = R0 + rw;
       const size_t o = gi + (size_t)col * ldv;
       double s = 0.0;
@@ -265,65 +317,68 @@ __global__ void __launch_bounds__(256) k_sbr_vtz(const double* __restrict__ V, i
     }
     __syncthreads();
 #pragma unroll 8
-    for (int rw = 0; rw < 32; ++rw) {
+    for (int rw = 0; rw < 64; ++rw) {
       const double va = Vs[rw][a];
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        g[x] = fma(va, Zs[rw][bq * 4 + x], g[x]);
-        gz[x] = fma(va, zs[rw][bq * 4 + x], gz[x]);
+      for (int x = 0; x < 2; ++x) {
+        g[x] = fma(va, Zs[rw][bq * 2 + x], g[x]);
+        gz[x] = fma(va, zs[rw][bq * 2 + x], gz[x]);
       }
     }
     __syncthreads();
   }
   double* out = Gp + (size_t)blockIdx.x * 2048;
 #pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    out[a * 32 + bq * 4 + x] = g[x];
-    out[1024 + a * 32 + bq * 4 + x] = gz[x];
+  for (int x = 0; x < 2; ++x) {
+    out[a * 32 + bq * 2 + x] = g[x];
+    out[1024 + a * 32 + bq * 2 + x] = gz[x];
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// W = Z0 T - 1/2 V (T' G0 T);  z <- z - V T' gz.  Thread = one row.
+// One CTA: G0, gz = fixed-order sums of the partials;  ST[0:1024] = S = T' G0 T,  ST[1024:2048] = T' gz  (row-major 32 x 32)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_sbr_st(const double* __restrict__ Gp, int nblk, const double* __restrict__ T,
+                                                 double* __restrict__ ST) {
+  __shared__ double Ts[32][kPad], Gs[32][kPad], Xs[32][kPad], gzs[32][kPad];
+  const int t = threadIdx.x, aa = t >> 5, cc = t & 31;
+  double g0 = 0.0, g1 = 0.0, z0 = 0.0, z1 = 0.0;
+  int bl = 0;
+  for (; bl + 1 < nblk; bl += 2) {
+    g0 += Gp[(size_t)bl * 2048 + t];
+    z0 += Gp[(size_t)bl * 2048 + 1024 + t];
+    g1 += Gp[(size_t)(bl + 1) * 2048 + t];
+    z1 += Gp[(size_t)(bl + 1) * 2048 + 1024 + t];
+  }
+  if (bl < nblk) { g0 += Gp[(size_t)bl * 2048 + t]; z0 += Gp[(size_t)bl * 2048 + 1024 + t]; }
+  Ts[aa][cc] = T[t];
+  Gs[aa][cc] = g0 + g1;
+  gzs[aa][cc] = z0 + z1;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll 8
+  for (int p = 0; p < 32; ++p) s = fma(Gs[aa][p], Ts[p][cc], s);      // X = G0 T
+  Xs[aa][cc] = s;
+  __syncthreads();
+  double u = 0.0;
+  s = 0.0;
+#pragma unroll 8
+  for (int p = 0; p < 32; ++p) {
+    s = fma(Ts[p][aa], Xs[p][cc], s);                                  // S = T' X
+    u = fma(Ts[p][aa], gzs[p][cc], u);                                 // T' gz
+  }
+  ST[t] = s;
+  ST[1024 + t] = u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// W = Z0 T - 1/2 V S;  z <- z - V (T' gz).  Thread = one row.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_sbr_w(const double* __restrict__ V, int ldv, int r, const double* __restrict__ Z0,
-                                               const double* __restrict__ T, const double* __restrict__ Gp, int nblk,
+                                               const double* __restrict__ T, const double* __restrict__ ST,
                                                double* __restrict__ W, double* __restrict__ z, int ldz, int zrow0, int L) {
-  __shared__ double Ts[32][kPad], Gs[32][kPad], Xs[32][kPad], gzs[32][kPad], tzs[32][kPad];
+  __shared__ double Ts[32][kPad], Ss[32][kPad], tzs[32][kPad];
   const int t = threadIdx.x;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int idx = t + 128 * q, aa = idx >> 5, cc = idx & 31;
-    double g = 0.0, gz = 0.0;
-    for (int bl = 0; bl < nblk; ++bl) {
-      g += Gp[(size_t)bl * 2048 + idx];
-      gz += Gp[(size_t)bl * 2048 + 1024 + idx];
-    }
-    Ts[aa][cc] = T[idx];
-    Gs[aa][cc] = g;
-    gzs[aa][cc] = gz;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {                 // X = G0 T
-    const int idx = t + 128 * q, aa = idx >> 5, cc = idx & 31;
-    double s = 0.0;
-    for (int p = 0; p < 32; ++p) s = fma(Gs[aa][p], Ts[p][cc], s);
-    Xs[aa][cc] = s;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {                 // S = T' X (into Gs), tz = T' gz
-    const int idx = t + 128 * q, aa = idx >> 5, cc = idx & 31;
-    double s = 0.0, u = 0.0;
-    for (int p = 0; p < 32; ++p) {
-      s = fma(Ts[p][aa], Xs[p][cc], s);
-      u = fma(Ts[p][aa], gzs[p][cc], u);
-    }
-    Gs[aa][cc] = s;                             // every thread has finished reading G0 (barrier above)
-    tzs[aa][cc] = u;
-  }
-  __syncthreads();
   const int i = blockIdx.x * 128 + t;           // < ldv
   double zr[32], vr[32];
 #pragma unroll
@@ -331,14 +386,24 @@ __global__ void __launch_bounds__(128) k_sbr_w(const double* __restrict__ V, int
     zr[q] = Z0[i + (size_t)q * ldv];
     vr[q] = V[i + (size_t)q * ldv];
   }
-  for (int cc = 0; cc < 32; ++cc) {
-    double w1 = 0.0, w2 = 0.0;
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
+  for (int q = 0; q < 8; ++q) {
+    const int idx = t + 128 * q, aa = idx >> 5, cc = idx & 31;
+    Ts[aa][cc] = T[idx];
+    Ss[aa][cc] = ST[idx];
+    tzs[aa][cc] = ST[1024 + idx];
+  }
+  __syncthreads();
+  for (int cc = 0; cc < 32; ++cc) {
+    double w1 = 0.0, w2 = 0.0, w3 = 0.0, w4 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 32; q += 2) {
       w1 = fma(zr[q], Ts[q][cc], w1);
-      w2 = fma(vr[q], Gs[q][cc], w2);
+      w2 = fma(vr[q], Ss[q][cc], w2);
+      w3 = fma(zr[q + 1], Ts[q + 1][cc], w3);
+      w4 = fma(vr[q + 1], Ss[q + 1][cc], w4);
     }
-    W[i + (size_t)cc * ldv] = w1 - 0.5 * w2;
+    W[i + (size_t)cc * ldv] = (w1 + w3) - 0.5 * (w2 + w4);
   }
   if (i < r)
     for (int l = 0; l < L; ++l) {
@@ -350,9 +415,12 @@ __global__ void __launch_bounds__(128) k_sbr_w(const double* __restrict__ V, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// C -= V W' + W V' on 128 x 128 tiles (full square); thread = 8 x 8 outputs, the operands of the whole tile in shared memory
+// C -= V W' + W V' on the 128 x 128 tiles of the lower triangle; thread = 8 x 8 outputs, the operands of the whole tile in
+// shared memory.  An off-diagonal tile is written twice: in place and - transposed through shared memory, so that both
+// stores are coalesced - into the upper triangle, which k_sbr_av reads as a plain square.
 // ---------------------------------------------------------------------------------------------
-constexpr size_t kR2kSmem = sizeof(double) * 4 * 32 * 128;
+constexpr int kR2kLds = 130;       // row stride of the transposed staging tile (16-byte aligned rows)
+constexpr size_t kR2kSmem = sizeof(double) * 128 * kR2kLds;     // >= 4 x 32 x 128 operands
 
 __global__ void __launch_bounds__(256, 1) k_sbr_r2k(double* __restrict__ C, int ld, int r, const double* __restrict__ V,
                                                     const double* __restrict__ W, int ldv) {
@@ -361,7 +429,12 @@ __global__ void __launch_bounds__(256, 1) k_sbr_r2k(double* __restrict__ C, int 
   double (*Wi)[128] = reinterpret_cast<double (*)[128]>(sm_r2k + 32 * 128);
   double (*Vj)[128] = reinterpret_cast<double (*)[128]>(sm_r2k + 2 * 32 * 128);
   double (*Wj)[128] = reinterpret_cast<double (*)[128]>(sm_r2k + 3 * 32 * 128);
-  const int t = threadIdx.x, I = blockIdx.x * 128, J = blockIdx.y * 128;
+  // lower-triangle tile index -> (bi >= bj)
+  int bi = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) ++bi;
+  while (bi * (bi + 1) / 2 > (int)blockIdx.x) --bi;
+  const int bj = blockIdx.x - bi * (bi + 1) / 2;
+  const int t = threadIdx.x, I = bi * 128, J = bj * 128;
   const int tx = t & 15, ty = t >> 4;           // rows tx*2 + 32*a + {0, 1}, columns ty*8 .. +7
   double acc[8][8];
   // the tile of C rides in the accumulators: its loads overlap the operand staging
@@ -421,6 +494,23 @@ __global__ void __launch_bounds__(256, 1) k_sbr_r2k(double* __restrict__ C, int 
       else if (rr < r) C[rr + (size_t)col * ld] = acc[2 * a4][j];
     }
   }
+  if (bi == bj) return;
+  // ---- mirror: S[row][col] = new C[I + row, J + col]  ->  C[J + col, I + row] -------------------------------------------
+  __syncthreads();                               // the operands are dead
+  double* S = sm_r2k;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rw = tx * 2 + 32 * (i >> 1) + (i & 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) S[rw * kR2kLds + ty * 8 + j] = acc[i][j];
+  }
+  __syncthreads();
+  const int c2 = (t & 63) * 2;                   // J + c2 + 1 <= J + 127 < I < r: always inside
+  for (int rw = t >> 6; rw < 128; rw += 4) {
+    if (I + rw >= r) break;
+    *reinterpret_cast<double2*>(C + (size_t)(J + c2) + (size_t)(I + rw) * ld) =
+        *reinterpret_cast<const double2*>(S + rw * kR2kLds + c2);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -450,126 +540,165 @@ struct ChaseArgs {
   int* prog;                       // [m] steps finished per sweep;  prog[m] = ticket counter, prog[m + 1] = error flag
 };
 
-// A wait that does not end within ~2^24 polls (seconds; a step takes microseconds) raises the error flag instead of
-// hanging the device: the host turns it into MB_E_NUMERIC.
-__device__ __forceinline__ void chase_wait(const int* p, int need, int* err) {
-  if ((threadIdx.x & 31) == 0) {
-    int v, spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    } while (v < need && ++spins < (1 << 24));
-    if (v < need) atomicExch(err, 1);
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void chase_post(int* p, int val) {
-  __threadfence();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(val) : "memory");
-}
+// One CTA (three warps) per sweep.  Per step: thread 0 waits for the predecessor sweep; warp 0 owns the off-diagonal block
+// (row in registers for the right-application and the new reflector, shared memory for the column pass), warp 1 the
+// diagonal block, warp 2 the right-hand sides - their loads are issued together, right after the wait, and the diagonal /
+// right-hand-side updates run beside the left-application of warp 0.  A wait that does not end within ~2^24 polls
+// (seconds; a step takes microseconds) raises the error flag instead of hanging the device.
+constexpr int kChaseThreads = 96;
 
-__global__ void __launch_bounds__(32) k_sbr_chase(ChaseArgs a) {
+__global__ void __launch_bounds__(kChaseThreads) k_sbr_chase(ChaseArgs a) {
   __shared__ double Bs[32][kPad], Ds[32][kPad], zs[32][kPad];
   __shared__ double vs[32], ws[32], vps[32], ts[32];
-  const int l = threadIdx.x, m = a.m;
+  __shared__ double sh_tau;
+  __shared__ int sh_s;
+  const int tid = threadIdx.x, l = tid & 31, wid = tid >> 5, m = a.m;
   constexpr int b = kBw;
   for (;;) {
-    int s = 0;
-    if (l == 0) s = atomicAdd(a.prog + m, 1);
-    s = __shfl_sync(0xffffffffu, s, 0);
+    __syncthreads();
+    if (tid == 0) sh_s = atomicAdd(a.prog + m, 1);
+    __syncthreads();
+    const int s = sh_s;
     if (s >= m - 2) break;
     const int totp = s > 0 ? (m - s + b - 1) / b : 0;     // steps of sweep s - 1
     const int tot = (m - s - 1 + b - 1) / b;              // steps of this sweep: row blocks below the diagonal of column s
-    double tau = 0.0;
+    double taup = 0.0;
     for (int k = 0; k < tot; ++k) {
-      if (s > 0) chase_wait(a.prog + (s - 1), min(k + 2, totp), a.prog + m + 1);
-      int r0, ln;
-      double beta, scale;
+      if (s > 0 && tid == 0) {
+        const int need = min(k + 2, totp);
+        const int* p = a.prog + (s - 1);
+        int v, spins = 0;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        } while (v < need && ++spins < (1 << 24));
+        if (v < need) atomicExch(a.prog + m + 1, 1);
+      }
+      __syncthreads();
+      // block geometry (uniform)
+      int st = 0, lp = 0, r0, ln;
       if (k == 0) {
-        // ---- type 1: reflector from column s, rows s+1 .. s+ln ---------------------------------------------
         ln = min(b, m - 1 - s);
         r0 = s + 1;
-        const double x = l < ln ? __ldcg(a.Bd + (1 + l) + (size_t)s * kLdb) : 0.0;
-        const double xn2 = wsum((l >= 1 && l < ln) ? x * x : 0.0);
-        make_house(__shfl_sync(0xffffffffu, x, 0), xn2, beta, tau, scale);
-        vs[l] = l == 0 ? 1.0 : ((l < ln && tau != 0.0) ? x * scale : 0.0);
-        if (l < ln) a.Bd[(1 + l) + (size_t)s * kLdb] = l == 0 ? beta : 0.0;
-        __syncwarp();
       } else {
-        // ---- type 2: block below the previous diagonal block: right-apply H_prev, new reflector, left-apply ----
-        const int st = s + 1 + (k - 1) * b;
-        const int lp = min(b, m - st);
-        const int j1 = st + lp;
-        ln = min(b, m - j1);
-        r0 = j1;
-        const double taup = tau;
-        vps[l] = vs[l];
-        __syncwarp();
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q)
-          Bs[l][q] = (l < ln && q < lp) ? __ldcg(a.Bd + (lp + l - q) + (size_t)(st + q) * kLdb) : 0.0;
-        double u = 0.0;
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q) u = fma(Bs[l][q], vps[q], u);
-        u *= taup;
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q) Bs[l][q] -= u * vps[q];
-        const double x = Bs[l][0];
-        const double xn2 = wsum((l >= 1 && l < ln) ? x * x : 0.0);
-        make_house(__shfl_sync(0xffffffffu, x, 0), xn2, beta, tau, scale);
-        vs[l] = l == 0 ? 1.0 : ((l < ln && tau != 0.0) ? x * scale : 0.0);
-        Bs[l][0] = l == 0 ? beta : 0.0;
-        __syncwarp();
-        if (l >= 1 && l < lp) {                 // lane = column
-          double y = 0.0;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) y = fma(vs[i], Bs[i][l], y);
-          y *= tau;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) Bs[i][l] -= vs[i] * y;
-        }
-        __syncwarp();
-        if (l < ln)
-#pragma unroll 8
+        st = s + 1 + (k - 1) * b;
+        lp = min(b, m - st);
+        r0 = st + lp;
+        ln = min(b, m - r0);
+      }
+      if (wid == 0) {
+        double beta, tau, scale, x;
+        if (k == 0) {
+          // ---- type 1: reflector from column s, rows s+1 .. s+ln ---------------------------------------------
+          x = l < ln ? __ldcg(a.Bd + (1 + l) + (size_t)s * kLdb) : 0.0;
+          const double xn2 = wsum((l >= 1 && l < ln) ? x * x : 0.0);
+          make_house(__shfl_sync(0xffffffffu, x, 0), xn2, beta, tau, scale);
+          vs[l] = l == 0 ? 1.0 : ((l < ln && tau != 0.0) ? x * scale : 0.0);
+          if (l == 0) sh_tau = tau;
+          if (l < ln) a.Bd[(1 + l) + (size_t)s * kLdb] = l == 0 ? beta : 0.0;
+        } else {
+          // ---- type 2: block below the previous diagonal block: right-apply H_prev, new reflector ---------------
+          double br[32];
+#pragma unroll
           for (int q = 0; q < 32; ++q)
-            if (q < lp) a.Bd[(lp + l - q) + (size_t)(st + q) * kLdb] = Bs[l][q];
-      }
-      // ---- type 3: two-sided update of the diagonal block r0 .. r0+ln-1 ---------------------------------------
-#pragma unroll 8
-      for (int q = 0; q < 32; ++q)
-        Ds[l][q] = (q <= l && l < ln) ? __ldcg(a.Bd + (l - q) + (size_t)(r0 + q) * kLdb) : 0.0;
-      __syncwarp();
-#pragma unroll 8
-      for (int q = 0; q < 32; ++q)
-        if (q > l) Ds[l][q] = Ds[q][l];
-      __syncwarp();
-      const double vl = vs[l];
-      double p = 0.0;
-#pragma unroll 8
-      for (int q = 0; q < 32; ++q) p = fma(Ds[l][q], vs[q], p);
-      p *= tau;
-      const double w = fma(-0.5 * tau * wsum(p * vl), vl, p);
-      ws[l] = w;
-      __syncwarp();
-      if (l < ln)
+            br[q] = (l < ln && q < lp) ? __ldcg(a.Bd + (lp + l - q) + (size_t)(st + q) * kLdb) : 0.0;
+          double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            u0 = fma(br[q], vps[q], u0);
+            u1 = fma(br[q + 1], vps[q + 1], u1);
+            u2 = fma(br[q + 2], vps[q + 2], u2);
+            u3 = fma(br[q + 3], vps[q + 3], u3);
+          }
+          const double u = taup * ((u0 + u1) + (u2 + u3));
+#pragma unroll
+          for (int q = 0; q < 32; ++q) br[q] = fma(-u, vps[q], br[q]);
+          x = br[0];
+          const double xn2 = wsum((l >= 1 && l < ln) ? x * x : 0.0);
+          make_house(__shfl_sync(0xffffffffu, x, 0), xn2, beta, tau, scale);
+          vs[l] = l == 0 ? 1.0 : ((l < ln && tau != 0.0) ? x * scale : 0.0);
+          if (l == 0) sh_tau = tau;
+          br[0] = l == 0 ? beta : 0.0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) Bs[l][q] = br[q];
+        }
+      } else if (wid == 1) {
+        // ---- diagonal block r0 .. r0+ln-1, both triangles in shared memory ----------------------------------------
+        double dr[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          dr[q] = (q <= l && l < ln) ? __ldcg(a.Bd + (l - q) + (size_t)(r0 + q) * kLdb) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) Ds[l][q] = dr[q];
+        __syncwarp();
 #pragma unroll 8
         for (int q = 0; q < 32; ++q)
-          if (q <= l) a.Bd[(l - q) + (size_t)(r0 + q) * kLdb] = Ds[l][q] - vl * ws[q] - w * vs[q];
-      // ---- right-hand sides: z[r0 .. r0+ln-1, :] <- H z ------------------------------------------------------------
-      if (a.L > 0) {
+          if (q > l) Ds[l][q] = Ds[q][l];
+      } else {
         for (int cc = 0; cc < a.L; ++cc) zs[l][cc] = l < ln ? __ldcg(a.z + (size_t)(r0 + l) + (size_t)cc * m) : 0.0;
+      }
+      __syncthreads();
+      const double tau = sh_tau;
+      const double vl = vs[l];
+      if (wid == 0) {
+        if (k > 0) {
+          // ---- left-apply the new reflector to columns 1 .. lp-1 (lane = column), then store the block by rows ----
+          if (l >= 1 && l < lp) {
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              y0 = fma(vs[i], Bs[i][l], y0);
+              y1 = fma(vs[i + 1], Bs[i + 1][l], y1);
+              y2 = fma(vs[i + 2], Bs[i + 2][l], y2);
+              y3 = fma(vs[i + 3], Bs[i + 3][l], y3);
+            }
+            const double y = tau * ((y0 + y1) + (y2 + y3));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) Bs[i][l] = fma(-vs[i], y, Bs[i][l]);
+          }
+          __syncwarp();
+          if (l < ln)
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (q < lp) a.Bd[(lp + l - q) + (size_t)(st + q) * kLdb] = Bs[l][q];
+        }
+        vps[l] = vl;                      // the reflector the next step applies from the right
+      } else if (wid == 1) {
+        // ---- type 3: D <- H D H ---------------------------------------------------------------------------------
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          p0 = fma(Ds[l][q], vs[q], p0);
+          p1 = fma(Ds[l][q + 1], vs[q + 1], p1);
+          p2 = fma(Ds[l][q + 2], vs[q + 2], p2);
+          p3 = fma(Ds[l][q + 3], vs[q + 3], p3);
+        }
+        const double p = tau * ((p0 + p1) + (p2 + p3));
+        const double w = fma(-0.5 * tau * wsum(p * vl), vl, p);
+        ws[l] = w;
         __syncwarp();
+        if (l < ln)
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (q <= l) a.Bd[(l - q) + (size_t)(r0 + q) * kLdb] = Ds[l][q] - vl * ws[q] - w * vs[q];
+      } else if (a.L > 0) {
+        // ---- right-hand sides: z[r0 .. r0+ln-1, :] <- H z -----------------------------------------------------------
         if (l < a.L) {
-          double tt = 0.0;
+          double t0 = 0.0, t1 = 0.0;
 #pragma unroll 8
-          for (int i = 0; i < 32; ++i) tt = fma(vs[i], zs[i][l], tt);
-          ts[l] = tau * tt;
+          for (int i = 0; i < 32; i += 2) {
+            t0 = fma(vs[i], zs[i][l], t0);
+            t1 = fma(vs[i + 1], zs[i + 1][l], t1);
+          }
+          ts[l] = tau * (t0 + t1);
         }
         __syncwarp();
         if (l < ln)
-          for (int cc = 0; cc < a.L; ++cc) a.z[(size_t)(r0 + l) + (size_t)cc * m] = zs[l][cc] - vl * ts[cc];
+          for (int cc = 0; cc < a.L; ++cc) a.z[(size_t)(r0 + l) + (size_t)cc * m] = fma(-vl, ts[cc], zs[l][cc]);
       }
-      chase_post(a.prog + s, k + 1);
+      taup = tau;
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.prog + s), "r"(k + 1) : "memory");
     }
   }
 }
@@ -585,11 +714,31 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   MB_REQUIRE(m >= 3 && ld >= m && ld % 2 == 0, "two-stage tridiagonalisation: bad matrix shape");
   MB_REQUIRE(L >= 0 && L <= 32, "at most 32 right-hand sides per tridiagonalisation");
   Arena& ar = ctx->arena;
-  static thread_local bool attr = false;
-  if (!attr) {
-    MB_CUDA(cudaFuncSetAttribute(k_sbr_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQrSmem));
+  // cluster size the panel QR may use: 16 (non-portable) if such a cluster can be scheduled, else 8, else none
+  static thread_local int max_cluster = -1;
+  if (max_cluster < 0) {
+    MB_CUDA(cudaFuncSetAttribute(k_sbr_qr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQrSmem));
+    MB_CUDA(cudaFuncSetAttribute(k_sbr_qr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQrSmem));
     MB_CUDA(cudaFuncSetAttribute(k_sbr_r2k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kR2kSmem));
-    attr = true;
+    MB_CUDA(cudaFuncSetAttribute(k_sbr_vtz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVtzSmem));
+    max_cluster = 0;
+    const bool np_ok = cudaFuncSetAttribute(k_sbr_qr<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    for (int cs : {16, 8}) {
+      if (cs > 8 && !np_ok) continue;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = kQrSmem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, k_sbr_qr<true>, &cfg) == cudaSuccess && nclusters >= 1) {
+        max_cluster = cs;
+        break;
+      }
+    }
+    (void)cudaGetLastError();
+    if (ctx->sbr_debug) std::fprintf(stderr, "[sbr] panel QR cluster size limit: %d\n", max_cluster);
   }
   const int rmax = m - kBw;
   if (rmax >= 2) {
@@ -602,8 +751,9 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     double* V = ar.take_n<double>((size_t)rpadmax * 32);
     double* W = ar.take_n<double>((size_t)rpadmax * 32);
     double* Z0 = ar.take_n<double>((size_t)rpadmax * 32);
-    double* Zp = ar.take_n<double>((size_t)16 * rpadmax * 32);
+    double* Zp = ar.take_n<double>((size_t)8 * rpadmax * 32);
     double* T = ar.take_n<double>(1024);
+    double* ST = ar.take_n<double>(2048);
     double* Gp = ar.take_n<double>((size_t)(rpadmax / 128) * 2048);
     double* slots = ar.take_n<double>((size_t)2 * (gmax + 1) * 32);
     unsigned* bars = ar.take_n<unsigned>((size_t)64 * npanel);
@@ -614,19 +764,33 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
       const int ldv = ceil_div(r, 128) * 128;
       const int rblocks = ldv / 128;
       QrArgs qa{A, ld, m, j0, V, ldv, T, slots, bars + (size_t)64 * pk};
-      void* params[] = {&qa};
-      MB_LAUNCH(ctx, "k_sbr_qr", st)
-        MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr, dim3(ceil_div(r, kQrRows)), dim3(kQrRows), params, kQrSmem, st));
+      const int gq = ceil_div(r, kQrRows);
+      if (gq <= max_cluster && ctx->sbr_qr_grid == 0) {
+        int cs = 1;
+        while (cs < gq) cs *= 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = kQrSmem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        MB_LAUNCH(ctx, "k_sbr_qr", st) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_qr<true>, qa));
+      } else {
+        void* params[] = {&qa};
+        MB_LAUNCH(ctx, "k_sbr_qr_grid", st)
+          MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr<false>, dim3(gq), dim3(kQrRows), params, kQrSmem, st));
+      }
       double* A22 = A + (size_t)(j0 + kBw) * ((size_t)ld + 1);
-      int nsplit = std::max(1, std::min(16, ceil_div(3 * ctx->sm_count, rblocks)));
+      int nsplit = std::max(1, std::min(8, ceil_div(2 * ctx->sm_count, rblocks)));
       const int chunk = ceil_div(ceil_div(r, nsplit), 16) * 16;
       nsplit = ceil_div(r, chunk);
       MB_LAUNCH(ctx, "k_sbr_av", st) k_sbr_av<<<dim3(rblocks, nsplit), 128, 0, st>>>(A22, ld, r, V, ldv, Zp, chunk);
       MB_LAUNCH(ctx, "k_sbr_vtz", st)
-        k_sbr_vtz<<<rblocks, 256, 0, st>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
-      MB_LAUNCH(ctx, "k_sbr_w", st) k_sbr_w<<<rblocks, 128, 0, st>>>(V, ldv, r, Z0, T, Gp, rblocks, W, z, m, j0 + kBw, L);
+        k_sbr_vtz<<<rblocks, 512, kVtzSmem, st>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
+      MB_LAUNCH(ctx, "k_sbr_st", st) k_sbr_st<<<1, 1024, 0, st>>>(Gp, rblocks, T, ST);
+      MB_LAUNCH(ctx, "k_sbr_w", st) k_sbr_w<<<rblocks, 128, 0, st>>>(V, ldv, r, Z0, T, ST, W, z, m, j0 + kBw, L);
       MB_LAUNCH(ctx, "k_sbr_r2k", st)
-        k_sbr_r2k<<<dim3(rblocks, rblocks), 256, kR2kSmem, st>>>(A22, ld, r, V, W, ldv);
+        k_sbr_r2k<<<rblocks * (rblocks + 1) / 2, 256, kR2kSmem, st>>>(A22, ld, r, V, W, ldv);
     }
     MB_CUDA(cudaGetLastError());
   }
@@ -643,7 +807,7 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   }
   ChaseArgs ca{Bd, m, z, L, prog};
   const int G = std::max(1, std::min(ctx->sm_count, ceil_div(m, 2 * kBw) + 2));
-  MB_LAUNCH(ctx, "k_sbr_chase", st) k_sbr_chase<<<G, 32, 0, st>>>(ca);
+  MB_LAUNCH(ctx, "k_sbr_chase", st) k_sbr_chase<<<G, kChaseThreads, 0, st>>>(ca);
   MB_LAUNCH(ctx, "k_sbr_diag", st) k_sbr_diag<<<ceil_div(m, 256), 256, 0, st>>>(Bd, m, d, e);
   MB_CUDA(cudaGetLastError());
   int chase_err = 0;

@@ -54,6 +54,11 @@ for n in sizes:
             eng.set_param("sytrd_mode", 0); a = eng.tps_fit(xy, Y)
             eng.set_param("sytrd_mode", 3); b = eng.tps_fit(xy, Y)
             print("   L=3 lambda rel diff", [f"{abs(p.lam - q.lam) / q.lam:.1e}" for p, q in zip(b, a)], flush=True)
+        if n in (600, 1100):
+            eng.set_param("sytrd_mode", 3); eng.set_param("sbr_qr_grid", 1)
+            g = eng.tps_fit(xy, y)
+            eng.set_param("sbr_qr_grid", 0)
+            print(f"   grid-barrier QR: lambda rel diff {abs(g.lam - sp0.lam) / sp0.lam:.1e}", flush=True)
         for mode in (0, 3):
             eng.set_param("sytrd_mode", mode)
             eng.timing(True); eng.timing_collect()
