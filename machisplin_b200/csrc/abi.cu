@@ -50,6 +50,7 @@ int mb_init(int device, mb_ctx** out) {
     MB_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
     MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    MB_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage1, cudaEventDisableTiming));
     init_logtab(ctx.get());
     *out = ctx.release();
   });
@@ -66,6 +67,7 @@ void mb_shutdown(mb_ctx* ctx) {
   ctx->arena.release();
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_stage1) cudaEventDestroy(ctx->ev_stage1);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->copy) cudaStreamDestroy(ctx->copy);
   for (auto& w : ctx->lanes) {
@@ -164,8 +166,11 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       ctx->eigen_impl = value;
     } else if (n == "sytrd_mode") {
       MB_REQUIRE(value >= 0 && value <= 3,
-                 "sytrd_mode must be 0 / 1 (persistent kernel), 2 (kernel per phase) or 3 (two-stage band reduction)");
+                 "sytrd_mode must be 0 (default = two-stage), 1 (one-stage persistent kernel), 2 (one-stage, kernel per phase) or 3 (two-stage)");
       ctx->sytrd_mode = value;
+    } else if (n == "defer_ensemble") {
+      MB_REQUIRE(value == 0 || value == 1, "defer_ensemble must be 0 or 1");
+      ctx->defer_ensemble = value;
     } else if (n == "sbr_qr_grid") {
       MB_REQUIRE(value == 0 || value == 1, "sbr_qr_grid must be 0 or 1");
       ctx->sbr_qr_grid = value;
@@ -535,17 +540,26 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
     MB_REQUIRE(C == ensemble_ncov(e), "number of covariate planes does not match the model descriptors (P = C + 2)");
     MB_REQUIRE(C == 0 || cov, "covariate planes are NULL");
   }
-  // part 2 (trees + svm) starts on the side stream; it only needs the covariates
+  // part 2 (trees + svm) runs on the side stream; it only needs the covariates.  With the two-stage GCV fit the launch is
+  // deferred to the point where stage 1 of the tridiagonalisation (full-GPU FP64 products, ~1/3 of the fit) has been
+  // enqueued, and waits for it on the device: the rest of the fit - bulge chasing, bisection, Cholesky - is latency-bound
+  // on a few SMs and shares the GPU with the per-cell kernels, whereas the panel kernels of stage 1 would be starved by
+  // their 262 144-CTA grids.  In the host-buffer entry point the covariate planes travel meanwhile.
   double* acc = nullptr;
   const bool heavy = e != nullptr;
+  const bool tps = knots_xy && resid && n > 0;
+  const bool one_spline = tps && (tile_px <= 0 || ((g.nrow + tile_px - 1) / tile_px) * ((g.ncol + tile_px - 1) / tile_px) == 1);
+  const bool defer = heavy && one_spline && lambda < 0 && ctx->eigen_impl != 1 && (ctx->sytrd_mode == 0 || ctx->sytrd_mode == 3) &&
+                     ctx->defer_ensemble;
+  int nblk_copy = 0, rows_per = 0;
   if (heavy) {
     acc = ctx->arena.take_n<double>((size_t)(acc_stride(full) * acc_rows(full)));
     MB_CUDA(cudaEventRecord(ctx->ev_fork, st));
     MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     if (cov_host && C > 0) {
       MB_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
-      const int nblk = std::max(1, std::min(8, g.nrow / 256));
-      const int rows_per = ((g.nrow + nblk - 1) / nblk + 63) / 64 * 64;
+      nblk_copy = std::max(1, std::min(8, g.nrow / 256));
+      rows_per = ((g.nrow + nblk_copy - 1) / nblk_copy + 63) / 64 * 64;
       int b = 0;
       for (int r0 = 0; r0 < g.nrow; r0 += rows_per, ++b) {
         const int r1 = std::min(g.nrow, r0 + rows_per);
@@ -560,6 +574,21 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
           ctx->ev_blocks.push_back(ev);
         }
         MB_CUDA(cudaEventRecord(ctx->ev_blocks[b], ctx->copy));
+      }
+    }
+  }
+  bool launched = false;
+  auto launch_ensemble = [&](bool after_stage1) {
+    if (launched || !heavy) return;
+    launched = true;
+    if (after_stage1) {
+      MB_CUDA(cudaEventRecord(ctx->ev_stage1, ctx->stream));
+      MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_stage1, 0));
+    }
+    if (nblk_copy > 0) {
+      int b = 0;
+      for (int r0 = 0; r0 < g.nrow; r0 += rows_per, ++b) {
+        const int r1 = std::min(g.nrow, r0 + rows_per);
         MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_blocks[b], 0));
         const mb_window wb{r0, r1, 0, g.ncol};
         ensemble_accumulate(ctx, e, cov, C, wb, acc + (int64_t)r0 * acc_stride(full), ctx->side);
@@ -568,9 +597,9 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
       ensemble_accumulate(ctx, e, cov, C, full, acc, ctx->side);
     }
     MB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
-  }
+  };
+  if (!defer) launch_ensemble(false);
   // part 3: fields::Tps of the residuals on the context stream, beside the kernels above
-  const bool tps = knots_xy && resid && n > 0;
   std::unique_ptr<mb_spline> sp;
   const double* surface = nullptr;
   if (tps) {
@@ -578,8 +607,16 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
     const int nCx = tile_px > 0 ? (g.ncol + tile_px - 1) / tile_px : 1;
     if (nRx * nCx == 1) {                                            // V73:748-753
       mb_spline* raw = nullptr;
-      tps_fit(ctx, knots_xy, resid, n, 1, lambda, &raw);
+      if (defer) ctx->after_stage1 = [&] { launch_ensemble(true); };
+      try {
+        tps_fit(ctx, knots_xy, resid, n, 1, lambda, &raw);
+      } catch (...) {
+        ctx->after_stage1 = nullptr;
+        throw;
+      }
+      ctx->after_stage1 = nullptr;
       sp.reset(raw);
+      launch_ensemble(false);          // not reached through the hook (e.g. a fit small enough to skip stage 1 entirely)
     } else {                                                         // V73:649-895
       double* surf = ctx->arena.take_n<double>(ncell);
       tiles_tps(ctx, g, knots_xy, resid, n, tile_px, 0.2, 0.025, 10, lambda, MB_EVAL_FAST, surf, ctx->stream);

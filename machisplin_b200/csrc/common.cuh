@@ -10,6 +10,7 @@
 #include <vector>
 #include <stdexcept>
 #include <memory>
+#include <functional>
 #include <algorithm>
 
 #include "../../include/machisplin_b200.h"
@@ -163,8 +164,8 @@ struct mb_ctx {
   mb::DevBuf<double2> logtab;
   int eval_precision = 0;     // fast evaluator: 0 = automatic, 1 = float64 only, 2 = force mixed
   int eigen_impl = 0;         // GCV fit: 0 = in-house tridiagonalisation + bisection, 1 = cuSOLVER Dsyevd (validation)
-  int sytrd_mode = 0;         // tridiagonalisation: 0 / 1 = persistent kernel with grid barrier, 2 = one kernel per phase,
-                              // 3 = two-stage (band reduction + bulge chasing, sbr.cu)
+  int sytrd_mode = 0;         // tridiagonalisation: 0 = default = 3 = two-stage (band reduction + bulge chasing, sbr.cu),
+                              // 1 = one-stage persistent kernel with grid barrier, 2 = one-stage, one kernel per phase
   int sbr_debug = 0;          // two-stage path: keep the band matrix of stage 1 for mb_debug_values("sbr_band")
   std::vector<double> dbg_band;
   int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits
@@ -174,7 +175,11 @@ struct mb_ctx {
   mb::Arena arena;
   // second stream + events: the TPS fit runs beside the per-cell ensemble kernels (mb_mltps_predict*)
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_stage1 = nullptr;
+  // mb_mltps_predict*: called by the two-stage tridiagonalisation once its stage 1 is enqueued on `stream` (starts the
+  // per-cell ensemble kernels behind it); "defer_ensemble" = 0 starts them before the fit instead
+  std::function<void()> after_stage1;
+  int defer_ensemble = 1;
   // copy stream + per-row-block events of the host-buffer path (H2D of block b+1 overlaps the kernels of block b)
   cudaStream_t copy = nullptr;
   std::vector<cudaEvent_t> ev_blocks;

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
     }
     red[seg * 32 + c] = acc0 + acc1;
     __syncthreads();
+    double s = 0.0, piv = 0.0;
     if (kCluster) {
       double* mine = part + (j & 1) * 64;
       if (t < 32) {
@@ -149,10 +150,12 @@ __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
       }
       cluster.sync();
       if (t < 32) {
-        double s = 0.0;
-        for (int q = 0; q < G; ++q) s += cluster.map_shared_rank(mine, q)[t];
-        s_sh[t] = s;
-        piv_sh[t] = cluster.map_shared_rank(mine, 0)[32 + t];
+        double pr[16];                                         // all remote loads in flight before the first add
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pr[q] = q < G ? cluster.map_shared_rank(mine, q)[t] : 0.0;
+        piv = cluster.map_shared_rank(mine, 0)[32 + t];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) s += pr[q];
       }
     } else {
       double* slot = a.slots + (size_t)(j & 1) * (G + 1) * 32;
@@ -165,22 +168,25 @@ __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
       }
       sbr_grid_sync(a.bar, gen);
       if (t < 32) {
-        double s = 0.0;
         for (int q = 0; q < G; ++q) s += __ldcg(slot + q * 32 + t);
-        s_sh[t] = s;
-        piv_sh[t] = __ldcg(slot + G * 32 + t);
+        piv = __ldcg(slot + G * 32 + t);
       }
     }
+    if (t < 32) {
+      // warp 0: the reflector, w_c = v'P[:, c] = piv_c + scale s_c (for c < j the same expression is V[:, c]'v_j)
+      double beta, tau, scale;
+      make_house(__shfl_sync(0xffffffffu, piv, j), __shfl_sync(0xffffffffu, s, j), beta, tau, scale);
+      s_sh[t] = fma(scale, s, piv);
+      if (t == 0) { piv_sh[0] = beta; piv_sh[1] = tau; piv_sh[2] = scale; }
+    }
     __syncthreads();
-    const double alpha = piv_sh[j];
-    double beta, tau, scale;
-    make_house(alpha, s_sh[j], beta, tau, scale);
+    const double beta = piv_sh[0], tau = piv_sh[1], scale = piv_sh[2];
     // ---- column j of T (CTA 0, warp 1): T[:j, j] = -tau T[:j, :j] (V[:, :j]' v_j) --------------------------
     if (blk == 0 && t >= 32 && t < 64) {
       const int q = t - 32;
       if (q < j) {
         double sum = 0.0;
-        for (int p = q; p < j; ++p) sum = fma(Tsh[q * kPad + p], fma(scale, s_sh[p], piv_sh[p]), sum);
+        for (int p = q; p < j; ++p) sum = fma(Tsh[q * kPad + p], s_sh[p], sum);
         Tsh[q * kPad + j] = -tau * sum;
       } else if (q == j) {
         Tsh[j * kPad + j] = tau;
@@ -190,10 +196,10 @@ __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
     if (gi > j) {
       const double vj = X[t * kPad + j] * scale;
       const double f = tau * vj;
-      for (int cc = j + 1; cc < 32; ++cc) X[t * kPad + cc] -= f * fma(scale, s_sh[cc], piv_sh[cc]);
+      for (int cc = j + 1; cc < 32; ++cc) X[t * kPad + cc] = fma(-f, s_sh[cc], X[t * kPad + cc]);
       X[t * kPad + j] = vj;
     } else if (gi == j) {
-      for (int cc = j + 1; cc < 32; ++cc) X[t * kPad + cc] -= tau * fma(scale, s_sh[cc], piv_sh[cc]);
+      for (int cc = j + 1; cc < 32; ++cc) X[t * kPad + cc] = fma(-tau, s_sh[cc], X[t * kPad + cc]);
       X[t * kPad + j] = beta;
     }
     __syncthreads();
@@ -794,6 +800,7 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     }
     MB_CUDA(cudaGetLastError());
   }
+  if (ctx->after_stage1) ctx->after_stage1();
   // ---- stage 2 ------------------------------------------------------------------------------------------------------
   const int ncolb = m + kLdb;
   double* Bd = ar.take_n<double>((size_t)kLdb * ncolb);

@@ -683,7 +683,7 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
   a.S = ar.take_n<double>((size_t)((m + kChunk - 1) / kChunk) * kSW);
   a.S2 = ar.take_n<double>(G);
   MB_CUDA(cudaMemsetAsync(a.bar, 0, 64 * sizeof(unsigned), st));
-  if (ctx->sytrd_mode == 3) {
+  if (ctx->sytrd_mode == 0 || ctx->sytrd_mode == 3) {
     // two-stage reduction (sbr.cu): dense -> band by compact-WY panels, band -> tridiagonal by bulge chasing
     sym_band_tridiag(ctx, A, ld, m, z_dev, L, a.d, a.e, st);
   } else if (ctx->sytrd_mode != 2) {
@@ -707,7 +707,7 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
   diag.resize(m);
   off.resize(m - 1);
   unsigned long long prof_ns[8] = {0};
-  if (a.prof && ctx->sytrd_mode < 2)
+  if (a.prof && ctx->sytrd_mode == 1)
     MB_CUDA(cudaMemcpyAsync(prof_ns, a.prof, sizeof(prof_ns), cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaMemcpyAsync(diag.data(), a.d, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaMemcpyAsync(off.data(), a.e, sizeof(double) * (m - 1), cudaMemcpyDeviceToHost, st));

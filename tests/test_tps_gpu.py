@@ -168,13 +168,19 @@ def test_mixed_path_is_refused_when_inaccurate(engine):
 
 @pytest.mark.parametrize("n", [35, 200, 1100])
 def test_fit_gcv_tridiagonal_paths_agree(engine, n):
-    """The in-house GCV fit (persistent Householder kernel + Sturm bisection + Cholesky) against its two
-    alternates: one kernel per phase (sytrd_mode = 2) and the cuSOLVER eigenvector path (eigen_impl = 1)."""
+    """The default GCV fit (two-stage tridiagonalisation: compact-WY band reduction + bulge chasing, then Sturm bisection
+    and the Cholesky at the selected lambda) against its alternates: the one-stage Householder reduction as one
+    persistent kernel (sytrd_mode = 1) or one kernel per phase (sytrd_mode = 2), and the cuSOLVER eigenvector path
+    (eigen_impl = 1)."""
     geom = synth.make_geom(1024, 1024)
     xy, _, _ = synth.make_knots(geom, n, 300 + n)
     y = synth.residual_field(xy, 300 + n)
     sp0 = engine.tps_fit(xy, y)
     try:
+        engine.set_param("sytrd_mode", 3)
+        sp3 = engine.tps_fit(xy, y)
+        engine.set_param("sytrd_mode", 1)
+        spp = engine.tps_fit(xy, y)
         engine.set_param("sytrd_mode", 2)
         sp2 = engine.tps_fit(xy, y)
         engine.set_param("sytrd_mode", 0)
@@ -183,14 +189,43 @@ def test_fit_gcv_tridiagonal_paths_agree(engine, n):
     finally:
         engine.set_param("sytrd_mode", 0)
         engine.set_param("eigen_impl", 0)
-    # the two schedules of the same algorithm are bit-identical (fixed summation order)
-    assert sp2.lam == sp0.lam
-    np.testing.assert_array_equal(sp2.c, sp0.c)
-    np.testing.assert_array_equal(sp2.decomposition()[0], sp0.decomposition()[0])
-    assert abs(sp1.lam - sp0.lam) <= 1e-6 * sp0.lam
-    assert np.max(np.abs(sp1.c - sp0.c)) <= 1e-7 * np.max(np.abs(sp0.c))
-    np.testing.assert_allclose(sp1.decomposition()[0], sp0.decomposition()[0], rtol=1e-7,
-                               atol=1e-13 * sp0.decomposition()[0].max())
+    # every path is deterministic (no atomics on data, fixed summation orders): repeating the default reproduces it bit
+    # for bit, and the two schedules of the one-stage algorithm are bit-identical to each other
+    assert sp3.lam == sp0.lam
+    np.testing.assert_array_equal(sp3.c, sp0.c)
+    np.testing.assert_array_equal(sp3.decomposition()[0], sp0.decomposition()[0])
+    assert sp2.lam == spp.lam
+    np.testing.assert_array_equal(sp2.c, spp.c)
+    np.testing.assert_array_equal(sp2.decomposition()[0], spp.decomposition()[0])
+    for alt in (spp, sp1):
+        assert abs(alt.lam - sp0.lam) <= 1e-6 * sp0.lam
+        assert np.max(np.abs(alt.c - sp0.c)) <= 1e-7 * np.max(np.abs(sp0.c))
+        np.testing.assert_allclose(alt.decomposition()[0], sp0.decomposition()[0], rtol=1e-7,
+                                   atol=1e-13 * sp0.decomposition()[0].max())
+
+
+@pytest.mark.parametrize("n", [20, 36, 37, 70, 165, 600])
+def test_fit_two_stage_edge_sizes(engine, n):
+    """Two-stage tridiagonalisation at the sizes where its structure changes: no panel at all (m <= 33: bulge chasing on
+    the dense matrix read as a band), one short panel (m = 34), panels with fewer rows than columns, ragged last row block,
+    three right-hand sides carried through both stages.  Reference: the one-stage reduction."""
+    geom = synth.make_geom(512, 512)
+    xy, _, _ = synth.make_knots(geom, n, 900 + n)
+    y = synth.residual_field(xy, 900 + n)
+    Y = np.stack([y, y[::-1].copy(), y * y], axis=1)
+    got = engine.tps_fit(xy, Y)
+    try:
+        engine.set_param("sytrd_mode", 1)
+        ref = engine.tps_fit(xy, Y)
+    finally:
+        engine.set_param("sytrd_mode", 0)
+    for g, r in zip(got, ref):
+        assert abs(g.lam - r.lam) <= 1e-8 * r.lam
+        assert np.max(np.abs(g.c - r.c)) <= 1e-8 * np.max(np.abs(r.c))
+        eg, (dg, og, zg) = g.decomposition()
+        er, (dr, orr, zr) = r.decomposition()
+        np.testing.assert_allclose(eg, er, rtol=0, atol=1e-13 * er.max())
+        assert abs(np.linalg.norm(zg) - np.linalg.norm(zr)) <= 1e-12 * np.linalg.norm(zr)
 
 
 @pytest.mark.parametrize("mode", [0, 2])

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""GPU check of the GCV fit paths: in-house persistent tridiagonalisation (sytrd_mode 0), one kernel per phase
-(sytrd_mode 2), cuSOLVER validation path (eigen_impl 1).  Usage: fit_check.py <mode: persistent|phases|cusolver|chol> [n ...]"""
+"""GPU check of the GCV fit paths: two-stage default (mode `default`), one-stage persistent tridiagonalisation (sytrd_mode 1), one kernel per phase
+(sytrd_mode 2), cuSOLVER validation path (eigen_impl 1).  Usage: fit_check.py <mode: default|persistent|phases|cusolver|chol> [n ...]"""
 import sys, time
 import numpy as np
 sys.path.insert(0, __file__.rsplit("/", 2)[0])
@@ -10,6 +10,8 @@ from machisplin_b200 import synth
 mode = sys.argv[1]
 sizes = [int(a) for a in sys.argv[2:]] or [35, 200, 1100, 5000]
 eng = mb.Engine(0)
+if mode.startswith("persistent"):
+    eng.set_param("sytrd_mode", 1)
 if mode == "phases":
     eng.set_param("sytrd_mode", 2)
 elif mode == "cusolver":

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""GPU check of the two-stage tridiagonalisation (sytrd_mode 3, csrc/sbr.cu) against the one-stage kernel (sytrd_mode 0):
+"""GPU check of the two-stage tridiagonalisation (sytrd_mode 3, csrc/sbr.cu) against the one-stage kernel (sytrd_mode 1):
 eigenvalues of the stage-1 band matrix, eigenvalues of the final tridiagonal, the transformed right-hand side (through
 RSS(lambda)), the selected lambda, and per-kernel times.  Usage: sbr_check.py [n ...]"""
 import sys, time, traceback
@@ -25,7 +25,7 @@ for n in sizes:
     try:
         xy, _, _ = synth.make_knots(geom, n, 300 + n)
         y = synth.residual_field(xy, 300 + n)
-        eng.set_param("sytrd_mode", 0)
+        eng.set_param("sytrd_mode", 1)
         sp0 = eng.tps_fit(xy, y)
         eta0, (d0, e0, z0) = sp0.decomposition()
         eng.set_param("sytrd_mode", 3)
@@ -51,7 +51,7 @@ for n in sizes:
         # three responses at once
         if n in (200, 1100):
             Y = np.stack([y, y[::-1].copy(), y * y], axis=1)
-            eng.set_param("sytrd_mode", 0); a = eng.tps_fit(xy, Y)
+            eng.set_param("sytrd_mode", 1); a = eng.tps_fit(xy, Y)
             eng.set_param("sytrd_mode", 3); b = eng.tps_fit(xy, Y)
             print("   L=3 lambda rel diff", [f"{abs(p.lam - q.lam) / q.lam:.1e}" for p, q in zip(b, a)], flush=True)
         if n in (600, 1100):
@@ -59,7 +59,7 @@ for n in sizes:
             g = eng.tps_fit(xy, y)
             eng.set_param("sbr_qr_grid", 0)
             print(f"   grid-barrier QR: lambda rel diff {abs(g.lam - sp0.lam) / sp0.lam:.1e}", flush=True)
-        for mode in (0, 3):
+        for mode in (1, 3):
             eng.set_param("sytrd_mode", mode)
             eng.timing(True); eng.timing_collect()
             t0 = time.perf_counter()
