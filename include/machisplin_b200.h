@@ -210,7 +210,8 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * "sytrd_mode" = tridiagonalisation of the GCV fit: 0 / 3 = two-stage (band reduction + bulge chasing, the default),
  * 1 = one-stage persistent kernel, 2 = one-stage with one kernel per phase; "sytrd_ctas_per_sm" = grid size of the
  * one-stage persistent kernel; "sbr_qr_grid" = 1 makes the panel QR of the two-stage path use the software grid
- * barrier instead of a thread-block cluster; "sbr_debug" = 1 keeps the band matrix for mb_debug_values("sbr_band");
+ * barrier instead of a thread-block cluster; "sbr_qr_impl" = 1 / 2 keeps the panel rows in shared memory / registers
+ * (0 = chosen by cluster size); "sbr_debug" = 1 keeps the band matrix for mb_debug_values("sbr_band");
  * "defer_ensemble" = 0 starts the per-cell ensemble kernels of mb_mltps_predict* before the fit instead of behind stage 1
  * of its tridiagonalisation; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd (validation of the in-house path only). */
 int mb_set_param(mb_ctx* ctx, const char* name, int value);

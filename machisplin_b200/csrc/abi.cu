@@ -68,12 +68,16 @@ void mb_shutdown(mb_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_stage1) cudaEventDestroy(ctx->ev_stage1);
+  for (cudaEvent_t ev : ctx->sbr_ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->sbr_aux) cudaStreamDestroy(ctx->sbr_aux);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->copy) cudaStreamDestroy(ctx->copy);
   for (auto& w : ctx->lanes) {
     w->logtab.p = nullptr; w->logtab.n = 0;
     w->arena.release();
     for (cudaEvent_t e : w->event_pool) cudaEventDestroy(e);
+    for (cudaEvent_t ev : w->sbr_ev) if (ev) cudaEventDestroy(ev);
+    if (w->sbr_aux) cudaStreamDestroy(w->sbr_aux);
     if (w->stream) cudaStreamDestroy(w->stream);
   }
   ctx->lanes.clear();
@@ -171,6 +175,9 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
     } else if (n == "defer_ensemble") {
       MB_REQUIRE(value == 0 || value == 1, "defer_ensemble must be 0 or 1");
       ctx->defer_ensemble = value;
+    } else if (n == "sbr_qr_impl") {
+      MB_REQUIRE(value >= 0 && value <= 2, "sbr_qr_impl must be 0 (automatic), 1 (panel rows in shared memory) or 2 (in registers)");
+      ctx->sbr_qr_impl = value;
     } else if (n == "sbr_qr_grid") {
       MB_REQUIRE(value == 0 || value == 1, "sbr_qr_grid must be 0 or 1");
       ctx->sbr_qr_grid = value;

@@ -168,6 +168,9 @@ struct mb_ctx {
                               // 1 = one-stage persistent kernel with grid barrier, 2 = one-stage, one kernel per phase
   int sbr_debug = 0;          // two-stage path: keep the band matrix of stage 1 for mb_debug_values("sbr_band")
   std::vector<double> dbg_band;
+  cudaStream_t sbr_aux = nullptr;   // two-stage path: stream of the look-ahead trailing updates + its events
+  cudaEvent_t sbr_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers
   int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits
   int sytrd_ctas_per_sm = 0;  // persistent grid size (0 = 2 per SM)
   double sytrd_prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per-phase time of the last k_sytrd launch (timing on)

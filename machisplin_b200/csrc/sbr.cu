@@ -222,6 +222,139 @@ __global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr(QrArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// panel QR, rows in REGISTERS (used for clusters of up to 4 CTAs; the kernel above keeps them in shared memory and is bound
+// by its bandwidth: 3 wavefronts per row and column in the reduction, 5 in the update).  Thread t holds row t of the panel as 32 doubles; the
+// 32 column sums of one step are reduced inside the warp by a reduce-scatter butterfly (16 + 16 shuffles: after the exchange
+// over lane bits 4..1 lane L holds the sum of column L >> 1, one more exchange over bit 0 completes it), across the 16 warps
+// through 4 KB of shared memory, across the CTAs as above.  The update H_j x is 31 - j register FMAs.
+// ---------------------------------------------------------------------------------------------
+constexpr size_t kQrRegSmem = sizeof(double) * (16 * 32 + 32 + 4 + 32 * kPad + 2 * 64);
+
+template <bool kCluster>
+__global__ void __launch_bounds__(kQrRows, 1) k_sbr_qr_reg(QrArgs a) {
+  extern __shared__ double sm_qr[];
+  double* red = sm_qr;                    // [16][32]
+  double* s_sh = red + 16 * 32;           // [32]
+  double* par = s_sh + 32;                // beta, tau, scale
+  double* Tsh = par + 4;                  // [32][33]
+  double* part = Tsh + 32 * kPad;         // [2][64]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int t = threadIdx.x, blk = blockIdx.x, G = gridDim.x, lane = t & 31, wid = t >> 5;
+  const int r = a.m - a.j0 - kBw;
+  const int gi = blk * kQrRows + t;
+  const size_t row = (size_t)(a.j0 + kBw) + gi;
+  double x[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) x[c] = gi < r ? a.A[row + (size_t)(a.j0 + c) * a.ld] : 0.0;
+  for (int i = t; i < 32 * kPad; i += kQrRows) Tsh[i] = 0.0;
+  __syncthreads();
+  const int nref = min(kBw, r - 1);
+  unsigned gen = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < nref) {                                            // uniform over the grid
+      // ---- s_c = sum over rows i > j of x_i[j] x_i[c] ----------------------------------------------------
+      const double xj = gi > j ? x[j] : 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = xj * x[16 * h + i];
+#pragma unroll
+        for (int o = 16, n = 8; n >= 1; o >>= 1, n >>= 1) {
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const double send = up ? v[i] : v[i + n];
+            const double keep = up ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        if ((lane & 1) == 0) red[wid * 32 + 16 * h + (lane >> 1)] = v[0];
+      }
+      __syncthreads();
+      double s = 0.0, piv = 0.0;
+      double* mine = kCluster ? part + (j & 1) * 64 : a.slots + (size_t)(j & 1) * (G + 1) * 32;
+      if (t < 32) {
+        double p = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) p += red[q * 32 + t];
+        if (kCluster) mine[t] = p; else mine[blk * 32 + t] = p;
+      }
+      if (gi == j) {                                           // the pivot row: thread j of CTA 0
+        double* pr = kCluster ? mine + 32 : mine + G * 32;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pr[c] = x[c];
+      }
+      if (kCluster) {
+        cluster.sync();
+        if (t < 32) {
+          double pr[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) pr[q] = q < G ? cluster.map_shared_rank(mine, q)[t] : 0.0;
+          piv = cluster.map_shared_rank(mine, 0)[32 + t];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) s += pr[q];
+        }
+      } else {
+        sbr_grid_sync(a.bar, gen);
+        if (t < 32) {
+          for (int q = 0; q < G; ++q) s += __ldcg(mine + q * 32 + t);
+          piv = __ldcg(mine + G * 32 + t);
+        }
+      }
+      if (t < 32) {
+        double beta, tau, scale;
+        make_house(__shfl_sync(0xffffffffu, piv, j), __shfl_sync(0xffffffffu, s, j), beta, tau, scale);
+        s_sh[t] = fma(scale, s, piv);                          // w_c = v'P[:, c]; for c < j it is V[:, c]'v_j
+        if (t == 0) { par[0] = beta; par[1] = tau; par[2] = scale; }
+      }
+      __syncthreads();
+      const double beta = par[0], tau = par[1], scale = par[2];
+      if (blk == 0 && t >= 32 && t < 64) {                     // column j of T
+        const int q = t - 32;
+        if (q < j) {
+          double sum = 0.0;
+          for (int p = q; p < j; ++p) sum = fma(Tsh[q * kPad + p], s_sh[p], sum);
+          Tsh[q * kPad + j] = -tau * sum;
+        } else if (q == j) {
+          Tsh[j * kPad + j] = tau;
+        }
+      }
+      if (gi > j) {
+        const double vj = x[j] * scale;
+        const double f = tau * vj;
+#pragma unroll
+        for (int cc = j + 1; cc < 32; ++cc) x[cc] = fma(-f, s_sh[cc], x[cc]);
+        x[j] = vj;
+      } else if (gi == j) {
+#pragma unroll
+        for (int cc = j + 1; cc < 32; ++cc) x[cc] = fma(-tau, s_sh[cc], x[cc]);
+        x[j] = beta;
+      }
+    }
+  }
+  __syncthreads();
+  if (gi < a.ldv) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      double v = 0.0;
+      if (gi < r && q < nref) v = gi > q ? x[q] : (gi == q ? 1.0 : 0.0);
+      a.V[gi + (size_t)q * a.ldv] = v;
+    }
+  }
+  if (blk == 0 && t < 32 && gi < r) {
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc)
+      if (cc >= t) a.A[row + (size_t)(a.j0 + cc) * a.ld] = x[cc];
+  }
+  if (blk == 0)
+    for (int i = t; i < 1024; i += kQrRows) a.T[i] = Tsh[(i >> 5) * kPad + (i & 31)];
+  if (kCluster) cluster.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Z0 = A22 V : CTA = 128 rows x 32 columns over the k range [sp * chunk, (sp + 1) * chunk); thread = 8 x 4 outputs;
 // the next 16-column slab of A22 and V travels in registers while the current one is multiplied
 // ---------------------------------------------------------------------------------------------
@@ -422,7 +555,8 @@ __global__ void __launch_bounds__(128) k_sbr_w(const double* __restrict__ V, int
 
 // ---------------------------------------------------------------------------------------------
 // C -= V W' + W V' on the 128 x 128 tiles of the lower triangle; thread = 8 x 8 outputs, the operands of the whole tile in
-// shared memory.  An off-diagonal tile is written twice: in place and - transposed through shared memory, so that both
+// shared memory.  Rows >= 32 of the first 32 columns - the next panel - are left to k_sbr_pu, so that the QR of the next
+// panel runs beside this kernel (look-ahead).  An off-diagonal tile is written twice: in place and - transposed through shared memory, so that both
 // stores are coalesced - into the upper triangle, which k_sbr_av reads as a plain square.
 // ---------------------------------------------------------------------------------------------
 constexpr int kR2kLds = 130;       // row stride of the transposed staging tile (16-byte aligned rows)
@@ -451,7 +585,7 @@ __global__ void __launch_bounds__(256, 1) k_sbr_r2k(double* __restrict__ C, int 
     for (int a4 = 0; a4 < 4; ++a4) {
       const int rr = I + tx * 2 + 32 * a4;
       double2 cv = make_double2(0.0, 0.0);
-      if (col < r) {
+      if (col < r && !(col < 32 && rr >= 32)) {          // rows >= 32 of the first 32 columns = the next panel (k_sbr_pu)
         if (rr + 1 < r) cv = *reinterpret_cast<const double2*>(C + rr + (size_t)col * ld);
         else if (rr < r) cv.x = C[rr + (size_t)col * ld];
       }
@@ -496,6 +630,7 @@ __global__ void __launch_bounds__(256, 1) k_sbr_r2k(double* __restrict__ C, int 
 #pragma unroll
     for (int a4 = 0; a4 < 4; ++a4) {
       const int rr = I + tx * 2 + 32 * a4;
+      if (col < 32 && rr >= 32) continue;
       if (rr + 1 < r) *reinterpret_cast<double2*>(C + rr + (size_t)col * ld) = make_double2(acc[2 * a4][j], acc[2 * a4 + 1][j]);
       else if (rr < r) C[rr + (size_t)col * ld] = acc[2 * a4][j];
     }
@@ -512,10 +647,44 @@ __global__ void __launch_bounds__(256, 1) k_sbr_r2k(double* __restrict__ C, int 
   }
   __syncthreads();
   const int c2 = (t & 63) * 2;                   // J + c2 + 1 <= J + 127 < I < r: always inside
+  if (J == 0 && c2 < 32) return;                 // mirror image of the next panel: never read again
   for (int rw = t >> 6; rw < 128; rw += 4) {
     if (I + rw >= r) break;
     *reinterpret_cast<double2*>(C + (size_t)(J + c2) + (size_t)(I + rw) * ld) =
         *reinterpret_cast<const double2*>(S + rw * kR2kLds + c2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// look-ahead: the same update restricted to the next panel, C[32:, 0:32] -= V W[0:32]' + W V[0:32]'.  Thread = one row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_sbr_pu(double* __restrict__ C, int ld, int r, const double* __restrict__ V,
+                                                const double* __restrict__ W, int ldv) {
+  __shared__ double Vt[32][kPad], Wt[32][kPad];          // [k][c] = V[c, k], W[c, k] of the first 32 rows
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int idx = t + 128 * q, kk = idx >> 5, cc = idx & 31;
+    Vt[kk][cc] = V[cc + (size_t)kk * ldv];
+    Wt[kk][cc] = W[cc + (size_t)kk * ldv];
+  }
+  const int i = 32 + blockIdx.x * 128 + t;
+  double vr[32], wr[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    vr[q] = i < r ? V[i + (size_t)q * ldv] : 0.0;
+    wr[q] = i < r ? W[i + (size_t)q * ldv] : 0.0;
+  }
+  __syncthreads();
+  if (i >= r) return;
+  for (int cc = 0; cc < 32; ++cc) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      s0 = fma(vr[q], Wt[q][cc], s0);
+      s1 = fma(wr[q], Vt[q][cc], s1);
+    }
+    C[i + (size_t)cc * ld] -= s0 + s1;
   }
 }
 
@@ -725,6 +894,7 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   if (max_cluster < 0) {
     MB_CUDA(cudaFuncSetAttribute(k_sbr_qr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQrSmem));
     MB_CUDA(cudaFuncSetAttribute(k_sbr_qr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQrSmem));
+    (void)cudaFuncSetAttribute(k_sbr_qr_reg<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     MB_CUDA(cudaFuncSetAttribute(k_sbr_r2k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kR2kSmem));
     MB_CUDA(cudaFuncSetAttribute(k_sbr_vtz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVtzSmem));
     max_cluster = 0;
@@ -754,8 +924,8 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     const int gmax = ceil_div(rmax, kQrRows);
     int npanel = 0;
     for (int j0 = 0; m - j0 - kBw >= 2; j0 += kBw) ++npanel;
-    double* V = ar.take_n<double>((size_t)rpadmax * 32);
-    double* W = ar.take_n<double>((size_t)rpadmax * 32);
+    double* Vb[2] = {ar.take_n<double>((size_t)rpadmax * 32), ar.take_n<double>((size_t)rpadmax * 32)};
+    double* Wb[2] = {ar.take_n<double>((size_t)rpadmax * 32), ar.take_n<double>((size_t)rpadmax * 32)};
     double* Z0 = ar.take_n<double>((size_t)rpadmax * 32);
     double* Zp = ar.take_n<double>((size_t)8 * rpadmax * 32);
     double* T = ar.take_n<double>(1024);
@@ -764,40 +934,68 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     double* slots = ar.take_n<double>((size_t)2 * (gmax + 1) * 32);
     unsigned* bars = ar.take_n<unsigned>((size_t)64 * npanel);
     MB_CUDA(cudaMemsetAsync(bars, 0, sizeof(unsigned) * 64 * npanel, st));
+    // look-ahead: the trailing update of panel k runs on a second stream beside the QR of panel k + 1
+    if (!ctx->sbr_aux) {
+      int prio_lo = 0, prio_hi = 0;
+      MB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      MB_CUDA(cudaStreamCreateWithPriority(&ctx->sbr_aux, cudaStreamNonBlocking, prio_hi));
+      for (cudaEvent_t& ev : ctx->sbr_ev) MB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    cudaStream_t aux = ctx->sbr_aux;
     int pk = 0;
     for (int j0 = 0; m - j0 - kBw >= 2; j0 += kBw, ++pk) {
       const int r = m - j0 - kBw;
       const int ldv = ceil_div(r, 128) * 128;
       const int rblocks = ldv / 128;
+      double* V = Vb[pk & 1];
+      double* W = Wb[pk & 1];
       QrArgs qa{A, ld, m, j0, V, ldv, T, slots, bars + (size_t)64 * pk};
       const int gq = ceil_div(r, kQrRows);
       if (gq <= max_cluster && ctx->sbr_qr_grid == 0) {
         int cs = 1;
         while (cs < gq) cs *= 2;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = kQrSmem; cfg.stream = st;
+        // measured (profiles/r1v_two_stage_check.txt): rows in registers win up to clusters of 4 CTAs (2.6 vs 3.3 us per
+        // column), rows in shared memory at 8 and 16 (3.4 vs 4.0 us)
+        const bool reg = ctx->sbr_qr_impl == 2 || (ctx->sbr_qr_impl == 0 && cs <= 4);
+        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = reg ? kQrRegSmem : kQrSmem; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        MB_LAUNCH(ctx, "k_sbr_qr", st) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_qr<true>, qa));
+        if (reg) {
+          MB_LAUNCH(ctx, "k_sbr_qr", st) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_qr_reg<true>, qa));
+        } else {
+          MB_LAUNCH(ctx, "k_sbr_qr_smem", st) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_qr<true>, qa));
+        }
       } else {
         void* params[] = {&qa};
-        MB_LAUNCH(ctx, "k_sbr_qr_grid", st)
-          MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr<false>, dim3(gq), dim3(kQrRows), params, kQrSmem, st));
+        if (ctx->sbr_qr_impl != 1) {
+          MB_LAUNCH(ctx, "k_sbr_qr_grid", st)
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr_reg<false>, dim3(gq), dim3(kQrRows), params, kQrRegSmem, st));
+        } else {
+          MB_LAUNCH(ctx, "k_sbr_qr_smem_grid", st)
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr<false>, dim3(gq), dim3(kQrRows), params, kQrSmem, st));
+        }
       }
       double* A22 = A + (size_t)(j0 + kBw) * ((size_t)ld + 1);
       int nsplit = std::max(1, std::min(8, ceil_div(2 * ctx->sm_count, rblocks)));
       const int chunk = ceil_div(ceil_div(r, nsplit), 16) * 16;
       nsplit = ceil_div(r, chunk);
+      if (pk > 0) MB_CUDA(cudaStreamWaitEvent(st, ctx->sbr_ev[2 + ((pk - 1) & 1)], 0));      // trailing update of panel k - 1
       MB_LAUNCH(ctx, "k_sbr_av", st) k_sbr_av<<<dim3(rblocks, nsplit), 128, 0, st>>>(A22, ld, r, V, ldv, Zp, chunk);
       MB_LAUNCH(ctx, "k_sbr_vtz", st)
         k_sbr_vtz<<<rblocks, 512, kVtzSmem, st>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
       MB_LAUNCH(ctx, "k_sbr_st", st) k_sbr_st<<<1, 1024, 0, st>>>(Gp, rblocks, T, ST);
       MB_LAUNCH(ctx, "k_sbr_w", st) k_sbr_w<<<rblocks, 128, 0, st>>>(V, ldv, r, Z0, T, ST, W, z, m, j0 + kBw, L);
-      MB_LAUNCH(ctx, "k_sbr_r2k", st)
-        k_sbr_r2k<<<rblocks * (rblocks + 1) / 2, 256, kR2kSmem, st>>>(A22, ld, r, V, W, ldv);
+      if (r > 32) MB_LAUNCH(ctx, "k_sbr_pu", st) k_sbr_pu<<<ceil_div(r - 32, 128), 128, 0, st>>>(A22, ld, r, V, W, ldv);
+      MB_CUDA(cudaEventRecord(ctx->sbr_ev[pk & 1], st));
+      MB_CUDA(cudaStreamWaitEvent(aux, ctx->sbr_ev[pk & 1], 0));
+      MB_LAUNCH(ctx, "k_sbr_r2k", aux)
+        k_sbr_r2k<<<rblocks * (rblocks + 1) / 2, 256, kR2kSmem, aux>>>(A22, ld, r, V, W, ldv);
+      MB_CUDA(cudaEventRecord(ctx->sbr_ev[2 + (pk & 1)], aux));
     }
+    if (pk > 0) MB_CUDA(cudaStreamWaitEvent(st, ctx->sbr_ev[2 + ((pk - 1) & 1)], 0));
     MB_CUDA(cudaGetLastError());
   }
   if (ctx->after_stage1) ctx->after_stage1();
