@@ -367,16 +367,25 @@ def run_b200(args):
         cov_np = h_cov.numpy() if C else None
         out_np = h_out.numpy()
 
+        host_s = {"ensemble_create": 0.0, "mltps_predict": 0.0}
+
         def step_e2e():
+            t0 = time.perf_counter()
             ens2 = eng.ensemble_create(geom, models, kept, w, wt, P) if kept else None   # descriptor upload + tree packing
+            t1 = time.perf_counter()
             eng.mltps_predict(geom, ens2, cov_np, xy, resid, lam=args.lam, out=out_np)
+            host_s["ensemble_create"] += t1 - t0
+            host_s["mltps_predict"] += time.perf_counter() - t1
             return out_np[krow, kcol]
 
         step_e2e()
+        for k in host_s:
+            host_s[k] = 0.0
         ms_e2e = timed(step_e2e, max(1, args.steps))
         e2e = {"value": world * cells / (ms_e2e * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h_cov.numel() * 4 + xy.nbytes + resid.nbytes),
-               "d2h_bytes_per_step": int(h_out.numel() * 8)}
+               "d2h_bytes_per_step": int(h_out.numel() * 8),
+               "host_ms_per_step": {k: v * 1e3 / max(1, args.steps) for k, v in host_s.items()}}
         del h_cov
 
     if rank != 0:

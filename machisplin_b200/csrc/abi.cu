@@ -5,6 +5,9 @@
 #include "internal.h"
 
 #include <cmath>
+#include <cstdlib>
+#include <map>
+#include <mutex>
 
 namespace mb {
 static thread_local std::string g_last_error;
@@ -12,6 +15,94 @@ void set_last_error(const std::string& m) { g_last_error = m; }
 }  // namespace mb
 
 using namespace mb;
+
+// ---- cache of freed device blocks (DevBuf, common.cuh) ------------------------------------------------------------------
+namespace mb {
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::map<void*, std::pair<int, size_t>> live;                       // block -> (device, capacity)
+  std::map<std::pair<int, size_t>, std::vector<void*>> spare;         // (device, capacity) -> blocks
+  size_t spare_bytes = 0;
+  const bool on = [] { const char* v = std::getenv("MB_DEV_CACHE"); return !(v && v[0] == '0'); }();
+};
+DevCache& dev_cache() { static DevCache* c = new DevCache; return *c; }   // never destroyed: handles may outlive main()
+constexpr size_t kSpareLimit = size_t(2) << 30;
+size_t size_class(size_t bytes) {
+  size_t c = 512;
+  while (c < bytes && c < (size_t(1) << 20)) c <<= 1;                  // powers of two up to 1 MiB
+  if (c >= bytes) return c;
+  return (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);   // then whole MiB
+}
+}  // namespace
+
+void* dev_cache_take(size_t bytes) {
+  DevCache& c = dev_cache();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t cap = c.on ? size_class(bytes) : bytes;
+  if (c.on) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.spare.find({dev, cap});
+    if (it != c.spare.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      c.spare_bytes -= cap;
+      c.live[p] = {dev, cap};
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, cap);
+  if (e != cudaSuccess && c.on) {                                      // give the cached blocks back and retry once
+    (void)cudaGetLastError();
+    dev_cache_flush();
+    e = cudaMalloc(&p, cap);
+  }
+  if (e != cudaSuccess) throw Error(MB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  if (c.on) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.live[p] = {dev, cap};
+  }
+  return p;
+}
+
+void dev_cache_give(void* p) noexcept {
+  if (!p) return;
+  DevCache& c = dev_cache();
+  if (!c.on) { cudaFree(p); return; }
+  std::pair<int, size_t> key{-1, 0};
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.live.find(p);
+    if (it != c.live.end()) { key = it->second; c.live.erase(it); }
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (key.first != dev || key.second == 0) { cudaFree(p); return; }    // unknown block or another device: plain free
+  cudaDeviceSynchronize();                                             // nothing in flight may still touch the block
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (c.spare_bytes + key.second > kSpareLimit) { cudaFree(p); return; }
+  c.spare[key].push_back(p);
+  c.spare_bytes += key.second;
+}
+
+void dev_cache_flush() noexcept {
+  DevCache& c = dev_cache();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::vector<void*> blocks;
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto& kv : c.spare)
+      if (kv.first.first == dev) {
+        for (void* p : kv.second) { blocks.push_back(p); c.spare_bytes -= kv.first.second; }
+        kv.second.clear();
+      }
+  }
+  for (void* p : blocks) cudaFree(p);
+}
+}  // namespace mb
 
 extern "C" {
 
@@ -84,6 +175,7 @@ void mb_shutdown(mb_ctx* ctx) {
   for (cudaEvent_t ev : ctx->ev_blocks) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+  mb::dev_cache_flush();
 }
 
 int mb_sync(mb_ctx* ctx) {

@@ -55,6 +55,13 @@ int guarded(F&& f) {
 }
 
 // ---- RAII device buffer -----------------------------------------------------------------
+// Long-lived device arrays (model descriptors, spline coefficients) come from a process-wide cache of freed blocks (abi.cu):
+// cudaMalloc / cudaFree cost 0.5 - 2 ms each on a 180 GB device and an ensemble handle owns ~30 arrays, which made creating
+// and freeing one per response 80 ms of the host-buffer path.  give() synchronises the device before a block can be reused
+// (what cudaFree did implicitly); MB_DEV_CACHE=0 in the environment restores plain cudaMalloc / cudaFree.
+void* dev_cache_take(size_t bytes);          // throws Error(MB_E_NOMEM)
+void dev_cache_give(void* p) noexcept;
+void dev_cache_flush() noexcept;             // cudaFree of every cached block of the current device
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -69,12 +76,11 @@ struct DevBuf {
     return *this;
   }
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) dev_cache_give(p); p = nullptr; n = 0; }
   void alloc(size_t n_) {
     release();
     if (n_ == 0) return;
-    cudaError_t e = cudaMalloc(&p, n_ * sizeof(T));
-    if (e != cudaSuccess) throw Error(MB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    p = static_cast<T*>(dev_cache_take(n_ * sizeof(T)));
     n = n_;
   }
   void ensure(size_t n_) { if (n_ > n) alloc(n_); }

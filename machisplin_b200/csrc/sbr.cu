@@ -871,7 +871,8 @@ __global__ void __launch_bounds__(kChaseThreads) k_sbr_chase(ChaseArgs a) {
           for (int cc = 0; cc < a.L; ++cc) a.z[(size_t)(r0 + l) + (size_t)cc * m] = fma(-vl, ts[cc], zs[l][cc]);
       }
       taup = tau;
-      __threadfence();
+      // publish the step: the CTA barrier orders every thread's stores before thread 0's release store (cumulativity), the
+      // pattern of a cooperative-groups grid barrier - one fence on the critical path instead of two
       __syncthreads();
       if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.prog + s), "r"(k + 1) : "memory");
     }
