@@ -408,11 +408,16 @@ def run_b200(args):
     for name, (tms, cnt) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
         per_launch = tms / max(cnt, 1)
         ent = {"ms_per_step": tms / args.steps, "launches_per_step": cnt / args.steps, "share": tms / tot_ms}
-        if name in bytes_per_cell:
+        twin = {"k_leaf": "k_leaf_f64", "k_leaf_f64": "k_leaf", "k_leaf_fused": "k_leaf_f64_fused",
+                "k_leaf_f64_fused": "k_leaf_fused"}.get(name)
+        if twin in ktimes and ktimes[twin][0] > tms:
+            ent["note"] = "twin of the selected leaf kernel: exits at its first instruction (DESIGN.md 4.1)"
+        elif name in bytes_per_cell:
             gbs = cells * bytes_per_cell[name] / (per_launch * 1e-3) / 1e9
             ent.update({"algorithmic_bytes_per_cell": bytes_per_cell[name], "achieved_gbs": gbs, "hbm_frac": gbs / peak})
         kern[name] = ent
-    lname = next((k for k in ("k_leaf_fused", "k_leaf", "k_leaf_f64_fused", "k_leaf_f64") if k in kern), "k_leaf")
+    leaf_names = ("k_leaf_fused", "k_leaf", "k_leaf_f64_fused", "k_leaf_f64")
+    lname = next((k for k in leaf_names if "hbm_frac" in kern.get(k, {})), next((k for k in leaf_names if k in kern), "k_leaf"))
     leaf = kern.get(lname, {})
     # DRAM traffic of the kernel per launch from the committed ncu --set full capture of this workload (profiles/)
     traffic = None
