@@ -216,6 +216,26 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * of its tridiagonalisation; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd (validation of the in-house path only). */
 int mb_set_param(mb_ctx* ctx, const char* name, int value);
 
+/* ---- GeoTIFF in / out: terra::rast(path) (README Example 1, V73:68-70) and terra::writeRaster() (V73:1011, 1020) -----------------
+ * Host-only (no context, no GPU).  Readers accept classic TIFF, striped or tiled, chunky or planar bands, 8 / 16 / 32-bit integers
+ * and 32 / 64-bit floats, compression none / LZW / PackBits, predictor 1 / 2 - which covers the rasters the reference bundles
+ * (INT16, 128 x 128 tiles, none or LZW, GDAL_NODATA) and what terra writes by default.  Everything else is refused with a message.
+ * Cell order is terra's: row-major from the NW corner.  NoData cells come back as NaN (terra: NA). */
+typedef struct {
+  mb_grid grid;            /* extent from ModelPixelScale + ModelTiepoint (has_georef), else [0, ncol] x [0, nrow] */
+  int32_t nbands, bits, sample_format /* 1 unsigned, 2 signed, 3 float */, compression, predictor;
+  int32_t tiled, chunk_w, chunk_h;     /* tile size, or (image width, rows per strip) */
+  int32_t has_georef, has_nodata, epsg /* 0 = not given */;
+  double nodata;
+} mb_tiff_meta;
+int mb_tiff_info(const char* path, mb_tiff_meta* out);
+/* one band (0-based) as float32, nrow * ncol values; tiles / strips are decoded by nthreads host threads (0 = all) */
+int mb_tiff_read_f32(const char* path, int band, float* out, int nthreads);
+/* FLT4S GeoTIFF (terra::writeRaster's default datatype), 256 x 256 tiles, compression 1 (none) or 5 (LZW), NaN = NoData;
+ * epsg > 0 adds the CRS key (4326 for the LONG / LAT rasters of the reference) */
+int mb_tiff_write_f32(const char* path, const mb_grid* g, const float* data, int compression, int epsg, int nthreads);
+int mb_tiff_write_f64(const char* path, const mb_grid* g, const double* data, int compression, int epsg, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,10 @@ SIGNATURES = {
     "mb_timing_collect": (C.c_int, [VP, C.c_int, C.POINTER(C.c_char_p), PD, C.POINTER(C.c_int64)]),
     "mb_set_fast_eval_params": (C.c_int, [VP, C.c_int, C.c_int, C.c_int]),
     "mb_set_param": (C.c_int, [VP, C.c_char_p, C.c_int]),
+    "mb_tiff_info": (C.c_int, [C.c_char_p, VP]),
+    "mb_tiff_read_f32": (C.c_int, [C.c_char_p, C.c_int, PF, C.c_int]),
+    "mb_tiff_write_f32": (C.c_int, [C.c_char_p, PG, PF, C.c_int, C.c_int, C.c_int]),
+    "mb_tiff_write_f64": (C.c_int, [C.c_char_p, PG, PD, C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None

@@ -67,3 +67,8 @@ mb_mltps_predict <- function(mb, rast_stack, n.covars, models, kept, w, w.total,
 
 # V73:329-333 / 369-373: the objective handed to optimx becomes a 6 x 6 quadratic form.
 mb_rss_objective <- function(mb, R) { G <- .Call("mbR_gram", mb, as.matrix(R)); function(k) drop(k %*% G %*% k) / sum(k)^2 }
+
+# README Example 1 / V73:68-70 without terra in the data path: the covariate GeoTIFFs are decoded by the library into the float32
+# planes mb_mltps_predict() uploads (list(grid, cov)); V73:1011 / 1020: the final raster as a FLT4S GeoTIFF.
+mb_read_stack <- function(paths) .Call("mbR_read_stack", as.character(paths))
+mb_write_raster <- function(path, grid, values, epsg = 4326L) invisible(.Call("mbR_write_raster", as.character(path), as.numeric(grid), as.numeric(values), as.integer(epsg)))

@@ -116,3 +116,36 @@ SEXP mbR_gram(SEXP ctx, SEXP R) {
   UNPROTECT(1);
   return G;
 }
+
+/* terra::rast(path) for the covariate stack (README Example 1, V73:68-70): the rasters are decoded by the library's host
+ * threads straight into float32 planes (C x nrow x ncol, terra cell order, NoData = NaN) packed in a raw vector - the layout
+ * mbR_mltps_predict takes - without the round trip through terra::values() and writeBin().  Returns
+ * list(grid = c(xmin, xmax, ymin, ymax, nrow, ncol), cov = raw). */
+SEXP mbR_read_stack(SEXP paths) {
+  const int C = Rf_length(paths);
+  mb_tiff_meta m0;
+  MB_CHECK(mb_tiff_info(CHAR(STRING_ELT(paths, 0)), &m0));
+  const R_xlen_t ncell = (R_xlen_t)m0.grid.nrow * m0.grid.ncol;
+  SEXP cov = PROTECT(Rf_allocVector(RAWSXP, ncell * C * (R_xlen_t)sizeof(float)));
+  for (int k = 0; k < C; ++k) {
+    mb_tiff_meta m;
+    MB_CHECK(mb_tiff_info(CHAR(STRING_ELT(paths, k)), &m));
+    if (m.grid.nrow != m0.grid.nrow || m.grid.ncol != m0.grid.ncol) Rf_error("machisplin_b200: extents do not match");
+    MB_CHECK(mb_tiff_read_f32(CHAR(STRING_ELT(paths, k)), 0, (float*)RAW(cov) + ncell * k, 0));
+  }
+  SEXP grid = PROTECT(Rf_allocVector(REALSXP, 6));
+  REAL(grid)[0] = m0.grid.xmin; REAL(grid)[1] = m0.grid.xmax; REAL(grid)[2] = m0.grid.ymin; REAL(grid)[3] = m0.grid.ymax;
+  REAL(grid)[4] = m0.grid.nrow; REAL(grid)[5] = m0.grid.ncol;
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, grid);
+  SET_VECTOR_ELT(out, 1, cov);
+  UNPROTECT(3);
+  return out;
+}
+
+/* terra::writeRaster(x, filename, overwrite = TRUE) (V73:1011, 1020): FLT4S GeoTIFF, LZW, NA = NoData. */
+SEXP mbR_write_raster(SEXP path, SEXP grid, SEXP values, SEXP epsg) {
+  mb_grid g = grid_of(grid);
+  MB_CHECK(mb_tiff_write_f64(CHAR(STRING_ELT(path, 0)), &g, REAL(values), 5, Rf_asInteger(epsg), 0));
+  return R_NilValue;
+}
