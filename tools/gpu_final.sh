@@ -14,6 +14,11 @@ timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 timeout -k 10 900 ncu --set full --clock-control none --import-source on -k "regex:k_leaf_stream|k_ens_trees|k_ens_svm|k_syrk_dmma|k_leaf_prep" -c 12 -f -o gpurun_out/${TAG}_prof \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+# two-stage fit: the first panels (largest trailing matrix) of stage 1, then the bulge chase on its own
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k "regex:k_sbr_qr|k_sbr_av|k_sbr_r2k|k_sbr_vtz|k_sbr_w|k_sbr_pu" -c 14 -f -o gpurun_out/${TAG}_prof_sbr \
+  python tools/fit_check.py default 5000 > gpurun_out/${TAG}_ncu_sbr.log 2>&1; echo "ncu sbr rc=$?"
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k "regex:k_sbr_chase" -c 1 -f -o gpurun_out/${TAG}_prof_chase \
+  python tools/fit_check.py default 5000 > gpurun_out/${TAG}_ncu_chase.log 2>&1; echo "ncu chase rc=$?"
 timeout -k 10 600 ncu --set full --clock-control none --import-source on -k "regex:k_leaf_stream" -c 2 -f -o gpurun_out/${TAG}_prof_tps \
   python bench.py --config c2 --nrow 8192 --ncol 8192 --knots 5000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_full_tps.log 2>&1; echo "ncu full tps rc=$?"
 python - <<PY
