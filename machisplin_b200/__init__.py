@@ -8,6 +8,6 @@ There is no CPU fallback: creating an Engine without the library or without a GP
 from .engine import Engine, Geom, Spline, Ensemble, as_geom, EVAL_DIRECT, EVAL_FAST  # noqa: F401
 from .mltps import mltps_response, select_models, rss_objective_from_gram, knot_cells  # noqa: F401
 from .tiles import tiles_create, tiles_merge, crop_window  # noqa: F401
-from .geotiff import raster_info, read_raster, read_stack, write_raster  # noqa: F401
+from .geotiff import raster_info, read_raster, read_stack, write_raster, write_geotiff  # noqa: F401
 
 __version__ = "0.1.0"

@@ -91,3 +91,21 @@ def write_raster(path: str, geom, values: np.ndarray, compression: str = "LZW", 
     else:
         a = np.ascontiguousarray(a, dtype=np.float32)
         check(lib.mb_tiff_write_f32(str(path).encode(), C.byref(g), a.ctypes.data_as(_lib.PF), comp, int(epsg), int(threads)))
+
+
+def write_geotiff(layers, geom, out_names=None, out_dir: str = ".", compression: str = "LZW", epsg: int = 0):
+    """``machisplin.write.geotiff(mltps.in, out.names)`` (V73:998-1022), raster part: one ``<name>.tif`` per response layer in
+    ``out_dir`` (the reference writes into ``getwd()``), named after the layer unless ``out_names`` is given.
+    ``layers`` maps layer name -> final raster (nrow x ncol), in response order.  Returns the paths written."""
+    names = list(layers)
+    if out_names is not None:
+        out_names = list(out_names)
+        if len(out_names) < len(names):
+            raise ValueError("out_names is shorter than the number of layers")
+    import os
+    paths = []
+    for i, name in enumerate(names):
+        p = os.path.join(out_dir, f"{out_names[i] if out_names is not None else name}.tif")
+        write_raster(p, geom, layers[name], compression=compression, epsg=epsg)
+        paths.append(p)
+    return paths

@@ -164,3 +164,48 @@ def test_read_stack_checks_the_grids(tmp_path):
     mb.write_raster(str(tmp_path / "c.tif"), mb.Geom(10.0, 10.6, -2.0, -1.8, 20, 50), a)
     with pytest.raises(ValueError):
         mb.read_stack([str(tmp_path / "a.tif"), str(tmp_path / "c.tif")])
+
+
+def test_write_geotiff_names_layers_like_the_reference(tmp_path):
+    """machisplin.write.geotiff (V73:998-1022): <layer>.tif per response, or out.names"""
+    g = mb.Geom(0.0, 4.0, 0.0, 3.0, 3, 4)
+    layers = {"bio1": np.arange(12, dtype=np.float64).reshape(3, 4), "bio12": np.full((3, 4), np.nan)}
+    paths = mb.write_geotiff(layers, g, out_dir=str(tmp_path))
+    assert [os.path.basename(p) for p in paths] == ["bio1.tif", "bio12.tif"]
+    assert same(mb.read_raster(paths[0])[1], layers["bio1"].astype(np.float32))
+    assert np.isnan(mb.read_raster(paths[1])[1]).all()
+    paths = mb.write_geotiff(layers, g, out_names=["temp", "prec"], out_dir=str(tmp_path))
+    assert [os.path.basename(p) for p in paths] == ["temp.tif", "prec.tif"]
+    with pytest.raises(ValueError):
+        mb.write_geotiff(layers, g, out_names=["only_one"], out_dir=str(tmp_path))
+
+
+def test_corrupted_files_fail_cleanly(tmp_path):
+    """random byte flips and truncations of the golden fixture: an error or a raster, never a crash or an out-of-bounds write"""
+    src = open(os.path.join(GOLD, "twi_2x2_tiles.tif"), "rb").read()
+    ifd_at = int.from_bytes(src[4:8], "little")
+    rng = np.random.default_rng(11)
+    p = str(tmp_path / "f.tif")
+    outcomes = {"ok": 0, "err": 0}
+    for it in range(60):
+        b = bytearray(src)
+        mode = it % 4
+        if mode == 0:
+            for _ in range(rng.integers(1, 6)):
+                b[rng.integers(ifd_at - 200, len(b))] = rng.integers(0, 256)
+        elif mode == 1:
+            for _ in range(rng.integers(1, 40)):
+                b[rng.integers(8, ifd_at - 200)] = rng.integers(0, 256)
+        elif mode == 2:
+            b = b[:rng.integers(8, len(b))]
+        else:
+            b[rng.integers(0, 8)] = rng.integers(0, 256)
+        open(p, "wb").write(bytes(b))
+        try:
+            info = mb.raster_info(p)
+            if info.geom.nrow * info.geom.ncol <= 1_000_000:
+                mb.read_raster(p)
+            outcomes["ok"] += 1
+        except (MbError, MemoryError):
+            outcomes["err"] += 1
+    assert outcomes["err"] > 0 and outcomes["ok"] + outcomes["err"] == 60
