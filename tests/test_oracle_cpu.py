@@ -216,3 +216,33 @@ def test_model_descriptors_match_scikit_learn_predict():
     v = m["v"]
     ref = sk["v"].predict((X - v["x_center"]) / v["x_scale"]) * v["y_scale"] + v["y_center"]
     np.testing.assert_allclose(om.predict_svm_exact(v, X), ref, rtol=1e-9)
+
+
+def test_gcv_criterion_against_the_brute_force_hat_matrix():
+    """Independent of the eigen-decomposition the oracle (and the engine) search on: the smoother matrix A(lambda) from the
+    full block system [[K + lambda I, T], [T', 0]], trA = trace(A), GCV = (RSS / n) / (1 - trA / n)^2 (Krig.fgcv with cost 1).
+    The oracle's eff.df and GCV value agree with it, and the lambda it selects minimises the brute-force criterion."""
+    rng = np.random.default_rng(21)
+    n = 160
+    xy = rng.uniform(0, 1, (n, 2)) * [2.0, 1.0] + [3.0, 40.0]
+    y = np.sin(3 * xy[:, 0]) * np.cos(5 * xy[:, 1]) + 0.15 * rng.standard_normal(n)
+    fit = otps.tps_fit(xy, y)
+    s = fit.knots_s
+    K = otps.rad_cov(s, s)
+    T = np.column_stack([np.ones(n), s])
+
+    def brute(lam):
+        S = np.block([[K + lam * np.eye(n), T], [T.T, np.zeros((3, 3))]])
+        sol = np.linalg.solve(S, np.vstack([np.eye(n), np.zeros((3, n))]))
+        A = K @ sol[:n] + T @ sol[n:]                  # fitted values = A y
+        r = y - A @ y
+        tra = np.trace(A)
+        return float(r @ r) / n / (1.0 - tra / n) ** 2, tra
+
+    D = np.concatenate([np.zeros(3), 1.0 / fit.eta])
+    g_star, tra_star = brute(fit.lam)
+    assert abs(tra_star - fit.eff_df) < 1e-7 * fit.eff_df
+    assert abs(g_star - otps.gcv_value(fit.lam, D, fit.u, fit.n_obs, fit.pure_ss)) < 1e-8 * g_star
+    assert not fit.gcv_at_endpoint
+    for f in (0.5, 0.7, 0.85, 0.95, 1.05, 1.15, 1.3, 2.0):
+        assert brute(fit.lam * f)[0] >= g_star * (1 - 1e-9), f
