@@ -264,6 +264,9 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 3,
                  "sytrd_mode must be 0 (default = two-stage), 1 (one-stage persistent kernel), 2 (one-stage, kernel per phase) or 3 (two-stage)");
       ctx->sytrd_mode = value;
+    } else if (n == "svm_impl") {
+      MB_REQUIRE(value == 0 || value == 1, "svm_impl must be 0 (packed FP32) or 1 (3 x TF32 tensor-core dot products, experimental)");
+      ctx->svm_impl = value;
     } else if (n == "defer_ensemble") {
       MB_REQUIRE(value == 0 || value == 1, "defer_ensemble must be 0 or 1");
       ctx->defer_ensemble = value;

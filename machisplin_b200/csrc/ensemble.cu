@@ -59,6 +59,10 @@ struct mb_ensemble {
   int svm_pairs = 0;                 // ceil(S / 2)
   mb::DevBuf<float4> svm_svp;        // [pair][NQ]: (sv_2j[2q], sv_2j+1[2q], sv_2j[2q+1], sv_2j+1[2q+1]) x 2 sigma log2e
   mb::DevBuf<float4> svm_bap;        // [pair]: (b_2j, b_2j+1, alpha_2j, alpha_2j+1), b = -sigma |sv|^2 log2e
+  // tensor-core variant (k_ens_svm_mma, "svm_impl" = 1, P <= 8; built only when that variant is selected at create time):
+  int svm_oct = 0;                   // ceil(S / 8)
+  mb::DevBuf<float4> svm_bq;         // [octet][lane]: B fragments of mma.m16n8k8.tf32, (hi f=tig, hi f=tig+4, lo f=tig, lo f=tig+4) of SV 8o + (lane >> 2)
+  mb::DevBuf<float4> svm_baq;        // svm_bap padded with zeros to 4 pairs per octet
   mb::DevBuf<double> svm_xc, svm_xis; // centre, 1/scale
   double svm_bias = 0, svm_sigma = 0, svm_yc = 0, svm_ys = 1;
   // trees
@@ -688,6 +692,27 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
     e->svm_bias = m.svm_b; e->svm_sigma = m.svm_sigma; e->svm_yc = m.svm_y_center; e->svm_ys = m.svm_y_scale;
     e->svp_sv.upload(m.svm_sv, (size_t)S * P, st);
     e->svp_alpha.upload(m.svm_alpha, S, st);
+    if (ctx->svm_impl == 1 && P <= 8) {
+      // 3 x TF32 operands: value = hi + lo with hi, lo exactly representable in TF32 (low 13 mantissa bits zero)
+      auto tf32 = [](float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; float y; std::memcpy(&y, &u, 4); return y; };
+      const int noct = (S + 7) / 8;
+      std::vector<float4> bq((size_t)noct * 32, make_float4(0.f, 0.f, 0.f, 0.f)), baq((size_t)noct * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      for (int o = 0; o < noct; ++o)
+        for (int ln = 0; ln < 32; ++ln) {
+          const int i = 8 * o + (ln >> 2), tig = ln & 3;
+          if (i >= S) continue;
+          float v[2];
+          for (int fh = 0; fh < 2; ++fh) {
+            const int f = tig + 4 * fh;
+            v[fh] = f < P ? (float)(2.0 * m.svm_sigma * l2e * m.svm_sv[(size_t)i * P + f]) : 0.f;
+          }
+          const float h0 = tf32(v[0]), h1 = tf32(v[1]);
+          bq[(size_t)o * 32 + ln] = make_float4(h0, h1, tf32(v[0] - h0), tf32(v[1] - h1));
+        }
+      for (int pr = 0; pr < npairs; ++pr) baq[pr] = bap[pr];
+      e->svm_oct = noct;
+      e->svm_bq.upload(bq, st); e->svm_baq.upload(baq, st);
+    }
   }
   std::vector<int2> nodes;          // both forests, rf first (child indices are absolute)
   std::vector<int> froots;
@@ -855,6 +880,134 @@ static void launch_trees(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
 
 static SmoothParams smooth_params(const mb_ensemble* e);
 
+
+// ---------------------------------------------------------------------------------------------
+// k_ens_svm_mma ("svm_impl" = 1, P <= 8; NOT the default - see DESIGN.md section 9): the 8-feature dot products of
+// k_ens_svm on the tensor pipe.  ncu (r1s) shows k_ens_svm bound by the FMA pipe (67 % busy: 16 of the 20 packed FP32
+// instructions per 2 SV x 2 cells are the dot products), with MUFU.EX2 at 53 %; moving the dot products to
+// mma.sync.m16n8k8.tf32 leaves 2 FADD2 + 2 FFMA2 + 4 MUFU per 16 cells x 8 SVs per M-tile on the other pipes.
+// Accuracy: 3 x TF32 (x = x_hi + x_lo, sv = sv_hi + sv_lo, products hi.hi + hi.lo + lo.hi, FP32 accumulation), i.e. a
+// relative error of ~2^-21 per product instead of TF32's 2^-11 - the exponent needs ~1e-6 absolute.
+// A warp owns 32 cells of one row = two 16-cell M-tiles; the A fragments (cells x features) stay in registers for the whole
+// support-vector loop, the B fragments (features x 8 SVs) come pre-shuffled from the host, one LDS.128 per octet.
+// Fragment layouts (PTX ISA, m16n8k8 .tf32; g = lane >> 2, t = lane & 3):  A a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);
+// B b0 (k = t, n = g) b1 (k = t+4, n = g);  C/D c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSvmOct = 32;          // octets (256 support vectors) per shared-memory stage
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+__global__ void __launch_bounds__(kSvmThreads) k_ens_svm_mma(
+    const float* __restrict__ cov, int C, int P, int64_t plane, EnsGeom eg, mb_window w,
+    const float4* __restrict__ bq, const float4* __restrict__ baq, int noct,
+    const double* __restrict__ xc, const double* __restrict__ xis, double sigma, double bias, double ys, double yc,
+    double wv, int accumulate, SmoothParams sp, int64_t acc_stride, double* __restrict__ acc) {
+  __shared__ float4 s_bq[kSvmOct * 32];
+  __shared__ float4 s_ba[kSvmOct * 4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int row = w.r0 + blockIdx.y * 8 + warp;
+  const int col_first = w.c0 + blockIdx.x * 32;
+  // the float64 smooth models of the cell this thread OWNS (cell `lane` of the strip)
+  const int ocol = col_first + lane;
+  const bool olive = ocol < w.c1 && row < w.r1;
+  double smooth = 0.0;
+  if ((sp.gam || sp.nn || sp.mars_T > 0) && olive) smooth = smooth_cell(cov, C, plane, eg, row, ocol, sp);
+  // A fragments of the two M-tiles
+  float ah[2][4], al[2][4], a0c[2][2];
+  int nanf[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int col = col_first + 16 * mt + g + 8 * hr;
+      const bool live = col < w.c1 && row < w.r1;
+      double n2 = 0.0;
+      int anynan = 0;
+#pragma unroll
+      for (int fh = 0; fh < 2; ++fh) {
+        const int f = t + 4 * fh;
+        double xs = 0.0;
+        if (f < P) {
+          double v;
+          if (f < C) v = live ? (double)__ldg(&cov[f * plane + (int64_t)row * eg.ncol + col]) : 0.0;
+          else if (f == C) v = eg.xmin + (col + 0.5) * eg.rx;
+          else v = eg.ymax - (row + 0.5) * eg.ry;
+          anynan |= (v != v);
+          xs = (v - xc[f]) * xis[f];
+        }
+        n2 += xs * xs;
+        const float xf = (float)xs;
+        const float hi = to_tf32(xf);
+        ah[mt][hr + 2 * fh] = hi;
+        al[mt][hr + 2 * fh] = to_tf32(xf - hi);
+      }
+      n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+      n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+      anynan |= __shfl_xor_sync(0xffffffffu, anynan, 1);
+      anynan |= __shfl_xor_sync(0xffffffffu, anynan, 2);
+      a0c[mt][hr] = (float)(-sigma * n2 * 1.4426950408889634);
+      nanf[mt][hr] = anynan;
+    }
+  float2 part[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) part[mt][hr] = make_float2(0.f, 0.f);
+  for (int base = 0; base < noct; base += kSvmOct) {
+    const int n = min(kSvmOct, noct - base);
+    __syncthreads();
+    for (int i = tid; i < n * 32; i += kSvmThreads) s_bq[i] = __ldg(&bq[(size_t)base * 32 + i]);
+    for (int i = tid; i < n * 4; i += kSvmThreads) s_ba[i] = __ldg(&baq[(size_t)base * 4 + i]);
+    __syncthreads();
+#pragma unroll 2
+    for (int o = 0; o < n; ++o) {
+      const float4 bf = s_bq[o * 32 + lane];
+      const float4 ba = s_ba[o * 4 + t];          // (b, b, alpha, alpha) of support vectors 2t, 2t+1 of the octet
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float d[4] = {a0c[mt][0] + ba.x, a0c[mt][0] + ba.y, a0c[mt][1] + ba.x, a0c[mt][1] + ba.y};
+        mma_tf32(d, al[mt], bf.x, bf.y);          // x_lo . sv_hi
+        mma_tf32(d, ah[mt], bf.z, bf.w);          // x_hi . sv_lo
+        mma_tf32(d, ah[mt], bf.x, bf.y);          // x_hi . sv_hi
+        part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), ex2_approx(d[1])), part[mt][0]);
+        part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), ex2_approx(d[3])), part[mt][1]);
+      }
+    }
+  }
+  // per-cell totals: the four lanes of a group hold the 8 support-vector columns; then to the lane that owns the cell
+  double mine = 0.0;
+  int mynan = 0;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      double tot = (double)part[mt][hr].x + (double)part[mt][hr].y;
+      tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+      tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+      // cell 16 mt + 8 hr + g lives in lanes 4 g .. 4 g + 3; its owner is lane 16 mt + 8 hr + g
+      const double v = __shfl_sync(0xffffffffu, tot, 4 * (lane & 7));
+      const int nf = __shfl_sync(0xffffffffu, nanf[mt][hr], 4 * (lane & 7));
+      if ((lane >> 4) == mt && ((lane >> 3) & 1) == hr) { mine = v; mynan = nf; }
+    }
+  if (olive) {
+    double* dst = acc + (int64_t)(row - w.r0) * acc_stride + (ocol - w.c0);
+    double v = __longlong_as_double(0x7ff8000000000000LL);
+    if (!mynan) v = (accumulate ? *dst : 0.0) + wv * ((mine - bias) * ys + yc) + smooth;
+    *dst = v;
+  }
+}
+
 template <int NQ>
 static void launch_svm(const mb_ensemble* e, const float* cov, int64_t plane, const EnsGeom& eg, const mb_window& w,
                        double* acc, int accumulate, cudaStream_t st) {
@@ -894,7 +1047,12 @@ void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
     launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, st);
     started = true;
   }
-  if (e->has[MB_V]) {
+  if (e->has[MB_V] && ctx->svm_impl == 1 && e->svm_oct > 0) {
+    dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
+    MB_LAUNCH(ctx, "k_ens_svm_mma", st) k_ens_svm_mma<<<grid, kSvmThreads, 0, st>>>(
+        cov, e->C, e->P, plane, eg, w, e->svm_bq.p, e->svm_baq.p, e->svm_oct, e->svm_xc.p, e->svm_xis.p, e->svm_sigma,
+        e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], started ? 1 : 0, smooth_params(e), astride, acc);
+  } else if (e->has[MB_V]) {
     switch ((e->P + 1) / 2) {
 #define MB_SVM_CASE(n) case n: launch_svm<n>(e, cov, plane, eg, w, acc, started ? 1 : 0, st); break;
       MB_SVM_CASE(1) MB_SVM_CASE(2) MB_SVM_CASE(3) MB_SVM_CASE(4) MB_SVM_CASE(5) MB_SVM_CASE(6) MB_SVM_CASE(7)

@@ -216,3 +216,24 @@ def test_tiled_mode_is_independent_of_lane_concurrency(engine, case):
         engine.tiles_tps_dev(geom, xy, y, out.data_ptr(), tile_px=60, stream=s.cuda_stream)
     s.synchronize()
     np.testing.assert_array_equal(a, out.cpu().numpy())
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
+                    reason="k_ens_svm_mma (svm_impl = 1) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
+@pytest.mark.parametrize("kept", ["v", "gnmv", "bgnmrv"])
+def test_svm_tensor_core_variant(engine, case, kept):
+    """ksvm dot products on the tensor pipe (3 x TF32, k_ens_svm_mma): same tolerance as the packed-FP32 kernel, same NA mask,
+    ragged window (160 x 224 is not a multiple of the 8-row CTA tile in general windows)."""
+    geom, C, models, cov = case
+    ws = [1.0 / len(kept)] * len(kept)
+    ref = cbind.ensemble_eval(models, kept, ws, 1.0, cov, geom.as_tuple())
+    try:
+        engine.set_param("svm_impl", 1)
+        ens = engine.ensemble_create(geom, models, kept, ws, 1.0, C + 2)
+        got = engine.ensemble_eval(ens, cov)
+        sub = (3, 150, 5, 201)
+        got_w = engine.ensemble_eval(ens, cov, window=sub)
+    finally:
+        engine.set_param("svm_impl", 0)
+    _cmp(got, ref, 5e-6)
+    _cmp(got_w, ref[sub[0]:sub[1], sub[2]:sub[3]], 5e-6)
