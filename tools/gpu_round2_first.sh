@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 timeout -k 10 600 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
 MB_EXPERIMENTAL=1 timeout -k 10 200 python -m pytest tests/test_ensemble_gpu.py -m gpu -q -k svm_tensor > gpurun_out/${TAG}_pytest_svm_mma.log 2>&1; echo "svm_mma pytest rc=$?"; tail -15 gpurun_out/${TAG}_pytest_svm_mma.log
 timeout -k 10 300 python bench.py > gpurun_out/${TAG}_bench_c3.json 2> gpurun_out/${TAG}_bench_c3.err; echo "bench rc=$?"
-timeout -k 10 300 python bench.py --no-cpu-baseline --param svm_impl=1 > gpurun_out/${TAG}_bench_c3_svm_mma.json 2> gpurun_out/${TAG}_bench_c3_svm_mma.err; echo "bench svm_mma rc=$?"
+timeout -k 10 300 python bench.py --param svm_impl=1 > gpurun_out/${TAG}_bench_c3_svm_mma.json 2> gpurun_out/${TAG}_bench_c3_svm_mma.err; echo "bench svm_mma rc=$?"
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 python - <<PY
