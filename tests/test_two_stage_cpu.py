@@ -54,3 +54,18 @@ def test_panel_qr_is_a_qr():
         QtP = Q.T @ P
         assert np.abs(np.tril(QtP, -1)).max() < 1e-12 * np.abs(P).max()
         assert np.abs(np.triu(QtP)[:min(r, b)] - np.triu(X)[:min(r, b)]).max() < 1e-12
+
+
+@pytest.mark.parametrize("m,b", [(40, 8), (131, 32), (200, 32), (70, 32)])
+def test_coefficients_from_the_band_form(m, b):
+    """(M + lambda I)^-1 z = Q1 (B + lambda I)^-1 Q1'z with a block band Cholesky: the planned replacement of the dense
+    Cholesky at the selected lambda agrees with the dense solve."""
+    rng = np.random.default_rng(m)
+    Qr, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    M = (Qr * (6.0 * np.exp(-np.linspace(0, 20, m)))) @ Qr.T
+    M = 0.5 * (M + M.T)
+    z = rng.standard_normal((m, 2))
+    lam = 3e-3
+    ref = np.linalg.solve(M + lam * np.eye(m), z)
+    got = proto.coefficients_from_band(M, z, lam, b)
+    assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()

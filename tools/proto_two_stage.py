@@ -249,6 +249,89 @@ def check(m, b, L=2, seed=0, random_schedule=False):
                 rss_rel=abs(rss - rss_ref) / rss_ref, znorm=abs(np.linalg.norm(zh) - np.linalg.norm(z)))
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# Coefficients at the selected lambda from the BAND form instead of a dense Cholesky of M + lambda I (DESIGN.md section 9,
+# not implemented on the device yet):  M = Q1 B Q1' after stage 1, so (M + lambda I)^-1 z = Q1 (B + lambda I)^-1 Q1'z.
+# Q1'z is what stage 1 leaves in z; B + lambda I is banded (b sub-diagonals): block Cholesky with 32 x 32 blocks, O(m b^2);
+# Q1 = H_1 ... H_K is applied panel by panel, last panel first, from the stored compact-WY factors (V_k, T_k).
+# ---------------------------------------------------------------------------------------------------------------------------
+def stage1_keep(A: np.ndarray, z: np.ndarray, b: int):
+    """stage1() that also returns the compact-WY factors of every panel: list of (row offset, V, T)."""
+    m = A.shape[0]
+    j0 = 0
+    panels = []
+    while m - j0 - b >= 2:
+        P = A[j0 + b:, j0:j0 + b]
+        V, T, nref = panel_qr(P)
+        for c in range(b):
+            P[c + 1:, c] = 0.0
+        A[j0:j0 + b, j0 + b:] = P.T
+        A22 = A[j0 + b:, j0 + b:]
+        Z0 = A22 @ V
+        S = T.T @ (V.T @ Z0) @ T
+        W = Z0 @ T - 0.5 * V @ S
+        z[j0 + b:, :] -= V @ (T.T @ (V.T @ z[j0 + b:, :]))
+        A22 -= V @ W.T + W @ V.T
+        panels.append((j0 + b, V.copy(), T.copy()))
+        j0 += b
+    return panels
+
+
+def band_cholesky_solve(B: np.ndarray, m: int, b: int, lam: float, rhs: np.ndarray) -> np.ndarray:
+    """Solves (Bmat + lam I) x = rhs for the symmetric band matrix in lower band storage B[off, j] (off <= b), by a block
+    Cholesky with b x b blocks: diagonal block potrf, one sub-diagonal block trsm, one trailing syrk per block column -
+    what one persistent CTA would do, 156 steps at m = 5000."""
+    nb = (m + b - 1) // b
+
+    def blk(I, J):            # dense b x b block (I >= J) of the band matrix, zero outside the band / the matrix
+        out = np.zeros((b, b))
+        for p_ in range(b):
+            for q_ in range(b):
+                i, j = I * b + p_, J * b + q_
+                if i < m and j < m and 0 <= i - j <= b:
+                    out[p_, q_] = B[i - j, j]
+                elif i < m and j < m and 0 < j - i <= b and I == J:
+                    out[p_, q_] = B[j - i, i]
+        if I == J:
+            for p_ in range(b):
+                i = I * b + p_
+                out[p_, p_] = out[p_, p_] + lam if i < m else 1.0      # pad the last block with the identity
+        return out
+
+    Ld, Ls = [], []            # diagonal factors L_jj, sub-diagonal blocks L_{j+1,j}
+    D = blk(0, 0)
+    for j in range(nb):
+        Ljj = np.linalg.cholesky(D)
+        Ld.append(Ljj)
+        if j + 1 < nb:
+            S_ = blk(j + 1, j)
+            Lsj = np.linalg.solve(Ljj, S_.T).T          # L_{j+1,j} = A_{j+1,j} L_jj^-T
+            Ls.append(Lsj)
+            D = blk(j + 1, j + 1) - Lsj @ Lsj.T
+    x = np.zeros((nb * b, rhs.shape[1]))
+    x[:m] = rhs
+    for j in range(nb):                                  # forward
+        x[j * b:(j + 1) * b] = np.linalg.solve(Ld[j], x[j * b:(j + 1) * b])
+        if j + 1 < nb:
+            x[(j + 1) * b:(j + 2) * b] -= Ls[j] @ x[j * b:(j + 1) * b]
+    for j in range(nb - 1, -1, -1):                      # backward
+        if j + 1 < nb:
+            x[j * b:(j + 1) * b] -= Ls[j].T @ x[(j + 1) * b:(j + 2) * b]
+        x[j * b:(j + 1) * b] = np.linalg.solve(Ld[j].T, x[j * b:(j + 1) * b])
+    return x[:m]
+
+
+def coefficients_from_band(M: np.ndarray, z: np.ndarray, lam: float, b: int) -> np.ndarray:
+    A = M.copy()
+    z1 = z.copy()
+    panels = stage1_keep(A, z1, b)
+    B = to_band(A, b)
+    y = band_cholesky_solve(B, M.shape[0], b, lam, z1)
+    for (r0, V, T) in reversed(panels):                  # beta = Q1 y,  H_k = I - V T V'
+        y[r0:] -= V @ (T @ (V.T @ y[r0:]))
+    return y
+
+
 if __name__ == "__main__":
     for (m, b) in [(37, 8), (64, 8), (65, 8), (100, 32), (131, 32), (200, 32), (3, 8), (10, 8), (34, 32), (35, 32)]:
         print(check(m, b))
