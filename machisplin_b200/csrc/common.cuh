@@ -155,6 +155,19 @@ struct mb_timed_launch {
   cudaEvent_t start, stop;
 };
 
+// What the two-stage tridiagonalisation leaves behind for the coefficient solve at the selected lambda ("coef_impl" = 1):
+// M = Q1 B Q1' with B banded, Q1 = H_1 ... H_K in compact-WY form.  All pointers are arena memory of the current call.
+struct mb_band_form {
+  bool valid = false;
+  int m = 0, L = 0, npanel = 0, rmax = 0;
+  double* Vall = nullptr;            // panel k: V at Vall + voff[k], ldv[k] x 32 column-major, rows r0[k] .. m-1 of the matrix
+  double* Tall = nullptr;            // 32 x 32 row-major per panel
+  double* band = nullptr;            // 64 x (m + 64) band storage after stage 1
+  double* z1 = nullptr;              // Q1' z, m x L
+  std::vector<size_t> voff;
+  std::vector<int> r, ldv, r0;
+};
+
 struct mb_ctx {
   int device = 0;
   bool timing = false;
@@ -177,6 +190,9 @@ struct mb_ctx {
   std::vector<double> dbg_band;
   cudaStream_t sbr_aux = nullptr;   // two-stage path: stream of the look-ahead trailing updates + its events
   cudaEvent_t sbr_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int coef_impl = 0;          // coefficients at the selected lambda: 0 = dense Cholesky of M + lambda I, 1 = band form of the two-stage
+                              // reduction (block band Cholesky + back-transformation; experimental)
+  mb_band_form band_form;
   int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers
   int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits
   int sytrd_ctas_per_sm = 0;  // persistent grid size (0 = 2 per SM)

@@ -16,6 +16,10 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
 void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L, double* d_dev, double* e_dev,
                       cudaStream_t st);
 
+// (M + lambda I)^-1 z_r from the band form kept by the last sym_band_tridiag of this call (ctx->band_form.valid): block band
+// Cholesky + back-transformation by the stored panel reflectors.  out_dev: m doubles.  False if the form cannot be used.
+bool band_coefficients(mb_ctx* ctx, double lambda, int rhs, double* out_dev, cudaStream_t st);
+
 // ensemble.cu - terra::predict x6 + weighted sum (V73:468-619) + part-5 combine (V73:906-907)
 mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, const char* kept, const double* w,
                              double w_total);

@@ -883,6 +883,260 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Coefficients from the band form ("coef_impl" = 1; experimental, see DESIGN.md section 9 and tools/proto_two_stage.py
+// coefficients_from_band):  (M + lam I)^-1 z = Q1 (B + lam I)^-1 Q1'z.
+// k_band_solve: ONE warp.  Block Cholesky of B + lam I with 32 x 32 blocks (lane = row; diagonal block potrf, its inverse,
+// L_{j+1,j} = A_{j+1,j} L_jj^-T, next diagonal block -= L_{j+1,j} L_{j+1,j}'), factors kept in global memory, then forward and
+// backward substitution of one right-hand side as 32 x 32 matrix-vector products.  O(m b^2) flops, m / 32 dependent steps.
+// ---------------------------------------------------------------------------------------------
+struct BandSolveArgs {
+  const double* Bd; int m; double lam;
+  double* fac;                     // [nb][2][1024]: Linv_j (row-major, lower), Ls_j = L_{j+1,j} (row-major)
+  double* x;                       // nb * 32 doubles: right-hand side in, solution out (rows >= m are zero)
+  int* err;                        // set to 1 if a pivot is not positive
+};
+
+__global__ void __launch_bounds__(32) k_band_solve(BandSolveArgs a) {
+  __shared__ double B0[32][kPad], B1[32][kPad], B2[32][kPad];
+  __shared__ double xs[32], tv[32], xn[32];
+  const int l = threadIdx.x, m = a.m;
+  constexpr int b = 32;
+  const int nb = (m + b - 1) / b;
+  double (*D)[kPad] = B0;          // current diagonal block / its Cholesky factor, then L_{j+1,j}
+  double (*S)[kPad] = B1;          // sub-diagonal block, then the next diagonal block
+  double (*Li)[kPad] = B2;         // inverse of the diagonal factor
+  // diagonal block J of B + lam I, lower part, identity padding past m
+  auto load_diag = [&](double (*dst)[kPad], int J) {
+    const int i = J * b + l;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      const int j = J * b + q;
+      double v = 0.0;
+      if (q <= l) {
+        if (i < m) v = __ldcg(a.Bd + (i - j) + (size_t)j * kLdb) + (q == l ? a.lam : 0.0);
+        else v = q == l ? 1.0 : 0.0;
+      }
+      dst[l][q] = v;
+    }
+  };
+  load_diag(D, 0);
+  for (int j = 0; j < nb; ++j) {
+    // ---- D = L L' in place (lower), lane = row ----------------------------------------------------------------
+    for (int c = 0; c < 32; ++c) {
+      __syncwarp();
+      const double dcc = D[c][c];
+      if (!(dcc > 0.0) && l == 0) *a.err = 1;
+      const double dd = sqrt(dcc > 0.0 ? dcc : 1.0);
+      const double lic = l > c ? D[l][c] / dd : 0.0;
+      __syncwarp();
+      if (l == c) D[c][c] = dd;
+      else if (l > c) D[l][c] = lic;
+      __syncwarp();
+      for (int q = c + 1; q <= l; ++q) D[l][q] -= lic * D[q][c];
+    }
+    __syncwarp();
+    // ---- Li = L^-1, lane = column --------------------------------------------------------------------------------
+    for (int i = 0; i < 32; ++i) {
+      double sacc = 0.0;
+      if (i >= l) {
+        sacc = i == l ? 1.0 : 0.0;
+        for (int k = l; k < i; ++k) sacc -= D[i][k] * Li[k][l];
+        sacc /= D[i][i];
+      }
+      Li[i][l] = sacc;
+    }
+    __syncwarp();
+    double* fj = a.fac + (size_t)j * 2048;
+    for (int i = 0; i < 32; ++i) fj[i * 32 + l] = Li[i][l];
+    if (j + 1 < nb) {
+      // ---- S = A_{j+1,j}: rows (j+1) b + l, columns j b + q, inside the band for l <= q -------------------------
+      {
+        const int i = (j + 1) * b + l;
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) {
+          const int jj = j * b + q;
+          S[l][q] = (l <= q && i < m) ? __ldcg(a.Bd + (i - jj) + (size_t)jj * kLdb) : 0.0;
+        }
+      }
+      __syncwarp();
+      // ---- Ls = S Li' (into D: the factor itself is not needed any more), lane = row -------------------------------
+      for (int c = 0; c < 32; ++c) {
+        double sacc = 0.0;
+        for (int k = 0; k <= c; ++k) sacc = fma(S[l][k], Li[c][k], sacc);
+        D[l][c] = sacc;
+      }
+      __syncwarp();
+      for (int i = 0; i < 32; ++i) fj[1024 + i * 32 + l] = D[i][l];
+      // ---- next diagonal block = A_{j+1,j+1} + lam I - Ls Ls' (into S), lane = row ----------------------------------
+      load_diag(S, j + 1);
+      __syncwarp();
+      for (int q = 0; q <= l; ++q) {
+        double sacc = 0.0;
+        for (int k = 0; k < 32; ++k) sacc = fma(D[l][k], D[q][k], sacc);
+        S[l][q] -= sacc;
+      }
+      __syncwarp();
+      double (*tmp)[kPad] = D; D = S; S = tmp;
+    }
+  }
+  __syncwarp();
+  __threadfence_block();
+  // ---- forward substitution: t = Linv_j x_j ; x_{j+1} -= Ls_j t ---------------------------------------------------
+  for (int j = 0; j < nb; ++j) {
+    const double* fj = a.fac + (size_t)j * 2048;
+    for (int i = 0; i < 32; ++i) { Li[i][l] = fj[i * 32 + l]; if (j + 1 < nb) S[i][l] = fj[1024 + i * 32 + l]; }
+    xs[l] = a.x[j * b + l];
+    __syncwarp();
+    double t = 0.0;
+    for (int k = 0; k <= l; ++k) t = fma(Li[l][k], xs[k], t);
+    tv[l] = t;
+    a.x[j * b + l] = t;
+    __syncwarp();
+    if (j + 1 < nb) {
+      double u = 0.0;
+      for (int k = 0; k < 32; ++k) u = fma(S[l][k], tv[k], u);
+      a.x[(j + 1) * b + l] -= u;
+    }
+    __syncwarp();
+  }
+  // ---- backward substitution: x_j -= Ls_j' x_{j+1} ; x_j = Linv_j' x_j ------------------------------------------------
+  for (int j = nb - 1; j >= 0; --j) {
+    const double* fj = a.fac + (size_t)j * 2048;
+    for (int i = 0; i < 32; ++i) { Li[i][l] = fj[i * 32 + l]; if (j + 1 < nb) S[i][l] = fj[1024 + i * 32 + l]; }
+    xs[l] = a.x[j * b + l];
+    xn[l] = j + 1 < nb ? a.x[(j + 1) * b + l] : 0.0;
+    __syncwarp();
+    double v = xs[l];
+    if (j + 1 < nb)
+      for (int k = 0; k < 32; ++k) v = fma(-S[k][l], xn[k], v);
+    tv[l] = v;
+    __syncwarp();
+    double t = 0.0;
+    for (int k = l; k < 32; ++k) t = fma(Li[k][l], tv[k], t);
+    a.x[j * b + l] = t;
+    __syncwarp();
+  }
+}
+
+// k_apply_q1: y <- Q1 y = H_1 ... H_K y, H_k = I - V_k T_k V_k', last panel first.  One thread-block cluster, thread = row of
+// the panel (as in the panel QR): V_k'y is reduced inside the warp by the reduce-scatter butterfly, across warps through shared
+// memory, across the CTAs through distributed shared memory; u = T_k (V_k'y); y -= V_k u.
+struct ApplyQ1Args {
+  const double* Vall; const double* Tall;
+  const unsigned long long* voff; const int* rk; const int* ldvk; const int* r0k;   // device arrays, one entry per panel
+  int npanel;
+  double* y;                       // m doubles
+};
+
+__global__ void __launch_bounds__(kQrRows, 1) k_apply_q1(ApplyQ1Args a) {
+  __shared__ double red[16 * 32], Tsh[32 * kPad], tsh[32], ush[32], part[2 * 32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int t = threadIdx.x, blk = blockIdx.x, G = gridDim.x, lane = t & 31, wid = t >> 5;
+  const int gi = blk * kQrRows + t;
+  for (int k = a.npanel - 1; k >= 0; --k) {
+    const int r = a.rk[k], ldv = a.ldvk[k], r0 = a.r0k[k];
+    const double* V = a.Vall + a.voff[k];
+    const double* T = a.Tall + (size_t)1024 * k;
+    const bool live = gi < r;
+    double vr[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) vr[q] = live ? V[gi + (size_t)q * ldv] : 0.0;
+    for (int i = t; i < 1024; i += kQrRows) Tsh[(i >> 5) * kPad + (i & 31)] = T[i];
+    const double yv = live ? __ldcg(a.y + r0 + gi) : 0.0;
+    // ---- t_q = sum over rows of V[row][q] y[row] ----------------------------------------------------------------
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = vr[16 * h + i] * yv;
+#pragma unroll
+      for (int o = 16, n = 8; n >= 1; o >>= 1, n >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          const double send = up ? v[i] : v[i + n];
+          const double keepv = up ? v[i + n] : v[i];
+          v[i] = keepv + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+      if ((lane & 1) == 0) red[wid * 32 + 16 * h + (lane >> 1)] = v[0];
+    }
+    __syncthreads();
+    double* mine = part + (k & 1) * 32;
+    if (t < 32) {
+      double p = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) p += red[q * 32 + t];
+      mine[t] = p;
+    }
+    cluster.sync();
+    if (t < 32) {
+      double pr[16], s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pr[q] = q < G ? cluster.map_shared_rank(mine, q)[t] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s += pr[q];
+      tsh[t] = s;
+    }
+    __syncthreads();
+    if (t < 32) {
+      double u = 0.0;
+      for (int q = 0; q < 32; ++q) u = fma(Tsh[t * kPad + q], tsh[q], u);
+      ush[t] = u;
+    }
+    __syncthreads();
+    if (live) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) acc = fma(vr[q], ush[q], acc);
+      a.y[r0 + gi] = yv - acc;
+    }
+    __threadfence();
+    cluster.sync();                 // the next panel reads rows that other CTAs have just written
+  }
+}
+
+bool band_coefficients(mb_ctx* ctx, double lambda, int rhs, double* out_dev, cudaStream_t st) {
+  mb_band_form& bf = ctx->band_form;
+  if (!bf.valid || rhs < 0 || rhs >= bf.L) return false;
+  const int m = bf.m, nb = ceil_div(m, 32);
+  // the back-transformation runs as one cluster: the largest panel must fit into 16 x 512 rows
+  int cs = 1;
+  while (cs * kQrRows < std::max(bf.rmax, 1)) cs *= 2;
+  if (bf.npanel > 0 && cs > 16) return false;
+  Arena& ar = ctx->arena;
+  double* fac = ar.take_n<double>((size_t)nb * 2048);
+  double* x = ar.take_n<double>((size_t)nb * 32);
+  int* err = ar.take_n<int>(1);
+  MB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * nb * 32, st));
+  MB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+  MB_CUDA(cudaMemcpyAsync(x, bf.z1 + (size_t)rhs * m, sizeof(double) * m, cudaMemcpyDeviceToDevice, st));
+  BandSolveArgs sa{bf.band, m, lambda, fac, x, err};
+  MB_LAUNCH(ctx, "k_band_solve", st) k_band_solve<<<1, 32, 0, st>>>(sa);
+  if (bf.npanel > 0) {
+    std::vector<unsigned long long> voff(bf.voff.begin(), bf.voff.end());
+    ApplyQ1Args qa{bf.Vall, bf.Tall, ar.upload(voff.data(), voff.size(), st), ar.upload(bf.r.data(), bf.r.size(), st),
+                   ar.upload(bf.ldv.data(), bf.ldv.size(), st), ar.upload(bf.r0.data(), bf.r0.size(), st), bf.npanel, x};
+    static thread_local bool attr = false;
+    if (!attr) { (void)cudaFuncSetAttribute(k_apply_q1, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); attr = true; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MB_LAUNCH(ctx, "k_apply_q1", st) MB_CUDA(cudaLaunchKernelEx(&cfg, k_apply_q1, qa));
+  }
+  MB_CUDA(cudaMemcpyAsync(out_dev, x, sizeof(double) * m, cudaMemcpyDeviceToDevice, st));
+  int herr = 0;
+  MB_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));      // also keeps the uploaded panel tables alive until the kernels are done
+  if (herr) throw Error(MB_E_NUMERIC, "band Cholesky: B + lambda I is not positive definite");
+  return true;
+}
+
 // Reduces the symmetric m x m matrix at A (column-major, leading dimension ld >= m, LOWER triangle valid on entry, both
 // triangles destroyed) to tridiagonal form: d (m) and e (m - 1) on the device; the L right-hand sides z (m x L, ld = m)
 // become Q'z.  Synchronises st.
@@ -890,6 +1144,7 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   MB_REQUIRE(m >= 3 && ld >= m && ld % 2 == 0, "two-stage tridiagonalisation: bad matrix shape");
   MB_REQUIRE(L >= 0 && L <= 32, "at most 32 right-hand sides per tridiagonalisation");
   Arena& ar = ctx->arena;
+  ctx->band_form = mb_band_form();
   // cluster size the panel QR may use: 16 (non-portable) if such a cluster can be scheduled, else 8, else none
   static thread_local int max_cluster = -1;
   if (max_cluster < 0) {
@@ -925,7 +1180,22 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     const int gmax = ceil_div(rmax, kQrRows);
     int npanel = 0;
     for (int j0 = 0; m - j0 - kBw >= 2; j0 += kBw) ++npanel;
-    double* Vb[2] = {ar.take_n<double>((size_t)rpadmax * 32), ar.take_n<double>((size_t)rpadmax * 32)};
+    const bool keep = ctx->coef_impl == 1;
+    mb_band_form& bf = ctx->band_form;
+    if (keep) {
+      size_t tot = 0;
+      for (int j0 = 0; m - j0 - kBw >= 2; j0 += kBw) {
+        const int r = m - j0 - kBw, ldv = ceil_div(r, 128) * 128;
+        bf.voff.push_back(tot); bf.r.push_back(r); bf.ldv.push_back(ldv); bf.r0.push_back(j0 + kBw);
+        tot += (size_t)ldv * 32;
+      }
+      bf.npanel = npanel;
+      bf.rmax = rmax;
+      bf.Vall = ar.take_n<double>(tot);
+      bf.Tall = ar.take_n<double>((size_t)1024 * npanel);
+    }
+    double* Vb[2] = {nullptr, nullptr};
+    if (!keep) { Vb[0] = ar.take_n<double>((size_t)rpadmax * 32); Vb[1] = ar.take_n<double>((size_t)rpadmax * 32); }
     double* Wb[2] = {ar.take_n<double>((size_t)rpadmax * 32), ar.take_n<double>((size_t)rpadmax * 32)};
     double* Z0 = ar.take_n<double>((size_t)rpadmax * 32);
     double* Zp = ar.take_n<double>((size_t)8 * rpadmax * 32);
@@ -948,9 +1218,10 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
       const int r = m - j0 - kBw;
       const int ldv = ceil_div(r, 128) * 128;
       const int rblocks = ldv / 128;
-      double* V = Vb[pk & 1];
+      double* V = keep ? bf.Vall + bf.voff[pk] : Vb[pk & 1];
       double* W = Wb[pk & 1];
-      QrArgs qa{A, ld, m, j0, V, ldv, T, slots, bars + (size_t)64 * pk};
+      double* Tk = keep ? bf.Tall + (size_t)1024 * pk : T;
+      QrArgs qa{A, ld, m, j0, V, ldv, Tk, slots, bars + (size_t)64 * pk};
       const int gq = ceil_div(r, kQrRows);
       if (gq <= max_cluster && ctx->sbr_qr_grid == 0) {
         int cs = 1;
@@ -987,8 +1258,8 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
       MB_LAUNCH(ctx, "k_sbr_av", st) k_sbr_av<<<dim3(rblocks, nsplit), 128, 0, st>>>(A22, ld, r, V, ldv, Zp, chunk);
       MB_LAUNCH(ctx, "k_sbr_vtz", st)
         k_sbr_vtz<<<rblocks, 512, kVtzSmem, st>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
-      MB_LAUNCH(ctx, "k_sbr_st", st) k_sbr_st<<<1, 1024, 0, st>>>(Gp, rblocks, T, ST);
-      MB_LAUNCH(ctx, "k_sbr_w", st) k_sbr_w<<<rblocks, 128, 0, st>>>(V, ldv, r, Z0, T, ST, W, z, m, j0 + kBw, L);
+      MB_LAUNCH(ctx, "k_sbr_st", st) k_sbr_st<<<1, 1024, 0, st>>>(Gp, rblocks, Tk, ST);
+      MB_LAUNCH(ctx, "k_sbr_w", st) k_sbr_w<<<rblocks, 128, 0, st>>>(V, ldv, r, Z0, Tk, ST, W, z, m, j0 + kBw, L);
       if (r > 32) MB_LAUNCH(ctx, "k_sbr_pu", st) k_sbr_pu<<<ceil_div(r - 32, 128), 128, 0, st>>>(A22, ld, r, V, W, ldv);
       MB_CUDA(cudaEventRecord(ctx->sbr_ev[pk & 1], st));
       MB_CUDA(cudaStreamWaitEvent(aux, ctx->sbr_ev[pk & 1], 0));
@@ -1006,6 +1277,16 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   int* prog = ar.take_n<int>((size_t)m + 2);
   MB_CUDA(cudaMemsetAsync(prog, 0, sizeof(int) * ((size_t)m + 2), st));
   MB_LAUNCH(ctx, "k_sbr_band", st) k_sbr_band<<<ceil_div(ncolb, 4), 256, 0, st>>>(A, ld, m, Bd, ncolb);
+  if (ctx->coef_impl == 1 && L > 0) {
+    // band form for the coefficient solve: B and Q1'z as they are now (the chase below overwrites both)
+    mb_band_form& bf = ctx->band_form;
+    bf.m = m; bf.L = L;
+    bf.band = ar.take_n<double>((size_t)kLdb * ncolb);
+    bf.z1 = ar.take_n<double>((size_t)m * L);
+    MB_CUDA(cudaMemcpyAsync(bf.band, Bd, sizeof(double) * kLdb * ncolb, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA(cudaMemcpyAsync(bf.z1, z, sizeof(double) * (size_t)m * L, cudaMemcpyDeviceToDevice, st));
+    bf.valid = true;
+  }
   if (ctx->sbr_debug) {
     ctx->dbg_band.resize((size_t)kLdb * m);
     MB_CUDA(cudaMemcpyAsync(ctx->dbg_band.data(), Bd, sizeof(double) * kLdb * m, cudaMemcpyDeviceToHost, st));

@@ -771,6 +771,12 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
       // ---- Krig.coef at the selected lambda: (M + lambda I) beta = z by the tensor-core Cholesky ----------
       ABuf<double> d_B(ar, m), d_tmp(ar, m);
       for (int r = 0; r < L; ++r) {
+        // experimental ("coef_impl" = 1): from the band form of the two-stage reduction, no dense factorisation
+        if (ctx->coef_impl == 1 && band_coefficients(ctx, lam[r], r, d_B.p, st)) {
+          MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+          MB_CUDA(cudaStreamSynchronize(st));
+          continue;
+        }
         MB_CUDA(cudaMemcpyAsync(d_T.p, M, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToDevice, st));
         MB_LAUNCH(ctx, "k_add_diag", st) k_add_diag<<<(m + 255) / 256, 256, 0, st>>>(d_T.p, m, m, lam[r]);
         const double* d_inv = cholesky_lower(ctx, d_T.p, m, m, st);

@@ -271,3 +271,26 @@ def test_leaf_elongated_knot_cloud(engine, strip):
         finally:
             engine.set_param("eval_precision", 0)
         assert relerr(got, ref) < (2e-6 if mode == 0 else TOL)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
+                    reason="coef_impl = 1 (band-form coefficient solve) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
+@pytest.mark.parametrize("n", [20, 36, 37, 70, 165, 600, 1100])
+def test_coefficients_from_band_form(engine, n):
+    """(M + lambda I)^-1 z from the band form of the two-stage reduction (block band Cholesky + back-transformation by the stored
+    panel reflectors, tools/proto_two_stage.py coefficients_from_band) against the dense Cholesky: same lambda (the search does
+    not depend on it), coefficients to 1e-9, three responses."""
+    geom = synth.make_geom(512, 512)
+    xy, _, _ = synth.make_knots(geom, n, 700 + n)
+    y = synth.residual_field(xy, 700 + n)
+    Y = np.stack([y, y[::-1].copy(), y * y], axis=1)
+    ref = engine.tps_fit(xy, Y)
+    try:
+        engine.set_param("coef_impl", 1)
+        got = engine.tps_fit(xy, Y)
+    finally:
+        engine.set_param("coef_impl", 0)
+    for g, r in zip(got, ref):
+        assert g.lam == r.lam
+        assert np.max(np.abs(g.c - r.c)) <= 1e-9 * np.max(np.abs(r.c))
+        assert np.max(np.abs(g.d - r.d)) <= 1e-9 * max(np.max(np.abs(r.d)), 1e-300)

@@ -59,6 +59,19 @@ for n in sizes:
             g = eng.tps_fit(xy, y)
             eng.set_param("sbr_qr_grid", 0)
             print(f"   grid-barrier QR: lambda rel diff {abs(g.lam - sp0.lam) / sp0.lam:.1e}", flush=True)
+        try:                                   # experimental: coefficients from the band form instead of the dense Cholesky
+            eng.set_param("sytrd_mode", 3); eng.set_param("coef_impl", 1)
+            eng.timing(True); eng.timing_collect()
+            t0 = time.perf_counter()
+            b = eng.tps_fit(xy, y)
+            dt = time.perf_counter() - t0
+            kt = eng.timing_collect(); eng.timing(False)
+            print(f"   coef_impl 1: wall {dt * 1e3:.1f} ms, c err {np.abs(b.c - sp0.c).max() / np.abs(sp0.c).max():.2e}, "
+                  f"k_band_solve {kt.get('k_band_solve', (0, 0))[0]:.2f} ms, k_apply_q1 {kt.get('k_apply_q1', (0, 0))[0]:.2f} ms", flush=True)
+        except Exception:
+            traceback.print_exc()
+        finally:
+            eng.timing(False); eng.set_param("coef_impl", 0)
         for mode in (1, 3):
             eng.set_param("sytrd_mode", mode)
             eng.timing(True); eng.timing_collect()
