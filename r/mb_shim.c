@@ -8,6 +8,7 @@
  */
 #include <R.h>
 #include <Rinternals.h>
+#include <string.h>
 #include "machisplin_b200.h"
 
 #define MB_CHECK(call) do { int rc_ = (call); if (rc_ != MB_OK) Rf_error("machisplin_b200: %s", mb_last_error()); } while (0)
