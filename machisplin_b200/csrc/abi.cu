@@ -264,6 +264,9 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 3,
                  "sytrd_mode must be 0 (default = two-stage), 1 (one-stage persistent kernel), 2 (one-stage, kernel per phase) or 3 (two-stage)");
       ctx->sytrd_mode = value;
+    } else if (n == "sbr_chase_impl") {
+      MB_REQUIRE(value == 0 || value == 1, "sbr_chase_impl must be 0 or 1 (watcher / publisher warps, experimental)");
+      ctx->sbr_chase_impl = value;
     } else if (n == "coef_impl") {
       MB_REQUIRE(value == 0 || value == 1, "coef_impl must be 0 (dense Cholesky) or 1 (band form of the two-stage reduction, experimental)");
       ctx->coef_impl = value;

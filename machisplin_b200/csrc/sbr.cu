@@ -720,35 +720,88 @@ struct ChaseArgs {
 // diagonal block, warp 2 the right-hand sides - their loads are issued together, right after the wait, and the diagonal /
 // right-hand-side updates run beside the left-application of warp 0.  A wait that does not end within ~2^24 polls
 // (seconds; a step takes microseconds) raises the error flag instead of hanging the device.
+//
+// kDec ("sbr_chase_impl" = 1, experimental - DESIGN.md section 9 option (a)): two more warps take the global hand-shakes off
+// the step time.  A WATCHER warp polls the predecessor's progress word (ld.acquire.gpu) into shared memory, so the compute
+// warps check a shared-memory word; a PUBLISHER warp turns "step k stored" (shared memory) into fence + st.release.gpu, so the
+// compute warps go on with step k + 1 at once.  The compute warps then synchronise on named barrier 1 (96 threads).
 constexpr int kChaseThreads = 96;
+constexpr int kChaseThreadsDec = 160;
 
-__global__ void __launch_bounds__(kChaseThreads) k_sbr_chase(ChaseArgs a) {
+template <bool kDec>
+__device__ __forceinline__ void chase_csync() {
+  if (kDec) asm volatile("bar.sync 1, 96;" ::: "memory");
+  else __syncthreads();
+}
+
+template <bool kDec>
+__global__ void __launch_bounds__(kDec ? kChaseThreadsDec : kChaseThreads) k_sbr_chase_t(ChaseArgs a) {
   __shared__ double Bs[32][kPad], Ds[32][kPad], zs[32][kPad];
   __shared__ double vs[32], ws[32], vps[32], ts[32];
   __shared__ double sh_tau;
   __shared__ int sh_s;
+  __shared__ int sh_seen, sh_done;   // kDec: predecessor progress seen by the watcher; steps of this sweep stored
   const int tid = threadIdx.x, l = tid & 31, wid = tid >> 5, m = a.m;
   constexpr int b = kBw;
   for (;;) {
     __syncthreads();
-    if (tid == 0) sh_s = atomicAdd(a.prog + m, 1);
+    if (tid == 0) {
+      sh_s = atomicAdd(a.prog + m, 1);
+      if (kDec) { sh_seen = 0; sh_done = 0; }
+    }
     __syncthreads();
     const int s = sh_s;
     if (s >= m - 2) break;
     const int totp = s > 0 ? (m - s + b - 1) / b : 0;     // steps of sweep s - 1
     const int tot = (m - s - 1 + b - 1) / b;              // steps of this sweep: row blocks below the diagonal of column s
+    if (kDec && wid == 3) {                               // watcher
+      if (l == 0 && s > 0) {
+        const int* p = a.prog + (s - 1);
+        int v = 0, last = 0;
+        long long spins = 0;
+        while (v < totp && ++spins < (1ll << 28)) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+          if (v > last) { *(volatile int*)&sh_seen = v; last = v; }
+        }
+        if (v < totp) atomicExch(a.prog + m + 1, 1);
+      }
+      continue;
+    }
+    if (kDec && wid == 4) {                               // publisher
+      if (l == 0) {
+        int pub = 0;
+        long long spins = 0;
+        while (pub < tot && ++spins < (1ll << 32)) {
+          const int dn = *(volatile int*)&sh_done;
+          if (dn > pub) {
+            __threadfence();                              // cumulative: the compute warps' stores, seen through sh_done
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.prog + s), "r"(dn) : "memory");
+            pub = dn;
+          }
+        }
+        if (pub < tot) atomicExch(a.prog + m + 1, 1);
+      }
+      continue;
+    }
     double taup = 0.0;
     for (int k = 0; k < tot; ++k) {
       if (s > 0 && tid == 0) {
         const int need = min(k + 2, totp);
-        const int* p = a.prog + (s - 1);
-        int v, spins = 0;
-        do {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-        } while (v < need && ++spins < (1 << 24));
-        if (v < need) atomicExch(a.prog + m + 1, 1);
+        if (kDec) {
+          int spins = 0;
+          while (*(volatile int*)&sh_seen < need && ++spins < (1 << 28)) {}
+          if (*(volatile int*)&sh_seen < need) atomicExch(a.prog + m + 1, 1);
+          __threadfence_block();                          // the block loads below stay behind the flag
+        } else {
+          const int* p = a.prog + (s - 1);
+          int v, spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+          } while (v < need && ++spins < (1 << 24));
+          if (v < need) atomicExch(a.prog + m + 1, 1);
+        }
       }
-      __syncthreads();
+      chase_csync<kDec>();
       // block geometry (uniform)
       int st = 0, lp = 0, r0, ln;
       if (k == 0) {
@@ -811,7 +864,7 @@ __global__ void __launch_bounds__(kChaseThreads) k_sbr_chase(ChaseArgs a) {
       } else {
         for (int cc = 0; cc < a.L; ++cc) zs[l][cc] = l < ln ? __ldcg(a.z + (size_t)(r0 + l) + (size_t)cc * m) : 0.0;
       }
-      __syncthreads();
+      chase_csync<kDec>();
       const double tau = sh_tau;
       const double vl = vs[l];
       if (wid == 0) {
@@ -873,8 +926,11 @@ __global__ void __launch_bounds__(kChaseThreads) k_sbr_chase(ChaseArgs a) {
       taup = tau;
       // publish the step: the CTA barrier orders every thread's stores before thread 0's release store (cumulativity), the
       // pattern of a cooperative-groups grid barrier - one fence on the critical path instead of two
-      __syncthreads();
-      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.prog + s), "r"(k + 1) : "memory");
+      chase_csync<kDec>();
+      if (tid == 0) {
+        if (kDec) { __threadfence_block(); *(volatile int*)&sh_done = k + 1; }
+        else asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.prog + s), "r"(k + 1) : "memory");
+      }
     }
   }
 }
@@ -1294,7 +1350,11 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   }
   ChaseArgs ca{Bd, m, z, L, prog};
   const int G = std::max(1, std::min(ctx->sm_count, ceil_div(m, 2 * kBw) + 2));
-  MB_LAUNCH(ctx, "k_sbr_chase", st) k_sbr_chase<<<G, kChaseThreads, 0, st>>>(ca);
+  if (ctx->sbr_chase_impl == 1) {
+    MB_LAUNCH(ctx, "k_sbr_chase_dec", st) k_sbr_chase_t<true><<<G, kChaseThreadsDec, 0, st>>>(ca);
+  } else {
+    MB_LAUNCH(ctx, "k_sbr_chase", st) k_sbr_chase_t<false><<<G, kChaseThreads, 0, st>>>(ca);
+  }
   MB_LAUNCH(ctx, "k_sbr_diag", st) k_sbr_diag<<<ceil_div(m, 256), 256, 0, st>>>(Bd, m, d, e);
   MB_CUDA(cudaGetLastError());
   int chase_err = 0;

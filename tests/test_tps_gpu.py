@@ -294,3 +294,22 @@ def test_coefficients_from_band_form(engine, n):
         assert g.lam == r.lam
         assert np.max(np.abs(g.c - r.c)) <= 1e-9 * np.max(np.abs(r.c))
         assert np.max(np.abs(g.d - r.d)) <= 1e-9 * max(np.max(np.abs(r.d)), 1e-300)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
+                    reason="sbr_chase_impl = 1 (watcher / publisher warps) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
+@pytest.mark.parametrize("n", [36, 70, 200, 1100])
+def test_chase_with_watcher_and_publisher_warps(engine, n):
+    """same arithmetic in the same order as the default chase kernel, only the hand-shakes move to two extra warps: bit-identical"""
+    geom = synth.make_geom(512, 512)
+    xy, _, _ = synth.make_knots(geom, n, 800 + n)
+    y = synth.residual_field(xy, 800 + n)
+    ref = engine.tps_fit(xy, y)
+    try:
+        engine.set_param("sbr_chase_impl", 1)
+        got = engine.tps_fit(xy, y)
+    finally:
+        engine.set_param("sbr_chase_impl", 0)
+    assert got.lam == ref.lam
+    np.testing.assert_array_equal(got.c, ref.c)
+    np.testing.assert_array_equal(got.decomposition()[0], ref.decomposition()[0])

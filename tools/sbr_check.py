@@ -59,6 +59,18 @@ for n in sizes:
             g = eng.tps_fit(xy, y)
             eng.set_param("sbr_qr_grid", 0)
             print(f"   grid-barrier QR: lambda rel diff {abs(g.lam - sp0.lam) / sp0.lam:.1e}", flush=True)
+        try:                                   # experimental: watcher / publisher warps in the bulge chase
+            eng.set_param("sytrd_mode", 3); eng.set_param("sbr_chase_impl", 1)
+            eng.tps_fit(xy, y)
+            eng.timing(True); eng.timing_collect()
+            b = eng.tps_fit(xy, y)
+            kt = eng.timing_collect(); eng.timing(False)
+            print(f"   sbr_chase_impl 1: lambda rel diff {abs(b.lam - sp0.lam) / sp0.lam:.1e}, c err {np.abs(b.c - sp0.c).max() / np.abs(sp0.c).max():.2e}, "
+                  f"k_sbr_chase_dec {kt.get('k_sbr_chase_dec', (0, 0))[0]:.2f} ms", flush=True)
+        except Exception:
+            traceback.print_exc()
+        finally:
+            eng.timing(False); eng.set_param("sbr_chase_impl", 0)
         try:                                   # experimental: coefficients from the band form instead of the dense Cholesky
             eng.set_param("sytrd_mode", 3); eng.set_param("coef_impl", 1)
             eng.timing(True); eng.timing_collect()
