@@ -271,7 +271,7 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value == 0 || value == 1, "coef_impl must be 0 (dense Cholesky) or 1 (band form of the two-stage reduction, experimental)");
       ctx->coef_impl = value;
     } else if (n == "svm_impl") {
-      MB_REQUIRE(value == 0 || value == 1, "svm_impl must be 0 (packed FP32) or 1 (3 x TF32 tensor-core dot products, experimental)");
+      MB_REQUIRE(value >= 0 && value <= 2, "svm_impl must be 0 (packed FP32), 1 (3 x TF32 tensor-core dot products) or 2 (1 + half of the exponentials on the FMA pipe); 1 and 2 are experimental");
       ctx->svm_impl = value;
     } else if (n == "defer_ensemble") {
       MB_REQUIRE(value == 0 || value == 1, "defer_ensemble must be 0 or 1");

@@ -179,7 +179,8 @@ struct mb_ctx {
   // fast-evaluator tunables (0 = automatic)
   int cheb_p = 0, leaf_cols = 0, leaf_rows = 0;
   int tree_rows = 0;          // cells per thread of the tree tile (1, 2, 4; 0 = automatic)
-  int svm_impl = 0;           // ksvm kernel: 0 = packed FP32 (k_ens_svm), 1 = dot products on the tensor pipe (k_ens_svm_mma; set before mb_ensemble_create)
+  int svm_impl = 0;           // ksvm kernel: 0 = packed FP32 (k_ens_svm), 1 = dot products on the tensor pipe (k_ens_svm_mma; set before mb_ensemble_create),
+                              // 2 = 1 + half of the exponentials as a polynomial on the FMA pipe
   // 256-entry (1/m_k, -log(1/m_k)) table for the float64 table-driven log
   mb::DevBuf<double2> logtab;
   int eval_precision = 0;     // fast evaluator: 0 = automatic, 1 = float64 only, 2 = force mixed

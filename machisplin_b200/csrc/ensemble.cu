@@ -692,7 +692,7 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
     e->svm_bias = m.svm_b; e->svm_sigma = m.svm_sigma; e->svm_yc = m.svm_y_center; e->svm_ys = m.svm_y_scale;
     e->svp_sv.upload(m.svm_sv, (size_t)S * P, st);
     e->svp_alpha.upload(m.svm_alpha, S, st);
-    if (ctx->svm_impl == 1 && P <= 8) {
+    if (ctx->svm_impl >= 1 && P <= 8) {
       // 3 x TF32 operands: value = hi + lo with hi, lo exactly representable in TF32 (low 13 mantissa bits zero)
       auto tf32 = [](float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; float y; std::memcpy(&y, &u, 4); return y; };
       const int noct = (S + 7) / 8;
@@ -907,6 +907,27 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], flo
                  "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
+// 2^e for two values on the FMA pipe instead of MUFU.EX2 ("svm_impl" = 2): round-to-nearest split e = n + f through the
+// 1.5 * 2^23 trick, degree-5 minimax polynomial on f in [-0.5, 0.5] (max relative error 1.9e-7, ex2.approx: ~2 ulp), the integer
+// part goes into the exponent field.  e is clamped to [-126, 126] (the exponents of a Gaussian kernel are <= 0).
+__device__ __forceinline__ float2 exp2_poly2(float2 e) {
+  e.x = fminf(fmaxf(e.x, -126.f), 126.f);
+  e.y = fminf(fmaxf(e.y, -126.f), 126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = __fadd2_rn(e, magic);
+  const float2 nf = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(nf, make_float2(-1.f, -1.f), e);
+  float2 p = make_float2(0.0013264744775369763f, 0.0013264744775369763f);
+  p = __ffma2_rn(p, f, make_float2(0.009671512991189957f, 0.009671512991189957f));
+  p = __ffma2_rn(p, f, make_float2(0.05550733581185341f, 0.05550733581185341f));
+  p = __ffma2_rn(p, f, make_float2(0.24022242426872253f, 0.24022242426872253f));
+  p = __ffma2_rn(p, f, make_float2(0.6931470036506653f, 0.6931470036506653f));
+  p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
+}
+
+template <bool kPoly>   // kPoly: half of the exponentials (support vectors 2t + 1) on the FMA pipe
 __global__ void __launch_bounds__(kSvmThreads) k_ens_svm_mma(
     const float* __restrict__ cov, int C, int P, int64_t plane, EnsGeom eg, mb_window w,
     const float4* __restrict__ bq, const float4* __restrict__ baq, int noct,
@@ -980,8 +1001,14 @@ __global__ void __launch_bounds__(kSvmThreads) k_ens_svm_mma(
         mma_tf32(d, al[mt], bf.x, bf.y);          // x_lo . sv_hi
         mma_tf32(d, ah[mt], bf.z, bf.w);          // x_hi . sv_lo
         mma_tf32(d, ah[mt], bf.x, bf.y);          // x_hi . sv_hi
-        part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), ex2_approx(d[1])), part[mt][0]);
-        part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), ex2_approx(d[3])), part[mt][1]);
+        if (kPoly) {
+          const float2 eb = exp2_poly2(make_float2(d[1], d[3]));
+          part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), eb.x), part[mt][0]);
+          part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), eb.y), part[mt][1]);
+        } else {
+          part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), ex2_approx(d[1])), part[mt][0]);
+          part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), ex2_approx(d[3])), part[mt][1]);
+        }
       }
     }
   }
@@ -1047,11 +1074,17 @@ void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
     launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, st);
     started = true;
   }
-  if (e->has[MB_V] && ctx->svm_impl == 1 && e->svm_oct > 0) {
+  if (e->has[MB_V] && ctx->svm_impl >= 1 && e->svm_oct > 0) {
     dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
-    MB_LAUNCH(ctx, "k_ens_svm_mma", st) k_ens_svm_mma<<<grid, kSvmThreads, 0, st>>>(
-        cov, e->C, e->P, plane, eg, w, e->svm_bq.p, e->svm_baq.p, e->svm_oct, e->svm_xc.p, e->svm_xis.p, e->svm_sigma,
-        e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], started ? 1 : 0, smooth_params(e), astride, acc);
+    if (ctx->svm_impl == 2) {
+      MB_LAUNCH(ctx, "k_ens_svm_mma_poly", st) k_ens_svm_mma<true><<<grid, kSvmThreads, 0, st>>>(
+          cov, e->C, e->P, plane, eg, w, e->svm_bq.p, e->svm_baq.p, e->svm_oct, e->svm_xc.p, e->svm_xis.p, e->svm_sigma,
+          e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], started ? 1 : 0, smooth_params(e), astride, acc);
+    } else {
+      MB_LAUNCH(ctx, "k_ens_svm_mma", st) k_ens_svm_mma<false><<<grid, kSvmThreads, 0, st>>>(
+          cov, e->C, e->P, plane, eg, w, e->svm_bq.p, e->svm_baq.p, e->svm_oct, e->svm_xc.p, e->svm_xis.p, e->svm_sigma,
+          e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], started ? 1 : 0, smooth_params(e), astride, acc);
+    }
   } else if (e->has[MB_V]) {
     switch ((e->P + 1) / 2) {
 #define MB_SVM_CASE(n) case n: launch_svm<n>(e, cov, plane, eg, w, acc, started ? 1 : 0, st); break;

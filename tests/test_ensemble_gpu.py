@@ -220,15 +220,16 @@ def test_tiled_mode_is_independent_of_lane_concurrency(engine, case):
 
 @pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
                     reason="k_ens_svm_mma (svm_impl = 1) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("kept", ["v", "gnmv", "bgnmrv"])
-def test_svm_tensor_core_variant(engine, case, kept):
+def test_svm_tensor_core_variant(engine, case, kept, impl):
     """ksvm dot products on the tensor pipe (3 x TF32, k_ens_svm_mma): same tolerance as the packed-FP32 kernel, same NA mask,
-    ragged window (160 x 224 is not a multiple of the 8-row CTA tile in general windows)."""
+    ragged window; impl 2 also evaluates half of the exponentials as a degree-5 polynomial on the FMA pipe."""
     geom, C, models, cov = case
     ws = [1.0 / len(kept)] * len(kept)
     ref = cbind.ensemble_eval(models, kept, ws, 1.0, cov, geom.as_tuple())
     try:
-        engine.set_param("svm_impl", 1)
+        engine.set_param("svm_impl", impl)
         ens = engine.ensemble_create(geom, models, kept, ws, 1.0, C + 2)
         got = engine.ensemble_eval(ens, cov)
         sub = (3, 150, 5, 201)

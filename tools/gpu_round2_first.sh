@@ -10,11 +10,12 @@ MB_EXPERIMENTAL=1 timeout -k 10 200 python -m pytest tests/test_tps_gpu.py -m gp
 timeout -k 10 200 python tools/sbr_check.py 1100 5000 > gpurun_out/${TAG}_check.log 2>&1; echo "check rc=$?"; cat gpurun_out/${TAG}_check.log
 timeout -k 10 300 python bench.py > gpurun_out/${TAG}_bench_c3.json 2> gpurun_out/${TAG}_bench_c3.err; echo "bench rc=$?"
 timeout -k 10 300 python bench.py --param svm_impl=1 > gpurun_out/${TAG}_bench_c3_svm_mma.json 2> gpurun_out/${TAG}_bench_c3_svm_mma.err; echo "bench svm_mma rc=$?"
+timeout -k 10 300 python bench.py --param svm_impl=2 > gpurun_out/${TAG}_bench_c3_svm_mma_poly.json 2> gpurun_out/${TAG}_bench_c3_svm_mma_poly.err; echo "bench svm_mma_poly rc=$?"
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 python - <<PY
 import json
-for f in ("bench_c3", "bench_c3_svm_mma"):
+for f in ("bench_c3", "bench_c3_svm_mma", "bench_c3_svm_mma_poly"):
     try:
         d = json.loads(open("gpurun_out/${TAG}_%s.json" % f).read().strip().splitlines()[-1])
         print(f, "value", round(d["value"], 1), "ms", round(d["ms_per_step"], 2), "e2e ms", round(d["e2e"]["ms_per_step"], 1), "parity", d.get("parity"))
