@@ -69,3 +69,24 @@ def test_coefficients_from_the_band_form(m, b):
     ref = np.linalg.solve(M + lam * np.eye(m), z)
     got = proto.coefficients_from_band(M, z, lam, b)
     assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("m,b,g,seed", [(90, 8, 4, 1), (150, 32, 4, 2), (70, 8, 3, 3), (64, 8, 8, 5), (40, 32, 4, 6)])
+def test_grouped_chase_with_a_row_window(m, b, g, seed):
+    """g sweeps per CTA on a sliding window of band ROWS (the planned shared-memory variant of k_sbr_chase): loading rows only
+    after the previous group has retired them and retiring rows no sweep of the group touches again reproduces the sequential
+    chase bit for bit under a random interleaving of the groups, with at most ~(2 g - 1) row blocks resident."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((m, m))
+    A = A @ A.T
+    z = rng.standard_normal((m, 2))
+    A1, z1 = A.copy(), z.copy()
+    proto.stage1(A1, z1, b)
+    B_seq, z_seq = proto.to_band(A1, b), z1.copy()
+    B_grp, z_grp = B_seq.copy(), z1.copy()
+    d0, e0 = proto.stage2(B_seq, z_seq, m, b)
+    d1, e1 = proto.stage2_grouped(B_grp, z_grp, m, b, g, np.random.default_rng(seed + 50))
+    np.testing.assert_array_equal(d0, d1)
+    np.testing.assert_array_equal(e0, e1)
+    np.testing.assert_array_equal(z_seq, z_grp)
+    assert proto.stage2_grouped.max_resident <= (2 * g) * b + g

@@ -172,7 +172,8 @@ def chase_step(Bv: BandView, z: np.ndarray, b: int, s: int, k: int, state: dict)
     w = p + alpha * v
     D -= np.outer(v, w) + np.outer(w, v)
     _put_lower(Bv, r0, D)
-    z[r0:r0 + ln, :] -= tau * np.outer(v, v @ z[r0:r0 + ln, :])
+    zr = z[r0:r0 + ln, :]
+    z[r0:r0 + ln, :] = zr - tau * np.outer(v, v @ zr)
     state["v"], state["tau"] = v, tau
 
 
@@ -330,6 +331,148 @@ def coefficients_from_band(M: np.ndarray, z: np.ndarray, lam: float, b: int) -> 
     for (r0, V, T) in reversed(panels):                  # beta = Q1 y,  H_k = I - V T V'
         y[r0:] -= V @ (T @ (V.T @ y[r0:]))
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Stage 2 with g consecutive sweeps per CTA and the band rows they work on kept in a sliding SHARED-MEMORY WINDOW (DESIGN.md
+# section 9, option (c); not implemented on the device yet).  What this prototype pins down is the hand-over protocol:
+#   * the window is organised by matrix ROWS (row i holds B[i - j, j] for its 64 band columns; a task of sweep s, step k only
+#     touches rows of its row block R_k(s) = [s + 1 + k b, s + 1 + (k + 1) b));
+#   * group-step K runs the tasks (s0 + i, K - 2 i), i < g - they are two steps apart, hence independent;
+#   * before group-step K the group LOADS the rows below  s0 + 1 + (K + 1) b  that are not resident yet, which needs the previous
+#     group to have RETIRED them;  after it the group RETIRES (writes back, publishes) every row none of its sweeps will touch again:
+#     rows below  min_i (s0 + i + 1 + (K - 2 i + 1) b)  over its unfinished sweeps.
+# Finality by rows needs no special cases (the by-column view has one element per step that changes hands early).
+# ---------------------------------------------------------------------------------------------------------------------------
+class _RowWindow:
+    """BandView on top of a cache of rows; every access asserts that the row is resident."""
+
+    def __init__(self, m, width):
+        self.m, self.width, self.rows = m, width, {}
+
+    def _get(self, i, j):
+        if i < j:
+            i, j = j, i
+        assert i in self.rows, ("row not resident", i)
+        return self.rows[i][i - j]
+
+    def _set(self, i, j, v):
+        assert i >= j and i in self.rows, ("row not resident", i)
+        self.rows[i][i - j] = v
+
+    def blk(self, r0, nr, c0, nc):
+        return np.array([[self._get(r0 + p_, c0 + q_) for q_ in range(nc)] for p_ in range(nr)])
+
+    def put(self, r0, c0, M, lower_only=False):
+        for p_ in range(M.shape[0]):
+            for q_ in range(M.shape[1]):
+                if r0 + p_ >= c0 + q_:
+                    self._set(r0 + p_, c0 + q_, M[p_, q_])
+
+    @property
+    def B(self):
+        return self
+
+    def __setitem__(self, key, v):          # _put_lower writes Bv.B[off, col]
+        off, col = key
+        self._set(col + off, col, v)
+
+
+def stage2_grouped(B: np.ndarray, z: np.ndarray, m: int, b: int, g: int, rng):
+    """Bulge chasing with groups of g sweeps, each group working on its own row window; groups are interleaved at random
+    subject to the load rule above.  Returns (d, e) like stage2()."""
+    width = 2 * b
+    nsweep = max(m - 2, 0)
+    total = [chase_steps(m, b, s) for s in range(nsweep)]
+    ngroup = (nsweep + g - 1) // g
+
+    class Group:
+        pass
+
+    groups = []
+    for ga in range(ngroup):
+        G = Group()
+        G.s0 = ga * g
+        G.sweeps = list(range(G.s0, min(G.s0 + g, nsweep)))
+        G.K = 0
+        G.win = _RowWindow(m, width)
+        G.zrows = {}
+        G.loaded = G.s0 + 1                 # rows [s0 + 1, loaded) are resident or already retired
+        G.retired = G.s0 + 1                # rows below are final for this group (and written back)
+        G.states = [dict() for _ in G.sweeps]
+        G.nsteps = max([total[s] + 2 * i for i, s in enumerate(G.sweeps)] + [0])
+        G.done = G.nsteps == 0
+        if G.done:
+            G.retired = m
+        groups.append(G)
+
+    def row_from_global(i):
+        return np.array([B[off, i - off] if i - off >= 0 else 0.0 for off in range(width)])
+
+    def row_to_global(i, row):
+        for off in range(width):
+            if i - off >= 0:
+                B[off, i - off] = row[off]
+
+    def can_run(ga):
+        G = groups[ga]
+        if G.done:
+            return False
+        need = min(m, G.s0 + 1 + (G.K + 1) * b)
+        return ga == 0 or groups[ga - 1].retired >= need
+
+    def run(ga):
+        G = groups[ga]
+        need = min(m, G.s0 + 1 + (G.K + 1) * b)
+        for i in range(G.loaded, need):                       # load
+            G.win.rows[i] = row_from_global(i)
+            G.zrows[i] = z[i].copy()
+        G.loaded = max(G.loaded, need)
+        zview = _ZRows(G.zrows, z.shape[1])
+        for idx, s in enumerate(G.sweeps):                    # the g independent tasks of this group-step
+            k = G.K - 2 * idx
+            if 0 <= k < total[s]:
+                chase_step(G.win, zview, b, s, k, G.states[idx])
+        G.K += 1
+        bound = m
+        for idx, s in enumerate(G.sweeps):                    # retire
+            k_next = G.K - 2 * idx
+            if k_next >= total[s]:
+                continue                                      # this sweep has finished
+            bound = min(bound, s + 1 + max(k_next, 0) * b)
+        if G.K >= G.nsteps:
+            bound = m
+            G.done = True
+        for i in range(G.retired, min(bound, G.loaded)):
+            row_to_global(i, G.win.rows.pop(i))
+            z[i] = G.zrows.pop(i)
+        G.retired = max(G.retired, min(bound, G.loaded)) if not G.done else m
+        G.max_resident = max(getattr(G, "max_resident", 0), len(G.win.rows))
+
+    while True:
+        ready = [ga for ga in range(ngroup) if can_run(ga)]
+        if not ready:
+            break
+        run(ready[rng.integers(len(ready))])
+    assert all(G.done for G in groups), "schedule stalled"
+    stage2_grouped.max_resident = max(getattr(G, "max_resident", 0) for G in groups) if groups else 0
+    return B[0, :m].copy(), B[1, :m - 1].copy()
+
+
+class _ZRows:
+    """z[r0:r0+ln, :] views on the cached right-hand-side rows"""
+
+    def __init__(self, rows, L):
+        self.rows, self.L = rows, L
+
+    def __getitem__(self, key):
+        sl, _ = key
+        return np.array([self.rows[i] for i in range(sl.start, sl.stop)])
+
+    def __setitem__(self, key, v):
+        sl, _ = key
+        for n_, i in enumerate(range(sl.start, sl.stop)):
+            self.rows[i] = np.array(v[n_])
 
 
 if __name__ == "__main__":
