@@ -212,9 +212,9 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * one-stage persistent kernel; "sbr_qr_grid" = 1 makes the panel QR of the two-stage path use the software grid
  * barrier instead of a thread-block cluster; "sbr_qr_impl" = 1 / 2 keeps the panel rows in shared memory / registers
  * (0 = chosen by cluster size); "sbr_debug" = 1 keeps the band matrix for mb_debug_values("sbr_band");
- * "svm_impl" = 1 (before mb_ensemble_create), "coef_impl" = 1 and "sbr_chase_impl" = 1 select experimental kernels that have not run
- * on a GPU yet (ksvm dot products on the tensor pipe; coefficients from the band form of the two-stage reduction; watcher and
- * publisher warps in the bulge chase) - see DESIGN.md section 9;
+ * "svm_impl" = 1 / 2 (before mb_ensemble_create), "coef_impl" = 1, "sbr_chase_impl" = 1 and "sbr_fuse" = 1 select experimental kernels
+ * that have not run on a GPU yet (ksvm dot products on the tensor pipe; coefficients from the band form of the two-stage reduction;
+ * watcher and publisher warps in the bulge chase; one fused cluster kernel per panel) - see DESIGN.md section 9;
  * "defer_ensemble" = 0 starts the per-cell ensemble kernels of mb_mltps_predict* before the fit instead of behind stage 1
  * of its tridiagonalisation; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd (validation of the in-house path only). */
 int mb_set_param(mb_ctx* ctx, const char* name, int value);

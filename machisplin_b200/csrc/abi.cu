@@ -264,6 +264,9 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 3,
                  "sytrd_mode must be 0 (default = two-stage), 1 (one-stage persistent kernel), 2 (one-stage, kernel per phase) or 3 (two-stage)");
       ctx->sytrd_mode = value;
+    } else if (n == "sbr_fuse") {
+      MB_REQUIRE(value == 0 || value == 1, "sbr_fuse must be 0 or 1 (fused per-panel cluster kernel, experimental)");
+      ctx->sbr_fuse = value;
     } else if (n == "sbr_chase_impl") {
       MB_REQUIRE(value == 0 || value == 1, "sbr_chase_impl must be 0 or 1 (watcher / publisher warps, experimental)");
       ctx->sbr_chase_impl = value;

@@ -194,6 +194,7 @@ struct mb_ctx {
   int coef_impl = 0;          // coefficients at the selected lambda: 0 = dense Cholesky of M + lambda I, 1 = band form of the two-stage
                               // reduction (block band Cholesky + back-transformation; experimental)
   mb_band_form band_form;
+  int sbr_fuse = 0;           // two-stage path: 1 = one cluster kernel (k_sbr_fin) instead of vtz + st + w + pu per panel (experimental)
   int sbr_chase_impl = 0;     // bulge chase: 0 = three warps per sweep, 1 = + watcher and publisher warps (experimental)
   int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers
   int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits

@@ -313,3 +313,27 @@ def test_chase_with_watcher_and_publisher_warps(engine, n):
     assert got.lam == ref.lam
     np.testing.assert_array_equal(got.c, ref.c)
     np.testing.assert_array_equal(got.decomposition()[0], ref.decomposition()[0])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
+                    reason="sbr_fuse = 1 (fused per-panel cluster kernel) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
+@pytest.mark.parametrize("n", [37, 70, 165, 600, 1100])
+def test_fused_panel_kernel(engine, n):
+    """k_sbr_fin = vtz + st + w + pu in one cluster kernel: same mathematics, different (still fixed) summation order of the
+    32 x 32 Gram partials, so agreement to rounding; three responses."""
+    geom = synth.make_geom(512, 512)
+    xy, _, _ = synth.make_knots(geom, n, 600 + n)
+    y = synth.residual_field(xy, 600 + n)
+    Y = np.stack([y, y[::-1].copy(), y * y], axis=1)
+    ref = engine.tps_fit(xy, Y)
+    try:
+        engine.set_param("sbr_fuse", 1)
+        got = engine.tps_fit(xy, Y)
+        again = engine.tps_fit(xy, Y)
+    finally:
+        engine.set_param("sbr_fuse", 0)
+    for g, r, a in zip(got, ref, again):
+        assert abs(g.lam - r.lam) <= 1e-9 * r.lam
+        assert np.max(np.abs(g.c - r.c)) <= 1e-9 * np.max(np.abs(r.c))
+        np.testing.assert_allclose(g.decomposition()[0], r.decomposition()[0], rtol=0, atol=1e-13 * r.decomposition()[0].max())
+        assert a.lam == g.lam and np.array_equal(a.c, g.c)        # deterministic

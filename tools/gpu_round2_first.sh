@@ -6,7 +6,7 @@ TAG=${1:-r2a}
 mkdir -p gpurun_out
 timeout -k 10 600 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
 MB_EXPERIMENTAL=1 timeout -k 10 200 python -m pytest tests/test_ensemble_gpu.py -m gpu -q -k svm_tensor > gpurun_out/${TAG}_pytest_svm_mma.log 2>&1; echo "svm_mma pytest rc=$?"; tail -15 gpurun_out/${TAG}_pytest_svm_mma.log
-MB_EXPERIMENTAL=1 timeout -k 10 200 python -m pytest tests/test_tps_gpu.py -m gpu -q -k "band_form or watcher" > gpurun_out/${TAG}_pytest_band_form.log 2>&1; echo "band_form pytest rc=$?"; tail -15 gpurun_out/${TAG}_pytest_band_form.log
+MB_EXPERIMENTAL=1 timeout -k 10 200 python -m pytest tests/test_tps_gpu.py -m gpu -q -k "band_form or watcher or fused_panel" > gpurun_out/${TAG}_pytest_band_form.log 2>&1; echo "band_form pytest rc=$?"; tail -15 gpurun_out/${TAG}_pytest_band_form.log
 timeout -k 10 200 python tools/sbr_check.py 1100 5000 > gpurun_out/${TAG}_check.log 2>&1; echo "check rc=$?"; cat gpurun_out/${TAG}_check.log
 timeout -k 10 300 python bench.py > gpurun_out/${TAG}_bench_c3.json 2> gpurun_out/${TAG}_bench_c3.err; echo "bench rc=$?"
 timeout -k 10 300 python bench.py --param svm_impl=1 > gpurun_out/${TAG}_bench_c3_svm_mma.json 2> gpurun_out/${TAG}_bench_c3_svm_mma.err; echo "bench svm_mma rc=$?"

@@ -59,6 +59,20 @@ for n in sizes:
             g = eng.tps_fit(xy, y)
             eng.set_param("sbr_qr_grid", 0)
             print(f"   grid-barrier QR: lambda rel diff {abs(g.lam - sp0.lam) / sp0.lam:.1e}", flush=True)
+        try:                                   # experimental: fused per-panel cluster kernel
+            eng.set_param("sytrd_mode", 3); eng.set_param("sbr_fuse", 1)
+            eng.tps_fit(xy, y)
+            eng.timing(True); eng.timing_collect()
+            t0 = time.perf_counter()
+            b = eng.tps_fit(xy, y)
+            dt = time.perf_counter() - t0
+            kt = eng.timing_collect(); eng.timing(False)
+            print(f"   sbr_fuse 1: wall {dt * 1e3:.1f} ms, lambda rel diff {abs(b.lam - sp0.lam) / sp0.lam:.1e}, c err {np.abs(b.c - sp0.c).max() / np.abs(sp0.c).max():.2e}, "
+                  f"k_sbr_fin {kt.get('k_sbr_fin', (0, 0))[0]:.2f} ms x{kt.get('k_sbr_fin', (0, 0))[1]}", flush=True)
+        except Exception:
+            traceback.print_exc()
+        finally:
+            eng.timing(False); eng.set_param("sbr_fuse", 0)
         try:                                   # experimental: watcher / publisher warps in the bulge chase
             eng.set_param("sytrd_mode", 3); eng.set_param("sbr_chase_impl", 1)
             eng.tps_fit(xy, y)
