@@ -317,7 +317,7 @@ def run_b200(args):
         # parts 2-5 (V73:442-932): ensemble kernels || fields::Tps fit, then the fused per-cell pass
         sp = eng.mltps_predict_dev(geom, ens, cov.data_ptr() if C else 0, C, xy, resid, out.data_ptr(), lam=args.lam,
                                    stream=stream)
-        f_actual = eng.gather_cells_dev(out.data_ptr(), geom.ncol, krow, kcol, stream=stream)
+        f_actual = eng.gather_cells_dev(out.data_ptr(), geom.ncol, geom.nrow, geom.ncol, krow, kcol, stream=stream)
         state["sp"], state["f_actual"] = sp, f_actual
         return f_actual
 
@@ -627,7 +627,7 @@ def run_batch(args):
         sps = eng.tps_fit(xy, Y[:, mine]) if len(mine) > 1 else [eng.tps_fit(xy, Y[:, mine[0]])]
         for sp in sps:
             eng.ensemble_eval_dev(ens, cov.data_ptr(), C, out.data_ptr(), spline=sp, stream=stream)
-            state["f"] = eng.gather_cells_dev(out.data_ptr(), geom.ncol, krow, kcol, stream=stream)
+            state["f"] = eng.gather_cells_dev(out.data_ptr(), geom.ncol, geom.nrow, geom.ncol, krow, kcol, stream=stream)
         state["lam"] = [sp.lam for sp in sps]
 
     def sync_all():

@@ -167,8 +167,10 @@ int mb_gram(mb_ctx* ctx, const double* R_host, int n, int K, double* G_host);
 int mb_gram_dev(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, void* stream);
 
 /* ---- a7: part 5  (V73:906-930) --------------------------------------------------------- */
-/* gather raster values at the cells (row[i], col[i]) - f.actual <- extract(final, points). */
-int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row,
+/* gather raster values at the cells (row[i], col[i]) - f.actual <- extract(final, points), V73:910.  The raster has nrow
+ * rows of ncol cells, row_stride doubles apart; a cell outside it (e.g. row = col = -1 for a point outside the extent) gives
+ * NaN, which is what terra::extract returns there. */
+int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, int nrow, int ncol, const int32_t* row,
                         const int32_t* col, int n, double* out_host, void* stream);
 
 /* ---- mltps parts 2-5 for one response in ONE call  (V73:442-932) --------------------------- */

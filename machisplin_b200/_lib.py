@@ -87,7 +87,7 @@ SIGNATURES = {
     "mb_tiles_merge_dev": (C.c_int, [VP, PG, C.c_int, C.c_int, PW, PVP, VP, VP]),
     "mb_gram": (C.c_int, [VP, PD, C.c_int, C.c_int, PD]),
     "mb_gram_dev": (C.c_int, [VP, VP, C.c_int, C.c_int, VP, VP]),
-    "mb_gather_cells_dev": (C.c_int, [VP, VP, C.c_int64, PI32, PI32, C.c_int, PD, VP]),
+    "mb_gather_cells_dev": (C.c_int, [VP, VP, C.c_int64, C.c_int, C.c_int, PI32, PI32, C.c_int, PD, VP]),
     "mb_mltps_predict_dev": (C.c_int, [VP, PG, VP, VP, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, VP, PVP, VP]),
     "mb_mltps_predict": (C.c_int, [VP, PG, VP, PF, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, PD, PVP]),
     "mb_dev_alloc": (C.c_int, [VP, C.c_size_t, PVP]),

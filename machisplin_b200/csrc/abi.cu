@@ -401,7 +401,7 @@ int mb_spline_get_decomp(const mb_spline* s, double* eta, double* tri_diag, doub
 
 void mb_spline_free(mb_spline* s) {
   if (!s) return;
-  if (s->ctx) cudaSetDevice(s->ctx->device);
+  cudaSetDevice(s->device);   // the context may already be gone (R finalizer order, Python GC): never touch s->ctx here
   delete s;
 }
 
@@ -623,14 +623,15 @@ int mb_gram(mb_ctx* ctx, const double* R_host, int n, int K, double* G_host) {
   });
 }
 
-int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row,
+int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, int nrow, int ncol, const int32_t* row,
                         const int32_t* col, int n, double* out_host, void* stream) {
   return guarded([&] {
     MB_REQUIRE(ctx && raster_dev && row && col && out_host, "NULL argument");
+    MB_REQUIRE(nrow > 0 && ncol > 0 && row_stride >= ncol, "raster shape / row stride");
     MB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     ctx->arena.begin(st);
-    gather_cells(ctx, raster_dev, row_stride, row, col, n, out_host, st);
+    gather_cells(ctx, raster_dev, row_stride, nrow, ncol, row, col, n, out_host, st);
   });
 }
 
@@ -644,6 +645,11 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
   const mb_window full{0, g.nrow, 0, g.ncol};
   const size_t ncell = (size_t)g.nrow * g.ncol;
   if (spline_out) *spline_out = nullptr;
+  // this call forks onto the context's streams: the next arena.begin() has to drain all of them before it reuses the blocks
+  ctx->arena.also_used(ctx->stream);
+  ctx->arena.also_used(ctx->side);
+  ctx->arena.also_used(ctx->copy);
+  ctx->arena.also_used(st);
   if (e) {
     const mb_grid eg = ensemble_grid(e);
     MB_REQUIRE(eg.nrow == g.nrow && eg.ncol == g.ncol && eg.xmin == g.xmin && eg.xmax == g.xmax &&
@@ -759,7 +765,12 @@ int mb_mltps_predict_dev(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, co
     MB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     ctx->arena.begin(st);
-    mltps_predict(ctx, *g, e, const_cast<float*>(cov_dev), C, knots_xy, resid, n, lambda, tile_px, out_dev, spline_out, st);
+    try {
+      mltps_predict(ctx, *g, e, const_cast<float*>(cov_dev), C, knots_xy, resid, n, lambda, tile_px, out_dev, spline_out, st);
+    } catch (...) {
+      cudaDeviceSynchronize();   // side / copy / fit streams may still be running on arena blocks and caller buffers
+      throw;
+    }
   });
 }
 
@@ -781,9 +792,14 @@ int mb_mltps_predict(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, const 
     double* d_out = ctx->arena.take_n<double>(ncell);
     // planes travel in row blocks on the copy stream, block b's ensemble kernels follow on `side`, the fit
     // runs on the context stream meanwhile
-    mltps_predict(ctx, *g, e, d_cov, C, knots_xy, resid, n, lambda, tile_px, d_out, spline_out, st, cov_host);
-    MB_CUDA(cudaMemcpyAsync(out_host, d_out, ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
-    MB_CUDA(cudaStreamSynchronize(st));
+    try {
+      mltps_predict(ctx, *g, e, d_cov, C, knots_xy, resid, n, lambda, tile_px, d_out, spline_out, st, cov_host);
+      MB_CUDA(cudaMemcpyAsync(out_host, d_out, ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+      MB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+      cudaDeviceSynchronize();   // the copy stream may still be reading cov_host, the side stream the arena
+      throw;
+    }
   });
 }
 

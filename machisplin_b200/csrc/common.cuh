@@ -95,15 +95,25 @@ struct DevBuf {
 // Temporaries of one top-level call are bump-allocated from blocks that stay alive across calls, so
 // the hot path performs no cudaMalloc / cudaFree (both synchronise the device).  begin(stream) starts a
 // new call: if the previous call ran on a different stream it is drained first, because its kernels may
-// still be reading the blocks that are about to be reused.
+// still be reading the blocks that are about to be reused.  A call that forks work onto further streams (mb_mltps_predict*:
+// fit / ensemble / copy streams) registers them with also_used(); the next begin() drains every one of them, whatever
+// stream it runs on and however the forking call ended (normal return, asynchronous return, exception).
 struct Arena {
   struct Block { char* p; size_t cap; };
   std::vector<Block> blocks;
   size_t cur = 0, off = 0;
   cudaStream_t last = nullptr;
   bool used = false;
+  std::vector<cudaStream_t> forked;
+  void also_used(cudaStream_t s) { if (s && std::find(forked.begin(), forked.end(), s) == forked.end()) forked.push_back(s); }
   void begin(cudaStream_t st) {
-    if (used && last != st) cudaStreamSynchronize(last);
+    if (!forked.empty()) {
+      for (cudaStream_t s : forked) cudaStreamSynchronize(s);
+      if (used) cudaStreamSynchronize(last);
+      forked.clear();
+    } else if (used && last != st) {
+      cudaStreamSynchronize(last);
+    }
     last = st; used = true; cur = 0; off = 0;
   }
   void* take(size_t bytes) {
@@ -217,7 +227,8 @@ struct mb_ctx {
 };
 
 struct mb_spline {
-  mb_ctx* ctx = nullptr;
+  mb_ctx* ctx = nullptr;             // NOT dereferenced by mb_spline_free: a handle may outlive its context
+  int device = 0;                    // copied at creation for the free path
   int np = 0;
   std::vector<double> sx, sy;        // scaled knot coordinates
   std::vector<double> kx, ky;        // unscaled

@@ -40,7 +40,8 @@ struct PackedForest {
 };
 
 struct mb_ensemble {
-  mb_ctx* ctx = nullptr;
+  mb_ctx* ctx = nullptr;             // not dereferenced by ensemble_free (a handle may outlive its context)
+  int device = 0;
   mb_grid g{};
   int P = 0, C = 0;
   double w[6] = {0, 0, 0, 0, 0, 0};  // b g n m r v
@@ -616,6 +617,7 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
   cudaStream_t st = ctx->stream;
   auto e = std::make_unique<mb_ensemble>();
   e->ctx = ctx;
+  e->device = ctx->device;
   e->g = g;
   e->P = m.P;
   e->C = m.P - 2;
@@ -834,7 +836,7 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
 
 void ensemble_free(mb_ensemble* e) {
   if (!e) return;
-  if (e->ctx) cudaSetDevice(e->ctx->device);
+  cudaSetDevice(e->device);
   delete e;
 }
 

@@ -43,7 +43,7 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
 void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window* wins,
                  const double* const* tiles_dev, double* out_dev, cudaStream_t st);
 void gram(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, cudaStream_t st);
-void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row, const int32_t* col,
-                  int n, double* out_host, cudaStream_t st);
+void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, int nrow, int ncol, const int32_t* row,
+                  const int32_t* col, int n, double* out_host, cudaStream_t st);
 
 }  // namespace mb

@@ -411,20 +411,24 @@ void gram(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, cudaStr
 // ---------------------------------------------------------------------------------------------
 // part 5: f.actual <- extract(final, points)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_gather(const double* __restrict__ ras, int64_t stride, const int* __restrict__ row,
+__global__ void k_gather(const double* __restrict__ ras, int64_t stride, int nrow, int ncol, const int* __restrict__ row,
                          const int* __restrict__ col, int n, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = ras[(int64_t)row[i] * stride + col[i]];
+  if (i >= n) return;
+  const int r = row[i], c = col[i];
+  // terra::extract gives NA for a point outside the raster
+  out[i] = ((unsigned)r < (unsigned)nrow && (unsigned)c < (unsigned)ncol) ? ras[(int64_t)r * stride + c]
+                                                                          : __longlong_as_double(0x7ff8000000000000LL);
 }
 
-void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, const int32_t* row, const int32_t* col,
-                  int n, double* out_host, cudaStream_t st) {
+void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, int nrow, int ncol, const int32_t* row,
+                  const int32_t* col, int n, double* out_host, cudaStream_t st) {
   if (n <= 0) return;
   ABuf<int> dr(ctx->arena, n), dc(ctx->arena, n);
   ABuf<double> dout(ctx->arena, n);
   dr.upload(row, n, st);
   dc.upload(col, n, st);
-  MB_LAUNCH(ctx, "k_gather", st) k_gather<<<(n + 255) / 256, 256, 0, st>>>(raster_dev, row_stride, dr.p, dc.p, n, dout.p);
+  MB_LAUNCH(ctx, "k_gather", st) k_gather<<<(n + 255) / 256, 256, 0, st>>>(raster_dev, row_stride, nrow, ncol, dr.p, dc.p, n, dout.p);
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaMemcpyAsync(out_host, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaStreamSynchronize(st));

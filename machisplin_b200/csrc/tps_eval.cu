@@ -136,6 +136,7 @@ void tps_predict_points_dev(mb_ctx* ctx, const mb_spline* s, const double* x_dev
 
 void spline_finalize(mb_ctx* ctx, mb_spline* s, double fscale_known) {
   s->ctx = ctx;
+  s->device = ctx->device;
   cudaStream_t st = ctx->stream;
   s->d_sx.upload(s->sx, st);
   s->d_sy.upload(s->sy, st);

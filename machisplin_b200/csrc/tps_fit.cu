@@ -860,6 +860,7 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
     if (lambda < 0) { s->eta = eta_desc; s->tri_diag = tri_diag; s->tri_off = tri_off; s->zhat = zhat[r]; }
     // K c through the evaluation kernel with d = 0 (K was overwritten by the projection)
     s->ctx = ctx;
+    s->device = ctx->device;
     s->d_sx.upload(s->sx, st); s->d_sy.upload(s->sy, st); s->d_c.upload(s->c, st);
     ABuf<double> d_kx(ar), d_ky(ar), d_kc(ar, np);
     d_kx.upload(kx, st); d_ky.upload(ky, st);

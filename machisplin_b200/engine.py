@@ -392,11 +392,12 @@ class Engine:
         check(self.lib.mb_gram(self._h, _pd(R), n, K, _pd(G)))
         return G
 
-    def gather_cells_dev(self, raster_ptr: int, row_stride: int, row, col, stream: int = 0) -> np.ndarray:
+    def gather_cells_dev(self, raster_ptr: int, row_stride: int, nrow: int, ncol: int, row, col, stream: int = 0) -> np.ndarray:
+        """``f.actual <- extract(final, points)`` (V73:910) on a device raster; NaN for cells outside it."""
         row = np.ascontiguousarray(row, dtype=np.int32)
         col = np.ascontiguousarray(col, dtype=np.int32)
         out = np.empty(row.size)
-        check(self.lib.mb_gather_cells_dev(self._h, C.c_void_p(raster_ptr), row_stride,
+        check(self.lib.mb_gather_cells_dev(self._h, C.c_void_p(raster_ptr), row_stride, int(nrow), int(ncol),
                                            row.ctypes.data_as(_lib.PI32), col.ctypes.data_as(_lib.PI32), row.size,
                                            _pd(out), C.c_void_p(stream)))
         return out

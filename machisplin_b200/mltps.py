@@ -87,6 +87,7 @@ def mltps_response(engine: Engine, geom, cov: np.ndarray, points_xy, resp, model
     summary.update({"rsq_final": rsq_final, "tps_kept": bool(rsq_final > rsq_model),
                     "lambda": None if spline is None else spline.lam})
     if not rsq_final > rsq_model:                                            # V73:925-930: keep the better of the two
+        # the reference has already overwritten l$residuals with resp - f.actual (V73:913) and never restores it:
+        # with tps = TRUE the residuals are the TPS-corrected ones even when the TPS raster is discarded
         final, _ = engine.mltps_predict(g, ens, cov, None, None)
-        return {"final": final, "residuals": res_final, "summary": summary}
     return {"final": final, "residuals": resp - f_actual, "summary": summary}

@@ -100,11 +100,14 @@ def _training_table(geom: Geom, C: int, n: int, seed: int):
 
 def make_models(geom: Geom, C: int, n_train: int, seed: int, kept: str = "bgnmrv", rf_trees: int = 500,
                 gbm_trees: int = 1000, svm_frac: float = 0.5, mars_terms: int = 21,
-                keep_estimators: bool = False) -> dict:
+                keep_estimators: bool = False, table=None) -> dict:
     """Six fitted-model descriptors with the reference's structural sizes: gam (linear), nnet(10),
-    earth (<= 21 hinge terms), ksvm (~0.5 n SVs), randomForest (500 trees), gbm (1000 trees, 5 splits)."""
+    earth (<= 21 hinge terms), ksvm (~0.5 n SVs), randomForest (500 trees), gbm (1000 trees, 5 splits).
+    table = (X, resp): fit on that training table (rows = points, columns = cov_1..cov_C, LONG, LAT as at V73:145-154)
+    instead of the synthetic one - the tests on the reference's bundled data use this."""
     P = C + 2
-    X, resp = _training_table(geom, C, n_train, seed)
+    X, resp = _training_table(geom, C, n_train, seed) if table is None else (np.asarray(table[0], float), np.asarray(table[1], float))
+    assert X.shape[1] == P
     rng = np.random.default_rng(seed + 77)
     out = {}
     sk = {"X": X, "resp": resp}     # fitted scikit-learn objects (tests: independent check of the descriptors)

@@ -125,3 +125,15 @@ def ensemble_eval(models: dict, kept: str, w, w_total, cov: np.ndarray, geom, wi
                              C.c_double((xmax - xmin) / ncol), C.c_double((ymax - ymin) / nrow), C.c_int(r0),
                              C.c_int(r1), C.c_int(c0), C.c_int(c1), tp, _p(out, PD), C.c_int(threads))
     return out
+
+
+def interpolate_c(fit, geom, r0=0, r1=None, c0=0, c1=None):
+    """Drop-in for ``oracle.tps.tps_interpolate`` (same arithmetic, the C + OpenMP loop): the ``interpolate`` hook of
+    ``oracle.tiles.tps_tiled_surface`` / ``oracle.mltps.mltps_one_response`` on config-sized rasters."""
+    nrow, ncol = int(geom[4]), int(geom[5])
+    return tps_eval(fit, geom, (r0, nrow if r1 is None else r1, c0, ncol if c1 is None else c1))
+
+
+def ensemble_raster_c(geom, cov, models, kept, w, w_total):
+    """Drop-in for ``oracle.mltps.ensemble_raster`` (pred.elev, V73:447-619) through the C loops."""
+    return ensemble_eval(models, kept, w, w_total, cov, geom)

@@ -57,14 +57,14 @@ def ensemble_residuals(X_pts, resp, models, kept, w, w_total):
 
 
 def mltps_one_response(geom, cov, points_xy, resp, models, kept, w, w_total, tps=True,
-                       tile_px=1500, lam=None):
+                       tile_px=1500, lam=None, interpolate=None, ensemble=None):
     """Parts 2-5 for one response column.  Returns a dict mirroring the reference's ``l`` list
     (V73:919-930): final raster, residuals, r2 ensemble, r2 final, plus the intermediate rasters."""
     knots_xy, krow, kcol = otl.knot_coordinates(geom, points_xy)
     X_pts = point_features(geom, cov, krow, kcol)
     ok = ~np.isnan(X_pts).any(axis=1) & (krow >= 0)             # complete.cases, V73:154
     knots_xy, krow, kcol, X_pts, resp = knots_xy[ok], krow[ok], kcol[ok], X_pts[ok], np.asarray(resp, float)[ok]
-    pred = ensemble_raster(geom, cov, models, kept, w, w_total)
+    pred = (ensemble or ensemble_raster)(geom, cov, models, kept, w, w_total)
     res_final = ensemble_residuals(X_pts, resp, models, kept, w, w_total)
     rss_m = float(np.sum(res_final ** 2))                        # V73:625
     tss = float(np.sum((resp - resp.mean()) ** 2))               # V73:626
@@ -73,7 +73,7 @@ def mltps_one_response(geom, cov, points_xy, resp, models, kept, w, w_total, tps
     if not tps:
         out["final"] = pred                                      # V73:951-952
         return out
-    surf = otl.tps_tiled_surface(geom, knots_xy, res_final, tile_px=tile_px, lam=lam)
+    surf = otl.tps_tiled_surface(geom, knots_xy, res_final, tile_px=tile_px, lam=lam, interpolate=interpolate)
     final = pred + surf                                          # app(c(pred, TPS), sum): NA propagates
     f_actual = final[krow, kcol]                                 # V73:910
     rss_final = float(np.nansum((resp - f_actual) ** 2)) if not np.isnan(f_actual).any() \

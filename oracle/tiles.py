@@ -203,16 +203,19 @@ def feather_merge(geom, wins, tiles, nCx, nRx):
 
 
 def tps_tiled_surface(geom, knots_xy, resid, tile_px=1500, fit_halo=0.2, keep_halo=0.025,
-                      min_pts=10, lam=None, return_parts=False):
+                      min_pts=10, lam=None, return_parts=False, interpolate=None):
     """mltps part 3 + 4 (V73:636-897): the TPS-of-residuals raster.
 
     ``knots_xy`` are the LONG/LAT columns (cell-centre coordinates, one row per input point that
-    survived complete.cases, V73:154), ``resid`` = res.FINAL.
+    survived complete.cases, V73:154), ``resid`` = res.FINAL.  ``interpolate(fit, geom, r0, r1, c0, c1)``
+    replaces the numpy statement of terra::interpolate (``oracle.tps.tps_interpolate``) - the tests of
+    config-sized rasters pass the C loop of ``oracle/c`` (same arithmetic, OpenMP) here.
     """
+    interp = interpolate or otps.tps_interpolate
     lay = mltps_tile_layout(geom, tile_px, fit_halo, keep_halo)
     if lay.nRx * lay.nCx == 1:                       # V73:748-753
         fit = otps.tps_fit(knots_xy, resid, lam=lam)
-        out = otps.tps_interpolate(fit, geom)
+        out = interp(fit, geom, 0, geom[4], 0, geom[5])
         return (out, lay, [fit]) if return_parts else out
     krow, kcol = cell_of_points(geom, knots_xy)
     tiles, fits = [], []
@@ -223,7 +226,7 @@ def tps_tiled_surface(geom, knots_xy, resid, tile_px=1500, fit_halo=0.2, keep_ha
             fits.append(None)
             continue
         fit = otps.tps_fit(knots_xy[inside], resid[inside], lam=lam)       # V73:722
-        tiles.append(otps.tps_interpolate(fit, geom, kw[0], kw[1], kw[2], kw[3]))  # V73:726-728
+        tiles.append(interp(fit, geom, kw[0], kw[1], kw[2], kw[3]))              # V73:726-728
         fits.append(fit)
     out = feather_merge(geom, lay.keep_win, tiles, lay.nCx, lay.nRx)
     return (out, lay, fits) if return_parts else out

@@ -57,7 +57,9 @@ mb_export_models <- function(P, gam = NULL, nn = NULL, nn.max2 = 1, nn.min = 0, 
 # NA-propagating final sum (V73:906-907).  `kept`, `w` = round(p, 2) of the kept models, `w.total` = sum of ALL p (V73:337).
 mb_mltps_predict <- function(mb, rast_stack, n.covars, models, kept, w, w.total, xy = NULL, res.FINAL = NULL, tile.px = 1500L) {
   g <- mb_grid(rast_stack)
-  cov <- writeBin(as.numeric(t(terra::values(rast_stack[[seq_len(n.covars)]]))), raw(), size = 4)   # float32 planes
+  # terra::values() is ncell x nlyr (cell order within a column = terra cell order), so its column-major storage already is
+  # the plane layout [C][nrow][ncol] the engine expects - no transpose (a t() here would interleave the layers per cell)
+  cov <- writeBin(as.numeric(terra::values(rast_stack[[seq_len(n.covars)]])), raw(), size = 4)      # float32 planes
   ens <- .Call("mbR_ensemble_create", mb, g, models, kept, as.numeric(w), as.numeric(w.total))
   v <- .Call("mbR_mltps_predict", mb, g, ens, cov, as.integer(n.covars),
              if (is.null(xy)) NULL else as.matrix(xy), res.FINAL, -1, as.integer(tile.px))

@@ -1,7 +1,9 @@
 /*
  * .Call shim between R and libmachisplin_b200.so (include/machisplin_b200.h).
- * NOT compiled in the build image (no R toolchain there); build where R exists with
+ * Build where R exists with
  *     R CMD SHLIB mb_shim.c -I../include -L../machisplin_b200 -lmachisplin_b200
+ * The build image has no R: there the shim is compiled against the stub R API of tests/r_stub/ (fake SEXPs) and every wrapper is
+ * called by tests/test_rshim_*.py - on the GPU box through to the kernels.
  * Every wrapper converts SEXP <-> plain pointers, calls ONE C-ABI entry point and turns a non-zero status
  * into an R error after the C frames have unwound.  Device-resident handles (context, spline, ensemble) are
  * R external pointers with finalizers.  R owns every host array for the duration of the call.
@@ -17,8 +19,10 @@ static void ctx_fin(SEXP p) { mb_shutdown((mb_ctx*)R_ExternalPtrAddr(p)); R_Clea
 static void spl_fin(SEXP p) { mb_spline_free((mb_spline*)R_ExternalPtrAddr(p)); R_ClearExternalPtr(p); }
 static void ens_fin(SEXP p) { mb_ensemble_free((mb_ensemble*)R_ExternalPtrAddr(p)); R_ClearExternalPtr(p); }
 
-static SEXP wrap(void* h, R_CFinalizer_t fin) {
-  SEXP p = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+/* `keep` (the context's external pointer, or R_NilValue for the context itself) becomes the `prot` field of the handle: R then
+ * keeps the context alive at least as long as any spline / ensemble created from it, whatever order the GC finalizes in. */
+static SEXP wrap(void* h, R_CFinalizer_t fin, SEXP keep) {
+  SEXP p = PROTECT(R_MakeExternalPtr(h, R_NilValue, keep));
   R_RegisterCFinalizerEx(p, fin, TRUE);
   UNPROTECT(1);
   return p;
@@ -32,7 +36,7 @@ static mb_grid grid_of(SEXP g) {           /* c(xmin, xmax, ymin, ymax, nrow, nc
 SEXP mbR_init(SEXP device) {
   mb_ctx* ctx = NULL;
   MB_CHECK(mb_init(Rf_asInteger(device), &ctx));
-  return wrap(ctx, ctx_fin);
+  return wrap(ctx, ctx_fin, R_NilValue);
 }
 
 /* fields::Tps(x, Y) -> external pointer of the fitted spline (V73:722, V73:751).  lambda < 0 = GCV. */
@@ -40,7 +44,7 @@ SEXP mbR_tps_fit(SEXP ctx, SEXP xy, SEXP y, SEXP lambda) {
   const int n = Rf_nrows(xy);
   mb_spline* s = NULL;
   MB_CHECK(mb_tps_fit((mb_ctx*)R_ExternalPtrAddr(ctx), REAL(xy), REAL(y), n, 1, Rf_asReal(lambda), &s));
-  return wrap(s, spl_fin);
+  return wrap(s, spl_fin, ctx);
 }
 
 /* terra::interpolate(rast(template), Tps): values in terra cell order (V73:726, V73:753). */
@@ -90,7 +94,7 @@ SEXP mbR_ensemble_create(SEXP ctx, SEXP grid, SEXP d, SEXP kept, SEXP w, SEXP w_
   mb_ensemble* e = NULL;
   MB_CHECK(mb_ensemble_create((mb_ctx*)R_ExternalPtrAddr(ctx), &g, &m, CHAR(STRING_ELT(kept, 0)), REAL(w),
                               Rf_asReal(w_total), &e));
-  return wrap(e, ens_fin);
+  return wrap(e, ens_fin, ctx);
 }
 
 /* mltps parts 2-5 for one response (V73:442-932): cov = float32 planes packed in a raw vector (C x nrow x ncol,
