@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the CPU sample (0 = auto, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the secondary mltps-tiled measurement (N = 1)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one raster of N x nrow rows (a config-sized block per GPU); strong = the nrow x ncol raster cut in N")
     ap.add_argument("--lam", type=float, default=None, help="fixed lambda (Cholesky path) instead of GCV")
     ap.add_argument("--tree-rows", type=int, default=0, help="forest tile: cells per thread (1, 2, 4; 0 = auto)")
     ap.add_argument("--eval-precision", type=int, default=0, help="leaf kernel path: 0 auto, 1 float64, 2 mixed")
@@ -213,7 +216,8 @@ def run_reference(args):
     cfg = workload(args)
     geom, xy, krow, kcol, resid, models, kept, w, wt = build_inputs(cfg, 0)
     from machisplin_b200 import synth
-    threads = cbind.max_threads()
+    threads = host_threads()       # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    lapack_threads(threads)
     # fit once with a fixed lambda close to the GCV optimum (a 5k-knot GCV fit alone takes ~10 s of LAPACK)
     nfit = min(cfg["knots"], 1500)
     t0 = time.perf_counter()
@@ -241,8 +245,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(cfg, args, "global"),
+        "note": "CPU throughput of the whole box (all host cores), independent of --gpus: the per-cell work is the same for every row",
         "cpu_baseline": {"value": value, "unit": "Mcells/s", "cores": threads, "kind": "port",
                          "sample": f"{S} full-width rows ({cells} cells) per step: TPS surface ({cfg['knots']} knots, "
                                    f"float64 pair loop) + {len(kept)}-model ensemble; fit excluded (oracle GCV fit of "
@@ -275,10 +280,45 @@ def workload_config(cfg, args, tps_mode):
 
 
 # ------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1: the CPU arm must not inherit that)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def lapack_threads(n: int):
+    """Give the BLAS / OpenMP pools behind numpy / scipy n threads (OMP_NUM_THREADS=1 from torchrun was read at import)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+
+
+# what bounds each kernel according to its committed ncu --set full capture (profiles/): the pipe that saturates first
+TRUE_BOUND = {
+    "k_ens_svm": "mufu (ex2) / issue balanced: XU pipe 53 %, FMA pipe 67 %, issue 64 % (profiles/r1s_ncu_full_c3.md)",
+    "k_ens_svm_mma": "mufu (ex2): dot products on the tensor pipe (3 x TF32)",
+    "k_ens_trees": "issue: 73 % issue-active, ALU pipe 51 %, LSU 30 % (profiles/r1s_ncu_full_c3.md)",
+    "k_ens_fused": "issue + mufu: forest warps and support-vector warps share the SM",
+    "k_sbr_chase": "latency: dependent L2 round trips between consecutive sweeps",
+    "k_leaf_fused": "hbm / issue: DRAM 51 %, issue-active 53 % (profiles/r1n_ncu_full_k_leaf_fused.md)",
+    "k_leaf": "hbm write / issue",
+}
+
+
 def run_b200(args):
+    """Default arm.  One raster, one fitted spline, one ensemble: N = 1 is BASELINE config 3 as is; at N > 1 the SAME problem is
+    sharded by row blocks over the library's own NCCL communicator - `--scaling weak` (default): the raster grows to
+    (N x nrow) x ncol cells so that every GPU owns one config-3-sized block (per-GPU work fixed); `--scaling strong`: the
+    nrow x ncol raster itself is cut into N blocks.  Either way fields::Tps runs ONCE (on rank 0) beside the per-cell ensemble
+    kernels of every rank, its descriptor is broadcast, the Gram and the R^2 sums are all-reduced - inside the library."""
     import torch
     import torch.distributed as dist
     import machisplin_b200 as mb
+    from machisplin_b200 import parallel as par, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -290,8 +330,14 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = workload(args)
-    geom, xy, krow, kcol, resid, models, kept, w, wt = build_inputs(cfg, rank)
+    weak = args.scaling == "weak"
+    if world > 1 and weak:
+        cfg["nrow"] = cfg["nrow"] * world          # one shared raster, N times as tall; the knots spread over all of it
+    geom, xy, krow, kcol, resid, models, kept, w, wt = build_inputs(cfg, 0)
+    r0, r1 = par.row_blocks(geom.nrow, world)[rank]
+    bgeom = par.block_geom(geom, r0, r1)
     eng = mb.Engine(local)
+    par.comm_init(eng)                              # the library's own communicator; torch only ships the 128-byte id
     eng.set_param("tree_rows", args.tree_rows)
     eng.set_param("eval_precision", args.eval_precision)
     for kv in args.param:
@@ -299,26 +345,27 @@ def run_b200(args):
         eng.set_param(name, int(val))
     C = cfg["C"]
     P = C + 2
-    cov = device_covariates(geom, C, dev) if C else torch.zeros((0,), device=dev)
-    out = torch.empty((geom.nrow, geom.ncol), dtype=torch.float64, device=dev)
-    ens = eng.ensemble_create(geom, models, kept, w, wt, P) if kept else None
-    # cross-validation residual matrix of this rank's points for the Gram reduction (a6)
-    rng = np.random.default_rng(5 + rank)
-    Rcv = rng.standard_normal((cfg["knots"], 6 if "b" in kept or not kept else 4))
+    n = len(resid)
+    cov = device_covariates(bgeom, C, dev, disc_geom=geom) if C else torch.zeros((0,), device=dev)
+    out = torch.empty((bgeom.nrow, bgeom.ncol), dtype=torch.float64, device=dev)
+    ens = eng.ensemble_create(bgeom, models, kept, w, wt, P) if kept else None
+    # k-fold residual matrix for the Gram reduction (a6): the same matrix everywhere, every rank owns a slice of its rows
+    Rcv_all = np.random.default_rng(5).standard_normal((cfg["knots"], 6 if "b" in kept or not kept else 4))
+    Rcv = Rcv_all[par.shard_rows(cfg["knots"], world, rank)]
+    mine = (krow >= r0) & (krow < r1)               # the points whose cells this rank owns (part 5 extract)
+    krow_b, kcol_b, resid_b = (krow[mine] - r0).astype(np.int32), kcol[mine], resid[mine]
     stream = torch.cuda.current_stream().cuda_stream
-    cells = geom.nrow * geom.ncol
+    cells_total = geom.nrow * geom.ncol
     state = {}
 
     def step_device():
-        G = eng.gram(Rcv)
-        if world > 1:
-            g = torch.from_numpy(G).to(dev)
-            dist.all_reduce(g)
-        # parts 2-5 (V73:442-932): ensemble kernels || fields::Tps fit, then the fused per-cell pass
-        sp = eng.mltps_predict_dev(geom, ens, cov.data_ptr() if C else 0, C, xy, resid, out.data_ptr(), lam=args.lam,
-                                   stream=stream)
-        f_actual = eng.gather_cells_dev(out.data_ptr(), geom.ncol, geom.nrow, geom.ncol, krow, kcol, stream=stream)
-        state["sp"], state["f_actual"] = sp, f_actual
+        G = eng.gram_allreduce(Rcv)                                           # V73:329-333 (ncclAllReduce of K x K doubles)
+        # parts 2-5 (V73:442-932): ensemble kernels of this block || fields::Tps fit on rank 0, broadcast, fused per-cell pass
+        sp = eng.mltps_predict_shard_dev(bgeom, ens, cov.data_ptr() if C else 0, C, xy, resid, n, out.data_ptr(), lam=args.lam,
+                                         root=0, stream=stream)
+        f_actual = eng.gather_cells_dev(out.data_ptr(), bgeom.ncol, bgeom.nrow, bgeom.ncol, krow_b, kcol_b, stream=stream)
+        rss = eng.allreduce([float(np.nansum((resid_b - f_actual) ** 2))])    # V73:912 summed over the ranks
+        state.update(sp=sp, f_actual=f_actual, rss=float(rss[0]), G=G)
         return f_actual
 
     def sync_all():
@@ -355,7 +402,22 @@ def run_b200(args):
     ktimes = eng.timing_collect()
     eng.timing(False)
     clocks = sampler.stop() if rank == 0 else None
-    value = world * cells / (ms * 1e-3) / 1e6
+    value = cells_total / (ms * 1e-3) / 1e6
+
+    # ---- the same raster the way machisplin.mltps() itself would cut it: 1500-px TPS sub-tiles (V73:649-895), N = 1 only -----
+    tiled = None
+    if world == 1 and not args.no_tiled and kept:
+        def step_tiled():
+            eng.gram_allreduce(Rcv)
+            eng.mltps_predict_dev(geom, ens, cov.data_ptr() if C else 0, C, xy, resid, out.data_ptr(), lam=args.lam, tile_px=1500,
+                                  stream=stream, want_spline=False)
+            return eng.gather_cells_dev(out.data_ptr(), geom.ncol, geom.nrow, geom.ncol, krow, kcol, stream=stream)
+        step_tiled()
+        ms_t = timed(step_tiled, max(1, args.steps))
+        nt = -(-geom.nrow // 1500) * -(-geom.ncol // 1500)
+        tiled = {"tps_mode": f"mltps tiling, 1500 px: {nt} sub-tiles with own GCV fits, mean mosaic + seam feather",
+                 "value": cells_total / (ms_t * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms_t}
+        step_device()                                  # leave the global-spline raster in `out` for the parity check below
 
     # ---- e2e: pinned host inputs -> device -> result back to pinned host ---------------------------
     e2e = None
@@ -371,105 +433,166 @@ def run_b200(args):
 
         def step_e2e():
             t0 = time.perf_counter()
-            ens2 = eng.ensemble_create(geom, models, kept, w, wt, P) if kept else None   # descriptor upload + tree packing
+            eng.gram_allreduce(Rcv)
+            ens2 = eng.ensemble_create(bgeom, models, kept, w, wt, P) if kept else None   # descriptor upload + tree packing
             t1 = time.perf_counter()
-            eng.mltps_predict(geom, ens2, cov_np, xy, resid, lam=args.lam, out=out_np)
+            eng.mltps_predict_shard(bgeom, ens2, cov_np, xy, resid, n, lam=args.lam, root=0, out=out_np)
             host_s["ensemble_create"] += t1 - t0
             host_s["mltps_predict"] += time.perf_counter() - t1
-            return out_np[krow, kcol]
+            f = out_np[krow_b, kcol_b]
+            eng.allreduce([float(np.nansum((resid_b - f) ** 2))])
+            return f
 
         step_e2e()
         for k in host_s:
             host_s[k] = 0.0
         ms_e2e = timed(step_e2e, max(1, args.steps))
-        e2e = {"value": world * cells / (ms_e2e * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": int(h_cov.numel() * 4 + xy.nbytes + resid.nbytes),
-               "d2h_bytes_per_step": int(h_out.numel() * 8),
+        e2e = {"value": cells_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(world * (h_cov.numel() * 4) + xy.nbytes + resid.nbytes),
+               "d2h_bytes_per_step": int(world * h_out.numel() * 8),
                "host_ms_per_step": {k: v * 1e3 / max(1, args.steps) for k, v in host_s.items()}}
         del h_cov
 
+    # ---- parity sample: a few rows of EVERY rank's block travel to rank 0 (outside the timed region) --------------------
+    S_par = 2
+    pr0 = bgeom.nrow // 2
+    sample = {"rank": rank, "row0": r0 + pr0, "rows": out[pr0:pr0 + S_par].cpu().numpy(),
+              "cov": cov[:, pr0:pr0 + S_par].cpu().numpy() if C else np.zeros((0, S_par, bgeom.ncol), np.float32),
+              "lam": state["sp"].lam}
+    samples = [sample]
+    if world > 1:
+        box = [None] * world if rank == 0 else None
+        dist.gather_object(sample, box, dst=0)
+        samples = box
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the grid-evaluation kernel (north-star kernel) + per-kernel table -----------------
+    # ---- roofline: dominant kernel by share, the north-star kernel, and the whole step against section 8(d)'s bytes -------
     peak, peak_src = measured_peak()
     kern = {}
     tot_ms = sum(v[0] for v in ktimes.values()) or 1.0
     heavy = bool(kept) and bool(set(kept) & set("brv"))
+    cells_rank = bgeom.nrow * bgeom.ncol
     # algorithmic HBM bytes per cell: k_leaf writes the float64 surface; k_leaf_fused reads the
     # float64 ensemble accumulator and writes the final raster; the ensemble kernels read the C float32 planes
-    # and write (k_ens_trees) or read-modify-write (k_ens_svm, k_ens_smooth) the accumulator
+    # and write (k_ens_trees, k_ens_fused) or read-modify-write (k_ens_svm, k_ens_smooth) the accumulator
     bytes_per_cell = {"k_leaf": 8.0, "k_leaf_f64": 8.0, "k_leaf_fused": 16.0, "k_leaf_f64_fused": 16.0,
-                      "k_ens_final": 24.0, "k_ens_trees": 4.0 * C + 8.0,
+                      "k_ens_final": 24.0, "k_ens_trees": 4.0 * C + 8.0, "k_ens_fused": 4.0 * C + 8.0,
                       "k_ens_svm": 4.0 * C + (16.0 if set(kept) & set("br") else 8.0),
+                      "k_ens_svm_mma": 4.0 * C + (16.0 if set(kept) & set("br") else 8.0),
                       "k_ens_smooth": 4.0 * C + (16.0 if heavy else 8.0)}
     for name, (tms, cnt) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
         per_launch = tms / max(cnt, 1)
-        ent = {"ms_per_step": tms / args.steps, "launches_per_step": cnt / args.steps, "share": tms / tot_ms}
+        ent = {"ms_per_step": tms / args.steps, "launches_per_step": cnt / args.steps, "share_of_kernel_time": tms / tot_ms,
+               "share_of_step": tms / args.steps / ms}
         twin = {"k_leaf": "k_leaf_f64", "k_leaf_f64": "k_leaf", "k_leaf_fused": "k_leaf_f64_fused",
                 "k_leaf_f64_fused": "k_leaf_fused"}.get(name)
         if twin in ktimes and ktimes[twin][0] > tms:
             ent["note"] = "twin of the selected leaf kernel: exits at its first instruction (DESIGN.md 4.1)"
         elif name in bytes_per_cell:
-            gbs = cells * bytes_per_cell[name] / (per_launch * 1e-3) / 1e9
+            gbs = cells_rank * bytes_per_cell[name] / (per_launch * 1e-3) / 1e9
             ent.update({"algorithmic_bytes_per_cell": bytes_per_cell[name], "achieved_gbs": gbs, "hbm_frac": gbs / peak})
+        if name in TRUE_BOUND:
+            ent["true_bound"] = TRUE_BOUND[name]
         kern[name] = ent
     leaf_names = ("k_leaf_fused", "k_leaf", "k_leaf_f64_fused", "k_leaf_f64")
     lname = next((k for k in leaf_names if "hbm_frac" in kern.get(k, {})), next((k for k in leaf_names if k in kern), "k_leaf"))
     leaf = kern.get(lname, {})
-    # DRAM traffic of the kernel per launch from the committed ncu --set full capture of this workload (profiles/)
-    traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        key = f"{lname}@{cfg['nrow']}x{cfg['ncol']}"
-        traffic = tr.get(key, {}).get("dram_bytes_per_launch")
     except Exception:
-        pass
-    roofline = {"kernel": f"{lname} (grid-evaluation kernel: per-cell TPS surface" +
-                          (" + ensemble combine, mltps part 5)" if "fused" in lname else ")"),
-                "bound": "hbm", "achieved": leaf.get("achieved_gbs"),
-                "peak": peak, "unit": "GB/s", "frac": leaf.get("hbm_frac"), "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_cell": bytes_per_cell[lname],
-                "note": "roofline of the north-star kernel; `kernels` lists every kernel of the step with its share"}
+        tr = {}
+
+    def traffic_of(name):
+        return tr.get(f"{name}@{bgeom.nrow}x{bgeom.ncol}", {}).get("dram_bytes_per_launch")
+
+    dom = next((k for k in kern if "hbm_frac" in kern[k]), lname)          # kern is sorted by time: the dominant per-cell kernel
+    step_bytes = (4.0 * C + 8.0) * cells_total                             # C float32 planes in, one float64 raster out
+    step_gbs = step_bytes / (ms * 1e-3) / 1e9
+    roofline = {
+        "kernel": dom, "bound": "hbm", "achieved": kern.get(dom, {}).get("achieved_gbs"), "peak": peak, "unit": "GB/s",
+        "frac": kern.get(dom, {}).get("hbm_frac"), "traffic": traffic_of(dom), "peak_source": peak_src,
+        "algorithmic_bytes_per_cell": bytes_per_cell.get(dom), "share_of_step": kern.get(dom, {}).get("share_of_step"),
+        "true_bound": TRUE_BOUND.get(dom, "see profiles/"),
+        "note": "dominant per-cell kernel of the step by device time; its HBM fraction is small because it is bound by the pipe named "
+                "in true_bound, not by memory - the memory-bound kernel of the path is north_star_kernel",
+        "north_star_kernel": {"kernel": f"{lname} (grid evaluation: per-cell TPS surface" +
+                                        (" + ensemble combine, mltps part 5)" if "fused" in lname else ")"),
+                              "bound": "hbm", "achieved": leaf.get("achieved_gbs"), "peak": peak, "unit": "GB/s",
+                              "frac": leaf.get("hbm_frac"), "traffic": traffic_of(lname),
+                              "algorithmic_bytes_per_cell": bytes_per_cell[lname], "share_of_step": leaf.get("share_of_step")},
+        "step": {"algorithmic_bytes": step_bytes, "bytes_per_cell": 4.0 * C + 8.0, "achieved": step_gbs, "peak": peak * world,
+                 "unit": "GB/s", "frac": step_gbs / (peak * world),
+                 "note": "whole step against SURVEY.md 8(d): (4 C + 8) B/cell over ms_per_step; the step is bound by the serial "
+                         "GCV fit and the MUFU / issue-bound ensemble kernels, not by HBM"}}
 
     # ---- parity + CPU baseline on a bounded row sample ---------------------------------------------------
     cpu = None
     parity = None
-    if not args.no_cpu_baseline and world == 1:
-        from oracle import cbind
+    if not args.no_cpu_baseline:
+        from oracle import cbind, tps as otps
+        threads = host_threads()
+        lapack_threads(threads)                                # LAPACK of the oracle fit: torchrun pinned it to 1
         sp = state["sp"]
+        # parity: fields::Tps restated by the ORACLE (LAPACK eigendecomposition + fields' lambda search, ~10 s at 5 000 knots),
+        # then the oracle's C loops on the sampled rows - nothing of the GPU fit enters the reference values
+        t0 = time.perf_counter()
+        ofit = otps.tps_fit(xy, resid, lam=args.lam)
+        fit_s = time.perf_counter() - t0
+        worst_abs, worst_rel, na_ok, rows_checked = 0.0, 0.0, True, []
+        for smp in samples:
+            ref, _ = cpu_sample(geom, ofit, models, kept, w, wt, smp["cov"], smp["row0"], threads)
+            got = smp["rows"]
+            m = ~np.isnan(ref)
+            na_ok = na_ok and bool(np.array_equal(np.isnan(got), np.isnan(ref)))
+            worst_abs = max(worst_abs, float(np.max(np.abs(got[m] - ref[m]))))
+            worst_rel = max(worst_rel, float(np.max(np.abs(got[m] - ref[m])) / np.max(np.abs(ref[m]))))
+            rows_checked.append([int(smp["row0"]), int(smp["row0"]) + S_par])
+        parity = {"rows": rows_checked, "reference": "oracle GCV fit (LAPACK) + oracle C loops", "max_abs_err": worst_abs,
+                  "max_rel_err": worst_rel, "na_mask_equal": na_ok, "tolerance": 1e-5,
+                  "lambda_gpu": sp.lam, "lambda_oracle": ofit.lam, "lambda_rel_diff": abs(sp.lam - ofit.lam) / ofit.lam,
+                  "lambda_equal_on_all_ranks": bool(all(s["lam"] == sp.lam for s in samples)),
+                  "gram_max_rel_err": float(np.max(np.abs(state["G"] - Rcv_all.T @ Rcv_all)) / np.max(np.abs(Rcv_all.T @ Rcv_all)))}
+        # CPU baseline: the same rows of work per cell, timed on a sample sized to ~10-15 s
         S = args.cpu_sample_rows or 2
-        r0 = geom.nrow // 2
-        fl = FitLike(sp)
-        cov_rows = cov[:, r0:r0 + S].cpu().numpy() if C else np.zeros((0, S, geom.ncol), np.float32)
-        ref, dt = cpu_sample(geom, fl, models, kept, w, wt, cov_rows, r0)
-        if not args.cpu_sample_rows and dt < 8.0:       # grow the sample to ~10-15 s of CPU work
-            S2 = int(max(S, min(geom.nrow - r0, round(S * 12.0 / max(dt, 1e-3)))))
+        pr = min(pr0, bgeom.nrow - S)
+        cov_rows = cov[:, pr:pr + S].cpu().numpy() if C else np.zeros((0, S, geom.ncol), np.float32)
+        _, dt = cpu_sample(geom, ofit, models, kept, w, wt, cov_rows, r0 + pr, threads)
+        if not args.cpu_sample_rows and dt < 8.0:
+            S2 = int(max(S, min(bgeom.nrow - pr, round(S * 12.0 / max(dt, 1e-3)))))
             if S2 > S:
                 S = S2
-                cov_rows = cov[:, r0:r0 + S].cpu().numpy() if C else np.zeros((0, S, geom.ncol), np.float32)
-                ref, dt = cpu_sample(geom, fl, models, kept, w, wt, cov_rows, r0)
-        got = out[r0:r0 + S].cpu().numpy()
-        m = ~np.isnan(ref)
-        parity = {"rows": [r0, r0 + S], "max_abs_err": float(np.max(np.abs(got[m] - ref[m]))),
-                  "max_rel_err": float(np.max(np.abs(got[m] - ref[m])) / np.max(np.abs(ref[m]))),
-                  "na_mask_equal": bool(np.array_equal(np.isnan(got), np.isnan(ref))), "tolerance": 1e-5}
-        cpu = {"value": S * geom.ncol / dt / 1e6, "unit": "Mcells/s", "cores": cbind.max_threads(), "kind": "port",
-               "sample": f"{S} full-width rows ({S * geom.ncol} cells), TPS surface + ensemble with the GPU-fitted "
-                         f"coefficients, {dt:.1f} s; fit excluded"}
+                cov_rows = cov[:, pr:pr + S].cpu().numpy() if C else np.zeros((0, S, geom.ncol), np.float32)
+                _, dt = cpu_sample(geom, ofit, models, kept, w, wt, cov_rows, r0 + pr, threads)
+        cpu = {"value": S * geom.ncol / dt / 1e6, "unit": "Mcells/s", "cores": threads, "kind": "port",
+               "sample": f"{S} full-width rows ({S * geom.ncol} cells), TPS surface + ensemble, {dt:.1f} s; fit excluded "
+                         f"(the oracle's GCV fit took {fit_s:.1f} s on the same cores)"}
 
+    par_desc = "1 GPU" if world == 1 else \
+        (f"{world} row blocks of {bgeom.nrow} rows of ONE {geom.nrow}x{geom.ncol} raster ({args.scaling} scaling); one fields::Tps fit on "
+         f"rank 0, spline descriptor by ncclBroadcast, Gram + R^2 sums by ncclAllReduce, all inside the library; no raster exchange")
+    conf = workload_config(cfg, args, "global")
+    conf["parallelism"] = par_desc
+    conf["comm"] = eng.comm_backend() if world > 1 else None
     line = {
         "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, args, "global"),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+        "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": conf,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
-        "cpu_baseline": cpu, "parity": parity,
-        "fit": {"lambda": state["sp"].lam, "eff_df": state["sp"].eff_df, "knots": state["sp"].np},
+        "cpu_baseline": cpu, "parity": parity, "mltps_tiled": tiled,
+        "limiter": "serial part: the GCV fit of fields::Tps on rank 0 (two-stage tridiagonalisation, bulge chase) - every rank waits "
+                   "for its broadcast; per-cell kernels shard perfectly" if world > 1 else
+                   "fit (serial, latency-bound) beside the MUFU / issue-bound ensemble kernels",
+        "fit": {"lambda": state["sp"].lam, "eff_df": state["sp"].eff_df, "knots": state["sp"].np, "rss_final": state["rss"]},
     }
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

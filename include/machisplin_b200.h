@@ -187,6 +187,39 @@ int mb_mltps_predict(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, const 
                      const double* knots_xy, const double* resid, int n, double lambda, int tile_px,
                      double* out_host, mb_spline** spline_out);
 
+/* ---- multi-GPU: one process per GPU, one NCCL communicator per context -------------------------------------------------
+ * The raster shards by tile (machisplin.tiles.create boundaries, V73:1165-1256) or by row block; cells are independent given the
+ * spline and model descriptors, so no raster strip ever moves.  What crosses NVLink: the K x K Gram of the k-fold residuals
+ * (V73:329-333), and the descriptor of a fitted spline (24 bytes per knot) from the rank that ran fields::Tps to the ranks
+ * that evaluate it on their own cells.  NCCL is bound at run time (dlopen of libnccl.so.2; MB_NCCL_LIB overrides): a single-GPU
+ * host needs none.  Rank 0 creates an id (mb_comm_unique_id), the HOST ships its 128 bytes to the other processes (R: a file,
+ * a socket, parallel::clusterExport; the Python tests: torch.distributed), every process calls mb_comm_init. */
+#define MB_COMM_ID_BYTES 128
+enum { MB_SUM = 0, MB_MAX = 1 };
+int mb_comm_unique_id(void* id_out /* MB_COMM_ID_BYTES */);
+int mb_comm_init(mb_ctx* ctx, int nranks, int rank, const void* id);
+int mb_comm_destroy(mb_ctx* ctx);            /* also done by mb_shutdown */
+int mb_comm_rank(const mb_ctx* ctx);         /* 0 without a communicator */
+int mb_comm_size(const mb_ctx* ctx);         /* 1 without a communicator */
+const char* mb_comm_backend(void);           /* which libnccl was bound, or why none could be */
+/* in-place all-reduce of n host doubles (bench bookkeeping: max over ranks of a time; sums of R^2 terms) */
+int mb_comm_allreduce_f64(mb_ctx* ctx, double* values_host, int n, int op);
+/* a6 with the residual rows sharded over the ranks: G = sum_r R_r' R_r, every rank gets G (n_local may be 0) */
+int mb_gram_allreduce(mb_ctx* ctx, const double* R_host, int n_local, int K, double* G_host);
+/* ship a fitted spline from `root` to every rank (*s is input on the root, output elsewhere); max_knots >= its knot count */
+int mb_spline_bcast(mb_ctx* ctx, mb_spline** s, int max_knots, int root);
+/* mb_mltps_predict* for ONE ROW BLOCK of a raster sharded over the communicator (global spline, V73:748-753): g_block is the
+ * extent + shape of this rank's rows (same xmin / xmax as the raster), e / cov / out belong to the block.  fields::Tps runs
+ * once, on `root`, beside the per-cell ensemble kernels that every rank - the root too - runs on its own block; the spline
+ * descriptor is broadcast and each rank finishes its own cells.  knots_xy / resid are read on the root only; n (the number of
+ * observations) must be the same on every rank.  Without a communicator this is mb_mltps_predict* with tile_px = 0. */
+int mb_mltps_predict_shard_dev(mb_ctx* ctx, const mb_grid* g_block, const mb_ensemble* e, const float* cov_dev, int C,
+                               const double* knots_xy, const double* resid, int n, double lambda, int root,
+                               double* out_dev, mb_spline** spline_out, void* stream);
+int mb_mltps_predict_shard(mb_ctx* ctx, const mb_grid* g_block, const mb_ensemble* e, const float* cov_host, int C,
+                           const double* knots_xy, const double* resid, int n, double lambda, int root,
+                           double* out_host, mb_spline** spline_out);
+
 /* ---- device memory helpers for hosts without a CUDA allocator (R) ---------------------- */
 int mb_dev_alloc(mb_ctx* ctx, size_t bytes, void** out);
 int mb_dev_free(mb_ctx* ctx, void* p);

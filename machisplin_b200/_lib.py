@@ -90,6 +90,17 @@ SIGNATURES = {
     "mb_gather_cells_dev": (C.c_int, [VP, VP, C.c_int64, C.c_int, C.c_int, PI32, PI32, C.c_int, PD, VP]),
     "mb_mltps_predict_dev": (C.c_int, [VP, PG, VP, VP, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, VP, PVP, VP]),
     "mb_mltps_predict": (C.c_int, [VP, PG, VP, PF, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, PD, PVP]),
+    "mb_comm_unique_id": (C.c_int, [VP]),
+    "mb_comm_init": (C.c_int, [VP, C.c_int, C.c_int, VP]),
+    "mb_comm_destroy": (C.c_int, [VP]),
+    "mb_comm_rank": (C.c_int, [VP]),
+    "mb_comm_size": (C.c_int, [VP]),
+    "mb_comm_backend": (C.c_char_p, []),
+    "mb_comm_allreduce_f64": (C.c_int, [VP, PD, C.c_int, C.c_int]),
+    "mb_gram_allreduce": (C.c_int, [VP, PD, C.c_int, C.c_int, PD]),
+    "mb_spline_bcast": (C.c_int, [VP, PVP, C.c_int, C.c_int]),
+    "mb_mltps_predict_shard_dev": (C.c_int, [VP, PG, VP, VP, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, VP, PVP, VP]),
+    "mb_mltps_predict_shard": (C.c_int, [VP, PG, VP, PF, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, PD, PVP]),
     "mb_dev_alloc": (C.c_int, [VP, C.c_size_t, PVP]),
     "mb_dev_free": (C.c_int, [VP, VP]),
     "mb_h2d": (C.c_int, [VP, VP, VP, C.c_size_t]),

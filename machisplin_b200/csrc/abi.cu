@@ -151,6 +151,7 @@ void mb_shutdown(mb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_release(ctx);
   fit_release(ctx);
   for (const mb_timed_launch& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
@@ -641,7 +642,13 @@ int mb_gather_cells_dev(mb_ctx* ctx, const double* raster_dev, int64_t row_strid
 // PCIe transfer (1.6 GB at config 3) hides behind part 2 instead of preceding it.
 static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, float* cov, int C,
                           const double* knots_xy, const double* resid, int n, double lambda, int tile_px,
-                          double* out, mb_spline** spline_out, cudaStream_t st, const float* cov_host = nullptr) {
+                          double* out, mb_spline** spline_out, cudaStream_t st, const float* cov_host = nullptr,
+                          int bcast_root = -1) {
+  // bcast_root >= 0 (mb_mltps_predict_shard*): g is this rank's row block of a raster that is sharded over the communicator.
+  // The global spline is fitted once, on the root, while every rank - the root included - runs the per-cell ensemble kernels of
+  // its own block; its descriptor (24 bytes per knot) then travels by ncclBroadcast and each rank evaluates it on its own cells.
+  const bool sharded = bcast_root >= 0 && ctx->comm != nullptr;
+  const bool fit_here = !sharded || ctx->comm_rank == bcast_root;
   const mb_window full{0, g.nrow, 0, g.ncol};
   const size_t ncell = (size_t)g.nrow * g.ncol;
   if (spline_out) *spline_out = nullptr;
@@ -664,10 +671,12 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
   // their 262 144-CTA grids.  In the host-buffer entry point the covariate planes travel meanwhile.
   double* acc = nullptr;
   const bool heavy = e != nullptr;
-  const bool tps = knots_xy && resid && n > 0;
+  const bool tps = sharded ? n > 0 : (knots_xy && resid && n > 0);
+  MB_REQUIRE(!sharded || !tps || tile_px <= 0, "the sharded entry point evaluates one global spline (tile_px <= 0)");
+  MB_REQUIRE(!(sharded && tps && fit_here) || (knots_xy && resid), "the broadcast root needs the knots and residuals");
   const bool one_spline = tps && (tile_px <= 0 || ((g.nrow + tile_px - 1) / tile_px) * ((g.ncol + tile_px - 1) / tile_px) == 1);
-  const bool defer = heavy && one_spline && lambda < 0 && ctx->eigen_impl != 1 && (ctx->sytrd_mode == 0 || ctx->sytrd_mode == 3) &&
-                     ctx->defer_ensemble;
+  const bool defer = heavy && one_spline && fit_here && lambda < 0 && ctx->eigen_impl != 1 &&
+                     (ctx->sytrd_mode == 0 || ctx->sytrd_mode == 3) && ctx->defer_ensemble;
   int nblk_copy = 0, rows_per = 0;
   if (heavy) {
     acc = ctx->arena.take_n<double>((size_t)(acc_stride(full) * acc_rows(full)));
@@ -722,18 +731,24 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
   if (tps) {
     const int nRx = tile_px > 0 ? (g.nrow + tile_px - 1) / tile_px : 1;
     const int nCx = tile_px > 0 ? (g.ncol + tile_px - 1) / tile_px : 1;
-    if (nRx * nCx == 1) {                                            // V73:748-753
+    if (nRx * nCx == 1 || sharded) {                                 // V73:748-753
       mb_spline* raw = nullptr;
-      if (defer) ctx->after_stage1 = [&] { launch_ensemble(true); };
-      try {
-        tps_fit(ctx, knots_xy, resid, n, 1, lambda, &raw);
-      } catch (...) {
+      if (fit_here) {
+        if (defer) ctx->after_stage1 = [&] { launch_ensemble(true); };
+        try {
+          tps_fit(ctx, knots_xy, resid, n, 1, lambda, &raw);
+        } catch (...) {
+          ctx->after_stage1 = nullptr;
+          throw;
+        }
         ctx->after_stage1 = nullptr;
-        throw;
+        sp.reset(raw);
+        launch_ensemble(false);        // not reached through the hook (e.g. a fit small enough to skip stage 1 entirely)
+        if (sharded) spline_bcast(ctx, sp.get(), n, bcast_root);
+      } else {
+        launch_ensemble(false);        // this rank's cells first; the receive below then waits for the root's fit
+        sp.reset(spline_bcast(ctx, nullptr, n, bcast_root));
       }
-      ctx->after_stage1 = nullptr;
-      sp.reset(raw);
-      launch_ensemble(false);          // not reached through the hook (e.g. a fit small enough to skip stage 1 entirely)
     } else {                                                         // V73:649-895
       double* surf = ctx->arena.take_n<double>(ncell);
       tiles_tps(ctx, g, knots_xy, resid, n, tile_px, 0.2, 0.025, 10, lambda, MB_EVAL_FAST, surf, ctx->stream);
@@ -798,6 +813,55 @@ int mb_mltps_predict(mb_ctx* ctx, const mb_grid* g, const mb_ensemble* e, const 
       MB_CUDA(cudaStreamSynchronize(st));
     } catch (...) {
       cudaDeviceSynchronize();   // the copy stream may still be reading cov_host, the side stream the arena
+      throw;
+    }
+  });
+}
+
+// ---- the same for one row block of a raster sharded over the communicator ------------------------------------------------
+int mb_mltps_predict_shard_dev(mb_ctx* ctx, const mb_grid* g_block, const mb_ensemble* e, const float* cov_dev, int C,
+                               const double* knots_xy, const double* resid, int n, double lambda, int root,
+                               double* out_dev, mb_spline** spline_out, void* stream) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && out_dev, "NULL argument");
+    check_grid(g_block);
+    MB_REQUIRE(root >= 0 && root < ctx->comm_size, "root out of range");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    try {
+      mltps_predict(ctx, *g_block, e, const_cast<float*>(cov_dev), C, knots_xy, resid, n, lambda, 0, out_dev, spline_out, st,
+                    nullptr, root);
+    } catch (...) {
+      cudaDeviceSynchronize();
+      throw;
+    }
+  });
+}
+
+int mb_mltps_predict_shard(mb_ctx* ctx, const mb_grid* g_block, const mb_ensemble* e, const float* cov_host, int C,
+                           const double* knots_xy, const double* resid, int n, double lambda, int root,
+                           double* out_host, mb_spline** spline_out) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && out_host, "NULL argument");
+    check_grid(g_block);
+    MB_REQUIRE(root >= 0 && root < ctx->comm_size, "root out of range");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->side;
+    ctx->arena.begin(st);
+    const size_t ncell = (size_t)g_block->nrow * g_block->ncol;
+    float* d_cov = nullptr;
+    if (e && C > 0) {
+      MB_REQUIRE(cov_host, "covariate planes are NULL");
+      d_cov = ctx->arena.take_n<float>((size_t)C * ncell);
+    }
+    double* d_out = ctx->arena.take_n<double>(ncell);
+    try {
+      mltps_predict(ctx, *g_block, e, d_cov, C, knots_xy, resid, n, lambda, 0, d_out, spline_out, st, cov_host, root);
+      MB_CUDA(cudaMemcpyAsync(out_host, d_out, ncell * sizeof(double), cudaMemcpyDeviceToHost, st));
+      MB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+      cudaDeviceSynchronize();
       throw;
     }
   });

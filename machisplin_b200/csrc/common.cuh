@@ -224,6 +224,10 @@ struct mb_ctx {
   std::vector<cudaEvent_t> ev_blocks;
   // worker lanes of the tile loop (mltps part 3): own stream + arena each, created on first use
   std::vector<std::unique_ptr<mb_ctx>> lanes;
+  // multi-GPU (comm.cu): NCCL communicator of this context (ncclComm_t), one process per GPU
+  void* comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  std::vector<double> comm_host;   // host staging of broadcast / gathered descriptors
 };
 
 struct mb_spline {

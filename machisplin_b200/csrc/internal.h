@@ -36,6 +36,16 @@ void ensemble_finish(mb_ctx* ctx, const mb_ensemble* e, const mb_spline* spline,
                      const mb_window& w, const double* acc, double* out_dev, cudaStream_t st);
 void ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X, int n, double* out_host);
 
+// comm.cu - NCCL communicator of the context; every collective of the path
+void comm_release(mb_ctx* ctx);
+void comm_allreduce_f64(mb_ctx* ctx, double* dev, int n, int op, cudaStream_t st);
+void comm_allgather_f64(mb_ctx* ctx, const double* send_dev, double* recv_dev, size_t count_per_rank, cudaStream_t st);
+size_t spline_wire_doubles(int cap);
+void spline_pack(const mb_spline* s, int cap, double* w);
+mb_spline* spline_unpack(mb_ctx* ctx, const double* w, int cap);
+// root sends its spline, the other ranks get a new handle (NULL on the root); on ctx->stream, synchronises it
+mb_spline* spline_bcast(mb_ctx* ctx, const mb_spline* s_root, int cap, int root);
+
 // tiles.cu - mltps part 3/4 (V73:649-895), machisplin.tiles.merge (V73:1392-1548), gram, gather
 void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const double* resid, int n, int tile_px,
                double fit_halo, double keep_halo, int min_pts, double lambda, int method, double* out_dev,

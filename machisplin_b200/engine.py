@@ -402,6 +402,90 @@ class Engine:
                                            _pd(out), C.c_void_p(stream)))
         return out
 
+    # -- multi-GPU: NCCL communicator of the context (one process per GPU) ------------------------------------
+    def comm_unique_id(self) -> bytes:
+        """Rank 0 creates the id; the host ships its 128 bytes to the other processes, each calls ``comm_init``."""
+        buf = C.create_string_buffer(128)
+        check(self.lib.mb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        assert len(uid) == 128
+        check(self.lib.mb_comm_init(self._h, int(nranks), int(rank), C.c_char_p(uid)))
+
+    def comm_destroy(self):
+        check(self.lib.mb_comm_destroy(self._h))
+
+    @property
+    def rank(self) -> int:
+        return int(self.lib.mb_comm_rank(self._h))
+
+    @property
+    def world(self) -> int:
+        return int(self.lib.mb_comm_size(self._h))
+
+    def comm_backend(self) -> str:
+        return self.lib.mb_comm_backend().decode()
+
+    def allreduce(self, values, op: str = "sum") -> np.ndarray:
+        v = np.ascontiguousarray(np.atleast_1d(np.asarray(values, dtype=np.float64))).copy()
+        check(self.lib.mb_comm_allreduce_f64(self._h, _pd(v), v.size, {"sum": 0, "max": 1}[op]))
+        return v
+
+    def gram_allreduce(self, R_local) -> np.ndarray:
+        """a6 with the k-fold residual rows sharded over the ranks (V73:329-333): every rank gets G = R'R."""
+        R = np.asfortranarray(np.asarray(R_local, dtype=np.float64))
+        n, K = R.shape
+        G = np.empty((K, K))
+        check(self.lib.mb_gram_allreduce(self._h, _pd(R) if n else None, n, K, _pd(G)))
+        return G
+
+    def spline_bcast(self, spline: Optional[Spline], max_knots: int, root: int = 0) -> Spline:
+        h = C.c_void_p(spline._h.value if spline is not None else None)
+        check(self.lib.mb_spline_bcast(self._h, C.byref(h), int(max_knots), int(root)))
+        if self.rank == root:
+            return spline
+        return Spline(self, h.value)
+
+    def mltps_predict_shard_dev(self, geom_block, ens: Optional[Ensemble], cov_ptr: int, Cn: int, knots_xy, resid, n: int,
+                                out_ptr: int, lam: Optional[float] = None, root: int = 0, stream: int = 0):
+        """Parts 2-5 for this rank's row block of a raster sharded over the communicator; one fit (on ``root``), broadcast."""
+        geom = as_geom(geom_block)
+        k = r = None
+        if knots_xy is not None:
+            k = np.asfortranarray(np.asarray(knots_xy, dtype=np.float64))
+            r = _f64(resid)
+            assert k.shape == (n, 2) and r.shape == (n,)
+        g = geom.c()
+        h = C.c_void_p()
+        check(self.lib.mb_mltps_predict_shard_dev(self._h, C.byref(g), ens._h if ens is not None else None,
+                                                  C.c_void_p(cov_ptr) if cov_ptr else None, Cn, _pd(k), _pd(r), int(n),
+                                                  -1.0 if lam is None else float(lam), int(root), C.c_void_p(out_ptr),
+                                                  C.byref(h), C.c_void_p(stream)))
+        return Spline(self, h.value) if h.value else None
+
+    def mltps_predict_shard(self, geom_block, ens: Optional[Ensemble], cov: Optional[np.ndarray], knots_xy, resid, n: int,
+                            lam: Optional[float] = None, root: int = 0, out: Optional[np.ndarray] = None):
+        """Host-buffer twin of ``mltps_predict_shard_dev``.  Returns (block raster, Spline)."""
+        geom = as_geom(geom_block)
+        k = r = None
+        if knots_xy is not None:
+            k = np.asfortranarray(np.asarray(knots_xy, dtype=np.float64))
+            r = _f64(resid)
+            assert k.shape == (n, 2) and r.shape == (n,)
+        Cn = 0 if cov is None else cov.shape[0]
+        if cov is not None:
+            cov = np.ascontiguousarray(cov, dtype=np.float32)
+            assert cov.shape == (Cn, geom.nrow, geom.ncol)
+        if out is None:
+            out = np.empty((geom.nrow, geom.ncol))
+        g = geom.c()
+        h = C.c_void_p()
+        check(self.lib.mb_mltps_predict_shard(self._h, C.byref(g), ens._h if ens is not None else None,
+                                              None if cov is None else cov.ctypes.data_as(_lib.PF), Cn, _pd(k), _pd(r), int(n),
+                                              -1.0 if lam is None else float(lam), int(root), _pd(out), C.byref(h)))
+        return out, (Spline(self, h.value) if h.value else None)
+
     # -- mltps parts 2-5 in one call (V73:442-932) ---------------------------------------------------------
     def _mltps_args(self, geom, ens, knots_xy, resid, lam, tile_px):
         geom = as_geom(geom)

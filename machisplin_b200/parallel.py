@@ -49,6 +49,28 @@ def row_blocks(nrow: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
     return out
 
 
+def block_geom(geom, r0: int, r1: int):
+    """Extent + shape of rows [r0, r1) of a raster: what a rank passes as ``g_block`` to ``mb_mltps_predict_shard*`` and creates
+    its ensemble handle for (same xmin / xmax, so LONG / LAT of a cell are those of the full raster)."""
+    from .engine import Geom, as_geom
+    g = as_geom(geom)
+    return Geom(g.xmin, g.xmax, g.ymax - r1 * g.ry, g.ymax - r0 * g.ry, r1 - r0, g.ncol)
+
+
+def comm_init(engine, backend_group=None):
+    """Give ``engine`` the library's own NCCL communicator over the ranks of the torch process group: rank 0 draws the
+    unique id (``mb_comm_unique_id``), the HOST side ships its 128 bytes (here: ``torch.distributed``; an R host would use a
+    file or a socket), every rank calls ``mb_comm_init``.  Data-path collectives then run inside the library."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0, 1
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=backend_group)
+    engine.comm_init(world, rank, box[0])
+    return rank, world
+
+
 def shard_rows(n: int, world: int, rank: int) -> slice:
     """Contiguous shard of n cross-validation residual rows."""
     base, extra = divmod(n, world)

@@ -73,6 +73,19 @@ def test_sharding_covers_everything_once():
         assert np.array_equal(rows, np.arange(90001))
 
 
+def test_row_block_geometry_reproduces_the_cell_centres():
+    """A rank's block geometry (parallel.block_geom) gives the cells of its rows the LONG / LAT of the full raster."""
+    geom = synth.make_geom(8192 + 17, 4096)
+    for (r0, r1) in par.row_blocks(geom.nrow, 8):
+        b = par.block_geom(geom, r0, r1)
+        assert (b.nrow, b.ncol, b.xmin, b.xmax) == (r1 - r0, geom.ncol, geom.xmin, geom.xmax)
+        rows = np.arange(r0, r1)
+        y_full = geom.ymax - (rows + 0.5) * geom.ry
+        y_blk = b.ymax - (rows - r0 + 0.5) * b.ry
+        assert np.max(np.abs(y_full - y_blk)) < 4e-16 * max(1.0, abs(geom.ymax))
+        assert abs(b.rx - geom.rx) == 0 and abs(b.ry - geom.ry) < 1e-18
+
+
 WORKER = r'''
 import os, sys
 import numpy as np
@@ -101,6 +114,22 @@ if rank == 0:
     assert [tuple(t.shape) for t in tl] == shapes and float(tl[1][1, 4]) == 2.0 and float(tl[0][0, 0]) == 1.0
 else:
     assert tl is None
+# the library's own NCCL communicator: rank 0 draws the id through the C ABI, the host ships it (here: gloo), every rank
+# would call mb_comm_init with the same 128 bytes (needs a GPU; the recording engine below stands in for that one call)
+import ctypes as C
+from machisplin_b200 import _lib
+class Rec:
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        assert _lib.load().mb_comm_unique_id(buf) == 0, _lib.load().mb_last_error()
+        return buf.raw
+    def comm_init(self, world, rank, uid):
+        self.got = (world, rank, uid)
+rec = Rec()
+assert par.comm_init(rec) == (rank, world)
+ids = [None] * world
+dist.all_gather_object(ids, rec.got[2])
+assert rec.got[:2] == (world, rank) and len(rec.got[2]) == 128 and ids[0] == ids[1] and any(ids[0])
 dist.barrier()
 dist.destroy_process_group()
 sys.stdout.write(f"rank{rank}ok\n"); sys.stdout.flush()
