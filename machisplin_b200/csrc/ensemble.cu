@@ -218,43 +218,44 @@ constexpr int kTreeSeg = kTreeChunk / 8;
 constexpr int kTreeIlp = 2;
 constexpr int kKindShift = 30;
 
+// Two-level variant (the default): the CTA tile of 32 x 8 cells is cut into eight 8 x 4 blocks, one per warp.  After the CTA-level
+// prune (phase 2, as above) every warp prunes the CTA's fork list once more with the feature intervals of ITS 32 cells, from the
+// fork nodes down (phase 2b): most surviving trees collapse to a warp constant there, and the cells walk only what forks inside
+// their own 8 x 4 block.  Measured on config 3 (tools/forest_prune_sim.c): 41 + 698 node visits per cell with one level,
+// 41 + 17 + 186 with two.  Every comparison is still the reference's own; the summation order is fixed (ballot order at both
+// levels), so results are deterministic.  On rough rasters (the reference's slope / TWI) most trees fork at every level and the
+// kernel degrades to the plain per-cell walk plus two cheap interval passes.
+constexpr int kWarpList = 256;       // fork-list entries a warp prunes per pass (bounds its residual list)
+
 template <int R>
 __global__ void __launch_bounds__(kTreeThreads) k_ens_trees(
     const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg, mb_window w,
     const int2* __restrict__ nodes, const int* __restrict__ roots, int n_rf, int n_gb, int zero_leaf,
     double rf_scale, double gb_scale, double base, int accumulate, int64_t acc_stride, double* __restrict__ acc) {
+  static_assert(R == 1, "the two-level kernel owns one cell per thread");
   extern __shared__ __align__(16) unsigned char tree_smem[];
-  float* s_feat = reinterpret_cast<float*>(tree_smem);                    // [(C + 2)][256 R]
-  int* s_list = reinterpret_cast<int*>(s_feat + (C + 2) * kTreeThreads * R);   // [8][kTreeSeg + kTreeIlp]
+  float* s_feat = reinterpret_cast<float*>(tree_smem);                    // [(C + 2)][256]
+  int* s_list = reinterpret_cast<int*>(s_feat + (C + 2) * kTreeThreads);  // [8][kTreeSeg + kTreeIlp]   CTA-level fork list
+  int* s_wlist = s_list + 8 * (kTreeSeg + kTreeIlp);                      // [8][kWarpList + kTreeIlp]  warp-level fork lists
   __shared__ float s_wlo[16][8], s_whi[16][8], s_lo[16], s_hi[16];
   __shared__ double s_wsum[8];
   __shared__ int s_cnt[8];
-  constexpr int kCells = kTreeThreads * R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int col = w.c0 + blockIdx.x * 32 + lane;
-  const int row0 = w.r0 + blockIdx.y * (8 * R) + warp;
+  // warp = 8 x 4 block (bx, by) of the tile, lane = cell (dx, dy) of the block
+  const int col = w.c0 + blockIdx.x * 32 + 8 * (warp & 3) + (lane & 7);
+  const int row = w.r0 + blockIdx.y * 8 + 4 * (warp >> 2) + (lane >> 3);
   const int64_t wc = acc_stride;
-  // ---- phase 1 -------------------------------------------------------------------------------
-  unsigned evalmask = 0;          // bit r: cell r of this thread is inside the window and has no NA
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int row = row0 + 8 * r;
-    if (col < w.c1 && row < w.r1) evalmask |= 1u << r;
-  }
+  const bool inside = col < w.c1 && row < w.r1;
+  // ---- phase 1: features -> shared memory, intervals of the warp's block and of the tile -------------------
+  bool eval = inside;
   for (int f = 0; f < C; ++f) {
-    float lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int row = row0 + 8 * r;
-      float v = 0.f;
-      if (col < w.c1 && row < w.r1) {
-        v = __ldg(&cov[f * plane + (int64_t)row * eg.ncol + col]);
-        if (v != v) evalmask &= ~(1u << r);
-        lo = fminf(lo, v);          // fminf / fmaxf drop NaN operands
-        hi = fmaxf(hi, v);
-      }
-      s_feat[f * kCells + r * kTreeThreads + tid] = v;
+    float v = 0.f, lo = INFINITY, hi = -INFINITY;
+    if (inside) {
+      v = __ldg(&cov[f * plane + (int64_t)row * eg.ncol + col]);
+      if (v != v) eval = false;
+      lo = hi = v;                    // NaN: dropped by fminf / fmaxf below
     }
+    s_feat[f * kTreeThreads + tid] = v;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -262,42 +263,35 @@ __global__ void __launch_bounds__(kTreeThreads) k_ens_trees(
     }
     if (lane == 0) { s_wlo[f][warp] = lo; s_whi[f][warp] = hi; }
   }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    s_feat[C * kCells + r * kTreeThreads + tid] = (float)col;
-    s_feat[(C + 1) * kCells + r * kTreeThreads + tid] = (float)(row0 + 8 * r);
+  s_feat[C * kTreeThreads + tid] = (float)col;
+  s_feat[(C + 1) * kTreeThreads + tid] = (float)row;
+  if (lane == 0) {
+    const int c_lo = w.c0 + blockIdx.x * 32 + 8 * (warp & 3), r_lo = w.r0 + blockIdx.y * 8 + 4 * (warp >> 2);
+    s_wlo[C][warp] = (float)c_lo; s_whi[C][warp] = (float)min(w.c1 - 1, c_lo + 7);
+    s_wlo[C + 1][warp] = (float)r_lo; s_whi[C + 1][warp] = (float)min(w.r1 - 1, r_lo + 3);
   }
-  const int any_eval = __syncthreads_or(evalmask != 0);
+  const int any_eval = __syncthreads_or(eval);
   if (!any_eval) {                                  // sea tile: nothing to evaluate
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int row = row0 + 8 * r;
-      if (col < w.c1 && row < w.r1 && !accumulate) acc[(int64_t)(row - w.r0) * wc + (col - w.c0)] = 0.0;
-    }
+    if (inside && !accumulate) acc[(int64_t)(row - w.r0) * wc + (col - w.c0)] = 0.0;
     return;
   }
-  if (tid < C) {
+  if (tid < C + 2) {
     float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
     for (int q = 0; q < 8; ++q) { lo = fminf(lo, s_wlo[tid][q]); hi = fmaxf(hi, s_whi[tid][q]); }
     s_lo[tid] = lo; s_hi[tid] = hi;
-  } else if (tid == C) {
-    s_lo[C] = (float)(w.c0 + blockIdx.x * 32);
-    s_hi[C] = (float)min(w.c1 - 1, w.c0 + blockIdx.x * 32 + 31);
-  } else if (tid == C + 1) {
-    s_lo[C + 1] = (float)(w.r0 + blockIdx.y * (8 * R));
-    s_hi[C + 1] = (float)min(w.r1 - 1, w.r0 + blockIdx.y * (8 * R) + 8 * R - 1);
   }
   __syncthreads();
   const int ntrees = n_rf + n_gb;
   const float* sf = s_feat + tid;
-  double cell_sum[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) cell_sum[r] = 0.0;
-  double csum = 0.0;                                // collapsed trees walked by this thread
+  double cell_sum = 0.0;
+  double csum = 0.0;                                // trees that collapse on the whole tile, walked by this thread
+  double wsum = 0.0;                                // trees that collapse on this warp's block, walked by this lane
   int* my_list = s_list + warp * (kTreeSeg + kTreeIlp);
+  int* my_wlist = s_wlist + warp * (kWarpList + kTreeIlp);
+  const bool warp_eval = __any_sync(0xffffffffu, eval);
   for (int t0 = 0; t0 < ntrees; t0 += kTreeChunk) {
-    // ---- phase 2 -----------------------------------------------------------------------------
+    // ---- phase 2: CTA-level prune, warp q owns trees [q per, (q + 1) per) of the chunk ----------------------
     const int nchunk = min(kTreeChunk, ntrees - t0);
     const int per = ((nchunk + 7) / 8 + 31) & ~31;   // trees per warp, whole rounds of 32
     int cnt = 0;
@@ -323,61 +317,85 @@ __global__ void __launch_bounds__(kTreeThreads) k_ens_trees(
       if (fork) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = idx | (kind << kKindShift);
       cnt += __popc(m);
     }
-    if (lane < kTreeIlp) my_list[cnt + lane] = zero_leaf;   // pad to a whole ILP batch
     if (lane == 0) s_cnt[warp] = cnt;
     __syncthreads();
-    // ---- phase 3 -----------------------------------------------------------------------------
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (!(evalmask >> r & 1u)) continue;
-      const float* sfr = sf + r * kTreeThreads;
-      double s = 0.0;
+    // ---- phase 2b + 3, warp-local: prune the CTA list with the block's intervals, then walk what is left -----
+    if (warp_eval) {
       for (int q = 0; q < 8; ++q) {
         const int n = s_cnt[q];
         const int* lst = s_list + q * (kTreeSeg + kTreeIlp);
-        for (int i = 0; i < n; i += kTreeIlp) {
-          int e[kTreeIlp], idx[kTreeIlp];
-          int2 nd[kTreeIlp];
-#pragma unroll
-          for (int u = 0; u < kTreeIlp; ++u) { e[u] = lst[i + u]; idx[u] = e[u] & ((1 << kKindShift) - 1); }
-          for (;;) {
-            int leafs = kMetaLeaf;
-#pragma unroll
-            for (int u = 0; u < kTreeIlp; ++u) { nd[u] = __ldg(&nodes[idx[u]]); leafs &= nd[u].y; }
-            if (leafs) break;
-#pragma unroll
-            for (int u = 0; u < kTreeIlp; ++u) {
-              if (!(nd[u].y & kMetaLeaf)) {
-                const float x = sfr[(nd[u].y & 15) * kCells];
-                idx[u] = (nd[u].y >> 5) + (x <= __int_as_float(nd[u].x) ? 0 : 1);
+        for (int i0 = 0; i0 < n; i0 += kWarpList) {
+          const int n1 = min(kWarpList, n - i0);
+          int wcnt = 0;
+          for (int i = 0; i < n1; i += 32) {
+            bool fork = false;
+            int e = 0, idx = 0;
+            if (i + lane < n1) {
+              e = lst[i0 + i + lane];
+              idx = e & ((1 << kKindShift) - 1);
+              for (;;) {
+                const int2 nd = __ldg(&nodes[idx]);
+                if (nd.y & kMetaLeaf) { wsum += ((e >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd.x); break; }
+                const int f = nd.y & 15;
+                const float thr = __int_as_float(nd.x);
+                if (s_whi[f][warp] <= thr) idx = nd.y >> 5;
+                else if (s_wlo[f][warp] > thr) idx = (nd.y >> 5) + 1;
+                else { fork = true; break; }
               }
             }
+            const unsigned m = __ballot_sync(0xffffffffu, fork);
+            if (fork) my_wlist[wcnt + __popc(m & ((1u << lane) - 1u))] = idx | (e & (1 << kKindShift));
+            wcnt += __popc(m);
           }
+          if (lane < kTreeIlp) my_wlist[wcnt + lane] = zero_leaf;   // pad to a whole ILP batch
+          __syncwarp();
+          if (eval) {
+            double s = 0.0;
+            for (int i = 0; i < wcnt; i += kTreeIlp) {
+              int e[kTreeIlp], idx[kTreeIlp];
+              int2 nd[kTreeIlp];
 #pragma unroll
-          for (int u = 0; u < kTreeIlp; ++u)
-            s += ((e[u] >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd[u].x);
+              for (int u = 0; u < kTreeIlp; ++u) { e[u] = my_wlist[i + u]; idx[u] = e[u] & ((1 << kKindShift) - 1); }
+              for (;;) {
+                int leafs = kMetaLeaf;
+#pragma unroll
+                for (int u = 0; u < kTreeIlp; ++u) { nd[u] = __ldg(&nodes[idx[u]]); leafs &= nd[u].y; }
+                if (leafs) break;
+#pragma unroll
+                for (int u = 0; u < kTreeIlp; ++u) {
+                  if (!(nd[u].y & kMetaLeaf)) {
+                    const float x = sf[(nd[u].y & 15) * kTreeThreads];
+                    idx[u] = (nd[u].y >> 5) + (x <= __int_as_float(nd[u].x) ? 0 : 1);
+                  }
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < kTreeIlp; ++u)
+                s += ((e[u] >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd[u].x);
+            }
+            cell_sum += s;
+          }
+          __syncwarp();                              // the warp list is rewritten by the next pass
         }
       }
-      cell_sum[r] += s;
     }
-    __syncthreads();                                 // lists are rewritten by the next chunk
+    __syncthreads();                                 // the CTA list is rewritten by the next chunk
   }
-  // ---- tile constant: fixed-order reduction of the per-thread sums -----------------------------
+  // ---- constants: fixed-order reductions of the per-thread sums (tile) and per-lane sums (block) ----------
 #pragma unroll
-  for (int o = 16; o; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+  for (int o = 16; o; o >>= 1) {
+    csum += __shfl_xor_sync(0xffffffffu, csum, o);
+    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  }
   if (lane == 0) s_wsum[warp] = csum;
   __syncthreads();
   double tile_const = base;
 #pragma unroll
   for (int q = 0; q < 8; ++q) tile_const += s_wsum[q];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int row = row0 + 8 * r;
-    if (col < w.c1 && row < w.r1) {
-      double* dst = acc + (int64_t)(row - w.r0) * wc + (col - w.c0);
-      const double v = (evalmask >> r & 1u) ? tile_const + cell_sum[r] : 0.0;
-      *dst = accumulate ? *dst + v : v;
-    }
+  if (inside) {
+    double* dst = acc + (int64_t)(row - w.r0) * wc + (col - w.c0);
+    const double v = eval ? (tile_const + wsum) + cell_sum : 0.0;
+    *dst = accumulate ? *dst + v : v;
   }
 }
 
@@ -859,9 +877,10 @@ static void launch_trees(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
                          const mb_window& w, const int* roots, int n_rf, int n_gb, double* acc, cudaStream_t st) {
   const double rf_scale = n_rf ? e->w[MB_R] / n_rf : 0.0, gb_scale = e->w[MB_B];
   const double base = (n_rf ? e->w[MB_R] * e->rf.offset : 0.0) + (n_gb ? e->w[MB_B] * e->gb_initF : 0.0);
-  const int R = ctx->tree_rows > 0 ? ctx->tree_rows : 1;   // measured: R = 1 gives the shortest step (profiles/r1r_tree_rows.txt)
-  const size_t smem = sizeof(float) * (size_t)(C + 2) * kTreeThreads * R + sizeof(int) * 8 * (kTreeSeg + kTreeIlp);
-  dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 8 * R - 1) / (8 * R));
+  const int R = 1;                                          // one cell per thread (R = 2 / 4 measured slower in round 1, profiles/r1r_tree_rows.txt)
+  const size_t smem = sizeof(float) * (size_t)(C + 2) * kTreeThreads +
+                      sizeof(int) * 8 * ((kTreeSeg + kTreeIlp) + (kWarpList + kTreeIlp));
+  dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
 #define MB_TREES_CASE(RR)                                                                                         \
   case RR: {                                                                                                      \
     static thread_local bool attr = false;                                                                        \
@@ -874,8 +893,8 @@ static void launch_trees(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
         0, acc_stride(w), acc);                                                                                   \
   } break;
   switch (R) {
-    MB_TREES_CASE(1) MB_TREES_CASE(2) MB_TREES_CASE(4)
-    default: throw Error(MB_E_ARG, "tree tile rows-per-thread must be 1, 2 or 4");
+    MB_TREES_CASE(1)
+    default: throw Error(MB_E_ARG, "tree tile rows-per-thread must be 1");
   }
 #undef MB_TREES_CASE
 }

@@ -189,33 +189,37 @@ def test_gather_cells_matches_numpy(engine):
 @pytest.mark.parametrize("tps_helps", [True, False])
 def test_part5_keeps_the_better_r2(engine, tps_helps):
     """V73:910-930: final = ensemble + TPS only if its R^2 at the points beats the ensemble's; the residuals are the
-    TPS-corrected ones either way (V73:913 overwrites l$residuals before the test)."""
+    TPS-corrected ones either way (V73:913 overwrites l$residuals before the test).
+    A smoothing spline never increases the RSS at its own knots, so the TPS can only lose through the reference's weight quirk
+    (V73:337, 619-620): the divisor is the UNROUNDED total over ALL candidates, so with a dropped model the kept weights sum to
+    s < 1, res.FINAL = s (resp - f) and ensemble + TPS ~ s resp at the points - off by (1 - s) resp."""
     geom = synth.make_geom(192, 256)
     C = 2
     cov = synth.covariate_planes(geom, C, nan_frac=0.0)
     xy, krow, kcol = synth.make_knots(geom, 400, 12)
     X = np.column_stack([cov[:, krow, kcol].T.astype(np.float64), xy])
-    coef = np.array([5.0, 0.02, -0.01, 3.0, -2.0])
+    coef = np.array([200.0, 0.02, -0.01, 3.0, -2.0])
     lin = coef[0] + X @ coef[1:]
-    models = {"g": {"coef": coef}}
-    p = np.array([1.0])
+    rng = np.random.default_rng(4)
     if tps_helps:
+        models, letters, p = {"g": {"coef": coef}}, "g", np.array([1.0])
         resp = lin + 2.0 * np.sin(6 * xy[:, 0]) * np.cos(4 * xy[:, 1])      # smooth spatial residual: the TPS recovers it
-        lam = None
     else:
-        resp = lin.copy()                                                   # exact ensemble, zero residuals; a heavily smoothed TPS of
-        resp[::7] += 1e-3                                                   # a few spikes moves every knot away from its response
-        lam = 1e-2
-    kept, w, wt = om.select_models(p, letters="g")
-    ref = oml.mltps_one_response(geom.as_tuple(), cov, xy, resp, models, kept, w, wt, tile_px=1500, lam=lam)
-    got = mm.mltps_response(engine, geom, cov, xy, resp, models, p, letters="g", tile_px=1500, lam=lam)
+        nn = synth.make_models(geom, C, 300, 9, kept="n")["n"]
+        models, letters, p = {"g": {"coef": coef}, "n": nn}, "gn", np.array([0.96, 0.04])   # nnet dropped: 0.04 < 0.05 * 1.0
+        resp = lin + 0.01 * rng.standard_normal(lin.size)                   # the ensemble alone is (almost) exact
+    kept, w, wt = om.select_models(p, letters=letters)
+    assert kept == "g"
+    ref = oml.mltps_one_response(geom.as_tuple(), cov, xy, resp, models, kept, w, wt, tile_px=1500)
+    got = mm.mltps_response(engine, geom, cov, xy, resp, models, p, letters=letters, tile_px=1500)
     assert ref["tps_kept"] == tps_helps
     assert got["summary"]["tps_kept"] == tps_helps
+    assert abs(got["summary"]["rsq_model"] - ref["rsq_model"]) < 1e-9
+    assert abs(got["summary"]["rsq_final"] - ref["rsq_final"]) < 1e-6 * max(1.0, abs(ref["rsq_final"]))
     assert relerr(got["final"], ref["final"]) < 2e-6
     scale = np.max(np.abs(ref["final"]))
     assert np.max(np.abs(got["residuals"] - ref["residuals"])) < 2e-6 * scale
     if not tps_helps:
-        ens_only = coef[0] + cov[0] * coef[1] + cov[1] * coef[2]            # final is the ensemble raster alone
         x, yv = otps.cell_centres(geom.as_tuple(), np.arange(geom.nrow), np.arange(geom.ncol))
-        ens_only = ens_only + coef[3] * x[None, :] + coef[4] * yv[:, None]
-        assert np.max(np.abs(got["final"] - ens_only)) < 1e-9 * scale
+        ens_only = 0.96 * (coef[0] + cov[0] * coef[1] + cov[1] * coef[2] + coef[3] * x[None, :] + coef[4] * yv[:, None])
+        assert np.max(np.abs(got["final"] - ens_only)) < 1e-9 * scale      # the final raster is the ensemble alone
