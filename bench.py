@@ -54,7 +54,6 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one raster of N x nrow rows (a config-sized block per GPU); strong = the nrow x ncol raster cut in N")
     ap.add_argument("--lam", type=float, default=None, help="fixed lambda (Cholesky path) instead of GCV")
-    ap.add_argument("--tree-rows", type=int, default=0, help="forest tile: cells per thread (1, 2, 4; 0 = auto)")
     ap.add_argument("--eval-precision", type=int, default=0, help="leaf kernel path: 0 auto, 1 float64, 2 mixed")
     ap.add_argument("--param", action="append", default=[], help="engine tunable name=value (mb_set_param), repeatable")
     return ap.parse_args()
@@ -338,7 +337,6 @@ def run_b200(args):
     bgeom = par.block_geom(geom, r0, r1)
     eng = mb.Engine(local)
     par.comm_init(eng)                              # the library's own communicator; torch only ships the 128-byte id
-    eng.set_param("tree_rows", args.tree_rows)
     eng.set_param("eval_precision", args.eval_precision)
     for kv in args.param:
         name, val = kv.split("=")

@@ -240,16 +240,16 @@ int mb_debug_values(mb_ctx* ctx, const char* name, double* out, int cap);
 
 /* Tunables of the fast evaluator (0 = automatic). */
 int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows);
-/* Named integer tunables (0 = automatic): "tree_rows" = cells per thread of the forest tile (1, 2, 4);
+/* Named integer tunables (0 = automatic):
  * "eval_precision" = leaf kernel code path of the fast evaluator (1 = float64 only, 2 = force mixed);
  * "sytrd_mode" = tridiagonalisation of the GCV fit: 0 / 3 = two-stage (band reduction + bulge chasing, the default),
  * 1 = one-stage persistent kernel, 2 = one-stage with one kernel per phase; "sytrd_ctas_per_sm" = grid size of the
  * one-stage persistent kernel; "sbr_qr_grid" = 1 makes the panel QR of the two-stage path use the software grid
  * barrier instead of a thread-block cluster; "sbr_qr_impl" = 1 / 2 keeps the panel rows in shared memory / registers
  * (0 = chosen by cluster size); "sbr_debug" = 1 keeps the band matrix for mb_debug_values("sbr_band");
- * "svm_impl" = 1 / 2 (before mb_ensemble_create), "coef_impl" = 1, "sbr_chase_impl" = 1 and "sbr_fuse" = 1 select experimental kernels
- * that have not run on a GPU yet (ksvm dot products on the tensor pipe; coefficients from the band form of the two-stage reduction;
- * watcher and publisher warps in the bulge chase; one fused cluster kernel per panel) - see DESIGN.md section 9;
+ * "svm_impl" (before mb_ensemble_create) = 1 ksvm dot products on the tensor pipe (3 x TF32; the default for P <= 8), 2 packed FP32;
+ * "coef_impl" = 1 coefficients from the band form of the two-stage reduction (default), 2 dense Cholesky of M + lambda I;
+ * "sbr_chase_impl" = 1 watcher and publisher warps in the bulge chase (default), 2 three warps per sweep;
  * "defer_ensemble" = 0 starts the per-cell ensemble kernels of mb_mltps_predict* before the fit instead of behind stage 1
  * of its tridiagonalisation; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd (validation of the in-house path only). */
 int mb_set_param(mb_ctx* ctx, const char* name, int value);

@@ -255,27 +255,21 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
   return guarded([&] {
     MB_REQUIRE(ctx && name, "NULL argument");
     const std::string n(name);
-    if (n == "tree_rows") {
-      MB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4, "tree_rows must be 0, 1, 2 or 4");
-      ctx->tree_rows = value;
-    } else if (n == "eigen_impl") {
+    if (n == "eigen_impl") {
       MB_REQUIRE(value == 0 || value == 1, "eigen_impl must be 0 (in-house) or 1 (cuSOLVER, validation)");
       ctx->eigen_impl = value;
     } else if (n == "sytrd_mode") {
       MB_REQUIRE(value >= 0 && value <= 3,
                  "sytrd_mode must be 0 (default = two-stage), 1 (one-stage persistent kernel), 2 (one-stage, kernel per phase) or 3 (two-stage)");
       ctx->sytrd_mode = value;
-    } else if (n == "sbr_fuse") {
-      MB_REQUIRE(value == 0 || value == 1, "sbr_fuse must be 0 or 1 (fused per-panel cluster kernel, experimental)");
-      ctx->sbr_fuse = value;
     } else if (n == "sbr_chase_impl") {
-      MB_REQUIRE(value == 0 || value == 1, "sbr_chase_impl must be 0 or 1 (watcher / publisher warps, experimental)");
+      MB_REQUIRE(value >= 0 && value <= 2, "sbr_chase_impl must be 0 (default = 1), 1 (watcher / publisher warps) or 2 (three warps per sweep)");
       ctx->sbr_chase_impl = value;
     } else if (n == "coef_impl") {
-      MB_REQUIRE(value == 0 || value == 1, "coef_impl must be 0 (dense Cholesky) or 1 (band form of the two-stage reduction, experimental)");
+      MB_REQUIRE(value >= 0 && value <= 2, "coef_impl must be 0 (default = 1), 1 (band form of the two-stage reduction) or 2 (dense Cholesky)");
       ctx->coef_impl = value;
     } else if (n == "svm_impl") {
-      MB_REQUIRE(value >= 0 && value <= 2, "svm_impl must be 0 (packed FP32), 1 (3 x TF32 tensor-core dot products) or 2 (1 + half of the exponentials on the FMA pipe); 1 and 2 are experimental");
+      MB_REQUIRE(value >= 0 && value <= 2, "svm_impl must be 0 (default: 1 when P <= 8, else 2), 1 (3 x TF32 tensor-core dot products) or 2 (packed FP32)");
       ctx->svm_impl = value;
     } else if (n == "defer_ensemble") {
       MB_REQUIRE(value == 0 || value == 1, "defer_ensemble must be 0 or 1");

@@ -188,9 +188,8 @@ struct mb_ctx {
   int64_t launches = 0;
   // fast-evaluator tunables (0 = automatic)
   int cheb_p = 0, leaf_cols = 0, leaf_rows = 0;
-  int tree_rows = 0;          // cells per thread of the tree tile (1, 2, 4; 0 = automatic)
-  int svm_impl = 0;           // ksvm kernel: 0 = packed FP32 (k_ens_svm), 1 = dot products on the tensor pipe (k_ens_svm_mma; set before mb_ensemble_create),
-                              // 2 = 1 + half of the exponentials as a polynomial on the FMA pipe
+  int svm_impl = 0;           // ksvm kernel: 0 = automatic (1 when P <= 8), 1 = dot products on the tensor pipe (k_ens_svm_mma, P <= 8),
+                              // 2 = packed FP32 (k_ens_svm); read by mb_ensemble_create
   // 256-entry (1/m_k, -log(1/m_k)) table for the float64 table-driven log
   mb::DevBuf<double2> logtab;
   int eval_precision = 0;     // fast evaluator: 0 = automatic, 1 = float64 only, 2 = force mixed
@@ -201,11 +200,10 @@ struct mb_ctx {
   std::vector<double> dbg_band;
   cudaStream_t sbr_aux = nullptr;   // two-stage path: stream of the look-ahead trailing updates + its events
   cudaEvent_t sbr_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  int coef_impl = 0;          // coefficients at the selected lambda: 0 = dense Cholesky of M + lambda I, 1 = band form of the two-stage
-                              // reduction (block band Cholesky + back-transformation; experimental)
+  int coef_impl = 0;          // coefficients at the selected lambda: 0 = default = 1 = band form of the two-stage reduction (block band
+                              // Cholesky + back-transformation by the stored panel reflectors), 2 = dense Cholesky of M + lambda I
   mb_band_form band_form;
-  int sbr_fuse = 0;           // two-stage path: 1 = one cluster kernel (k_sbr_fin) instead of vtz + st + w + pu per panel (experimental)
-  int sbr_chase_impl = 0;     // bulge chase: 0 = three warps per sweep, 1 = + watcher and publisher warps (experimental)
+  int sbr_chase_impl = 0;     // bulge chase: 0 = default = 1 = three warps per sweep + watcher and publisher warps, 2 = three warps per sweep
   int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers
   int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits
   int sytrd_ctas_per_sm = 0;  // persistent grid size (0 = 2 per SM)

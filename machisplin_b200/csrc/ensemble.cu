@@ -60,7 +60,7 @@ struct mb_ensemble {
   int svm_pairs = 0;                 // ceil(S / 2)
   mb::DevBuf<float4> svm_svp;        // [pair][NQ]: (sv_2j[2q], sv_2j+1[2q], sv_2j[2q+1], sv_2j+1[2q+1]) x 2 sigma log2e
   mb::DevBuf<float4> svm_bap;        // [pair]: (b_2j, b_2j+1, alpha_2j, alpha_2j+1), b = -sigma |sv|^2 log2e
-  // tensor-core variant (k_ens_svm_mma, "svm_impl" = 1, P <= 8; built only when that variant is selected at create time):
+  // tensor-core variant (k_ens_svm_mma, P <= 8, the default there; not built with "svm_impl" = 2):
   int svm_oct = 0;                   // ceil(S / 8)
   mb::DevBuf<float4> svm_bq;         // [octet][lane]: B fragments of mma.m16n8k8.tf32, (hi f=tig, hi f=tig+4, lo f=tig, lo f=tig+4) of SV 8o + (lane >> 2)
   mb::DevBuf<float4> svm_baq;        // svm_bap padded with zeros to 4 pairs per octet
@@ -228,7 +228,7 @@ constexpr int kKindShift = 30;
 constexpr int kWarpList = 256;       // fork-list entries a warp prunes per pass (bounds its residual list)
 
 template <int R>
-__global__ void __launch_bounds__(kTreeThreads) k_ens_trees(
+__global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
     const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg, mb_window w,
     const int2* __restrict__ nodes, const int* __restrict__ roots, int n_rf, int n_gb, int zero_leaf,
     double rf_scale, double gb_scale, double base, int accumulate, int64_t acc_stride, double* __restrict__ acc) {
@@ -712,7 +712,7 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
     e->svm_bias = m.svm_b; e->svm_sigma = m.svm_sigma; e->svm_yc = m.svm_y_center; e->svm_ys = m.svm_y_scale;
     e->svp_sv.upload(m.svm_sv, (size_t)S * P, st);
     e->svp_alpha.upload(m.svm_alpha, S, st);
-    if (ctx->svm_impl >= 1 && P <= 8) {
+    if (ctx->svm_impl != 2 && P <= 8) {
       // 3 x TF32 operands: value = hi + lo with hi, lo exactly representable in TF32 (low 13 mantissa bits zero)
       auto tf32 = [](float x) { uint32_t u; std::memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; float y; std::memcpy(&y, &u, 4); return y; };
       const int noct = (S + 7) / 8;
@@ -903,7 +903,7 @@ static SmoothParams smooth_params(const mb_ensemble* e);
 
 
 // ---------------------------------------------------------------------------------------------
-// k_ens_svm_mma ("svm_impl" = 1, P <= 8; NOT the default - see DESIGN.md section 9): the 8-feature dot products of
+// k_ens_svm_mma (the default for P <= 8; measured 59.0 against 65.4 ms for k_ens_svm on config 3, profiles/r2a_*): the 8-feature dot products of
 // k_ens_svm on the tensor pipe.  ncu (r1s) shows k_ens_svm bound by the FMA pipe (67 % busy: 16 of the 20 packed FP32
 // instructions per 2 SV x 2 cells are the dot products), with MUFU.EX2 at 53 %; moving the dot products to
 // mma.sync.m16n8k8.tf32 leaves 2 FADD2 + 2 FFMA2 + 4 MUFU per 16 cells x 8 SVs per M-tile on the other pipes.
@@ -928,27 +928,6 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], flo
                  "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
-// 2^e for two values on the FMA pipe instead of MUFU.EX2 ("svm_impl" = 2): round-to-nearest split e = n + f through the
-// 1.5 * 2^23 trick, degree-5 minimax polynomial on f in [-0.5, 0.5] (max relative error 1.9e-7, ex2.approx: ~2 ulp), the integer
-// part goes into the exponent field.  e is clamped to [-126, 126] (the exponents of a Gaussian kernel are <= 0).
-__device__ __forceinline__ float2 exp2_poly2(float2 e) {
-  e.x = fminf(fmaxf(e.x, -126.f), 126.f);
-  e.y = fminf(fmaxf(e.y, -126.f), 126.f);
-  const float2 magic = make_float2(12582912.f, 12582912.f);
-  const float2 t = __fadd2_rn(e, magic);
-  const float2 nf = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __ffma2_rn(nf, make_float2(-1.f, -1.f), e);
-  float2 p = make_float2(0.0013264744775369763f, 0.0013264744775369763f);
-  p = __ffma2_rn(p, f, make_float2(0.009671512991189957f, 0.009671512991189957f));
-  p = __ffma2_rn(p, f, make_float2(0.05550733581185341f, 0.05550733581185341f));
-  p = __ffma2_rn(p, f, make_float2(0.24022242426872253f, 0.24022242426872253f));
-  p = __ffma2_rn(p, f, make_float2(0.6931470036506653f, 0.6931470036506653f));
-  p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
-  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
-                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
-}
-
-template <bool kPoly>   // kPoly: half of the exponentials (support vectors 2t + 1) on the FMA pipe
 __global__ void __launch_bounds__(kSvmThreads) k_ens_svm_mma(
     const float* __restrict__ cov, int C, int P, int64_t plane, EnsGeom eg, mb_window w,
     const float4* __restrict__ bq, const float4* __restrict__ baq, int noct,
@@ -1022,14 +1001,8 @@ __global__ void __launch_bounds__(kSvmThreads) k_ens_svm_mma(
         mma_tf32(d, al[mt], bf.x, bf.y);          // x_lo . sv_hi
         mma_tf32(d, ah[mt], bf.z, bf.w);          // x_hi . sv_lo
         mma_tf32(d, ah[mt], bf.x, bf.y);          // x_hi . sv_hi
-        if (kPoly) {
-          const float2 eb = exp2_poly2(make_float2(d[1], d[3]));
-          part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), eb.x), part[mt][0]);
-          part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), eb.y), part[mt][1]);
-        } else {
-          part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), ex2_approx(d[1])), part[mt][0]);
-          part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), ex2_approx(d[3])), part[mt][1]);
-        }
+        part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), ex2_approx(d[1])), part[mt][0]);
+        part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), ex2_approx(d[3])), part[mt][1]);
       }
     }
   }
@@ -1095,17 +1068,11 @@ void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
     launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, st);
     started = true;
   }
-  if (e->has[MB_V] && ctx->svm_impl >= 1 && e->svm_oct > 0) {
+  if (e->has[MB_V] && e->svm_oct > 0) {           // the handle was created for the tensor-pipe kernel (P <= 8, svm_impl != 2)
     dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
-    if (ctx->svm_impl == 2) {
-      MB_LAUNCH(ctx, "k_ens_svm_mma_poly", st) k_ens_svm_mma<true><<<grid, kSvmThreads, 0, st>>>(
-          cov, e->C, e->P, plane, eg, w, e->svm_bq.p, e->svm_baq.p, e->svm_oct, e->svm_xc.p, e->svm_xis.p, e->svm_sigma,
-          e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], started ? 1 : 0, smooth_params(e), astride, acc);
-    } else {
-      MB_LAUNCH(ctx, "k_ens_svm_mma", st) k_ens_svm_mma<false><<<grid, kSvmThreads, 0, st>>>(
-          cov, e->C, e->P, plane, eg, w, e->svm_bq.p, e->svm_baq.p, e->svm_oct, e->svm_xc.p, e->svm_xis.p, e->svm_sigma,
-          e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], started ? 1 : 0, smooth_params(e), astride, acc);
-    }
+    MB_LAUNCH(ctx, "k_ens_svm_mma", st) k_ens_svm_mma<<<grid, kSvmThreads, 0, st>>>(
+        cov, e->C, e->P, plane, eg, w, e->svm_bq.p, e->svm_baq.p, e->svm_oct, e->svm_xc.p, e->svm_xis.p, e->svm_sigma,
+        e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], started ? 1 : 0, smooth_params(e), astride, acc);
   } else if (e->has[MB_V]) {
     switch ((e->P + 1) / 2) {
 #define MB_SVM_CASE(n) case n: launch_svm<n>(e, cov, plane, eg, w, acc, started ? 1 : 0, st); break;

@@ -554,176 +554,6 @@ __global__ void __launch_bounds__(128) k_sbr_w(const double* __restrict__ V, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_sbr_fin ("sbr_fuse" = 1, experimental - DESIGN.md section 9 item 3): k_sbr_vtz + k_sbr_st + k_sbr_w + k_sbr_pu as ONE
-// cluster kernel, thread = row of the panel as in the panel QR.  Z0 (sum of the k-split partials) stays in registers, the V
-// rows of the CTA in shared memory; the 32 x 32 Gram partials G0 = V'Z0 and V'z are exchanged over distributed shared memory;
-// every CTA then forms S = T'G0 T and T'(V'z) itself, writes its rows of W, updates its rows of z, and - after the first 32
-// rows of V and W have been broadcast from CTA 0 - applies the look-ahead update to its rows of the next panel.
-// ---------------------------------------------------------------------------------------------
-struct FinArgs {
-  const double* V; int ldv; int r;
-  const double* Zp; int nsplit;
-  const double* T;
-  double* W;
-  double* z; int ldz; int zrow0; int L;
-  double* C; int ld;               // trailing matrix (for the look-ahead update of its first 32 columns)
-};
-constexpr size_t kFinSmem = sizeof(double) * (kQrRows * kPad + 2 * 64 * kPad + 3 * 32 * kPad + 2048 + 2 * 32 * kPad);
-
-__global__ void __launch_bounds__(kQrRows, 1) k_sbr_fin(FinArgs a) {
-  extern __shared__ double sm_fin[];
-  double* Vs = sm_fin;                              // [512][33]
-  double* Zc = Vs + kQrRows * kPad;                 // [64][33]  chunk of Z0 rows; later X = G0 T; later the local copy of W[0:32]
-  double* zc = Zc + 64 * kPad;                      // [64][33]  chunk of z rows; later the local copy of V[0:32]
-  double* Ts = zc + 64 * kPad;                      // [32][33]
-  double* Ss = Ts + 32 * kPad;                      // [32][33]  G0, then S
-  double* tzs = Ss + 32 * kPad;                     // [32][33]  V'z, then T'(V'z)
-  double* Gpart = tzs + 32 * kPad;                  // [2048]    this CTA's partial G0 | V'z, read by the peers
-  double* TopW = Gpart + 2048;                      // [32][33]  CTA 0: rows 0..31 of W, read by the peers
-  double* TopV = TopW + 32 * kPad;                  // [32][33]  CTA 0: rows 0..31 of V
-  cg::cluster_group cluster = cg::this_cluster();
-  const int t = threadIdx.x, blk = blockIdx.x, G = gridDim.x;
-  const int gi = blk * kQrRows + t;
-  const bool inld = gi < a.ldv;
-  // ---- Z0 row in registers, V row in shared memory ----------------------------------------------------------------
-  double zr[32];
-#pragma unroll
-  for (int q = 0; q < 32; ++q) {
-    double sacc = 0.0;
-    if (inld)
-      for (int sp = 0; sp < a.nsplit; ++sp) sacc += a.Zp[(size_t)sp * a.ldv * 32 + gi + (size_t)q * a.ldv];
-    zr[q] = sacc;
-    Vs[t * kPad + q] = inld ? a.V[gi + (size_t)q * a.ldv] : 0.0;
-  }
-  // ---- partial G0 = V'Z0 and V'z over this CTA's 512 rows, 64 at a time ----------------------------------------------
-  const int ga = t & 31, bq = t >> 5;               // outputs [ga][2 bq], [ga][2 bq + 1]
-  double g0[2] = {0.0, 0.0}, gz[2] = {0.0, 0.0};
-  for (int ch = 0; ch < 8; ++ch) {
-    if ((t >> 6) == ch) {
-      const int rw = t & 63;
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        Zc[rw * kPad + q] = zr[q];
-        zc[rw * kPad + q] = (q < a.L && gi < a.r) ? a.z[(size_t)a.zrow0 + gi + (size_t)q * a.ldz] : 0.0;
-      }
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int rw = 0; rw < 64; ++rw) {
-      const double va = Vs[(ch * 64 + rw) * kPad + ga];
-#pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        g0[x] = fma(va, Zc[rw * kPad + 2 * bq + x], g0[x]);
-        gz[x] = fma(va, zc[rw * kPad + 2 * bq + x], gz[x]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int x = 0; x < 2; ++x) {
-    Gpart[ga * 32 + 2 * bq + x] = g0[x];
-    Gpart[1024 + ga * 32 + 2 * bq + x] = gz[x];
-  }
-  cluster.sync();
-  // ---- totals over the cluster (fixed order), T ----------------------------------------------------------------------
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int idx = t + kQrRows * h;                // 0 .. 1023
-    double p0[16], p1[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const double* peer = cluster.map_shared_rank(Gpart, q < G ? q : 0);
-      p0[q] = q < G ? peer[idx] : 0.0;
-      p1[q] = q < G ? peer[1024 + idx] : 0.0;
-    }
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { s0 += p0[q]; s1 += p1[q]; }
-    Ss[(idx >> 5) * kPad + (idx & 31)] = s0;
-    tzs[(idx >> 5) * kPad + (idx & 31)] = s1;
-    Ts[(idx >> 5) * kPad + (idx & 31)] = a.T[idx];
-  }
-  __syncthreads();
-  // ---- X = G0 T (into Zc), then S = T'X (into Ss) and T'(V'z) (into tzs) -----------------------------------------------
-  double* Xs = Zc;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int idx = t + kQrRows * h, aa = idx >> 5, cc = idx & 31;
-    double sacc = 0.0;
-    for (int p = 0; p < 32; ++p) sacc = fma(Ss[aa * kPad + p], Ts[p * kPad + cc], sacc);
-    Xs[aa * kPad + cc] = sacc;
-  }
-  __syncthreads();
-  double sv[2], uv[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int idx = t + kQrRows * h, aa = idx >> 5, cc = idx & 31;
-    double sacc = 0.0, u = 0.0;
-    for (int p = 0; p < 32; ++p) {
-      sacc = fma(Ts[p * kPad + aa], Xs[p * kPad + cc], sacc);
-      u = fma(Ts[p * kPad + aa], tzs[p * kPad + cc], u);
-    }
-    sv[h] = sacc; uv[h] = u;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int idx = t + kQrRows * h, aa = idx >> 5, cc = idx & 31;
-    Ss[aa * kPad + cc] = sv[h];
-    tzs[aa * kPad + cc] = uv[h];
-  }
-  __syncthreads();
-  // ---- W = Z0 T - 1/2 V S (rows), z <- z - V T'(V'z) --------------------------------------------------------------------
-  for (int cc = 0; cc < 32; ++cc) {
-    double w1 = 0.0, w2 = 0.0;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      w1 = fma(zr[q], Ts[q * kPad + cc], w1);
-      w2 = fma(Vs[t * kPad + q], Ss[q * kPad + cc], w2);
-    }
-    const double wv = w1 - 0.5 * w2;
-    if (inld) a.W[gi + (size_t)cc * a.ldv] = wv;
-    if (blk == 0 && t < 32) { TopW[t * kPad + cc] = wv; TopV[t * kPad + cc] = Vs[t * kPad + cc]; }
-  }
-  if (gi < a.r)
-    for (int l = 0; l < a.L; ++l) {
-      double u = 0.0;
-#pragma unroll
-      for (int q = 0; q < 32; ++q) u = fma(Vs[t * kPad + q], tzs[q * kPad + l], u);
-      a.z[(size_t)a.zrow0 + gi + (size_t)l * a.ldz] -= u;
-    }
-  cluster.sync();
-  // ---- look-ahead: C[32:, 0:32] -= V W[0:32]' + W V[0:32]' --------------------------------------------------------------
-  double* LW = Zc;                                  // [32][33] local copies of CTA 0's TopW, TopV
-  double* LV = zc;
-  {
-    const double* pw = cluster.map_shared_rank(TopW, 0);
-    const double* pv = cluster.map_shared_rank(TopV, 0);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int idx = t + kQrRows * h, aa = idx >> 5, cc = idx & 31;
-      LW[aa * kPad + cc] = pw[aa * kPad + cc];
-      LV[aa * kPad + cc] = pv[aa * kPad + cc];
-    }
-  }
-  __syncthreads();
-  if (gi >= 32 && gi < a.r) {
-#pragma unroll
-    for (int q = 0; q < 32; ++q) zr[q] = a.W[gi + (size_t)q * a.ldv];      // this thread's own row of W
-    for (int cc = 0; cc < 32; ++cc) {
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        s0 = fma(Vs[t * kPad + q], LW[cc * kPad + q], s0);
-        s1 = fma(zr[q], LV[cc * kPad + q], s1);
-      }
-      a.C[gi + (size_t)cc * a.ld] -= s0 + s1;
-    }
-  }
-  cluster.sync();                                   // CTA 0 must not leave while a peer still reads TopW / TopV
-}
-
-// ---------------------------------------------------------------------------------------------
 // C -= V W' + W V' on the 128 x 128 tiles of the lower triangle; thread = 8 x 8 outputs, the operands of the whole tile in
 // shared memory.  Rows >= 32 of the first 32 columns - the next panel - are left to k_sbr_pu, so that the QR of the next
 // panel runs beside this kernel (look-ahead).  An off-diagonal tile is written twice: in place and - transposed through shared memory, so that both
@@ -1378,8 +1208,6 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     MB_CUDA(cudaFuncSetAttribute(k_sbr_qr<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kQrSmem));
     (void)cudaFuncSetAttribute(k_sbr_qr_reg<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     MB_CUDA(cudaFuncSetAttribute(k_sbr_r2k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kR2kSmem));
-    (void)cudaFuncSetAttribute(k_sbr_fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmem);
-    (void)cudaFuncSetAttribute(k_sbr_fin, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     MB_CUDA(cudaFuncSetAttribute(k_sbr_vtz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVtzSmem));
     max_cluster = 0;
     const bool np_ok = cudaFuncSetAttribute(k_sbr_qr<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
@@ -1408,7 +1236,7 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     const int gmax = ceil_div(rmax, kQrRows);
     int npanel = 0;
     for (int j0 = 0; m - j0 - kBw >= 2; j0 += kBw) ++npanel;
-    const bool keep = ctx->coef_impl == 1;
+    const bool keep = ctx->coef_impl != 2;
     mb_band_form& bf = ctx->band_form;
     if (keep) {
       size_t tot = 0;
@@ -1484,24 +1312,11 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
       nsplit = ceil_div(r, chunk);
       if (pk > 0) MB_CUDA(cudaStreamWaitEvent(st, ctx->sbr_ev[2 + ((pk - 1) & 1)], 0));      // trailing update of panel k - 1
       MB_LAUNCH(ctx, "k_sbr_av", st) k_sbr_av<<<dim3(rblocks, nsplit), 128, 0, st>>>(A22, ld, r, V, ldv, Zp, chunk);
-      if (ctx->sbr_fuse == 1 && ceil_div(ldv, kQrRows) <= max_cluster) {
-        int cs = 1;
-        while (cs * kQrRows < ldv) cs *= 2;
-        FinArgs fa{V, ldv, r, Zp, nsplit, Tk, W, z, m, j0 + kBw, L, A22, ld};
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = kFinSmem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        MB_LAUNCH(ctx, "k_sbr_fin", st) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_fin, fa));
-      } else {
-        MB_LAUNCH(ctx, "k_sbr_vtz", st)
-          k_sbr_vtz<<<rblocks, 512, kVtzSmem, st>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
-        MB_LAUNCH(ctx, "k_sbr_st", st) k_sbr_st<<<1, 1024, 0, st>>>(Gp, rblocks, Tk, ST);
-        MB_LAUNCH(ctx, "k_sbr_w", st) k_sbr_w<<<rblocks, 128, 0, st>>>(V, ldv, r, Z0, Tk, ST, W, z, m, j0 + kBw, L);
-        if (r > 32) MB_LAUNCH(ctx, "k_sbr_pu", st) k_sbr_pu<<<ceil_div(r - 32, 128), 128, 0, st>>>(A22, ld, r, V, W, ldv);
-      }
+      MB_LAUNCH(ctx, "k_sbr_vtz", st)
+        k_sbr_vtz<<<rblocks, 512, kVtzSmem, st>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
+      MB_LAUNCH(ctx, "k_sbr_st", st) k_sbr_st<<<1, 1024, 0, st>>>(Gp, rblocks, Tk, ST);
+      MB_LAUNCH(ctx, "k_sbr_w", st) k_sbr_w<<<rblocks, 128, 0, st>>>(V, ldv, r, Z0, Tk, ST, W, z, m, j0 + kBw, L);
+      if (r > 32) MB_LAUNCH(ctx, "k_sbr_pu", st) k_sbr_pu<<<ceil_div(r - 32, 128), 128, 0, st>>>(A22, ld, r, V, W, ldv);
       MB_CUDA(cudaEventRecord(ctx->sbr_ev[pk & 1], st));
       MB_CUDA(cudaStreamWaitEvent(aux, ctx->sbr_ev[pk & 1], 0));
       MB_LAUNCH(ctx, "k_sbr_r2k", aux)
@@ -1518,7 +1333,7 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   int* prog = ar.take_n<int>((size_t)m + 2);
   MB_CUDA(cudaMemsetAsync(prog, 0, sizeof(int) * ((size_t)m + 2), st));
   MB_LAUNCH(ctx, "k_sbr_band", st) k_sbr_band<<<ceil_div(ncolb, 4), 256, 0, st>>>(A, ld, m, Bd, ncolb);
-  if (ctx->coef_impl == 1 && L > 0) {
+  if (ctx->coef_impl != 2 && L > 0) {
     // band form for the coefficient solve: B and Q1'z as they are now (the chase below overwrites both)
     mb_band_form& bf = ctx->band_form;
     bf.m = m; bf.L = L;
@@ -1535,7 +1350,7 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   }
   ChaseArgs ca{Bd, m, z, L, prog};
   const int G = std::max(1, std::min(ctx->sm_count, ceil_div(m, 2 * kBw) + 2));
-  if (ctx->sbr_chase_impl == 1) {
+  if (ctx->sbr_chase_impl != 2) {
     MB_LAUNCH(ctx, "k_sbr_chase_dec", st) k_sbr_chase_t<true><<<G, kChaseThreadsDec, 0, st>>>(ca);
   } else {
     MB_LAUNCH(ctx, "k_sbr_chase", st) k_sbr_chase_t<false><<<G, kChaseThreads, 0, st>>>(ca);

@@ -772,7 +772,7 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
       ABuf<double> d_B(ar, m), d_tmp(ar, m);
       for (int r = 0; r < L; ++r) {
         // experimental ("coef_impl" = 1): from the band form of the two-stage reduction, no dense factorisation
-        if (ctx->coef_impl == 1 && band_coefficients(ctx, lam[r], r, d_B.p, st)) {
+        if (ctx->coef_impl != 2 && band_coefficients(ctx, lam[r], r, d_B.p, st)) {
           MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
           MB_CUDA(cudaStreamSynchronize(st));
           continue;

@@ -159,18 +159,14 @@ def test_mltps_predict_tiled_mode(engine, case):
     _cmp(got, ref, 2e-6)
 
 
-@pytest.mark.parametrize("rows", [1, 2, 4])
-def test_forest_tile_shapes_agree(engine, case, rows):
-    """the tile-pruned forest kernel must give the same raster for every tile height (same comparisons,
-    only the order of the float64 sum over trees changes)."""
+@pytest.mark.parametrize("win", [(3, 150, 5, 217), (0, 8, 0, 32), (17, 18, 40, 41), (120, 160, 200, 224)])
+def test_forest_on_ragged_windows(engine, case, win):
+    """the two-level tile-pruned forest kernel on windows that cut its 32 x 8 tiles and 8 x 4 warp blocks anywhere (same
+    comparisons as the reference, only the order of the float64 sum over trees differs)."""
     geom, C, models, cov = case
     ens = engine.ensemble_create(geom, models, "rb", [0.6, 0.4], 1.0, C + 2)
-    engine.set_param("tree_rows", rows)
-    try:
-        got = engine.ensemble_eval(ens, cov, window=(3, 150, 5, 217))
-    finally:
-        engine.set_param("tree_rows", 0)
-    ref = cbind.ensemble_eval(models, "rb", [0.6, 0.4], 1.0, cov, geom.as_tuple())[3:150, 5:217]
+    got = engine.ensemble_eval(ens, cov, window=win)
+    ref = cbind.ensemble_eval(models, "rb", [0.6, 0.4], 1.0, cov, geom.as_tuple())[win[0]:win[1], win[2]:win[3]]
     _cmp(got, ref, 2e-7)
 
 
@@ -218,13 +214,11 @@ def test_tiled_mode_is_independent_of_lane_concurrency(engine, case):
     np.testing.assert_array_equal(a, out.cpu().numpy())
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
-                    reason="k_ens_svm_mma (svm_impl = 1) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
 @pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("kept", ["v", "gnmv", "bgnmrv"])
-def test_svm_tensor_core_variant(engine, case, kept, impl):
-    """ksvm dot products on the tensor pipe (3 x TF32, k_ens_svm_mma): same tolerance as the packed-FP32 kernel, same NA mask,
-    ragged window; impl 2 also evaluates half of the exponentials as a degree-5 polynomial on the FMA pipe."""
+def test_svm_kernel_variants(engine, case, kept, impl):
+    """Both ksvm kernels against the oracle: impl 1 = dot products on the tensor pipe (3 x TF32, k_ens_svm_mma; the default for
+    P <= 8), impl 2 = packed FP32 (k_ens_svm; the only one for P > 8).  Same tolerance, same NA mask, ragged window."""
     geom, C, models, cov = case
     ws = [1.0 / len(kept)] * len(kept)
     ref = cbind.ensemble_eval(models, kept, ws, 1.0, cov, geom.as_tuple())

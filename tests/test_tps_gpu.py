@@ -273,21 +273,19 @@ def test_leaf_elongated_knot_cloud(engine, strip):
         assert relerr(got, ref) < (2e-6 if mode == 0 else TOL)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
-                    reason="coef_impl = 1 (band-form coefficient solve) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
 @pytest.mark.parametrize("n", [20, 36, 37, 70, 165, 600, 1100])
 def test_coefficients_from_band_form(engine, n):
     """(M + lambda I)^-1 z from the band form of the two-stage reduction (block band Cholesky + back-transformation by the stored
-    panel reflectors, tools/proto_two_stage.py coefficients_from_band) against the dense Cholesky: same lambda (the search does
-    not depend on it), coefficients to 1e-9, three responses."""
+    panel reflectors, tools/proto_two_stage.py coefficients_from_band; the default) against the dense Cholesky (coef_impl = 2):
+    same lambda (the search does not depend on it), coefficients to 1e-9, three responses."""
     geom = synth.make_geom(512, 512)
     xy, _, _ = synth.make_knots(geom, n, 700 + n)
     y = synth.residual_field(xy, 700 + n)
     Y = np.stack([y, y[::-1].copy(), y * y], axis=1)
-    ref = engine.tps_fit(xy, Y)
+    got = engine.tps_fit(xy, Y)
     try:
-        engine.set_param("coef_impl", 1)
-        got = engine.tps_fit(xy, Y)
+        engine.set_param("coef_impl", 2)
+        ref = engine.tps_fit(xy, Y)
     finally:
         engine.set_param("coef_impl", 0)
     for g, r in zip(got, ref):
@@ -296,44 +294,19 @@ def test_coefficients_from_band_form(engine, n):
         assert np.max(np.abs(g.d - r.d)) <= 1e-9 * max(np.max(np.abs(r.d)), 1e-300)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
-                    reason="sbr_chase_impl = 1 (watcher / publisher warps) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
 @pytest.mark.parametrize("n", [36, 70, 200, 1100])
 def test_chase_with_watcher_and_publisher_warps(engine, n):
-    """same arithmetic in the same order as the default chase kernel, only the hand-shakes move to two extra warps: bit-identical"""
+    """The default chase kernel (hand-shakes on two extra warps) does the same arithmetic in the same order as the three-warp
+    kernel (sbr_chase_impl = 2): bit-identical."""
     geom = synth.make_geom(512, 512)
     xy, _, _ = synth.make_knots(geom, n, 800 + n)
     y = synth.residual_field(xy, 800 + n)
-    ref = engine.tps_fit(xy, y)
+    got = engine.tps_fit(xy, y)
     try:
-        engine.set_param("sbr_chase_impl", 1)
-        got = engine.tps_fit(xy, y)
+        engine.set_param("sbr_chase_impl", 2)
+        ref = engine.tps_fit(xy, y)
     finally:
         engine.set_param("sbr_chase_impl", 0)
     assert got.lam == ref.lam
     np.testing.assert_array_equal(got.c, ref.c)
     np.testing.assert_array_equal(got.decomposition()[0], ref.decomposition()[0])
-
-
-@pytest.mark.skipif(__import__("os").environ.get("MB_EXPERIMENTAL") != "1",
-                    reason="sbr_fuse = 1 (fused per-panel cluster kernel) has not run on a GPU yet: set MB_EXPERIMENTAL=1 to include it")
-@pytest.mark.parametrize("n", [37, 70, 165, 600, 1100])
-def test_fused_panel_kernel(engine, n):
-    """k_sbr_fin = vtz + st + w + pu in one cluster kernel: same mathematics, different (still fixed) summation order of the
-    32 x 32 Gram partials, so agreement to rounding; three responses."""
-    geom = synth.make_geom(512, 512)
-    xy, _, _ = synth.make_knots(geom, n, 600 + n)
-    y = synth.residual_field(xy, 600 + n)
-    Y = np.stack([y, y[::-1].copy(), y * y], axis=1)
-    ref = engine.tps_fit(xy, Y)
-    try:
-        engine.set_param("sbr_fuse", 1)
-        got = engine.tps_fit(xy, Y)
-        again = engine.tps_fit(xy, Y)
-    finally:
-        engine.set_param("sbr_fuse", 0)
-    for g, r, a in zip(got, ref, again):
-        assert abs(g.lam - r.lam) <= 1e-9 * r.lam
-        assert np.max(np.abs(g.c - r.c)) <= 1e-9 * np.max(np.abs(r.c))
-        np.testing.assert_allclose(g.decomposition()[0], r.decomposition()[0], rtol=0, atol=1e-13 * r.decomposition()[0].max())
-        assert a.lam == g.lam and np.array_equal(a.c, g.c)        # deterministic

@@ -59,41 +59,28 @@ for n in sizes:
             g = eng.tps_fit(xy, y)
             eng.set_param("sbr_qr_grid", 0)
             print(f"   grid-barrier QR: lambda rel diff {abs(g.lam - sp0.lam) / sp0.lam:.1e}", flush=True)
-        try:                                   # experimental: fused per-panel cluster kernel
-            eng.set_param("sytrd_mode", 3); eng.set_param("sbr_fuse", 1)
-            eng.tps_fit(xy, y)
-            eng.timing(True); eng.timing_collect()
-            t0 = time.perf_counter()
-            b = eng.tps_fit(xy, y)
-            dt = time.perf_counter() - t0
-            kt = eng.timing_collect(); eng.timing(False)
-            print(f"   sbr_fuse 1: wall {dt * 1e3:.1f} ms, lambda rel diff {abs(b.lam - sp0.lam) / sp0.lam:.1e}, c err {np.abs(b.c - sp0.c).max() / np.abs(sp0.c).max():.2e}, "
-                  f"k_sbr_fin {kt.get('k_sbr_fin', (0, 0))[0]:.2f} ms x{kt.get('k_sbr_fin', (0, 0))[1]}", flush=True)
-        except Exception:
-            traceback.print_exc()
-        finally:
-            eng.timing(False); eng.set_param("sbr_fuse", 0)
-        try:                                   # experimental: watcher / publisher warps in the bulge chase
-            eng.set_param("sytrd_mode", 3); eng.set_param("sbr_chase_impl", 1)
+        try:                                   # the three-warp chase kernel (default: + watcher / publisher warps)
+            eng.set_param("sytrd_mode", 3); eng.set_param("sbr_chase_impl", 2)
             eng.tps_fit(xy, y)
             eng.timing(True); eng.timing_collect()
             b = eng.tps_fit(xy, y)
             kt = eng.timing_collect(); eng.timing(False)
-            print(f"   sbr_chase_impl 1: lambda rel diff {abs(b.lam - sp0.lam) / sp0.lam:.1e}, c err {np.abs(b.c - sp0.c).max() / np.abs(sp0.c).max():.2e}, "
-                  f"k_sbr_chase_dec {kt.get('k_sbr_chase_dec', (0, 0))[0]:.2f} ms", flush=True)
+            print(f"   sbr_chase_impl 2 (three warps, no watcher): lambda rel diff {abs(b.lam - sp0.lam) / sp0.lam:.1e}, c err {np.abs(b.c - sp0.c).max() / np.abs(sp0.c).max():.2e}, "
+                  f"k_sbr_chase {kt.get('k_sbr_chase', (0, 0))[0]:.2f} ms", flush=True)
         except Exception:
             traceback.print_exc()
         finally:
             eng.timing(False); eng.set_param("sbr_chase_impl", 0)
-        try:                                   # experimental: coefficients from the band form instead of the dense Cholesky
-            eng.set_param("sytrd_mode", 3); eng.set_param("coef_impl", 1)
+        try:                                   # dense Cholesky instead of the band-form coefficient solve (default)
+            eng.set_param("sytrd_mode", 3); eng.set_param("coef_impl", 2)
+            eng.tps_fit(xy, y)
             eng.timing(True); eng.timing_collect()
             t0 = time.perf_counter()
             b = eng.tps_fit(xy, y)
             dt = time.perf_counter() - t0
             kt = eng.timing_collect(); eng.timing(False)
-            print(f"   coef_impl 1: wall {dt * 1e3:.1f} ms, c err {np.abs(b.c - sp0.c).max() / np.abs(sp0.c).max():.2e}, "
-                  f"k_band_solve {kt.get('k_band_solve', (0, 0))[0]:.2f} ms, k_apply_q1 {kt.get('k_apply_q1', (0, 0))[0]:.2f} ms", flush=True)
+            print(f"   coef_impl 2 (dense Cholesky): wall {dt * 1e3:.1f} ms, c err {np.abs(b.c - sp0.c).max() / np.abs(sp0.c).max():.2e}, "
+                  f"Cholesky kernels {sum(kt.get(k, (0, 0))[0] for k in ('k_potrf_diag', 'k_trsm_panel', 'k_syrk_dmma', 'k_chol_sweep')):.2f} ms", flush=True)
         except Exception:
             traceback.print_exc()
         finally:
