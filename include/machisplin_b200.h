@@ -226,6 +226,23 @@ int mb_dev_free(mb_ctx* ctx, void* p);
 int mb_h2d(mb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int mb_d2h(mb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
+/* ---- .C()-loadable twins: all-pointer arguments, void return, status[0] = MB_OK or a negative MB_E_* ---------
+ * dyn.load("libmachisplin_b200.so"); .C("mbC_tps_surface", as.double(xy), as.double(y), as.integer(n), as.double(grid6), ...).
+ * One process-wide context (device $MB_DEVICE, default 0) is created on first use; grid6 = c(xmin, xmax, ymin, ymax, nrow, ncol).
+ * Covered: the call sites whose inputs / outputs are plain numeric vectors.  The per-cell ensemble needs the model descriptors
+ * and device handles and goes through the .Call shim (r/mb_shim.c). */
+/* V73:329-333: G = R'R, R n x K column-major */
+void mbC_gram(const double* R, const int* n, const int* K, double* G, int* status);
+/* V73:722-753 (+ 649-895 when tile_px > 0): fields::Tps(xy, y) + terra::interpolate over the grid, values in terra cell order;
+ * lambda < 0 = GCV; lambda_out (length 1) gets the selected lambda of the global spline (NaN in tiled mode) */
+void mbC_tps_surface(const double* xy, const double* y, const int* n, const double* grid6, const double* lambda,
+                     const int* tile_px, double* out, double* lambda_out, int* status);
+/* V73:1392-1548: wins = 4 integers (r0, r1, c0, c1) per tile, tiles_flat = the tile rasters one after another, row-major */
+void mbC_tiles_merge(const double* grid6, const int* nC, const int* nR, const int* wins, const double* tiles_flat, double* out,
+                     int* status);
+void mbC_last_error(char** buf);     /* message of the last failure, copied into buf[0] up to its allocated length */
+void mbC_shutdown(void);
+
 /* ---- per-kernel device timing (bench bookkeeping) ---------------------------------------- */
 /* When enabled, every kernel launch of this context is bracketed by CUDA events on the launching
  * stream.  mb_timing_collect synchronises, sums the elapsed time per kernel name and resets the
@@ -241,6 +258,11 @@ int mb_debug_values(mb_ctx* ctx, const char* name, double* out, int cap);
 /* Tunables of the fast evaluator (0 = automatic). */
 int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_rows);
 /* Named integer tunables (0 = automatic):
+ * "ens_overlap" = 2 (default) the forest kernel, then the tensor-pipe ksvm kernel; 1 side by side on two streams when both are
+ * kept (measured slower); "svm_ctas_per_sm" = persistent grid of the ksvm kernel in that mode (default 2); "ens_tma" = 1 (default)
+ * covariate tiles of the ksvm kernel by TMA tensor copies (cp.async.bulk.tensor), 2 plain loads;
+ * "ens_order" = 2 (default) the ksvm kernel runs before the forest kernel, 1 after it;
+ * "tree_levels" = 1 forest kernel with the CTA-level interval prune only, 2 (default) + the warp-level prune;
  * "eval_precision" = leaf kernel code path of the fast evaluator (1 = float64 only, 2 = force mixed);
  * "sytrd_mode" = tridiagonalisation of the GCV fit: 0 / 3 = two-stage (band reduction + bulge chasing, the default),
  * 1 = one-stage persistent kernel, 2 = one-stage with one kernel per phase; "sytrd_ctas_per_sm" = grid size of the
@@ -248,7 +270,8 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * barrier instead of a thread-block cluster; "sbr_qr_impl" = 1 / 2 keeps the panel rows in shared memory / registers
  * (0 = chosen by cluster size); "sbr_debug" = 1 keeps the band matrix for mb_debug_values("sbr_band");
  * "svm_impl" (before mb_ensemble_create) = 1 ksvm dot products on the tensor pipe (3 x TF32; the default for P <= 8), 2 packed FP32;
- * "coef_impl" = 1 coefficients from the band form of the two-stage reduction (default), 2 dense Cholesky of M + lambda I;
+ * "coef_impl" = 0 coefficients from the band form of the two-stage reduction when cond(M + lambda I) <= 1e8 (default), 1 whenever
+ * that form exists, 2 always the dense Cholesky of M + lambda I;
  * "sbr_chase_impl" = 1 watcher and publisher warps in the bulge chase (default), 2 three warps per sweep;
  * "defer_ensemble" = 0 starts the per-cell ensemble kernels of mb_mltps_predict* before the fit instead of behind stage 1
  * of its tridiagonalisation; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd (validation of the in-house path only). */

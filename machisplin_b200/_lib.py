@@ -101,6 +101,11 @@ SIGNATURES = {
     "mb_spline_bcast": (C.c_int, [VP, PVP, C.c_int, C.c_int]),
     "mb_mltps_predict_shard_dev": (C.c_int, [VP, PG, VP, VP, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, VP, PVP, VP]),
     "mb_mltps_predict_shard": (C.c_int, [VP, PG, VP, PF, C.c_int, PD, PD, C.c_int, C.c_double, C.c_int, PD, PVP]),
+    "mbC_gram": (None, [PD, PI32, PI32, PD, PI32]),
+    "mbC_tps_surface": (None, [PD, PD, PI32, PD, PD, PI32, PD, PD, PI32]),
+    "mbC_tiles_merge": (None, [PD, PI32, PI32, PI32, PD, PD, PI32]),
+    "mbC_last_error": (None, [C.POINTER(C.c_char_p)]),
+    "mbC_shutdown": (None, []),
     "mb_dev_alloc": (C.c_int, [VP, C.c_size_t, PVP]),
     "mb_dev_free": (C.c_int, [VP, VP]),
     "mb_h2d": (C.c_int, [VP, VP, VP, C.c_size_t]),

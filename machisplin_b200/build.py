@@ -11,7 +11,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libmachisplin_b200.so"
-SOURCES = ["abi.cu", "tps_eval.cu", "tps_fit.cu", "sytrd.cu", "sbr.cu", "ensemble.cu", "tiles.cu", "tiff_io.cu", "comm.cu"]
+SOURCES = ["abi.cu", "tps_eval.cu", "tps_fit.cu", "sytrd.cu", "sbr.cu", "ensemble.cu", "tiles.cu", "tiff_io.cu", "comm.cu", "abi_dotc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print("\n".join(log))
     cuda_lib = str(Path(nvcc).resolve().parent.parent / "lib64")
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-L" + cuda_lib, "-lcusolver", "-lcudart", "-ldl",
+    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-L" + cuda_lib, "-lcudart", "-ldl",
            "-Xlinker", "-rpath," + cuda_lib]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

@@ -162,6 +162,8 @@ void mb_shutdown(mb_ctx* ctx) {
   if (ctx->ev_stage1) cudaEventDestroy(ctx->ev_stage1);
   for (cudaEvent_t ev : ctx->sbr_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->sbr_aux) cudaStreamDestroy(ctx->sbr_aux);
+  for (cudaEvent_t ev : ctx->ev_ens) if (ev) cudaEventDestroy(ev);
+  if (ctx->ens_aux) cudaStreamDestroy(ctx->ens_aux);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->copy) cudaStreamDestroy(ctx->copy);
   for (auto& w : ctx->lanes) {
@@ -255,7 +257,22 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
   return guarded([&] {
     MB_REQUIRE(ctx && name, "NULL argument");
     const std::string n(name);
-    if (n == "eigen_impl") {
+    if (n == "ens_overlap") {
+      MB_REQUIRE(value >= 0 && value <= 2, "ens_overlap must be 0 (default = 2), 1 (forest and ksvm kernels side by side) or 2 (one after the other)");
+      ctx->ens_overlap = value;
+    } else if (n == "ens_order") {
+      MB_REQUIRE(value >= 0 && value <= 2, "ens_order must be 0 (default = 2), 1 (forest kernel first) or 2 (ksvm kernel first)");
+      ctx->ens_order = value;
+    } else if (n == "svm_ctas_per_sm") {
+      MB_REQUIRE(value >= 0 && value <= 4, "svm_ctas_per_sm must be in [0, 4]");
+      ctx->svm_ctas_per_sm = value;
+    } else if (n == "ens_tma") {
+      MB_REQUIRE(value >= 0 && value <= 2, "ens_tma must be 0 (default = 1), 1 (TMA tensor copies) or 2 (plain loads)");
+      ctx->ens_tma = value;
+    } else if (n == "tree_levels") {
+      MB_REQUIRE(value >= 0 && value <= 2, "tree_levels must be 0 (default = 2), 1 or 2");
+      ctx->tree_levels = value;
+    } else if (n == "eigen_impl") {
       MB_REQUIRE(value == 0 || value == 1, "eigen_impl must be 0 (in-house) or 1 (cuSOLVER, validation)");
       ctx->eigen_impl = value;
     } else if (n == "sytrd_mode") {
@@ -266,7 +283,7 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 2, "sbr_chase_impl must be 0 (default = 1), 1 (watcher / publisher warps) or 2 (three warps per sweep)");
       ctx->sbr_chase_impl = value;
     } else if (n == "coef_impl") {
-      MB_REQUIRE(value >= 0 && value <= 2, "coef_impl must be 0 (default = 1), 1 (band form of the two-stage reduction) or 2 (dense Cholesky)");
+      MB_REQUIRE(value >= 0 && value <= 2, "coef_impl must be 0 (band form when well conditioned), 1 (band form whenever it exists) or 2 (dense Cholesky)");
       ctx->coef_impl = value;
     } else if (n == "svm_impl") {
       MB_REQUIRE(value >= 0 && value <= 2, "svm_impl must be 0 (default: 1 when P <= 8, else 2), 1 (3 x TF32 tensor-core dot products) or 2 (packed FP32)");

@@ -188,6 +188,13 @@ struct mb_ctx {
   int64_t launches = 0;
   // fast-evaluator tunables (0 = automatic)
   int cheb_p = 0, leaf_cols = 0, leaf_rows = 0;
+  int ens_overlap = 0;        // per-cell ensemble: 0 = 2 = forest kernel, then the tensor-pipe ksvm kernel (default); 1 = side by side on two streams (A/B)
+  int ens_order = 0;          // forests + tensor-pipe ksvm: 0 = 2 = ksvm kernel first, 1 = forest kernel first
+  int ens_tma = 0;            // k_ens_svm_tma: 0 = 1 = covariate tiles by TMA tensor copies when the raster layout allows, 2 = plain loads
+  int svm_ctas_per_sm = 0;    // persistent grid of k_ens_svm_tma beside the forest kernel (0 = 2 per SM)
+  cudaStream_t ens_aux = nullptr;   // stream of the ksvm kernel in overlap mode + fork / join events
+  cudaEvent_t ev_ens[2] = {nullptr, nullptr};
+  int tree_levels = 0;        // forest kernel: 0 = 2 = CTA-level + warp-level interval pruning, 1 = CTA-level only (A/B measurements)
   int svm_impl = 0;           // ksvm kernel: 0 = automatic (1 when P <= 8), 1 = dot products on the tensor pipe (k_ens_svm_mma, P <= 8),
                               // 2 = packed FP32 (k_ens_svm); read by mb_ensemble_create
   // 256-entry (1/m_k, -log(1/m_k)) table for the float64 table-driven log
@@ -200,8 +207,9 @@ struct mb_ctx {
   std::vector<double> dbg_band;
   cudaStream_t sbr_aux = nullptr;   // two-stage path: stream of the look-ahead trailing updates + its events
   cudaEvent_t sbr_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  int coef_impl = 0;          // coefficients at the selected lambda: 0 = default = 1 = band form of the two-stage reduction (block band
-                              // Cholesky + back-transformation by the stored panel reflectors), 2 = dense Cholesky of M + lambda I
+  int coef_impl = 0;          // coefficients at the selected lambda: 0 = band form of the two-stage reduction (block band Cholesky +
+                              // back-transformation by the stored panel reflectors) when cond(M + lambda I) <= 1e8, else dense Cholesky;
+                              // 1 = band form whenever it exists, 2 = always the dense Cholesky of M + lambda I
   mb_band_form band_form;
   int sbr_chase_impl = 0;     // bulge chase: 0 = default = 1 = three warps per sweep + watcher and publisher warps, 2 = three warps per sweep
   int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include "ens_device.cuh"
+#include "async_copy.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -215,7 +216,8 @@ __global__ void __launch_bounds__(kTreeThreads) k_ens_trees_plain(
 // ---------------------------------------------------------------------------------------------
 constexpr int kTreeChunk = 2048;     // trees pruned per pass (bounds the residual lists)
 constexpr int kTreeSeg = kTreeChunk / 8;
-constexpr int kTreeIlp = 2;
+constexpr int kTreeIlp = 4;      // subtrees a cell walks at once (independent dependent-load chains: the walk is bound by L2 latency)
+constexpr int kPruneIlp = 3;     // trees a lane prunes at once in phase 2
 constexpr int kKindShift = 30;
 
 // Two-level variant (the default): the CTA tile of 32 x 8 cells is cut into eight 8 x 4 blocks, one per warp.  After the CTA-level
@@ -231,7 +233,7 @@ template <int R>
 __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
     const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg, mb_window w,
     const int2* __restrict__ nodes, const int* __restrict__ roots, int n_rf, int n_gb, int zero_leaf,
-    double rf_scale, double gb_scale, double base, int accumulate, int64_t acc_stride, double* __restrict__ acc) {
+    double rf_scale, double gb_scale, double base, int accumulate, int64_t acc_stride, double* __restrict__ acc, int levels) {
   static_assert(R == 1, "the two-level kernel owns one cell per thread");
   extern __shared__ __align__(16) unsigned char tree_smem[];
   float* s_feat = reinterpret_cast<float*>(tree_smem);                    // [(C + 2)][256]
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
   }
   const int any_eval = __syncthreads_or(eval);
   if (!any_eval) {                                  // sea tile: nothing to evaluate
-    if (inside && !accumulate) acc[(int64_t)(row - w.r0) * wc + (col - w.c0)] = 0.0;
+    if (inside && !accumulate) acc[(int64_t)(row - w.r0) * wc + (col - w.c0)] = 0.0;   // accumulate 1 / 2: nothing to add
     return;
   }
   if (tid < C + 2) {
@@ -295,27 +297,49 @@ __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
     const int nchunk = min(kTreeChunk, ntrees - t0);
     const int per = ((nchunk + 7) / 8 + 31) & ~31;   // trees per warp, whole rounds of 32
     int cnt = 0;
-    for (int k = 0; k < per; k += 32) {
-      const int tl = warp * per + k + lane;          // tree of this lane within the chunk
-      bool fork = false;
-      int idx = 0, kind = 0;
-      if (tl < nchunk) {
-        const int tree = t0 + tl;
-        kind = tree >= n_rf;
-        idx = __ldg(&roots[tree]);
-        for (;;) {
-          const int2 nd = __ldg(&nodes[idx]);
-          if (nd.y & kMetaLeaf) { csum += (kind ? gb_scale : rf_scale) * (double)__int_as_float(nd.x); break; }
-          const int f = nd.y & 15;
-          const float thr = __int_as_float(nd.x);
-          if (s_hi[f] <= thr) idx = nd.y >> 5;
-          else if (s_lo[f] > thr) idx = (nd.y >> 5) + 1;
-          else { fork = true; break; }
+    for (int k = 0; k < per; k += 32 * kPruneIlp) {
+      // kPruneIlp trees per lane, walked side by side: every step is a dependent L2 access, the chains overlap
+      int idx[kPruneIlp], kind[kPruneIlp];
+      bool act[kPruneIlp], fork[kPruneIlp];
+      double leafv[kPruneIlp];
+#pragma unroll
+      for (int u = 0; u < kPruneIlp; ++u) {
+        const int tw = k + 32 * u + lane;            // tree of this lane within the warp's share
+        const int tl = warp * per + tw;              // ... within the chunk
+        act[u] = tw < per && tl < nchunk;
+        fork[u] = false;
+        leafv[u] = 0.0;
+        kind[u] = 0;
+        idx[u] = 0;
+        if (act[u]) { kind[u] = (t0 + tl) >= n_rf; idx[u] = __ldg(&roots[t0 + tl]); }
+      }
+      for (;;) {
+        bool any = false;
+        int2 nd[kPruneIlp];
+#pragma unroll
+        for (int u = 0; u < kPruneIlp; ++u) {
+          if (act[u]) nd[u] = __ldg(&nodes[idx[u]]);
+          any |= act[u];
+        }
+        if (!any) break;
+#pragma unroll
+        for (int u = 0; u < kPruneIlp; ++u) {
+          if (!act[u]) continue;
+          if (nd[u].y & kMetaLeaf) { leafv[u] = (kind[u] ? gb_scale : rf_scale) * (double)__int_as_float(nd[u].x); act[u] = false; continue; }
+          const int f = nd[u].y & 15;
+          const float thr = __int_as_float(nd[u].x);
+          if (s_hi[f] <= thr) idx[u] = nd[u].y >> 5;
+          else if (s_lo[f] > thr) idx[u] = (nd[u].y >> 5) + 1;
+          else { fork[u] = true; act[u] = false; }
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, fork);
-      if (fork) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = idx | (kind << kKindShift);
-      cnt += __popc(m);
+#pragma unroll
+      for (int u = 0; u < kPruneIlp; ++u) {          // fixed order: the sums and the list do not depend on who finished first
+        csum += leafv[u];
+        const unsigned m = __ballot_sync(0xffffffffu, fork[u]);
+        if (fork[u]) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = idx[u] | (kind[u] << kKindShift);
+        cnt += __popc(m);
+      }
     }
     if (lane == 0) s_cnt[warp] = cnt;
     __syncthreads();
@@ -333,7 +357,8 @@ __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
             if (i + lane < n1) {
               e = lst[i0 + i + lane];
               idx = e & ((1 << kKindShift) - 1);
-              for (;;) {
+              fork = levels < 2;                       // "tree_levels" = 1 (A/B measurements): no second prune, every entry stays
+              while (!fork) {
                 const int2 nd = __ldg(&nodes[idx]);
                 if (nd.y & kMetaLeaf) { wsum += ((e >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd.x); break; }
                 const int f = nd.y & 15;
@@ -395,7 +420,8 @@ __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
   if (inside) {
     double* dst = acc + (int64_t)(row - w.r0) * wc + (col - w.c0);
     const double v = eval ? (tile_const + wsum) + cell_sum : 0.0;
-    *dst = accumulate ? *dst + v : v;
+    if (accumulate == 2) atomicAdd(dst, v);          // beside k_ens_svm_tma on a zeroed accumulator: two commutative adds per cell
+    else *dst = accumulate ? *dst + v : v;
   }
 }
 
@@ -874,7 +900,7 @@ static SmoothParams smooth_params(const mb_ensemble* e) {
 }
 
 static void launch_trees(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, int64_t plane, const EnsGeom& eg,
-                         const mb_window& w, const int* roots, int n_rf, int n_gb, double* acc, cudaStream_t st) {
+                         const mb_window& w, const int* roots, int n_rf, int n_gb, double* acc, int accumulate, cudaStream_t st) {
   const double rf_scale = n_rf ? e->w[MB_R] / n_rf : 0.0, gb_scale = e->w[MB_B];
   const double base = (n_rf ? e->w[MB_R] * e->rf.offset : 0.0) + (n_gb ? e->w[MB_B] * e->gb_initF : 0.0);
   const int R = 1;                                          // one cell per thread (R = 2 / 4 measured slower in round 1, profiles/r1r_tree_rows.txt)
@@ -890,7 +916,7 @@ static void launch_trees(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
     }                                                                                                             \
     MB_LAUNCH(ctx, "k_ens_trees", st) k_ens_trees<RR><<<grid, kTreeThreads, smem, st>>>(                          \
         cov, C, plane, eg, w, e->forest_nodes.p, roots, n_rf, n_gb, e->forest_zero_leaf, rf_scale, gb_scale, base, \
-        0, acc_stride(w), acc);                                                                                   \
+        accumulate, acc_stride(w), acc, ctx->tree_levels == 1 ? 1 : 2);                                                    \
   } break;
   switch (R) {
     MB_TREES_CASE(1)
@@ -903,7 +929,8 @@ static SmoothParams smooth_params(const mb_ensemble* e);
 
 
 // ---------------------------------------------------------------------------------------------
-// k_ens_svm_mma (the default for P <= 8; measured 59.0 against 65.4 ms for k_ens_svm on config 3, profiles/r2a_*): the 8-feature dot products of
+// ksvm on the tensor pipe (k_ens_svm_tma below; the default for P <= 8; measured 46.1 against 52.7 ms for k_ens_svm on config 3,
+// profiles/r2d_ens_check.txt): the 8-feature dot products of
 // k_ens_svm on the tensor pipe.  ncu (r1s) shows k_ens_svm bound by the FMA pipe (67 % busy: 16 of the 20 packed FP32
 // instructions per 2 SV x 2 cells are the dot products), with MUFU.EX2 at 53 %; moving the dot products to
 // mma.sync.m16n8k8.tf32 leaves 2 FADD2 + 2 FFMA2 + 4 MUFU per 16 cells x 8 SVs per M-tile on the other pipes.
@@ -928,105 +955,215 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], flo
                  "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
-__global__ void __launch_bounds__(kSvmThreads) k_ens_svm_mma(
-    const float* __restrict__ cov, int C, int P, int64_t plane, EnsGeom eg, mb_window w,
-    const float4* __restrict__ bq, const float4* __restrict__ baq, int noct,
-    const double* __restrict__ xc, const double* __restrict__ xis, double sigma, double bias, double ys, double yc,
-    double wv, int accumulate, SmoothParams sp, int64_t acc_stride, double* __restrict__ acc) {
-  __shared__ float4 s_bq[kSvmOct * 32];
-  __shared__ float4 s_ba[kSvmOct * 4];
+// ---------------------------------------------------------------------------------------------
+// k_ens_svm_tma: k_ens_svm_mma with the covariate tile staged by TMA (the default ksvm kernel for P <= 8).
+//   * a CTA of 8 warps walks tiles of 32 x 8 cells (warp = one row of 32 cells = two 16-cell M-tiles); the tile's C covariate
+//     planes arrive by ONE 3-D tensor copy (cp.async.bulk.tensor, box 32 x 8 x C, UTMALDG.3D; cells outside the raster are
+//     filled with NaN = NA) into a two-stage shared-memory ring: the copy of the next tile is in flight while the current one is
+//     evaluated (mbarrier complete_tx).  A raster whose row stride is not a multiple of 16 bytes cannot be described by a tensor
+//     map: the same ring is then filled with plain loads.
+//   * two schedules.  PERSISTENT (mode 0; used when forests are kept too): 2 CTAs per SM - enough warps to saturate MUFU.EX2,
+//     which bounds this kernel - loop over all tiles while k_ens_trees, launched on a second stream, fills the rest of every SM
+//     with its latency-bound node walks: the two kernels saturate different resources and run side by side (each adds its sum
+//     to the zeroed accumulator with one RED.ADD.F64 per cell - two commutative adds, so the result does not depend on who
+//     comes first).  CHUNKED (mode 1; no forest): a CTA owns 8 consecutive tiles and retires, so that the small kernels of the
+//     TPS fit on the other stream keep finding free SMs.
+//   A single fused kernel (forest warps + ksvm warps per CTA, one TMA-staged tile, accumulator written once) was built and
+//   measured first (profiles/r2d_*): DRAM traffic 1.007 x the algorithmic bytes, but 97 ms against 85 for the two kernels one
+//   after the other - the forest walk is bound by L2 latency and needs every warp slot of the SM, which a fused CTA cannot give it.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileCells = 256;                            // 32 x 8
+constexpr int kSvmChunkTiles = 8;
+struct __align__(16) SvmTmaScratch {
+  float4 bq[kSvmOct * 32];
+  float4 ba[kSvmOct * 4];
+  unsigned long long bar[2];
+};
+struct SvmTmaArgs {
+  const float* cov; int C, P; int64_t plane; EnsGeom eg; mb_window w;
+  const float4* bq; const float4* baq; int noct; const double* xc; const double* xis;
+  double sigma, bias, ys, yc, wv;
+  SmoothParams sp;
+  int64_t acc_stride; double* acc;
+  int epilogue;                    // 0 store, 1 acc += (plain read-modify-write, after the forest kernel), 2 RED.ADD (beside it)
+  int use_tma, tiles_x, ntiles, chunked;
+  int cbase;                       // column of the first tile: w.c0 snapped down to a multiple of 4 (16-byte aligned tile rows)
+};
+
+__global__ void __launch_bounds__(kSvmThreads, 4) k_ens_svm_tma(const __grid_constant__ CUtensorMap tmap, SvmTmaArgs a) {
+  extern __shared__ __align__(128) unsigned char svm_smem[];
+  const int C = a.C;
+  const int stage_floats = (C * kTileCells + 31) & ~31;
+  float* stage0 = reinterpret_cast<float*>(svm_smem);
+  float* stage1 = stage0 + stage_floats;
+  SvmTmaScratch& S = *reinterpret_cast<SvmTmaScratch*>(stage1 + stage_floats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(S.bar);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int row = w.r0 + blockIdx.y * 8 + warp;
-  const int col_first = w.c0 + blockIdx.x * 32;
-  // the float64 smooth models of the cell this thread OWNS (cell `lane` of the strip)
-  const int ocol = col_first + lane;
-  const bool olive = ocol < w.c1 && row < w.r1;
-  double smooth = 0.0;
-  if ((sp.gam || sp.nn || sp.mars_T > 0) && olive) smooth = smooth_cell(cov, C, plane, eg, row, ocol, sp);
-  // A fragments of the two M-tiles
-  float ah[2][4], al[2][4], a0c[2][2];
-  int nanf[2][2];
+  const mb_window w = a.w;
+  const uint32_t tile_bytes = (uint32_t)C * kTileCells * 4u;
+  const bool tma = a.use_tma != 0 && C > 0;
+  const int first = a.chunked ? blockIdx.x * kSvmChunkTiles : blockIdx.x;
+  const int step = a.chunked ? 1 : gridDim.x;
+  const int last = a.chunked ? min(a.ntiles, first + kSvmChunkTiles) : a.ntiles;
+  if (tid == 0 && tma) {
+    ac_mbar_init(&bars[0], 1);
+    ac_mbar_init(&bars[1], 1);
+    ac_fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0 && tma && first < last) {
+    ac_mbar_expect_tx(&bars[0], tile_bytes);
+    ac_tma_load_3d(stage0, &tmap, a.cbase + (first % a.tiles_x) * 32, w.r0 + (first / a.tiles_x) * 8, 0, &bars[0]);
+  }
+  int it = 0;
+  for (int tile = first; tile < last; tile += step, ++it) {
+    float* feat = (it & 1) ? stage1 : stage0;
+    const int col0 = a.cbase + (tile % a.tiles_x) * 32, row0 = w.r0 + (tile / a.tiles_x) * 8;
+    if (tma) {
+      if (tid == 0 && tile + step < last) {               // the other stage was released by the barrier that ended the last tile
+        const int nt = tile + step;
+        ac_mbar_expect_tx(&bars[(it + 1) & 1], tile_bytes);
+        ac_tma_load_3d((it & 1) ? stage0 : stage1, &tmap, a.cbase + (nt % a.tiles_x) * 32, w.r0 + (nt / a.tiles_x) * 8, 0,
+                       &bars[(it + 1) & 1]);
+      }
+      ac_mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
+    } else {
+      for (int i = tid; i < C * kTileCells; i += kSvmThreads) {
+        const int f = i >> 8, cell = i & 255, r = row0 + (cell >> 5), c = col0 + (cell & 31);
+        feat[i] = (r < a.eg.nrow && c < a.eg.ncol) ? __ldg(&a.cov[f * a.plane + (int64_t)r * a.eg.ncol + c]) : __int_as_float(0x7fc00000);
+      }
+      __syncthreads();
+    }
+    const int row = row0 + warp;
+    const int ocol = col0 + lane;
+    const bool olive = ocol >= w.c0 && ocol < w.c1 && row < w.r1;
+    const float* frow = feat + warp * 32;
+    // the forest kernel's sum of this thread's cell, requested now and used after the support-vector loop (epilogue 1)
+    double* const dst = a.acc + (int64_t)(row - w.r0) * a.acc_stride + (ocol - w.c0);
+    double prev = 0.0;
+    if (olive && a.epilogue == 1) prev = __ldcs(dst);
+    // the float64 smooth models of the cell this thread OWNS (cell `lane` of the row)
+    double smooth = 0.0;
+    if ((a.sp.gam || a.sp.nn || a.sp.mars_T > 0) && olive) {
+      double x[16];
+      for (int f = 0; f < C; ++f) x[f] = (double)frow[f * kTileCells + lane];
+      x[C] = a.eg.xmin + (ocol + 0.5) * a.eg.rx;
+      x[C + 1] = a.eg.ymax - (row + 0.5) * a.eg.ry;
+      smooth = smooth_models(x, C + 2, a.sp);
+    }
+    float ah[2][4], al[2][4], a0c[2][2];
+    int nanf[2][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int hr = 0; hr < 2; ++hr) {
-      const int col = col_first + 16 * mt + g + 8 * hr;
-      const bool live = col < w.c1 && row < w.r1;
-      double n2 = 0.0;
-      int anynan = 0;
+      for (int hr = 0; hr < 2; ++hr) {
+        const int cl = 16 * mt + g + 8 * hr;
+        const int col = col0 + cl;
+        const bool live = col >= w.c0 && col < w.c1 && row < w.r1;
+        double n2 = 0.0;
+        int anynan = 0;
 #pragma unroll
-      for (int fh = 0; fh < 2; ++fh) {
-        const int f = t + 4 * fh;
-        double xs = 0.0;
-        if (f < P) {
-          double v;
-          if (f < C) v = live ? (double)__ldg(&cov[f * plane + (int64_t)row * eg.ncol + col]) : 0.0;
-          else if (f == C) v = eg.xmin + (col + 0.5) * eg.rx;
-          else v = eg.ymax - (row + 0.5) * eg.ry;
-          anynan |= (v != v);
-          xs = (v - xc[f]) * xis[f];
+        for (int fh = 0; fh < 2; ++fh) {
+          const int f = t + 4 * fh;
+          double xs = 0.0;
+          if (f < a.P) {
+            double v;
+            if (f < C) v = live ? (double)frow[f * kTileCells + cl] : 0.0;
+            else if (f == C) v = a.eg.xmin + (col + 0.5) * a.eg.rx;
+            else v = a.eg.ymax - (row + 0.5) * a.eg.ry;
+            anynan |= (v != v);
+            xs = (v - a.xc[f]) * a.xis[f];
+          }
+          n2 += xs * xs;
+          const float xf = (float)xs;
+          const float hi = to_tf32(xf);
+          ah[mt][hr + 2 * fh] = hi;
+          al[mt][hr + 2 * fh] = to_tf32(xf - hi);
         }
-        n2 += xs * xs;
-        const float xf = (float)xs;
-        const float hi = to_tf32(xf);
-        ah[mt][hr + 2 * fh] = hi;
-        al[mt][hr + 2 * fh] = to_tf32(xf - hi);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+        anynan |= __shfl_xor_sync(0xffffffffu, anynan, 1);
+        anynan |= __shfl_xor_sync(0xffffffffu, anynan, 2);
+        a0c[mt][hr] = (float)(-a.sigma * n2 * 1.4426950408889634);
+        nanf[mt][hr] = anynan;
       }
-      n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
-      n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
-      anynan |= __shfl_xor_sync(0xffffffffu, anynan, 1);
-      anynan |= __shfl_xor_sync(0xffffffffu, anynan, 2);
-      a0c[mt][hr] = (float)(-sigma * n2 * 1.4426950408889634);
-      nanf[mt][hr] = anynan;
-    }
-  float2 part[2][2];
+    float2 part[2][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int hr = 0; hr < 2; ++hr) part[mt][hr] = make_float2(0.f, 0.f);
-  for (int base = 0; base < noct; base += kSvmOct) {
-    const int n = min(kSvmOct, noct - base);
-    __syncthreads();
-    for (int i = tid; i < n * 32; i += kSvmThreads) s_bq[i] = __ldg(&bq[(size_t)base * 32 + i]);
-    for (int i = tid; i < n * 4; i += kSvmThreads) s_ba[i] = __ldg(&baq[(size_t)base * 4 + i]);
-    __syncthreads();
+      for (int hr = 0; hr < 2; ++hr) part[mt][hr] = make_float2(0.f, 0.f);
+    for (int base = 0; base < a.noct; base += kSvmOct) {
+      const int n = min(kSvmOct, a.noct - base);
+      __syncthreads();
+      for (int i = tid; i < n * 32; i += kSvmThreads) S.bq[i] = __ldg(&a.bq[(size_t)base * 32 + i]);
+      for (int i = tid; i < n * 4; i += kSvmThreads) S.ba[i] = __ldg(&a.baq[(size_t)base * 4 + i]);
+      __syncthreads();
 #pragma unroll 2
-    for (int o = 0; o < n; ++o) {
-      const float4 bf = s_bq[o * 32 + lane];
-      const float4 ba = s_ba[o * 4 + t];          // (b, b, alpha, alpha) of support vectors 2t, 2t+1 of the octet
+      for (int o = 0; o < n; ++o) {
+        const float4 bf = S.bq[o * 32 + lane];
+        const float4 ba = S.ba[o * 4 + t];          // (b, b, alpha, alpha) of support vectors 2t, 2t+1 of the octet
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        float d[4] = {a0c[mt][0] + ba.x, a0c[mt][0] + ba.y, a0c[mt][1] + ba.x, a0c[mt][1] + ba.y};
-        mma_tf32(d, al[mt], bf.x, bf.y);          // x_lo . sv_hi
-        mma_tf32(d, ah[mt], bf.z, bf.w);          // x_hi . sv_lo
-        mma_tf32(d, ah[mt], bf.x, bf.y);          // x_hi . sv_hi
-        part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), ex2_approx(d[1])), part[mt][0]);
-        part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), ex2_approx(d[3])), part[mt][1]);
+        for (int mt = 0; mt < 2; ++mt) {
+          float d[4] = {a0c[mt][0] + ba.x, a0c[mt][0] + ba.y, a0c[mt][1] + ba.x, a0c[mt][1] + ba.y};
+          mma_tf32(d, al[mt], bf.x, bf.y);          // x_lo . sv_hi
+          mma_tf32(d, ah[mt], bf.z, bf.w);          // x_hi . sv_lo
+          mma_tf32(d, ah[mt], bf.x, bf.y);          // x_hi . sv_hi
+          part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), ex2_approx(d[1])), part[mt][0]);
+          part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), ex2_approx(d[3])), part[mt][1]);
+        }
       }
     }
-  }
-  // per-cell totals: the four lanes of a group hold the 8 support-vector columns; then to the lane that owns the cell
-  double mine = 0.0;
-  int mynan = 0;
+    // per-cell totals: the four lanes of a group hold the 8 support-vector columns; then to the lane that owns the cell
+    double mine = 0.0;
+    int mynan = 0;
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int hr = 0; hr < 2; ++hr) {
-      double tot = (double)part[mt][hr].x + (double)part[mt][hr].y;
-      tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-      tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-      // cell 16 mt + 8 hr + g lives in lanes 4 g .. 4 g + 3; its owner is lane 16 mt + 8 hr + g
-      const double v = __shfl_sync(0xffffffffu, tot, 4 * (lane & 7));
-      const int nf = __shfl_sync(0xffffffffu, nanf[mt][hr], 4 * (lane & 7));
-      if ((lane >> 4) == mt && ((lane >> 3) & 1) == hr) { mine = v; mynan = nf; }
+      for (int hr = 0; hr < 2; ++hr) {
+        double tot = (double)part[mt][hr].x + (double)part[mt][hr].y;
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        const double v = __shfl_sync(0xffffffffu, tot, 4 * (lane & 7));
+        const int nf = __shfl_sync(0xffffffffu, nanf[mt][hr], 4 * (lane & 7));
+        if ((lane >> 4) == mt && ((lane >> 3) & 1) == hr) { mine = v; mynan = nf; }
+      }
+    if (olive) {
+      // last link of the chain: NA rule (V73: terra::predict returns NA where any layer is NA)
+      const double v = mynan ? __longlong_as_double(0x7ff8000000000000LL) : a.wv * ((mine - a.bias) * a.ys + a.yc) + smooth;
+      if (a.epilogue == 2) atomicAdd(dst, v);
+      else *dst = prev + v;
     }
-  if (olive) {
-    double* dst = acc + (int64_t)(row - w.r0) * acc_stride + (ocol - w.c0);
-    double v = __longlong_as_double(0x7ff8000000000000LL);
-    if (!mynan) v = (accumulate ? *dst : 0.0) + wv * ((mine - bias) * ys + yc) + smooth;
-    *dst = v;
+    __syncthreads();                                         // this stage and the support-vector buffers may be overwritten
   }
+}
+
+static void launch_svm_tma(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int64_t plane, const EnsGeom& eg,
+                           const mb_window& w, double* acc, int epilogue, bool chunked, cudaStream_t st) {
+  const mb_grid& g = e->g;
+  SvmTmaArgs sa{};
+  sa.cov = cov; sa.C = e->C; sa.P = e->P; sa.plane = plane; sa.eg = eg; sa.w = w;
+  sa.bq = e->svm_bq.p; sa.baq = e->svm_baq.p; sa.noct = e->svm_oct; sa.xc = e->svm_xc.p; sa.xis = e->svm_xis.p;
+  sa.sigma = e->svm_sigma; sa.bias = e->svm_bias; sa.ys = e->svm_ys; sa.yc = e->svm_yc; sa.wv = e->w[MB_V];
+  sa.sp = smooth_params(e);
+  sa.acc_stride = acc_stride(w); sa.acc = acc; sa.epilogue = epilogue;
+  sa.cbase = w.c0 & ~3;      // tile rows start on 16-byte boundaries of the raster row (probed: tools/tma_probe.cu)
+  sa.tiles_x = (w.c1 - sa.cbase + 31) / 32;
+  sa.ntiles = sa.tiles_x * ((w.r1 - w.r0 + 7) / 8);
+  sa.chunked = chunked ? 1 : 0;
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof tmap);
+  sa.use_tma = (ctx->ens_tma != 2 && make_plane_tensor_map(&tmap, cov, g.ncol, g.nrow, e->C, plane, 32, 8)) ? 1 : 0;
+  const size_t stage = ((size_t)e->C * kTileCells + 31) / 32 * 32 * sizeof(float);
+  const size_t smem = 2 * stage + sizeof(SvmTmaScratch);
+  static thread_local bool attr = false;
+  if (!attr) {
+    MB_CUDA(cudaFuncSetAttribute(k_ens_svm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  const int per_sm = ctx->svm_ctas_per_sm > 0 ? ctx->svm_ctas_per_sm : 2;
+  const int grid = chunked ? (sa.ntiles + kSvmChunkTiles - 1) / kSvmChunkTiles : std::min(sa.ntiles, per_sm * ctx->sm_count);
+  MB_LAUNCH(ctx, "k_ens_svm_tma", st) k_ens_svm_tma<<<grid, kSvmThreads, smem, st>>>(tmap, sa);
 }
 
 template <int NQ>
@@ -1065,14 +1202,41 @@ void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
       MB_CUDA(cudaGetLastError());
       return;                                // gbm alone: numbers on NA cells too, nothing else to add
     }
-    launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, st);
+    // "ens_overlap" = 1 (A/B measurements; NOT the default - measured 139 ms against 83 ms one after the other on config 3,
+    // profiles/r2e_ens_check.txt: the persistent ksvm CTAs need 4 per SM to hide the MUFU latency, which leaves the forest kernel
+    // nothing): the two kernels side by side, each adding its sum to the zeroed accumulator with RED.ADD.F64
+    const bool overlap = e->has[MB_V] && e->svm_oct > 0 && ctx->ens_overlap == 1;
+    if (overlap) {
+      if (!ctx->ens_aux) {
+        int prio_lo = 0, prio_hi = 0;
+        MB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        MB_CUDA(cudaStreamCreateWithPriority(&ctx->ens_aux, cudaStreamNonBlocking, prio_hi));
+        for (cudaEvent_t& ev : ctx->ev_ens) MB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      }
+      MB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * astride * (w.r1 - w.r0), st));
+      MB_CUDA(cudaEventRecord(ctx->ev_ens[0], st));
+      MB_CUDA(cudaStreamWaitEvent(ctx->ens_aux, ctx->ev_ens[0], 0));
+      launch_svm_tma(ctx, e, cov, plane, eg, w, acc, /*epilogue=*/2, /*chunked=*/false, ctx->ens_aux);
+      launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, 2, st);
+      MB_CUDA(cudaEventRecord(ctx->ev_ens[1], ctx->ens_aux));
+      MB_CUDA(cudaStreamWaitEvent(st, ctx->ev_ens[1], 0));
+      MB_CUDA(cudaGetLastError());
+      return;
+    }
+    // "ens_order": the ksvm kernel (MUFU-bound) first by default, the forest kernel (L2-latency-bound) second.  Inside
+    // mb_mltps_predict the first kernel runs beside the bulge chase of the fit, whose fences and polling hurt the forest walk
+    // (57 instead of 34 ms, profiles/r2g_bench_c3.json) and leave the ksvm kernel alone (50.8 against 50.0 ms).
+    if (e->has[MB_V] && e->svm_oct > 0 && ctx->ens_order != 1) {
+      launch_svm_tma(ctx, e, cov, plane, eg, w, acc, /*epilogue=*/0, /*chunked=*/true, st);
+      launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, 1, st);
+      MB_CUDA(cudaGetLastError());
+      return;
+    }
+    launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, 0, st);
     started = true;
   }
   if (e->has[MB_V] && e->svm_oct > 0) {           // the handle was created for the tensor-pipe kernel (P <= 8, svm_impl != 2)
-    dim3 grid((w.c1 - w.c0 + 31) / 32, (w.r1 - w.r0 + 7) / 8);
-    MB_LAUNCH(ctx, "k_ens_svm_mma", st) k_ens_svm_mma<<<grid, kSvmThreads, 0, st>>>(
-        cov, e->C, e->P, plane, eg, w, e->svm_bq.p, e->svm_baq.p, e->svm_oct, e->svm_xc.p, e->svm_xis.p, e->svm_sigma,
-        e->svm_bias, e->svm_ys, e->svm_yc, e->w[MB_V], started ? 1 : 0, smooth_params(e), astride, acc);
+    launch_svm_tma(ctx, e, cov, plane, eg, w, acc, started ? 1 : 0, /*chunked=*/true, st);
   } else if (e->has[MB_V]) {
     switch ((e->P + 1) / 2) {
 #define MB_SVM_CASE(n) case n: launch_svm<n>(e, cov, plane, eg, w, acc, started ? 1 : 0, st); break;

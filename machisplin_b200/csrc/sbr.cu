@@ -1189,8 +1189,7 @@ bool band_coefficients(mb_ctx* ctx, double lambda, int rhs, double* out_dev, cud
   int herr = 0;
   MB_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
   MB_CUDA(cudaStreamSynchronize(st));      // also keeps the uploaded panel tables alive until the kernels are done
-  if (herr) throw Error(MB_E_NUMERIC, "band Cholesky: B + lambda I is not positive definite");
-  return true;
+  return herr == 0;     // a non-positive pivot (B + lambda I numerically indefinite): the caller falls back to the dense Cholesky
 }
 
 // Reduces the symmetric m x m matrix at A (column-major, leading dimension ld >= m, LOWER triangle valid on entry, both

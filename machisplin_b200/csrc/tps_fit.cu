@@ -14,7 +14,8 @@
 #include "common.cuh"
 #include "internal.h"
 
-#include <cusolverDn.h>
+#include <cusolverDn.h>   // types only: the validation path binds libcusolver at run time, the library does not link it
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -26,6 +27,39 @@ namespace mb {
 // ---------------------------------------------------------------------------------------------
 // library handles kept per context
 // ---------------------------------------------------------------------------------------------
+// cuSOLVER serves ONE purpose: "eigen_impl" = 1, the validation of the in-house GCV fit against Dsyevd (tests, tools/fit_check.py).
+// It is resolved with dlopen when that parameter is first used, so the product library carries no dependency on it.
+struct CusolverApi {
+  void* handle = nullptr;
+  cusolverStatus_t (*Create)(cusolverDnHandle_t*) = nullptr;
+  cusolverStatus_t (*Destroy)(cusolverDnHandle_t) = nullptr;
+  cusolverStatus_t (*SetStream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+  cusolverStatus_t (*DsyevdBufferSize)(cusolverDnHandle_t, cusolverEigMode_t, cublasFillMode_t, int, const double*, int,
+                                       const double*, int*) = nullptr;
+  cusolverStatus_t (*Dsyevd)(cusolverDnHandle_t, cusolverEigMode_t, cublasFillMode_t, int, double*, int, double*, double*, int,
+                             int*) = nullptr;
+};
+static CusolverApi& cusolver() {
+  static CusolverApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* n : {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so"}) {
+      api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+      if (api.handle) break;
+    }
+    if (api.handle) {
+      api.Create = reinterpret_cast<decltype(api.Create)>(dlsym(api.handle, "cusolverDnCreate"));
+      api.Destroy = reinterpret_cast<decltype(api.Destroy)>(dlsym(api.handle, "cusolverDnDestroy"));
+      api.SetStream = reinterpret_cast<decltype(api.SetStream)>(dlsym(api.handle, "cusolverDnSetStream"));
+      api.DsyevdBufferSize = reinterpret_cast<decltype(api.DsyevdBufferSize)>(dlsym(api.handle, "cusolverDnDsyevd_bufferSize"));
+      api.Dsyevd = reinterpret_cast<decltype(api.Dsyevd)>(dlsym(api.handle, "cusolverDnDsyevd"));
+    }
+  }
+  if (!api.handle || !api.Create || !api.Destroy || !api.SetStream || !api.DsyevdBufferSize || !api.Dsyevd)
+    throw Error(MB_E_UNSUPPORTED, "eigen_impl = 1 (validation against cuSOLVER Dsyevd) needs libcusolver, which could not be loaded");
+  return api;
+}
 struct FitLibs {
   cusolverDnHandle_t solver = nullptr;
 };
@@ -36,15 +70,15 @@ static std::map<mb_ctx*, FitLibs>& libs_map() {
 static FitLibs& libs(mb_ctx* ctx) {
   FitLibs& l = libs_map()[ctx];
   if (!l.solver) {
-    if (cusolverDnCreate(&l.solver) != CUSOLVER_STATUS_SUCCESS) throw Error(MB_E_CUDA, "cusolverDnCreate failed");
-    cusolverDnSetStream(l.solver, ctx->stream);
+    if (cusolver().Create(&l.solver) != CUSOLVER_STATUS_SUCCESS) throw Error(MB_E_CUDA, "cusolverDnCreate failed");
+    cusolver().SetStream(l.solver, ctx->stream);
   }
   return l;
 }
 void fit_release(mb_ctx* ctx) {
   auto it = libs_map().find(ctx);
   if (it == libs_map().end()) return;
-  if (it->second.solver) cusolverDnDestroy(it->second.solver);
+  if (it->second.solver) cusolver().Destroy(it->second.solver);
   libs_map().erase(it);
 }
 
@@ -617,6 +651,7 @@ static void gemv_n(mb_ctx* ctx, const double* A, int ld, int m, int n, const dou
 void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, double lambda, mb_spline** out) {
   cudaStream_t st = ctx->stream;
   for (int r = 0; r < L; ++r) out[r] = nullptr;
+  ctx->band_form = mb_band_form();   // arena pointers of an earlier fit: only the two-stage reduction of THIS call may set it
   // ---- transformx (scale.type = "range") + Krig.replicates -------------------------------------
   double cmin[2] = {1e300, 1e300}, cmax[2] = {-1e300, -1e300};
   for (int i = 0; i < n; ++i)
@@ -770,9 +805,15 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
       }
       // ---- Krig.coef at the selected lambda: (M + lambda I) beta = z by the tensor-core Cholesky ----------
       ABuf<double> d_B(ar, m), d_tmp(ar, m);
+      double eta_max = 0.0, eta_min = 0.0;
+      if (!eta.empty()) { eta_max = *std::max_element(eta.begin(), eta.end()); eta_min = *std::min_element(eta.begin(), eta.end()); }
       for (int r = 0; r < L; ++r) {
-        // experimental ("coef_impl" = 1): from the band form of the two-stage reduction, no dense factorisation
-        if (ctx->coef_impl != 2 && band_coefficients(ctx, lam[r], r, d_B.p, st)) {
+        // From the band form of the two-stage reduction (no dense factorisation, two launches instead of ~300) when the system is
+        // well conditioned: B = Q1'MQ1 carries the rounding of stage 1 (~1e-16 |M|), so the band solve is good to
+        // cond(M + lambda I) * 1e-16 - the known spectrum gives cond exactly.  Near-interpolating fits (GCV minimum at the small
+        // end of fields' grid, cond >= 1e8) keep the dense Cholesky of M + lambda I itself, as do non-positive band pivots.
+        const double cond = (eta_max + lam[r]) / std::max(eta_min + lam[r], 1e-300);
+        if (ctx->coef_impl != 2 && (cond <= 1e8 || ctx->coef_impl == 1) && band_coefficients(ctx, lam[r], r, d_B.p, st)) {
           MB_CUDA(cudaMemcpyAsync(beta[r].data(), d_B.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
           MB_CUDA(cudaStreamSynchronize(st));
           continue;
@@ -791,13 +832,13 @@ void tps_fit(mb_ctx* ctx, const double* xy, const double* y, int n, int L, doubl
       ABuf<double> d_eta(ar, m);
       ABuf<int> d_info(ar, 1);
       int lwork = 0;
-      if (cusolverDnDsyevd_bufferSize(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p,
+      if (cusolver().DsyevdBufferSize(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p,
                                       &lwork) != CUSOLVER_STATUS_SUCCESS)
         throw Error(MB_E_CUDA, "cusolverDnDsyevd_bufferSize failed");
       ABuf<double> d_work(ar, (size_t)lwork);
       cusolverStatus_t cs = CUSOLVER_STATUS_SUCCESS;
       MB_LAUNCH(ctx, "cusolverDnDsyevd", st)
-        cs = cusolverDnDsyevd(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p, d_work.p,
+        cs = cusolver().Dsyevd(lb.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m, M, m, d_eta.p, d_work.p,
                               lwork, d_info.p);
       if (cs != CUSOLVER_STATUS_SUCCESS) throw Error(MB_E_CUDA, "cusolverDnDsyevd failed");
       int info = 0;

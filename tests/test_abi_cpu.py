@@ -13,7 +13,7 @@ HEADER = os.path.join(ROOT, "include", "machisplin_b200.h")
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(mb_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(mbC?_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_header_declares_the_hot_path_boundary():
@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     names = declared_symbols()
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
     out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
-    exported = set(re.findall(r" T (mb_[a-z0-9_]+)", out))
+    exported = set(re.findall(r" T (mbC?_[A-Za-z0-9_]+)", out))
     assert set(names) <= exported, set(names) - exported
     assert lib.mb_version() == 100
 

@@ -232,3 +232,45 @@ def test_svm_kernel_variants(engine, case, kept, impl):
         engine.set_param("svm_impl", 0)
     _cmp(got, ref, 5e-6)
     _cmp(got_w, ref[sub[0]:sub[1], sub[2]:sub[3]], 5e-6)
+
+
+@pytest.mark.parametrize("overlap,tma,per_sm", [(1, 1, 0), (1, 2, 1), (2, 1, 0), (2, 2, 0)])
+@pytest.mark.parametrize("kept", ["rv", "bgnmrv", "gnmv"])
+def test_ensemble_kernel_schedules(engine, case, kept, overlap, tma, per_sm):
+    """The forest kernel and the tensor-pipe ksvm kernel side by side on two streams (each adds its sum to the zeroed accumulator)
+    or one after the other; covariate tiles of the ksvm kernel by TMA tensor copy or by plain loads; persistent or chunked tile
+    schedule - against the oracle, on the full grid and on a window that cuts the 32 x 8 tiles."""
+    geom, C, models, cov = case
+    ws = [1.0 / len(kept)] * len(kept)
+    ref = cbind.ensemble_eval(models, kept, ws, 1.0, cov, geom.as_tuple())
+    try:
+        engine.set_param("ens_overlap", overlap)
+        engine.set_param("ens_tma", tma)
+        engine.set_param("svm_ctas_per_sm", per_sm)
+        ens = engine.ensemble_create(geom, models, kept, ws, 1.0, C + 2)
+        got = engine.ensemble_eval(ens, cov)
+        again = engine.ensemble_eval(ens, cov)
+        wins = [(3, 150, 5, 201), (159, 160, 0, 224), (64, 97, 32, 65), (7, 150, 13, 201)]
+        got_w = [engine.ensemble_eval(ens, cov, window=sub) for sub in wins]
+    finally:
+        engine.set_param("ens_overlap", 0)
+        engine.set_param("ens_tma", 0)
+        engine.set_param("svm_ctas_per_sm", 0)
+    _cmp(got, ref, 5e-6)
+    np.testing.assert_array_equal(got, again)                 # two commutative adds per cell: the race does not show
+    for sub, g in zip(wins, got_w):
+        _cmp(g, ref[sub[0]:sub[1], sub[2]:sub[3]], 5e-6)
+
+
+def test_ensemble_on_a_raster_tma_cannot_describe(engine):
+    """ncol = 203: the row stride is not a multiple of 16 bytes, so no tensor map exists and the tile ring is filled by plain
+    loads; 3 covariates (P = 5 < 8: padded ksvm fragments); NA cells; last tile column and row ragged."""
+    geom = synth.make_geom(77, 203)
+    C = 3
+    models = synth.make_models(geom, C, 500, 8, kept="bgnmrv", rf_trees=40, gbm_trees=60)
+    cov = synth.covariate_planes(geom, C)
+    kept, w, wt = synth.ensemble_weights("bgnmrv")
+    ref = cbind.ensemble_eval(models, kept, w, wt, cov, geom.as_tuple())
+    ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
+    got = engine.ensemble_eval(ens, cov)
+    _cmp(got, ref, 5e-6)

@@ -70,3 +70,52 @@ def test_mltps_predict_takes_planes_as_terra_values_lays_them_out(rs, mb):
     m = ~np.isnan(ref)
     assert np.max(np.abs(got[m] - ref[m])) < 5e-6 * np.max(np.abs(ref[m]))
     rs.finalize(ens)
+
+
+def test_dot_c_twins():
+    """The .C()-loadable entry points (all-pointer arguments, status out-parameter) called the way R's .C()
+    calls them: mbC_gram, mbC_tps_surface (global and tiled), mbC_tiles_merge, the error path."""
+    import ctypes as C
+    from machisplin_b200 import _lib
+    from oracle import tiles as otl
+    lib = _lib.load()
+    i32 = lambda v: (C.c_int32 * 1)(v)
+    st = i32(99)
+    R = np.asfortranarray(np.random.default_rng(3).standard_normal((500, 4)))
+    G = np.empty((4, 4))
+    lib.mbC_gram(R.ctypes.data_as(_lib.PD), i32(500), i32(4), G.ctypes.data_as(_lib.PD), st)
+    assert st[0] == 0
+    np.testing.assert_allclose(G, R.T @ R, rtol=1e-12)
+    geom = synth.make_geom(120, 160)
+    xy, _, _ = synth.make_knots(geom, 300, 77)
+    y = synth.residual_field(xy, 77)
+    g6 = np.array(geom.as_tuple(), dtype=np.float64)
+    xyf = np.asfortranarray(xy)
+    for tile_px in (0, 60):
+        out = np.empty((geom.nrow, geom.ncol))
+        lam_in, lam_out = (C.c_double * 1)(-1.0), (C.c_double * 1)(0.0)
+        lib.mbC_tps_surface(xyf.ctypes.data_as(_lib.PD), y.ctypes.data_as(_lib.PD), i32(300), g6.ctypes.data_as(_lib.PD), lam_in,
+                            i32(tile_px), out.ctypes.data_as(_lib.PD), lam_out, st)
+        assert st[0] == 0
+        ref = otl.tps_tiled_surface(geom.as_tuple(), xy, y, tile_px=tile_px or 10 ** 9)
+        assert np.max(np.abs(out - ref)) < 2e-6 * np.max(np.abs(ref))
+        assert np.isnan(lam_out[0]) == (tile_px > 0)
+    lib.mbC_tps_surface(xyf.ctypes.data_as(_lib.PD), y.ctypes.data_as(_lib.PD), i32(3), g6.ctypes.data_as(_lib.PD), lam_in, i32(0),
+                        out.ctypes.data_as(_lib.PD), lam_out, st)
+    assert st[0] < 0                                           # n <= 3: status, no crash
+    buf = C.create_string_buffer(b" " * 200)
+    p = (C.c_char_p * 1)(C.addressof(buf))
+    lib.mbC_last_error(p)
+    assert b"more than 3" in buf.value
+    tc = otl.tiles_create(geom.as_tuple(), np.zeros((0, 2)), out_ncol=2, out_nrow=2, feather_d=20)
+    wins = np.array([t["win"] for t in tc["tiles"]], dtype=np.int32)
+    rng = np.random.default_rng(1)
+    tiles = [rng.standard_normal((w[1] - w[0], w[3] - w[2])) for w in wins]
+    flat = np.concatenate([t.ravel() for t in tiles])
+    merged = np.empty((geom.nrow, geom.ncol))
+    lib.mbC_tiles_merge(g6.ctypes.data_as(_lib.PD), i32(2), i32(2), wins.ctypes.data_as(_lib.PI32), flat.ctypes.data_as(_lib.PD),
+                        merged.ctypes.data_as(_lib.PD), st)
+    assert st[0] == 0
+    ref = otl.tiles_merge(geom.as_tuple(), [tuple(w) for w in wins], tiles, 2, 2)
+    np.testing.assert_allclose(merged, ref, rtol=1e-13, atol=1e-13)
+    lib.mbC_shutdown()
