@@ -261,6 +261,7 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * "ens_overlap" = 2 (default) the forest kernel, then the tensor-pipe ksvm kernel; 1 side by side on two streams when both are
  * kept (measured slower); "svm_ctas_per_sm" = persistent grid of the ksvm kernel in that mode (default 2); "ens_tma" = 1 (default)
  * covariate tiles of the ksvm kernel by TMA tensor copies (cp.async.bulk.tensor), 2 plain loads;
+ * "leaf_tma" = 1 (default) the grid-evaluation kernel fetches the accumulator tile of a box with one 2-D tensor copy, 2 row by row;
  * "ens_order" = 2 (default) the ksvm kernel runs before the forest kernel, 1 after it;
  * "tree_levels" = 1 forest kernel with the CTA-level interval prune only, 2 (default) + the warp-level prune;
  * "eval_precision" = leaf kernel code path of the fast evaluator (1 = float64 only, 2 = force mixed);

@@ -260,6 +260,9 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
     if (n == "ens_overlap") {
       MB_REQUIRE(value >= 0 && value <= 2, "ens_overlap must be 0 (default = 2), 1 (forest and ksvm kernels side by side) or 2 (one after the other)");
       ctx->ens_overlap = value;
+    } else if (n == "leaf_tma") {
+      MB_REQUIRE(value >= 0 && value <= 2, "leaf_tma must be 0 (default = 1), 1 (2-D tensor copy of the accumulator tile) or 2 (row copies)");
+      ctx->leaf_tma = value;
     } else if (n == "ens_order") {
       MB_REQUIRE(value >= 0 && value <= 2, "ens_order must be 0 (default = 2), 1 (forest kernel first) or 2 (ksvm kernel first)");
       ctx->ens_order = value;

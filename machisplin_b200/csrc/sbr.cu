@@ -722,8 +722,8 @@ struct ChaseArgs {
 // (seconds; a step takes microseconds) raises the error flag instead of hanging the device.
 //
 // kDec ("sbr_chase_impl" = 1, experimental - DESIGN.md section 9 option (a)): two more warps take the global hand-shakes off
-// the step time.  A WATCHER warp polls the predecessor's progress word (ld.acquire.gpu) into shared memory, so the compute
-// warps check a shared-memory word; a PUBLISHER warp turns "step k stored" (shared memory) into fence + st.release.gpu, so the
+// the step time.  A WATCHER warp polls the predecessor's progress word (ld.relaxed.gpu) into shared memory, so the compute
+// warps check a shared-memory word; a PUBLISHER warp turns "step k stored" (shared memory) into fence + st.relaxed.gpu, so the
 // compute warps go on with step k + 1 at once.  The compute warps then synchronise on named barrier 1 (96 threads).
 constexpr int kChaseThreads = 96;
 constexpr int kChaseThreadsDec = 160;
@@ -759,8 +759,12 @@ __global__ void __launch_bounds__(kDec ? kChaseThreadsDec : kChaseThreads) k_sbr
         const int* p = a.prog + (s - 1);
         int v = 0, last = 0;
         long long spins = 0;
+        // RELAXED poll: ld.acquire.gpu is LDG.STRONG.GPU + CCTL.IVALL in SASS - an invalidation of the SM's whole L1 per poll, i.e.
+        // continuously on 80 SMs for the 45 ms of the chase, which the per-cell ensemble kernels sharing those SMs pay for
+        // (+20 ms on whichever of them runs beside the chase, profiles/r2h_*).  No acquire is needed: every load of band data
+        // below is ld.global.cg (LDG.STRONG.GPU, served by L2), issued after the flag value has travelled through shared memory.
         while (v < totp && ++spins < (1ll << 28)) {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+          asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
           if (v > last) { *(volatile int*)&sh_seen = v; last = v; }
         }
         if (v < totp) atomicExch(a.prog + m + 1, 1);
@@ -774,8 +778,10 @@ __global__ void __launch_bounds__(kDec ? kChaseThreadsDec : kChaseThreads) k_sbr
         while (pub < tot && ++spins < (1ll << 32)) {
           const int dn = *(volatile int*)&sh_done;
           if (dn > pub) {
-            __threadfence();                              // cumulative: the compute warps' stores, seen through sh_done
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.prog + s), "r"(dn) : "memory");
+            // ONE gpu-scope fence (cumulative: the compute warps' stores, seen through sh_done) + a relaxed store; st.release
+            // on top of __threadfence() was a second MEMBAR + CCTL.IVALL per step
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.prog + s), "r"(dn) : "memory");
             pub = dn;
           }
         }
@@ -795,8 +801,8 @@ __global__ void __launch_bounds__(kDec ? kChaseThreadsDec : kChaseThreads) k_sbr
         } else {
           const int* p = a.prog + (s - 1);
           int v, spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+          do {                                            // relaxed: see the watcher warp above
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
           } while (v < need && ++spins < (1 << 24));
           if (v < need) atomicExch(a.prog + m + 1, 1);
         }

@@ -12,9 +12,11 @@
 //                    directly.  Everything is float64: the coefficients c cancel by up to 1e8
 //                    (T'c = 0), so float32 pair terms are not accurate enough.
 #include "common.cuh"
+#include "async_copy.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <mutex>
 
@@ -501,6 +503,7 @@ __device__ __forceinline__ float lg2_fast(float x) {
 
 template <int P, bool kAcc>
 __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream(
+    const __grid_constant__ CUtensorMap acc_map, int acc_tma,
     Lattice lat, mb_window w, const unsigned char* __restrict__ recs, const float4* __restrict__ near_over,
     const unsigned long long* __restrict__ est_bits, double mixed_threshold, AccFuse fz, double* __restrict__ out,
     int64_t stride) {
@@ -530,17 +533,27 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
   const int dI = G % lat.nbx, dJ = G / lat.nbx;
   int pbi = blockIdx.x % lat.nbx, pbj = blockIdx.x / lat.nbx;      // producer cursor (warp 0)
   int ibox = 0;                                                     // producer: next box to issue
-  auto issue = [&]() {   // warp 0: bulk copies of this CTA's next box into stage ibox % kLeafStages
+  // Stage layout: [accumulator tile, bh rows of 256 bytes (kAcc)] [record].  The tile comes first because the destination of a
+  // tensor copy must be 128-byte aligned (stage_bytes is a multiple of 128), the record's bulk copy needs 16 bytes only.
+  const uint32_t acc_bytes = kAcc ? (uint32_t)bh * 256u : 0u;
+  auto issue = [&]() {   // warp 0: copies of this CTA's next box into stage ibox % kLeafStages
     const int s = ibox & (kLeafStages - 1);
     unsigned char* sp = leaf_smem + s * stage_bytes;
     if (lane == 0) {
-      mbar_expect_tx(&s_full[s], kRecBytes + (kAcc ? (uint32_t)bh * 256u : 0u));
-      bulk_g2s(sp, recs + (size_t)(blockIdx.x + ibox * G) * kRecBytes, kRecBytes, &s_full[s]);
+      mbar_expect_tx(&s_full[s], kRecBytes + acc_bytes);
+      bulk_g2s(sp + acc_bytes, recs + (size_t)(blockIdx.x + ibox * G) * kRecBytes, kRecBytes, &s_full[s]);
+      // the box's 32 x bh tile of the accumulator: ONE 2-D tensor copy (UTMALDG) issued by one lane.  The 32 row copies it
+      // replaces were serialised by the uniform datapath (ELECT + R2UR + UBLKCP per row: ~250 instructions of warp 0 per box,
+      // as many as a box's whole row work - every other warp waited for them at the box barrier: 51 % of all stall samples,
+      // profiles/r2h_ncu_full_leaf.md)
+      if (kAcc && acc_tma) ac_tma_load_2d(sp, &acc_map, pbi * 32, pbj * bh, &s_full[s]);
     }
     if (kAcc) {
-      __syncwarp();
-      const double* src = fz.acc + (int64_t)pbj * bh * fz.stride + pbi * 32;
-      for (int r = lane; r < bh; r += 32) bulk_g2s(sp + kRecBytes + r * 256, src + (int64_t)r * fz.stride, 256, &s_full[s]);
+      if (!acc_tma) {       // no tensor map (driver entry point missing): one 256-byte bulk copy per row
+        __syncwarp();
+        const double* src = fz.acc + (int64_t)pbj * bh * fz.stride + pbi * 32;
+        for (int r = lane; r < bh; r += 32) bulk_g2s(sp + r * 256, src + (int64_t)r * fz.stride, 256, &s_full[s]);
+      }
       pbi += dI; pbj += dJ;
       if (pbi >= lat.nbx) { pbi -= lat.nbx; ++pbj; }
     }
@@ -572,7 +585,7 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
   // part in ty serve both.  Column 0 in float64 (one thread per row pair), columns k >= 1 in float32, two columns per
   // thread (packed FMA): G[lr][k] = sum_j T_j(ty_lr) A[j][k].
   auto collapse = [&](int i) {
-    const unsigned char* rec = leaf_smem + (i & (kLeafStages - 1)) * stage_bytes;
+    const unsigned char* rec = leaf_smem + (i & (kLeafStages - 1)) * stage_bytes + acc_bytes;
     const double* a0 = reinterpret_cast<const double*>(rec + 256);
     const float2* af = reinterpret_cast<const float2*>(rec + 256 + 8 * P);     // [P][NQ]
     double* g0buf = s_G0 + (i & 1) * bh;
@@ -678,8 +691,8 @@ __global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream
     // ---- rows of box i: warp -> row pairs warp, warp + 8, ... ; lane half -> row of the pair -------------------
     {
       const unsigned char* sp = leaf_smem + (i & (kLeafStages - 1)) * stage_bytes;
-      const NearBlk* nb = reinterpret_cast<const NearBlk*>(sp);
-      const double* accT = reinterpret_cast<const double*>(sp + kRecBytes);
+      const NearBlk* nb = reinterpret_cast<const NearBlk*>(sp + acc_bytes);
+      const double* accT = reinterpret_cast<const double*>(sp);
       const int cnt = nb->cnt;
       const double* g0buf = s_G0 + (i & 1) * bh;
       const float* gfbuf = s_Gf + (i & 1) * bh * GFS;
@@ -895,12 +908,17 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
   if (thr > 0) {
     const size_t smem = (size_t)kLeafStages * leaf_stage_bytes(P, lat.bh, fuse != nullptr) +
                         2 * (size_t)lat.bh * (sizeof(double) + leaf_gfs(P) * sizeof(float));
+    CUtensorMap amap;
+    std::memset(&amap, 0, sizeof amap);
     if (fuse) {
+      // all boxes of the lattice lie inside the padded accumulator (acc_rows(w) = rows + 128, stride = columns rounded up to 32)
+      const int acc_tma = (ctx->leaf_tma != 2 &&
+                           make_f64_matrix_tensor_map(&amap, fz.acc, fz.stride, (int64_t)lat.nby * lat.bh, 32, lat.bh)) ? 1 : 0;
       const int grid = leaf_grid(ctx, k_leaf_stream<P, true>, smem, nboxes);
-      MB_LAUNCH(ctx, "k_leaf_fused", st) k_leaf_stream<P, true><<<grid, kLeafThreads, smem, st>>>(lat, w, d_recs, d_over, d_est, thr, fz, out, stride);
+      MB_LAUNCH(ctx, "k_leaf_fused", st) k_leaf_stream<P, true><<<grid, kLeafThreads, smem, st>>>(amap, acc_tma, lat, w, d_recs, d_over, d_est, thr, fz, out, stride);
     } else {
       const int grid = leaf_grid(ctx, k_leaf_stream<P, false>, smem, nboxes);
-      MB_LAUNCH(ctx, "k_leaf", st) k_leaf_stream<P, false><<<grid, kLeafThreads, smem, st>>>(lat, w, d_recs, d_over, d_est, thr, fz, out, stride);
+      MB_LAUNCH(ctx, "k_leaf", st) k_leaf_stream<P, false><<<grid, kLeafThreads, smem, st>>>(amap, 0, lat, w, d_recs, d_over, d_est, thr, fz, out, stride);
     }
     MB_CUDA(cudaGetLastError());
   }
