@@ -300,10 +300,13 @@ def lapack_threads(n: int):
 TRUE_BOUND = {
     "k_ens_svm": "mufu (ex2) / issue balanced: XU pipe 53 %, FMA pipe 67 %, issue 64 % (profiles/r1s_ncu_full_c3.md)",
     "k_ens_svm_mma": "mufu (ex2): dot products on the tensor pipe (3 x TF32)",
+    "k_ens_svm_tma": "mufu (ex2): 2 500 exponentials per cell, floor 36 ms at 16 / clk / SM; dot products on the tensor pipe (3 x TF32), "
+                     "covariate tiles by TMA tensor copies (profiles/r2j_ncu_full_svm_tma.md)",
     "k_ens_trees": "issue: 73 % issue-active, ALU pipe 51 %, LSU 30 % (profiles/r1s_ncu_full_c3.md)",
     "k_ens_fused": "issue + mufu: forest warps and support-vector warps share the SM",
     "k_sbr_chase": "latency: dependent L2 round trips between consecutive sweeps",
-    "k_leaf_fused": "hbm / issue: DRAM 51 %, issue-active 53 % (profiles/r1n_ncu_full_k_leaf_fused.md)",
+    "k_leaf_fused": "hbm (profiles/r2j_ncu_full_leaf.md; before the 2-D tensor copy of the accumulator tile it was bound by the box "
+                    "barrier: 51 % of the stall samples, profiles/r2h_ncu_full_leaf_before_tma.md)",
     "k_leaf": "hbm write / issue",
 }
 
@@ -479,9 +482,10 @@ def run_b200(args):
     # float64 ensemble accumulator and writes the final raster; the ensemble kernels read the C float32 planes
     # and write (k_ens_trees, k_ens_fused) or read-modify-write (k_ens_svm, k_ens_smooth) the accumulator
     bytes_per_cell = {"k_leaf": 8.0, "k_leaf_f64": 8.0, "k_leaf_fused": 16.0, "k_leaf_f64_fused": 16.0,
-                      "k_ens_final": 24.0, "k_ens_trees": 4.0 * C + 8.0, "k_ens_fused": 4.0 * C + 8.0,
+                      "k_ens_final": 24.0, "k_ens_trees": 4.0 * C + (16.0 if "v" in kept else 8.0), "k_ens_fused": 4.0 * C + 8.0,
                       "k_ens_svm": 4.0 * C + (16.0 if set(kept) & set("br") else 8.0),
                       "k_ens_svm_mma": 4.0 * C + (16.0 if set(kept) & set("br") else 8.0),
+                      "k_ens_svm_tma": 4.0 * C + 8.0,
                       "k_ens_smooth": 4.0 * C + (16.0 if heavy else 8.0)}
     for name, (tms, cnt) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
         per_launch = tms / max(cnt, 1)
@@ -605,7 +609,7 @@ def run_tiled(args):
     import torch
     import torch.distributed as dist
     import machisplin_b200 as mb
-    from machisplin_b200 import synth, tiles as mtiles, parallel
+    from machisplin_b200 import synth, tiles as mtiles, parallel as par
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -641,23 +645,20 @@ def run_tiled(args):
     cov = device_covariates(tg, C, dev, disc_geom=geom)
     ens = eng.ensemble_create(tg, models, kept, w, wt, C + 2)
     out_tile = torch.empty((tg.nrow, tg.ncol), dtype=torch.float64, device=dev)
-    out_full = torch.empty((geom.nrow, geom.ncol), dtype=torch.float64, device=dev) if rank == 0 else None
-    shapes = [(t.geom.nrow, t.geom.ncol) for t in ts.tiles]
     wins = [t.win for t in ts.tiles]
-    Rcv = np.random.default_rng(5).standard_normal((cfg["knots"], 6))[parallel.shard_rows(cfg["knots"], world, rank)]
+    par.comm_init(eng)                                  # the library's own communicator: Gram all-reduce + seam-strip exchange
+    own = eng.tiles_owned_window(geom, wins, nC, nR, rank)
+    out_own = torch.empty((own[1] - own[0], own[3] - own[2]), dtype=torch.float64, device=dev)   # this rank's part of the merged raster
+    Rcv = np.random.default_rng(5).standard_normal((cfg["knots"], 6))[par.shard_rows(cfg["knots"], world, rank)]
     stream = torch.cuda.current_stream().cuda_stream
     tile_px = 1500
 
     def step():
-        G = eng.gram(Rcv)
-        if world > 1:
-            g = torch.from_numpy(G).to(dev)
-            dist.all_reduce(g)
+        eng.gram_allreduce(Rcv)                                                # V73:329-333, ncclAllReduce inside the library
         eng.mltps_predict_dev(tg, ens, cov.data_ptr(), C, xy[pts], resid[pts], out_tile.data_ptr(), lam=args.lam,
-                              tile_px=tile_px, stream=stream)
-        tl = parallel.gather_tiles_device(out_tile, shapes, dst=0)
-        if rank == 0:
-            eng.tiles_merge_dev(geom, wins, [t.data_ptr() for t in tl], nC, nR, out_full.data_ptr(), stream=stream)
+                              tile_px=tile_px, stream=stream, want_spline=False)
+        # machisplin.tiles.merge across the GPUs: seam strips point to point, every rank blends the cells it owns (no gather)
+        eng.tiles_merge_shard_dev(geom, wins, {rank: out_tile.data_ptr()}, nC, nR, {rank: out_own.data_ptr()}, stream=stream)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -689,23 +690,112 @@ def run_tiled(args):
     ktimes = eng.timing_collect()
     eng.timing(False)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- parity sample of the MERGED raster against the oracle: a patch across the seam between tiles 0 and 1 (two GPUs) -------
+    parity = None
+    if world > 1 and not args.no_cpu_baseline:
+        parity = tiled_parity_patch(eng, dist, dev, rank, geom, ts, own, out_own, cov, models, kept, w, wt, xy, resid, tile_px, args.lam)
+    nan_own = torch.isnan(out_own).sum().to(torch.float64)
+    if world > 1:
+        dist.all_reduce(nan_own)
     if rank == 0:
         cells = geom.nrow * geom.ncol
         tot = sum(v[0] for v in ktimes.values()) or 1.0
         kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps, "share": v[0] / tot}
                 for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:12]}
         conf = workload_config(cfg, args, f"mltps tiling {tile_px} px inside {nC}x{nR} machisplin.tiles")
-        conf["parallelism"] = f"tiles{nC}x{nR}"
-        nan_frac = float(torch.isnan(out_full).float().mean().item())
+        conf["parallelism"] = (f"tiles{nC}x{nR}: one machisplin.tiles.create tile per GPU (own knots, own GCV fits), tile-border blend by "
+                               f"seam-strip exchange (ncclSend / ncclRecv) + local blend of the owned cells, Gram by ncclAllReduce; no gather")
+        conf["comm"] = eng.comm_backend() if world > 1 else None
+        strip_bytes = 0
+        for a in range(len(wins)):
+            for b in range(len(wins)):
+                if a % world != b % world:
+                    ob = eng.tiles_owned_window(geom, wins, nC, nR, b)
+                    rr, cc = min(wins[a][1], ob[1]) - max(wins[a][0], ob[0]), min(wins[a][3], ob[3]) - max(wins[a][2], ob[2])
+                    if rr > 0 and cc > 0:
+                        strip_bytes += rr * cc * 8
         line = {"metric": METRIC, "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
                 "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "kernels_rank0": kern,
-                "roofline": None, "cpu_baseline": None, "na_fraction": nan_frac,
-                "collectives": {"gram": "all_reduce 36 doubles", "tile_gather_bytes": int(sum(a * b for a, b in shapes[1:]) * 8)}}
+                "roofline": None, "cpu_baseline": None, "parity": parity, "na_fraction": float(nan_own.item()) / cells,
+                "collectives": {"gram": "ncclAllReduce 36 doubles", "seam_boxes": "ncclAllReduce(min) 4 ints per seam",
+                                "seam_strip_bytes_per_step": int(strip_bytes),
+                                "whole_tile_gather_bytes_avoided": int(sum((t.win[1] - t.win[0]) * (t.win[3] - t.win[2]) for t in ts.tiles[1:]) * 8)}}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
+        eng.comm_destroy()
         dist.destroy_process_group()
+
+
+def tiled_parity_patch(eng, dist, dev, rank, geom, ts, own, out_own, cov, models, kept, w, wt, xy, resid, tile_px, lam):
+    """Oracle values of the merged raster on a patch that straddles the seam between tiles 0 and 1 (east-west neighbours on two
+    GPUs): per tile, the oracle's fields::Tps fit of the internal 1500-px sub-tile that covers the patch + its C loops for the
+    surface and the ensemble (V73:649-753, 468-619), then oracle.tiles.tiles_merge on the two patch-high tiles (V73:1392-1548:
+    the cross-fade weights depend on x only and the patch spans the whole overlap).  Ranks 0 and 1 compute their tile's side;
+    rank 0 compares with the cells the two ranks own."""
+    import torch
+    from oracle import cbind, tiles as otl, tps as otps
+    A, B = ts.tiles[0], ts.tiles[1]
+    assert A.win[0] == B.win[0] and A.win[1] == B.win[1]
+    lay = otl.mltps_tile_layout(A.geom.as_tuple(), tile_px)
+    share = A.geom.nrow / lay.nRx
+    tr0 = int((lay.nRx // 2 + 0.5) * share) - 2                     # 4 rows at the centre of an internal sub-tile row (tile coordinates)
+    pr0, pr1 = A.win[0] + tr0, A.win[0] + tr0 + 4                   # ... in raster coordinates
+    pc0, pc1 = B.win[2] - 16, A.win[3] + 16                         # the whole overlap zone + 16 cells either side
+    res = None
+    if rank in (0, 1):
+        T = A if rank == 0 else B
+        tgeom = T.geom.as_tuple()
+        c0, c1 = max(pc0, T.win[2]) - T.win[2], min(pc1, T.win[3]) - T.win[2]        # patch columns inside this tile (tile coordinates)
+        r0, r1 = pr0 - T.win[0], pr1 - T.win[0]
+        layT = otl.mltps_tile_layout(tgeom, tile_px)
+        hit = [k for k, kw in enumerate(layT.keep_win) if kw[0] < r1 and kw[1] > r0 and kw[2] < c1 and kw[3] > c0]
+        ok = len(hit) == 1 and layT.keep_win[hit[0]][0] <= r0 and layT.keep_win[hit[0]][1] >= r1 and \
+            layT.keep_win[hit[0]][2] <= c0 and layT.keep_win[hit[0]][3] >= c1
+        if ok:
+            fw = layT.fit_win[hit[0]]
+            kxy = xy[T.points]
+            krow, kcol = otl.cell_of_points(tgeom, kxy)
+            inside = (krow >= fw[0]) & (krow < fw[1]) & (kcol >= fw[2]) & (kcol < fw[3])
+            fit = otps.tps_fit(kxy[inside], resid[T.points][inside], lam=lam)
+            tps = cbind.interpolate_c(fit, tgeom, r0, r1, c0, c1)
+            Cn = cov.shape[0]
+            cv = np.zeros((Cn, T.geom.nrow, T.geom.ncol), dtype=np.float32)           # only the patch rows are read
+            cv[:, r0:r1, c0:c1] = cov[:, r0:r1, c0:c1].cpu().numpy()
+            ens = cbind.ensemble_eval(models, kept, w, wt, cv, tgeom, window=(r0, r1, c0, c1))
+            res = {"win": (pr0, pr1, T.win[2] + c0, T.win[2] + c1), "val": ens + tps, "knots": int(inside.sum()), "lam": fit.lam}
+        # the cells of the patch this rank owns
+        oc0, oc1 = max(pc0, own[2]), min(pc1, own[3])
+        mine = out_own[pr0 - own[0]:pr1 - own[0], oc0 - own[2]:oc1 - own[2]].cpu().numpy()
+        res = {"oracle": res, "own_cols": (oc0, oc1), "got": mine}
+    box = [None, None]
+    if rank == 0:
+        box[0] = res
+        other = [None]
+        dist.recv_object_list(other, src=1)
+        box[1] = other[0]
+    elif rank == 1:
+        dist.send_object_list([res], dst=0)
+    if rank != 0:
+        return None
+    if box[0]["oracle"] is None or box[1]["oracle"] is None:
+        return {"skipped": "the patch touches an internal sub-tile seam of a tile"}
+    oa, ob = box[0]["oracle"], box[1]["oracle"]
+    ref = otl.tiles_merge((geom.xmin, geom.xmax, geom.ymax - pr1 * geom.ry, geom.ymax - pr0 * geom.ry, pr1 - pr0, geom.ncol),
+                          [(0, pr1 - pr0, oa["win"][2], oa["win"][3]), (0, pr1 - pr0, ob["win"][2], ob["win"][3])],
+                          [oa["val"], ob["val"]], 2, 1)[:, pc0:pc1]
+    got = np.full((pr1 - pr0, pc1 - pc0), np.nan)
+    for b in box:
+        got[:, b["own_cols"][0] - pc0:b["own_cols"][1] - pc0] = b["got"]
+    m = ~np.isnan(ref)
+    err = float(np.max(np.abs(got[m] - ref[m])))
+    return {"patch": {"rows": [int(pr0), int(pr1)], "cols": [int(pc0), int(pc1)], "overlap_cols": [int(B.win[2]), int(A.win[3])]},
+            "reference": "oracle sub-tile GCV fits + oracle C loops per tile, oracle.tiles.tiles_merge across the seam of tiles 0 | 1",
+            "max_abs_err": err, "max_rel_err": err / float(np.max(np.abs(ref[m]))), "na_mask_equal": bool(np.array_equal(np.isnan(got), np.isnan(ref))),
+            "tolerance": 1e-5, "knots_of_the_two_sub_tiles": [oa["knots"], ob["knots"]], "lambda_oracle": [oa["lam"], ob["lam"]]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -787,12 +877,30 @@ def run_batch(args):
         kern = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps, "share": v[0] / tot}
                 for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:12]}
         conf = workload_config(cfg, args, "global")
-        conf["parallelism"] = f"layers{world}"
+        conf["parallelism"] = f"layers{world}: the {L} response layers dealt round-robin to the GPUs, one shared tridiagonalisation per GPU for its layers"
+        parity = None
+        if not args.no_cpu_baseline:
+            # the raster of the LAST layer of rank 0 (still in `out`) against the oracle: own LAPACK GCV fit of that layer + C loops
+            from oracle import tps as otps
+            threads = host_threads()
+            lapack_threads(threads)
+            lay = mine[-1]
+            ofit = otps.tps_fit(xy, Y[:, lay], lam=args.lam)
+            pr = geom.nrow // 2
+            cov_rows = cov[:, pr:pr + 2].cpu().numpy()
+            ref, _ = cpu_sample(geom, ofit, models, kept, w, wt, cov_rows, pr, threads)
+            got = out[pr:pr + 2].cpu().numpy()
+            m = ~np.isnan(ref)
+            err = float(np.max(np.abs(got[m] - ref[m])))
+            parity = {"layer": int(lay), "rows": [pr, pr + 2], "reference": "oracle GCV fit (LAPACK) + oracle C loops",
+                      "max_abs_err": err, "max_rel_err": err / float(np.max(np.abs(ref[m]))),
+                      "na_mask_equal": bool(np.array_equal(np.isnan(got), np.isnan(ref))), "tolerance": 1e-5,
+                      "lambda_gpu": state["lam"][-1], "lambda_oracle": ofit.lam}
         line = {"metric": METRIC, "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": conf,
                 "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "kernels_rank0": kern,
-                "roofline": None, "cpu_baseline": None, "layers": L, "lambda_rank0": state["lam"]}
+                "roofline": None, "cpu_baseline": None, "parity": parity, "layers": L, "lambda_rank0": state["lam"]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -161,6 +161,18 @@ int mb_tiles_merge(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_windo
 int mb_tiles_merge_dev(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_window* wins,
                        const double* const* tiles_dev, double* out_dev, void* stream);
 
+/* machisplin.tiles.merge with the tiles spread over the GPUs of the context's communicator (the tile-border blend of the
+ * multi-GPU path): tile t lives on rank t % mb_comm_size(ctx).  The raster is partitioned into one OWNED window per tile (its
+ * share of the raster, cut through the middle of every overlap zone; mb_tiles_owned_window, host-only arithmetic); the ranks
+ * exchange the seam strips they need point to point (ncclSend / ncclRecv: rectangles a feather.d / 2 wide), agree on the seam
+ * boxes with one ncclAllReduce(min) of 4 integers per seam, and each blends the cells its tiles own.  No rank gathers a
+ * neighbour's tile; the merged raster stays distributed: out_dev[t] (owned-window-shaped, row-major) for the tiles of this rank.
+ * my_tiles_dev[t] / out_dev[t] are NULL for tiles of other ranks.  Without a communicator every tile is local (one process).
+ * Values are bit-identical to mb_tiles_merge_dev on the same tiles. */
+int mb_tiles_owned_window(const mb_grid* g, int nC, int nR, const mb_window* wins, int t, mb_window* own);
+int mb_tiles_merge_shard_dev(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_window* wins,
+                             const double* const* my_tiles_dev, double* const* out_dev, void* stream);
+
 /* ---- a6: RSS objective of the ensemble-weight search  (V73:329-333, 369-373) ---------- */
 /* G = R'R for R n x K column-major (K <= 8); fit(w) = w'Gw / (sum w)^2. */
 int mb_gram(mb_ctx* ctx, const double* R_host, int n, int K, double* G_host);

@@ -85,6 +85,8 @@ SIGNATURES = {
                                    C.c_int, VP, VP]),
     "mb_tiles_merge": (C.c_int, [VP, PG, C.c_int, C.c_int, PW, C.POINTER(PD), PD]),
     "mb_tiles_merge_dev": (C.c_int, [VP, PG, C.c_int, C.c_int, PW, PVP, VP, VP]),
+    "mb_tiles_owned_window": (C.c_int, [PG, C.c_int, C.c_int, PW, C.c_int, PW]),
+    "mb_tiles_merge_shard_dev": (C.c_int, [VP, PG, C.c_int, C.c_int, PW, PVP, PVP, VP]),
     "mb_gram": (C.c_int, [VP, PD, C.c_int, C.c_int, PD]),
     "mb_gram_dev": (C.c_int, [VP, VP, C.c_int, C.c_int, VP, VP]),
     "mb_gather_cells_dev": (C.c_int, [VP, VP, C.c_int64, C.c_int, C.c_int, PI32, PI32, C.c_int, PD, VP]),

@@ -589,6 +589,29 @@ int mb_tiles_merge_dev(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_w
   });
 }
 
+int mb_tiles_owned_window(const mb_grid* g, int nC, int nR, const mb_window* wins, int t, mb_window* own) {
+  return guarded([&] {
+    MB_REQUIRE(wins && own, "NULL argument");
+    check_grid(g);
+    MB_REQUIRE(nC >= 1 && nR >= 1, "need at least one tile");
+    for (int u = 0; u < nC * nR; ++u) check_window(g, &wins[u]);
+    *own = tiles_owned_window(*g, nC, nR, wins, t);
+  });
+}
+
+int mb_tiles_merge_shard_dev(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_window* wins,
+                             const double* const* my_tiles_dev, double* const* out_dev, void* stream) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && wins && my_tiles_dev && out_dev, "NULL argument");
+    check_grid(g);
+    MB_REQUIRE(nC >= 1 && nR >= 1, "need at least one tile");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    tiles_merge_shard(ctx, *g, nC, nR, wins, my_tiles_dev, out_dev, st);
+  });
+}
+
 int mb_tiles_merge(mb_ctx* ctx, const mb_grid* g, int nC, int nR, const mb_window* wins,
                    const double* const* tiles_host, double* out_host) {
   return guarded([&] {

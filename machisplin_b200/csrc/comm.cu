@@ -27,6 +27,10 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   std::string source;
 };
@@ -56,6 +60,10 @@ NcclApi& nccl() {
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
     api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   });
   if (!err.empty()) throw Error(MB_E_UNSUPPORTED, "NCCL: " + err);
@@ -99,6 +107,31 @@ void comm_allgather_f64(mb_ctx* ctx, const double* send_dev, double* recv_dev, s
   }
   ctx->launches++;
   MB_NCCL(nccl().AllGather(send_dev, recv_dev, count_per_rank, ncclDouble, comm_of(ctx), st));
+}
+
+void comm_allreduce_i32_min(mb_ctx* ctx, int* dev, int n, cudaStream_t st) {
+  if (!ctx->comm) return;
+  ctx->launches++;
+  MB_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclInt32, ncclMin, comm_of(ctx), st));
+}
+
+// Point-to-point exchange of float64 blocks (the seam strips of machisplin.tiles.merge): every message of the list is posted
+// inside ONE NCCL group, so the call cannot deadlock whatever the order; messages between the same pair of ranks are matched
+// in list order, which both sides derive from the same (source tile, destination tile) enumeration.
+void comm_exchange_f64(mb_ctx* ctx, const std::vector<CommMsg>& msgs, cudaStream_t st) {
+  if (msgs.empty()) return;
+  MB_REQUIRE(ctx->comm != nullptr, "no communicator: call mb_comm_init first");
+  MB_NCCL(nccl().GroupStart());
+  for (const CommMsg& m : msgs) {
+    ctx->launches++;
+    ncclResult_t r = m.send ? nccl().Send(m.ptr, m.count, ncclDouble, m.peer, comm_of(ctx), st)
+                            : nccl().Recv(m.ptr, m.count, ncclDouble, m.peer, comm_of(ctx), st);
+    if (r != ncclSuccess) {
+      nccl().GroupEnd();
+      throw Error(MB_E_CUDA, std::string("ncclSend / ncclRecv: ") + nccl().GetErrorString(r));
+    }
+  }
+  MB_NCCL(nccl().GroupEnd());
 }
 
 // Spline descriptor on the wire: 16 header doubles + 3 * cap payload doubles (kx | ky | c, each cap long, np <= cap used).

@@ -40,6 +40,14 @@ void ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X,
 void comm_release(mb_ctx* ctx);
 void comm_allreduce_f64(mb_ctx* ctx, double* dev, int n, int op, cudaStream_t st);
 void comm_allgather_f64(mb_ctx* ctx, const double* send_dev, double* recv_dev, size_t count_per_rank, cudaStream_t st);
+void comm_allreduce_i32_min(mb_ctx* ctx, int* dev, int n, cudaStream_t st);
+struct CommMsg {
+  int peer;          // the other rank
+  double* ptr;       // device buffer (source of a send, destination of a receive)
+  size_t count;      // doubles
+  bool send;
+};
+void comm_exchange_f64(mb_ctx* ctx, const std::vector<CommMsg>& msgs, cudaStream_t st);
 size_t spline_wire_doubles(int cap);
 void spline_pack(const mb_spline* s, int cap, double* w);
 mb_spline* spline_unpack(mb_ctx* ctx, const double* w, int cap);
@@ -52,6 +60,11 @@ void tiles_tps(mb_ctx* ctx, const mb_grid& g, const double* knots_xy, const doub
                cudaStream_t st);
 void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window* wins,
                  const double* const* tiles_dev, double* out_dev, cudaStream_t st);
+// machisplin.tiles.merge with the tiles spread over the ranks of the context's communicator (tile t on rank t % size): seam
+// strips travel point to point, every rank blends the cells it owns (tiles_owned_window) - no gather
+mb_window tiles_owned_window(const mb_grid& g, int nC, int nR, const mb_window* wins, int t);
+void tiles_merge_shard(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window* wins, const double* const* my_tiles_dev,
+                       double* const* out_dev, cudaStream_t st);
 void gram(mb_ctx* ctx, const double* R_dev, int n, int K, double* G_dev, cudaStream_t st);
 void gather_cells(mb_ctx* ctx, const double* raster_dev, int64_t row_stride, int nrow, int ncol, const int32_t* row,
                   const int32_t* col, int n, double* out_host, cudaStream_t st);

@@ -47,7 +47,7 @@ struct SeamDesc {
 
 __global__ void __launch_bounds__(256) k_seam_bbox(const TileDesc* __restrict__ tiles,
                                                    const SeamDesc* __restrict__ seams, int* __restrict__ bbox) {
-  const SeamDesc s = seams[blockIdx.y];
+  const SeamDesc s = seams[blockIdx.y];   // an empty window (r0 = r1): nothing to scan, the box keeps its initial value
   const int wc = s.c1 - s.c0, wr = s.r1 - s.r0;
   const int64_t n = (int64_t)wc * wr;
   int rmin = INT_MAX, rmax = INT_MIN, cmin = INT_MAX, cmax = INT_MIN;
@@ -71,10 +71,11 @@ __global__ void __launch_bounds__(256) k_seam_bbox(const TileDesc* __restrict__ 
 __global__ void __launch_bounds__(256) k_tile_blend(
     const TileDesc* __restrict__ tiles, int nC, int nR, const int2* __restrict__ colcand,
     const int2* __restrict__ rowcand, const int* __restrict__ vbbox, const int* __restrict__ hbbox,
-    double xmin, double ymax, double rx, double ry, int nrow, int ncol, double* __restrict__ out) {
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int row = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (col >= ncol || row >= nrow) return;
+    double xmin, double ymax, double rx, double ry, mb_window ow, double* __restrict__ out) {
+  // ow: the window of the raster this launch writes (the whole raster, or the cells a rank owns); out is ow-shaped
+  const int col = ow.c0 + blockIdx.x * 32 + (threadIdx.x & 31);
+  const int row = ow.r0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (col >= ow.c1 || row >= ow.r1) return;
   const int2 hc = colcand[col];     // tile columns h in [hc.x, hc.y]
   const int2 jc = rowcand[row];     // tile rows    j in [jc.x, jc.y]  (j counts from the south)
   double v[3][3];
@@ -136,73 +137,213 @@ __global__ void __launch_bounds__(256) k_tile_blend(
   if (scnt > 0) r = ssum / scnt;
   else if (tcnt > 0) r = tsum / tcnt;
   else r = __longlong_as_double(0x7ff8000000000000LL);
-  out[(int64_t)row * ncol + col] = r;
+  out[(int64_t)(row - ow.r0) * (ow.c1 - ow.c0) + (col - ow.c0)] = r;
 }
 
-void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window* wins,
-                 const double* const* tiles_dev, double* out_dev, cudaStream_t st) {
+// Host side of the blend: which tile columns / rows can cover a raster column / row, and the seams of the lattice
+struct MergeLattice {
+  std::vector<int2> colcand, rowcand;
+  std::vector<SeamDesc> seams;      // nR (nC - 1) vertical seams, then (nR - 1) nC horizontal ones
+  int nv = 0;
+};
+static MergeLattice merge_lattice(const mb_grid& g, int nC, int nR, const mb_window* wins) {
+  MergeLattice L;
   const int nt = nC * nR;
-  std::vector<TileDesc> td(nt);
-  for (int t = 0; t < nt; ++t) {
-    check_window(&g, &wins[t]);
-    td[t] = TileDesc{tiles_dev[t], wins[t].r0, wins[t].r1, wins[t].c0, wins[t].c1};
-  }
+  for (int t = 0; t < nt; ++t) check_window(&g, &wins[t]);
   // candidate tile columns / rows of every raster column / row (windows are monotone along the lattice)
-  std::vector<int2> colcand(g.ncol, make_int2(0, -1)), rowcand(g.nrow, make_int2(0, -1));
+  L.colcand.assign(g.ncol, make_int2(0, -1));
+  L.rowcand.assign(g.nrow, make_int2(0, -1));
   for (int h = 0; h < nC; ++h) {
     int lo = g.ncol, hi = 0;
     for (int j = 0; j < nR; ++j) { lo = std::min(lo, wins[j * nC + h].c0); hi = std::max(hi, wins[j * nC + h].c1); }
     for (int c = lo; c < hi; ++c) {
-      if (colcand[c].y < colcand[c].x) colcand[c] = make_int2(h, h);
-      else colcand[c].y = h;
+      if (L.colcand[c].y < L.colcand[c].x) L.colcand[c] = make_int2(h, h);
+      else L.colcand[c].y = h;
     }
   }
   for (int j = 0; j < nR; ++j) {
     int lo = g.nrow, hi = 0;
     for (int h = 0; h < nC; ++h) { lo = std::min(lo, wins[j * nC + h].r0); hi = std::max(hi, wins[j * nC + h].r1); }
     for (int r = lo; r < hi; ++r) {
-      if (rowcand[r].y < rowcand[r].x) rowcand[r] = make_int2(j, j);
-      else rowcand[r].y = j;
+      if (L.rowcand[r].y < L.rowcand[r].x) L.rowcand[r] = make_int2(j, j);
+      else L.rowcand[r].y = j;
     }
   }
-  for (auto& c : colcand) MB_REQUIRE(c.y - c.x <= 2, "more than three tile columns overlap on one raster column");
-  for (auto& r : rowcand) MB_REQUIRE(r.y - r.x <= 2, "more than three tile rows overlap on one raster row");
-  // seams
-  std::vector<SeamDesc> seams;
+  for (auto& c : L.colcand) MB_REQUIRE(c.y - c.x <= 2, "more than three tile columns overlap on one raster column");
+  for (auto& r : L.rowcand) MB_REQUIRE(r.y - r.x <= 2, "more than three tile rows overlap on one raster row");
   auto add_seam = [&](int a, int b, int axis) {
     SeamDesc s{a, b, axis, std::max(wins[a].r0, wins[b].r0), std::min(wins[a].r1, wins[b].r1),
                std::max(wins[a].c0, wins[b].c0), std::min(wins[a].c1, wins[b].c1)};
     if (s.r1 <= s.r0 || s.c1 <= s.c0) { s.r0 = s.r1 = s.c0 = s.c1 = 0; }
-    seams.push_back(s);
+    L.seams.push_back(s);
   };
-  const int nv = nR * (nC - 1), nh = (nR - 1) * nC;
+  L.nv = nR * (nC - 1);
   for (int j = 0; j < nR; ++j)
     for (int h = 0; h + 1 < nC; ++h) add_seam(j * nC + h, j * nC + h + 1, 0);
   for (int j = 0; j + 1 < nR; ++j)
     for (int h = 0; h < nC; ++h) add_seam(j * nC + h, (j + 1) * nC + h, 1);
+  return L;
+}
+static std::vector<int> bbox_initial(size_t nseams) {
+  std::vector<int> b(4 * std::max<size_t>(1, nseams));
+  for (size_t s = 0; s < b.size() / 4; ++s) {
+    b[4 * s + 0] = INT_MAX; b[4 * s + 1] = INT_MIN;
+    b[4 * s + 2] = INT_MAX; b[4 * s + 3] = INT_MIN;
+  }
+  return b;
+}
+
+void tiles_merge(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window* wins,
+                 const double* const* tiles_dev, double* out_dev, cudaStream_t st) {
+  const int nt = nC * nR;
+  const MergeLattice L = merge_lattice(g, nC, nR, wins);
+  std::vector<TileDesc> td(nt);
+  for (int t = 0; t < nt; ++t) td[t] = TileDesc{tiles_dev[t], wins[t].r0, wins[t].r1, wins[t].c0, wins[t].c1};
   Arena& ar = ctx->arena;
   ABuf<TileDesc> d_tiles(ar);
   ABuf<SeamDesc> d_seams(ar);
   ABuf<int2> d_col(ar), d_row(ar);
-  ABuf<int> d_bbox(ar, (size_t)4 * std::max<size_t>(1, seams.size()));
+  ABuf<int> d_bbox(ar, (size_t)4 * std::max<size_t>(1, L.seams.size()));
   d_tiles.upload(td, st);
-  d_col.upload(colcand, st);
-  d_row.upload(rowcand, st);
-  std::vector<int> bbox_init(4 * std::max<size_t>(1, seams.size()));
-  for (size_t s = 0; s < bbox_init.size() / 4; ++s) {
-    bbox_init[4 * s + 0] = INT_MAX; bbox_init[4 * s + 1] = INT_MIN;
-    bbox_init[4 * s + 2] = INT_MAX; bbox_init[4 * s + 3] = INT_MIN;
-  }
+  d_col.upload(L.colcand, st);
+  d_row.upload(L.rowcand, st);
+  const std::vector<int> bbox_init = bbox_initial(L.seams.size());
   d_bbox.upload(bbox_init, st);
-  if (!seams.empty()) {
-    d_seams.upload(seams, st);
-    MB_LAUNCH(ctx, "k_seam_bbox", st) k_seam_bbox<<<dim3(64, (unsigned)seams.size()), 256, 0, st>>>(d_tiles.p, d_seams.p, d_bbox.p);
+  if (!L.seams.empty()) {
+    d_seams.upload(L.seams, st);
+    MB_LAUNCH(ctx, "k_seam_bbox", st) k_seam_bbox<<<dim3(64, (unsigned)L.seams.size()), 256, 0, st>>>(d_tiles.p, d_seams.p, d_bbox.p);
   }
   const double rx = (g.xmax - g.xmin) / g.ncol, ry = (g.ymax - g.ymin) / g.nrow;
   dim3 grid((g.ncol + 31) / 32, (g.nrow + 7) / 8);
-  MB_LAUNCH(ctx, "k_tile_blend", st) k_tile_blend<<<grid, 256, 0, st>>>(d_tiles.p, nC, nR, d_col.p, d_row.p, d_bbox.p, d_bbox.p + 4 * (size_t)nv,
-                                     g.xmin, g.ymax, rx, ry, g.nrow, g.ncol, out_dev);
-  (void)nh;
+  MB_LAUNCH(ctx, "k_tile_blend", st) k_tile_blend<<<grid, 256, 0, st>>>(d_tiles.p, nC, nR, d_col.p, d_row.p, d_bbox.p, d_bbox.p + 4 * (size_t)L.nv,
+                                     g.xmin, g.ymax, rx, ry, mb_window{0, g.nrow, 0, g.ncol}, out_dev);
+  MB_CUDA(cudaGetLastError());
+  MB_CUDA(cudaStreamSynchronize(st));   // descriptor uploads come from host vectors that die here
+}
+
+// ---------------------------------------------------------------------------------------------
+// machisplin.tiles.merge across GPUs (the tile-border blend of the multi-GPU path).
+// Tile t of the nC x nR lattice lives on rank t % size.  The raster is PARTITIONED into one owned window per tile - the
+// tile's share, cut through the middle of every overlap zone - and every rank blends the cells its tiles own, so the merged
+// raster stays distributed and no rank ever sees a whole neighbour tile:
+//   1. for each pair (source tile a, destination tile b) on different ranks with W_a intersecting own_b, rank(a) packs that
+//      rectangle (cudaMemcpy2DAsync) and sends it to rank(b) - ncclSend / ncclRecv inside one group; with the reference's
+//      feather.d = 50 these are strips 25 cells wide (a few MB per seam, against GBs for the tiles themselves);
+//   2. every rank scans the seams inside its owned windows for the cells where both neighbours are non-NA; the bounding boxes
+//      of the seam strips (V73:772-779) are the min / max over all ranks: ONE ncclAllReduce(min) of 4 integers per seam;
+//   3. k_tile_blend runs on the owned windows with the received strips standing in for the neighbour tiles.
+// Every cell sees the same tile values and the same boxes as in tiles_merge, so the result is bit-identical to it.
+// ---------------------------------------------------------------------------------------------
+mb_window tiles_owned_window(const mb_grid& g, int nC, int nR, const mb_window* wins, int t) {
+  MB_REQUIRE(nC >= 1 && nR >= 1 && t >= 0 && t < nC * nR, "tile index out of range");
+  const int h = t % nC, j = t / nC;
+  for (int jj = 0; jj < nR; ++jj)
+    MB_REQUIRE(wins[jj * nC + h].c0 == wins[t].c0 && wins[jj * nC + h].c1 == wins[t].c1,
+               "sharded merge needs a regular tile lattice: the tiles of one column share their column range");
+  for (int hh = 0; hh < nC; ++hh)
+    MB_REQUIRE(wins[j * nC + hh].r0 == wins[t].r0 && wins[j * nC + hh].r1 == wins[t].r1,
+               "sharded merge needs a regular tile lattice: the tiles of one row share their row range");
+  mb_window o;
+  o.c0 = h == 0 ? 0 : (wins[t - 1].c1 + wins[t].c0) / 2;
+  o.c1 = h == nC - 1 ? g.ncol : (wins[t].c1 + wins[t + 1].c0) / 2;
+  o.r1 = j == 0 ? g.nrow : (wins[t - nC].r0 + wins[t].r1) / 2;          // tile rows count from the south
+  o.r0 = j == nR - 1 ? 0 : (wins[t].r0 + wins[t + nC].r1) / 2;
+  MB_REQUIRE(o.c0 < o.c1 && o.r0 < o.r1, "a tile owns no cell: the windows do not form a lattice");
+  return o;
+}
+
+static mb_window intersect(const mb_window& a, const mb_window& b) {
+  mb_window w{std::max(a.r0, b.r0), std::min(a.r1, b.r1), std::max(a.c0, b.c0), std::min(a.c1, b.c1)};
+  if (w.r1 <= w.r0 || w.c1 <= w.c0) w = mb_window{0, 0, 0, 0};
+  return w;
+}
+static bool empty(const mb_window& w) { return w.r1 <= w.r0 || w.c1 <= w.c0; }
+
+__global__ void k_bbox_flip(int* bbox, int n4) {   // (min, max, min, max) <-> (min, -max, min, -max) so that ONE min-reduction serves both
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4 || (i & 1) == 0) return;
+  const int v = bbox[i];
+  bbox[i] = v == INT_MIN ? INT_MAX : (v == INT_MAX ? INT_MIN : -v);
+}
+
+void tiles_merge_shard(mb_ctx* ctx, const mb_grid& g, int nC, int nR, const mb_window* wins, const double* const* my_tiles_dev,
+                       double* const* out_dev, cudaStream_t st) {
+  const int nt = nC * nR;
+  const int size = ctx->comm ? ctx->comm_size : 1, me = ctx->comm ? ctx->comm_rank : 0;
+  const MergeLattice L = merge_lattice(g, nC, nR, wins);
+  std::vector<mb_window> own(nt);
+  for (int t = 0; t < nt; ++t) own[t] = tiles_owned_window(g, nC, nR, wins, t);
+  auto rank_of = [&](int t) { return t % size; };
+  for (int t = 0; t < nt; ++t)
+    if (rank_of(t) == me) MB_REQUIRE(my_tiles_dev[t] && out_dev[t], "a tile of this rank (t % size == rank) has no raster or no output buffer");
+  Arena& ar = ctx->arena;
+  // ---- 1. strips: (source tile a -> owned window of tile b), same enumeration on every rank --------------------------
+  std::vector<std::vector<TileDesc>> view(nt);          // view[b][a]: what the blend of own_b reads for tile a (my tiles b only)
+  std::vector<CommMsg> msgs;
+  for (int b = 0; b < nt; ++b)
+    if (rank_of(b) == me) view[b].assign(nt, TileDesc{nullptr, 0, 0, 0, 0});
+  for (int a = 0; a < nt; ++a)
+    for (int b = 0; b < nt; ++b) {
+      const mb_window I = intersect(wins[a], own[b]);
+      if (empty(I)) continue;
+      const bool mine_a = rank_of(a) == me, mine_b = rank_of(b) == me;
+      if (mine_a && mine_b) {                            // both here: the tile itself serves
+        view[b][a] = TileDesc{my_tiles_dev[a], wins[a].r0, wins[a].r1, wins[a].c0, wins[a].c1};
+        continue;
+      }
+      if (!mine_a && !mine_b) continue;
+      const size_t cnt = (size_t)(I.r1 - I.r0) * (I.c1 - I.c0);
+      double* buf = ar.take_n<double>(cnt);
+      if (mine_a) {
+        const int wa = wins[a].c1 - wins[a].c0;
+        MB_CUDA(cudaMemcpy2DAsync(buf, sizeof(double) * (I.c1 - I.c0),
+                                  my_tiles_dev[a] + (size_t)(I.r0 - wins[a].r0) * wa + (I.c0 - wins[a].c0), sizeof(double) * wa,
+                                  sizeof(double) * (I.c1 - I.c0), (size_t)(I.r1 - I.r0), cudaMemcpyDeviceToDevice, st));
+        msgs.push_back(CommMsg{rank_of(b), buf, cnt, true});
+      } else {
+        view[b][a] = TileDesc{buf, I.r0, I.r1, I.c0, I.c1};
+        msgs.push_back(CommMsg{rank_of(a), buf, cnt, false});
+      }
+    }
+  comm_exchange_f64(ctx, msgs, st);
+  // ---- 2. seam boxes: partial over the owned windows, then min / max over the ranks ------------------------------------
+  ABuf<int2> d_col(ar), d_row(ar);
+  d_col.upload(L.colcand, st);
+  d_row.upload(L.rowcand, st);
+  const size_t ns = L.seams.size();
+  ABuf<int> d_bbox(ar, (size_t)4 * std::max<size_t>(1, ns));
+  const std::vector<int> bbox_init = bbox_initial(ns);
+  d_bbox.upload(bbox_init, st);
+  std::vector<std::vector<SeamDesc>> clipped(nt);       // kept alive until the stream has consumed the uploads
+  std::vector<TileDesc*> d_views(nt, nullptr);
+  for (int b = 0; b < nt; ++b) {
+    if (rank_of(b) != me) continue;
+    d_views[b] = ar.upload(view[b].data(), view[b].size(), st);
+    if (ns == 0) continue;
+    clipped[b] = L.seams;
+    for (SeamDesc& s : clipped[b]) {
+      const mb_window I = intersect(mb_window{s.r0, s.r1, s.c0, s.c1}, own[b]);
+      // both tiles of a seam that reaches into own_b have a strip here (their windows contain the seam window)
+      s.r0 = I.r0; s.r1 = I.r1; s.c0 = I.c0; s.c1 = I.c1;
+    }
+    SeamDesc* d_seams = ar.upload(clipped[b].data(), clipped[b].size(), st);
+    MB_LAUNCH(ctx, "k_seam_bbox", st) k_seam_bbox<<<dim3(64, (unsigned)ns), 256, 0, st>>>(d_views[b], d_seams, d_bbox.p);
+  }
+  if (ns > 0 && ctx->comm) {
+    const int n4 = (int)(4 * ns);
+    k_bbox_flip<<<(n4 + 255) / 256, 256, 0, st>>>(d_bbox.p, n4);
+    comm_allreduce_i32_min(ctx, d_bbox.p, n4, st);
+    k_bbox_flip<<<(n4 + 255) / 256, 256, 0, st>>>(d_bbox.p, n4);
+  }
+  // ---- 3. blend the owned windows ------------------------------------------------------------------------------------------
+  const double rx = (g.xmax - g.xmin) / g.ncol, ry = (g.ymax - g.ymin) / g.nrow;
+  for (int b = 0; b < nt; ++b) {
+    if (rank_of(b) != me) continue;
+    const mb_window o = own[b];
+    dim3 grid((o.c1 - o.c0 + 31) / 32, (o.r1 - o.r0 + 7) / 8);
+    MB_LAUNCH(ctx, "k_tile_blend", st) k_tile_blend<<<grid, 256, 0, st>>>(d_views[b], nC, nR, d_col.p, d_row.p, d_bbox.p, d_bbox.p + 4 * (size_t)L.nv,
+                                       g.xmin, g.ymax, rx, ry, o, out_dev[b]);
+  }
   MB_CUDA(cudaGetLastError());
   MB_CUDA(cudaStreamSynchronize(st));   // descriptor uploads come from host vectors that die here
 }

@@ -192,6 +192,17 @@ def pack_models(models: dict, P: int):
     return m, keep
 
 
+def tiles_owned_window(lib, geom, wins, ncol: int, nrow: int, t: int) -> tuple:
+    """``mb_tiles_owned_window``: needs the library but neither a context nor a GPU."""
+    geom = as_geom(geom)
+    nt = ncol * nrow
+    wa = (Window * nt)(*[Window(*map(int, w)) for w in wins])
+    own = Window()
+    g = geom.c()
+    check(lib.mb_tiles_owned_window(C.byref(g), ncol, nrow, wa, int(t), C.byref(own)))
+    return (own.r0, own.r1, own.c0, own.c1)
+
+
 class Engine:
     """One context = one GPU (one process per GPU in multi-GPU runs)."""
 
@@ -383,6 +394,23 @@ class Engine:
         pa = (C.c_void_p * nt)(*[C.c_void_p(int(p)) for p in tile_ptrs])
         g = geom.c()
         check(self.lib.mb_tiles_merge_dev(self._h, C.byref(g), ncol, nrow, wa, pa, C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def tiles_owned_window(self, geom, wins, ncol: int, nrow: int, t: int) -> tuple:
+        """(r0, r1, c0, c1) of the cells tile ``t`` owns in the sharded merge (host arithmetic only)."""
+        return tiles_owned_window(self.lib, geom, wins, ncol, nrow, t)
+
+    def tiles_merge_shard_dev(self, geom, wins, my_tile_ptrs: dict, ncol: int, nrow: int, out_ptrs: dict, stream: int = 0):
+        """``machisplin.tiles.merge`` with the tiles spread over the ranks of this engine's communicator (tile t on rank
+        t % world): ``my_tile_ptrs`` / ``out_ptrs`` map the tile indices of THIS rank to device pointers of the tile raster
+        (window-shaped) and of the owned-window-shaped output.  Seam strips travel over NCCL inside the library."""
+        geom = as_geom(geom)
+        nt = ncol * nrow
+        assert len(wins) == nt
+        wa = (Window * nt)(*[Window(*map(int, w)) for w in wins])
+        pa = (C.c_void_p * nt)(*[C.c_void_p(int(my_tile_ptrs[t])) if t in my_tile_ptrs else None for t in range(nt)])
+        po = (C.c_void_p * nt)(*[C.c_void_p(int(out_ptrs[t])) if t in out_ptrs else None for t in range(nt)])
+        g = geom.c()
+        check(self.lib.mb_tiles_merge_shard_dev(self._h, C.byref(g), ncol, nrow, wa, pa, po, C.c_void_p(stream)))
 
     # -- a6 / a7 --------------------------------------------------------------------------------------------
     def gram(self, R) -> np.ndarray:

@@ -117,3 +117,58 @@ def test_two_ranks_share_one_raster(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2, r.stdout
+
+
+WORKER_MERGE = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["MB_ROOT"])
+import torch, torch.distributed as dist
+import machisplin_b200 as mb
+from machisplin_b200 import parallel as par, synth
+sys.path.insert(0, os.path.join(os.environ["MB_ROOT"], "tests"))
+from test_tiles_gpu import _merge_case
+rank, world, local = par.env_rank()
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+eng = mb.Engine(local)
+par.comm_init(eng)
+geom = synth.make_geom(240, 310)
+for nc, nr in [(2, 1), (2, 2), (3, 2), (4, 2)]:
+    wins, rasters = _merge_case(geom, nc, nr)
+    nt = nc * nr
+    mine = [t for t in range(nt) if t % world == rank]
+    tiles = {t: torch.from_numpy(rasters[t]).to(dev) for t in mine}
+    own = {t: eng.tiles_owned_window(geom, wins, nc, nr, t) for t in mine}
+    outs = {t: torch.full((o[1] - o[0], o[3] - o[2]), -1.0, dtype=torch.float64, device=dev) for t, o in own.items()}
+    eng.tiles_merge_shard_dev(geom, wins, {t: v.data_ptr() for t, v in tiles.items()}, nc, nr, {t: v.data_ptr() for t, v in outs.items()})
+    torch.cuda.synchronize()
+    full = mb.Engine(local)                                   # no communicator: the gathered merge of ALL tiles on this GPU
+    ref = full.tiles_merge(geom, wins, rasters, nc, nr)
+    full.close()
+    for t, o in own.items():
+        got = outs[t].cpu().numpy()
+        assert np.array_equal(got, ref[o[0]:o[1], o[2]:o[3]], equal_nan=True), (nc, nr, t)
+dist.barrier()
+eng.comm_destroy()
+dist.destroy_process_group()
+sys.stdout.write(f"rank{rank}ok\n"); sys.stdout.flush()
+'''
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs (NCCL refuses two ranks on one device): run under gpurun --gpus 2")
+def test_two_ranks_blend_tile_borders_without_a_gather(tmp_path):
+    """machisplin.tiles.merge with the tiles on two ranks (tile t on rank t % 2): seam strips by ncclSend / ncclRecv, seam boxes by
+    ncclAllReduce(min), every rank blends the cells its tiles own - bit-identical to the gathered merge."""
+    script = tmp_path / "worker_merge.py"
+    script.write_text(WORKER_MERGE)
+    env = dict(os.environ, MB_ROOT=ROOT)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2, r.stdout

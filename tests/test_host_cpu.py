@@ -150,3 +150,28 @@ def test_two_rank_gloo_gram_allreduce_and_tile_gather(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2, r.stdout
+
+
+@pytest.mark.parametrize("shape,nc,nr,fd", [((240, 310), 2, 2, 30), ((240, 310), 4, 2, 50), ((1000, 700), 3, 3, 50), ((64, 900), 8, 1, 10),
+                                            ((500, 500), 1, 1, 50)])
+def test_owned_windows_partition_the_raster(shape, nc, nr, fd):
+    """mb_tiles_owned_window (host arithmetic of the sharded tiles.merge): the windows the tiles own are disjoint, cover every
+    cell, lie inside their tile's window, and are cut through the middle of the overlap zones of machisplin.tiles.create."""
+    from machisplin_b200 import _lib, engine as eng_mod, synth, tiles as mtiles
+    lib = _lib.load()
+    geom = synth.make_geom(*shape)
+    ts = mtiles.tiles_create(geom, np.zeros((0, 2)), nc, nr, feather_d=fd)
+    wins = [t.win for t in ts.tiles]
+    cover = np.zeros(shape, dtype=int)
+    for t, w in enumerate(wins):
+        o = eng_mod.tiles_owned_window(lib, geom, wins, nc, nr, t)
+        assert w[0] <= o[0] < o[1] <= w[1] and w[2] <= o[2] < o[3] <= w[3]
+        cover[o[0]:o[1], o[2]:o[3]] += 1
+        h, j = t % nc, t // nc
+        if h + 1 < nc:                                   # the boundary halves the overlap with the eastern neighbour
+            assert o[3] == (w[3] + wins[t + 1][2]) // 2
+        if j + 1 < nr:                                   # tile rows count from the south: the northern neighbour is t + nc
+            assert o[0] == (w[0] + wins[t + nc][1]) // 2
+    assert np.all(cover == 1)
+    with pytest.raises(_lib.MbError):
+        eng_mod.tiles_owned_window(lib, geom, wins, nc, nr, nc * nr)

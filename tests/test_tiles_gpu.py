@@ -92,3 +92,46 @@ def test_tiled_surface_with_heterogeneous_tiles(engine):
     for _ in range(3):                                     # the lanes race differently every time
         got = engine.tiles_tps(geom, xy, y, tile_px=150, lam=2e-3)
         assert relerr(got, ref) < 2e-6
+
+
+def _merge_case(geom, nc, nr, feather_d=30, seed=0):
+    rng = np.random.default_rng(seed + nc * 10 + nr)
+    tc = otl.tiles_create(geom.as_tuple(), np.zeros((0, 2)), out_ncol=nc, out_nrow=nr, feather_d=feather_d)
+    yy, xx = np.mgrid[0:geom.nrow, 0:geom.ncol]
+    base = np.sin(xx / 40.0) + np.cos(yy / 55.0)
+    hole = (xx - 150) ** 2 + (yy - 120) ** 2 < 30 ** 2
+    wins, rasters = [], []
+    for k, t in enumerate(tc["tiles"]):
+        w = t["win"]
+        r = (base + 0.1 * k + 0.01 * rng.standard_normal(base.shape))[w[0]:w[1], w[2]:w[3]].copy()
+        r[hole[w[0]:w[1], w[2]:w[3]]] = np.nan
+        if k == 0:
+            r[:5, :] = np.nan                    # ragged NA edge inside an overlap: moves a seam box
+        wins.append(tuple(int(v) for v in w))
+        rasters.append(r)
+    return wins, rasters
+
+
+@pytest.mark.parametrize("nc,nr", [(2, 2), (3, 2), (2, 1), (1, 3), (1, 1), (4, 2)])
+def test_sharded_merge_equals_the_gathered_merge(engine, nc, nr):
+    """mb_tiles_merge_shard_dev without a communicator (every tile local): the owned windows partition the raster and each holds
+    exactly the cells mb_tiles_merge computes (bit-identical), which itself matches the oracle (V73:1392-1548)."""
+    import torch
+    geom = synth.make_geom(240, 310)
+    wins, rasters = _merge_case(geom, nc, nr)
+    ref = engine.tiles_merge(geom, wins, rasters, nc, nr)
+    dev = torch.device("cuda", 0)
+    tiles = {t: torch.from_numpy(r).to(dev) for t, r in enumerate(rasters)}
+    own = {t: engine.tiles_owned_window(geom, wins, nc, nr, t) for t in range(nc * nr)}
+    outs = {t: torch.full((o[1] - o[0], o[3] - o[2]), -1.0, dtype=torch.float64, device=dev) for t, o in own.items()}
+    engine.tiles_merge_shard_dev(geom, wins, {t: v.data_ptr() for t, v in tiles.items()}, nc, nr,
+                                 {t: v.data_ptr() for t, v in outs.items()})
+    torch.cuda.synchronize()
+    got = np.full((geom.nrow, geom.ncol), -2.0)
+    cover = np.zeros((geom.nrow, geom.ncol), dtype=int)
+    for t, o in own.items():
+        got[o[0]:o[1], o[2]:o[3]] = outs[t].cpu().numpy()
+        cover[o[0]:o[1], o[2]:o[3]] += 1
+    assert np.all(cover == 1)
+    np.testing.assert_array_equal(got, ref)
+    assert relerr(got, otl.tiles_merge(geom.as_tuple(), wins, rasters, nc, nr)) < 1e-13
