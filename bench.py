@@ -71,22 +71,26 @@ def workload(args):
     return cfg
 
 
-def build_inputs(cfg, rank):
-    """Host-side synthetic inputs of one rank's tile."""
+def build_inputs(cfg, rank, model_cfg=None):
+    """Host-side synthetic inputs of one rank's tile.  model_cfg: the config whose geometry the synthetic model
+    descriptors are fitted on (weak scaling keeps the descriptors of the base config - the number of support vectors of the
+    scikit-learn SVR they are exported from depends on the training table - so that the work per cell is the same at every N)."""
     from machisplin_b200 import synth
-    geom = synth.make_geom(cfg["nrow"], cfg["ncol"])
+    geom = synth.make_geom(cfg["nrow"], cfg["ncol"], cfg.get("cell", 0.0))
+    mcfg = model_cfg or cfg
+    mgeom = synth.make_geom(mcfg["nrow"], mcfg["ncol"])
     seed = cfg["seed"] + 101 * rank
     xy, krow, kcol = synth.make_knots(geom, cfg["knots"], seed)
     resid = synth.residual_field(xy, seed)
     kept = cfg["kept"]
     models, w, wt = {}, np.zeros(0), 1.0
     if kept:
-        cache = f"/tmp/mb_models_{cfg['nrow']}x{cfg['ncol']}_{cfg['knots']}_{cfg['C']}_{kept}_{seed}.npz"
+        cache = f"/tmp/mb_models_{mcfg['nrow']}x{mcfg['ncol']}_{cfg['knots']}_{cfg['C']}_{kept}_{seed}.npz"
         if os.path.exists(cache):
             z = np.load(cache, allow_pickle=True)
             models = z["models"].item()
         else:
-            models = synth.make_models(geom, cfg["C"], cfg["knots"], seed, kept=kept)
+            models = synth.make_models(mgeom, cfg["C"], cfg["knots"], seed, kept=kept)
             try:
                 np.savez(cache, models=np.array(models, dtype=object))
             except Exception:
@@ -333,9 +337,13 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = workload(args)
     weak = args.scaling == "weak"
+    base_cfg = dict(cfg)
     if world > 1 and weak:
-        cfg["nrow"] = cfg["nrow"] * world          # one shared raster, N times as tall; the knots spread over all of it
-    geom, xy, krow, kcol, resid, models, kept, w, wt = build_inputs(cfg, 0)
+        # one shared raster, N times as tall, SAME cell size (every block looks like the base raster: the covariates are functions of
+        # the coordinates, so a smaller cell would make them smoother and the forest pruning cheaper); the knots spread over all of it
+        cfg["cell"] = 1.0 / max(cfg["nrow"], cfg["ncol"])
+        cfg["nrow"] = cfg["nrow"] * world
+    geom, xy, krow, kcol, resid, models, kept, w, wt = build_inputs(cfg, 0, model_cfg=base_cfg)
     r0, r1 = par.row_blocks(geom.nrow, world)[rank]
     bgeom = par.block_geom(geom, r0, r1)
     eng = mb.Engine(local)
@@ -482,10 +490,10 @@ def run_b200(args):
     # float64 ensemble accumulator and writes the final raster; the ensemble kernels read the C float32 planes
     # and write (k_ens_trees, k_ens_fused) or read-modify-write (k_ens_svm, k_ens_smooth) the accumulator
     bytes_per_cell = {"k_leaf": 8.0, "k_leaf_f64": 8.0, "k_leaf_fused": 16.0, "k_leaf_f64_fused": 16.0,
-                      "k_ens_final": 24.0, "k_ens_trees": 4.0 * C + (16.0 if "v" in kept else 8.0), "k_ens_fused": 4.0 * C + 8.0,
+                      "k_ens_final": 24.0, "k_ens_trees": 4.0 * C + 8.0, "k_ens_fused": 4.0 * C + 8.0,
                       "k_ens_svm": 4.0 * C + (16.0 if set(kept) & set("br") else 8.0),
                       "k_ens_svm_mma": 4.0 * C + (16.0 if set(kept) & set("br") else 8.0),
-                      "k_ens_svm_tma": 4.0 * C + 8.0,
+                      "k_ens_svm_tma": 4.0 * C + (16.0 if set(kept) & set("br") else 8.0),
                       "k_ens_smooth": 4.0 * C + (16.0 if heavy else 8.0)}
     for name, (tms, cnt) in sorted(ktimes.items(), key=lambda kv: -kv[1][0]):
         per_launch = tms / max(cnt, 1)

@@ -274,7 +274,7 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * kept (measured slower); "svm_ctas_per_sm" = persistent grid of the ksvm kernel in that mode (default 2); "ens_tma" = 1 (default)
  * covariate tiles of the ksvm kernel by TMA tensor copies (cp.async.bulk.tensor), 2 plain loads;
  * "leaf_tma" = 1 (default) the grid-evaluation kernel fetches the accumulator tile of a box with one 2-D tensor copy, 2 row by row;
- * "ens_order" = 2 (default) the ksvm kernel runs before the forest kernel, 1 after it;
+ * "ens_order" = 1 (default) the forest kernel runs before the ksvm kernel, 2 after it;
  * "tree_levels" = 1 forest kernel with the CTA-level interval prune only, 2 (default) + the warp-level prune;
  * "eval_precision" = leaf kernel code path of the fast evaluator (1 = float64 only, 2 = force mixed);
  * "sytrd_mode" = tridiagonalisation of the GCV fit: 0 / 3 = two-stage (band reduction + bulge chasing, the default),
@@ -285,7 +285,9 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * "svm_impl" (before mb_ensemble_create) = 1 ksvm dot products on the tensor pipe (3 x TF32; the default for P <= 8), 2 packed FP32;
  * "coef_impl" = 0 coefficients from the band form of the two-stage reduction when cond(M + lambda I) <= 1e8 (default), 1 whenever
  * that form exists, 2 always the dense Cholesky of M + lambda I;
- * "sbr_chase_impl" = 1 watcher and publisher warps in the bulge chase (default), 2 three warps per sweep;
+ * "sbr_chase_impl" = 1 watcher and publisher warps in the bulge chase, 2 three warps per sweep, 0 (default) = 1 for a fit that has
+ * the GPU to itself and 2 inside mb_mltps_predict* with an ensemble (smaller register footprint beside the per-cell kernels);
+ * "sbr_chase_sleep" = nanoseconds of back-off in the spin loops of the chase (0 = none; measured: no effect);
  * "defer_ensemble" = 0 starts the per-cell ensemble kernels of mb_mltps_predict* before the fit instead of behind stage 1
  * of its tridiagonalisation; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd (validation of the in-house path only). */
 int mb_set_param(mb_ctx* ctx, const char* name, int value);

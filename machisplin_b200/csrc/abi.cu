@@ -264,7 +264,7 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 2, "leaf_tma must be 0 (default = 1), 1 (2-D tensor copy of the accumulator tile) or 2 (row copies)");
       ctx->leaf_tma = value;
     } else if (n == "ens_order") {
-      MB_REQUIRE(value >= 0 && value <= 2, "ens_order must be 0 (default = 2), 1 (forest kernel first) or 2 (ksvm kernel first)");
+      MB_REQUIRE(value >= 0 && value <= 2, "ens_order must be 0 (default = 1), 1 (forest kernel first) or 2 (ksvm kernel first)");
       ctx->ens_order = value;
     } else if (n == "svm_ctas_per_sm") {
       MB_REQUIRE(value >= 0 && value <= 4, "svm_ctas_per_sm must be in [0, 4]");
@@ -282,8 +282,11 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 3,
                  "sytrd_mode must be 0 (default = two-stage), 1 (one-stage persistent kernel), 2 (one-stage, kernel per phase) or 3 (two-stage)");
       ctx->sytrd_mode = value;
+    } else if (n == "sbr_chase_sleep") {
+      MB_REQUIRE(value >= -1 && value <= 100000, "sbr_chase_sleep must be in [-1, 100000] nanoseconds");
+      ctx->sbr_chase_sleep = value;
     } else if (n == "sbr_chase_impl") {
-      MB_REQUIRE(value >= 0 && value <= 2, "sbr_chase_impl must be 0 (default = 1), 1 (watcher / publisher warps) or 2 (three warps per sweep)");
+      MB_REQUIRE(value >= 0 && value <= 2, "sbr_chase_impl must be 0 (automatic), 1 (watcher / publisher warps) or 2 (three warps per sweep)");
       ctx->sbr_chase_impl = value;
     } else if (n == "coef_impl") {
       MB_REQUIRE(value >= 0 && value <= 2, "coef_impl must be 0 (band form when well conditioned), 1 (band form whenever it exists) or 2 (dense Cholesky)");
@@ -772,13 +775,16 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
       mb_spline* raw = nullptr;
       if (fit_here) {
         if (defer) ctx->after_stage1 = [&] { launch_ensemble(true); };
+        ctx->fit_shares_gpu = heavy;     // the bulge chase picks its small-footprint variant (sbr.cu)
         try {
           tps_fit(ctx, knots_xy, resid, n, 1, lambda, &raw);
         } catch (...) {
           ctx->after_stage1 = nullptr;
+          ctx->fit_shares_gpu = false;
           throw;
         }
         ctx->after_stage1 = nullptr;
+        ctx->fit_shares_gpu = false;
         sp.reset(raw);
         launch_ensemble(false);        // not reached through the hook (e.g. a fit small enough to skip stage 1 entirely)
         if (sharded) spline_bcast(ctx, sp.get(), n, bcast_root);

@@ -190,7 +190,7 @@ struct mb_ctx {
   int cheb_p = 0, leaf_cols = 0, leaf_rows = 0;
   int ens_overlap = 0;        // per-cell ensemble: 0 = 2 = forest kernel, then the tensor-pipe ksvm kernel (default); 1 = side by side on two streams (A/B)
   int leaf_tma = 0;           // grid-evaluation kernel: 0 = 1 = accumulator tile by one 2-D tensor copy, 2 = one bulk copy per row
-  int ens_order = 0;          // forests + tensor-pipe ksvm: 0 = 2 = ksvm kernel first, 1 = forest kernel first
+  int ens_order = 0;          // forests + tensor-pipe ksvm: 0 = 1 = forest kernel first, 2 = ksvm kernel first
   int ens_tma = 0;            // k_ens_svm_tma: 0 = 1 = covariate tiles by TMA tensor copies when the raster layout allows, 2 = plain loads
   int svm_ctas_per_sm = 0;    // persistent grid of k_ens_svm_tma beside the forest kernel (0 = 2 per SM)
   cudaStream_t ens_aux = nullptr;   // stream of the ksvm kernel in overlap mode + fork / join events
@@ -212,7 +212,12 @@ struct mb_ctx {
                               // back-transformation by the stored panel reflectors) when cond(M + lambda I) <= 1e8, else dense Cholesky;
                               // 1 = band form whenever it exists, 2 = always the dense Cholesky of M + lambda I
   mb_band_form band_form;
-  int sbr_chase_impl = 0;     // bulge chase: 0 = default = 1 = three warps per sweep + watcher and publisher warps, 2 = three warps per sweep
+  int sbr_chase_sleep = 0;    // nanoseconds the spinning lanes of the bulge chase sleep between polls (-1 = none)
+  int sbr_chase_impl = 0;     // bulge chase: 1 = three warps per sweep + watcher and publisher warps (faster alone: 41 against 44 ms at
+                              // 5 000 knots), 2 = three warps per sweep (160 x 192 registers -> 96 x 160: a CTA of it costs the per-cell
+                              // kernel sharing its SM one CTA of four instead of two), 0 = 1 for a fit that has the GPU to itself, 2 when
+                              // the ensemble kernels run beside it
+  bool fit_shares_gpu = false;  // set by mb_mltps_predict* around its fit
   int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers
   int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits
   int sytrd_ctas_per_sm = 0;  // persistent grid size (0 = 2 per SM)

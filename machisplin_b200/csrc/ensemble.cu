@@ -1223,10 +1223,10 @@ void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
       MB_CUDA(cudaGetLastError());
       return;
     }
-    // "ens_order": the ksvm kernel (MUFU-bound) first by default, the forest kernel (L2-latency-bound) second.  Inside
-    // mb_mltps_predict the first kernel runs beside the bulge chase of the fit, whose fences and polling hurt the forest walk
-    // (57 instead of 34 ms, profiles/r2g_bench_c3.json) and leave the ksvm kernel alone (50.8 against 50.0 ms).
-    if (e->has[MB_V] && e->svm_oct > 0 && ctx->ens_order != 1) {
+    // "ens_order" = 2: the ksvm kernel first, the forest kernel second (default: the other way round).  Inside mb_mltps_predict the
+    // first kernel runs beside the bulge chase of the fit, whose CTAs take registers from it on 80 SMs (sbr.cu); measured on config 3
+    // with the small-footprint chase: forests first 140.2 ms / step, ksvm first 142.4 (profiles/r2n_*).
+    if (e->has[MB_V] && e->svm_oct > 0 && ctx->ens_order == 2) {
       launch_svm_tma(ctx, e, cov, plane, eg, w, acc, /*epilogue=*/0, /*chunked=*/true, st);
       launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, 1, st);
       MB_CUDA(cudaGetLastError());

@@ -713,7 +713,12 @@ struct ChaseArgs {
   double* Bd; int m;
   double* z; int L;                // m x L, ld = m
   int* prog;                       // [m] steps finished per sweep;  prog[m] = ticket counter, prog[m + 1] = error flag
+  unsigned sleep_ns;               // back-off of the spinning lanes (watcher, publisher, thread 0): the chase shares its SMs with the
+                                   // per-cell ensemble kernels, and three hot spin loops per CTA cost those kernels issue slots
 };
+__device__ __forceinline__ void chase_backoff(unsigned ns) {
+  if (ns) __nanosleep(ns);
+}
 
 // One CTA (three warps) per sweep.  Per step: thread 0 waits for the predecessor sweep; warp 0 owns the off-diagonal block
 // (row in registers for the right-application and the new reflector, shared memory for the column pass), warp 1 the
@@ -766,6 +771,7 @@ __global__ void __launch_bounds__(kDec ? kChaseThreadsDec : kChaseThreads) k_sbr
         while (v < totp && ++spins < (1ll << 28)) {
           asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
           if (v > last) { *(volatile int*)&sh_seen = v; last = v; }
+          else chase_backoff(a.sleep_ns);
         }
         if (v < totp) atomicExch(a.prog + m + 1, 1);
       }
@@ -777,7 +783,8 @@ __global__ void __launch_bounds__(kDec ? kChaseThreadsDec : kChaseThreads) k_sbr
         long long spins = 0;
         while (pub < tot && ++spins < (1ll << 32)) {
           const int dn = *(volatile int*)&sh_done;
-          if (dn > pub) {
+          if (dn <= pub) { chase_backoff(a.sleep_ns); continue; }
+          {
             // ONE gpu-scope fence (cumulative: the compute warps' stores, seen through sh_done) + a relaxed store; st.release
             // on top of __threadfence() was a second MEMBAR + CCTL.IVALL per step
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -795,15 +802,17 @@ __global__ void __launch_bounds__(kDec ? kChaseThreadsDec : kChaseThreads) k_sbr
         const int need = min(k + 2, totp);
         if (kDec) {
           int spins = 0;
-          while (*(volatile int*)&sh_seen < need && ++spins < (1 << 28)) {}
+          while (*(volatile int*)&sh_seen < need && ++spins < (1 << 28)) chase_backoff(a.sleep_ns);
           if (*(volatile int*)&sh_seen < need) atomicExch(a.prog + m + 1, 1);
           __threadfence_block();                          // the block loads below stay behind the flag
         } else {
           const int* p = a.prog + (s - 1);
           int v, spins = 0;
-          do {                                            // relaxed: see the watcher warp above
+          for (;;) {                                      // relaxed: see the watcher warp above
             asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-          } while (v < need && ++spins < (1 << 24));
+            if (v >= need || ++spins >= (1 << 24)) break;
+            chase_backoff(a.sleep_ns);
+          }
           if (v < need) atomicExch(a.prog + m + 1, 1);
         }
       }
@@ -1353,9 +1362,14 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     MB_CUDA(cudaMemcpyAsync(ctx->dbg_band.data(), Bd, sizeof(double) * kLdb * m, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
   }
-  ChaseArgs ca{Bd, m, z, L, prog};
+  ChaseArgs ca{Bd, m, z, L, prog, (unsigned)(ctx->sbr_chase_sleep < 0 ? 0 : ctx->sbr_chase_sleep)};
   const int G = std::max(1, std::min(ctx->sm_count, ceil_div(m, 2 * kBw) + 2));
-  if (ctx->sbr_chase_impl != 2) {
+  // Register footprint decides (profiles/r2l_*, r2m_*): the chase sits on 80 SMs for ~50 ms; a CTA with the watcher / publisher
+  // warps holds 160 x 192 registers, which costs a co-resident per-cell kernel (ksvm: 4 CTAs of 16 K registers = the whole file)
+  // TWO of its four CTAs on that SM (k_ens_svm_tma 50 -> 69 ms), the three-warp CTA (96 x 160) one (-> 59 ms).  Spinning is not
+  // the cost: back-off in the poll loops ("sbr_chase_sleep") changes nothing.
+  const bool dec = ctx->sbr_chase_impl == 1 || (ctx->sbr_chase_impl == 0 && !ctx->fit_shares_gpu);
+  if (dec) {
     MB_LAUNCH(ctx, "k_sbr_chase_dec", st) k_sbr_chase_t<true><<<G, kChaseThreadsDec, 0, st>>>(ca);
   } else {
     MB_LAUNCH(ctx, "k_sbr_chase", st) k_sbr_chase_t<false><<<G, kChaseThreads, 0, st>>>(ca);

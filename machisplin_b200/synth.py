@@ -17,9 +17,9 @@ CONFIGS = {
 ENSEMBLE_WEIGHTS = {"b": 0.31, "g": 0.22, "n": 0.17, "m": 0.12, "r": 0.10, "v": 0.08}
 
 
-def make_geom(nrow: int, ncol: int) -> Geom:
-    """Square cells of size 1/max(nrow, ncol); extent [0, ncol r] x [0, nrow r], NW origin."""
-    r = 1.0 / max(nrow, ncol)
+def make_geom(nrow: int, ncol: int, cell: float = 0.0) -> Geom:
+    """Square cells of size 1/max(nrow, ncol) (or ``cell``); extent [0, ncol r] x [0, nrow r], NW origin."""
+    r = cell if cell > 0 else 1.0 / max(nrow, ncol)
     return Geom(0.0, ncol * r, 0.0, nrow * r, nrow, ncol)
 
 
