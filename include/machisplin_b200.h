@@ -285,8 +285,10 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * "svm_impl" (before mb_ensemble_create) = 1 ksvm dot products on the tensor pipe (3 x TF32; the default for P <= 8), 2 packed FP32;
  * "coef_impl" = 0 coefficients from the band form of the two-stage reduction when cond(M + lambda I) <= 1e8 (default), 1 whenever
  * that form exists, 2 always the dense Cholesky of M + lambda I;
- * "sbr_chase_impl" = 1 watcher and publisher warps in the bulge chase, 2 three warps per sweep, 0 (default) = 1 for a fit that has
- * the GPU to itself and 2 inside mb_mltps_predict* with an ensemble (smaller register footprint beside the per-cell kernels);
+ * "sbr_chase_impl" = bulge chase: 1 flags with watcher / publisher warps, 2 flags with three warps per sweep, 3 tagged band elements
+ * (every double travels as two 8-byte words carrying the number of the sweep that wrote it: no flags, no fences), 0 (default) = 3
+ * for a fit that has the GPU to itself and 2 inside mb_mltps_predict* with an ensemble (smallest register footprint beside the
+ * per-cell kernels); all three are bit-identical;
  * "sbr_chase_sleep" = nanoseconds of back-off in the spin loops of the chase (0 = none; measured: no effect);
  * "defer_ensemble" = 0 starts the per-cell ensemble kernels of mb_mltps_predict* before the fit instead of behind stage 1
  * of its tridiagonalisation; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd (validation of the in-house path only). */

@@ -286,7 +286,7 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= -1 && value <= 100000, "sbr_chase_sleep must be in [-1, 100000] nanoseconds");
       ctx->sbr_chase_sleep = value;
     } else if (n == "sbr_chase_impl") {
-      MB_REQUIRE(value >= 0 && value <= 2, "sbr_chase_impl must be 0 (automatic), 1 (watcher / publisher warps) or 2 (three warps per sweep)");
+      MB_REQUIRE(value >= 0 && value <= 3, "sbr_chase_impl must be 0 (automatic), 1 (watcher / publisher warps), 2 (three warps per sweep) or 3 (tagged elements, no flags)");
       ctx->sbr_chase_impl = value;
     } else if (n == "coef_impl") {
       MB_REQUIRE(value >= 0 && value <= 2, "coef_impl must be 0 (band form when well conditioned), 1 (band form whenever it exists) or 2 (dense Cholesky)");

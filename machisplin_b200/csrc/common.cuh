@@ -213,10 +213,10 @@ struct mb_ctx {
                               // 1 = band form whenever it exists, 2 = always the dense Cholesky of M + lambda I
   mb_band_form band_form;
   int sbr_chase_sleep = 0;    // nanoseconds the spinning lanes of the bulge chase sleep between polls (-1 = none)
-  int sbr_chase_impl = 0;     // bulge chase: 1 = three warps per sweep + watcher and publisher warps (faster alone: 41 against 44 ms at
-                              // 5 000 knots), 2 = three warps per sweep (160 x 192 registers -> 96 x 160: a CTA of it costs the per-cell
-                              // kernel sharing its SM one CTA of four instead of two), 0 = 1 for a fit that has the GPU to itself, 2 when
-                              // the ensemble kernels run beside it
+  int sbr_chase_impl = 0;     // bulge chase: 1 = three warps per sweep + watcher and publisher warps (flags + one fence per step), 2 = three
+                              // warps per sweep (96 x 160 registers: the smallest footprint beside a per-cell kernel), 3 = tagged elements
+                              // (LL protocol: no flags, no fences; 3 compute + 4 loader warps), 0 = 3 for a fit that has the GPU to
+                              // itself, 2 when the ensemble kernels run beside it
   bool fit_shares_gpu = false;  // set by mb_mltps_predict* around its fit
   int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers
   int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits

@@ -950,6 +950,278 @@ __global__ void __launch_bounds__(kDec ? kChaseThreadsDec : kChaseThreads) k_sbr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bulge chase without flags and without fences ("sbr_chase_impl" = 3): the LL protocol of collective libraries applied to the
+// band.  Every stored double travels as two 8-byte words, each carrying 32 bits of the value and a 32-bit TAG = 1 + the number of
+// the sweep that wrote it (0 = the band as stage 1 left it); 8-byte accesses are single-copy atomic, so a reader that finds the
+// expected tag in both words holds the value that sweep wrote - no flag, no fence, no release / acquire pair, and a step is
+// handed to the successor element by element, as soon as each store lands in L2, instead of "two steps later, after a fence".
+// Why one expected tag per sweep suffices: sweep s - 1 partitions rows s .. m-1 into blocks R''_k of 32 and rewrites every band
+// element whose row and column blocks differ by at most one (diagonal blocks, sub-diagonal blocks incl. their bulge), each
+// exactly once; sweep s's blocks are those shifted by one row and column, so everything it reads at step k was written by
+// sweep s - 1 at step k or k + 1 and carries tag s - EXCEPT the last row of its sub-diagonal block left of that block's last
+// column (row block k + 1 against column block k - 1 of the predecessor): structurally zero (outside band and bulge), never
+// written, and not read here.  The arithmetic is the one of k_sbr_chase_t, bit for bit.
+// A wait that does not end (or the error flag raised by another sweep) aborts the sweep instead of hanging the device.
+// ---------------------------------------------------------------------------------------------
+struct ChaseLLArgs {
+  ulonglong2* Bt; int m;           // tagged band, element (off, col) at off + col * kLdb
+  ulonglong2* zt; int L;           // tagged right-hand sides, m x L
+  int* ctl;                        // ctl[0] = ticket counter, ctl[1] = error flag
+};
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t) : "memory");
+}
+// load and check are separate so that a lane can have a batch of loads in flight before it looks at the first tag (a check
+// right behind every load would serialise 32 L2 round trips per step); volatile, no memory clobber: the loads keep their order
+// among themselves and are re-issued in every pass of a spin loop, but do not fence the surrounding code
+__device__ __forceinline__ ulonglong2 ll_ld(const ulonglong2* p) {
+  ulonglong2 w;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w.x), "=l"(w.y) : "l"(p));
+  return w;
+}
+__device__ __forceinline__ bool ll_ok(const ulonglong2 w, unsigned tag, double& v) {
+  if ((unsigned)(w.x >> 32) != tag || (unsigned)(w.y >> 32) != tag) return false;
+  v = __longlong_as_double((long long)((w.x & 0xffffffffull) | (w.y << 32)));
+  return true;
+}
+__device__ __forceinline__ bool ll_try(const ulonglong2* p, unsigned tag, double& v) { return ll_ok(ll_ld(p), tag, v); }
+constexpr int kLLBatch = 16;
+// true = give up (own time-out or somebody else's error)
+__device__ __forceinline__ bool ll_giveup(int* ctl, unsigned& spins) {
+  if ((++spins & 1023u) != 0) return false;
+  int e;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(e) : "l"(ctl + 1) : "memory");
+  if (e) return true;
+  if (spins >= (1u << 23)) { atomicExch(ctl + 1, 1); return true; }
+  return false;
+}
+
+// CTA = 3 compute warps (the roles of k_sbr_chase_t) + 4 loader warps.  The loaders fetch the blocks of step k + 1 - every
+// thread ONE batch of <= 16 tagged elements, so a block costs one L2 round trip however often it has to be polled - into the
+// other half of a double-buffered shared-memory stage while the compute warps work on step k: blocks of different steps of a
+// sweep are disjoint, and what step k + 1 reads comes from the predecessor sweep, not from step k.  Producer / consumer
+// hand-over through named barriers (full[2] = 1, 2; empty[2] = 3, 4; compute-only = 5).
+constexpr int kLLCompute = 96, kLLLoaders = 128, kLLThreads = kLLCompute + kLLLoaders;
+__device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(kLLThreads) k_sbr_chase_ll(ChaseLLArgs a) {
+  __shared__ double Bs[2][32][kPad], Ds[2][32][kPad], zs[32][kPad];
+  __shared__ double vs[32], ws[32], vps[32], ts[32];
+  __shared__ double sh_tau;
+  __shared__ int sh_s;
+  const int tid = threadIdx.x, l = tid & 31, wid = tid >> 5, m = a.m;
+  constexpr int b = kBw;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sh_s = atomicAdd(a.ctl, 1);
+    __syncthreads();
+    const int s = sh_s;
+    if (s >= m - 2) break;
+    const unsigned rtag = (unsigned)s, wtag = (unsigned)s + 1u;   // written by sweep s - 1 (or initial) / by this sweep
+    const int tot = (m - s - 1 + b - 1) / b;
+    unsigned spins = 0;
+    if (wid >= 3) {
+      // =================================== loaders: warps 3, 4 sub-diagonal block, 5, 6 diagonal block ===================
+      const int lw = wid - 3, half = lw & 1;                        // half: columns q in [16 half, 16 half + 16)
+      for (int k = 0; k < tot; ++k) {
+        int st = 0, lp = 0, r0, ln;
+        if (k == 0) { ln = min(b, m - 1 - s); r0 = s + 1; }
+        else { st = s + 1 + (k - 1) * b; lp = min(b, m - st); r0 = st + lp; ln = min(b, m - r0); }
+        const int buf = k & 1;
+        if (k >= 2) nb_sync(3 + buf, kLLThreads);                   // the compute warps are done with step k - 2
+        double v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0;
+        unsigned pend = 0;
+        const ulonglong2* base;
+        if (lw < 2) {
+          if (k == 0) {                                             // column s, rows s+1 .. s+ln -> Bs[.][l][0]
+            base = a.Bt + (1 + l) + (size_t)s * kLdb;
+            pend = (half == 0 && l < ln) ? 1u : 0u;
+          } else {
+            // (l == 31, q <= 30): row block k + 1 against column block k - 1 of the predecessor - structurally zero, never written
+            const unsigned rowmask = l < ln ? ((l == 31 ? 0x80000000u : 0xffffffffu) & (lp >= 32 ? 0xffffffffu : ((1u << lp) - 1u))) : 0u;
+            pend = (rowmask >> (16 * half)) & 0xffffu;
+            base = a.Bt + (lp + l) + (size_t)st * kLdb + (size_t)(16 * half) * (kLdb - 1);   // element q at + q (kLdb - 1)
+          }
+        } else {
+          const unsigned rowmask = l < ln ? (l >= 31 ? 0xffffffffu : ((2u << l) - 1u)) : 0u;  // q <= l
+          pend = (rowmask >> (16 * half)) & 0xffffu;
+          base = a.Bt + l + (size_t)r0 * kLdb + (size_t)(16 * half) * (kLdb - 1);
+        }
+        while (pend) {
+          ulonglong2 raw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if ((pend >> j) & 1u) raw[j] = ll_ld(base + (size_t)j * (kLdb - 1));
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (((pend >> j) & 1u) && ll_ok(raw[j], rtag, v[j])) pend &= ~(1u << j);
+          if (pend && ll_giveup(a.ctl, spins)) break;
+        }
+        double (*dst)[kPad] = lw < 2 ? Bs[buf] : Ds[buf];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[l][16 * half + j] = v[j];
+        nb_arrive(1 + buf, kLLThreads);                             // stage `buf` holds step k
+      }
+      continue;
+    }
+    // ======================================= compute warps ============================================================
+    double taup = 0.0;
+    for (int k = 0; k < tot; ++k) {
+      int st = 0, lp = 0, r0, ln;
+      if (k == 0) { ln = min(b, m - 1 - s); r0 = s + 1; }
+      else { st = s + 1 + (k - 1) * b; lp = min(b, m - st); r0 = st + lp; ln = min(b, m - r0); }
+      const int buf = k & 1;
+      double (*B)[kPad] = Bs[buf];
+      double (*D)[kPad] = Ds[buf];
+      if (wid == 2) {                                               // right-hand sides: few elements, fetched here
+        for (int c0 = 0; c0 < a.L; c0 += 16) {
+          const int nc = min(16, a.L - c0);
+          double v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.0;
+          unsigned pend = l < ln ? ((1u << nc) - 1u) : 0u;
+          const ulonglong2* base = a.zt + (size_t)(r0 + l) + (size_t)c0 * m;
+          while (pend) {
+            ulonglong2 raw[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if ((pend >> j) & 1u) raw[j] = ll_ld(base + (size_t)j * m);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (((pend >> j) & 1u) && ll_ok(raw[j], rtag, v[j])) pend &= ~(1u << j);
+            if (pend && ll_giveup(a.ctl, spins)) break;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nc) zs[l][c0 + j] = v[j];
+        }
+      }
+      nb_sync(1 + buf, kLLThreads);                                 // the loaders have filled stage `buf`
+      if (wid == 0) {
+        double beta, tau, scale, x;
+        if (k == 0) {
+          // ---- type 1: reflector from column s, rows s+1 .. s+ln ---------------------------------------------
+          x = l < ln ? B[l][0] : 0.0;
+          const double xn2 = wsum((l >= 1 && l < ln) ? x * x : 0.0);
+          make_house(__shfl_sync(0xffffffffu, x, 0), xn2, beta, tau, scale);
+          vs[l] = l == 0 ? 1.0 : ((l < ln && tau != 0.0) ? x * scale : 0.0);
+          if (l == 0) sh_tau = tau;
+          if (l < ln) ll_store(a.Bt + (1 + l) + (size_t)s * kLdb, l == 0 ? beta : 0.0, wtag);
+        } else {
+          // ---- type 2: block below the previous diagonal block: right-apply H_prev, new reflector ---------------
+          double br[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) br[q] = B[l][q];
+          double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            u0 = fma(br[q], vps[q], u0);
+            u1 = fma(br[q + 1], vps[q + 1], u1);
+            u2 = fma(br[q + 2], vps[q + 2], u2);
+            u3 = fma(br[q + 3], vps[q + 3], u3);
+          }
+          const double u = taup * ((u0 + u1) + (u2 + u3));
+#pragma unroll
+          for (int q = 0; q < 32; ++q) br[q] = fma(-u, vps[q], br[q]);
+          x = br[0];
+          const double xn2 = wsum((l >= 1 && l < ln) ? x * x : 0.0);
+          make_house(__shfl_sync(0xffffffffu, x, 0), xn2, beta, tau, scale);
+          vs[l] = l == 0 ? 1.0 : ((l < ln && tau != 0.0) ? x * scale : 0.0);
+          if (l == 0) sh_tau = tau;
+          br[0] = l == 0 ? beta : 0.0;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) B[l][q] = br[q];
+        }
+      } else if (wid == 1) {
+        // ---- diagonal block r0 .. r0+ln-1: mirror the lower triangle the loaders brought ----------------------------
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q)
+          if (q > l) D[l][q] = D[q][l];
+      }
+      nb_sync(5, kLLCompute);
+      const double tau = sh_tau;
+      const double vl = vs[l];
+      if (wid == 0) {
+        if (k > 0) {
+          // ---- left-apply the new reflector to columns 1 .. lp-1 (lane = column), then store the block by rows ----
+          if (l >= 1 && l < lp) {
+            double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              y0 = fma(vs[i], B[i][l], y0);
+              y1 = fma(vs[i + 1], B[i + 1][l], y1);
+              y2 = fma(vs[i + 2], B[i + 2][l], y2);
+              y3 = fma(vs[i + 3], B[i + 3][l], y3);
+            }
+            const double y = tau * ((y0 + y1) + (y2 + y3));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) B[i][l] = fma(-vs[i], y, B[i][l]);
+          }
+          __syncwarp();
+          if (l < ln)
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (q < lp) ll_store(a.Bt + (lp + l - q) + (size_t)(st + q) * kLdb, B[l][q], wtag);
+        }
+        vps[l] = vl;                      // the reflector the next step applies from the right
+      } else if (wid == 1) {
+        // ---- type 3: D <- H D H ---------------------------------------------------------------------------------
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          p0 = fma(D[l][q], vs[q], p0);
+          p1 = fma(D[l][q + 1], vs[q + 1], p1);
+          p2 = fma(D[l][q + 2], vs[q + 2], p2);
+          p3 = fma(D[l][q + 3], vs[q + 3], p3);
+        }
+        const double p = tau * ((p0 + p1) + (p2 + p3));
+        const double w = fma(-0.5 * tau * wsum(p * vl), vl, p);
+        ws[l] = w;
+        __syncwarp();
+        if (l < ln)
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (q <= l) ll_store(a.Bt + (l - q) + (size_t)(r0 + q) * kLdb, D[l][q] - vl * ws[q] - w * vs[q], wtag);
+      } else if (a.L > 0) {
+        // ---- right-hand sides: z[r0 .. r0+ln-1, :] <- H z -----------------------------------------------------------
+        if (l < a.L) {
+          double t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+          for (int i = 0; i < 32; i += 2) {
+            t0 = fma(vs[i], zs[i][l], t0);
+            t1 = fma(vs[i + 1], zs[i + 1][l], t1);
+          }
+          ts[l] = tau * (t0 + t1);
+        }
+        __syncwarp();
+        if (l < ln)
+          for (int cc = 0; cc < a.L; ++cc) ll_store(a.zt + (size_t)(r0 + l) + (size_t)cc * m, fma(-vl, ts[cc], zs[l][cc]), wtag);
+      }
+      taup = tau;
+      nb_sync(5, kLLCompute);             // vs / zs / ts are rewritten by the next step
+      if (k + 2 < tot) nb_arrive(3 + buf, kLLThreads);   // stage `buf` may be refilled (step k + 2); nobody waits after that
+    }
+  }
+}
+
+// plain <-> tagged storage (tag 0 = "as stage 1 left it")
+__global__ void k_sbr_tag(const double* __restrict__ src, ulonglong2* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ll_store(dst + i, src[i], 0u);
+}
+__global__ void k_sbr_untag(const ulonglong2* __restrict__ src, double* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ulonglong2 w = src[i];
+  dst[i] = __longlong_as_double((long long)((w.x & 0xffffffffull) | (w.y << 32)));
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace
@@ -1368,8 +1640,22 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   // warps holds 160 x 192 registers, which costs a co-resident per-cell kernel (ksvm: 4 CTAs of 16 K registers = the whole file)
   // TWO of its four CTAs on that SM (k_ens_svm_tma 50 -> 69 ms), the three-warp CTA (96 x 160) one (-> 59 ms).  Spinning is not
   // the cost: back-off in the poll loops ("sbr_chase_sleep") changes nothing.
-  const bool dec = ctx->sbr_chase_impl == 1 || (ctx->sbr_chase_impl == 0 && !ctx->fit_shares_gpu);
-  if (dec) {
+  // A fit that has the GPU to itself takes the tagged-element chase (34 against 41 ms at 5 000 knots, faster at every size,
+  // profiles/r2o3_chase_check.txt); its CTA (224 threads x 255 registers) would leave a co-resident per-cell kernel nothing,
+  // so beside the ensemble the three-warp CTA stays.
+  const bool dec = ctx->sbr_chase_impl == 1;
+  if (ctx->sbr_chase_impl == 3 || (ctx->sbr_chase_impl == 0 && !ctx->fit_shares_gpu)) {
+    // tagged copies of the band and the right-hand sides, chase, plain copies back (2 x 5 MB at 5 000 knots: ~10 us each)
+    const size_t nb = (size_t)kLdb * ncolb, nz = (size_t)m * std::max(L, 0);
+    ulonglong2* Bt = ar.take_n<ulonglong2>(nb);
+    ulonglong2* zt = ar.take_n<ulonglong2>(std::max<size_t>(nz, 1));
+    k_sbr_tag<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(Bd, Bt, nb);
+    if (nz) k_sbr_tag<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(z, zt, nz);
+    ChaseLLArgs la{Bt, m, zt, L, prog + m};
+    MB_LAUNCH(ctx, "k_sbr_chase_ll", st) k_sbr_chase_ll<<<G, kLLThreads, 0, st>>>(la);
+    k_sbr_untag<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(Bt, Bd, nb);
+    if (nz) k_sbr_untag<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(zt, z, nz);
+  } else if (dec) {
     MB_LAUNCH(ctx, "k_sbr_chase_dec", st) k_sbr_chase_t<true><<<G, kChaseThreadsDec, 0, st>>>(ca);
   } else {
     MB_LAUNCH(ctx, "k_sbr_chase", st) k_sbr_chase_t<false><<<G, kChaseThreads, 0, st>>>(ca);

@@ -296,18 +296,29 @@ def test_coefficients_from_band_form(engine, n):
 
 
 @pytest.mark.parametrize("n", [36, 70, 200, 1100])
-def test_chase_with_watcher_and_publisher_warps(engine, n):
-    """The default chase kernel (hand-shakes on two extra warps) does the same arithmetic in the same order as the three-warp
-    kernel (sbr_chase_impl = 2): bit-identical."""
+def test_chase_variants_are_bit_identical(engine, n):
+    """The three bulge-chase kernels - flags with three warps (2), flags with watcher / publisher warps (1), tagged band elements
+    with loader warps (3, the default of a stand-alone fit) - do the same arithmetic in the same order: bit-identical lambda,
+    coefficients and eigenvalues, for one and for three responses."""
     geom = synth.make_geom(512, 512)
     xy, _, _ = synth.make_knots(geom, n, 800 + n)
     y = synth.residual_field(xy, 800 + n)
-    got = engine.tps_fit(xy, y)
+    Y = np.stack([y, y[::-1].copy(), y * y], axis=1)
+    if n == 200:                                   # 20 responses: more right-hand sides than one batch of tagged loads
+        Y = np.concatenate([Y] + [np.roll(Y, 7 * (j + 1), axis=0) * (1.0 + 0.1 * j) for j in range(6)], axis=1)[:, :20]
+    res = {}
     try:
-        engine.set_param("sbr_chase_impl", 2)
-        ref = engine.tps_fit(xy, y)
+        for impl in (2, 1, 3, 0):
+            engine.set_param("sbr_chase_impl", impl)
+            res[impl] = (engine.tps_fit(xy, y), engine.tps_fit(xy, Y))
     finally:
         engine.set_param("sbr_chase_impl", 0)
-    assert got.lam == ref.lam
-    np.testing.assert_array_equal(got.c, ref.c)
-    np.testing.assert_array_equal(got.decomposition()[0], ref.decomposition()[0])
+    ref, ref3 = res[2]
+    for impl in (1, 3, 0):
+        got, got3 = res[impl]
+        assert got.lam == ref.lam
+        np.testing.assert_array_equal(got.c, ref.c)
+        np.testing.assert_array_equal(got.decomposition()[0], ref.decomposition()[0])
+        for g, r in zip(got3, ref3):
+            assert g.lam == r.lam
+            np.testing.assert_array_equal(g.c, r.c)
