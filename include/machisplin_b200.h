@@ -295,7 +295,7 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
 int mb_set_param(mb_ctx* ctx, const char* name, int value);
 
 /* ---- GeoTIFF in / out: terra::rast(path) (README Example 1, V73:68-70) and terra::writeRaster() (V73:1011, 1020) -----------------
- * Host-only (no context, no GPU).  Readers accept classic TIFF, striped or tiled, chunky or planar bands, 8 / 16 / 32-bit integers
+ * Host-only (no context, no GPU) except mb_tiff_read_f32_dev.  Readers accept classic TIFF, striped or tiled, chunky or planar bands, 8 / 16 / 32-bit integers
  * and 32 / 64-bit floats, compression none / LZW / PackBits, predictor 1 / 2 - which covers the rasters the reference bundles
  * (INT16, 128 x 128 tiles, none or LZW, GDAL_NODATA) and what terra writes by default.  Everything else is refused with a message.
  * Cell order is terra's: row-major from the NW corner.  NoData cells come back as NaN (terra: NA). */
@@ -309,6 +309,17 @@ typedef struct {
 int mb_tiff_info(const char* path, mb_tiff_meta* out);
 /* one band (0-based) as float32, nrow * ncol values; tiles / strips are decoded by nthreads host threads (0 = all) */
 int mb_tiff_read_f32(const char* path, int band, float* out, int nthreads);
+/* The same band decoded ON THE DEVICE into a float32 plane in HBM (out_dev: nrow * ncol floats), ready for mb_mltps_predict_dev:
+ * the file's compressed bytes cross PCIe through pinned bounce buffers, the GPU undoes LZW (one warp per tile / strip), the
+ * horizontal predictor, the sample type and NoData.  Little-endian files with compression none / LZW take this path; big-endian
+ * files, PackBits and predictor 2 on pixel-interleaved bands fall back to the host decoder + one upload (stats says which).
+ * Synchronous: the plane is complete when the call returns.  Values are bit-identical to mb_tiff_read_f32. */
+typedef struct {
+  int32_t decoded_on_gpu;   /* 1 = LZW / predictor / conversion ran on the device, 0 = host decoder + upload */
+  int32_t chunks;           /* tiles or strips of the band */
+  int64_t h2d_bytes;        /* bytes that crossed PCIe */
+} mb_tiff_dev_stats;
+int mb_tiff_read_f32_dev(mb_ctx* ctx, const char* path, int band, float* out_dev, int nthreads, void* stream, mb_tiff_dev_stats* stats /* may be NULL */);
 /* FLT4S GeoTIFF (terra::writeRaster's default datatype), 256 x 256 tiles, compression 1 (none) or 5 (LZW), NaN = NoData;
  * epsg > 0 adds the CRS key (4326 for the LONG / LAT rasters of the reference) */
 int mb_tiff_write_f32(const char* path, const mb_grid* g, const float* data, int compression, int epsg, int nthreads);

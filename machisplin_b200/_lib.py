@@ -118,6 +118,7 @@ SIGNATURES = {
     "mb_set_param": (C.c_int, [VP, C.c_char_p, C.c_int]),
     "mb_tiff_info": (C.c_int, [C.c_char_p, VP]),
     "mb_tiff_read_f32": (C.c_int, [C.c_char_p, C.c_int, PF, C.c_int]),
+    "mb_tiff_read_f32_dev": (C.c_int, [VP, C.c_char_p, C.c_int, VP, C.c_int, VP, VP]),
     "mb_tiff_write_f32": (C.c_int, [C.c_char_p, PG, PF, C.c_int, C.c_int, C.c_int]),
     "mb_tiff_write_f64": (C.c_int, [C.c_char_p, PG, PD, C.c_int, C.c_int, C.c_int]),
 }

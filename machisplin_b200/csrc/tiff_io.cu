@@ -484,6 +484,273 @@ void write_f32(const char* path, const mb_grid& g, const T* data, int compressio
   if (!ok) throw Error(MB_E_ARG, std::string("write to '") + path + "' failed");
 }
 
+
+// =========================================================================================================================
+// Device path: mb_tiff_read_f32_dev.  The file's COMPRESSED bytes cross PCIe (through a pair of pinned bounce buffers), the
+// GPU undoes LZW, the horizontal predictor, the sample type and the NoData value, and the float32 plane is born in HBM - where
+// mb_mltps_predict_dev wants it.  One warp per tile / strip:
+//   k_tiff_lzw     lane 0 walks the code stream; the dictionary holds, per code, WHERE in the already decoded output its string
+//                  starts and how long it is (every LZW string is a copy of earlier output + 1 byte), 24 KB of shared memory; strings
+//                  of 16 bytes or more are copied by the whole warp.  Same early-change rule and tolerance of a missing
+//                  EOI as the host decoder.
+//   k_tiff_unpack  rows of the decoded chunk -> output plane, coalesced; predictor 2 as a warp-wide inclusive scan per 32 pixels
+//                  with a running carry (modulo 2^bits, like libtiff).
+// Big-endian files, PackBits and predictor 2 on pixel-interleaved multi-band chunks take the host decoder + one upload.
+// =========================================================================================================================
+struct ChunkJob {
+  unsigned long long src;      // offset of the chunk's bytes in the compressed device buffer
+  unsigned int nsrc;           // their number
+  int r0, c0, nr, nc;          // where the chunk's pixels go: rows [r0, r0 + nr), columns [c0, c0 + nc)
+  int rows;                    // rows held by the chunk buffer (tile height, or the strip's real height)
+};
+struct UnpackArgs {
+  const unsigned char* raw;    // decoded (or uncompressed) chunk bytes: chunk j at raw_base[j]
+  const unsigned long long* raw_off;
+  const ChunkJob* jobs;
+  int cw, cspp, sel, bytes, fmt, predictor, width;
+  int has_nodata; double nodata;
+  float* out;
+};
+
+__global__ void __launch_bounds__(32) k_tiff_lzw(const unsigned char* __restrict__ comp, const ChunkJob* __restrict__ jobs,
+                                                   const unsigned long long* __restrict__ raw_off, unsigned char* __restrict__ raw,
+                                                   const unsigned long long* __restrict__ raw_cap, int* __restrict__ err) {
+  __shared__ unsigned int s_pos[4096];
+  __shared__ unsigned short s_len[4096];
+  const ChunkJob jb = jobs[blockIdx.x];
+  const unsigned char* src = comp + jb.src;
+  unsigned char* dst = raw + raw_off[blockIdx.x];
+  const size_t cap = (size_t)raw_cap[blockIdx.x];
+  const size_t n = jb.nsrc;
+  const int lane = threadIdx.x;
+  // lane 0 decodes; the other lanes wait for copy orders (len >= 16) or the end
+  size_t out = 0, ip = 0;
+  unsigned int acc = 0;
+  int nbits = 0, width = 9, next = 258, prev = -1;
+  size_t prev_pos = 0;
+  int prev_len = 0;
+  for (;;) {
+    // ---- lane 0: next code -> (from, len, kwkwk) ----
+    unsigned int cmd_from = 0; int cmd_len = -1;     // -1 = stop, 0 = nothing to copy (clear code)
+    int kw = 0;
+    if (lane == 0) {
+      if (out < cap) {
+        while (nbits < width && ip < n) { acc = (acc << 8) | src[ip++]; nbits += 8; }
+        if (nbits >= width) {
+          const int code = (int)((acc >> (nbits - width)) & ((1u << width) - 1));
+          nbits -= width;
+          if (code == 257) cmd_len = -1;
+          else if (code == 256) { width = 9; next = 258; prev = -1; cmd_len = 0; }
+          else {
+            const bool kwkwk = prev >= 0 && code == next;
+            if ((prev < 0 && code > 255) || (!kwkwk && code >= next)) { *err = 1; cmd_len = -1; }
+            else {
+              size_t pos; int len;
+              if (kwkwk) { pos = prev_pos; len = prev_len + 1; kw = 1; }
+              else if (code < 256) { pos = (size_t)-1; len = 1; }
+              else { pos = s_pos[code]; len = s_len[code]; }
+              // new dictionary entry: str(prev) + first byte of this string = the prev_len + 1 bytes starting at prev_pos
+              if (prev >= 0 && next < 4096) {
+                s_pos[next] = (unsigned int)prev_pos;
+                s_len[next] = (unsigned short)(prev_len + 1);
+                ++next;
+                if (next + 1 >= (1 << width) && width < 12) ++width;
+              }
+              const size_t room = cap - out;
+              const int k = (size_t)len <= room ? len : (int)room;
+              if (code < 256 && !kwkwk) { dst[out] = (unsigned char)code; cmd_len = 0; }
+              else if (k < 16) { for (int i = 0; i < k; ++i) dst[out + i] = dst[pos + i]; cmd_len = 0; }   // forward copy: overlap is the point (kwkwk)
+              else { cmd_from = (unsigned int)pos; cmd_len = k; }
+              prev = code; prev_pos = out; prev_len = len;
+              if (cmd_len == 0) out += k;
+            }
+          }
+        }
+      }
+    }
+    cmd_len = __shfl_sync(0xffffffffu, cmd_len, 0);
+    if (cmd_len < 0) break;
+    if (cmd_len > 0) {
+      cmd_from = __shfl_sync(0xffffffffu, cmd_from, 0);
+      const unsigned long long o = __shfl_sync(0xffffffffu, (unsigned long long)out, 0);
+      kw = __shfl_sync(0xffffffffu, kw, 0);
+      // source [from, from + len) and destination [o, o + len) overlap only in the kwkwk case (from + len - 1 == o): the last byte
+      // equals the first, which is old output
+      for (int i = lane; i < cmd_len; i += 32) {
+        const size_t sidx = (kw && i == cmd_len - 1 && (size_t)cmd_from + i == o) ? (size_t)cmd_from : (size_t)cmd_from + i;
+        dst[o + i] = dst[sidx];
+      }
+      __syncwarp();
+      if (lane == 0) out += cmd_len;
+    }
+  }
+  // zero what the stream did not cover (truncated chunk), like the host path
+  out = __shfl_sync(0xffffffffu, (unsigned long long)out, 0);
+  for (size_t i = out + lane; i < cap; i += 32) dst[i] = 0;
+}
+
+__device__ __forceinline__ unsigned long long tiff_load(const unsigned char* q, int bytes) {
+  unsigned long long v = 0;
+  for (int i = 0; i < bytes; ++i) v |= (unsigned long long)q[i] << (8 * i);      // little-endian samples
+  return v;
+}
+__device__ __forceinline__ float tiff_value(unsigned long long raw_v, int bytes, int fmt, int has_nodata, double nodata) {
+  double val;
+  if (fmt == 3) val = bytes == 4 ? (double)__uint_as_float((unsigned int)raw_v) : __longlong_as_double((long long)raw_v);
+  else if (fmt == 2) val = bytes == 1 ? (double)(signed char)raw_v : bytes == 2 ? (double)(short)raw_v : (double)(int)raw_v;
+  else val = (double)raw_v;
+  return (has_nodata && val == nodata) ? __int_as_float(0x7fc00000) : (float)val;
+}
+
+__global__ void __launch_bounds__(256) k_tiff_unpack(UnpackArgs a) {
+  const ChunkJob jb = a.jobs[blockIdx.x];
+  const unsigned char* data = a.raw + a.raw_off[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t pix = (size_t)a.cspp * a.bytes;
+  const unsigned long long mask = a.bytes == 8 ? ~0ull : ((1ull << (8 * a.bytes)) - 1ull);
+  for (int rr = warp; rr < jb.nr; rr += 8) {
+    const unsigned char* line = data + (size_t)rr * a.cw * pix;
+    float* dst = a.out + (size_t)(jb.r0 + rr) * a.width + jb.c0;
+    unsigned long long carry = 0;
+    for (int c0 = 0; c0 < jb.nc; c0 += 32) {
+      const int cc = c0 + lane;
+      unsigned long long v = cc < jb.nc ? tiff_load(line + (size_t)cc * pix + (size_t)a.sel * a.bytes, a.bytes) : 0ull;
+      if (a.predictor == 2) {                       // cspp == 1 here (host side checks): inclusive scan over the row
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned long long u = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= d) v += u;
+        }
+        v = (v + carry) & mask;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+      if (cc < jb.nc) dst[cc] = tiff_value(v, a.bytes, a.fmt, a.has_nodata, a.nodata);
+    }
+  }
+}
+
+// pinned bounce buffers, one pair per process (the reader is synchronous on the host side)
+struct Bounce {
+  unsigned char* p[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  size_t cap = 0;
+  void ensure(size_t want) {
+    if (cap >= want) return;
+    for (int i = 0; i < 2; ++i) {
+      if (p[i]) cudaFreeHost(p[i]);
+      p[i] = nullptr;
+      if (cudaMallocHost(reinterpret_cast<void**>(&p[i]), want) != cudaSuccess) { cap = 0; throw Error(MB_E_NOMEM, "cudaMallocHost (GeoTIFF bounce buffer)"); }
+      if (!ev[i] && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) throw Error(MB_E_CUDA, "cudaEventCreate");
+    }
+    cap = want;
+  }
+};
+Bounce& bounce() { static Bounce b; return b; }
+
+void read_band_dev(mb_ctx* ctx, const Mapped& f, const Meta& m, int band, float* out_dev, int nthreads, cudaStream_t st,
+                   mb_tiff_dev_stats* stats) {
+  MB_REQUIRE(band >= 0 && band < m.spp, "TIFF: no such band");
+  const int bytes = m.bits / 8;
+  const int cspp = m.planar == 1 ? m.spp : 1;
+  const size_t across = ((size_t)m.width + m.cw - 1) / m.cw, down = ((size_t)m.height + m.ch - 1) / m.ch;
+  const size_t plane0 = m.planar == 2 ? (size_t)band * across * down : 0;
+  const int sel = m.planar == 1 ? band : 0;
+  const size_t nchunk = across * down;
+  bool gpu_ok = m.le && (m.compression == 1 || m.compression == 5) && !(m.predictor == 2 && cspp > 1) && nchunk > 0;
+  if (gpu_ok && m.compression == 1)               // a truncated uncompressed chunk is zero-padded by the host decoder only
+    for (size_t ci = 0; ci < nchunk; ++ci) {
+      const int rows = m.tiled ? m.ch : std::min(m.ch, m.height - (int)(ci / across) * m.ch);
+      if (m.cnt[plane0 + ci] < (uint64_t)rows * m.cw * cspp * bytes) gpu_ok = false;
+    }
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  Arena& ar = ctx->arena;
+  if (!gpu_ok) {
+    // host decoder into a pinned plane, one upload
+    const size_t ncell = (size_t)m.width * m.height;
+    Bounce& b = bounce();
+    b.ensure(std::max<size_t>(ncell * sizeof(float), size_t(32) << 20));
+    read_band(f, m, band, reinterpret_cast<float*>(b.p[0]), nthreads);
+    MB_CUDA(cudaMemcpyAsync(out_dev, b.p[0], ncell * sizeof(float), cudaMemcpyHostToDevice, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (stats) { stats->decoded_on_gpu = 0; stats->h2d_bytes = (int64_t)(ncell * sizeof(float)); stats->chunks = (int32_t)nchunk; }
+    return;
+  }
+  // ---- jobs -----------------------------------------------------------------------------------------------------------
+  std::vector<ChunkJob> jobs(nchunk);
+  std::vector<unsigned long long> raw_off(nchunk), raw_cap(nchunk);
+  size_t comp_total = 0, raw_total = 0;
+  for (size_t ci = 0; ci < nchunk; ++ci) {
+    const size_t cx = ci % across, cy = ci / across;
+    const int rows = m.tiled ? m.ch : std::min(m.ch, m.height - (int)cy * m.ch);
+    const size_t raw = (size_t)rows * m.cw * cspp * bytes;
+    ChunkJob& j = jobs[ci];
+    j.src = comp_total;
+    j.nsrc = (unsigned int)m.cnt[plane0 + ci];
+    j.r0 = (int)cy * m.ch; j.c0 = (int)cx * m.cw;
+    j.nr = std::min(rows, m.height - j.r0); j.nc = std::min(m.cw, m.width - j.c0);
+    j.rows = rows;
+    comp_total += (j.nsrc + 15u) & ~size_t(15);
+    raw_cap[ci] = raw;
+    if (m.compression == 1) {
+      // the chunk's own bytes are the raw bytes; a short chunk is padded with zeros on the device
+      raw_off[ci] = raw_total;
+      raw_total += (raw + 15) & ~size_t(15);
+    } else {
+      raw_off[ci] = raw_total;
+      raw_total += (raw + 15) & ~size_t(15);
+    }
+  }
+  unsigned char* d_comp = ar.take_n<unsigned char>(std::max<size_t>(comp_total, 16));
+  unsigned char* d_raw = m.compression == 1 ? nullptr : ar.take_n<unsigned char>(std::max<size_t>(raw_total, 16));
+  // ---- compressed bytes -> device through the pinned pair ---------------------------------------------------------------------
+  Bounce& b = bounce();
+  b.ensure(size_t(32) << 20);
+  {
+    size_t ci = 0;
+    int which = 0;
+    bool used[2] = {false, false};
+    while (ci < nchunk) {
+      size_t first = ci, fill = 0;
+      while (ci < nchunk && fill + ((jobs[ci].nsrc + 15u) & ~size_t(15)) <= b.cap) { fill += (jobs[ci].nsrc + 15u) & ~size_t(15); ++ci; }
+      MB_REQUIRE(ci > first, "TIFF: a chunk is larger than the bounce buffer (32 MB)");
+      if (used[which]) MB_CUDA(cudaEventSynchronize(b.ev[which]));
+      unsigned char* hp = b.p[which];
+      const size_t base = (size_t)jobs[first].src;
+      parallel_chunks(ci - first, nthreads, [&](size_t k) {
+        const ChunkJob& j = jobs[first + k];
+        std::memcpy(hp + (j.src - base), f.p + m.off[plane0 + first + k], j.nsrc);
+      });
+      MB_CUDA(cudaMemcpyAsync(d_comp + base, hp, fill, cudaMemcpyHostToDevice, st));
+      MB_CUDA(cudaEventRecord(b.ev[which], st));
+      used[which] = true;
+      which ^= 1;
+    }
+  }
+  ChunkJob* d_jobs = ar.upload(jobs.data(), jobs.size(), st);
+  unsigned long long* d_cap = ar.upload(raw_cap.data(), raw_cap.size(), st);
+  int* d_err = ar.take_n<int>(1);
+  MB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+  const unsigned char* raw_src = d_comp;
+  std::vector<unsigned long long> src_off(nchunk);
+  unsigned long long* d_roff;
+  if (m.compression == 5) {
+    d_roff = ar.upload(raw_off.data(), raw_off.size(), st);
+    MB_LAUNCH(ctx, "k_tiff_lzw", st) k_tiff_lzw<<<(unsigned)nchunk, 32, 0, st>>>(d_comp, d_jobs, d_roff, d_raw, d_cap, d_err);
+    raw_src = d_raw;
+  } else {
+    // uncompressed: unpack straight from the uploaded bytes
+    for (size_t ci = 0; ci < nchunk; ++ci) src_off[ci] = jobs[ci].src;
+    d_roff = ar.upload(src_off.data(), src_off.size(), st);
+  }
+  UnpackArgs ua{raw_src, d_roff, d_jobs, m.cw, cspp, sel, bytes, m.fmt, m.predictor, m.width, m.has_nodata ? 1 : 0, m.nodata, out_dev};
+  MB_LAUNCH(ctx, "k_tiff_unpack", st) k_tiff_unpack<<<(unsigned)nchunk, 256, 0, st>>>(ua);
+  MB_CUDA(cudaGetLastError());
+  int herr = 0;
+  MB_CUDA(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));      // the job tables are host vectors; the bounce buffers are reused by the next call
+  if (herr) throw Error(MB_E_ARG, "TIFF: corrupt LZW stream");
+  if (stats) { stats->decoded_on_gpu = 1; stats->h2d_bytes = (int64_t)comp_total; stats->chunks = (int32_t)nchunk; }
+}
+
 }  // namespace
 }  // namespace mb
 
@@ -518,6 +785,18 @@ int mb_tiff_read_f32(const char* path, int band, float* out, int nthreads) {
     Mapped f(path);
     const Meta m = parse(f);
     read_band(f, m, band, out, nthreads);
+  });
+}
+
+int mb_tiff_read_f32_dev(mb_ctx* ctx, const char* path, int band, float* out_dev, int nthreads, void* stream, mb_tiff_dev_stats* stats) {
+  return guarded([&] {
+    MB_REQUIRE(ctx && path && out_dev, "NULL argument");
+    MB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    ctx->arena.begin(st);
+    Mapped f(path);
+    const Meta m = parse(f);
+    read_band_dev(ctx, f, m, band, out_dev, nthreads, st, stats);
   });
 }
 

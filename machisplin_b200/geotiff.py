@@ -1,5 +1,6 @@
 """GeoTIFF in / out through the C ABI (``mb_tiff_*``, csrc/tiff_io.cu): the host-side mirror of ``terra::rast(path)``
-(README Example 1, V73:68-70) and ``terra::writeRaster(x, filename)`` (V73:1011, 1020).  No GPU is needed for these calls."""
+(README Example 1, V73:68-70) and ``terra::writeRaster(x, filename)`` (V73:1011, 1020).  No GPU is needed for these calls,
+except ``read_raster_dev`` (decode on the device, plane born in HBM)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -60,6 +61,20 @@ def read_raster(path: str, band: int = 0, out: Optional[np.ndarray] = None, thre
         raise ValueError(f"out must be a C-contiguous float32 array of shape {shape}")
     check(_lib.load().mb_tiff_read_f32(str(path).encode(), int(band), out.ctypes.data_as(_lib.PF), int(threads)))
     return info.geom, out
+
+
+class _DevStats(C.Structure):
+    _fields_ = [("decoded_on_gpu", C.c_int32), ("chunks", C.c_int32), ("h2d_bytes", C.c_int64)]
+
+
+def read_raster_dev(engine, path: str, out_ptr: int, band: int = 0, threads: int = 0, stream: int = 0) -> dict:
+    """The band decoded ON THE DEVICE into the float32 plane at ``out_ptr`` (nrow * ncol floats in HBM, e.g. one plane of the
+    covariate stack ``Engine.mltps_predict_dev`` reads): compressed bytes cross PCIe, the GPU undoes LZW, predictor, sample
+    type and NoData (``mb_tiff_read_f32_dev``).  Returns {"decoded_on_gpu", "chunks", "h2d_bytes"}."""
+    st = _DevStats()
+    check(engine.lib.mb_tiff_read_f32_dev(engine._h, str(path).encode(), int(band), C.c_void_p(int(out_ptr)), int(threads),
+                                          C.c_void_p(int(stream)), C.byref(st)))
+    return {"decoded_on_gpu": bool(st.decoded_on_gpu), "chunks": int(st.chunks), "h2d_bytes": int(st.h2d_bytes)}
 
 
 def read_stack(paths, threads: int = 0):
