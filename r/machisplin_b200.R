@@ -74,3 +74,27 @@ mb_rss_objective <- function(mb, R) { G <- .Call("mbR_gram", mb, as.matrix(R)); 
 # planes mb_mltps_predict() uploads (list(grid, cov)); V73:1011 / 1020: the final raster as a FLT4S GeoTIFF.
 mb_read_stack <- function(paths) .Call("mbR_read_stack", as.character(paths))
 mb_write_raster <- function(path, grid, values, epsg = 4326L) invisible(.Call("mbR_write_raster", as.character(path), as.numeric(grid), as.numeric(values), as.integer(epsg)))
+
+# machisplin.tiles.merge (V73:1392-1548) on the $final rasters of the tiles; wins = 4 x ntiles integer matrix of 0-based half-open
+# cell windows (r0, r1, c0, c1), tiles in the reference's order (row-major from the SW tile)
+mb_tiles_merge <- function(mb, template, in.ncol, in.nrow, wins, tiles)
+  .Call("mbR_tiles_merge", mb, mb_grid(template), as.integer(in.ncol), as.integer(in.nrow), as.integer(wins), lapply(tiles, as.numeric))
+mb_tiles_owned_window <- function(template, in.ncol, in.nrow, wins, t)
+  .Call("mbR_tiles_owned_window", mb_grid(template), as.integer(in.ncol), as.integer(in.nrow), as.integer(wins), as.integer(t))
+
+# Multi-GPU, one R process per GPU (what the reference's deleted snowfall path did, old/...V69.R:937-968): rank 0 draws the id,
+# the hosts ship its bytes (saveRDS / socket), every rank joins; then the Gram of V73:329-333 is summed over the ranks and every
+# rank predicts its own row block of the raster while fields::Tps runs on `root` only.
+mb_comm_unique_id <- function() .Call("mbR_comm_unique_id")
+mb_comm_init <- function(mb, nranks, rank, id) invisible(.Call("mbR_comm_init", mb, as.integer(nranks), as.integer(rank), id))
+mb_rss_objective_sharded <- function(mb, R.local) { G <- .Call("mbR_gram_allreduce", mb, as.matrix(R.local)); function(k) drop(k %*% G %*% k) / sum(k)^2 }
+mb_mltps_predict_block <- function(mb, block_stack, n.covars, models, kept, w, w.total, xy, res.FINAL, n, root = 0L) {
+  g <- mb_grid(block_stack)
+  cov <- writeBin(as.numeric(terra::values(block_stack[[seq_len(n.covars)]])), raw(), size = 4)
+  ens <- .Call("mbR_ensemble_create", mb, g, models, kept, as.numeric(w), as.numeric(w.total))
+  v <- .Call("mbR_mltps_predict_shard", mb, g, ens, cov, as.integer(n.covars), if (is.null(xy)) NULL else as.matrix(xy), res.FINAL,
+             as.integer(n), -1, as.integer(root))
+  out <- terra::rast(block_stack[[1]]); terra::values(out) <- v
+  out
+}
+

@@ -154,3 +154,76 @@ SEXP mbR_write_raster(SEXP path, SEXP grid, SEXP values, SEXP epsg) {
   MB_CHECK(mb_tiff_write_f64(CHAR(STRING_ELT(path, 0)), &g, REAL(values), 5, Rf_asInteger(epsg), 0));
   return R_NilValue;
 }
+
+/* ---- machisplin.tiles.* and the multi-GPU path (one R process per GPU) ------------------------------------------------------ */
+static void wins_of(SEXP wins, int nt, mb_window* out) {      /* integer matrix 4 x ntiles: (r0, r1, c0, c1) per tile, 0-based, half-open */
+  const int* v = INTEGER(wins);
+  for (int t = 0; t < nt; ++t) { out[t].r0 = v[4 * t]; out[t].r1 = v[4 * t + 1]; out[t].c0 = v[4 * t + 2]; out[t].c1 = v[4 * t + 3]; }
+}
+
+/* machisplin.tiles.merge(tiles, in.ncol, in.nrow) (V73:1392-1548): tiles = list of numeric vectors (tile rasters in terra cell
+ * order, row-major from the SW tile), wins as above.  Returns the merged raster values. */
+SEXP mbR_tiles_merge(SEXP ctx, SEXP grid, SEXP nC, SEXP nR, SEXP wins, SEXP tiles) {
+  mb_grid g = grid_of(grid);
+  const int nt = Rf_asInteger(nC) * Rf_asInteger(nR);
+  if (nt < 1 || nt > 4096 || Rf_length(tiles) != nt || Rf_length(wins) != 4 * nt) Rf_error("machisplin_b200: tiles / wins do not match in.ncol x in.nrow");
+  mb_window w[4096];
+  const double* ptr[4096];
+  wins_of(wins, nt, w);
+  for (int t = 0; t < nt; ++t) ptr[t] = REAL(VECTOR_ELT(tiles, t));
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)g.nrow * g.ncol));
+  MB_CHECK(mb_tiles_merge((mb_ctx*)R_ExternalPtrAddr(ctx), &g, Rf_asInteger(nC), Rf_asInteger(nR), w, ptr, REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
+
+/* the window of cells tile t owns when the merge is spread over the GPUs (mb_tiles_owned_window): c(r0, r1, c0, c1) */
+SEXP mbR_tiles_owned_window(SEXP grid, SEXP nC, SEXP nR, SEXP wins, SEXP t) {
+  mb_grid g = grid_of(grid);
+  const int nt = Rf_asInteger(nC) * Rf_asInteger(nR);
+  if (nt < 1 || nt > 4096 || Rf_length(wins) != 4 * nt) Rf_error("machisplin_b200: wins does not match in.ncol x in.nrow");
+  mb_window w[4096], own;
+  wins_of(wins, nt, w);
+  MB_CHECK(mb_tiles_owned_window(&g, Rf_asInteger(nC), Rf_asInteger(nR), w, Rf_asInteger(t), &own));
+  SEXP out = PROTECT(Rf_allocVector(INTSXP, 4));
+  INTEGER(out)[0] = own.r0; INTEGER(out)[1] = own.r1; INTEGER(out)[2] = own.c0; INTEGER(out)[3] = own.c1;
+  UNPROTECT(1);
+  return out;
+}
+
+/* communicator of the context: rank 0 draws the id (raw vector of MB_COMM_ID_BYTES), the R hosts ship it (file, socket), every
+ * rank calls mbR_comm_init.  What the reference's deleted snowfall path did with sockets (old/...V69.R:937-968) */
+SEXP mbR_comm_unique_id(void) {
+  SEXP id = PROTECT(Rf_allocVector(RAWSXP, MB_COMM_ID_BYTES));
+  MB_CHECK(mb_comm_unique_id(RAW(id)));
+  UNPROTECT(1);
+  return id;
+}
+SEXP mbR_comm_init(SEXP ctx, SEXP nranks, SEXP rank, SEXP id) {
+  if (Rf_length(id) != MB_COMM_ID_BYTES) Rf_error("machisplin_b200: the communicator id must have %d bytes", MB_COMM_ID_BYTES);
+  MB_CHECK(mb_comm_init((mb_ctx*)R_ExternalPtrAddr(ctx), Rf_asInteger(nranks), Rf_asInteger(rank), RAW(id)));
+  return R_NilValue;
+}
+/* G = sum over the ranks of R_r' R_r: the objective of V73:329-333 with the cross-validation rows sharded */
+SEXP mbR_gram_allreduce(SEXP ctx, SEXP R) {
+  const int n = Rf_nrows(R), K = Rf_ncols(R);
+  SEXP G = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+  MB_CHECK(mb_gram_allreduce((mb_ctx*)R_ExternalPtrAddr(ctx), REAL(R), n, K, REAL(G)));
+  UNPROTECT(1);
+  return G;
+}
+/* mbR_mltps_predict for THIS rank's row block of a raster sharded over the communicator: grid = the block's extent and shape,
+ * fields::Tps runs on `root` only (knots_xy / resid may be NULL elsewhere; n = number of observations everywhere) */
+SEXP mbR_mltps_predict_shard(SEXP ctx, SEXP grid, SEXP ens, SEXP cov_raw, SEXP C, SEXP knots_xy, SEXP resid, SEXP n, SEXP lambda,
+                             SEXP root) {
+  mb_grid g = grid_of(grid);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)g.nrow * g.ncol));
+  MB_CHECK(mb_mltps_predict_shard((mb_ctx*)R_ExternalPtrAddr(ctx), &g,
+                                  ens == R_NilValue ? NULL : (mb_ensemble*)R_ExternalPtrAddr(ens),
+                                  cov_raw == R_NilValue ? NULL : (const float*)RAW(cov_raw), Rf_asInteger(C),
+                                  knots_xy == R_NilValue ? NULL : REAL(knots_xy), resid == R_NilValue ? NULL : REAL(resid),
+                                  Rf_asInteger(n), Rf_asReal(lambda), Rf_asInteger(root), REAL(out), NULL));
+  UNPROTECT(1);
+  return out;
+}
+

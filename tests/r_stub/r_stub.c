@@ -101,6 +101,8 @@ void stub_finalize(SEXP s) { if (s->type == EXTPTRSXP && s->fin) { R_CFinalizer_
 typedef SEXP (*fn1)(SEXP); typedef SEXP (*fn2)(SEXP, SEXP); typedef SEXP (*fn3)(SEXP, SEXP, SEXP);
 typedef SEXP (*fn4)(SEXP, SEXP, SEXP, SEXP); typedef SEXP (*fn6)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*fn9)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*fn0)(void); typedef SEXP (*fn5)(SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*fn10)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 /* .Call(fn, args...): returns the result, or NULL after an R error (message in stub_last_error) */
 SEXP stub_call(void* fn, int nargs, SEXP* a) {
   g_err[0] = 0;
@@ -109,11 +111,14 @@ SEXP stub_call(void* fn, int nargs, SEXP* a) {
   g_top_set = 1;
   SEXP r = NULL;
   switch (nargs) {
+    case 0: r = ((fn0)fn)(); break;
     case 1: r = ((fn1)fn)(a[0]); break;
     case 2: r = ((fn2)fn)(a[0], a[1]); break;
     case 3: r = ((fn3)fn)(a[0], a[1], a[2]); break;
     case 4: r = ((fn4)fn)(a[0], a[1], a[2], a[3]); break;
+    case 5: r = ((fn5)fn)(a[0], a[1], a[2], a[3], a[4]); break;
     case 6: r = ((fn6)fn)(a[0], a[1], a[2], a[3], a[4], a[5]); break;
+    case 10: r = ((fn10)fn)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]); break;
     case 9: r = ((fn9)fn)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]); break;
     default: snprintf(g_err, sizeof g_err, "stub_call: unsupported arity %d", nargs); r = NULL;
   }

@@ -9,7 +9,8 @@ from tests.rshim_harness import RStub
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 WRAPPERS = ["mbR_init", "mbR_tps_fit", "mbR_tps_eval", "mbR_ensemble_create", "mbR_mltps_predict", "mbR_gram",
-            "mbR_read_stack", "mbR_write_raster"]
+            "mbR_read_stack", "mbR_write_raster", "mbR_tiles_merge", "mbR_tiles_owned_window", "mbR_comm_unique_id", "mbR_comm_init",
+            "mbR_gram_allreduce", "mbR_mltps_predict_shard"]
 
 
 @pytest.fixture(scope="module")
@@ -57,3 +58,20 @@ def test_write_raster_round_trip_and_error_path(rs, tmp_path):
     with pytest.raises(RuntimeError, match="machisplin_b200"):
         rs.call("mbR_write_raster", rs.string("/nonexistent-dir/o.tif"), rs.real([10.0, 17.0, -4.0, 0.0, 40, 70]),
                 rs.real(v.ravel()), rs.integer(0))
+
+
+def test_owned_window_through_the_shim(rs):
+    """mbR_tiles_owned_window needs no GPU: the windows of a 2 x 2 lattice partition the raster."""
+    from machisplin_b200 import synth, tiles as mtiles
+    geom = synth.make_geom(240, 310)
+    ts = mtiles.tiles_create(geom, np.zeros((0, 2)), 2, 2, feather_d=30)
+    wins = np.array([t.win for t in ts.tiles], dtype=np.int32)            # ntiles x 4, row-major = R's 4 x ntiles column-major
+    grid = rs.real([geom.xmin, geom.xmax, geom.ymin, geom.ymax, geom.nrow, geom.ncol])
+    cover = np.zeros((geom.nrow, geom.ncol), dtype=int)
+    for t in range(4):
+        o = rs.as_numpy(rs.call("mbR_tiles_owned_window", grid, rs.integer(2), rs.integer(2), rs.integer(wins.ravel()), rs.integer(t)))
+        cover[o[0]:o[1], o[2]:o[3]] += 1
+    assert np.all(cover == 1)
+    with pytest.raises(RuntimeError, match="machisplin_b200"):
+        rs.call("mbR_tiles_owned_window", grid, rs.integer(2), rs.integer(2), rs.integer(wins.ravel()), rs.integer(4))
+

@@ -119,3 +119,44 @@ def test_dot_c_twins():
     ref = otl.tiles_merge(geom.as_tuple(), [tuple(w) for w in wins], tiles, 2, 2)
     np.testing.assert_allclose(merged, ref, rtol=1e-13, atol=1e-13)
     lib.mbC_shutdown()
+
+
+def test_tiles_merge_and_the_multi_gpu_wrappers(rs, mb):
+    """mbR_tiles_merge against the oracle (V73:1392-1548); mbR_comm_unique_id / mbR_comm_init with one rank, then
+    mbR_gram_allreduce and mbR_mltps_predict_shard - the calls an R process per GPU makes - give what the single-process calls give."""
+    from oracle import tiles as otl
+    geom = synth.make_geom(120, 170)
+    tc = otl.tiles_create(geom.as_tuple(), np.zeros((0, 2)), out_ncol=2, out_nrow=2, feather_d=20)
+    wins = np.array([t["win"] for t in tc["tiles"]], dtype=np.int32)
+    rng = np.random.default_rng(1)
+    tiles = [rng.standard_normal((w[1] - w[0], w[3] - w[2])) for w in wins]
+    lst = rs.named_list({f"t{k}": rs.real(t.ravel()) for k, t in enumerate(tiles)})
+    out = rs.call("mbR_tiles_merge", mb, r_grid(rs, geom), rs.integer(2), rs.integer(2), rs.integer(wins.ravel()), lst)
+    got = rs.as_numpy(out).reshape(geom.nrow, geom.ncol)
+    ref = otl.tiles_merge(geom.as_tuple(), [tuple(w) for w in wins], tiles, 2, 2)
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13)
+    # one-rank communicator through the shim (a second GPU is not needed to exercise the wrappers)
+    ctx2 = rs.call("mbR_init", rs.integer(0))
+    uid = rs.call("mbR_comm_unique_id")
+    assert rs.as_numpy(uid).size == 128
+    rs.call("mbR_comm_init", ctx2, rs.integer(1), rs.integer(0), uid)
+    R = rng.standard_normal((500, 6))
+    G = rs.as_numpy(rs.call("mbR_gram_allreduce", ctx2, rs.real(R, matrix=True)))
+    np.testing.assert_allclose(G, R.T @ R, rtol=1e-12, atol=1e-12)
+    C = 3
+    g2 = synth.make_geom(64, 96)
+    cov = synth.covariate_planes(g2, C)
+    xy, _, _ = synth.make_knots(g2, 150, 2)
+    res = synth.residual_field(xy, 2)
+    models = synth.make_models(g2, C, 300, 2, kept="gnmv")
+    kept, w, wt = om.select_models(np.array([0.4, 0.3, 0.2, 0.1]), letters="gnmv")
+    packed = cov.astype(np.float32).tobytes()
+    ens = rs.call("mbR_ensemble_create", ctx2, r_grid(rs, g2), models_to_r(rs, models, C + 2), rs.string(kept), rs.real(w), rs.real([wt]))
+    a = rs.as_numpy(rs.call("mbR_mltps_predict_shard", ctx2, r_grid(rs, g2), ens, rs.raw(packed), rs.integer(C), rs.real(xy, matrix=True),
+                            rs.real(res), rs.integer(len(res)), rs.real([-1.0]), rs.integer(0)))
+    b = rs.as_numpy(rs.call("mbR_mltps_predict", ctx2, r_grid(rs, g2), ens, rs.raw(packed), rs.integer(C), rs.real(xy, matrix=True),
+                            rs.real(res), rs.real([-1.0]), rs.integer(0)))
+    np.testing.assert_array_equal(a, b)
+    rs.finalize(ens)
+    rs.finalize(ctx2)
+
