@@ -13,6 +13,28 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libmachisplin_b200.so"
 
 
+def _pin_nccl():
+    """One NCCL per process.  The library binds NCCL with dlopen at the first collective; a Python host usually also runs torch,
+    whose libtorch_cuda.so NEEDS the libnccl.so.2 bundled with it (nvidia/nccl).  If the library mapped the SYSTEM copy first
+    (older, same SONAME), a later ``import torch`` would resolve against that copy and fail on a missing symbol - so, unless the
+    user chose a library, point MB_NCCL_LIB at the copy torch will load (found without importing torch)."""
+    if os.environ.get("MB_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["MB_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
+_pin_nccl()
+
+
 class MbError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"machisplin_b200 error {code}: {msg}")

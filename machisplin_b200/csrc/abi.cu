@@ -799,10 +799,21 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
       surface = surf;
     }
   }
-  if (heavy) MB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-  // parts 3-5: TPS surface + smooth models + combine, one pass over the grid
+  // parts 3-5: TPS surface + smooth models + combine, one pass over the grid.  With a spline the join of the ensemble stream is
+  // deferred to the point where the fast evaluator launches its grid-evaluation kernel (its far-field set-up needs the spline only)
+  if (heavy && e && sp) ctx->leaf_wait = ctx->ev_join;
+  else if (heavy) MB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
   if (e) {
-    ensemble_finish(ctx, e, sp.get(), surface, full, acc, out, st);
+    try {
+      ensemble_finish(ctx, e, sp.get(), surface, full, acc, out, st);
+    } catch (...) {
+      ctx->leaf_wait = nullptr;
+      throw;
+    }
+    if (ctx->leaf_wait) {            // not consumed (cannot happen with a spline; defensive): wait here
+      MB_CUDA(cudaStreamWaitEvent(st, ctx->leaf_wait, 0));
+      ctx->leaf_wait = nullptr;
+    }
   } else if (sp) {
     tps_eval_fast(ctx, sp.get(), g, full, out, g.ncol, st);
   } else if (surface) {

@@ -217,6 +217,7 @@ struct mb_ctx {
                               // warps per sweep (96 x 160 registers: the smallest footprint beside a per-cell kernel), 3 = tagged elements
                               // (LL protocol: no flags, no fences; 3 compute + 4 loader warps), 0 = 3 for a fit that has the GPU to
                               // itself, 2 when the ensemble kernels run beside it
+  cudaEvent_t leaf_wait = nullptr;   // consumed by the fast evaluator right before its grid-evaluation kernel (tps_eval.cu)
   bool fit_shares_gpu = false;  // set by mb_mltps_predict* around its fit
   int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers
   int sbr_qr_grid = 0;        // two-stage path: 1 = panel QR through the software grid barrier even where a cluster fits

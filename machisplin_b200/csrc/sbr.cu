@@ -1229,7 +1229,7 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // ---------------------------------------------------------------------------------------------
 // Coefficients from the band form ("coef_impl" = 1; experimental, see DESIGN.md section 9 and tools/proto_two_stage.py
 // coefficients_from_band):  (M + lam I)^-1 z = Q1 (B + lam I)^-1 Q1'z.
-// k_band_solve: ONE warp.  Block Cholesky of B + lam I with 32 x 32 blocks (lane = row; diagonal block potrf, its inverse,
+// k_band_solve: ONE CTA.  Block Cholesky of B + lam I with 32 x 32 blocks (diagonal block potrf, its inverse,
 // L_{j+1,j} = A_{j+1,j} L_jj^-T, next diagonal block -= L_{j+1,j} L_{j+1,j}'), factors kept in global memory, then forward and
 // backward substitution of one right-hand side as 32 x 32 matrix-vector products.  O(m b^2) flops, m / 32 dependent steps.
 // ---------------------------------------------------------------------------------------------
@@ -1240,21 +1240,27 @@ struct BandSolveArgs {
   int* err;                        // set to 1 if a pivot is not positive
 };
 
-__global__ void __launch_bounds__(32) k_band_solve(BandSolveArgs a) {
+// One CTA of 8 warps.  The sequential part of a block step - potrf of the 32 x 32 diagonal block and the inverse of its factor -
+// stays on warp 0 (fully unrolled, predicated: the shared-memory operands of the dependent FMA chains are in flight ahead of
+// them); the two 32 x 32 x 32 products (L_{j+1,j} = A_{j+1,j} L_jj^-T, next diagonal block -= L_{j+1,j} L_{j+1,j}') and all
+// block loads / stores are spread over the 256 threads (thread = row x 4 columns).  Every output element is still ONE fma
+// chain in ascending k, so the factors are bit-identical to the one-warp kernel of r2a (9.4 ms at 5 000 knots).
+constexpr int kBandThreads = 256;
+__global__ void __launch_bounds__(kBandThreads) k_band_solve(BandSolveArgs a) {
   __shared__ double B0[32][kPad], B1[32][kPad], B2[32][kPad];
   __shared__ double xs[32], tv[32], xn[32];
-  const int l = threadIdx.x, m = a.m;
+  const int tid = threadIdx.x, l = tid & 31, wq = (tid >> 5) * 4, m = a.m;      // this thread: row l, columns wq .. wq + 3
   constexpr int b = 32;
   const int nb = (m + b - 1) / b;
   double (*D)[kPad] = B0;          // current diagonal block / its Cholesky factor, then L_{j+1,j}
   double (*S)[kPad] = B1;          // sub-diagonal block, then the next diagonal block
   double (*Li)[kPad] = B2;         // inverse of the diagonal factor
-  // diagonal block J of B + lam I, lower part, identity padding past m
+  // diagonal block J of B + lam I, lower part, identity padding past m (this thread's 4 elements)
   auto load_diag = [&](double (*dst)[kPad], int J) {
     const int i = J * b + l;
-#pragma unroll 8
-    for (int q = 0; q < 32; ++q) {
-      const int j = J * b + q;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int q = wq + qq, j = J * b + q;
       double v = 0.0;
       if (q <= l) {
         if (i < m) v = __ldcg(a.Bd + (i - j) + (size_t)j * kLdb) + (q == l ? a.lam : 0.0);
@@ -1264,101 +1270,144 @@ __global__ void __launch_bounds__(32) k_band_solve(BandSolveArgs a) {
     }
   };
   load_diag(D, 0);
+  __syncthreads();
   for (int j = 0; j < nb; ++j) {
-    // ---- D = L L' in place (lower), lane = row ----------------------------------------------------------------
-    for (int c = 0; c < 32; ++c) {
-      __syncwarp();
-      const double dcc = D[c][c];
-      if (!(dcc > 0.0) && l == 0) *a.err = 1;
-      const double dd = sqrt(dcc > 0.0 ? dcc : 1.0);
-      const double lic = l > c ? D[l][c] / dd : 0.0;
-      __syncwarp();
-      if (l == c) D[c][c] = dd;
-      else if (l > c) D[l][c] = lic;
-      __syncwarp();
-      for (int q = c + 1; q <= l; ++q) D[l][q] -= lic * D[q][c];
-    }
-    __syncwarp();
-    // ---- Li = L^-1, lane = column --------------------------------------------------------------------------------
-    for (int i = 0; i < 32; ++i) {
-      double sacc = 0.0;
-      if (i >= l) {
-        sacc = i == l ? 1.0 : 0.0;
-        for (int k = l; k < i; ++k) sacc -= D[i][k] * Li[k][l];
-        sacc /= D[i][i];
+    if (tid < 32) {
+      // ---- D = L L' in place (lower), lane = row ----------------------------------------------------------------
+      for (int c = 0; c < 32; ++c) {
+        __syncwarp();
+        const double dcc = D[c][c];
+        if (!(dcc > 0.0) && l == 0) *a.err = 1;
+        const double dd = sqrt(dcc > 0.0 ? dcc : 1.0);
+        const double lic = l > c ? D[l][c] / dd : 0.0;
+        __syncwarp();
+        if (l == c) D[c][c] = dd;
+        else if (l > c) D[l][c] = lic;
+        __syncwarp();
+#pragma unroll
+        for (int q = 1; q < 32; ++q)
+          if (q > c && q <= l) D[l][q] -= lic * D[q][c];
       }
-      Li[i][l] = sacc;
+      __syncwarp();
+      // ---- Li = L^-1, lane = column --------------------------------------------------------------------------------
+      for (int i = 0; i < 32; ++i) {
+        double sacc = 0.0;
+        if (i >= l) {
+          sacc = i == l ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < 31; ++k)
+            if (k >= l && k < i) sacc -= D[i][k] * Li[k][l];
+          sacc /= D[i][i];
+        }
+        Li[i][l] = sacc;
+      }
     }
-    __syncwarp();
+    __syncthreads();
     double* fj = a.fac + (size_t)j * 2048;
-    for (int i = 0; i < 32; ++i) fj[i * 32 + l] = Li[i][l];
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) fj[l * 32 + wq + qq] = Li[l][wq + qq];
     if (j + 1 < nb) {
       // ---- S = A_{j+1,j}: rows (j+1) b + l, columns j b + q, inside the band for l <= q -------------------------
       {
         const int i = (j + 1) * b + l;
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q) {
-          const int jj = j * b + q;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int q = wq + qq, jj = j * b + q;
           S[l][q] = (l <= q && i < m) ? __ldcg(a.Bd + (i - jj) + (size_t)jj * kLdb) : 0.0;
         }
       }
-      __syncwarp();
-      // ---- Ls = S Li' (into D: the factor itself is not needed any more), lane = row -------------------------------
-      for (int c = 0; c < 32; ++c) {
-        double sacc = 0.0;
-        for (int k = 0; k <= c; ++k) sacc = fma(S[l][k], Li[c][k], sacc);
-        D[l][c] = sacc;
+      __syncthreads();
+      // ---- Ls = S Li' (into D: the factor itself is not needed any more) -----------------------------------------
+      {
+        double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const double sv = S[l][k];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            if (k <= wq + qq) acc4[qq] = fma(sv, Li[wq + qq][k], acc4[qq]);
+        }
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) D[l][wq + qq] = acc4[qq];
       }
-      __syncwarp();
-      for (int i = 0; i < 32; ++i) fj[1024 + i * 32 + l] = D[i][l];
-      // ---- next diagonal block = A_{j+1,j+1} + lam I - Ls Ls' (into S), lane = row ----------------------------------
+      __syncthreads();
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) fj[1024 + l * 32 + wq + qq] = D[l][wq + qq];
+      // ---- next diagonal block = A_{j+1,j+1} + lam I - Ls Ls' (into S) ---------------------------------------------
       load_diag(S, j + 1);
-      __syncwarp();
-      for (int q = 0; q <= l; ++q) {
-        double sacc = 0.0;
-        for (int k = 0; k < 32; ++k) sacc = fma(D[l][k], D[q][k], sacc);
-        S[l][q] -= sacc;
+      {
+        double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const double dv = D[l][k];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) acc4[qq] = fma(dv, D[wq + qq][k], acc4[qq]);
+        }
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+          if (wq + qq <= l) S[l][wq + qq] -= acc4[qq];
       }
-      __syncwarp();
+      __syncthreads();
       double (*tmp)[kPad] = D; D = S; S = tmp;
     }
   }
-  __syncwarp();
+  __syncthreads();
   __threadfence_block();
   // ---- forward substitution: t = Linv_j x_j ; x_{j+1} -= Ls_j t ---------------------------------------------------
   for (int j = 0; j < nb; ++j) {
     const double* fj = a.fac + (size_t)j * 2048;
-    for (int i = 0; i < 32; ++i) { Li[i][l] = fj[i * 32 + l]; if (j + 1 < nb) S[i][l] = fj[1024 + i * 32 + l]; }
-    xs[l] = a.x[j * b + l];
-    __syncwarp();
-    double t = 0.0;
-    for (int k = 0; k <= l; ++k) t = fma(Li[l][k], xs[k], t);
-    tv[l] = t;
-    a.x[j * b + l] = t;
-    __syncwarp();
-    if (j + 1 < nb) {
-      double u = 0.0;
-      for (int k = 0; k < 32; ++k) u = fma(S[l][k], tv[k], u);
-      a.x[(j + 1) * b + l] -= u;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      Li[l][wq + qq] = fj[l * 32 + wq + qq];
+      if (j + 1 < nb) S[l][wq + qq] = fj[1024 + l * 32 + wq + qq];
     }
-    __syncwarp();
+    if (tid < 32) xs[l] = a.x[j * b + l];
+    __syncthreads();
+    if (tid < 32) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k <= l) t = fma(Li[l][k], xs[k], t);
+      tv[l] = t;
+      a.x[j * b + l] = t;
+      __syncwarp();
+      if (j + 1 < nb) {
+        double u = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) u = fma(S[l][k], tv[k], u);
+        a.x[(j + 1) * b + l] -= u;
+      }
+    }
+    __syncthreads();
   }
   // ---- backward substitution: x_j -= Ls_j' x_{j+1} ; x_j = Linv_j' x_j ------------------------------------------------
   for (int j = nb - 1; j >= 0; --j) {
     const double* fj = a.fac + (size_t)j * 2048;
-    for (int i = 0; i < 32; ++i) { Li[i][l] = fj[i * 32 + l]; if (j + 1 < nb) S[i][l] = fj[1024 + i * 32 + l]; }
-    xs[l] = a.x[j * b + l];
-    xn[l] = j + 1 < nb ? a.x[(j + 1) * b + l] : 0.0;
-    __syncwarp();
-    double v = xs[l];
-    if (j + 1 < nb)
-      for (int k = 0; k < 32; ++k) v = fma(-S[k][l], xn[k], v);
-    tv[l] = v;
-    __syncwarp();
-    double t = 0.0;
-    for (int k = l; k < 32; ++k) t = fma(Li[k][l], tv[k], t);
-    a.x[j * b + l] = t;
-    __syncwarp();
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      Li[l][wq + qq] = fj[l * 32 + wq + qq];
+      if (j + 1 < nb) S[l][wq + qq] = fj[1024 + l * 32 + wq + qq];
+    }
+    if (tid < 32) {
+      xs[l] = a.x[j * b + l];
+      xn[l] = j + 1 < nb ? a.x[(j + 1) * b + l] : 0.0;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      double v = xs[l];
+      if (j + 1 < nb) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v = fma(-S[k][l], xn[k], v);
+      }
+      tv[l] = v;
+      __syncwarp();
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k >= l) t = fma(Li[k][l], tv[k], t);
+      a.x[j * b + l] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -1457,7 +1506,7 @@ bool band_coefficients(mb_ctx* ctx, double lambda, int rhs, double* out_dev, cud
   MB_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
   MB_CUDA(cudaMemcpyAsync(x, bf.z1 + (size_t)rhs * m, sizeof(double) * m, cudaMemcpyDeviceToDevice, st));
   BandSolveArgs sa{bf.band, m, lambda, fac, x, err};
-  MB_LAUNCH(ctx, "k_band_solve", st) k_band_solve<<<1, 32, 0, st>>>(sa);
+  MB_LAUNCH(ctx, "k_band_solve", st) k_band_solve<<<1, kBandThreads, 0, st>>>(sa);
   if (bf.npanel > 0) {
     std::vector<unsigned long long> voff(bf.voff.begin(), bf.voff.end());
     ApplyQ1Args qa{bf.Vall, bf.Tall, ar.upload(voff.data(), voff.size(), st), ar.upload(bf.r.data(), bf.r.size(), st),
@@ -1598,6 +1647,8 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
       nsplit = ceil_div(r, chunk);
       if (pk > 0) MB_CUDA(cudaStreamWaitEvent(st, ctx->sbr_ev[2 + ((pk - 1) & 1)], 0));      // trailing update of panel k - 1
       MB_LAUNCH(ctx, "k_sbr_av", st) k_sbr_av<<<dim3(rblocks, nsplit), 128, 0, st>>>(A22, ld, r, V, ldv, Zp, chunk);
+      // (vtz + st and w + pu as two fused launches were measured in r2q: 36 + 36 us per panel against 24 + 13 + 14 + 24 -
+      //  the last-CTA epilogue and the recomputed W rows cost what the two launches save; deleted)
       MB_LAUNCH(ctx, "k_sbr_vtz", st)
         k_sbr_vtz<<<rblocks, 512, kVtzSmem, st>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
       MB_LAUNCH(ctx, "k_sbr_st", st) k_sbr_st<<<1, 1024, 0, st>>>(Gp, rblocks, Tk, ST);

@@ -905,6 +905,13 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
     MB_CUDA(cudaGetLastError());
   }
   const AccFuse fz = fuse ? *fuse : AccFuse{nullptr, 0, 0.0};
+  // Everything above depends on the spline alone; only the kernels below read the ensemble accumulator.  mb_mltps_predict* hands
+  // the join of its ensemble stream over here (instead of waiting for it before the far-field set-up), so that the ~1.5 ms of
+  // k_far_p2l / k_far_transform / k_leaf_prep run beside the last ensemble kernel.
+  if (ctx->leaf_wait) {
+    MB_CUDA(cudaStreamWaitEvent(st, ctx->leaf_wait, 0));
+    ctx->leaf_wait = nullptr;
+  }
   if (thr > 0) {
     const size_t smem = (size_t)kLeafStages * leaf_stage_bytes(P, lat.bh, fuse != nullptr) +
                         2 * (size_t)lat.bh * (sizeof(double) + leaf_gfs(P) * sizeof(float));
