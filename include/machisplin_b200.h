@@ -273,6 +273,10 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * "ens_overlap" = 2 (default) the forest kernel, then the tensor-pipe ksvm kernel; 1 side by side on two streams when both are
  * kept (measured slower); "svm_ctas_per_sm" = persistent grid of the ksvm kernel in that mode (default 2); "ens_tma" = 1 (default)
  * covariate tiles of the ksvm kernel by TMA tensor copies (cp.async.bulk.tensor), 2 plain loads;
+ * "gc_split" = SM count of the fit partition when mb_mltps_predict* splits the device with CUDA green contexts (stage 1 of the GCV fit
+ * on one partition, the forest kernel on the other from the start; 0 = default 72, -1 = no partitions: the ensemble waits for stage 1;
+ * the partitions are created once per context, with the size in force at the first call that uses them); "gc_share" = percent of
+ * the raster's rows whose forest kernel runs on the ensemble partition beside stage 1, the rest follows on all SMs (0 = default = all rows);
  * "leaf_tma" = 1 (default) the grid-evaluation kernel fetches the accumulator tile of a box with one 2-D tensor copy, 2 row by row;
  * "ens_order" = 1 (default) the forest kernel runs before the ksvm kernel, 2 after it;
  * "tree_levels" = 1 forest kernel with the CTA-level interval prune only, 2 (default) + the warp-level prune;
@@ -289,6 +293,7 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * (every double travels as two 8-byte words carrying the number of the sweep that wrote it: no flags, no fences), 0 (default) = 3
  * for a fit that has the GPU to itself and 2 inside mb_mltps_predict* with an ensemble (smallest register footprint beside the
  * per-cell kernels); all three are bit-identical;
+ * "sbr_chase_ctas" = cap of the bulge chase's grid (0 = one CTA per sweep that can be in flight);
  * "sbr_chase_sleep" = nanoseconds of back-off in the spin loops of the chase (0 = none; measured: no effect);
  * "defer_ensemble" = 0 starts the per-cell ensemble kernels of mb_mltps_predict* before the fit instead of behind stage 1
  * of its tridiagonalisation; "eigen_impl" = 1 routes the GCV fit through cuSOLVER Dsyevd (validation of the in-house path only). */

@@ -11,7 +11,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libmachisplin_b200.so"
-SOURCES = ["abi.cu", "tps_eval.cu", "tps_fit.cu", "sytrd.cu", "sbr.cu", "ensemble.cu", "tiles.cu", "tiff_io.cu", "comm.cu", "abi_dotc.cu"]
+SOURCES = ["abi.cu", "tps_eval.cu", "tps_fit.cu", "sytrd.cu", "sbr.cu", "ensemble.cu", "tiles.cu", "tiff_io.cu", "comm.cu", "abi_dotc.cu", "greenctx.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

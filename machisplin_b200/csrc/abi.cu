@@ -162,6 +162,7 @@ void mb_shutdown(mb_ctx* ctx) {
   if (ctx->ev_stage1) cudaEventDestroy(ctx->ev_stage1);
   for (cudaEvent_t ev : ctx->sbr_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->sbr_aux) cudaStreamDestroy(ctx->sbr_aux);
+  greenctx_release(ctx);
   for (cudaEvent_t ev : ctx->ev_ens) if (ev) cudaEventDestroy(ev);
   if (ctx->ens_aux) cudaStreamDestroy(ctx->ens_aux);
   if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -260,6 +261,12 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
     if (n == "ens_overlap") {
       MB_REQUIRE(value >= 0 && value <= 2, "ens_overlap must be 0 (default = 2), 1 (forest and ksvm kernels side by side) or 2 (one after the other)");
       ctx->ens_overlap = value;
+    } else if (n == "gc_split") {
+      MB_REQUIRE(value >= -1 && value <= 1024, "gc_split must be -1 (no SM partitions), 0 (default) or the SM count of the fit partition");
+      ctx->gc_split = value;
+    } else if (n == "gc_share") {
+      MB_REQUIRE(value >= 0 && value <= 100, "gc_share must be 0 (default) or a percentage of the raster's rows");
+      ctx->gc_share = value;
     } else if (n == "leaf_tma") {
       MB_REQUIRE(value >= 0 && value <= 2, "leaf_tma must be 0 (default = 1), 1 (2-D tensor copy of the accumulator tile) or 2 (row copies)");
       ctx->leaf_tma = value;
@@ -282,11 +289,14 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 3,
                  "sytrd_mode must be 0 (default = two-stage), 1 (one-stage persistent kernel), 2 (one-stage, kernel per phase) or 3 (two-stage)");
       ctx->sytrd_mode = value;
+    } else if (n == "sbr_chase_ctas") {
+      MB_REQUIRE(value >= 0 && value <= 4096, "sbr_chase_ctas must be in [0, 4096]");
+      ctx->sbr_chase_ctas = value;
     } else if (n == "sbr_chase_sleep") {
       MB_REQUIRE(value >= -1 && value <= 100000, "sbr_chase_sleep must be in [-1, 100000] nanoseconds");
       ctx->sbr_chase_sleep = value;
     } else if (n == "sbr_chase_impl") {
-      MB_REQUIRE(value >= 0 && value <= 3, "sbr_chase_impl must be 0 (automatic), 1 (watcher / publisher warps), 2 (three warps per sweep) or 3 (tagged elements, no flags)");
+      MB_REQUIRE(value >= 0 && value <= 4, "sbr_chase_impl must be 0 (automatic), 1 (watcher / publisher warps), 2 (three warps per sweep), 3 (tagged elements, no flags) or 4 (3 with capped registers)");
       ctx->sbr_chase_impl = value;
     } else if (n == "coef_impl") {
       MB_REQUIRE(value >= 0 && value <= 2, "coef_impl must be 0 (band form when well conditioned), 1 (band form whenever it exists) or 2 (dense Cholesky)");
@@ -743,6 +753,40 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
       }
     }
   }
+  // SM partitions (greenctx.cu): with a forest kernel in the chain and a fit large enough to have a stage 1 worth the name, the
+  // forest kernel starts NOW on the ensemble partition while stage 1 runs on the fit partition; what follows the forest kernel
+  // (ksvm + smooth models) is deferred behind stage 1 as before, on all SMs.
+  const bool use_gc = defer && ctx->gc_split >= 0 && n >= 1500 && ensemble_has_forest_kernel(e) &&
+                      greenctx_setup(ctx, ctx->gc_split > 0 ? ctx->gc_split : 72);
+  // rows [lo, hi) of the raster, in the row blocks the covariates travel in (host-buffer entry point) or in one piece
+  auto accumulate = [&](cudaStream_t s, int part, int lo, int hi) {
+    if (hi <= lo) return;
+    if (nblk_copy > 0) {
+      int b = 0;
+      for (int r0 = 0; r0 < g.nrow; r0 += rows_per, ++b) {
+        const int r1 = std::min(g.nrow, r0 + rows_per);
+        const int a0 = std::max(r0, lo), a1 = std::min(r1, hi);
+        if (a1 <= a0) continue;
+        MB_CUDA(cudaStreamWaitEvent(s, ctx->ev_blocks[b], 0));
+        const mb_window wb{a0, a1, 0, g.ncol};
+        ensemble_accumulate(ctx, e, cov, C, wb, acc + (int64_t)a0 * acc_stride(full), s, part);
+      }
+    } else {
+      const mb_window wb{lo, hi, 0, g.ncol};
+      ensemble_accumulate(ctx, e, cov, C, wb, acc + (int64_t)lo * acc_stride(full), s, part);
+    }
+  };
+  // the forest kernel's rows that run on the ensemble partition beside stage 1 (the rest follows on all SMs): sized so that the
+  // partition is done when stage 1 is ("gc_share" percent of the rows; multiples of the 8-row forest tiles)
+  int rows_gc = 0;
+  if (use_gc) {
+    const int share = ctx->gc_share > 0 ? ctx->gc_share : 100;    // measured flat between 78 and 100 (profiles/r2u_*)
+    rows_gc = share >= 100 ? g.nrow : std::min(g.nrow, (int)((int64_t)g.nrow * share / 100) / 64 * 64);
+    ctx->arena.also_used(ctx->gc_ens_stream);
+    MB_CUDA(cudaStreamWaitEvent(ctx->gc_ens_stream, ctx->ev_fork, 0));
+    accumulate(ctx->gc_ens_stream, 1, 0, rows_gc);
+    MB_CUDA(cudaEventRecord(ctx->gc_ev[2], ctx->gc_ens_stream));
+  }
   bool launched = false;
   auto launch_ensemble = [&](bool after_stage1) {
     if (launched || !heavy) return;
@@ -751,16 +795,12 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
       MB_CUDA(cudaEventRecord(ctx->ev_stage1, ctx->stream));
       MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_stage1, 0));
     }
-    if (nblk_copy > 0) {
-      int b = 0;
-      for (int r0 = 0; r0 < g.nrow; r0 += rows_per, ++b) {
-        const int r1 = std::min(g.nrow, r0 + rows_per);
-        MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_blocks[b], 0));
-        const mb_window wb{r0, r1, 0, g.ncol};
-        ensemble_accumulate(ctx, e, cov, C, wb, acc + (int64_t)r0 * acc_stride(full), ctx->side);
-      }
+    if (use_gc) {
+      accumulate(ctx->side, 1, rows_gc, g.nrow);                      // the forest kernel's remaining rows, all SMs
+      MB_CUDA(cudaStreamWaitEvent(ctx->side, ctx->gc_ev[2], 0));
+      accumulate(ctx->side, 2, 0, g.nrow);
     } else {
-      ensemble_accumulate(ctx, e, cov, C, full, acc, ctx->side);
+      accumulate(ctx->side, 0, 0, g.nrow);
     }
     MB_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   };
@@ -776,15 +816,18 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
       if (fit_here) {
         if (defer) ctx->after_stage1 = [&] { launch_ensemble(true); };
         ctx->fit_shares_gpu = heavy;     // the bulge chase picks its small-footprint variant (sbr.cu)
+        ctx->gc_stage1 = use_gc;         // stage 1 of the tridiagonalisation on the fit partition
         try {
           tps_fit(ctx, knots_xy, resid, n, 1, lambda, &raw);
         } catch (...) {
           ctx->after_stage1 = nullptr;
           ctx->fit_shares_gpu = false;
+          ctx->gc_stage1 = false;
           throw;
         }
         ctx->after_stage1 = nullptr;
         ctx->fit_shares_gpu = false;
+        ctx->gc_stage1 = false;
         sp.reset(raw);
         launch_ensemble(false);        // not reached through the hook (e.g. a fit small enough to skip stage 1 entirely)
         if (sharded) spline_bcast(ctx, sp.get(), n, bcast_root);

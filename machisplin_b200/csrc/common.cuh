@@ -212,11 +212,21 @@ struct mb_ctx {
                               // back-transformation by the stored panel reflectors) when cond(M + lambda I) <= 1e8, else dense Cholesky;
                               // 1 = band form whenever it exists, 2 = always the dense Cholesky of M + lambda I
   mb_band_form band_form;
+  int sbr_chase_ctas = 0;     // cap of the bulge chase's grid (0 = one CTA per sweep that can be in flight)
   int sbr_chase_sleep = 0;    // nanoseconds the spinning lanes of the bulge chase sleep between polls (-1 = none)
   int sbr_chase_impl = 0;     // bulge chase: 1 = three warps per sweep + watcher and publisher warps (flags + one fence per step), 2 = three
                               // warps per sweep (96 x 160 registers: the smallest footprint beside a per-cell kernel), 3 = tagged elements
                               // (LL protocol: no flags, no fences; 3 compute + 4 loader warps), 0 = 3 for a fit that has the GPU to
                               // itself, 2 when the ensemble kernels run beside it
+  // SM partitions (greenctx.cu): stage 1 of the fit on one, the forest kernel on the other, inside mb_mltps_predict*
+  bool gc_tried = false, gc_ok = false;
+  void* gc_fit = nullptr;  void* gc_ens = nullptr;                 // CUgreenCtx
+  cudaStream_t gc_fit_stream = nullptr, gc_fit_aux = nullptr, gc_ens_stream = nullptr;
+  int gc_fit_sms = 0, gc_ens_sms = 0;
+  cudaEvent_t gc_ev[4] = {nullptr, nullptr, nullptr, nullptr};     // 0 fork to the fit partition, 1 its join, 2 forest kernels done, 3 spare
+  int gc_split = 0;           // "gc_split": SMs of the fit partition (0 = default 72, -1 = no partitions: deferred ensemble)
+  int gc_share = 0;           // "gc_share": percent of the raster's rows whose forest kernel runs on the ensemble partition (0 = default)
+  bool gc_stage1 = false;     // set by mb_mltps_predict* around its fit: stage 1 of the tridiagonalisation runs on the fit partition
   cudaEvent_t leaf_wait = nullptr;   // consumed by the fast evaluator right before its grid-evaluation kernel (tps_eval.cu)
   bool fit_shares_gpu = false;  // set by mb_mltps_predict* around its fit
   int sbr_qr_impl = 0;        // two-stage path, panel QR: 0 = by cluster size, 1 = panel rows in shared memory, 2 = in registers

@@ -885,6 +885,7 @@ void ensemble_free(mb_ensemble* e) {
 }
 
 mb_grid ensemble_grid(const mb_ensemble* e) { return e->g; }
+bool ensemble_has_forest_kernel(const mb_ensemble* e) { return (e->has[MB_R] || e->has[MB_B]) && !e->only_gbm; }
 int ensemble_ncov(const mb_ensemble* e) { return e->C; }
 
 static SmoothParams smooth_params(const mb_ensemble* e) {
@@ -1183,14 +1184,19 @@ static EnsGeom ens_geom(const mb_grid& g) {
 // acc <- sum_k round(w_k, 2) f_k(cell) over EVERY kept model for window w, in the padded accumulator layout
 // (acc_stride(w) x acc_rows(w) doubles); NaN where a covariate is NA (except a gbm-only ensemble, which
 // follows MissingNode).  Chain: trees -> svm (+ smooth models) | smooth; the last kernel applies the NA rule.
+// part: 0 = the whole chain; 1 = the forest kernel only (it opens the chain: stores); 2 = what follows the forest kernel (adds).
+// mb_mltps_predict* with SM partitions runs part 1 on the ensemble partition beside stage 1 of the fit and part 2 afterwards.
 void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, int C, const mb_window& w, double* acc,
-                         cudaStream_t st) {
+                         cudaStream_t st, int part) {
   const mb_grid& g = e->g;
   const int64_t plane = (int64_t)g.nrow * g.ncol;
   const int64_t astride = acc_stride(w);
   const EnsGeom eg = ens_geom(g);
   bool started = false;
-  if (e->has[MB_R] || e->has[MB_B]) {
+  if ((e->has[MB_R] || e->has[MB_B]) && part == 2) {
+    if (e->only_gbm) return;
+    started = true;                           // the forest kernel has run (part 1)
+  } else if (e->has[MB_R] || e->has[MB_B]) {
     const int n_rf = e->has[MB_R] ? e->rf.ntrees : 0, n_gb = e->has[MB_B] ? e->gbm.ntrees : 0;
     const int* roots = e->forest_roots.p;   // rf trees first (if kept), then gbm
     if (e->only_gbm) {
@@ -1205,7 +1211,7 @@ void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
     // "ens_overlap" = 1 (A/B measurements; NOT the default - measured 139 ms against 83 ms one after the other on config 3,
     // profiles/r2e_ens_check.txt: the persistent ksvm CTAs need 4 per SM to hide the MUFU latency, which leaves the forest kernel
     // nothing): the two kernels side by side, each adding its sum to the zeroed accumulator with RED.ADD.F64
-    const bool overlap = e->has[MB_V] && e->svm_oct > 0 && ctx->ens_overlap == 1;
+    const bool overlap = e->has[MB_V] && e->svm_oct > 0 && ctx->ens_overlap == 1 && part == 0;
     if (overlap) {
       if (!ctx->ens_aux) {
         int prio_lo = 0, prio_hi = 0;
@@ -1226,7 +1232,7 @@ void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
     // "ens_order" = 2: the ksvm kernel first, the forest kernel second (default: the other way round).  Inside mb_mltps_predict the
     // first kernel runs beside the bulge chase of the fit, whose CTAs take registers from it on 80 SMs (sbr.cu); measured on config 3
     // with the small-footprint chase: forests first 140.2 ms / step, ksvm first 142.4 (profiles/r2n_*).
-    if (e->has[MB_V] && e->svm_oct > 0 && ctx->ens_order == 2) {
+    if (e->has[MB_V] && e->svm_oct > 0 && ctx->ens_order == 2 && part == 0) {
       launch_svm_tma(ctx, e, cov, plane, eg, w, acc, /*epilogue=*/0, /*chunked=*/true, st);
       launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, 1, st);
       MB_CUDA(cudaGetLastError());
@@ -1234,6 +1240,10 @@ void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov, in
     }
     launch_trees(ctx, e, cov, C, plane, eg, w, roots, n_rf, n_gb, acc, 0, st);
     started = true;
+  }
+  if (part == 1) {
+    MB_CUDA(cudaGetLastError());
+    return;
   }
   if (e->has[MB_V] && e->svm_oct > 0) {           // the handle was created for the tensor-pipe kernel (P <= 8, svm_impl != 2)
     launch_svm_tma(ctx, e, cov, plane, eg, w, acc, started ? 1 : 0, /*chunked=*/true, st);

@@ -31,10 +31,15 @@ void ensemble_eval(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int 
 int ensemble_ncov(const mb_ensemble* e);
 // acc: padded accumulator layout (AccFuse, common.cuh): acc_stride(w) * acc_rows(w) doubles
 void ensemble_accumulate(mb_ctx* ctx, const mb_ensemble* e, const float* cov_dev, int C, const mb_window& w,
-                         double* acc, cudaStream_t st);
+                         double* acc, cudaStream_t st, int part = 0);
+bool ensemble_has_forest_kernel(const mb_ensemble* e);   // a forest kernel opens the chain and something follows it
 void ensemble_finish(mb_ctx* ctx, const mb_ensemble* e, const mb_spline* spline, const double* tps_surface_dev,
                      const mb_window& w, const double* acc, double* out_dev, cudaStream_t st);
 void ensemble_predict_points(mb_ctx* ctx, const mb_ensemble* e, const double* X, int n, double* out_host);
+
+// greenctx.cu - SM partitions for the fit / ensemble overlap of mb_mltps_predict*
+bool greenctx_setup(mb_ctx* ctx, int fit_sms);
+void greenctx_release(mb_ctx* ctx);
 
 // comm.cu - NCCL communicator of the context; every collective of the path
 void comm_release(mb_ctx* ctx);

@@ -1008,7 +1008,9 @@ constexpr int kLLCompute = 96, kLLLoaders = 128, kLLThreads = kLLCompute + kLLLo
 __device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__global__ void __launch_bounds__(kLLThreads) k_sbr_chase_ll(ChaseLLArgs a) {
+// kMinCtas = 2 caps the registers at 146 per thread (some spills): half the footprint beside a co-resident per-cell kernel
+template <int kMinCtas>
+__global__ void __launch_bounds__(kLLThreads, kMinCtas) k_sbr_chase_ll(ChaseLLArgs a) {
   __shared__ double Bs[2][32][kPad], Ds[2][32][kPad], zs[32][kPad];
   __shared__ double vs[32], ws[32], vps[32], ts[32];
   __shared__ double sh_tau;
@@ -1604,6 +1606,36 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
       for (cudaEvent_t& ev : ctx->sbr_ev) MB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
     cudaStream_t aux = ctx->sbr_aux;
+    // inside mb_mltps_predict* with SM partitions (greenctx.cu): stage 1 runs on the streams of the FIT partition
+    cudaStream_t s1 = st;
+    const bool gc = ctx->gc_stage1 && ctx->gc_ok;
+    int cluster_limit = max_cluster;
+    if (gc) {
+      MB_CUDA(cudaEventRecord(ctx->gc_ev[0], st));
+      MB_CUDA(cudaStreamWaitEvent(ctx->gc_fit_stream, ctx->gc_ev[0], 0));
+      s1 = ctx->gc_fit_stream;
+      aux = ctx->gc_fit_aux;
+      ar.also_used(s1);
+      ar.also_used(aux);
+      static thread_local int max_cluster_gc = -1;         // what the partition can co-schedule (<= the device-wide limit)
+      if (max_cluster_gc < 0) {
+        max_cluster_gc = 0;
+        for (int cs : {16, 8, 4, 2}) {
+          if (cs > max_cluster && cs > 4) continue;
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = kQrSmem; cfg.stream = s1;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          int nclusters = 0;
+          if (cudaOccupancyMaxActiveClusters(&nclusters, k_sbr_qr<true>, &cfg) == cudaSuccess && nclusters >= 1) { max_cluster_gc = cs; break; }
+        }
+        (void)cudaGetLastError();
+        if (ctx->sbr_debug) std::fprintf(stderr, "[sbr] panel QR cluster size limit on the fit partition (%d SMs): %d\n", ctx->gc_fit_sms, max_cluster_gc);
+      }
+      cluster_limit = std::min(max_cluster, max_cluster_gc);
+    }
     int pk = 0;
     for (int j0 = 0; m - j0 - kBw >= 2; j0 += kBw, ++pk) {
       const int r = m - j0 - kBw;
@@ -1614,53 +1646,57 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
       double* Tk = keep ? bf.Tall + (size_t)1024 * pk : T;
       QrArgs qa{A, ld, m, j0, V, ldv, Tk, slots, bars + (size_t)64 * pk};
       const int gq = ceil_div(r, kQrRows);
-      if (gq <= max_cluster && ctx->sbr_qr_grid == 0) {
+      if (gq <= cluster_limit && ctx->sbr_qr_grid == 0) {
         int cs = 1;
         while (cs < gq) cs *= 2;
         cudaLaunchConfig_t cfg = {};
         // measured (profiles/r1v_two_stage_check.txt): rows in registers win up to clusters of 4 CTAs (2.6 vs 3.3 us per
         // column), rows in shared memory at 8 and 16 (3.4 vs 4.0 us)
         const bool reg = ctx->sbr_qr_impl == 2 || (ctx->sbr_qr_impl == 0 && cs <= 4);
-        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = reg ? kQrRegSmem : kQrSmem; cfg.stream = st;
+        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kQrRows); cfg.dynamicSmemBytes = reg ? kQrRegSmem : kQrSmem; cfg.stream = s1;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         if (reg) {
-          MB_LAUNCH(ctx, "k_sbr_qr", st) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_qr_reg<true>, qa));
+          MB_LAUNCH(ctx, "k_sbr_qr", s1) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_qr_reg<true>, qa));
         } else {
-          MB_LAUNCH(ctx, "k_sbr_qr_smem", st) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_qr<true>, qa));
+          MB_LAUNCH(ctx, "k_sbr_qr_smem", s1) MB_CUDA(cudaLaunchKernelEx(&cfg, k_sbr_qr<true>, qa));
         }
       } else {
         void* params[] = {&qa};
         if (ctx->sbr_qr_impl != 1) {
-          MB_LAUNCH(ctx, "k_sbr_qr_grid", st)
-            MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr_reg<false>, dim3(gq), dim3(kQrRows), params, kQrRegSmem, st));
+          MB_LAUNCH(ctx, "k_sbr_qr_grid", s1)
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr_reg<false>, dim3(gq), dim3(kQrRows), params, kQrRegSmem, s1));
         } else {
-          MB_LAUNCH(ctx, "k_sbr_qr_smem_grid", st)
-            MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr<false>, dim3(gq), dim3(kQrRows), params, kQrSmem, st));
+          MB_LAUNCH(ctx, "k_sbr_qr_smem_grid", s1)
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)k_sbr_qr<false>, dim3(gq), dim3(kQrRows), params, kQrSmem, s1));
         }
       }
       double* A22 = A + (size_t)(j0 + kBw) * ((size_t)ld + 1);
       int nsplit = std::max(1, std::min(8, ceil_div(2 * ctx->sm_count, rblocks)));
       const int chunk = ceil_div(ceil_div(r, nsplit), 16) * 16;
       nsplit = ceil_div(r, chunk);
-      if (pk > 0) MB_CUDA(cudaStreamWaitEvent(st, ctx->sbr_ev[2 + ((pk - 1) & 1)], 0));      // trailing update of panel k - 1
-      MB_LAUNCH(ctx, "k_sbr_av", st) k_sbr_av<<<dim3(rblocks, nsplit), 128, 0, st>>>(A22, ld, r, V, ldv, Zp, chunk);
+      if (pk > 0) MB_CUDA(cudaStreamWaitEvent(s1, ctx->sbr_ev[2 + ((pk - 1) & 1)], 0));      // trailing update of panel k - 1
+      MB_LAUNCH(ctx, "k_sbr_av", s1) k_sbr_av<<<dim3(rblocks, nsplit), 128, 0, s1>>>(A22, ld, r, V, ldv, Zp, chunk);
       // (vtz + st and w + pu as two fused launches were measured in r2q: 36 + 36 us per panel against 24 + 13 + 14 + 24 -
       //  the last-CTA epilogue and the recomputed W rows cost what the two launches save; deleted)
-      MB_LAUNCH(ctx, "k_sbr_vtz", st)
-        k_sbr_vtz<<<rblocks, 512, kVtzSmem, st>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
-      MB_LAUNCH(ctx, "k_sbr_st", st) k_sbr_st<<<1, 1024, 0, st>>>(Gp, rblocks, Tk, ST);
-      MB_LAUNCH(ctx, "k_sbr_w", st) k_sbr_w<<<rblocks, 128, 0, st>>>(V, ldv, r, Z0, Tk, ST, W, z, m, j0 + kBw, L);
-      if (r > 32) MB_LAUNCH(ctx, "k_sbr_pu", st) k_sbr_pu<<<ceil_div(r - 32, 128), 128, 0, st>>>(A22, ld, r, V, W, ldv);
-      MB_CUDA(cudaEventRecord(ctx->sbr_ev[pk & 1], st));
+      MB_LAUNCH(ctx, "k_sbr_vtz", s1)
+        k_sbr_vtz<<<rblocks, 512, kVtzSmem, s1>>>(V, ldv, r, Zp, nsplit, Z0, z, m, j0 + kBw, L, Gp);
+      MB_LAUNCH(ctx, "k_sbr_st", s1) k_sbr_st<<<1, 1024, 0, s1>>>(Gp, rblocks, Tk, ST);
+      MB_LAUNCH(ctx, "k_sbr_w", s1) k_sbr_w<<<rblocks, 128, 0, s1>>>(V, ldv, r, Z0, Tk, ST, W, z, m, j0 + kBw, L);
+      if (r > 32) MB_LAUNCH(ctx, "k_sbr_pu", s1) k_sbr_pu<<<ceil_div(r - 32, 128), 128, 0, s1>>>(A22, ld, r, V, W, ldv);
+      MB_CUDA(cudaEventRecord(ctx->sbr_ev[pk & 1], s1));
       MB_CUDA(cudaStreamWaitEvent(aux, ctx->sbr_ev[pk & 1], 0));
       MB_LAUNCH(ctx, "k_sbr_r2k", aux)
         k_sbr_r2k<<<rblocks * (rblocks + 1) / 2, 256, kR2kSmem, aux>>>(A22, ld, r, V, W, ldv);
       MB_CUDA(cudaEventRecord(ctx->sbr_ev[2 + (pk & 1)], aux));
     }
-    if (pk > 0) MB_CUDA(cudaStreamWaitEvent(st, ctx->sbr_ev[2 + ((pk - 1) & 1)], 0));
+    if (pk > 0) MB_CUDA(cudaStreamWaitEvent(s1, ctx->sbr_ev[2 + ((pk - 1) & 1)], 0));
+    if (gc) {                                      // back to the caller's stream (all SMs) for stage 2 and everything after it
+      MB_CUDA(cudaEventRecord(ctx->gc_ev[1], s1));
+      MB_CUDA(cudaStreamWaitEvent(st, ctx->gc_ev[1], 0));
+    }
     MB_CUDA(cudaGetLastError());
   }
   if (ctx->after_stage1) ctx->after_stage1();
@@ -1686,7 +1722,10 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     MB_CUDA(cudaStreamSynchronize(st));
   }
   ChaseArgs ca{Bd, m, z, L, prog, (unsigned)(ctx->sbr_chase_sleep < 0 ? 0 : ctx->sbr_chase_sleep)};
-  const int G = std::max(1, std::min(ctx->sm_count, ceil_div(m, 2 * kBw) + 2));
+  // one CTA per sweep in flight: at most m / (2 b) sweeps can overlap; "sbr_chase_ctas" caps the grid (fewer SMs held by the chase
+  // beside the ensemble kernels, at the price of a shallower pipeline at the start)
+  int G = std::max(1, std::min(ctx->sm_count, ceil_div(m, 2 * kBw) + 2));
+  if (ctx->sbr_chase_ctas > 0) G = std::max(1, std::min(G, ctx->sbr_chase_ctas));
   // Register footprint decides (profiles/r2l_*, r2m_*): the chase sits on 80 SMs for ~50 ms; a CTA with the watcher / publisher
   // warps holds 160 x 192 registers, which costs a co-resident per-cell kernel (ksvm: 4 CTAs of 16 K registers = the whole file)
   // TWO of its four CTAs on that SM (k_ens_svm_tma 50 -> 69 ms), the three-warp CTA (96 x 160) one (-> 59 ms).  Spinning is not
@@ -1695,7 +1734,7 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
   // profiles/r2o3_chase_check.txt); its CTA (224 threads x 255 registers) would leave a co-resident per-cell kernel nothing,
   // so beside the ensemble the three-warp CTA stays.
   const bool dec = ctx->sbr_chase_impl == 1;
-  if (ctx->sbr_chase_impl == 3 || (ctx->sbr_chase_impl == 0 && !ctx->fit_shares_gpu)) {
+  if (ctx->sbr_chase_impl == 3 || ctx->sbr_chase_impl == 4 || (ctx->sbr_chase_impl == 0 && (!ctx->fit_shares_gpu || (ctx->gc_stage1 && ctx->gc_ok)))) {
     // tagged copies of the band and the right-hand sides, chase, plain copies back (2 x 5 MB at 5 000 knots: ~10 us each)
     const size_t nb = (size_t)kLdb * ncolb, nz = (size_t)m * std::max(L, 0);
     ulonglong2* Bt = ar.take_n<ulonglong2>(nb);
@@ -1703,7 +1742,11 @@ void sym_band_tridiag(mb_ctx* ctx, double* A, int ld, int m, double* z, int L, d
     k_sbr_tag<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(Bd, Bt, nb);
     if (nz) k_sbr_tag<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(z, zt, nz);
     ChaseLLArgs la{Bt, m, zt, L, prog + m};
-    MB_LAUNCH(ctx, "k_sbr_chase_ll", st) k_sbr_chase_ll<<<G, kLLThreads, 0, st>>>(la);
+    if (ctx->sbr_chase_impl == 4) {
+      MB_LAUNCH(ctx, "k_sbr_chase_ll2", st) k_sbr_chase_ll<2><<<G, kLLThreads, 0, st>>>(la);
+    } else {
+      MB_LAUNCH(ctx, "k_sbr_chase_ll", st) k_sbr_chase_ll<1><<<G, kLLThreads, 0, st>>>(la);
+    }
     k_sbr_untag<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(Bt, Bd, nb);
     if (nz) k_sbr_untag<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(zt, z, nz);
   } else if (dec) {

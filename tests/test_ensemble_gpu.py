@@ -274,3 +274,28 @@ def test_ensemble_on_a_raster_tma_cannot_describe(engine):
     ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
     got = engine.ensemble_eval(ens, cov)
     _cmp(got, ref, 5e-6)
+
+
+def test_sm_partitions_do_not_change_the_raster(engine):
+    """mb_mltps_predict with CUDA green contexts (stage 1 of the GCV fit on the fit partition, the forest kernel on the ensemble
+    partition from the start, the rest of the chain behind stage 1) against the deferred schedule (gc_split = -1): same kernels,
+    same order of the additions - bit-identical raster and lambda.  1 600 knots: above the size where the partitions switch on."""
+    geom = synth.make_geom(384, 512)
+    C = 4
+    cov = synth.covariate_planes(geom, C)
+    xy, _, _ = synth.make_knots(geom, 1600, 77)
+    resid = synth.residual_field(xy, 77)
+    models = synth.make_models(geom, C, 600, 77, kept="bgnmrv", rf_trees=60, gbm_trees=90)
+    kept, w, wt = synth.ensemble_weights("bgnmrv")
+    ens = engine.ensemble_create(geom, models, kept, w, wt, C + 2)
+    try:
+        engine.set_param("gc_split", -1)
+        ref, sp_ref = engine.mltps_predict(geom, ens, cov, xy, resid)
+    finally:
+        engine.set_param("gc_split", 0)
+    got, sp = engine.mltps_predict(geom, ens, cov, xy, resid)
+    again, _ = engine.mltps_predict(geom, ens, cov, xy, resid)
+    assert sp.lam == sp_ref.lam
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(again, ref)
+
