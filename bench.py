@@ -304,13 +304,14 @@ def lapack_threads(n: int):
 TRUE_BOUND = {
     "k_ens_svm": "mufu (ex2) / issue balanced: XU pipe 53 %, FMA pipe 67 %, issue 64 % (profiles/r1s_ncu_full_c3.md)",
     "k_ens_svm_mma": "mufu (ex2): dot products on the tensor pipe (3 x TF32)",
-    "k_ens_svm_tma": "mufu (ex2): 2 500 exponentials per cell, floor 36 ms at 16 / clk / SM; dot products on the tensor pipe (3 x TF32), "
-                     "covariate tiles by TMA tensor copies (profiles/r2j_ncu_full_svm_tma.md)",
-    "k_ens_trees": "issue: 73 % issue-active, ALU pipe 51 %, LSU 30 % (profiles/r1s_ncu_full_c3.md)",
+    "k_ens_svm_tma": "mufu (ex2): XU pipe 67 %, tensor pipe 48 %, issue 54 % (profiles/r2z_ncu_full_svm_tma.md); 2 500 exponentials per cell, "
+                     "floor 36 ms at 16 / clk / SM; dot products as 3 x TF32 mma.sync, covariate tiles by TMA tensor copies",
+    "k_ens_trees": "L2 latency: issue 46 %, L2 hit 97 %, L1 hit 28 % (profiles/r2d_ncu_full_trees_l2.md, r2z_ncu_full_trees.md); inside the "
+                   "step it runs on the 76-SM ensemble partition beside stage 1 of the fit (34 ms on all SMs)",
     "k_ens_fused": "issue + mufu: forest warps and support-vector warps share the SM",
     "k_sbr_chase": "latency: dependent L2 round trips between consecutive sweeps",
-    "k_leaf_fused": "hbm (profiles/r2j_ncu_full_leaf.md; before the 2-D tensor copy of the accumulator tile it was bound by the box "
-                    "barrier: 51 % of the stall samples, profiles/r2h_ncu_full_leaf_before_tma.md)",
+    "k_leaf_fused": "hbm / issue: DRAM traffic 1.079 GB for 1.074 GB algorithmic, issue 69 % (profiles/r2z_ncu_full_leaf.md; before the 2-D "
+                    "tensor copy of the accumulator tile it was bound by the box barrier: 51 % of the stall samples, r2h_ncu_full_leaf_before_tma.md)",
     "k_leaf": "hbm write / issue",
 }
 
@@ -597,7 +598,8 @@ def run_b200(args):
         "cpu_baseline": cpu, "parity": parity, "mltps_tiled": tiled,
         "limiter": "serial part: the GCV fit of fields::Tps on rank 0 (two-stage tridiagonalisation, bulge chase) - every rank waits "
                    "for its broadcast; per-cell kernels shard perfectly" if world > 1 else
-                   "fit (serial, latency-bound) beside the MUFU / issue-bound ensemble kernels",
+                   "SM-time: ensemble kernels (84 ms of the whole GPU) + full-GPU kernels of the fit (17 ms) + the SMs the bulge chase holds "
+                   "(19 ms) packed into 134 ms by SM partitions (DESIGN.md section 6)",
         "fit": {"lambda": state["sp"].lam, "eff_df": state["sp"].eff_df, "knots": state["sp"].np, "rss_final": state["rss"]},
     }
     print(json.dumps(line))

@@ -13,6 +13,8 @@
 
 #include <cuda.h>
 
+#include <cstdlib>
+
 namespace mb {
 namespace {
 
@@ -35,6 +37,11 @@ bool entry(const char* name, F& fn) {
 bool greenctx_setup(mb_ctx* ctx, int fit_sms) {
   if (ctx->gc_tried) return ctx->gc_ok;
   ctx->gc_tried = true;
+  // Under a tool that injects into the process (Nsight Compute, compute-sanitizer) the context keeps the deferred schedule: ncu
+  // 2025.2 dies without a message (exit code 9) at the first launch on a green-context stream when it profiles EVERY kernel
+  // (`--metrics ... -c N` launch lists; `-k regex` captures survive) - measured in r2z, profiles/README.md.
+  if (std::getenv("CUDA_INJECTION64_PATH") || std::getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || std::getenv("MB_NO_SM_PARTITIONS"))
+    return false;
   CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
   CUresult (*GetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
   CUresult (*SplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
