@@ -501,8 +501,11 @@ __device__ __forceinline__ float lg2_fast(float x) {
   return y;
 }
 
+// 3 CTAs per SM (<= 85 registers): at 4 (64 registers) the compiler rematerialised the per-box address and shared-memory
+// arithmetic in every iteration of a kernel that is issue-bound - fused 0.785 -> 0.825 of the measured HBM bandwidth, TPS only
+// 0.547 -> 0.622; 2 CTAs (110 registers) fall back to 0.54 (profiles/r2y_leaf_launch_bounds.txt).
 template <int P, bool kAcc>
-__global__ void __launch_bounds__(kLeafThreads, (P <= 12) ? 4 : 3) k_leaf_stream(
+__global__ void __launch_bounds__(kLeafThreads, 3) k_leaf_stream(
     const __grid_constant__ CUtensorMap acc_map, int acc_tma,
     Lattice lat, mb_window w, const unsigned char* __restrict__ recs, const float4* __restrict__ near_over,
     const unsigned long long* __restrict__ est_bits, double mixed_threshold, AccFuse fz, double* __restrict__ out,
