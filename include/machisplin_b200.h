@@ -277,6 +277,7 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * on one partition, the forest kernel on the other from the start; 0 = default 72, -1 = no partitions: the ensemble waits for stage 1;
  * the partitions are created once per context, with the size in force at the first call that uses them); "gc_share" = percent of
  * the raster's rows whose forest kernel runs on the ensemble partition beside stage 1, the rest follows on all SMs (0 = default = all rows);
+ * "leaf_impl" = TPS-only grid evaluation: 1 (default) one warp per leaf box, 2 one CTA per leaf box;
  * "leaf_tma" = 1 (default) the grid-evaluation kernel fetches the accumulator tile of a box with one 2-D tensor copy, 2 row by row;
  * "ens_order" = 1 (default) the forest kernel runs before the ksvm kernel, 2 after it;
  * "tree_levels" = 1 forest kernel with the CTA-level interval prune only, 2 (default) + the warp-level prune;

@@ -267,6 +267,9 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
     } else if (n == "gc_share") {
       MB_REQUIRE(value >= 0 && value <= 100, "gc_share must be 0 (default) or a percentage of the raster's rows");
       ctx->gc_share = value;
+    } else if (n == "leaf_impl") {
+      MB_REQUIRE(value >= 0 && value <= 2, "leaf_impl must be 0 (default = 1), 1 (one warp per box) or 2 (one CTA per box)");
+      ctx->leaf_impl = value;
     } else if (n == "leaf_tma") {
       MB_REQUIRE(value >= 0 && value <= 2, "leaf_tma must be 0 (default = 1), 1 (2-D tensor copy of the accumulator tile) or 2 (row copies)");
       ctx->leaf_tma = value;

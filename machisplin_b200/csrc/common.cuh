@@ -189,6 +189,7 @@ struct mb_ctx {
   // fast-evaluator tunables (0 = automatic)
   int cheb_p = 0, leaf_cols = 0, leaf_rows = 0;
   int ens_overlap = 0;        // per-cell ensemble: 0 = 2 = forest kernel, then the tensor-pipe ksvm kernel (default); 1 = side by side on two streams (A/B)
+  int leaf_impl = 0;          // TPS-only grid evaluation: 0 = 1 = one warp per box (k_leaf_warp), 2 = one CTA per box (k_leaf_stream)
   int leaf_tma = 0;           // grid-evaluation kernel: 0 = 1 = accumulator tile by one 2-D tensor copy, 2 = one bulk copy per row
   int ens_order = 0;          // forests + tensor-pipe ksvm: 0 = 1 = forest kernel first, 2 = ksvm kernel first
   int ens_tma = 0;            // k_ens_svm_tma: 0 = 1 = covariate tiles by TMA tensor copies when the raster layout allows, 2 = plain loads

@@ -721,6 +721,167 @@ __global__ void __launch_bounds__(kLeafThreads, 3) k_leaf_stream(
 }
 
 // -----------------------------------------------------------------------------------------
+// k_leaf_warp - the TPS-only grid evaluation (no accumulator) with ONE WARP PER BOX and no CTA barrier at all.
+// k_leaf_stream<P, false> is issue-bound: of its ~1 800 warp-instructions per 1 024-cell box, ~640 are the per-box cursor,
+// barrier and staging arithmetic that each of the 8 warps of the CTA repeats, and the collapse of box i + 1 occupies 3 warps
+// while 5 wait for the box barrier.  Here a warp owns whole boxes: its own 4-stage record ring (one bulk copy + mbarrier per
+// box, issued by lane 0), its own G buffers, collapse (3 items per lane) -> __syncwarp -> 16 row pairs -> __syncwarp.  The per-box
+// overhead is paid once instead of eight times, nobody waits for anybody, and 24 warps per SM interleave.  Same arithmetic
+// per cell as k_leaf_stream: the output is bit-identical (tools/leaf_check.py).
+// -----------------------------------------------------------------------------------------
+constexpr int kLeafWarpStages = 4;
+__host__ __device__ inline int leaf_warp_bytes(int P, int bh) {      // shared memory of one warp
+  return kLeafWarpStages * ((leaf_rec_bytes(P) + 127) / 128 * 128) + ((((bh + 1) & ~1) * 8 + bh * leaf_gfs(P) * 4 + 127) / 128 * 128);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kLeafThreads, 4) k_leaf_warp(
+    Lattice lat, mb_window w, const unsigned char* __restrict__ recs, const float4* __restrict__ near_over,
+    const unsigned long long* __restrict__ est_bits, double mixed_threshold, double* __restrict__ out, int64_t stride) {
+  static_assert(P % 2 == 0, "P must be even");
+  if (!(__longlong_as_double((long long)__ldg(est_bits)) <= mixed_threshold)) return;   // k_leaf_f64 runs instead
+  constexpr int GFS = leaf_gfs(P);
+  constexpr int NQ = GFS / 2;
+  constexpr uint32_t kRecBytes = leaf_rec_bytes(P);
+  constexpr int kRecStride = (leaf_rec_bytes(P) + 127) / 128 * 128;
+  extern __shared__ __align__(128) unsigned char leaf_smem[];
+  __shared__ __align__(8) uint64_t s_full[kLeafThreads / 32][kLeafWarpStages];
+  const int bh = lat.bh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* mine = leaf_smem + (size_t)warp * leaf_warp_bytes(P, bh);
+  double* g0buf = reinterpret_cast<double*>(mine + kLeafWarpStages * kRecStride);    // [bh]
+  float* gfbuf = reinterpret_cast<float*>(g0buf + ((bh + 1) & ~1));                   // [bh][GFS], 16-byte aligned rows
+  const int nboxes = lat.nbx * lat.nby;
+  const int W = gridDim.x * (kLeafThreads / 32);
+  const int wg = blockIdx.x * (kLeafThreads / 32) + warp;
+  const int nmine = wg < nboxes ? (nboxes - wg + W - 1) / W : 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kLeafWarpStages; ++s) mbar_init(&s_full[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < min(kLeafWarpStages, nmine); ++i) {
+      mbar_expect_tx(&s_full[warp][i], kRecBytes);
+      bulk_g2s(mine + i * kRecStride, recs + (size_t)(wg + i * W) * kRecBytes, kRecBytes, &s_full[warp][i]);
+    }
+  }
+  __syncwarp();
+  const int half = lane >> 4, l = lane & 15;
+  float2 Tp[NQ];
+  {
+    float T[2 * NQ + 1];
+    const float tx = (2.0f * l + 1.0f) / 32.0f - 1.0f;
+    T[0] = 1.0f;
+    T[1] = tx;
+#pragma unroll
+    for (int k = 2; k <= 2 * NQ; ++k) T[k] = k < P ? 2.0f * tx * T[k - 1] - T[k - 2] : 0.0f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) Tp[q] = make_float2(T[2 * q + 1], T[2 * q + 2]);
+  }
+  const float cxa = (float)(lat.hx * ((l + 0.5) / 32.0)), cxb = (float)(lat.hx * ((31 - l + 0.5) / 32.0));
+  const double hyb = lat.hy / bh, inv_bh = 1.0 / bh;
+  const float inv_bh_f = (float)inv_bh;
+  const int npair = (bh + 1) >> 1;
+  const int n32 = npair * NQ;
+  const int wcols = w.c1 - w.c0, wrows = w.r1 - w.r0;
+  const int full_bi = wcols >> 5, full_bj = bh == 32 ? (wrows >> 5) : 0;
+  const int dI = W % lat.nbx, dJ = W / lat.nbx;
+  int cbi = wg % lat.nbx, cbj = wg / lat.nbx;
+  for (int i = 0; i < nmine; ++i) {
+    const int st = i & (kLeafWarpStages - 1);
+    const unsigned char* rec = mine + st * kRecStride;
+    mbar_wait(&s_full[warp][st], (i / kLeafWarpStages) & 1);
+    // ---- collapse y: G[lr][k] = sum_j T_j(ty_lr) A[j][k] (same statements as k_leaf_stream::collapse) ----------------------
+    {
+      const double* a0 = reinterpret_cast<const double*>(rec + 256);
+      const float2* af = reinterpret_cast<const float2*>(rec + 256 + 8 * P);
+      for (int o = lane; o < n32 + npair; o += 32) {
+        if (o < n32) {
+          const int lr = o / NQ, q = o % NQ;
+          const float ty = fmaf((float)(2 * lr + 1), inv_bh_f, -1.0f);
+          float t0 = 1.0f, t1 = ty;
+          float2 ev = af[q], od = af[NQ + q];
+          od.x *= ty; od.y *= ty;
+#pragma unroll
+          for (int j = 2; j < P; ++j) {
+            const float t2 = 2.0f * ty * t1 - t0;
+            if (j & 1) od = __ffma2_rn(make_float2(t2, t2), af[j * NQ + q], od);
+            else ev = __ffma2_rn(make_float2(t2, t2), af[j * NQ + q], ev);
+            t0 = t1; t1 = t2;
+          }
+          const int lm = bh - 1 - lr;
+          *reinterpret_cast<float2*>(gfbuf + lr * GFS + 2 * q) = make_float2(ev.x + od.x, ev.y + od.y);
+          *reinterpret_cast<float2*>(gfbuf + lm * GFS + 2 * q) = make_float2(ev.x - od.x, ev.y - od.y);
+        } else {
+          const int lr = o - n32;
+          const double ty = (2.0 * lr + 1.0) * inv_bh - 1.0;
+          double t0 = 1.0, t1 = ty, ev = a0[0], od = ty * a0[1];
+#pragma unroll
+          for (int j = 2; j < P; ++j) {
+            const double t2 = 2.0 * ty * t1 - t0;
+            if (j & 1) od = fma(t2, a0[j], od);
+            else ev = fma(t2, a0[j], ev);
+            t0 = t1; t1 = t2;
+          }
+          g0buf[lr] = ev + od;
+          g0buf[bh - 1 - lr] = ev - od;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- rows: lane = (row of a pair, column pair l / 31 - l) -----------------------------------------------------------------
+    {
+      const NearBlk* nb = reinterpret_cast<const NearBlk*>(rec);
+      const int cnt = nb->cnt;
+      const bool full = cbi < full_bi && cbj < full_bj;
+      const int rows_here = full ? bh : min(bh, wrows - cbj * bh);
+      const bool okA = full || cbi * 32 + l < wcols, okB = full || cbi * 32 + 31 - l < wcols;
+      double* dst = out + ((int64_t)cbj * bh + half) * stride + (cbi * 32 + l);
+      const int64_t dstep = 2 * stride;
+      for (int lr = half; lr < rows_here; lr += 2, dst += dstep) {
+        const float4* g4 = reinterpret_cast<const float4*>(gfbuf + lr * GFS);
+        float2 eo = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < GFS / 4; ++q) {
+          const float4 g = g4[q];
+          eo = __ffma2_rn(make_float2(g.x, g.y), Tp[2 * q], eo);
+          eo = __ffma2_rn(make_float2(g.z, g.w), Tp[2 * q + 1], eo);
+        }
+        float fa = eo.y + eo.x, fb = eo.y - eo.x;
+        if (cnt > 0) {
+          const float cyl = (float)(hyb * (lr + 0.5));
+          auto pair_term = [&](const float4 kn) {
+            const float dy = cyl - kn.y, dy2 = dy * dy;
+            const float dxa = cxa - kn.x, dxb = cxb - kn.x;
+            const float r2a = fmaxf(fmaf(dxa, dxa, dy2), 1e-20f), r2b = fmaxf(fmaf(dxb, dxb, dy2), 1e-20f);
+            fa = fmaf(kn.z * r2a, lg2_fast(r2a), fa);
+            fb = fmaf(kn.z * r2b, lg2_fast(r2b), fb);
+          };
+          if (cnt <= kNearInline) {
+#pragma unroll 1
+            for (int q = 0; q < cnt; ++q) pair_term(nb->e[q]);
+          } else {
+            const float4* src = near_over + nb->off;
+#pragma unroll 1
+            for (int q = 0; q < cnt; ++q) pair_term(__ldg(&src[q]));
+          }
+        }
+        const double g0 = g0buf[lr];
+        const double va = g0 + (double)fa, vb = g0 + (double)fb;
+        if (okA) __stcs(dst, va);
+        if (okB) __stcs(dst + (31 - 2 * l), vb);
+      }
+    }
+    cbi += dI; cbj += dJ;
+    if (cbi >= lat.nbx) { cbi -= lat.nbx; ++cbj; }
+    __syncwarp();                                  // the stage and the G buffers are free
+    if (lane == 0 && i + kLeafWarpStages < nmine) {
+      mbar_expect_tx(&s_full[warp][st], kRecBytes);
+      bulk_g2s(mine + st * kRecStride, recs + (size_t)(wg + (i + kLeafWarpStages) * W) * kRecBytes, kRecBytes, &s_full[warp][st]);
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
 // k_leaf_f64 - the same evaluation entirely in float64 with the table-driven log (always valid; runs when the
 // device-side estimate says the mixed path would not be accurate enough, or on request).  One leaf box per loop
 // iteration of a persistent CTA, lane = column:
@@ -926,6 +1087,10 @@ static void run_fast(mb_ctx* ctx, const mb_spline* s, const Lattice& lat, const 
                            make_f64_matrix_tensor_map(&amap, fz.acc, fz.stride, (int64_t)lat.nby * lat.bh, 32, lat.bh)) ? 1 : 0;
       const int grid = leaf_grid(ctx, k_leaf_stream<P, true>, smem, nboxes);
       MB_LAUNCH(ctx, "k_leaf_fused", st) k_leaf_stream<P, true><<<grid, kLeafThreads, smem, st>>>(amap, acc_tma, lat, w, d_recs, d_over, d_est, thr, fz, out, stride);
+    } else if (ctx->leaf_impl != 2) {            // TPS only: one warp per box ("leaf_impl" = 2: the CTA-per-box kernel)
+      const size_t wsm = (size_t)(kLeafThreads / 32) * leaf_warp_bytes(P, lat.bh);
+      const int grid = leaf_grid(ctx, k_leaf_warp<P>, wsm, (nboxes + kLeafThreads / 32 - 1) / (kLeafThreads / 32));
+      MB_LAUNCH(ctx, "k_leaf", st) k_leaf_warp<P><<<grid, kLeafThreads, wsm, st>>>(lat, w, d_recs, d_over, d_est, thr, out, stride);
     } else {
       const int grid = leaf_grid(ctx, k_leaf_stream<P, false>, smem, nboxes);
       MB_LAUNCH(ctx, "k_leaf", st) k_leaf_stream<P, false><<<grid, kLeafThreads, smem, st>>>(amap, 0, lat, w, d_recs, d_over, d_est, thr, fz, out, stride);
