@@ -305,7 +305,7 @@ int mb_set_param(mb_ctx* ctx, const char* name, int value) {
       MB_REQUIRE(value >= 0 && value <= 2, "coef_impl must be 0 (band form when well conditioned), 1 (band form whenever it exists) or 2 (dense Cholesky)");
       ctx->coef_impl = value;
     } else if (n == "svm_impl") {
-      MB_REQUIRE(value >= 0 && value <= 2, "svm_impl must be 0 (default: 1 when P <= 8, else 2), 1 (3 x TF32 tensor-core dot products) or 2 (packed FP32)");
+      MB_REQUIRE(value >= 0 && value <= 3, "svm_impl must be 0 (default: 3 when P <= 8, else 2), 1 (tensor-core dot products, 3 x TF32), 2 (packed FP32) or 3 (tensor-core dot products, FP16 split operands)");
       ctx->svm_impl = value;
     } else if (n == "defer_ensemble") {
       MB_REQUIRE(value == 0 || value == 1, "defer_ensemble must be 0 or 1");

@@ -197,8 +197,8 @@ struct mb_ctx {
   cudaStream_t ens_aux = nullptr;   // stream of the ksvm kernel in overlap mode + fork / join events
   cudaEvent_t ev_ens[2] = {nullptr, nullptr};
   int tree_levels = 0;        // forest kernel: 0 = 2 = CTA-level + warp-level interval pruning, 1 = CTA-level only (A/B measurements)
-  int svm_impl = 0;           // ksvm kernel: 0 = automatic (1 when P <= 8), 1 = dot products on the tensor pipe (k_ens_svm_mma, P <= 8),
-                              // 2 = packed FP32 (k_ens_svm); read by mb_ensemble_create
+  int svm_impl = 0;           // ksvm kernel: 0 = automatic (3 when P <= 8, else 2), 1 = dot products on the tensor pipe as 3 x TF32 (P <= 8),
+                              // 2 = packed FP32 (k_ens_svm), 3 = tensor pipe with FP16 split operands (P <= 8); read by mb_ensemble_create and at launch
   // 256-entry (1/m_k, -log(1/m_k)) table for the float64 table-driven log
   mb::DevBuf<double2> logtab;
   int eval_precision = 0;     // fast evaluator: 0 = automatic, 1 = float64 only, 2 = force mixed

@@ -28,6 +28,8 @@
 #include "ens_device.cuh"
 #include "async_copy.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -65,6 +67,8 @@ struct mb_ensemble {
   int svm_oct = 0;                   // ceil(S / 8)
   mb::DevBuf<float4> svm_bq;         // [octet][lane]: B fragments of mma.m16n8k8.tf32, (hi f=tig, hi f=tig+4, lo f=tig, lo f=tig+4) of SV 8o + (lane >> 2)
   mb::DevBuf<float4> svm_baq;        // svm_bap padded with zeros to 4 pairs per octet
+  mb::DevBuf<uint4> svm_bh;          // [octet][lane]: B fragments of mma.m16n8k16.f16 (svm_impl 3), half2 pairs of features 2 tig, 2 tig + 1: (hi, hi, lo, lo)
+  double svm_hs = 1.0;               // power of two that moves part of 2 sigma log2(e) from the support vectors to x in that layout
   mb::DevBuf<double> svm_xc, svm_xis; // centre, 1/scale
   double svm_bias = 0, svm_sigma = 0, svm_yc = 0, svm_ys = 1;
   // trees
@@ -758,6 +762,30 @@ mb_ensemble* ensemble_create(mb_ctx* ctx, const mb_grid& g, const mb_models& m, 
       for (int pr = 0; pr < npairs; ++pr) baq[pr] = bap[pr];
       e->svm_oct = noct;
       e->svm_bq.upload(bq, st); e->svm_baq.upload(baq, st);
+      // FP16 split operands for mma.m16n8k16 (svm_impl 3): value = hi + lo, both halves; the factor 2 sigma log2(e) is shared out
+      // between x and the support vectors by a power of two so that both stay in the middle of the half range
+      const double fac = 2.0 * m.svm_sigma * l2e;
+      const double hs = std::exp2(std::round(0.5 * std::log2(fac)));
+      std::vector<uint4> bh((size_t)noct * 32, make_uint4(0u, 0u, 0u, 0u));
+      bool in_range = std::isfinite(hs) && hs > 0;
+      for (int o = 0; o < noct && in_range; ++o)
+        for (int ln = 0; ln < 32; ++ln) {
+          const int i = 8 * o + (ln >> 2), tig = ln & 3;
+          if (i >= S) continue;
+          unsigned short hi[2], lo[2];
+          for (int k = 0; k < 2; ++k) {
+            const int f = 2 * tig + k;
+            const float v = f < P ? (float)(fac / hs * m.svm_sv[(size_t)i * P + f]) : 0.f;
+            if (!(std::fabs(v) < 16384.f)) in_range = false;
+            const __half h = __float2half_rn(v);
+            hi[k] = __half_as_ushort(h);
+            lo[k] = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+          }
+          // b0 = b1 (K rows 2t, 2t+1 and 2t+8, 2t+9 are the same two features): stored twice so that one LDS.128 delivers both register pairs
+          const unsigned h2 = (unsigned)hi[0] | ((unsigned)hi[1] << 16), l2 = (unsigned)lo[0] | ((unsigned)lo[1] << 16);
+          bh[(size_t)o * 32 + ln] = make_uint4(h2, h2, l2, l2);
+        }
+      if (in_range) { e->svm_hs = hs; e->svm_bh.upload(bh, st); }
     }
   }
   std::vector<int2> nodes;          // both forests, rf first (child indices are absolute)
@@ -983,6 +1011,7 @@ struct __align__(16) SvmTmaScratch {
 struct SvmTmaArgs {
   const float* cov; int C, P; int64_t plane; EnsGeom eg; mb_window w;
   const float4* bq; const float4* baq; int noct; const double* xc; const double* xis;
+  const uint4* bh; double hs;      // FP16 layout (F16 instantiations)
   double sigma, bias, ys, yc, wv;
   SmoothParams sp;
   int64_t acc_stride; double* acc;
@@ -991,6 +1020,61 @@ struct SvmTmaArgs {
   int cbase;                       // column of the first tile: w.c0 snapped down to a multiple of 4 (16-byte aligned tile rows)
 };
 
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void svm_octet(const float4 bf, const float4 ba, const float (&ah)[2][4], const float (&al)[2][4],
+                                          const float (&a0c)[2][2], float2 (&part)[2][2]) {
+  // the two M-tiles advance in lock-step (the mma statements are volatile, so this IS the issue order): the three dependent
+  // HMMAs of one tile hide behind those of the other instead of stalling the warp
+  float d[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const float2 d01 = __fadd2_rn(make_float2(a0c[mt][0], a0c[mt][0]), make_float2(ba.x, ba.y));
+    const float2 d23 = __fadd2_rn(make_float2(a0c[mt][1], a0c[mt][1]), make_float2(ba.x, ba.y));
+    d[mt][0] = d01.x; d[mt][1] = d01.y; d[mt][2] = d23.x; d[mt][3] = d23.y;
+  }
+  mma_tf32(d[0], al[0], bf.x, bf.y);          // x_lo . sv_hi
+  mma_tf32(d[1], al[1], bf.x, bf.y);
+  mma_tf32(d[0], ah[0], bf.z, bf.w);          // x_hi . sv_lo
+  mma_tf32(d[1], ah[1], bf.z, bf.w);
+  mma_tf32(d[0], ah[0], bf.x, bf.y);          // x_hi . sv_hi
+  mma_tf32(d[1], ah[1], bf.x, bf.y);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[mt][0]), ex2_approx(d[mt][1])), part[mt][0]);
+    part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[mt][2]), ex2_approx(d[mt][3])), part[mt][1]);
+  }
+}
+
+// The same octet with FP16 split operands (svm_impl 3): K = 16 holds the 8 features twice - A = [x_hi | x_lo], B = [sv_hi ; sv_hi] and
+// then [sv_lo ; sv_lo] - so TWO HMMA.16816 give x_hi.sv_hi + x_lo.sv_hi + x_hi.sv_lo + x_lo.sv_lo (products of halves are exact in
+// the FP32 accumulator: 22 bits per operand like 3 x TF32, plus the lo.lo term that scheme drops), the A fragments are the same
+// four registers for both.
+__device__ __forceinline__ void svm_octet16(const uint4 bf, const float4 ba, const uint32_t (&ax)[2][4], const float (&a0c)[2][2],
+                                            float2 (&part)[2][2]) {
+  float d[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const float2 d01 = __fadd2_rn(make_float2(a0c[mt][0], a0c[mt][0]), make_float2(ba.x, ba.y));
+    const float2 d23 = __fadd2_rn(make_float2(a0c[mt][1], a0c[mt][1]), make_float2(ba.x, ba.y));
+    d[mt][0] = d01.x; d[mt][1] = d01.y; d[mt][2] = d23.x; d[mt][3] = d23.y;
+  }
+  mma_f16(d[0], ax[0], bf.z, bf.w);           // (x_hi + x_lo) . sv_lo
+  mma_f16(d[1], ax[1], bf.z, bf.w);
+  mma_f16(d[0], ax[0], bf.x, bf.y);           // (x_hi + x_lo) . sv_hi
+  mma_f16(d[1], ax[1], bf.x, bf.y);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[mt][0]), ex2_approx(d[mt][1])), part[mt][0]);
+    part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[mt][2]), ex2_approx(d[mt][3])), part[mt][1]);
+  }
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(kSvmThreads, 4) k_ens_svm_tma(const __grid_constant__ CUtensorMap tmap, SvmTmaArgs a) {
   extern __shared__ __align__(128) unsigned char svm_smem[];
   const int C = a.C;
@@ -1037,24 +1121,10 @@ __global__ void __launch_bounds__(kSvmThreads, 4) k_ens_svm_tma(const __grid_con
       __syncthreads();
     }
     const int row = row0 + warp;
-    const int ocol = col0 + lane;
-    const bool olive = ocol >= w.c0 && ocol < w.c1 && row < w.r1;
     const float* frow = feat + warp * 32;
-    // the forest kernel's sum of this thread's cell, requested now and used after the support-vector loop (epilogue 1)
-    double* const dst = a.acc + (int64_t)(row - w.r0) * a.acc_stride + (ocol - w.c0);
-    double prev = 0.0;
-    if (olive && a.epilogue == 1) prev = __ldcs(dst);
-    // the float64 smooth models of the cell this thread OWNS (cell `lane` of the row)
-    double smooth = 0.0;
-    if ((a.sp.gam || a.sp.nn || a.sp.mars_T > 0) && olive) {
-      double x[16];
-      for (int f = 0; f < C; ++f) x[f] = (double)frow[f * kTileCells + lane];
-      x[C] = a.eg.xmin + (ocol + 0.5) * a.eg.rx;
-      x[C + 1] = a.eg.ymax - (row + 0.5) * a.eg.ry;
-      smooth = smooth_models(x, C + 2, a.sp);
-    }
     float ah[2][4], al[2][4], a0c[2][2];
-    int nanf[2][2];
+    uint32_t ax[2][4];                                 // F16: a0 / a1 = (hi, hi) of features 2t, 2t+1 of rows g / g + 8, a2 / a3 = (lo, lo)
+    unsigned nanbits = 0;                              // bit 2 mt + hr: an NA layer in cell (mt, hr) of this lane's group
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -1064,9 +1134,10 @@ __global__ void __launch_bounds__(kSvmThreads, 4) k_ens_svm_tma(const __grid_con
         const bool live = col >= w.c0 && col < w.c1 && row < w.r1;
         double n2 = 0.0;
         int anynan = 0;
+        float xf[2];
 #pragma unroll
         for (int fh = 0; fh < 2; ++fh) {
-          const int f = t + 4 * fh;
+          const int f = F16 ? 2 * t + fh : t + 4 * fh;
           double xs = 0.0;
           if (f < a.P) {
             double v;
@@ -1077,17 +1148,28 @@ __global__ void __launch_bounds__(kSvmThreads, 4) k_ens_svm_tma(const __grid_con
             xs = (v - a.xc[f]) * a.xis[f];
           }
           n2 += xs * xs;
-          const float xf = (float)xs;
-          const float hi = to_tf32(xf);
-          ah[mt][hr + 2 * fh] = hi;
-          al[mt][hr + 2 * fh] = to_tf32(xf - hi);
+          if constexpr (F16) {
+            xf[fh] = fminf(fmaxf((float)(xs * a.hs), -32768.f), 32768.f);   // beyond that exp(-sigma |x - sv|^2) is 0 in any precision
+          } else {
+            xf[fh] = (float)xs;
+            const float hi = to_tf32(xf[fh]);
+            ah[mt][hr + 2 * fh] = hi;
+            al[mt][hr + 2 * fh] = to_tf32(xf[fh] - hi);
+          }
+        }
+        if constexpr (F16) {
+          const __half2 hi = __floats2half2_rn(xf[0], xf[1]);
+          const float2 hf = __half22float2(hi);
+          const __half2 lo = __floats2half2_rn(xf[0] - hf.x, xf[1] - hf.y);
+          ax[mt][hr] = *reinterpret_cast<const uint32_t*>(&hi);
+          ax[mt][2 + hr] = *reinterpret_cast<const uint32_t*>(&lo);
         }
         n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
         n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
         anynan |= __shfl_xor_sync(0xffffffffu, anynan, 1);
         anynan |= __shfl_xor_sync(0xffffffffu, anynan, 2);
         a0c[mt][hr] = (float)(-a.sigma * n2 * 1.4426950408889634);
-        nanf[mt][hr] = anynan;
+        nanbits |= (anynan ? 1u : 0u) << (2 * mt + hr);
       }
     float2 part[2][2];
 #pragma unroll
@@ -1097,27 +1179,27 @@ __global__ void __launch_bounds__(kSvmThreads, 4) k_ens_svm_tma(const __grid_con
     for (int base = 0; base < a.noct; base += kSvmOct) {
       const int n = min(kSvmOct, a.noct - base);
       __syncthreads();
-      for (int i = tid; i < n * 32; i += kSvmThreads) S.bq[i] = __ldg(&a.bq[(size_t)base * 32 + i]);
+      uint4* const sbh = reinterpret_cast<uint4*>(S.bq);
+      if constexpr (F16) {
+        for (int i = tid; i < n * 32; i += kSvmThreads) sbh[i] = __ldg(&a.bh[(size_t)base * 32 + i]);
+      } else {
+        for (int i = tid; i < n * 32; i += kSvmThreads) S.bq[i] = __ldg(&a.bq[(size_t)base * 32 + i]);
+      }
       for (int i = tid; i < n * 4; i += kSvmThreads) S.ba[i] = __ldg(&a.baq[(size_t)base * 4 + i]);
       __syncthreads();
+      // (b, b', alpha, alpha') in S.ba are those of support vectors 2t, 2t+1 of the octet
+      if constexpr (F16) {
 #pragma unroll 2
-      for (int o = 0; o < n; ++o) {
-        const float4 bf = S.bq[o * 32 + lane];
-        const float4 ba = S.ba[o * 4 + t];          // (b, b, alpha, alpha) of support vectors 2t, 2t+1 of the octet
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          float d[4] = {a0c[mt][0] + ba.x, a0c[mt][0] + ba.y, a0c[mt][1] + ba.x, a0c[mt][1] + ba.y};
-          mma_tf32(d, al[mt], bf.x, bf.y);          // x_lo . sv_hi
-          mma_tf32(d, ah[mt], bf.z, bf.w);          // x_hi . sv_lo
-          mma_tf32(d, ah[mt], bf.x, bf.y);          // x_hi . sv_hi
-          part[mt][0] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[0]), ex2_approx(d[1])), part[mt][0]);
-          part[mt][1] = __ffma2_rn(make_float2(ba.z, ba.w), make_float2(ex2_approx(d[2]), ex2_approx(d[3])), part[mt][1]);
-        }
+        for (int o = 0; o < n; ++o) svm_octet16(sbh[o * 32 + lane], S.ba[o * 4 + t], ax, a0c, part);
+      } else {
+#pragma unroll 2
+        for (int o = 0; o < n; ++o) svm_octet(S.bq[o * 32 + lane], S.ba[o * 4 + t], ah, al, a0c, part);
       }
     }
     // per-cell totals: the four lanes of a group hold the 8 support-vector columns; then to the lane that owns the cell
     double mine = 0.0;
-    int mynan = 0;
+    const unsigned gbits = __shfl_sync(0xffffffffu, nanbits, 4 * (lane & 7));
+    const int mynan = (gbits >> (lane >> 3)) & 1u;           // lane = 16 mt + 8 hr + g
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -1126,10 +1208,23 @@ __global__ void __launch_bounds__(kSvmThreads, 4) k_ens_svm_tma(const __grid_con
         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
         tot += __shfl_xor_sync(0xffffffffu, tot, 2);
         const double v = __shfl_sync(0xffffffffu, tot, 4 * (lane & 7));
-        const int nf = __shfl_sync(0xffffffffu, nanf[mt][hr], 4 * (lane & 7));
-        if ((lane >> 4) == mt && ((lane >> 3) & 1) == hr) { mine = v; mynan = nf; }
+        if ((lane >> 4) == mt && ((lane >> 3) & 1) == hr) mine = v;
       }
-    if (olive) {
+    // everything that is per OWNED cell (cell `lane` of the row) comes after the support-vector loop, so that nothing of it
+    // is live across it: the loop needs the registers for two independent accumulator sets
+    const int ocol = col0 + lane;
+    if (ocol >= w.c0 && ocol < w.c1 && row < w.r1) {
+      double* const dst = a.acc + (int64_t)(row - w.r0) * a.acc_stride + (ocol - w.c0);
+      double prev = 0.0;
+      if (a.epilogue == 1) prev = __ldcs(dst);               // the forest kernel's sum of this cell
+      double smooth = 0.0;                                   // the float64 smooth models
+      if ((a.sp.gam || a.sp.nn || a.sp.mars_T > 0) && !mynan) {
+        double x[16];
+        for (int f = 0; f < C; ++f) x[f] = (double)frow[f * kTileCells + lane];
+        x[C] = a.eg.xmin + (ocol + 0.5) * a.eg.rx;
+        x[C + 1] = a.eg.ymax - (row + 0.5) * a.eg.ry;
+        smooth = smooth_models(x, C + 2, a.sp);
+      }
       // last link of the chain: NA rule (V73: terra::predict returns NA where any layer is NA)
       const double v = mynan ? __longlong_as_double(0x7ff8000000000000LL) : a.wv * ((mine - a.bias) * a.ys + a.yc) + smooth;
       if (a.epilogue == 2) atomicAdd(dst, v);
@@ -1157,14 +1252,18 @@ static void launch_svm_tma(mb_ctx* ctx, const mb_ensemble* e, const float* cov, 
   sa.use_tma = (ctx->ens_tma != 2 && make_plane_tensor_map(&tmap, cov, g.ncol, g.nrow, e->C, plane, 32, 8)) ? 1 : 0;
   const size_t stage = ((size_t)e->C * kTileCells + 31) / 32 * 32 * sizeof(float);
   const size_t smem = 2 * stage + sizeof(SvmTmaScratch);
-  static thread_local bool attr = false;
-  if (!attr) {
-    MB_CUDA(cudaFuncSetAttribute(k_ens_svm_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
-  }
   const int per_sm = ctx->svm_ctas_per_sm > 0 ? ctx->svm_ctas_per_sm : 2;
   const int grid = chunked ? (sa.ntiles + kSvmChunkTiles - 1) / kSvmChunkTiles : std::min(sa.ntiles, per_sm * ctx->sm_count);
-  MB_LAUNCH(ctx, "k_ens_svm_tma", st) k_ens_svm_tma<<<grid, kSvmThreads, smem, st>>>(tmap, sa);
+  const bool f16 = ctx->svm_impl != 1 && e->svm_bh.p != nullptr;     // svm_impl 1 = 3 x TF32 (A/B), 0 / 3 = FP16 split operands
+  sa.bh = e->svm_bh.p; sa.hs = e->svm_hs;
+  static thread_local bool attr = false;
+  if (!attr) {
+    MB_CUDA(cudaFuncSetAttribute(k_ens_svm_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MB_CUDA(cudaFuncSetAttribute(k_ens_svm_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  if (f16) MB_LAUNCH(ctx, "k_ens_svm_tma", st) k_ens_svm_tma<true><<<grid, kSvmThreads, smem, st>>>(tmap, sa);
+  else MB_LAUNCH(ctx, "k_ens_svm_tma", st) k_ens_svm_tma<false><<<grid, kSvmThreads, smem, st>>>(tmap, sa);
 }
 
 template <int NQ>

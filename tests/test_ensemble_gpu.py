@@ -214,11 +214,12 @@ def test_tiled_mode_is_independent_of_lane_concurrency(engine, case):
     np.testing.assert_array_equal(a, out.cpu().numpy())
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("kept", ["v", "gnmv", "bgnmrv"])
 def test_svm_kernel_variants(engine, case, kept, impl):
-    """Both ksvm kernels against the oracle: impl 1 = dot products on the tensor pipe (3 x TF32, k_ens_svm_mma; the default for
-    P <= 8), impl 2 = packed FP32 (k_ens_svm; the only one for P > 8).  Same tolerance, same NA mask, ragged window."""
+    """The ksvm kernels against the oracle: dot products on the tensor pipe with FP16 split operands (impl 3, two HMMA.16816 per
+    16 cells x 8 support vectors; the default for P <= 8) or 3 x TF32 (impl 1, three HMMA.1688), and packed FP32 (impl 2,
+    k_ens_svm; the only one for P > 8).  Same tolerance, same NA mask, ragged window."""
     geom, C, models, cov = case
     ws = [1.0 / len(kept)] * len(kept)
     ref = cbind.ensemble_eval(models, kept, ws, 1.0, cov, geom.as_tuple())

@@ -25,6 +25,7 @@ ap.add_argument("--levels", default="1,2")
 ap.add_argument("--svm", default="1,2")
 ap.add_argument("--fuse", default="1,2", help="ens_overlap values for the full ensemble (1 forest and ksvm kernels side by side, 2 one after the other)")
 ap.add_argument("--per-sm", default="0", help="svm_ctas_per_sm values in overlap mode")
+ap.add_argument("--kept", default="rb,v,bgnmrv")
 ap.add_argument("--nrow", type=int, default=8192)
 ap.add_argument("--ncol", type=int, default=8192)
 ap.add_argument("--reps", type=int, default=3)
@@ -41,24 +42,32 @@ def run(tag, geom, cov_t, models, kept_sets):
         full = bool(set(kept) & set("rb")) and "v" in kept
         for fz, psm in ([(int(x), int(q)) for x in args.fuse.split(",") for q in (args.per_sm.split(",") if int(x) == 1 else ["0"])] if full else [(0, 0)]):
           for lv in [int(x) for x in args.levels.split(",")] if (set(kept) & set("rb") and not full) else [0]:
-            for sv in [int(x) for x in args.svm.split(",")] if ("v" in kept and not full) else [0]:
-                eng.set_param("tree_levels", lv)
-                eng.set_param("svm_impl", sv)
-                eng.set_param("ens_overlap", fz); eng.set_param("svm_ctas_per_sm", psm)
-                ens = eng.ensemble_create(geom, models, kk, w, wt, C + 2)
+           for sv in [int(x) for x in args.svm.split(",")] if "v" in kept else [0]:
+            eng.set_param("tree_levels", lv)
+            eng.set_param("svm_impl", sv)
+            eng.set_param("ens_overlap", fz); eng.set_param("svm_ctas_per_sm", psm)
+            ens = eng.ensemble_create(geom, models, kk, w, wt, C + 2)
+            eng.ensemble_eval_dev(ens, cov_t.data_ptr(), C, out.data_ptr())
+            torch.cuda.synchronize()
+            eng.timing(True); eng.timing_collect()
+            t0 = time.perf_counter()
+            for _ in range(args.reps):
                 eng.ensemble_eval_dev(ens, cov_t.data_ptr(), C, out.data_ptr())
-                torch.cuda.synchronize()
-                eng.timing(True); eng.timing_collect()
-                t0 = time.perf_counter()
-                for _ in range(args.reps):
-                    eng.ensemble_eval_dev(ens, cov_t.data_ptr(), C, out.data_ptr())
-                torch.cuda.synchronize()
-                dt = (time.perf_counter() - t0) / args.reps
-                kt = eng.timing_collect(); eng.timing(False)
-                ks = ", ".join(f"{k} {v[0] / args.reps:.2f}" for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0]) if v[0] / args.reps > 0.05)
-                nanf = float(torch.isnan(out).float().mean())
-                print(f"{tag} kept={kept:7s} tree_levels={lv} svm_impl={sv} ens_overlap={fz} svm_ctas_per_sm={psm}: wall {dt * 1e3:7.2f} ms | {ks} | NA {nanf:.4f}", flush=True)
-                ens.free()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / args.reps
+            kt = eng.timing_collect(); eng.timing(False)
+            ks = ", ".join(f"{k} {v[0] / args.reps:.2f}" for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0]) if v[0] / args.reps > 0.05)
+            nanf = float(torch.isnan(out).float().mean())
+            if "v" in kept:
+                ref_out = globals().setdefault("_ref_out", {})
+                key = (tag, kept)
+                if key not in ref_out:
+                    ref_out[key] = out[::7, ::5].clone()
+                else:
+                    d = (out[::7, ::5] - ref_out[key]).abs()
+                    print(f"   svm_impl={sv}: max |diff to first variant| / max|ref| = {float(d[~torch.isnan(d)].max() / ref_out[key][~torch.isnan(ref_out[key])].abs().max()):.3e}")
+            print(f"{tag} kept={kept:7s} tree_levels={lv} svm_impl={sv} ens_overlap={fz} svm_ctas_per_sm={psm}: wall {dt * 1e3:7.2f} ms | {ks} | NA {nanf:.4f}", flush=True)
+            ens.free()
     eng.set_param("tree_levels", 0); eng.set_param("svm_impl", 0); eng.set_param("ens_overlap", 0); eng.set_param("svm_ctas_per_sm", 0)
 
 
@@ -68,7 +77,7 @@ if args.what in ("synthetic", "both"):
     cfg = dict(synth.CONFIGS["c3"]); cfg["nrow"], cfg["ncol"] = args.nrow, args.ncol
     geom, xy, krow, kcol, resid, models, kept, w, wt = bench.build_inputs(cfg, 0)
     cov = bench.device_covariates(geom, cfg["C"], dev)
-    run("synthetic", geom, cov, models, ["rb", "v", "bgnmrv"])
+    run("synthetic", geom, cov, models, args.kept.split(","))
     del cov
 
 ext = os.path.join(ROOT, "baseline", "_ref", "extdata")
