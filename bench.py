@@ -304,8 +304,9 @@ def lapack_threads(n: int):
 TRUE_BOUND = {
     "k_ens_svm": "mufu (ex2) / issue balanced: XU pipe 53 %, FMA pipe 67 %, issue 64 % (profiles/r1s_ncu_full_c3.md)",
     "k_ens_svm_mma": "mufu (ex2): dot products on the tensor pipe (3 x TF32)",
-    "k_ens_svm_tma": "mufu (ex2): XU pipe 67 %, tensor pipe 48 %, issue 54 % (profiles/r2z_ncu_full_svm_tma.md); 2 500 exponentials per cell, "
-                     "floor 36 ms at 16 / clk / SM; dot products as 3 x TF32 mma.sync, covariate tiles by TMA tensor copies",
+    "k_ens_svm_tma": "mufu (ex2): XU pipe 85 %, tensor pipe 42 %, issue 39 % (profiles/r3d_ncu_full_svm_f16.md); 2 500 exponentials per cell, "
+                     "floor 36 ms at 16 / clk / SM, 38.0 ms alone; dot products as two HMMA.16816 with FP16 split operands, covariate tiles by "
+                     "TMA tensor copies",
     "k_ens_trees": "L2 latency: issue 46 %, L2 hit 97 %, L1 hit 28 % (profiles/r2d_ncu_full_trees_l2.md, r2z_ncu_full_trees.md); inside the "
                    "step it runs on the 76-SM ensemble partition beside stage 1 of the fit (34 ms on all SMs)",
     "k_ens_fused": "issue + mufu: forest warps and support-vector warps share the SM",

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kTreeThreads) k_ens_trees_plain(
 // ---------------------------------------------------------------------------------------------
 // k_ens_trees: tile-pruned forest evaluation (see the file header).
 //   phase 1  features of the tile -> shared memory, per-feature [lo, hi] over the evaluated cells
-//   phase 2  warp w walks trees [w T/8, (w+1) T/8) with the interval: collapsed trees add to a
+//   phase 2  warp w walks the 32-tree blocks w, w + 8, ... with the interval: collapsed trees add to a
 //            per-thread constant, forking trees append (fork node | kind << 30) to the warp's list
 //            (ballot-ordered -> the summation order, hence the result, is deterministic)
 //   phase 3  every cell walks the surviving subtrees, kTreeIlp at a time
@@ -222,7 +222,9 @@ constexpr int kTreeChunk = 2048;     // trees pruned per pass (bounds the residu
 constexpr int kTreeSeg = kTreeChunk / 8;
 constexpr int kTreeIlp = 4;      // subtrees a cell walks at once (independent dependent-load chains: the walk is bound by L2 latency)
 constexpr int kPruneIlp = 3;     // trees a lane prunes at once in phase 2
+constexpr int kWarpPruneIlp = 2; // fork-list entries a lane prunes at once in phase 2b
 constexpr int kKindShift = 30;
+constexpr int kChainDone = (int)0x80000000, kChainFork = 1 << 29, kChainNode = (1 << 26) - 1;   // state word of a pruning chain
 
 // Two-level variant (the default): the CTA tile of 32 x 8 cells is cut into eight 8 x 4 blocks, one per warp.  After the CTA-level
 // prune (phase 2, as above) every warp prunes the CTA's fork list once more with the feature intervals of ITS 32 cells, from the
@@ -232,6 +234,17 @@ constexpr int kKindShift = 30;
 // levels), so results are deterministic.  On rough rasters (the reference's slope / TWI) most trees fork at every level and the
 // kernel degrades to the plain per-cell walk plus two cheap interval passes.
 constexpr int kWarpList = 256;       // fork-list entries a warp prunes per pass (bounds its residual list)
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
 
 template <int R>
 __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
@@ -243,7 +256,7 @@ __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
   float* s_feat = reinterpret_cast<float*>(tree_smem);                    // [(C + 2)][256]
   int* s_list = reinterpret_cast<int*>(s_feat + (C + 2) * kTreeThreads);  // [8][kTreeSeg + kTreeIlp]   CTA-level fork list
   int* s_wlist = s_list + 8 * (kTreeSeg + kTreeIlp);                      // [8][kWarpList + kTreeIlp]  warp-level fork lists
-  __shared__ float s_wlo[16][8], s_whi[16][8], s_lo[16], s_hi[16];
+  __shared__ float2 s_wiv[16][8], s_iv[16];        // (lo, hi) of feature f over warp q's block / over the tile: one LDS.64 per split
   __shared__ double s_wsum[8];
   __shared__ int s_cnt[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -267,14 +280,14 @@ __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
       lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if (lane == 0) { s_wlo[f][warp] = lo; s_whi[f][warp] = hi; }
+    if (lane == 0) s_wiv[f][warp] = make_float2(lo, hi);
   }
   s_feat[C * kTreeThreads + tid] = (float)col;
   s_feat[(C + 1) * kTreeThreads + tid] = (float)row;
   if (lane == 0) {
     const int c_lo = w.c0 + blockIdx.x * 32 + 8 * (warp & 3), r_lo = w.r0 + blockIdx.y * 8 + 4 * (warp >> 2);
-    s_wlo[C][warp] = (float)c_lo; s_whi[C][warp] = (float)min(w.c1 - 1, c_lo + 7);
-    s_wlo[C + 1][warp] = (float)r_lo; s_whi[C + 1][warp] = (float)min(w.r1 - 1, r_lo + 3);
+    s_wiv[C][warp] = make_float2((float)c_lo, (float)min(w.c1 - 1, c_lo + 7));
+    s_wiv[C + 1][warp] = make_float2((float)r_lo, (float)min(w.r1 - 1, r_lo + 3));
   }
   const int any_eval = __syncthreads_or(eval);
   if (!any_eval) {                                  // sea tile: nothing to evaluate
@@ -284,141 +297,173 @@ __global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
   if (tid < C + 2) {
     float lo = INFINITY, hi = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { lo = fminf(lo, s_wlo[tid][q]); hi = fmaxf(hi, s_whi[tid][q]); }
-    s_lo[tid] = lo; s_hi[tid] = hi;
+    for (int q = 0; q < 8; ++q) { lo = fminf(lo, s_wiv[tid][q].x); hi = fmaxf(hi, s_wiv[tid][q].y); }
+    s_iv[tid] = make_float2(lo, hi);
   }
   __syncthreads();
   const int ntrees = n_rf + n_gb;
-  const float* sf = s_feat + tid;
+  // 32-bit shared-memory addresses for the loads of the hot loops: through generic pointers the compiler rebuilt the shared window
+  // (S2UR SR_CgaCtaId + UMOV + UIADD3 + ULEA) at every node visit - 7 of the 18 instructions of a visit
+  const uint32_t sf_addr = (uint32_t)__cvta_generic_to_shared(s_feat) + 4u * tid;
+  const uint32_t iv_addr = (uint32_t)__cvta_generic_to_shared(&s_iv[0]);
+  const uint32_t wiv_addr = (uint32_t)__cvta_generic_to_shared(&s_wiv[0][warp]);
   double cell_sum = 0.0;
-  double csum = 0.0;                                // trees that collapse on the whole tile, walked by this thread
   double wsum = 0.0;                                // trees that collapse on this warp's block, walked by this lane
   int* my_list = s_list + warp * (kTreeSeg + kTreeIlp);
   int* my_wlist = s_wlist + warp * (kWarpList + kTreeIlp);
   const bool warp_eval = __any_sync(0xffffffffu, eval);
   for (int t0 = 0; t0 < ntrees; t0 += kTreeChunk) {
     // ---- phase 2: CTA-level prune, warp q owns trees [q per, (q + 1) per) of the chunk ----------------------
+    // Blocks of 32 consecutive trees are dealt round-robin to the warps (block b -> warp b mod 8), so that every warp gets the
+    // same mix of deep randomForest and shallow gbm trees (rf trees come first in the chunk): with contiguous shares the three
+    // warps that owned the rf trees needed 40 dependent rounds while the other five waited at the barrier after 8 (14 % of
+    // all stall samples, profiles/r2z_ncu_full_trees.md).  A block is homogeneous, so the side-by-side chains of a round
+    // have similar depths.
     const int nchunk = min(kTreeChunk, ntrees - t0);
-    const int per = ((nchunk + 7) / 8 + 31) & ~31;   // trees per warp, whole rounds of 32
+    const int nblk = (nchunk + 31) >> 5;
     int cnt = 0;
-    for (int k = 0; k < per; k += 32 * kPruneIlp) {
-      // kPruneIlp trees per lane, walked side by side: every step is a dependent L2 access, the chains overlap
-      int idx[kPruneIlp], kind[kPruneIlp];
-      bool act[kPruneIlp], fork[kPruneIlp];
-      double leafv[kPruneIlp];
+    double csum = 0.0;                              // trees that collapse on the whole tile, walked by this thread
+    for (int b0 = warp; b0 < nblk; b0 += 8 * kPruneIlp) {
+      // kPruneIlp trees per lane, walked side by side: every step is a dependent L2 access, the chains overlap.  The whole state
+      // of a chain is one integer (node | fork << 29 | kind << 30 | done << 31): flag arrays made ptxas spill predicates.
+      int st[kPruneIlp];
 #pragma unroll
       for (int u = 0; u < kPruneIlp; ++u) {
-        const int tw = k + 32 * u + lane;            // tree of this lane within the warp's share
-        const int tl = warp * per + tw;              // ... within the chunk
-        act[u] = tw < per && tl < nchunk;
-        fork[u] = false;
-        leafv[u] = 0.0;
-        kind[u] = 0;
-        idx[u] = 0;
-        if (act[u]) { kind[u] = (t0 + tl) >= n_rf; idx[u] = __ldg(&roots[t0 + tl]); }
+        const int tl = 32 * (b0 + 8 * u) + lane;     // tree of this lane within the chunk
+        st[u] = kChainDone;
+        if (tl < nchunk) st[u] = __ldg(&roots[t0 + tl]) | (((t0 + tl) >= n_rf ? 1 : 0) << kKindShift);
       }
       for (;;) {
-        bool any = false;
+        int live = -1;
         int2 nd[kPruneIlp];
 #pragma unroll
         for (int u = 0; u < kPruneIlp; ++u) {
-          if (act[u]) nd[u] = __ldg(&nodes[idx[u]]);
-          any |= act[u];
+          if (st[u] >= 0) nd[u] = __ldg(&nodes[st[u] & kChainNode]);
+          live &= st[u];
         }
-        if (!any) break;
+        if (live < 0) break;                         // every chain done
 #pragma unroll
         for (int u = 0; u < kPruneIlp; ++u) {
-          if (!act[u]) continue;
-          if (nd[u].y & kMetaLeaf) { leafv[u] = (kind[u] ? gb_scale : rf_scale) * (double)__int_as_float(nd[u].x); act[u] = false; continue; }
+          if (st[u] < 0) continue;
+          if (nd[u].y & kMetaLeaf) {                 // added in program order: fixed by the data, not by timing
+            csum += ((st[u] >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd[u].x);
+            st[u] = kChainDone;
+            continue;
+          }
           const int f = nd[u].y & 15;
           const float thr = __int_as_float(nd[u].x);
-          if (s_hi[f] <= thr) idx[u] = nd[u].y >> 5;
-          else if (s_lo[f] > thr) idx[u] = (nd[u].y >> 5) + 1;
-          else { fork[u] = true; act[u] = false; }
+          const int kindbit = st[u] & (1 << kKindShift);
+          const float2 iv = lds_f32x2(iv_addr + 8u * f);
+          if (iv.y <= thr) st[u] = (nd[u].y >> 5) | kindbit;
+          else if (iv.x > thr) st[u] = ((nd[u].y >> 5) + 1) | kindbit;
+          else st[u] |= kChainDone | kChainFork;
         }
       }
 #pragma unroll
-      for (int u = 0; u < kPruneIlp; ++u) {          // fixed order: the sums and the list do not depend on who finished first
-        csum += leafv[u];
-        const unsigned m = __ballot_sync(0xffffffffu, fork[u]);
-        if (fork[u]) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = idx[u] | (kind[u] << kKindShift);
+      for (int u = 0; u < kPruneIlp; ++u) {          // fixed order: the list does not depend on who finished first
+        const bool fork = (st[u] & kChainFork) != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, fork);
+        if (fork) my_list[cnt + __popc(m & ((1u << lane) - 1u))] = st[u] & (kChainNode | (1 << kKindShift));
         cnt += __popc(m);
       }
     }
-    if (lane == 0) s_cnt[warp] = cnt;
+    // the tile constant of this chunk goes to shared memory now (fixed-order reduction), so that nothing of phase 2 stays live
+#pragma unroll
+    for (int o = 16; o; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+    if (lane == 0) { s_cnt[warp] = cnt; s_wsum[warp] = (t0 ? s_wsum[warp] : 0.0) + csum; }
     __syncthreads();
     // ---- phase 2b + 3, warp-local: prune the CTA list with the block's intervals, then walk what is left -----
     if (warp_eval) {
+      // The survivors of all eight CTA lists collect in ONE warp list that is walked when it is nearly full and at the end:
+      // walked per CTA list (r2) most batches of kTreeIlp subtrees were padding (about 5 survivors per list on config 3).
+      int wcnt = 0;
+      auto walk_list = [&]() {
+        if (lane < kTreeIlp) my_wlist[wcnt + lane] = zero_leaf;   // pad to a whole ILP batch
+        __syncwarp();
+        if (eval) {
+          double s = 0.0;
+          for (int i = 0; i < wcnt; i += kTreeIlp) {
+            int e[kTreeIlp], idx[kTreeIlp];
+            int2 nd[kTreeIlp];
+#pragma unroll
+            for (int u = 0; u < kTreeIlp; ++u) { e[u] = my_wlist[i + u]; idx[u] = e[u] & ((1 << kKindShift) - 1); }
+            for (;;) {
+              int leafs = kMetaLeaf;
+#pragma unroll
+              for (int u = 0; u < kTreeIlp; ++u) { nd[u] = __ldg(&nodes[idx[u]]); leafs &= nd[u].y; }
+              if (leafs) break;
+#pragma unroll
+              for (int u = 0; u < kTreeIlp; ++u) {     // branch-free: a chain that sits on a leaf stays there
+                const float x = lds_f32(sf_addr + ((nd[u].y & 15) << 10));
+                const int nxt = (nd[u].y >> 5) + (x <= __int_as_float(nd[u].x) ? 0 : 1);
+                idx[u] = (nd[u].y & kMetaLeaf) ? idx[u] : nxt;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kTreeIlp; ++u)
+              s += ((e[u] >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd[u].x);
+          }
+          cell_sum += s;
+        }
+        __syncwarp();                                // the warp list is rewritten by the next pass
+        wcnt = 0;
+      };
       for (int q = 0; q < 8; ++q) {
         const int n = s_cnt[q];
         const int* lst = s_list + q * (kTreeSeg + kTreeIlp);
-        for (int i0 = 0; i0 < n; i0 += kWarpList) {
-          const int n1 = min(kWarpList, n - i0);
-          int wcnt = 0;
-          for (int i = 0; i < n1; i += 32) {
-            bool fork = false;
-            int e = 0, idx = 0;
-            if (i + lane < n1) {
-              e = lst[i0 + i + lane];
-              idx = e & ((1 << kKindShift) - 1);
-              fork = levels < 2;                       // "tree_levels" = 1 (A/B measurements): no second prune, every entry stays
-              while (!fork) {
-                const int2 nd = __ldg(&nodes[idx]);
-                if (nd.y & kMetaLeaf) { wsum += ((e >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd.x); break; }
-                const int f = nd.y & 15;
-                const float thr = __int_as_float(nd.x);
-                if (s_whi[f][warp] <= thr) idx = nd.y >> 5;
-                else if (s_wlo[f][warp] > thr) idx = (nd.y >> 5) + 1;
-                else { fork = true; break; }
-              }
+        for (int i = 0; i < n; i += 32 * kWarpPruneIlp) {
+          // kWarpPruneIlp entries per lane side by side (every step is a dependent L2 access); the list keeps the entry order
+          int st[kWarpPruneIlp];                     // chain state as in phase 2; the list entries are node | kind << 30
+#pragma unroll
+          for (int u = 0; u < kWarpPruneIlp; ++u) {
+            const int j = i + 32 * u + lane;
+            st[u] = kChainDone;
+            if (j < n) st[u] = lst[j] | (levels < 2 ? kChainDone | kChainFork : 0);   // "tree_levels" = 1 (A/B): every entry stays
+          }
+          for (;;) {
+            int live = -1;
+            int2 nd[kWarpPruneIlp];
+#pragma unroll
+            for (int u = 0; u < kWarpPruneIlp; ++u) {
+              if (st[u] >= 0) nd[u] = __ldg(&nodes[st[u] & kChainNode]);
+              live &= st[u];
             }
+            if (live < 0) break;
+#pragma unroll
+            for (int u = 0; u < kWarpPruneIlp; ++u) {
+              if (st[u] < 0) continue;
+              if (nd[u].y & kMetaLeaf) {
+                wsum += ((st[u] >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd[u].x);
+                st[u] = kChainDone;
+                continue;
+              }
+              const int f = nd[u].y & 15;
+              const float thr = __int_as_float(nd[u].x);
+              const int kindbit = st[u] & (1 << kKindShift);
+              const float2 iv = lds_f32x2(wiv_addr + 64u * f);
+              if (iv.y <= thr) st[u] = (nd[u].y >> 5) | kindbit;
+              else if (iv.x > thr) st[u] = ((nd[u].y >> 5) + 1) | kindbit;
+              else st[u] |= kChainDone | kChainFork;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kWarpPruneIlp; ++u) {
+            const bool fork = (st[u] & kChainFork) != 0;
             const unsigned m = __ballot_sync(0xffffffffu, fork);
-            if (fork) my_wlist[wcnt + __popc(m & ((1u << lane) - 1u))] = idx | (e & (1 << kKindShift));
+            if (fork) my_wlist[wcnt + __popc(m & ((1u << lane) - 1u))] = st[u] & (kChainNode | (1 << kKindShift));
             wcnt += __popc(m);
           }
-          if (lane < kTreeIlp) my_wlist[wcnt + lane] = zero_leaf;   // pad to a whole ILP batch
-          __syncwarp();
-          if (eval) {
-            double s = 0.0;
-            for (int i = 0; i < wcnt; i += kTreeIlp) {
-              int e[kTreeIlp], idx[kTreeIlp];
-              int2 nd[kTreeIlp];
-#pragma unroll
-              for (int u = 0; u < kTreeIlp; ++u) { e[u] = my_wlist[i + u]; idx[u] = e[u] & ((1 << kKindShift) - 1); }
-              for (;;) {
-                int leafs = kMetaLeaf;
-#pragma unroll
-                for (int u = 0; u < kTreeIlp; ++u) { nd[u] = __ldg(&nodes[idx[u]]); leafs &= nd[u].y; }
-                if (leafs) break;
-#pragma unroll
-                for (int u = 0; u < kTreeIlp; ++u) {
-                  if (!(nd[u].y & kMetaLeaf)) {
-                    const float x = sf[(nd[u].y & 15) * kTreeThreads];
-                    idx[u] = (nd[u].y >> 5) + (x <= __int_as_float(nd[u].x) ? 0 : 1);
-                  }
-                }
-              }
-#pragma unroll
-              for (int u = 0; u < kTreeIlp; ++u)
-                s += ((e[u] >> kKindShift) ? gb_scale : rf_scale) * (double)__int_as_float(nd[u].x);
-            }
-            cell_sum += s;
-          }
-          __syncwarp();                              // the warp list is rewritten by the next pass
+          if (wcnt > kWarpList - 32 * kWarpPruneIlp) walk_list();    // no room for another round of entries
         }
       }
+      if (wcnt > 0) walk_list();
     }
     __syncthreads();                                 // the CTA list is rewritten by the next chunk
   }
   // ---- constants: fixed-order reductions of the per-thread sums (tile) and per-lane sums (block) ----------
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    csum += __shfl_xor_sync(0xffffffffu, csum, o);
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-  }
-  if (lane == 0) s_wsum[warp] = csum;
-  __syncthreads();
-  double tile_const = base;
+  for (int o = 16; o; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  double tile_const = base;                         // s_wsum is complete since the barrier that ended the last chunk's phase 2
 #pragma unroll
   for (int q = 0; q < 8; ++q) tile_const += s_wsum[q];
   if (inside) {

@@ -1243,14 +1243,14 @@ struct BandSolveArgs {
 };
 
 // One CTA of 8 warps.  The sequential part of a block step - potrf of the 32 x 32 diagonal block and the inverse of its factor -
-// stays on warp 0 (fully unrolled, predicated: the shared-memory operands of the dependent FMA chains are in flight ahead of
-// them); the two 32 x 32 x 32 products (L_{j+1,j} = A_{j+1,j} L_jj^-T, next diagonal block -= L_{j+1,j} L_{j+1,j}') and all
-// block loads / stores are spread over the 256 threads (thread = row x 4 columns).  Every output element is still ONE fma
-// chain in ascending k, so the factors are bit-identical to the one-warp kernel of r2a (9.4 ms at 5 000 knots).
+// stays on warp 0 (fully unrolled, right-looking, operands in registers: see the comments there); the two 32 x 32 x 32 products (L_{j+1,j} = A_{j+1,j} L_jj^-T, next diagonal block -= L_{j+1,j} L_{j+1,j}') and all
+// block loads / stores are spread over the 256 threads (thread = row x 4 columns).  Every output element is ONE fma chain in
+// ascending k (deterministic; 9.4 ms at 5 000 knots on one warp, 6.9 ms with the CTA-wide products, r3: right-looking warp part).
 constexpr int kBandThreads = 256;
 __global__ void __launch_bounds__(kBandThreads) k_band_solve(BandSolveArgs a) {
   __shared__ double B0[32][kPad], B1[32][kPad], B2[32][kPad];
   __shared__ double xs[32], tv[32], xn[32];
+  __shared__ __align__(16) double colb[2][32];
   const int tid = threadIdx.x, l = tid & 31, wq = (tid >> 5) * 4, m = a.m;      // this thread: row l, columns wq .. wq + 3
   constexpr int b = 32;
   const int nb = (m + b - 1) / b;
@@ -1275,33 +1275,39 @@ __global__ void __launch_bounds__(kBandThreads) k_band_solve(BandSolveArgs a) {
   __syncthreads();
   for (int j = 0; j < nb; ++j) {
     if (tid < 32) {
-      // ---- D = L L' in place (lower), lane = row ----------------------------------------------------------------
+      // ---- D = L L' (lower), lane = row: the row lives in registers, a column travels through a 32-double buffer ---------
+      // Right-looking and fully unrolled.  Per column the dependent chain is shuffle (pivot) -> rsqrt -> one multiply -> buffer ->
+      // one FMA; sqrt(d) = d rsqrt(d) and 1 / sqrt(d) = rsqrt(d) replace the square root and 32 divisions of the first version,
+      // and the 31 - c updates of a lane are independent register FMAs (upper-triangle entries ride along unpredicated: they
+      // start as zeros and are never read by another lane).
+      double r[32], rs[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) r[q] = D[l][q];
+#pragma unroll
       for (int c = 0; c < 32; ++c) {
-        __syncwarp();
-        const double dcc = D[c][c];
+        const double dcc = __shfl_sync(0xffffffffu, r[c], c);
         if (!(dcc > 0.0) && l == 0) *a.err = 1;
-        const double dd = sqrt(dcc > 0.0 ? dcc : 1.0);
-        const double lic = l > c ? D[l][c] / dd : 0.0;
-        __syncwarp();
-        if (l == c) D[c][c] = dd;
-        else if (l > c) D[l][c] = lic;
+        rs[c] = rsqrt(dcc > 0.0 ? dcc : 1.0);
+        const double lic = r[c] * rs[c];              // lane c: the diagonal entry sqrt(d); lanes > c: L[l][c]
+        r[c] = lic;
+        colb[c & 1][l] = lic;
         __syncwarp();
 #pragma unroll
-        for (int q = 1; q < 32; ++q)
-          if (q > c && q <= l) D[l][q] -= lic * D[q][c];
+        for (int q = c + 1; q < 32; ++q) r[q] = fma(-lic, colb[c & 1][q], r[q]);
       }
-      __syncwarp();
-      // ---- Li = L^-1, lane = column --------------------------------------------------------------------------------
-      for (int i = 0; i < 32; ++i) {
-        double sacc = 0.0;
-        if (i >= l) {
-          sacc = i == l ? 1.0 : 0.0;
 #pragma unroll
-          for (int k = 0; k < 31; ++k)
-            if (k >= l && k < i) sacc -= D[i][k] * Li[k][l];
-          sacc /= D[i][i];
-        }
-        Li[i][l] = sacc;
+      for (int q = 0; q < 32; ++q) D[l][q] = r[q];
+      __syncwarp();
+      // ---- Li = L^-1, lane = column: right-looking too - once Li[k][l] is known every later row takes its term, so the
+      // chain per row is one FMA + one multiply by rsqrt(pivot) instead of a dot product of up to 31 dependent FMAs ---------
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = i == l ? 1.0 : 0.0;      // r = pending right-hand side of column l
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const double xk = r[k] * rs[k];               // zero above the diagonal (k < l) without a predicate
+        Li[k][l] = xk;
+#pragma unroll
+        for (int i = k + 1; i < 32; ++i) r[i] = fma(-D[i][k], xk, r[i]);
       }
     }
     __syncthreads();

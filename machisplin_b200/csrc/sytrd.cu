@@ -582,22 +582,26 @@ __global__ void k_sytrd_tail(SytrdArgs a) { sytrd_tail(a); }
 // eigenvalue index k (ascending): each evaluates the count at one of 8 interior points of the current bracket,
 // the bracket shrinks 9-fold per round (3.17 bits instead of 1), start = Gershgorin hull.  The count uses the
 // three-term recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (one FP64 FMA on the critical path instead of
-// a division), rescaled by an exact power of two every 4 steps; #{eigenvalues < x} = #{i : sign p_i != sign
+// a division), rescaled by an exact power of two every 4 steps (off the dependent chain, see the loop); #{eigenvalues < x} = #{i : sign p_i != sign
 // p_{i-1}}, an exact zero counting as a change.  Rounds stop when the bracket is below abstol (a fixed fraction
 // of ulp(|T|)) or 2 ulp of its own magnitude - deterministic, independent of the launch geometry.
 // ---------------------------------------------------------------------------------------------
-constexpr int kEigThreads = 128;            // 16 eigenvalues x 8 section points per CTA
-__global__ void __launch_bounds__(kEigThreads) k_tri_eig(const double* __restrict__ d, const double* __restrict__ e2,
-                                                         int m, double lo, double hi, double abstol,
-                                                         double* __restrict__ eta) {
+// Geometry: every CTA keeps its own copy of (d, e^2) in shared memory (16 m bytes: two CTAs per SM at 5 000 knots), and the run
+// time of a CTA is the length of the dependent recurrence, not the number of eigenvalues it owns - so the grid is ONE wave:
+// eigenvalues per CTA = ceil(m / (2 SMs)) rounded up to whole warps (round 2: 313 CTAs of 16 eigenvalues on 296 slots ran as two
+// waves, 5.8 ms).  Signs are read from the exponent word with integer instructions: the FP64 pipe (2 issue cycles per warp
+// instruction) keeps only the three operations of the recurrence.
+__global__ void __launch_bounds__(1024) k_tri_eig(const double* __restrict__ d, const double* __restrict__ e2,
+                                                  int m, int per_cta, double lo, double hi, double abstol,
+                                                  double* __restrict__ eta) {
   extern __shared__ double s_tri[];           // d | e2
   double* s_d = s_tri;
   double* s_e2 = s_tri + m;
   for (int i = threadIdx.x; i < m; i += blockDim.x) { s_d[i] = d[i]; s_e2[i] = i < m - 1 ? e2[i] : 0.0; }
   __syncthreads();
   const int sec = threadIdx.x & 7;
-  int k = blockIdx.x * (kEigThreads / 8) + (threadIdx.x >> 3);   // k-th smallest eigenvalue
-  const bool live = k < m;
+  int k = blockIdx.x * per_cta + (threadIdx.x >> 3);   // k-th smallest eigenvalue
+  const bool live = k < m && (int)(threadIdx.x >> 3) < per_cta;
   if (!live) k = m - 1;                       // keep the whole warp in the shuffles
   double a = lo, b = hi;
   for (int it = 0; it < 40; ++it) {
@@ -607,20 +611,46 @@ __global__ void __launch_bounds__(kEigThreads) k_tri_eig(const double* __restric
     double p0 = 1.0, p1 = s_d[0] - x;
     bool neg1 = p1 < 0.0 || p1 == 0.0;        // p_0 = 1 > 0: a zero counts as a sign change
     int cnt = neg1;
-    for (int i = 1; i < m; ++i) {
-      const double p2 = fma(s_d[i] - x, p1, -s_e2[i - 1] * p0);
-      const bool neg2 = p2 < 0.0 || (p2 == 0.0 && !neg1);
-      cnt += neg2 != neg1;
-      p0 = p1; p1 = p2; neg1 = neg2;
-      if ((i & 3) == 0) {
-        int ex = (__double2hiint(p1) >> 20) & 0x7ff;
-        if (ex == 0) ex = (__double2hiint(p0) >> 20) & 0x7ff;
-        if (ex > 0 && ex < 2046) {
-          const double sc = __hiloint2double((2046 - ex) << 20, 0);   // 2^(1023 - ex)
-          p0 *= sc; p1 *= sc;
-        }
-      }
+    // neg2 = p2 < 0 || (p2 == 0 && !neg1), from the bits of p2 (finite by the rescaling)
+#define MB_STURM_COUNT(p2)                                                               \
+    {                                                                                    \
+      const int h2 = __double2hiint(p2);                                                 \
+      const bool zero2 = ((h2 & 0x7fffffff) | __double2loint(p2)) == 0;                  \
+      const bool neg2 = zero2 ? !neg1 : h2 < 0;                                          \
+      cnt += neg2 != neg1;                                                               \
+      neg1 = neg2;                                                                       \
     }
+    // The power of two that brings the pair back to unit magnitude is taken from the values at the end of a group of four steps
+    // and folded into the COEFFICIENTS of the first step of the next group (the recurrence is linear in (p0, p1) and powers of
+    // two are exact, so every sign is the one of the unscaled sequence): the only dependent operation per step is one DFMA -
+    // with "p0 *= sc; p1 *= sc" the exponent extraction and a DMUL sat on the chain of a kernel that is nothing but that chain.
+    double sc = 1.0;
+    int i = 1;
+    for (; i + 3 < m; i += 4) {
+      {
+        const double dx = (s_d[i] - x) * sc, ee = s_e2[i - 1] * sc;
+        const double p2 = fma(dx, p1, -ee * p0);
+        p0 = p1 * sc; p1 = p2;
+        MB_STURM_COUNT(p2)
+      }
+#pragma unroll
+      for (int u = 1; u < 4; ++u) {
+        const double p2 = fma(s_d[i + u] - x, p1, -s_e2[i + u - 1] * p0);
+        p0 = p1; p1 = p2;
+        MB_STURM_COUNT(p2)
+      }
+      int ex = (__double2hiint(p1) >> 20) & 0x7ff;
+      if (ex == 0) ex = (__double2hiint(p0) >> 20) & 0x7ff;
+      sc = (ex > 0 && ex < 2046) ? __hiloint2double((2046 - ex) << 20, 0) : 1.0;   // 2^(1023 - ex)
+    }
+    for (; i < m; ++i) {
+      const double dx = (s_d[i] - x) * sc, ee = s_e2[i - 1] * sc;
+      const double p2 = fma(dx, p1, -ee * p0);
+      p0 = p1 * sc; p1 = p2;
+      sc = 1.0;
+      MB_STURM_COUNT(p2)
+    }
+#undef MB_STURM_COUNT
     // cnt = #eigenvalues < x, non-decreasing in sec: the new bracket is [largest x with cnt <= k, smallest x with cnt > k]
     const unsigned grp = 0xffu << ((threadIdx.x & 31) & ~7);
     const unsigned above = __ballot_sync(0xffffffffu, cnt > k) & grp;
@@ -738,7 +768,12 @@ void sym_tridiag_eig(mb_ctx* ctx, double* A, int ld, int m, double* z_dev, int L
   double tnorm = 0.0;
   for (int i = 0; i < m; ++i) tnorm = std::max(tnorm, std::fabs(diag[i]) + (i > 0 ? std::fabs(off[i - 1]) : 0.0) + (i < m - 1 ? std::fabs(off[i]) : 0.0));
   const double abstol = 1e-3 * 2.220446049250313e-16 * tnorm;   // far below what the reduction itself resolves
-  MB_LAUNCH(ctx, "k_tri_eig", st) k_tri_eig<<<(m + 15) / 16, kEigThreads, smem, st>>>(a.d, d_e2, m, lo, hi, abstol, d_eta);
+  // one wave: as many CTAs as fit beside each other (shared memory decides), whole warps of 4 eigenvalues x 8 section points
+  const int per_sm = std::max(1, std::min(8, (int)((220u * 1024u) / (smem + 1024))));
+  const int slots = std::max(1, per_sm * ctx->sm_count);
+  const int per_cta = std::min(128, ((m + slots - 1) / slots + 3) & ~3);
+  MB_LAUNCH(ctx, "k_tri_eig", st)
+    k_tri_eig<<<(m + per_cta - 1) / per_cta, 8 * per_cta, smem, st>>>(a.d, d_e2, m, per_cta, lo, hi, abstol, d_eta);
   MB_CUDA(cudaGetLastError());
   eta.resize(m);
   MB_CUDA(cudaMemcpyAsync(eta.data(), d_eta, sizeof(double) * m, cudaMemcpyDeviceToHost, st));

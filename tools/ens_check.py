@@ -103,5 +103,5 @@ if args.what in ("real", "both"):
         cols = np.concatenate([np.arange(g.ncol) if k % 2 == 0 else np.arange(g.ncol)[::-1] for k in range(rx)])[:args.ncol]
         big = torch.from_numpy(small).to(dev)[:, torch.from_numpy(rows.copy()).to(dev)][:, :, torch.from_numpy(cols.copy()).to(dev)].contiguous()
         geom = Geom(g.xmin, g.xmin + args.ncol * g0.rx, g.ymax - args.nrow * g0.ry, g.ymax, args.nrow, args.ncol)
-        run("real     ", geom, big, models, ["rb", "v", "bgnmrv"])
+        run("real     ", geom, big, models, args.kept.split(","))
 eng.close()
