@@ -274,7 +274,7 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * kept (measured slower); "svm_ctas_per_sm" = persistent grid of the ksvm kernel in that mode (default 2); "ens_tma" = 1 (default)
  * covariate tiles of the ksvm kernel by TMA tensor copies (cp.async.bulk.tensor), 2 plain loads;
  * "gc_split" = SM count of the fit partition when mb_mltps_predict* splits the device with CUDA green contexts (stage 1 of the GCV fit
- * on one partition, the forest kernel on the other from the start; 0 = default 72, -1 = no partitions: the ensemble waits for stage 1;
+ * on one partition, the forest kernel on the other from the start; 0 = default 64, -1 = no partitions: the ensemble waits for stage 1;
  * the partitions are created once per context, with the size in force at the first call that uses them); "gc_share" = percent of
  * the raster's rows whose forest kernel runs on the ensemble partition beside stage 1, the rest follows on all SMs (0 = default = all rows);
  * "leaf_impl" = TPS-only grid evaluation: 1 (default) one warp per leaf box, 2 one CTA per leaf box;

@@ -10,7 +10,8 @@ import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libmachisplin_b200.so"
+# MB_LIB: another build of the SAME library (tools/build_variants.sh: kernels compiled with other tuning constants for A/B runs)
+LIB_PATH = Path(os.environ["MB_LIB"]) if os.environ.get("MB_LIB") else HERE / "libmachisplin_b200.so"
 
 
 def _pin_nccl():

@@ -760,7 +760,7 @@ static void mltps_predict(mb_ctx* ctx, const mb_grid& g, const mb_ensemble* e, f
   // forest kernel starts NOW on the ensemble partition while stage 1 runs on the fit partition; what follows the forest kernel
   // (ksvm + smooth models) is deferred behind stage 1 as before, on all SMs.
   const bool use_gc = defer && ctx->gc_split >= 0 && n >= 1500 && ensemble_has_forest_kernel(e) &&
-                      greenctx_setup(ctx, ctx->gc_split > 0 ? ctx->gc_split : 72);
+                      greenctx_setup(ctx, ctx->gc_split > 0 ? ctx->gc_split : 64);   // 64: forest kernel (84 SMs) and stage 1 end together (profiles/r3g_*)
   // rows [lo, hi) of the raster, in the row blocks the covariates travel in (host-buffer entry point) or in one piece
   auto accumulate = [&](cudaStream_t s, int part, int lo, int hi) {
     if (hi <= lo) return;

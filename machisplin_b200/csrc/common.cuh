@@ -225,7 +225,7 @@ struct mb_ctx {
   cudaStream_t gc_fit_stream = nullptr, gc_fit_aux = nullptr, gc_ens_stream = nullptr;
   int gc_fit_sms = 0, gc_ens_sms = 0;
   cudaEvent_t gc_ev[4] = {nullptr, nullptr, nullptr, nullptr};     // 0 fork to the fit partition, 1 its join, 2 forest kernels done, 3 spare
-  int gc_split = 0;           // "gc_split": SMs of the fit partition (0 = default 72, -1 = no partitions: deferred ensemble)
+  int gc_split = 0;           // "gc_split": SMs of the fit partition (0 = default 64, -1 = no partitions: deferred ensemble)
   int gc_share = 0;           // "gc_share": percent of the raster's rows whose forest kernel runs on the ensemble partition (0 = default)
   bool gc_stage1 = false;     // set by mb_mltps_predict* around its fit: stage 1 of the tridiagonalisation runs on the fit partition
   cudaEvent_t leaf_wait = nullptr;   // consumed by the fast evaluator right before its grid-evaluation kernel (tps_eval.cu)

@@ -220,9 +220,22 @@ __global__ void __launch_bounds__(kTreeThreads) k_ens_trees_plain(
 // ---------------------------------------------------------------------------------------------
 constexpr int kTreeChunk = 2048;     // trees pruned per pass (bounds the residual lists)
 constexpr int kTreeSeg = kTreeChunk / 8;
-constexpr int kTreeIlp = 4;      // subtrees a cell walks at once (independent dependent-load chains: the walk is bound by L2 latency)
-constexpr int kPruneIlp = 3;     // trees a lane prunes at once in phase 2
-constexpr int kWarpPruneIlp = 2; // fork-list entries a lane prunes at once in phase 2b
+// tuning constants (-D overrides: tools/build_variants.sh builds A/B copies of the library)
+#ifndef MB_TREE_ILP
+#define MB_TREE_ILP 4
+#endif
+#ifndef MB_TREE_CTAS
+#define MB_TREE_CTAS 5
+#endif
+#ifndef MB_PRUNE_ILP
+#define MB_PRUNE_ILP 3
+#endif
+#ifndef MB_WPRUNE_ILP
+#define MB_WPRUNE_ILP 2
+#endif
+constexpr int kTreeIlp = MB_TREE_ILP;        // subtrees a cell walks at once (independent dependent-load chains: the walk is bound by L2 latency)
+constexpr int kPruneIlp = MB_PRUNE_ILP;      // trees a lane prunes at once in phase 2
+constexpr int kWarpPruneIlp = MB_WPRUNE_ILP; // fork-list entries a lane prunes at once in phase 2b
 constexpr int kKindShift = 30;
 constexpr int kChainDone = (int)0x80000000, kChainFork = 1 << 29, kChainNode = (1 << 26) - 1;   // state word of a pruning chain
 
@@ -247,7 +260,7 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
 }
 
 template <int R>
-__global__ void __launch_bounds__(kTreeThreads, 5) k_ens_trees(
+__global__ void __launch_bounds__(kTreeThreads, MB_TREE_CTAS) k_ens_trees(
     const float* __restrict__ cov, int C, int64_t plane, EnsGeom eg, mb_window w,
     const int2* __restrict__ nodes, const int* __restrict__ roots, int n_rf, int n_gb, int zero_leaf,
     double rf_scale, double gb_scale, double base, int accumulate, int64_t acc_stride, double* __restrict__ acc, int levels) {

@@ -604,59 +604,90 @@ __global__ void __launch_bounds__(1024) k_tri_eig(const double* __restrict__ d, 
   const bool live = k < m && (int)(threadIdx.x >> 3) < per_cta;
   if (!live) k = m - 1;                       // keep the whole warp in the shuffles
   double a = lo, b = hi;
+  constexpr int kPts = 1;                       // section points per thread: 8 kPts per eigenvalue, bracket / (8 kPts + 1) per round
+  constexpr double kInv = 1.0 / (8 * kPts + 1);
   for (int it = 0; it < 40; ++it) {
     const double w = b - a;
     if (!(w > abstol && w > 4.4e-16 * fmax(fabs(a), fabs(b)))) break;   // uniform within the group of 8
-    const double x = a + w * ((sec + 1) * (1.0 / 9.0));
-    double p0 = 1.0, p1 = s_d[0] - x;
-    bool neg1 = p1 < 0.0 || p1 == 0.0;        // p_0 = 1 > 0: a zero counts as a sign change
-    int cnt = neg1;
+    // The kPts recurrences of a thread are independent chains of one DFMA per step.  Two per thread (17-fold shrink per round, 16
+    // rounds instead of 20 at 5 000 knots) measured SLOWER: 5.2 against 4.0 ms (profiles/r3z_bench_tpsonly.json against
+    // r3f_bench_tpsonly.json) - with the rescaling off the chain the kernel is bound by the FP64 pipe as much as by its latency.
+    double x[kPts], p0[kPts], p1[kPts], sc[kPts];
+    bool neg1[kPts];
+    int cnt[kPts];
+#pragma unroll
+    for (int u = 0; u < kPts; ++u) {
+      x[u] = a + w * ((kPts * sec + u + 1) * kInv);
+      p0[u] = 1.0; p1[u] = s_d[0] - x[u];
+      neg1[u] = p1[u] < 0.0 || p1[u] == 0.0;     // p_0 = 1 > 0: a zero counts as a sign change
+      cnt[u] = neg1[u];
+      sc[u] = 1.0;
+    }
     // neg2 = p2 < 0 || (p2 == 0 && !neg1), from the bits of p2 (finite by the rescaling)
-#define MB_STURM_COUNT(p2)                                                               \
+#define MB_STURM_COUNT(u, p2)                                                            \
     {                                                                                    \
       const int h2 = __double2hiint(p2);                                                 \
       const bool zero2 = ((h2 & 0x7fffffff) | __double2loint(p2)) == 0;                  \
-      const bool neg2 = zero2 ? !neg1 : h2 < 0;                                          \
-      cnt += neg2 != neg1;                                                               \
-      neg1 = neg2;                                                                       \
+      const bool neg2 = zero2 ? !neg1[u] : h2 < 0;                                       \
+      cnt[u] += neg2 != neg1[u];                                                         \
+      neg1[u] = neg2;                                                                    \
     }
-    // The power of two that brings the pair back to unit magnitude is taken from the values at the end of a group of four steps
+    // The power of two that brings a pair back to unit magnitude is taken from the values at the end of a group of four steps
     // and folded into the COEFFICIENTS of the first step of the next group (the recurrence is linear in (p0, p1) and powers of
     // two are exact, so every sign is the one of the unscaled sequence): the only dependent operation per step is one DFMA -
     // with "p0 *= sc; p1 *= sc" the exponent extraction and a DMUL sat on the chain of a kernel that is nothing but that chain.
-    double sc = 1.0;
     int i = 1;
     for (; i + 3 < m; i += 4) {
       {
-        const double dx = (s_d[i] - x) * sc, ee = s_e2[i - 1] * sc;
-        const double p2 = fma(dx, p1, -ee * p0);
-        p0 = p1 * sc; p1 = p2;
-        MB_STURM_COUNT(p2)
+        const double di = s_d[i], ei = s_e2[i - 1];
+#pragma unroll
+        for (int u = 0; u < kPts; ++u) {
+          const double dx = (di - x[u]) * sc[u], ee = ei * sc[u];
+          const double p2 = fma(dx, p1[u], -ee * p0[u]);
+          p0[u] = p1[u] * sc[u]; p1[u] = p2;
+          MB_STURM_COUNT(u, p2)
+        }
       }
 #pragma unroll
-      for (int u = 1; u < 4; ++u) {
-        const double p2 = fma(s_d[i + u] - x, p1, -s_e2[i + u - 1] * p0);
-        p0 = p1; p1 = p2;
-        MB_STURM_COUNT(p2)
+      for (int v = 1; v < 4; ++v) {
+        const double di = s_d[i + v], ei = s_e2[i + v - 1];
+#pragma unroll
+        for (int u = 0; u < kPts; ++u) {
+          const double p2 = fma(di - x[u], p1[u], -ei * p0[u]);
+          p0[u] = p1[u]; p1[u] = p2;
+          MB_STURM_COUNT(u, p2)
+        }
       }
-      int ex = (__double2hiint(p1) >> 20) & 0x7ff;
-      if (ex == 0) ex = (__double2hiint(p0) >> 20) & 0x7ff;
-      sc = (ex > 0 && ex < 2046) ? __hiloint2double((2046 - ex) << 20, 0) : 1.0;   // 2^(1023 - ex)
+#pragma unroll
+      for (int u = 0; u < kPts; ++u) {
+        int ex = (__double2hiint(p1[u]) >> 20) & 0x7ff;
+        if (ex == 0) ex = (__double2hiint(p0[u]) >> 20) & 0x7ff;
+        sc[u] = (ex > 0 && ex < 2046) ? __hiloint2double((2046 - ex) << 20, 0) : 1.0;   // 2^(1023 - ex)
+      }
     }
     for (; i < m; ++i) {
-      const double dx = (s_d[i] - x) * sc, ee = s_e2[i - 1] * sc;
-      const double p2 = fma(dx, p1, -ee * p0);
-      p0 = p1 * sc; p1 = p2;
-      sc = 1.0;
-      MB_STURM_COUNT(p2)
+      const double di = s_d[i], ei = s_e2[i - 1];
+#pragma unroll
+      for (int u = 0; u < kPts; ++u) {
+        const double dx = (di - x[u]) * sc[u], ee = ei * sc[u];
+        const double p2 = fma(dx, p1[u], -ee * p0[u]);
+        p0[u] = p1[u] * sc[u]; p1[u] = p2;
+        sc[u] = 1.0;
+        MB_STURM_COUNT(u, p2)
+      }
     }
 #undef MB_STURM_COUNT
-    // cnt = #eigenvalues < x, non-decreasing in sec: the new bracket is [largest x with cnt <= k, smallest x with cnt > k]
+    // cnt = #eigenvalues < x, non-decreasing in the point index j = kPts sec + u: the new bracket is
+    // [largest x with cnt <= k, smallest x with cnt > k]
     const unsigned grp = 0xffu << ((threadIdx.x & 31) & ~7);
-    const unsigned above = __ballot_sync(0xffffffffu, cnt > k) & grp;
-    const int first = above ? (__ffs(above) - 1) & 7 : 8;    // first section point whose count exceeds k
-    const double na = first == 0 ? a : a + w * (first * (1.0 / 9.0));
-    const double nb = first == 8 ? b : a + w * ((first + 1) * (1.0 / 9.0));
+    int first = 8 * kPts;                         // first section point whose count exceeds k
+#pragma unroll
+    for (int u = 0; u < kPts; ++u) {
+      const unsigned above = __ballot_sync(0xffffffffu, cnt[u] > k) & grp;
+      if (above) first = min(first, kPts * ((__ffs(above) - 1) & 7) + u);
+    }
+    const double na = first == 0 ? a : a + w * (first * kInv);
+    const double nb = first == 8 * kPts ? b : a + w * ((first + 1) * kInv);
     a = na; b = nb;
   }
   if (live && sec == 0) eta[k] = 0.5 * (a + b);
