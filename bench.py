@@ -307,11 +307,11 @@ TRUE_BOUND = {
     "k_ens_svm_tma": "mufu (ex2): XU pipe 85 %, tensor pipe 42 %, issue 39 % (profiles/r3d_ncu_full_svm_f16.md); 2 500 exponentials per cell, "
                      "floor 36 ms at 16 / clk / SM, 38.0 ms alone; dot products as two HMMA.16816 with FP16 split operands, covariate tiles by "
                      "TMA tensor copies",
-    "k_ens_trees": "L2 latency: issue 46 %, L2 hit 97 %, L1 hit 28 % (profiles/r2d_ncu_full_trees_l2.md, r2z_ncu_full_trees.md); inside the "
-                   "step it runs on the 76-SM ensemble partition beside stage 1 of the fit (34 ms on all SMs)",
+    "k_ens_trees": "issue / L2 latency: issue-active 65 %, L2 hit 97 %, L1 hit 29 % (profiles/r3z_ncu_full_trees.md); inside the step it runs on the "
+                   "84-SM ensemble partition beside stage 1 of the fit (30.5 ms on all SMs)",
     "k_ens_fused": "issue + mufu: forest warps and support-vector warps share the SM",
     "k_sbr_chase": "latency: dependent L2 round trips between consecutive sweeps",
-    "k_leaf_fused": "hbm / issue: DRAM traffic 1.079 GB for 1.074 GB algorithmic, issue 69 % (profiles/r2z_ncu_full_leaf.md; before the 2-D "
+    "k_leaf_fused": "hbm / issue: DRAM traffic 1.077 GB for 1.074 GB algorithmic, issue 65 % (profiles/r3z_ncu_full_leaf.md; before the 2-D "
                     "tensor copy of the accumulator tile it was bound by the box barrier: 51 % of the stall samples, r2h_ncu_full_leaf_before_tma.md)",
     "k_leaf": "hbm write / issue",
 }

@@ -287,7 +287,9 @@ int mb_set_fast_eval_params(mb_ctx* ctx, int cheb_p, int leaf_cols, int leaf_row
  * one-stage persistent kernel; "sbr_qr_grid" = 1 makes the panel QR of the two-stage path use the software grid
  * barrier instead of a thread-block cluster; "sbr_qr_impl" = 1 / 2 keeps the panel rows in shared memory / registers
  * (0 = chosen by cluster size); "sbr_debug" = 1 keeps the band matrix for mb_debug_values("sbr_band");
- * "svm_impl" (before mb_ensemble_create) = 1 ksvm dot products on the tensor pipe (3 x TF32; the default for P <= 8), 2 packed FP32;
+ * "svm_impl" (before mb_ensemble_create) = ksvm dot products: 3 on the tensor pipe with FP16 split operands (two HMMA.16816 per 16 cells x 8
+ * support vectors; the default for P <= 8, falls back to 1 if a scaled support vector leaves the half range), 1 on the tensor pipe as
+ * 3 x TF32 (three HMMA.1688), 2 packed FP32 (the only one for P > 8); 0 = default;
  * "coef_impl" = 0 coefficients from the band form of the two-stage reduction when cond(M + lambda I) <= 1e8 (default), 1 whenever
  * that form exists, 2 always the dense Cholesky of M + lambda I;
  * "sbr_chase_impl" = bulge chase: 1 flags with watcher / publisher warps, 2 flags with three warps per sweep, 3 tagged band elements
