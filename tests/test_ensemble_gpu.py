@@ -214,6 +214,43 @@ def test_tiled_mode_is_independent_of_lane_concurrency(engine, case):
     np.testing.assert_array_equal(a, out.cpu().numpy())
 
 
+def test_forest_with_more_trees_than_one_chunk(engine, case):
+    """k_ens_trees prunes 2 048 trees per pass (kTreeChunk): 50 rf + 2 400 gbm trees (the 80 fitted trees thirty times over - the
+    descriptor's child indices are local to a tree) run as two passes whose tile constants, fork lists and per-cell sums have to
+    add up to the plain walk of the oracle; integer leaves make the gbm part exact."""
+    geom, C, models, cov = case
+    b = models["b"]
+    rep = 30
+    nt = len(b["tree_off"]) - 1
+    sizes = np.diff(b["tree_off"])
+    m2 = {"r": models["r"],
+          "b": {"initF": b["initF"], "tree_off": np.concatenate([[0], np.cumsum(np.tile(sizes, rep))]).astype(np.int32),
+                "splitvar": np.tile(b["splitvar"], rep), "splitcode": np.tile(b["splitcode"], rep),
+                "left": np.tile(b["left"], rep), "right": np.tile(b["right"], rep), "missing": np.tile(b["missing"], rep)}}
+    assert len(m2["b"]["tree_off"]) - 1 == rep * nt and models["r"]["ntree"] + rep * nt > 2048
+    for kept in ("b", "rb"):
+        ws = [1.0 / len(kept)] * len(kept)
+        ens = engine.ensemble_create(geom, m2, kept, ws, 1.0, C + 2)
+        got = engine.ensemble_eval(ens, cov)
+        sub = (5, 133, 9, 200)
+        got_w = engine.ensemble_eval(ens, cov, window=sub)
+        ref = cbind.ensemble_eval(m2, kept, ws, 1.0, cov, geom.as_tuple())
+        _cmp(got, ref, 2e-7)
+        _cmp(got_w, ref[sub[0]:sub[1], sub[2]:sub[3]], 2e-7)
+    # integer leaves: the float32 leaf storage is exact, so 2 400 trees in two passes must reproduce the reference bit for bit
+    rng = np.random.default_rng(1)
+    sc = m2["b"]["splitcode"].copy()
+    leaf = m2["b"]["splitvar"] == -1
+    sc[leaf] = rng.integers(-8, 8, int(leaf.sum()))
+    m3 = {"b": dict(m2["b"], splitcode=sc, initF=3.0)}
+    ens = engine.ensemble_create(geom, m3, "b", [1.0], 1.0, C + 2)
+    got = engine.ensemble_eval(ens, cov)
+    ref = cbind.ensemble_eval(m3, "b", [1.0], 1.0, cov, geom.as_tuple())
+    ok = ~np.isnan(ref)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(got[ok], ref[ok])
+
+
 @pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("kept", ["v", "gnmv", "bgnmrv"])
 def test_svm_kernel_variants(engine, case, kept, impl):
