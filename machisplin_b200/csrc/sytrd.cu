@@ -583,7 +583,7 @@ __global__ void k_sytrd_tail(SytrdArgs a) { sytrd_tail(a); }
 // the bracket shrinks 9-fold per round (3.17 bits instead of 1), start = Gershgorin hull.  The count uses the
 // three-term recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (one FP64 FMA on the critical path instead of
 // a division), rescaled by an exact power of two every 4 steps (off the dependent chain, see the loop); #{eigenvalues < x} = #{i : sign p_i != sign
-// p_{i-1}}, an exact zero counting as a change.  Rounds stop when the bracket is below abstol (a fixed fraction
+// p_{i-1}} (sign bits; an exact zero and its successor contribute one change).  Rounds stop when the bracket is below abstol (a fixed fraction
 // of ulp(|T|)) or 2 ulp of its own magnitude - deterministic, independent of the launch geometry.
 // ---------------------------------------------------------------------------------------------
 // Geometry: every CTA keeps its own copy of (d, e^2) in shared memory (16 m bytes: two CTAs per SM at 5 000 knots), and the run
@@ -613,24 +613,26 @@ __global__ void __launch_bounds__(1024) k_tri_eig(const double* __restrict__ d, 
     // rounds instead of 20 at 5 000 knots) measured SLOWER: 5.2 against 4.0 ms (profiles/r3z_bench_tpsonly.json against
     // r3f_bench_tpsonly.json) - with the rescaling off the chain the kernel is bound by the FP64 pipe as much as by its latency.
     double x[kPts], p0[kPts], p1[kPts], sc[kPts];
-    bool neg1[kPts];
+    int hprev[kPts];                              // exponent word of the previous term (its sign bit is what matters)
     int cnt[kPts];
 #pragma unroll
     for (int u = 0; u < kPts; ++u) {
       x[u] = a + w * ((kPts * sec + u + 1) * kInv);
       p0[u] = 1.0; p1[u] = s_d[0] - x[u];
-      neg1[u] = p1[u] < 0.0 || p1[u] == 0.0;     // p_0 = 1 > 0: a zero counts as a sign change
-      cnt[u] = neg1[u];
+      const bool neg1 = p1[u] < 0.0 || p1[u] == 0.0;   // p_0 = 1 > 0: a zero first term counts as a sign change
+      cnt[u] = neg1;
+      hprev[u] = neg1 ? (int)0x80000000 : 0;
       sc[u] = 1.0;
     }
-    // neg2 = p2 < 0 || (p2 == 0 && !neg1), from the bits of p2 (finite by the rescaling)
+    // A sign change is the XOR of the sign bits of consecutive terms: three integer instructions per step (the kernel is bound by
+    // its instruction count - 58 % issue-active with two warps per scheduler, profiles/r3x_ncu_full_tri_eig.md - and the
+    // "p2 < 0 || (p2 == 0 && !neg1)" logic was half of it).  An exact zero takes the sign of its sign bit; the term after it is
+    // -e^2 p_{i-1}, so the pair (zero, successor) still contributes exactly one change - the count is the one of the old rule.
 #define MB_STURM_COUNT(u, p2)                                                            \
     {                                                                                    \
       const int h2 = __double2hiint(p2);                                                 \
-      const bool zero2 = ((h2 & 0x7fffffff) | __double2loint(p2)) == 0;                  \
-      const bool neg2 = zero2 ? !neg1[u] : h2 < 0;                                       \
-      cnt[u] += neg2 != neg1[u];                                                         \
-      neg1[u] = neg2;                                                                    \
+      cnt[u] += (int)((unsigned)(h2 ^ hprev[u]) >> 31);                                  \
+      hprev[u] = h2;                                                                     \
     }
     // The power of two that brings a pair back to unit magnitude is taken from the values at the end of a group of four steps
     // and folded into the COEFFICIENTS of the first step of the next group (the recurrence is linear in (p0, p1) and powers of
