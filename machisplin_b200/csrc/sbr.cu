@@ -1016,7 +1016,7 @@ __device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arr
 template <int kMinCtas>
 __global__ void __launch_bounds__(kLLThreads, kMinCtas) k_sbr_chase_ll(ChaseLLArgs a) {
   __shared__ double Bs[2][32][kPad], Ds[2][32][kPad], zs[32][kPad];
-  __shared__ double vs[32], ws[32], vps[32], ts[32];
+  __shared__ __align__(16) double vs[32], ws[32], vps[32], ts[32];   // 16-byte aligned: broadcast reads of neighbours as one LDS.128
   __shared__ double sh_tau;
   __shared__ int sh_s;
   const int tid = threadIdx.x, l = tid & 31, wid = tid >> 5, m = a.m;
@@ -1156,24 +1156,39 @@ __global__ void __launch_bounds__(kLLThreads, kMinCtas) k_sbr_chase_ll(ChaseLLAr
       if (wid == 0) {
         if (k > 0) {
           // ---- left-apply the new reflector to columns 1 .. lp-1 (lane = column), then store the block by rows ----
+          // A step is ~900 instructions of THIS warp and its time is that count (two warps per scheduler at most: every
+          // instruction costs its 4 - 6 cycles of dependent issue), so the data movement is kept minimal: the column is read
+          // from shared memory once for the dot product and the update, and the 32 stores of a lane go to base + q (kLdb - 1)
+          // with the offsets as immediates (the full block - the common case - without a predicate per element).  Same
+          // operations in the same order as k_sbr_chase_t: the results stay bit-identical.
           if (l >= 1 && l < lp) {
+            double bc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bc[i] = B[i][l];
             double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              y0 = fma(vs[i], B[i][l], y0);
-              y1 = fma(vs[i + 1], B[i + 1][l], y1);
-              y2 = fma(vs[i + 2], B[i + 2][l], y2);
-              y3 = fma(vs[i + 3], B[i + 3][l], y3);
+              y0 = fma(vs[i], bc[i], y0);
+              y1 = fma(vs[i + 1], bc[i + 1], y1);
+              y2 = fma(vs[i + 2], bc[i + 2], y2);
+              y3 = fma(vs[i + 3], bc[i + 3], y3);
             }
             const double y = tau * ((y0 + y1) + (y2 + y3));
 #pragma unroll
-            for (int i = 0; i < 32; ++i) B[i][l] = fma(-vs[i], y, B[i][l]);
+            for (int i = 0; i < 32; ++i) B[i][l] = fma(-vs[i], y, bc[i]);
           }
           __syncwarp();
-          if (l < ln)
+          if (l < ln) {
+            ulonglong2* const base = a.Bt + (size_t)(lp + l) + (size_t)st * kLdb;   // (lp + l - q) + (st + q) kLdb = base + q (kLdb - 1)
+            if (lp == 32) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
-              if (q < lp) ll_store(a.Bt + (lp + l - q) + (size_t)(st + q) * kLdb, B[l][q], wtag);
+              for (int q = 0; q < 32; ++q) ll_store(base + q * (kLdb - 1), B[l][q], wtag);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q)
+                if (q < lp) ll_store(base + q * (kLdb - 1), B[l][q], wtag);
+            }
+          }
         }
         vps[l] = vl;                      // the reflector the next step applies from the right
       } else if (wid == 1) {
@@ -1190,10 +1205,14 @@ __global__ void __launch_bounds__(kLLThreads, kMinCtas) k_sbr_chase_ll(ChaseLLAr
         const double w = fma(-0.5 * tau * wsum(p * vl), vl, p);
         ws[l] = w;
         __syncwarp();
-        if (l < ln)
+        if (l < ln) {
+          ulonglong2* const base = a.Bt + (size_t)l + (size_t)r0 * kLdb;             // (l - q) + (r0 + q) kLdb = base + q (kLdb - 1)
 #pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (q <= l) ll_store(a.Bt + (l - q) + (size_t)(r0 + q) * kLdb, D[l][q] - vl * ws[q] - w * vs[q], wtag);
+          for (int q = 0; q < 32; ++q) {
+            const double val = D[l][q] - vl * ws[q] - w * vs[q];
+            if (q <= l) ll_store(base + q * (kLdb - 1), val, wtag);
+          }
+        }
       } else if (a.L > 0) {
         // ---- right-hand sides: z[r0 .. r0+ln-1, :] <- H z -----------------------------------------------------------
         if (l < a.L) {
