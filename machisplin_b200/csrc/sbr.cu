@@ -60,9 +60,10 @@ __device__ __forceinline__ void sbr_grid_sync(unsigned* bar, unsigned& gen) {
 
 // dlarfg: x = [alpha; x1], |x1|^2 = xn2  ->  H x = beta e1, v = [1; x1 * scale]
 // (r3i: reciprocal square root / reciprocal from the MUFU seeds with one third-order correction instead of sqrt() and the two
-// divisions, and the 32-term dot products of the bulge chase as trees instead of four 8-deep FMA chains, changed NOTHING -
-// chase 33.9 against 33.7 ms, panel QR 15.5 against 15.7, profiles/r3i_bench_tpsonly_fast_house.json: a step of those kernels
-// is bound by the instruction count of its busiest warp and by the hand-over, not by the FP64 latency of these chains.  Removed.)
+// divisions (~50 instructions fewer), together with the 32-term dot products of the bulge chase as trees instead of four 8-deep
+// FMA chains (~36 more), changed NOTHING - chase 33.9 against 33.7 ms, profiles/r3i_bench_tpsonly_fast_house.json: a step of
+// those kernels is bound by the instruction count of its busiest warp and by the hand-over, not by the FP64 latency of these
+// chains.  Removed; the seeds alone remain a candidate)
 __device__ __forceinline__ void make_house(double alpha, double xn2, double& beta, double& tau, double& scale) {
   beta = alpha; tau = 0.0; scale = 0.0;
   if (xn2 != 0.0) {
