@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(kLeafThreads, 3) k_leaf_stream(
       // the box's 32 x bh tile of the accumulator: ONE 2-D tensor copy (UTMALDG) issued by one lane.  The 32 row copies it
       // replaces were serialised by the uniform datapath (ELECT + R2UR + UBLKCP per row: ~250 instructions of warp 0 per box,
       // as many as a box's whole row work - every other warp waited for them at the box barrier: 51 % of all stall samples,
-      // profiles/r2h_ncu_full_leaf.md)
+      // profiles/r2h_ncu_full_leaf_before_tma.md)
       if (kAcc && acc_tma) ac_tma_load_2d(sp, &acc_map, pbi * 32, pbj * bh, &s_full[s]);
     }
     if (kAcc) {
