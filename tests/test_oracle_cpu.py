@@ -218,6 +218,38 @@ def test_model_descriptors_match_scikit_learn_predict():
     np.testing.assert_allclose(om.predict_svm_exact(v, X), ref, rtol=1e-9)
 
 
+def test_smooth_model_descriptors_match_scikit_learn_predict():
+    """gam (purely parametric formula = a linear model, V73:600-606) and nnet(size = 10, linout = TRUE) (V73:463-470): the oracle's
+    predictors on descriptors exported from fitted scikit-learn estimators reproduce those estimators' predict() - LinearRegression
+    and MLPRegressor(logistic hidden layer, identity output), weights re-ordered into nnet's `wts` layout (per hidden unit: bias,
+    inputs 1..P; then output bias, hidden 1..H)."""
+    import warnings
+    from sklearn.linear_model import LinearRegression
+    from sklearn.neural_network import MLPRegressor
+    from oracle import models as om
+    rng = np.random.default_rng(5)
+    n, P, H = 400, 5, 10
+    X = rng.standard_normal((n, P)) * [3.0, 0.5, 10.0, 1.0, 1.0] + [100.0, 2.0, -40.0, -77.0, -6.0]
+    y = 0.02 * X[:, 0] - 1.5 * X[:, 1] + np.tanh(0.1 * X[:, 2] + 4.0) + 0.1 * rng.standard_normal(n)
+    Xq = X[:150] + 0.2 * rng.standard_normal((150, P))
+    lr = LinearRegression().fit(X, y)
+    g = {"coef": np.concatenate([[lr.intercept_], lr.coef_])}
+    np.testing.assert_allclose(om.predict_gam(g, Xq), lr.predict(Xq), rtol=1e-12, atol=1e-12)
+    # nnet is fitted on the response scaled to [0, 1] and un-scaled after predict (V73:455-470)
+    mn, mx = y.min(), y.max()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mlp = MLPRegressor(hidden_layer_sizes=(H,), activation="logistic", solver="lbfgs", max_iter=60, random_state=0)
+        mlp.fit((X - X.mean(0)) / X.std(0), (y - mn) / (mx - mn))
+    # fold the input standardisation into the first layer: the reference feeds unscaled covariates
+    W1 = mlp.coefs_[0] / X.std(0)[:, None]                               # (P, H)
+    b1 = mlp.intercepts_[0] - (X.mean(0) / X.std(0)) @ mlp.coefs_[0]
+    wts = np.concatenate([np.column_stack([b1, W1.T]).ravel(), mlp.intercepts_[1], mlp.coefs_[1].ravel()])
+    nn = {"wts": wts, "H": H, "max2": mx - mn, "min": mn}
+    ref = mlp.predict((Xq - X.mean(0)) / X.std(0)) * (mx - mn) + mn
+    np.testing.assert_allclose(om.predict_nnet(nn, Xq), ref, rtol=1e-10, atol=1e-10)
+
+
 def test_gcv_criterion_against_the_brute_force_hat_matrix():
     """Independent of the eigen-decomposition the oracle (and the engine) search on: the smoother matrix A(lambda) from the
     full block system [[K + lambda I, T], [T', 0]], trA = trace(A), GCV = (RSS / n) / (1 - trA / n)^2 (Krig.fgcv with cost 1).
